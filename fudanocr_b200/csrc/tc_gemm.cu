@@ -1,0 +1,364 @@
+// tcgen05 + TMA implicit-GEMM engine (see tc_gemm.cuh for what it replaces in the reference).
+//
+// Persistent, warp-specialised CTA (256 threads, 1 CTA/SM):
+//   warp 0   : TMA producer  (A tile: 4-D box {64ch, W, 128/W rows, 1 image}, zero-filled halo;
+//                             B tile: 2-D box {64, BLOCK_N} of the per-tap weight matrix)
+//   warp 1   : MMA issuer    (one lane; 4 x tcgen05.mma 128xBLOCK_Nx16 per 64-wide K block)
+//   warp 2   : TMEM allocator
+//   warps 4-7: epilogue      (tcgen05.ld 32x32b -> bias/relu/residual/pixel-shuffle -> global)
+// Pipelines: smem ring full/empty (TMA<->MMA) and a 2-deep TMEM accumulator ring (MMA<->epilogue).
+#include "tc_gemm.cuh"
+
+#include <mutex>
+#include <unordered_map>
+
+namespace {
+
+constexpr int kTileM = 128;
+constexpr int kChunkK = 64;  // bf16 elements = one 128-byte swizzle row
+constexpr int kABytes = kTileM * 128;
+constexpr int kSmemBudget = 192 * 1024;
+
+template <int BLOCK_N>
+struct TcCfg {
+  static constexpr int kBBytes = BLOCK_N * 128;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = kSmemBudget / kStageBytes;
+  static constexpr int kTmemCols = 2 * BLOCK_N;  // 2 accumulator stages
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(256, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUtensorMap mA1,
+               const __grid_constant__ CUtensorMap mA2, const __grid_constant__ CUtensorMap mA3,
+               const __grid_constant__ CUtensorMap mB, const TcGemmParams p) {
+  using Cfg = TcCfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* empty = full + Cfg::kStages;
+  uint64_t* tfull = empty + Cfg::kStages;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int taps = p.ksize * p.ksize;
+  const int pad = p.ksize >> 1;
+  const int nk = taps * p.chunks;
+  const int total_tiles = p.m_tiles * p.n_blocks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mA0);
+    tma_prefetch_desc(&mB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const CUtensorMap* amaps[4] = {&mA0, &mA1, &mA2, &mA3};
+      int stage = 0;
+      uint32_t phase = 0;
+      const int hw = p.H * p.W;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m = tile / p.n_blocks, nb = tile % p.n_blocks;
+        const int p0 = m * kTileM;
+        const int b = p0 / hw;
+        const int h0 = (p0 - b * hw) / p.W;
+        for (int tap = 0; tap < taps; ++tap) {
+          const int dy = tap / p.ksize - pad, dx = tap % p.ksize - pad;
+          for (int ch = 0; ch < p.chunks; ++ch) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
+            uint8_t* sa = smem + stage * Cfg::kStageBytes;
+            const int mi = ch / p.chunks_per_map;
+            const int c0 = (ch - mi * p.chunks_per_map) * kChunkK;
+            tma_load_4d(sa, amaps[mi], &full[stage], c0, dx, h0 + dy, b);
+            tma_load_2d(sa + kABytes, &mB, &full[stage], ch * kChunkK,
+                        tap * p.n_total + nb * BLOCK_N);
+            if (++stage == Cfg::kStages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kTileM, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty[acc], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < nk; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint64_t da = umma_desc_k_sw128(sa);
+          const uint64_t db = umma_desc_k_sw128(sa + kABytes);
+#pragma unroll
+          for (int k = 0; k < kChunkK / 16; ++k) {
+            // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in 16-byte units
+            tc_mma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          }
+          tc_commit(&empty[stage]);
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        tc_commit(&tfull[acc]);
+        acc ^= 1;
+        if (acc == 0) aphase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    const int ew = warp - 4;  // == warp % 4 : TMEM lane quarter this warp may access
+    const int row = ew * 32 + lane;
+    int acc = 0;
+    uint32_t aphase = 0;
+    const int hw = p.H * p.W;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m = tile / p.n_blocks, nb = tile % p.n_blocks;
+      const long mg = (long)m * kTileM + row;
+      mbar_wait(&tfull[acc], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BLOCK_N;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(taddr + c0, r);
+        tmem_ld_wait();
+        const int n0 = nb * BLOCK_N + c0;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 bb = *reinterpret_cast<const float4*>(p.bias + n0 + j);
+            v[j] += bb.x;
+            v[j + 1] += bb.y;
+            v[j + 2] += bb.z;
+            v[j + 3] += bb.w;
+          }
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (p.epi == TC_EPI_BF16) {
+          const long off = mg * p.ldc + n0;
+          if (p.residual != nullptr) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 rv = rp[q];
+              float2 f;
+              f = unpack_bf16x2(rv.x); v[q * 8 + 0] += f.x; v[q * 8 + 1] += f.y;
+              f = unpack_bf16x2(rv.y); v[q * 8 + 2] += f.x; v[q * 8 + 3] += f.y;
+              f = unpack_bf16x2(rv.z); v[q * 8 + 4] += f.x; v[q * 8 + 5] += f.y;
+              f = unpack_bf16x2(rv.w); v[q * 8 + 6] += f.x; v[q * 8 + 7] += f.y;
+            }
+          }
+          uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + off);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 o;
+            o.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
+            o.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
+            o.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
+            o.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
+            op[q] = o;
+          }
+        } else if (p.epi == TC_EPI_F32) {
+          float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + mg * p.ldc + n0);
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            op[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+        } else {  // TC_EPI_PIXSHUF: n = sub*64 + c, sub = 2*i + j -> HR pixel (2h+i, 2w+j)
+          const int sub = n0 >> 6, c = n0 & 63;
+          const int b = (int)(mg / hw);
+          const int rem = (int)(mg - (long)b * hw);
+          const int h = rem / p.W, w = rem - h * p.W;
+          const long hp = ((long)b * 2 * p.H + 2 * h + (sub >> 1)) * (2 * p.W) + 2 * w + (sub & 1);
+          uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + hp * 64 + c);
+          uint4* op2 = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out2) + hp * 64 + c);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 o, o2;
+            float a[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              // round the pre-activation to bf16 first so that backward (which re-reads it)
+              // differentiates exactly the function that forward evaluated
+              a[j] = __bfloat162float(__float2bfloat16_rn(v[q * 8 + j]));
+            }
+            o.x = pack_bf16x2(a[0], a[1]);
+            o.y = pack_bf16x2(a[2], a[3]);
+            o.z = pack_bf16x2(a[4], a[5]);
+            o.w = pack_bf16x2(a[6], a[7]);
+            o2.x = pack_bf16x2(mish_f(a[0]), mish_f(a[1]));
+            o2.y = pack_bf16x2(mish_f(a[2]), mish_f(a[3]));
+            o2.z = pack_bf16x2(mish_f(a[4]), mish_f(a[5]));
+            o2.w = pack_bf16x2(mish_f(a[6]), mish_f(a[7]));
+            op[q] = o;
+            op2[q] = o2;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      acc ^= 1;
+      if (acc == 0) aphase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// host side: tensor maps (driver entry point fetched through the runtime: no libcuda link)
+// ------------------------------------------------------------------------------------
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                        const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                        const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_tmapEncodeTiled get_encode() {
+  static PFN_tmapEncodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_tmapEncodeTiled>(f);
+  });
+  return fn;
+}
+
+int make_map(CUtensorMap* out, const void* base, int rank, const cuuint64_t* dims,
+             const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+  PFN_tmapEncodeTiled enc = get_encode();
+  if (!enc) {
+    focr_set_error("cuTensorMapEncodeTiled entry point unavailable");
+    return FOCR_ERR_CUDA;
+  }
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims,
+                   strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    focr_set_error("cuTensorMapEncodeTiled failed (%d), rank %d dims %llu %llu", (int)r, rank,
+                   (unsigned long long)dims[0], (unsigned long long)dims[1]);
+    return FOCR_ERR_CUDA;
+  }
+  return FOCR_OK;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int BLOCK_N>
+int launch_impl(const CUtensorMap* am, const CUtensorMap& bm, const TcGemmParams& p, cudaStream_t stream) {
+  using Cfg = TcCfg<BLOCK_N>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    FOCR_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const int total = p.m_tiles * p.n_blocks;
+  const int grid = total < num_sms() ? total : num_sms();
+  tc_gemm_kernel<BLOCK_N><<<grid, 256, Cfg::kSmemBytes, stream>>>(am[0], am[1], am[2], am[3], bm, p);
+  FOCR_LAUNCH_CHECK();
+  return FOCR_OK;
+}
+
+}  // namespace
+
+int tc_gemm_block_n(int n_total) {
+  if (n_total % 128 == 0) return 128;
+  return 64;
+}
+
+int tc_gemm_launch(const bf16* const* a_ptrs, int n_amaps, long a_pix_stride, long a_row_stride,
+                   long a_img_stride, int a_channels, int B, const bf16* w, int cin, TcGemmParams p,
+                   cudaStream_t stream) {
+  FOCR_REQUIRE(n_amaps >= 1 && n_amaps <= 4, "tc_gemm: n_amaps %d", n_amaps);
+  FOCR_REQUIRE(p.W == 64 || p.W == 128, "tc_gemm: W must be 64 or 128 (got %d)", p.W);
+  FOCR_REQUIRE((p.H * p.W) % kTileM == 0, "tc_gemm: H*W must be a multiple of 128");
+  FOCR_REQUIRE(cin % 64 == 0 && a_channels % 64 == 0, "tc_gemm: channels must be multiples of 64");
+  FOCR_REQUIRE(p.ksize == 1 || p.ksize == 3, "tc_gemm: ksize %d", p.ksize);
+  FOCR_REQUIRE(p.n_total % 64 == 0, "tc_gemm: N %d", p.n_total);
+  const int block_n = tc_gemm_block_n(p.n_total);
+  p.n_blocks = p.n_total / block_n;
+  p.m_tiles = (int)((long)B * p.H * p.W / kTileM);
+  p.chunks = cin / 64;
+  p.chunks_per_map = a_channels / 64;
+  FOCR_REQUIRE(p.chunks_per_map * n_amaps == p.chunks, "tc_gemm: %d maps x %d ch != cin %d", n_amaps,
+               a_channels, cin);
+  if (p.epi == TC_EPI_PIXSHUF) FOCR_REQUIRE(p.n_total == 256, "pixel-shuffle epilogue needs N=256");
+
+  CUtensorMap am[4];
+  for (int i = 0; i < 4; ++i) {
+    const bf16* base = a_ptrs[i < n_amaps ? i : 0];
+    cuuint64_t dims[4] = {(cuuint64_t)a_channels, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)B};
+    cuuint64_t str[3] = {(cuuint64_t)a_pix_stride * 2, (cuuint64_t)a_row_stride * 2,
+                         (cuuint64_t)a_img_stride * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)p.W, (cuuint32_t)(kTileM / p.W), 1};
+    int rc = make_map(&am[i], base, 4, dims, str, box);
+    if (rc) return rc;
+  }
+  CUtensorMap bm;
+  {
+    const int taps = p.ksize * p.ksize;
+    cuuint64_t dims[2] = {(cuuint64_t)cin, (cuuint64_t)taps * p.n_total};
+    cuuint64_t str[1] = {(cuuint64_t)cin * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)block_n};
+    int rc = make_map(&bm, w, 2, dims, str, box);
+    if (rc) return rc;
+  }
+  if (block_n == 128) return launch_impl<128>(am, bm, p, stream);
+  return launch_impl<64>(am, bm, p, stream);
+}

@@ -1,0 +1,40 @@
+// tcgen05 + TMA implicit-GEMM engine for the NHWC bf16 feature maps of TBSRN/TSRN.
+//
+// One kernel serves
+//   * nn.Linear forward / input-gradient      (a 1x1 "conv" over the (B,16,64,C) token map)
+//   * nn.Conv2d 3x3 pad 1 forward / dgrad     (9 taps, TMA zero-fill supplies the padding)
+// as  D[M=pixels, N=Cout] = sum_{tap,chunk} A_tap[M, 64] * W_tap[N, 64]^T
+// with the fp32 accumulator in TMEM.  Reference call sites being replaced:
+//   scene-text-telescope/model/tbsrn.py:232,237 (SRB convs), :190 (block7), :264 (up-conv),
+//   :103,119-129 (attention linears), :158-163 (FFN), :74 (Linear 128->64).
+#pragma once
+#include "common.cuh"
+
+enum TcEpilogue : int {
+  TC_EPI_BF16 = 0,     // out bf16 [M, ldc]: acc + bias (+relu) (+residual)
+  TC_EPI_F32 = 1,      // out fp32 [M, ldc]: acc + bias
+  TC_EPI_PIXSHUF = 2,  // N = 4*64 ordered (sub, c): PixelShuffle(2) scatter to (B,2H,2W,64); out = pre-act,
+                       // out2 = mish(pre-act)
+};
+
+struct TcGemmParams {
+  int m_tiles;         // M / 128
+  int n_blocks;        // N_total / BLOCK_N
+  int n_total;         // N_total
+  int ksize;           // 1 or 3
+  int chunks;          // 64-wide K chunks per tap (Cin / 64)
+  int chunks_per_map;  // chunks served by one A tensor map
+  int W, H;            // spatial size of the A feature map (W in {64,128}); tile = 128 consecutive pixels
+  int epi;
+  int relu;
+  int ldc;             // leading dimension (elements) of out / residual
+  const float* bias;   // [N_total] or nullptr
+  void* out;
+  void* out2;
+  const bf16* residual;  // nullptr or [M, ldc]
+};
+
+int tc_gemm_launch(const bf16* const* a_ptrs, int n_amaps, long a_pix_stride /*elements between pixels*/,
+                   long a_row_stride /*elements between image rows*/, long a_img_stride, int a_channels,
+                   int B, const bf16* w /*[taps][N_total][Cin]*/, int cin, TcGemmParams p,
+                   cudaStream_t stream);
