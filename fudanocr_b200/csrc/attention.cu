@@ -1,0 +1,441 @@
+// Fused self-attention of the TBSRN FeatureEnhancer: h=4 heads, d_k=32, 1024 tokens
+// (scene-text-telescope/model/tbsrn.py:109-150: softmax(QK^T/sqrt(d_k)) -> dropout(0.1) -> PV).
+// The reference materialises P = (B,4,1024,1024) fp32 (4 GiB at B=256); here P never leaves
+// registers.  Input is the packed projection QKV (T,384) bf16 = [q | k | v], head h at columns
+// h*32 of each third; output O (T,128) bf16 in the "concat heads" layout the out-projection reads.
+//
+// d_k = 32 makes the op exp/issue-bound rather than MMA-bound (128 tensor FLOPs per exp), so the
+// kernels are warp-level mma.sync m16n8k16 flash kernels: one CTA per (batch, head) keeps the whole
+// K and V (or Q and dO) of that head in shared memory (2 x 64 KB, XOR-swizzled for ldmatrix) so they
+// are read from HBM exactly once.
+//   forward : warp owns 16 query rows, loops over 16 KV tiles of 64, online softmax
+//   backward: two passes without atomics -
+//     pass A (dQ)   : warp owns 16 query rows;  dS = P o (dP - D),  dQ = dS K
+//     pass B (dK,dV): warp owns 16 key rows;    works on S^T, dP^T; dV = Pd^T dO, dK = dS^T Q
+// Dropout uses the counter hash of common.cuh keyed on (b,h,q,k) so all three kernels regenerate the
+// same mask.
+#include "kernels.cuh"
+
+namespace {
+
+constexpr int kS = 1024;      // tokens
+constexpr int kLdQkv = 384;   // row stride of the packed projection
+constexpr int kLdO = 128;
+constexpr float kScale = 0.17677669529663687f;  // 1/sqrt(32)
+constexpr float kScaleLog2 = kScale * 1.4426950408889634f;
+constexpr int kTileBytes = kS * 64;  // one [1024][32] bf16 head slice
+
+__device__ __forceinline__ uint32_t sw_off(int row, int chunk) {
+  return (uint32_t)(row * 64 + (((chunk ^ (row >> 1)) & 3) << 4));
+}
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t ld32(const bf16* p) { return *reinterpret_cast<const uint32_t*>(p); }
+
+__device__ __forceinline__ void load_head_tile(uint32_t sbase, const bf16* g, long ld, int tid) {
+  for (int i = tid; i < kS * 4; i += 256) {
+    const int row = i >> 2, ch = i & 3;
+    cp_async_16(sbase + sw_off(row, ch), g + (long)row * ld + ch * 8, true);
+  }
+}
+// A-operand fragments (16 rows x 32 cols, two k-steps) of a row-major bf16 matrix in global memory
+__device__ __forceinline__ void load_a_frags(uint32_t (&a)[2][4], const bf16* row0, long ld, int c) {
+  const bf16* row1 = row0 + 8 * ld;
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks) {
+    a[ks][0] = ld32(row0 + ks * 16 + 2 * c);
+    a[ks][1] = ld32(row1 + ks * 16 + 2 * c);
+    a[ks][2] = ld32(row0 + ks * 16 + 8 + 2 * c);
+    a[ks][3] = ld32(row1 + ks * 16 + 8 + 2 * c);
+  }
+}
+// acc[8][4] (16 x 64) = A(16x32) * M^T, M = [64 rows of the smem head tile starting at row0][32]
+__device__ __forceinline__ void mma_a_mt(float (&acc)[8][4], const uint32_t (&a)[2][4], uint32_t sbase, int row0,
+                                         int lane) {
+#pragma unroll
+  for (int n = 0; n < 8; ++n) {
+    uint32_t r[4];
+    ldmatrix_x4(r, sbase + sw_off(row0 + n * 8 + (lane & 7), lane >> 3));
+    const uint32_t b0[2] = {r[0], r[1]}, b1[2] = {r[2], r[3]};
+    mma_bf16_16816(acc[n], a[0], b0);
+    mma_bf16_16816(acc[n], a[1], b1);
+  }
+}
+// acc[4][4] (16 x 32) += P(16x64, packed A frags) * M, M = [64 rows starting at row0][32] of the smem tile
+__device__ __forceinline__ void mma_p_m(float (&acc)[4][4], const uint32_t (&pa)[4][4], uint32_t sbase, int row0,
+                                        int lane) {
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    const int row = row0 + kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+#pragma unroll
+    for (int nd = 0; nd < 4; nd += 2) {
+      uint32_t r[4];
+      ldmatrix_x4_trans(r, sbase + sw_off(row, nd + (lane >> 4)));
+      const uint32_t b0[2] = {r[0], r[1]}, b1[2] = {r[2], r[3]};
+      mma_bf16_16816(acc[nd], pa[kk], b0);
+      mma_bf16_16816(acc[nd + 1], pa[kk], b1);
+    }
+  }
+}
+__device__ __forceinline__ void pack_frags(uint32_t (&pa)[4][4], const float (&s)[8][4]) {
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    pa[kk][0] = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
+    pa[kk][1] = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
+    pa[kk][2] = pack_bf16x2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+    pa[kk][3] = pack_bf16x2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+  }
+}
+__device__ __forceinline__ float quad_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  return v;
+}
+__device__ __forceinline__ float quad_max(float v) {
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------
+template <bool DROP>
+__global__ void __launch_bounds__(256, 1)
+attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __restrict__ lse2, uint32_t key,
+                uint32_t thresh16, float inv_keep) {
+  extern __shared__ __align__(128) uint8_t sm[];
+  const uint32_t sK = smem_u32(sm), sV = sK + kTileBytes;
+  const int bh = blockIdx.x, b = bh >> 2, h = bh & 3;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, c = lane & 3;
+  const bf16* base = qkv + (long)b * kS * kLdQkv + h * 32;
+  load_head_tile(sK, base + 128, kLdQkv, tid);
+  load_head_tile(sV, base + 256, kLdQkv, tid);
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncthreads();
+
+  for (int qt = 0; qt < kS / 128; ++qt) {
+    const int q0 = qt * 128 + warp * 16;
+    uint32_t qa[2][4];
+    load_a_frags(qa, base + (long)(q0 + g) * kLdQkv, kLdQkv, c);
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+    float o[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
+    const uint32_t rb0 = (uint32_t)(bh * kS + q0 + g) * 512u, rb1 = rb0 + 8u * 512u;
+
+#pragma unroll 1
+    for (int kt = 0; kt < kS / 64; ++kt) {
+      float s[8][4];
+#pragma unroll
+      for (int n = 0; n < 8; ++n) s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
+      mma_a_mt(s, qa, sK, kt * 64, lane);
+      float mx0 = s[0][0], mx1 = s[0][2];
+#pragma unroll
+      for (int n = 0; n < 8; ++n) {
+        mx0 = fmaxf(mx0, fmaxf(s[n][0], s[n][1]));
+        mx1 = fmaxf(mx1, fmaxf(s[n][2], s[n][3]));
+      }
+      mx0 = quad_max(mx0);
+      mx1 = quad_max(mx1);
+      const float mn0 = fmaxf(m0, mx0 * kScaleLog2), mn1 = fmaxf(m1, mx1 * kScaleLog2);
+      const float al0 = ex2(m0 - mn0), al1 = ex2(m1 - mn1);
+      m0 = mn0;
+      m1 = mn1;
+      float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+      for (int n = 0; n < 8; ++n) {
+        s[n][0] = ex2(fmaf(s[n][0], kScaleLog2, -mn0));
+        s[n][1] = ex2(fmaf(s[n][1], kScaleLog2, -mn0));
+        s[n][2] = ex2(fmaf(s[n][2], kScaleLog2, -mn1));
+        s[n][3] = ex2(fmaf(s[n][3], kScaleLog2, -mn1));
+        rs0 += s[n][0] + s[n][1];
+        rs1 += s[n][2] + s[n][3];
+      }
+      l0 = fmaf(l0, al0, rs0);
+      l1 = fmaf(l1, al1, rs1);
+#pragma unroll
+      for (int nd = 0; nd < 4; ++nd) {
+        o[nd][0] *= al0;
+        o[nd][1] *= al0;
+        o[nd][2] *= al1;
+        o[nd][3] *= al1;
+      }
+      if (DROP) {
+        const uint32_t cb = (uint32_t)(kt * 32 + c);
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+          const uint32_t h0 = drop_hash32(key, rb0 + cb + n * 4), h1 = drop_hash32(key, rb1 + cb + n * 4);
+          s[n][0] = (h0 & 0xFFFFu) >= thresh16 ? s[n][0] * inv_keep : 0.f;
+          s[n][1] = (h0 >> 16) >= thresh16 ? s[n][1] * inv_keep : 0.f;
+          s[n][2] = (h1 & 0xFFFFu) >= thresh16 ? s[n][2] * inv_keep : 0.f;
+          s[n][3] = (h1 >> 16) >= thresh16 ? s[n][3] * inv_keep : 0.f;
+        }
+      }
+      uint32_t pa[4][4];
+      pack_frags(pa, s);
+      mma_p_m(o, pa, sV, kt * 64, lane);
+    }
+    l0 = quad_sum(l0);
+    l1 = quad_sum(l1);
+    const float i0 = 1.f / l0, i1 = 1.f / l1;
+    bf16* orow0 = out + ((long)b * kS + q0 + g) * kLdO + h * 32;
+    bf16* orow1 = orow0 + 8 * kLdO;
+#pragma unroll
+    for (int nd = 0; nd < 4; ++nd) {
+      *reinterpret_cast<uint32_t*>(orow0 + nd * 8 + 2 * c) = pack_bf16x2(o[nd][0] * i0, o[nd][1] * i0);
+      *reinterpret_cast<uint32_t*>(orow1 + nd * 8 + 2 * c) = pack_bf16x2(o[nd][2] * i1, o[nd][3] * i1);
+    }
+    if (c == 0) {
+      lse2[(long)bh * kS + q0 + g] = m0 + log2f(l0);
+      lse2[(long)bh * kS + q0 + g + 8] = m1 + log2f(l1);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// backward pass A: dQ (and D = rowsum(dO o O), written for pass B)
+template <bool DROP>
+__global__ void __launch_bounds__(256, 1)
+attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o_in, const bf16* __restrict__ d_o,
+                   const float* __restrict__ lse2, float* __restrict__ dsum, bf16* __restrict__ dqkv, uint32_t key,
+                   uint32_t thresh16, float inv_keep) {
+  extern __shared__ __align__(128) uint8_t sm[];
+  const uint32_t sK = smem_u32(sm), sV = sK + kTileBytes;
+  const int bh = blockIdx.x, b = bh >> 2, h = bh & 3;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, c = lane & 3;
+  const bf16* base = qkv + (long)b * kS * kLdQkv + h * 32;
+  load_head_tile(sK, base + 128, kLdQkv, tid);
+  load_head_tile(sV, base + 256, kLdQkv, tid);
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncthreads();
+
+  for (int qt = 0; qt < kS / 128; ++qt) {
+    const int q0 = qt * 128 + warp * 16;
+    const long t0 = (long)b * kS + q0 + g;
+    uint32_t qa[2][4], da[2][4], oa[2][4];
+    load_a_frags(qa, base + (long)(q0 + g) * kLdQkv, kLdQkv, c);
+    load_a_frags(da, d_o + t0 * kLdO + h * 32, kLdO, c);
+    load_a_frags(oa, o_in + t0 * kLdO + h * 32, kLdO, c);
+    float D0 = 0.f, D1 = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 x = unpack_bf16x2(da[ks][j]), y = unpack_bf16x2(oa[ks][j]);
+        const float v = x.x * y.x + x.y * y.y;
+        if (j & 1) D1 += v; else D0 += v;
+      }
+    }
+    D0 = quad_sum(D0);
+    D1 = quad_sum(D1);
+    if (c == 0) {
+      dsum[(long)bh * kS + q0 + g] = D0;
+      dsum[(long)bh * kS + q0 + g + 8] = D1;
+    }
+    const float L0 = lse2[(long)bh * kS + q0 + g], L1 = lse2[(long)bh * kS + q0 + g + 8];
+    float dq[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dq[i][j] = 0.f;
+    const uint32_t rb0 = (uint32_t)(bh * kS + q0 + g) * 512u, rb1 = rb0 + 8u * 512u;
+
+#pragma unroll 1
+    for (int kt = 0; kt < kS / 64; ++kt) {
+      float s[8][4], dp[8][4];
+#pragma unroll
+      for (int n = 0; n < 8; ++n) {
+        s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
+        dp[n][0] = dp[n][1] = dp[n][2] = dp[n][3] = 0.f;
+      }
+      mma_a_mt(s, qa, sK, kt * 64, lane);
+      mma_a_mt(dp, da, sV, kt * 64, lane);
+      const uint32_t cb = (uint32_t)(kt * 32 + c);
+#pragma unroll
+      for (int n = 0; n < 8; ++n) {
+        const float p0 = ex2(fmaf(s[n][0], kScaleLog2, -L0)), p1 = ex2(fmaf(s[n][1], kScaleLog2, -L0));
+        const float p2 = ex2(fmaf(s[n][2], kScaleLog2, -L1)), p3 = ex2(fmaf(s[n][3], kScaleLog2, -L1));
+        float e0 = dp[n][0], e1 = dp[n][1], e2 = dp[n][2], e3 = dp[n][3];
+        if (DROP) {
+          const uint32_t h0 = drop_hash32(key, rb0 + cb + n * 4), h1 = drop_hash32(key, rb1 + cb + n * 4);
+          e0 = (h0 & 0xFFFFu) >= thresh16 ? e0 * inv_keep : 0.f;
+          e1 = (h0 >> 16) >= thresh16 ? e1 * inv_keep : 0.f;
+          e2 = (h1 & 0xFFFFu) >= thresh16 ? e2 * inv_keep : 0.f;
+          e3 = (h1 >> 16) >= thresh16 ? e3 * inv_keep : 0.f;
+        }
+        s[n][0] = p0 * (e0 - D0);
+        s[n][1] = p1 * (e1 - D0);
+        s[n][2] = p2 * (e2 - D1);
+        s[n][3] = p3 * (e3 - D1);
+      }
+      uint32_t pa[4][4];
+      pack_frags(pa, s);
+      mma_p_m(dq, pa, sK, kt * 64, lane);
+    }
+    bf16* r0 = dqkv + t0 * kLdQkv + h * 32;
+    bf16* r1 = r0 + 8 * kLdQkv;
+#pragma unroll
+    for (int nd = 0; nd < 4; ++nd) {
+      *reinterpret_cast<uint32_t*>(r0 + nd * 8 + 2 * c) = pack_bf16x2(dq[nd][0] * kScale, dq[nd][1] * kScale);
+      *reinterpret_cast<uint32_t*>(r1 + nd * 8 + 2 * c) = pack_bf16x2(dq[nd][2] * kScale, dq[nd][3] * kScale);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// backward pass B: dK, dV (warp owns 16 key rows; everything is the transpose of pass A)
+template <bool DROP>
+__global__ void __launch_bounds__(256, 1)
+attn_bwd_dkv_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ d_o, const float* __restrict__ lse2,
+                    const float* __restrict__ dsum, bf16* __restrict__ dqkv, uint32_t key, uint32_t thresh16,
+                    float inv_keep) {
+  extern __shared__ __align__(128) uint8_t sm[];
+  const uint32_t sQ = smem_u32(sm), sdO = sQ + kTileBytes;
+  float* sL = reinterpret_cast<float*>(sm + 2 * kTileBytes);
+  float* sD = sL + kS;
+  const int bh = blockIdx.x, b = bh >> 2, h = bh & 3;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, c = lane & 3;
+  const bf16* base = qkv + (long)b * kS * kLdQkv + h * 32;
+  load_head_tile(sQ, base, kLdQkv, tid);
+  load_head_tile(sdO, d_o + (long)b * kS * kLdO + h * 32, kLdO, tid);
+  cp_async_commit();
+  for (int i = tid; i < kS; i += 256) {
+    sL[i] = lse2[(long)bh * kS + i];
+    sD[i] = dsum[(long)bh * kS + i];
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+
+  for (int kb = 0; kb < kS / 128; ++kb) {
+    const int kv0 = kb * 128 + warp * 16;
+    uint32_t ka[2][4], va[2][4];
+    load_a_frags(ka, base + 128 + (long)(kv0 + g) * kLdQkv, kLdQkv, c);
+    load_a_frags(va, base + 256 + (long)(kv0 + g) * kLdQkv, kLdQkv, c);
+    float dk[4][4], dv[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dk[i][j] = dv[i][j] = 0.f;
+    // element (kv, q): counter = (bh*1024 + q)*512 + kv/2, 16-bit lane = kv & 1
+    const uint32_t kvh0 = (uint32_t)((kv0 + g) >> 1), kvh1 = (uint32_t)((kv0 + g + 8) >> 1);
+    const int sh = ((kv0 + g) & 1) * 16;  // same parity for row g and g+8
+
+#pragma unroll 1
+    for (int qt = 0; qt < kS / 64; ++qt) {
+      float st[8][4], dpt[8][4];
+#pragma unroll
+      for (int n = 0; n < 8; ++n) {
+        st[n][0] = st[n][1] = st[n][2] = st[n][3] = 0.f;
+        dpt[n][0] = dpt[n][1] = dpt[n][2] = dpt[n][3] = 0.f;
+      }
+      mma_a_mt(st, ka, sQ, qt * 64, lane);
+      mma_a_mt(dpt, va, sdO, qt * 64, lane);
+#pragma unroll
+      for (int n = 0; n < 8; ++n) {
+        const int q = qt * 64 + n * 8 + 2 * c;
+        const float2 Lq = *reinterpret_cast<const float2*>(sL + q);
+        const float2 Dq = *reinterpret_cast<const float2*>(sD + q);
+        const float p0 = ex2(fmaf(st[n][0], kScaleLog2, -Lq.x)), p1 = ex2(fmaf(st[n][1], kScaleLog2, -Lq.y));
+        const float p2 = ex2(fmaf(st[n][2], kScaleLog2, -Lq.x)), p3 = ex2(fmaf(st[n][3], kScaleLog2, -Lq.y));
+        float e0 = dpt[n][0], e1 = dpt[n][1], e2 = dpt[n][2], e3 = dpt[n][3];
+        float d0 = p0, d1 = p1, d2 = p2, d3 = p3;
+        if (DROP) {
+          const uint32_t qb0 = (uint32_t)(bh * kS + q) * 512u, qb1 = qb0 + 512u;
+          const bool k0 = ((drop_hash32(key, qb0 + kvh0) >> sh) & 0xFFFFu) >= thresh16;
+          const bool k1 = ((drop_hash32(key, qb1 + kvh0) >> sh) & 0xFFFFu) >= thresh16;
+          const bool k2 = ((drop_hash32(key, qb0 + kvh1) >> sh) & 0xFFFFu) >= thresh16;
+          const bool k3 = ((drop_hash32(key, qb1 + kvh1) >> sh) & 0xFFFFu) >= thresh16;
+          e0 = k0 ? e0 * inv_keep : 0.f; d0 = k0 ? p0 * inv_keep : 0.f;
+          e1 = k1 ? e1 * inv_keep : 0.f; d1 = k1 ? p1 * inv_keep : 0.f;
+          e2 = k2 ? e2 * inv_keep : 0.f; d2 = k2 ? p2 * inv_keep : 0.f;
+          e3 = k3 ? e3 * inv_keep : 0.f; d3 = k3 ? p3 * inv_keep : 0.f;
+        }
+        st[n][0] = p0 * (e0 - Dq.x);
+        st[n][1] = p1 * (e1 - Dq.y);
+        st[n][2] = p2 * (e2 - Dq.x);
+        st[n][3] = p3 * (e3 - Dq.y);
+        dpt[n][0] = d0;
+        dpt[n][1] = d1;
+        dpt[n][2] = d2;
+        dpt[n][3] = d3;
+      }
+      uint32_t pa[4][4];
+      pack_frags(pa, dpt);
+      mma_p_m(dv, pa, sdO, qt * 64, lane);
+      pack_frags(pa, st);
+      mma_p_m(dk, pa, sQ, qt * 64, lane);
+    }
+    bf16* r0 = dqkv + ((long)b * kS + kv0 + g) * kLdQkv + h * 32;
+    bf16* r1 = r0 + 8 * kLdQkv;
+#pragma unroll
+    for (int nd = 0; nd < 4; ++nd) {
+      *reinterpret_cast<uint32_t*>(r0 + 128 + nd * 8 + 2 * c) = pack_bf16x2(dk[nd][0] * kScale, dk[nd][1] * kScale);
+      *reinterpret_cast<uint32_t*>(r1 + 128 + nd * 8 + 2 * c) = pack_bf16x2(dk[nd][2] * kScale, dk[nd][3] * kScale);
+      *reinterpret_cast<uint32_t*>(r0 + 256 + nd * 8 + 2 * c) = pack_bf16x2(dv[nd][0], dv[nd][1]);
+      *reinterpret_cast<uint32_t*>(r1 + 256 + nd * 8 + 2 * c) = pack_bf16x2(dv[nd][2], dv[nd][3]);
+    }
+  }
+}
+
+template <typename K>
+int set_smem(K kernel, int bytes) {
+  FOCR_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  return FOCR_OK;
+}
+
+}  // namespace
+
+// p_drop = thresh16 / 65536; thresh16 == 0 disables dropout (eval / parity runs)
+int attn_forward(const bf16* qkv, bf16* out, float* lse2, int B, uint32_t key, uint32_t thresh16, cudaStream_t s) {
+  FOCR_REQUIRE(B >= 1 && B <= 1024, "attention: B=%d out of range", B);
+  const int smem = 2 * kTileBytes;
+  const float inv_keep = 65536.f / (65536.f - (float)thresh16);
+  static bool init = false;
+  if (!init) {
+    int rc = set_smem(attn_fwd_kernel<true>, smem);
+    if (rc) return rc;
+    rc = set_smem(attn_fwd_kernel<false>, smem);
+    if (rc) return rc;
+    init = true;
+  }
+  if (thresh16)
+    attn_fwd_kernel<true><<<B * 4, 256, smem, s>>>(qkv, out, lse2, key, thresh16, inv_keep);
+  else
+    attn_fwd_kernel<false><<<B * 4, 256, smem, s>>>(qkv, out, lse2, key, 0, 1.f);
+  FOCR_LAUNCH_CHECK();
+  return FOCR_OK;
+}
+
+int attn_backward(const bf16* qkv, const bf16* o, const bf16* d_o, const float* lse2, float* dsum, bf16* dqkv, int B,
+                  uint32_t key, uint32_t thresh16, cudaStream_t s) {
+  FOCR_REQUIRE(B >= 1 && B <= 1024, "attention: B=%d out of range", B);
+  const int smem_a = 2 * kTileBytes, smem_b = 2 * kTileBytes + 2 * kS * 4;
+  const float inv_keep = 65536.f / (65536.f - (float)thresh16);
+  static bool init = false;
+  if (!init) {
+    int rc = set_smem(attn_bwd_dq_kernel<true>, smem_a);
+    if (rc) return rc;
+    rc = set_smem(attn_bwd_dq_kernel<false>, smem_a);
+    if (rc) return rc;
+    rc = set_smem(attn_bwd_dkv_kernel<true>, smem_b);
+    if (rc) return rc;
+    rc = set_smem(attn_bwd_dkv_kernel<false>, smem_b);
+    if (rc) return rc;
+    init = true;
+  }
+  if (thresh16) {
+    attn_bwd_dq_kernel<true><<<B * 4, 256, smem_a, s>>>(qkv, o, d_o, lse2, dsum, dqkv, key, thresh16, inv_keep);
+    attn_bwd_dkv_kernel<true><<<B * 4, 256, smem_b, s>>>(qkv, d_o, lse2, dsum, dqkv, key, thresh16, inv_keep);
+  } else {
+    attn_bwd_dq_kernel<false><<<B * 4, 256, smem_a, s>>>(qkv, o, d_o, lse2, dsum, dqkv, key, 0, 1.f);
+    attn_bwd_dkv_kernel<false><<<B * 4, 256, smem_b, s>>>(qkv, d_o, lse2, dsum, dqkv, key, 0, 1.f);
+  }
+  FOCR_LAUNCH_CHECK();
+  return FOCR_OK;
+}

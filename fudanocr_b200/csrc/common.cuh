@@ -84,41 +84,21 @@ __device__ __forceinline__ float mish_grad_f(float x) {
 
 
 // ----------------------------------------------------------------------------------
-// counter-based RNG for dropout (Philox4x32, 7 rounds).  One call yields 128 random bits
-// = eight 16-bit lanes; an element is DROPPED when its 16-bit lane < thresh16
-// (thresh16 = round(p * 65536)).  The numpy twin lives in oracle/philox.py.
+// counter-based RNG for dropout: one 32-bit hash (murmur3 finaliser over a Weyl-premixed counter)
+// yields two 16-bit lanes; element 2*ctr + j is DROPPED when lane j < thresh16
+// (thresh16 = round(p * 65536)).  key = seed ^ (stream * golden).  numpy twin: oracle/dropout_rng.py.
 // ----------------------------------------------------------------------------------
-__host__ __device__ __forceinline__ uint4 philox4x32_7(uint4 c, uint32_t k0, uint32_t k1) {
-  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
-  for (int r = 0; r < 7; ++r) {
-#ifdef __CUDA_ARCH__
-    uint32_t hi0 = __umulhi(M0, c.x), hi1 = __umulhi(M1, c.z);
-#else
-    uint32_t hi0 = (uint32_t)(((uint64_t)M0 * c.x) >> 32), hi1 = (uint32_t)(((uint64_t)M1 * c.z) >> 32);
-#endif
-    uint32_t lo0 = M0 * c.x, lo1 = M1 * c.z;
-    c = make_uint4(hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0);
-    k0 += W0;
-    k1 += W1;
-  }
-  return c;
+__host__ __device__ __forceinline__ uint32_t drop_hash32(uint32_t key, uint32_t ctr) {
+  uint32_t h = ctr * 0x9E3779B1u + key;
+  h ^= h >> 16;
+  h *= 0x85EBCA6Bu;
+  h ^= h >> 13;
+  h *= 0xC2B2AE35u;
+  h ^= h >> 16;
+  return h;
 }
-// keep-flags for 8 consecutive elements of dropout group `grp` in stream `stream`:
-// bit j set = element j kept.
-__device__ __forceinline__ uint32_t dropout_keep8(uint32_t seed_lo, uint32_t seed_hi, uint32_t stream,
-                                                   uint64_t grp, uint32_t thresh16) {
-  uint4 r = philox4x32_7(make_uint4((uint32_t)grp, (uint32_t)(grp >> 32), stream, 0u), seed_lo, seed_hi);
-  uint32_t m = 0;
-  m |= ((r.x & 0xFFFFu) >= thresh16) << 0;
-  m |= ((r.x >> 16) >= thresh16) << 1;
-  m |= ((r.y & 0xFFFFu) >= thresh16) << 2;
-  m |= ((r.y >> 16) >= thresh16) << 3;
-  m |= ((r.z & 0xFFFFu) >= thresh16) << 4;
-  m |= ((r.z >> 16) >= thresh16) << 5;
-  m |= ((r.w & 0xFFFFu) >= thresh16) << 6;
-  m |= ((r.w >> 16) >= thresh16) << 7;
-  return m;
+__host__ __device__ __forceinline__ uint32_t drop_key(uint32_t seed, uint32_t stream) {
+  return seed ^ (stream * 0x9E3779B9u + 0x7F4A7C15u);
 }
 
 // ----------------------------------------------------------------------------------

@@ -172,6 +172,29 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
         }
+        if (p.drop_thresh16 != 0) {
+          const uint32_t c0h = (uint32_t)((mg * p.ldc + n0) >> 1);
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            const uint32_t hsh = drop_hash32(p.drop_key, c0h + q);
+            v[2 * q] = (hsh & 0xFFFFu) >= p.drop_thresh16 ? v[2 * q] * p.drop_scale : 0.f;
+            v[2 * q + 1] = (hsh >> 16) >= p.drop_thresh16 ? v[2 * q + 1] * p.drop_scale : 0.f;
+          }
+        }
+        if (p.gate != nullptr) {
+          const uint4* gp = reinterpret_cast<const uint4*>(p.gate + mg * p.ldc + n0);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 gv = gp[q];
+            const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float2 f = unpack_bf16x2(gw[j]);
+              v[q * 8 + 2 * j] = f.x > 0.f ? v[q * 8 + 2 * j] * p.gate_scale : 0.f;
+              v[q * 8 + 2 * j + 1] = f.y > 0.f ? v[q * 8 + 2 * j + 1] * p.gate_scale : 0.f;
+            }
+          }
+        }
         if (p.epi == TC_EPI_BF16) {
           const long off = mg * p.ldc + n0;
           if (p.residual != nullptr) {
