@@ -29,22 +29,45 @@ lib.focr_version.restype = C.c_int
 
 _vp, _i, _l, _sz, _fp = C.c_void_p, C.c_int, C.c_long, C.c_size_t, C.c_void_p
 
+_ll, _u, _f = C.c_longlong, C.c_uint, C.c_float
+_pp = C.POINTER(C.c_void_p)
+
 _SIGS = {
     "focr_sync_check": (C.c_int, [_vp]),
     "focr_conv2d_workspace_bytes": (_sz, [_i, _i, _i]),
     "focr_conv2d_fwd": (C.c_int, [_vp, _fp, _fp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
     "focr_conv2d_dgrad": (C.c_int, [_vp, _fp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "focr_wgrad_workspace_bytes": (_sz, []),
+    "focr_conv2d_wgrad": (C.c_int, [_vp, _vp, _fp, _i, _i, _i, _i, _vp, _sz, _vp]),
     "focr_linear_workspace_bytes": (_sz, [_i, _i]),
     "focr_linear_fwd": (C.c_int, [_vp, _fp, _fp, _vp, _vp, _l, _i, _i, _i, _vp, _sz, _vp]),
     "focr_linear_dgrad": (C.c_int, [_vp, _fp, _vp, _l, _i, _i, _vp, _sz, _vp]),
+    "focr_linear_wgrad": (C.c_int, [_vp, _vp, _fp, _l, _i, _i, _vp, _sz, _vp]),
+    "focr_bias_grad": (C.c_int, [_vp, _fp, _l, _i, _vp, _sz, _vp]),
+    "focr_bn_workspace_bytes": (_sz, []),
+    "focr_bn_train_fwd": (C.c_int, [_vp, _fp, _fp, _fp, _fp, _vp, _vp, _fp, _l, _i, _i, _vp, _sz, _vp]),
+    "focr_bn_bwd": (C.c_int, [_vp, _vp, _fp, _vp, _fp, _fp, _l, _i, _i, _vp, _sz, _vp]),
+    "focr_layernorm_std_fwd": (C.c_int, [_vp, _fp, _fp, _vp, _l, _f, _vp]),
+    "focr_layernorm_std_bwd": (C.c_int, [_vp, _vp, _fp, _vp, _fp, _fp, _l, _f, _vp, _sz, _vp]),
+    "focr_mha_flash_fwd": (C.c_int, [_vp, _vp, _fp, _i, _f, _u, _u, _vp]),
+    "focr_mha_flash_bwd": (C.c_int, [_vp, _vp, _vp, _fp, _fp, _vp, _i, _f, _u, _u, _vp]),
+    "focr_mse_loss_grad": (C.c_int, [_fp, _fp, _fp, _fp, _l, _f, _vp, _sz, _vp]),
+    "focr_adam_clip_step": (C.c_int, [_vp, _i, _f, _f, _f, _f, _f, _f, _vp, _fp, _vp, _sz, _vp]),
+    "focr_tbsrn_num_slots": (C.c_int, [_i]),
+    "focr_tbsrn_slot_name": (C.c_char_p, [_i, _i]),
+    "focr_tbsrn_workspace_bytes": (_sz, [_i, _i]),
+    "focr_tbsrn_forward": (C.c_int, [_pp, _fp, _fp, _i, _i, _i, _f, _u, _vp, _sz, _vp]),
+    "focr_tbsrn_backward": (C.c_int, [_pp, _pp, _fp, _fp, _i, _i, _i, _f, _u, _vp, _sz, _vp]),
+    "focr_prof_enable": (C.c_int, [_i, C.c_char_p]),
+    "focr_prof_collect": (C.c_int, [C.c_char_p, _i]),
+    "focr_launch_count": (_ll, []),
+    "focr_tbsrn_ws_tensor": (C.c_int, [_i, _i, C.c_char_p, C.POINTER(_ll), C.POINTER(_ll), C.POINTER(_i)]),
 }
 
 
 def _bind():
     for name, (res, args) in _SIGS.items():
-        fn = getattr(lib, name, None)
-        if fn is None:
-            continue
+        fn = getattr(lib, name)  # a missing symbol is a broken build: fail loudly
         fn.restype = res
         fn.argtypes = args
 
@@ -65,3 +88,14 @@ def ptr(t) -> int:
 def cur_stream() -> int:
     import torch
     return torch.cuda.current_stream().cuda_stream
+
+
+def prof_collect() -> dict:
+    """{scope: (launches, total_ms)} recorded since the last call (synchronises the device)."""
+    buf = C.create_string_buffer(1 << 16)
+    lib.focr_prof_collect(buf, len(buf))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, cnt, ms = line.split()
+        out[name] = (int(cnt), float(ms))
+    return out

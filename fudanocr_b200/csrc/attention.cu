@@ -393,6 +393,7 @@ int set_smem(K kernel, int bytes) {
 
 // p_drop = thresh16 / 65536; thresh16 == 0 disables dropout (eval / parity runs)
 int attn_forward(const bf16* qkv, bf16* out, float* lse2, int B, uint32_t key, uint32_t thresh16, cudaStream_t s) {
+  ProfScope _ps("attn_fwd", s);
   FOCR_REQUIRE(B >= 1 && B <= 1024, "attention: B=%d out of range", B);
   const int smem = 2 * kTileBytes;
   const float inv_keep = 65536.f / (65536.f - (float)thresh16);
@@ -429,13 +430,21 @@ int attn_backward(const bf16* qkv, const bf16* o, const bf16* d_o, const float* 
     if (rc) return rc;
     init = true;
   }
-  if (thresh16) {
-    attn_bwd_dq_kernel<true><<<B * 4, 256, smem_a, s>>>(qkv, o, d_o, lse2, dsum, dqkv, key, thresh16, inv_keep);
-    attn_bwd_dkv_kernel<true><<<B * 4, 256, smem_b, s>>>(qkv, d_o, lse2, dsum, dqkv, key, thresh16, inv_keep);
-  } else {
-    attn_bwd_dq_kernel<false><<<B * 4, 256, smem_a, s>>>(qkv, o, d_o, lse2, dsum, dqkv, key, 0, 1.f);
-    attn_bwd_dkv_kernel<false><<<B * 4, 256, smem_b, s>>>(qkv, d_o, lse2, dsum, dqkv, key, 0, 1.f);
+  {
+    ProfScope ps("attn_bwd_dq", s);
+    if (thresh16)
+      attn_bwd_dq_kernel<true><<<B * 4, 256, smem_a, s>>>(qkv, o, d_o, lse2, dsum, dqkv, key, thresh16, inv_keep);
+    else
+      attn_bwd_dq_kernel<false><<<B * 4, 256, smem_a, s>>>(qkv, o, d_o, lse2, dsum, dqkv, key, 0, 1.f);
+    FOCR_LAUNCH_CHECK();
   }
-  FOCR_LAUNCH_CHECK();
+  {
+    ProfScope ps("attn_bwd_dkv", s);
+    if (thresh16)
+      attn_bwd_dkv_kernel<true><<<B * 4, 256, smem_b, s>>>(qkv, d_o, lse2, dsum, dqkv, key, thresh16, inv_keep);
+    else
+      attn_bwd_dkv_kernel<false><<<B * 4, 256, smem_b, s>>>(qkv, d_o, lse2, dsum, dqkv, key, 0, 1.f);
+    FOCR_LAUNCH_CHECK();
+  }
   return FOCR_OK;
 }

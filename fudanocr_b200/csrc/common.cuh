@@ -34,7 +34,22 @@ void focr_set_error(const char* fmt, ...);
     }                                                                                    \
   } while (0)
 
-#define FOCR_LAUNCH_CHECK() FOCR_CHECK_CUDA(cudaGetLastError())
+void focr_count_launch(int n);
+#define FOCR_LAUNCH_CHECK()                \
+  do {                                     \
+    focr_count_launch(1);                  \
+    FOCR_CHECK_CUDA(cudaGetLastError());   \
+  } while (0)
+
+// named CUDA-event scope (prof.cu); no-op unless focr_prof_enable() turned profiling on
+bool prof_begin(const char* name, cudaStream_t s, void** tok);
+void prof_end(void* tok, cudaStream_t s);
+struct ProfScope {
+  void* tok;
+  cudaStream_t s;
+  ProfScope(const char* name, cudaStream_t st) : s(st) { prof_begin(name, st, &tok); }
+  ~ProfScope() { prof_end(tok, s); }
+};
 
 typedef __nv_bfloat16 bf16;
 typedef __nv_bfloat162 bf162;

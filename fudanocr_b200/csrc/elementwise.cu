@@ -133,7 +133,8 @@ __global__ void bn_eval_stats_kernel(const float* __restrict__ gamma, const floa
 __global__ void __launch_bounds__(kThreads) bn_apply_kernel(const bf16* __restrict__ x, long ld_x,
                                                             const float* __restrict__ stats, bf16* __restrict__ out,
                                                             long ld_out, long T, int C, int act,
-                                                            const bf16* __restrict__ pe, int pe_rows) {
+                                                            const bf16* __restrict__ pe, int pe_rows,
+                                                            const bf16* __restrict__ res) {
   const int tpr = C >> 3;
   const int rpb = kThreads / tpr;
   const int cg = threadIdx.x % tpr, rl = threadIdx.x / tpr;
@@ -148,6 +149,12 @@ __global__ void __launch_bounds__(kThreads) bn_apply_kernel(const bf16* __restri
     load8(x + t * ld_x + cg * 8, v);
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = act_fwd(fmaf(v[j], sc[j], sh[j]), act);
+    if (res != nullptr) {
+      float r[8];
+      load8(res + t * ld_out + cg * 8, r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += r[j];
+    }
     store8(out + t * ld_out + cg * 8, v);
     if (pe != nullptr) {
       const uint4 u = *reinterpret_cast<const uint4*>(pe + (long)(t % pe_rows) * C + cg * 8);
@@ -383,7 +390,9 @@ __global__ void __launch_bounds__(kThreads) ln_bwd_kernel(const bf16* __restrict
 // ---------------------------------------------------------------------------------------------
 // column sums (bias gradients): partial[blk][c] = sum_t x[t][c]
 // ---------------------------------------------------------------------------------------------
+// row t lives at x + (t / inner) * stride_outer + (t % inner) * ld   (inner == 0: plain row stride ld)
 __global__ void __launch_bounds__(kThreads) colsum_kernel(const bf16* __restrict__ x, long ld, long T, int C,
+                                                          long inner, long stride_outer,
                                                           float* __restrict__ partial) {
   __shared__ float red[kThreads][8];
   const int tpr = C >> 3;
@@ -395,7 +404,8 @@ __global__ void __launch_bounds__(kThreads) colsum_kernel(const bf16* __restrict
   if (rl < rpb) {
     for (long t = (long)blockIdx.x * rpb + rl; t < T; t += (long)gridDim.x * rpb) {
       float v[8];
-      load8(x + t * ld + cg * 8, v);
+      const long off = inner > 0 ? (t / inner) * stride_outer + (t % inner) * ld : t * ld;
+      load8(x + off + cg * 8, v);
 #pragma unroll
       for (int j = 0; j < 8; ++j) s[j] += v[j];
     }
@@ -506,6 +516,18 @@ __global__ void add_bf16_kernel(const bf16* __restrict__ a, const bf16* __restri
   }
 }
 
+// dx = dy * mish'(x)  (backward of the activation after PixelShuffle, tbsrn.py:272)
+__global__ void mish_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, bf16* __restrict__ dx, long n8) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long)gridDim.x * blockDim.x) {
+    float g[8], v[8];
+    load8(dy + i * 8, g);
+    load8(x + i * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] *= mish_grad_f(v[j]);
+    store8(dx + i * 8, g);
+  }
+}
+
 // positionalencoding2d(64,16,64) (tbsrn.py:39-61) as a (1024, 64) bf16 token-major table
 __global__ void pe_table_kernel(bf16* __restrict__ pe) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -540,6 +562,7 @@ int bn_partial_blocks(long T, int C) {
 
 int bn_train_stats(const bf16* x, long ld, long T, int C, const float* gamma, const float* beta, float* rm, float* rv,
                    long long* nbt, float eps, float momentum, float* partial, float* stats, cudaStream_t s) {
+  ProfScope _ps("bn_stats", s);
   FOCR_REQUIRE(C % 8 == 0 && kThreads % (C >> 3) == 0 && C <= 2048, "bn: unsupported C=%d", C);
   const int P = bn_partial_blocks(T, C);
   bn_stats_kernel<<<P, kThreads, 0, s>>>(x, ld, T, C, partial);
@@ -558,16 +581,18 @@ int bn_eval_stats(const float* gamma, const float* beta, const float* rm, const 
 }
 
 int bn_apply(const bf16* x, long ld_x, const float* stats, bf16* out, long ld_out, long T, int C, int act,
-             const bf16* pe, int pe_rows, cudaStream_t s) {
+             const bf16* pe, int pe_rows, const bf16* res, cudaStream_t s) {
+  ProfScope _ps("bn_apply", s);
   FOCR_REQUIRE(C % 8 == 0 && kThreads % (C >> 3) == 0, "bn_apply: unsupported C=%d", C);
   const int rpb = kThreads / (C >> 3);
-  bn_apply_kernel<<<ew_grid(T, rpb * 2), kThreads, 0, s>>>(x, ld_x, stats, out, ld_out, T, C, act, pe, pe_rows);
+  bn_apply_kernel<<<ew_grid(T, rpb * 2), kThreads, 0, s>>>(x, ld_x, stats, out, ld_out, T, C, act, pe, pe_rows, res);
   FOCR_LAUNCH_CHECK();
   return FOCR_OK;
 }
 
 int bn_backward(const bf16* dy, long ld_dy, const bf16* x, long ld_x, const float* stats, bf16* dx, long ld_dx, long T,
                 int C, int act, float* dgamma, float* dbeta, float* partial, float* coef, cudaStream_t s) {
+  ProfScope _ps("bn_bwd", s);
   FOCR_REQUIRE(C % 8 == 0 && kThreads % (C >> 3) == 0, "bn_backward: unsupported C=%d", C);
   const int P = bn_partial_blocks(T, C);
   bn_bwd_reduce_kernel<<<P, kThreads, 0, s>>>(dy, ld_dy, x, ld_x, stats, T, C, act, partial);
@@ -583,6 +608,7 @@ int bn_backward(const bf16* dy, long ld_dy, const bf16* x, long ld_x, const floa
 int ln_partial_blocks(long T) { return ew_grid(T, (kThreads / 16) * 8); }
 
 int ln_forward(const bf16* x, const float* a, const float* b, bf16* y, long T, float eps, cudaStream_t s) {
+  ProfScope _ps("ln_fwd", s);
   ln_fwd_kernel<<<ew_grid(T, (kThreads / 16) * 4), kThreads, 0, s>>>(x, a, b, y, T, eps);
   FOCR_LAUNCH_CHECK();
   return FOCR_OK;
@@ -590,10 +616,12 @@ int ln_forward(const bf16* x, const float* a, const float* b, bf16* y, long T, f
 
 int ln_backward(const bf16* dy, const bf16* x, const float* a, bf16* dx, float* da, float* db, float* partial, long T,
                 float eps, cudaStream_t s) {
+  ProfScope _ps("ln_bwd", s);
   const int P = ln_partial_blocks(T);
   ln_bwd_kernel<<<P, kThreads, 0, s>>>(dy, x, a, dx, partial, T, eps);
   FOCR_LAUNCH_CHECK();
   reduce_partials_kernel<<<1, 128, 0, s>>>(partial, P, 256, 128, da, 1.f);
+  FOCR_LAUNCH_CHECK();
   reduce_partials_kernel<<<1, 128, 0, s>>>(partial + 128, P, 256, 128, db, 1.f);
   FOCR_LAUNCH_CHECK();
   return FOCR_OK;
@@ -602,9 +630,22 @@ int ln_backward(const bf16* dy, const bf16* x, const float* a, bf16* dx, float* 
 int colsum_partial_blocks(long T, int C) { return ew_grid(T, (kThreads / (C >> 3)) * 8); }
 
 int colsum(const bf16* x, long ld, long T, int C, float* out, float* partial, cudaStream_t s) {
+  ProfScope _ps("colsum", s);
   FOCR_REQUIRE(C % 8 == 0 && (C >> 3) <= kThreads, "colsum: unsupported C=%d", C);
   const int P = colsum_partial_blocks(T, C);
-  colsum_kernel<<<P, kThreads, 0, s>>>(x, ld, T, C, partial);
+  colsum_kernel<<<P, kThreads, 0, s>>>(x, ld, T, C, 0, 0, partial);
+  FOCR_LAUNCH_CHECK();
+  reduce_partials_kernel<<<focr_cdiv(C, 128), 128, 0, s>>>(partial, P, C, C, out, 1.f);
+  FOCR_LAUNCH_CHECK();
+  return FOCR_OK;
+}
+
+int colsum2(const bf16* x, long t_outer, long t_inner, long stride_outer, long stride_inner, int C, float* out,
+            float* partial, cudaStream_t s) {
+  FOCR_REQUIRE(C % 8 == 0 && (C >> 3) <= kThreads, "colsum2: unsupported C=%d", C);
+  const long T = t_outer * t_inner;
+  const int P = colsum_partial_blocks(T, C);
+  colsum_kernel<<<P, kThreads, 0, s>>>(x, stride_inner, T, C, t_inner, stride_outer, partial);
   FOCR_LAUNCH_CHECK();
   reduce_partials_kernel<<<focr_cdiv(C, 128), 128, 0, s>>>(partial, P, C, C, out, 1.f);
   FOCR_LAUNCH_CHECK();
@@ -653,8 +694,52 @@ int add_bf16(const bf16* a, const bf16* b, bf16* o, long n, cudaStream_t s) {
   return FOCR_OK;
 }
 
+int mish_backward(const bf16* dy, const bf16* x, bf16* dx, long n, cudaStream_t s) {
+  FOCR_REQUIRE(n % 8 == 0, "mish_backward: n %% 8");
+  mish_bwd_kernel<<<ew_grid(n / 8, 256 * 2), 256, 0, s>>>(dy, x, dx, n / 8);
+  FOCR_LAUNCH_CHECK();
+  return FOCR_OK;
+}
+
 int pe_table(bf16* pe, cudaStream_t s) {
   pe_table_kernel<<<256, 256, 0, s>>>(pe);
+  FOCR_LAUNCH_CHECK();
+  return FOCR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// MSE loss head on the tanh output: loss = mean((sr-hr)^2), d_sr = gscale * 2 (sr-hr) / n
+// ---------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) mse_loss_grad_kernel(const float* __restrict__ sr, const float* __restrict__ hr,
+                                                            float* __restrict__ d_sr, long n, float k,
+                                                            float* __restrict__ partial) {
+  __shared__ float red[8];
+  float acc = 0.f;
+  for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long)gridDim.x * 256) {
+    const float d = sr[i] - hr[i];
+    acc += d * d;
+    if (d_sr) d_sr[i] = k * d;
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += red[w];
+    partial[blockIdx.x] = s;
+  }
+}
+}  // namespace
+
+extern "C" int focr_mse_loss_grad(const float* sr, const float* hr, float* d_sr, float* loss, long n, float gscale,
+                                  void* ws, size_t ws_bytes, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  const int P = ew_grid(n, 256 * 4);
+  FOCR_REQUIRE(ws_bytes >= (size_t)P * 4, "mse_loss_grad: workspace too small");
+  mse_loss_grad_kernel<<<P, 256, 0, s>>>(sr, hr, d_sr, n, gscale * 2.f / (float)n, (float*)ws);
+  FOCR_LAUNCH_CHECK();
+  reduce_partials_kernel<<<1, 32, 0, s>>>((const float*)ws, P, 1, 1, loss, 1.f / (float)n);
   FOCR_LAUNCH_CHECK();
   return FOCR_OK;
 }

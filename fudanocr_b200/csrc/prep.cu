@@ -51,15 +51,24 @@ __global__ void prep_bias_shuf_kernel(const float* __restrict__ b, float* __rest
   }
 }
 
+// inverse of prep_bias_shuf: o[c*4 + sub] = b[sub*(Co/4) + c]
+__global__ void bias_unshuf_kernel(const float* __restrict__ b, float* __restrict__ o, int Co) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < Co) {
+    const int q = Co / 4;
+    o[(i % q) * 4 + i / q] = b[i];
+  }
+}
+
 // fp32 [R][C] -> bf16 [R][C] and (optionally) bf16 transposed [C][R]
 __global__ void prep_linear_w_kernel(const float* __restrict__ w, bf16* __restrict__ o, bf16* __restrict__ ot,
-                                     int R, int C) {
+                                     int R, int C, int ot_ld, int ot_off) {
   const long n = (long)R * C;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
     const int c = (int)(i % C), r = (int)(i / C);
     const bf16 v = __float2bfloat16_rn(w[i]);
     if (o) o[i] = v;
-    if (ot) ot[(long)c * R + r] = v;
+    if (ot) ot[(long)c * ot_ld + ot_off + r] = v;
   }
 }
 
@@ -82,9 +91,15 @@ int prep_bias_shuf(const float* b, float* o, int Co, cudaStream_t s) {
   FOCR_LAUNCH_CHECK();
   return FOCR_OK;
 }
-int prep_linear_w(const float* w, bf16* o, bf16* ot, int R, int C, cudaStream_t s) {
+int bias_unshuf(const float* b, float* o, int Co, cudaStream_t s) {
+  bias_unshuf_kernel<<<focr_cdiv(Co, 128), 128, 0, s>>>(b, o, Co);
+  FOCR_LAUNCH_CHECK();
+  return FOCR_OK;
+}
+// ot (optional): transposed copy, element (c, r) written at ot[c*ot_ld + ot_off + r]
+int prep_linear_w(const float* w, bf16* o, bf16* ot, int R, int C, int ot_ld, int ot_off, cudaStream_t s) {
   const long n = (long)R * C;
-  prep_linear_w_kernel<<<focr_cdiv(n, 256), 256, 0, s>>>(w, o, ot, R, C);
+  prep_linear_w_kernel<<<focr_cdiv(n, 256), 256, 0, s>>>(w, o, ot, R, C, ot_ld, ot_off);
   FOCR_LAUNCH_CHECK();
   return FOCR_OK;
 }

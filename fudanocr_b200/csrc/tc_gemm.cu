@@ -45,8 +45,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int taps = p.ksize * p.ksize;
-  const int pad = p.ksize >> 1;
+  const int taps = p.kh * p.kw;
+  const int pad_h = p.kh >> 1, pad_w = p.kw >> 1;
   const int nk = taps * p.chunks;
   const int total_tiles = p.m_tiles * p.n_blocks;
 
@@ -86,7 +86,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
         const int b = p0 / hw;
         const int h0 = (p0 - b * hw) / p.W;
         for (int tap = 0; tap < taps; ++tap) {
-          const int dy = tap / p.ksize - pad, dx = tap % p.ksize - pad;
+          const int dy = tap / p.kw - pad_h, dx = tap % p.kw - pad_w;
           for (int ch = 0; ch < p.chunks; ++ch) {
             mbar_wait(&empty[stage], phase ^ 1);
             mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
@@ -197,6 +197,27 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
         }
         if (p.epi == TC_EPI_BF16) {
           const long off = mg * p.ldc + n0;
+          if (p.prelu_slope != nullptr) {
+            if (p.out2 != nullptr) {
+              uint4* op2 = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out2) + off);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                uint4 o;
+                o.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
+                o.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
+                o.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
+                o.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
+                op2[q] = o;
+              }
+            }
+            const float slope = p.prelu_slope[0];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              // differentiate what was stored: the pre-activation is kept in bf16
+              const float xr = __bfloat162float(__float2bfloat16_rn(v[j]));
+              v[j] = xr > 0.f ? xr : slope * xr;
+            }
+          }
           if (p.residual != nullptr) {
             const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off);
 #pragma unroll
@@ -352,7 +373,8 @@ int tc_gemm_launch(const bf16* const* a_ptrs, int n_amaps, long a_pix_stride, lo
   FOCR_REQUIRE(p.W == 64 || p.W == 128, "tc_gemm: W must be 64 or 128 (got %d)", p.W);
   FOCR_REQUIRE((p.H * p.W) % kTileM == 0, "tc_gemm: H*W must be a multiple of 128");
   FOCR_REQUIRE(cin % 64 == 0 && a_channels % 64 == 0, "tc_gemm: channels must be multiples of 64");
-  FOCR_REQUIRE(p.ksize == 1 || p.ksize == 3, "tc_gemm: ksize %d", p.ksize);
+  FOCR_REQUIRE(p.kh >= 1 && p.kw >= 1 && (p.kh & 1) && (p.kw & 1) && p.kh <= 9 && p.kw <= 9, "tc_gemm: taps %dx%d",
+               p.kh, p.kw);
   FOCR_REQUIRE(p.n_total % 64 == 0, "tc_gemm: N %d", p.n_total);
   const int block_n = tc_gemm_block_n(p.n_total);
   p.n_blocks = p.n_total / block_n;
@@ -375,13 +397,15 @@ int tc_gemm_launch(const bf16* const* a_ptrs, int n_amaps, long a_pix_stride, lo
   }
   CUtensorMap bm;
   {
-    const int taps = p.ksize * p.ksize;
+    const int taps = p.kh * p.kw;
     cuuint64_t dims[2] = {(cuuint64_t)cin, (cuuint64_t)taps * p.n_total};
     cuuint64_t str[1] = {(cuuint64_t)cin * 2};
     cuuint32_t box[2] = {64, (cuuint32_t)block_n};
     int rc = make_map(&bm, w, 2, dims, str, box);
     if (rc) return rc;
   }
+  const char* scope = p.kh * p.kw == 1 ? "tc_linear" : (p.kh == 3 && p.kw == 3 ? "tc_conv3x3" : "tc_conv9tap");
+  ProfScope _ps(scope, stream);
   if (block_n == 128) return launch_impl<128>(am, bm, p, stream);
   return launch_impl<64>(am, bm, p, stream);
 }

@@ -21,7 +21,7 @@ struct TcGemmParams {
   int m_tiles;         // M / 128
   int n_blocks;        // N_total / BLOCK_N
   int n_total;         // N_total
-  int ksize;           // 1 or 3
+  int kh, kw;          // filter taps (1x1, 3x3, 1x9, 9x1); zero padding kh/2, kw/2 via TMA OOB fill
   int chunks;          // 64-wide K chunks per tap (Cin / 64)
   int chunks_per_map;  // chunks served by one A tensor map
   int W, H;            // spatial size of the A feature map (W in {64,128}); tile = 128 consecutive pixels
@@ -40,6 +40,8 @@ struct TcGemmParams {
   // stored post-dropout activation)
   const bf16* gate;
   float gate_scale;
+  // PReLU epilogue (block1, tbsrn.py:180-182): out = x > 0 ? x : slope[0]*x ; out2 (optional) = x
+  const float* prelu_slope;
 };
 
 int tc_gemm_launch(const bf16* const* a_ptrs, int n_amaps, long a_pix_stride /*elements between pixels*/,

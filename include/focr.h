@@ -1,0 +1,102 @@
+/* libfocr_sm100.so — C ABI of the B200-native FudanOCR hot path (TBSRN train/eval step).
+ *
+ * The reference (FudanVI/FudanOCR) has no FFI: its seam is the Python nn.Module API that
+ * scene-text-telescope/interfaces/super_resolution.py:69-84 drives.  Each entry point below names the
+ * reference code it replaces (paths relative to the reference root, STT = scene-text-telescope).
+ *
+ * Conventions
+ *   - every pointer is a CUDA device pointer unless marked HOST; tensors are dense;
+ *     "bf16 (T,C)" = row-major matrix of __nv_bfloat16, NHWC feature maps are (B*H*W, C) matrices
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no call synchronises or allocates
+ *   - return 0 on success, negative on error (focr_last_error() gives the message); there is NO CPU
+ *     fallback: without an sm_100 device every compute entry point fails
+ *   - workspaces are caller-allocated device memory (torch.empty), sized by the *_workspace_bytes helpers
+ */
+#ifndef FOCR_H_
+#define FOCR_H_
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* focr_last_error(void);
+int focr_version(void);
+int focr_sync_check(void* stream); /* synchronise + surface asynchronous errors (tests only) */
+
+/* --- conv2d 3x3 / 1x1, stride 1, "same" padding, NHWC bf16, Ci and Co multiples of 64, W in {64,128} -------
+ * replaces nn.Conv2d at STT/model/tbsrn.py:190,232,237 (64->64) and :264 (64->256, UpsampleBLock).
+ * w: fp32 torch layout [Co][Ci][k][k].  flags bit0 relu; bit1 PixelShuffle(2)+mish epilogue (tbsrn.py:266-273):
+ * y = pre-activation (B,2H,2W,64), y2 = mish(y).  residual (optional) is added after the activation. */
+size_t focr_conv2d_workspace_bytes(int Ci, int Co, int ksize);
+int focr_conv2d_fwd(const void* x, const float* w, const float* bias, void* y, void* y2, const void* residual,
+                    int B, int H, int W, int Ci, int Co, int ksize, int flags, void* ws, size_t ws_bytes,
+                    void* stream);
+int focr_conv2d_dgrad(const void* dy, const float* w, void* dx, int B, int H, int W, int Ci, int Co, int ksize,
+                      int flags, void* ws, size_t ws_bytes, void* stream);
+size_t focr_wgrad_workspace_bytes(void);
+int focr_conv2d_wgrad(const void* dy, const void* x, float* dw, int B, int H, int Co, int flags, void* ws,
+                      size_t ws_bytes, void* stream);
+
+/* --- nn.Linear on token matrices: STT/model/tbsrn.py:74 (128->64), :103 (4 x 128->128), :158-159 (FFN) -------
+ * y[M,N] = x[M,K] w[N,K]^T + bias; flags bit0 relu, bit2 fp32 output; M % 128 == 0; K, N multiples of 64 */
+size_t focr_linear_workspace_bytes(int K, int N);
+int focr_linear_fwd(const void* x, const float* w, const float* bias, void* y, const void* residual, long M, int K,
+                    int N, int flags, void* ws, size_t ws_bytes, void* stream);
+int focr_linear_dgrad(const void* dy, const float* w, void* dx, long M, int K, int N, void* ws, size_t ws_bytes,
+                      void* stream);
+int focr_linear_wgrad(const void* dy, const void* x, float* dw, long M, int K, int N, void* ws, size_t ws_bytes,
+                      void* stream);
+int focr_bias_grad(const void* dy, float* db, long M, int N, void* ws, size_t ws_bytes, void* stream);
+
+/* --- nn.BatchNorm2d in train mode + activation: STT/model/tbsrn.py:233,238,191, stn_head.py:18-21 ----------
+ * act: 0 none, 1 mish (tbsrn.py:277-285), 2 relu.  stats: fp32 [4][C] = mean, invstd, scale, shift. */
+size_t focr_bn_workspace_bytes(void);
+int focr_bn_train_fwd(const void* x, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                      long long* num_batches_tracked, void* y, float* stats, long T, int C, int act, void* ws,
+                      size_t ws_bytes, void* stream);
+int focr_bn_bwd(const void* dy, const void* x, const float* stats, void* dx, float* dgamma, float* dbeta, long T, int C,
+                int act, void* ws, size_t ws_bytes, void* stream);
+
+/* --- the reference's home-made LayerNorm, features = 128: STT/model/tbsrn.py:23-36 ---------------------------
+ * y = a (x - mean) / (std_unbiased + eps) + b */
+int focr_layernorm_std_fwd(const void* x, const float* a, const float* b, void* y, long T, float eps, void* stream);
+int focr_layernorm_std_bwd(const void* dy, const void* x, const float* a, void* dx, float* da, float* db, long T,
+                           float eps, void* ws, size_t ws_bytes, void* stream);
+
+/* --- MultiHeadedAttention core, h = 4, d_k = 32, 1024 tokens: STT/model/tbsrn.py:109-150 ------------------------
+ * qkv (B*1024,384) bf16 = [q|k|v]; out (B*1024,128); lse2 fp32 (B*4*1024).  Dropout on P with rate p_drop,
+ * mask regenerated in backward from (seed, stream_id). */
+int focr_mha_flash_fwd(const void* qkv, void* out, float* lse2, int B, float p_drop, unsigned seed, unsigned stream_id,
+                       void* stream);
+int focr_mha_flash_bwd(const void* qkv, const void* out, const void* d_out, const float* lse2, float* dsum_ws,
+                       void* dqkv, int B, float p_drop, unsigned seed, unsigned stream_id, void* stream);
+
+/* --- step body: STT/interfaces/super_resolution.py:69-84, STT/loss/text_focus_loss.py:86, base.py:194-198 ------ */
+int focr_mse_loss_grad(const float* sr, const float* hr, float* d_sr, float* loss, long n, float gscale, void* ws,
+                       size_t ws_bytes, void* stream);
+int focr_adam_clip_step(const void* chunks, int n_chunks, float gscale, float max_norm, float lr, float beta1,
+                        float beta2, float eps, long long* step, float* state, void* ws, size_t ws_bytes, void* stream);
+
+/* --- whole network: STT/model/tbsrn.py:166-226 (TBSRN), stn_head.py, tps_spatial_transformer.py -------------------
+ * params / grads: HOST arrays of focr_tbsrn_num_slots() DEVICE pointers; slot i = reference state_dict entry
+ * focr_tbsrn_slot_name(srb_nums, i) (fp32 tensors, int64 for num_batches_tracked).  x_lr (B,3,16,64) fp32 NCHW in,
+ * sr (B,3,32,128) fp32 NCHW out.  flags bit0 training, bit1 STN present.  backward overwrites every gradient. */
+int focr_tbsrn_num_slots(int srb_nums);
+const char* focr_tbsrn_slot_name(int srb_nums, int idx);
+size_t focr_tbsrn_workspace_bytes(int B, int srb_nums);
+int focr_tbsrn_forward(void* const* params, const float* x_lr, float* sr, int B, int srb_nums, int flags, float p_drop,
+                       unsigned seed, void* ws, size_t ws_bytes, void* stream);
+int focr_tbsrn_backward(void* const* params, void* const* grads, const float* x_lr, const float* d_sr, int B,
+                        int srb_nums, int flags, float p_drop, unsigned seed, void* ws, size_t ws_bytes, void* stream);
+int focr_tbsrn_ws_tensor(int B, int srb_nums, const char* name, long long* byte_offset, long long* elems,
+                         int* elem_bytes);
+
+/* --- measurement hooks used by bench.py: CUDA-event scopes on the launching stream + launch counter ----------- */
+int focr_prof_enable(int mode /*0 off, 1 all, 2 focus*/, const char* focus_substring);
+int focr_prof_collect(char* buf, int cap); /* lines "scope launches total_ms"; synchronises; clears */
+long long focr_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FOCR_H_ */

@@ -99,15 +99,19 @@ def feature_enhancer(sd, pre, conv_feature: Tensor, masks: Optional[dict], p_dro
     return out.permute(0, 2, 1).contiguous()
 
 
-def srb(sd, pre, x, new_stats, training, masks):
+def srb(sd, pre, x, new_stats, training, masks, taps=None):
     """RecurrentResidualBlock.forward, model/tbsrn.py:246-257 (gru1/gru2 exist but are never called)."""
-    r = F.conv2d(x, sd[pre + ".conv1.weight"], sd[pre + ".conv1.bias"], padding=1)
-    r = mish(batch_norm_train(r, sd, pre + ".bn1", new_stats, training))
-    r = F.conv2d(r, sd[pre + ".conv2.weight"], sd[pre + ".conv2.bias"], padding=1)
-    r = batch_norm_train(r, sd, pre + ".bn2", new_stats, training)
+    c1 = F.conv2d(x, sd[pre + ".conv1.weight"], sd[pre + ".conv1.bias"], padding=1)
+    a1 = mish(batch_norm_train(c1, sd, pre + ".bn1", new_stats, training))
+    c2 = F.conv2d(a1, sd[pre + ".conv2.weight"], sd[pre + ".conv2.bias"], padding=1)
+    r = batch_norm_train(c2, sd, pre + ".bn2", new_stats, training)
     size = r.shape
     r = feature_enhancer(sd, pre + ".feature_enhancer", r.view(size[0], size[1], -1), masks)
-    return x + r.reshape(size)
+    out = x + r.reshape(size)
+    if taps is not None:
+        taps.update({pre + ".c1": c1.detach(), pre + ".a1": a1.detach(), pre + ".c2": c2.detach(),
+                     pre + ".out": out.detach()})
+    return out
 
 
 # ---------------------------------------------------------------------------------------------
@@ -144,16 +148,19 @@ def tps_transform(sd, x, ctrl, pre="tps"):
 # whole network and the training step
 # ---------------------------------------------------------------------------------------------
 def tbsrn_forward(sd: Dict[str, Tensor], x: Tensor, training: bool = True, stn: bool = True,
-                  srb_nums: int = 5, masks: Optional[dict] = None, new_stats: Optional[dict] = None) -> Tensor:
+                  srb_nums: int = 5, masks: Optional[dict] = None, new_stats: Optional[dict] = None,
+                  taps: Optional[dict] = None) -> Tensor:
     """TBSRN.forward, model/tbsrn.py:214-226."""
     if stn and training:
         ctrl = stn_head(sd, x, new_stats, training)
         x = tps_transform(sd, x, ctrl)
+        if taps is not None:
+            taps["ctrl"], taps["x_tps"] = ctrl.detach(), x.detach()
     b1 = F.conv2d(x, sd["block1.0.weight"], sd["block1.0.bias"], padding=4)
     b1 = F.prelu(b1, sd["block1.1.weight"])
     cur = b1
     for i in range(srb_nums):
-        cur = srb(sd, f"block{i + 2}", cur, new_stats, training, masks)
+        cur = srb(sd, f"block{i + 2}", cur, new_stats, training, masks, taps)
     k = srb_nums + 2
     cur = F.conv2d(cur, sd[f"block{k}.0.weight"], sd[f"block{k}.0.bias"], padding=1)
     cur = batch_norm_train(cur, sd, f"block{k}.1", new_stats, training)
@@ -161,6 +168,8 @@ def tbsrn_forward(sd: Dict[str, Tensor], x: Tensor, training: bool = True, stn: 
     u = F.conv2d(b1 + cur, sd[f"block{k}.0.conv.weight"], sd[f"block{k}.0.conv.bias"], padding=1)
     u = mish(F.pixel_shuffle(u, 2))
     out = F.conv2d(u, sd[f"block{k}.1.weight"], sd[f"block{k}.1.bias"], padding=4)
+    if taps is not None:
+        taps.update({"b1": b1.detach(), "s7": (b1 + cur).detach(), "u": u.detach(), "opre": out.detach()})
     return torch.tanh(out)
 
 
@@ -197,14 +206,15 @@ def adam_step(params, grads, state, lr=1e-4, betas=(0.5, 0.999), eps=1e-8):
 
 
 def train_step(sd: Dict[str, Tensor], lr_img: Tensor, hr_img: Tensor, opt_state: dict,
-               masks: Optional[dict] = None, stn: bool = True, srb_nums: int = 5):
+               masks: Optional[dict] = None, stn: bool = True, srb_nums: int = 5, taps: Optional[dict] = None):
     """The step body of TextSR.train (interfaces/super_resolution.py:60-84) with the MSE-only
     image_crit (loss/text_focus_loss.py:84-103, text_focus off): forward, mse, x100, backward,
     clip_grad_norm_(0.25), Adam.  Returns (new_sd, info)."""
     float_keys = [k for k, v in sd.items() if v.is_floating_point() and not is_buffer(k)]
     leaf = {k: (sd[k].detach().clone().requires_grad_(True) if k in float_keys else sd[k]) for k in sd}
     new_stats: dict = {}
-    sr = tbsrn_forward(leaf, lr_img, training=True, stn=stn, srb_nums=srb_nums, masks=masks, new_stats=new_stats)
+    sr = tbsrn_forward(leaf, lr_img, training=True, stn=stn, srb_nums=srb_nums, masks=masks, new_stats=new_stats,
+                       taps=taps)
     mse = F.mse_loss(sr, hr_img)
     (mse * 100).backward()
     grads = {k: leaf[k].grad for k in float_keys if leaf[k].grad is not None}
