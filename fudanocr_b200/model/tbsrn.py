@@ -162,9 +162,10 @@ class _TPS(_Holder):  # model/tps_spatial_transformer.py:54-95 (buffers only)
         yy, xx = torch.meshgrid(torch.arange(h, dtype=torch.float32), torch.arange(w, dtype=torch.float32),
                                 indexing="ij")
         coord = torch.stack([xx.reshape(-1) / (w - 1), yy.reshape(-1) / (h - 1)], 1)
-        self.register_buffer("inverse_kernel", torch.inverse(fk))
+        self.register_buffer("inverse_kernel", torch.inverse(fk).contiguous())  # torch.inverse returns column-major
         self.register_buffer("padding_matrix", torch.zeros(3, 2))
-        self.register_buffer("target_coordinate_repr", torch.cat([rbf(coord, tcp), torch.ones(h * w, 1), coord], 1))
+        self.register_buffer("target_coordinate_repr",
+                             torch.cat([rbf(coord, tcp), torch.ones(h * w, 1), coord], 1).contiguous())
         self.register_buffer("target_control_points", tcp)
 
 
@@ -250,6 +251,14 @@ class TBSRN(nn.Module):
                     raise KeyError(name)
                 tensors.append(None)
                 continue
+            if not t.is_contiguous() and not isinstance(t, nn.Parameter):
+                # buffers (e.g. a loaded column-major TPS matrix) are re-laid-out in place
+                mod, leaf = self, name
+                while "." in leaf:
+                    head, leaf = leaf.split(".", 1)
+                    mod = getattr(mod, head)
+                t = t.contiguous()
+                setattr(mod, leaf, t)
             if not t.is_cuda or not t.is_contiguous() or t.dtype not in (torch.float32, torch.int64):
                 raise L.FocrError(f"parameter {name}: the focr engine needs contiguous fp32 CUDA tensors "
                                   f"(got {t.dtype} on {t.device}); there is no CPU path")

@@ -1,0 +1,119 @@
+"""CPU tests of the host-side logic: C-ABI surface, drop-in module surface, data-parallel plumbing (gloo)."""
+import os
+import re
+import subprocess
+import sys
+import textwrap
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from fudanocr_b200 import _lib as L
+    hdr = open(os.path.join(ROOT, "include", "focr.h")).read()
+    names = set(re.findall(r"\b(focr_[a-z0-9_]+)\s*\(", hdr))
+    assert len(names) >= 30
+    for n in sorted(names):
+        assert hasattr(L.lib, n), f"{n} declared in include/focr.h but not exported"
+    assert L.lib.focr_version() >= 100
+    assert L.lib.focr_tbsrn_num_slots(5) == 227
+
+
+def test_no_cpu_fallback_for_the_engine():
+    """the product path must fail loudly without a GPU: no eager/PyTorch fallback"""
+    from fudanocr_b200 import _lib as L
+    from fudanocr_b200.model.tbsrn import TBSRN
+    m = TBSRN()
+    with pytest.raises(L.FocrError):
+        m(torch.rand(2, 3, 16, 64))
+
+
+def test_dropin_module_surface():
+    from fudanocr_b200.model.tbsrn import TBSRN
+    from fudanocr_b200.interfaces.parallel import DataParallel
+    from oracle import synth, tbsrn_oracle as O
+    spec = synth.load_spec("tbsrn")
+    m = TBSRN(scale_factor=2, width=128, height=32, STN=True, srb_nums=5, mask=False, hidden_units=32)
+    assert list(m.state_dict().keys()) == list(spec.keys())
+    assert all(list(v.shape) == spec[k] for k, v in m.state_dict().items())
+    sd = synth.synth_state_dict(spec, 7, O.tps_buffers())
+    m.load_state_dict(sd)  # reference checkpoints load unchanged
+    named = dict(m.named_parameters())
+    named.update(dict(m.named_buffers()))
+    for k in m._slot_names:  # every tensor handed to the engine by raw pointer must be dense fp32 / int64
+        assert named[k].is_contiguous() and named[k].dtype in (torch.float32, torch.int64), k
+    w = DataParallel(m)
+    assert w.module is m and len(list(w.parameters())) == len(list(m.parameters()))
+    pre = {"module." + k for k in spec}
+    assert set(w.state_dict().keys()) == pre  # 'module.'-prefixed keys as under nn.DataParallel (base.py:184-187)
+    m2 = TBSRN(STN=False)
+    assert not any(k.startswith("stn_head") or k.startswith("tps") for k in m2.state_dict())
+    with pytest.raises(NotImplementedError):
+        TBSRN(mask=True)
+
+
+def test_shard_bounds_cover_batch():
+    from fudanocr_b200.interfaces.parallel import shard_bounds, shard_batch
+    for n in (256, 7, 1024):
+        for world in (1, 2, 3, 8):
+            spans = [shard_bounds(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+    x, labels = torch.arange(10), list("abcdefghij")
+    a, b = shard_batch([x, labels], 1, 2)
+    assert a.tolist() == [5, 6, 7, 8, 9] and b == list("fghij")
+
+
+WORKER = textwrap.dedent("""
+    import os, sys, torch, torch.distributed as dist
+    sys.path.insert(0, %r)
+    from fudanocr_b200.interfaces.parallel import shard_batch, allreduce_mean_
+    from oracle import synth, tbsrn_oracle as O
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%%s" %% sys.argv[1], rank=int(sys.argv[2]), world_size=2)
+    rank = dist.get_rank()
+    torch.set_num_threads(2)
+    spec = {k: v for k, v in synth.load_spec("tbsrn").items()
+            if not (k.startswith("stn_head") or k.startswith("tps") or any(k.startswith("block%%d." %% i) for i in (3, 4, 5, 6)))}
+    # 1-SRB network: block2 = SRB, block7/8 of the reference become block3/4 here
+    spec = {k.replace("block7.", "block3.").replace("block8.", "block4."): v for k, v in spec.items()}
+    sd = synth.synth_state_dict(spec, 1234)
+    lr, hr = synth.synth_images(4)
+    keys = [k for k in sd if sd[k].is_floating_point() and not O.is_buffer(k) and "gru" not in k
+            and not k.startswith("conv.") and not k.startswith("bn.") and "compress" not in k]
+    def shard_grads(r):
+        l, h = shard_batch([lr, hr], r, 2)
+        leaf = {k: (sd[k].clone().requires_grad_(True) if k in keys else sd[k]) for k in sd}
+        sr = O.tbsrn_forward(leaf, l, training=True, stn=False, srb_nums=1)
+        (torch.nn.functional.mse_loss(sr, h) * 100).backward()
+        return torch.cat([leaf[k].grad.reshape(-1) for k in keys])
+    flat = shard_grads(rank)
+    allreduce_mean_(flat)
+    expect = (shard_grads(0) + shard_grads(1)) / 2   # single-process emulation of both replicas
+    assert torch.allclose(flat, expect, rtol=1e-5, atol=1e-7), (flat - expect).abs().max()
+    # clip AFTER the reduce -> identical step on every rank
+    norm = flat.norm()
+    gathered = [torch.zeros_like(norm) for _ in range(2)]
+    dist.all_gather(gathered, norm)
+    assert gathered[0] == gathered[1]
+    dist.destroy_process_group()
+    print("ok", rank)
+""")
+
+
+def test_two_rank_gloo_gradient_exchange(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER % ROOT)
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    procs = [subprocess.Popen([sys.executable, str(script), str(port), str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=300)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+        assert "ok" in o
