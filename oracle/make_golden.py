@@ -58,7 +58,7 @@ def main():
     sd = synth.synth_state_dict(spec, seed=1234, computed=tbuf)
     model.load_state_dict(sd)
     out = {}
-    B = 2
+    B = 4
     lr, hr = synth.synth_images(B, seed=1234)
 
     # ---- eval forward (STN off in eval, BN running stats, dropout off) ----------------------
@@ -115,10 +115,10 @@ def main():
     for k in new_sd:
         if new_sd[k].is_floating_point():
             assert torch.allclose(o_sd[k], new_sd[k], atol=2e-6, rtol=1e-4), k
-    torch.save(out, gd / "tbsrn_b2.pt")
-    h = hashlib.sha256((gd / "tbsrn_b2.pt").read_bytes()).hexdigest()
-    (gd / "SHA256SUMS").write_text(f"{h}  tbsrn_b2.pt\n")
-    print("golden written:", gd / "tbsrn_b2.pt", os.path.getsize(gd / "tbsrn_b2.pt"), "bytes; mse", loss.item(),
+    torch.save(out, gd / "tbsrn_b4.pt")
+    h = hashlib.sha256((gd / "tbsrn_b4.pt").read_bytes()).hexdigest()
+    (gd / "SHA256SUMS").write_text(f"{h}  tbsrn_b4.pt\n")
+    print("golden written:", gd / "tbsrn_b4.pt", os.path.getsize(gd / "tbsrn_b4.pt"), "bytes; mse", loss.item(),
           "gnorm", gnorm.item())
 
 

@@ -70,8 +70,23 @@ def identity_ctrl_points(n: int = 20, margin: float = 0.01) -> np.ndarray:
 
 
 def synth_images(B: int, seed: int = 1234):
-    """LR (B,3,16,64) and HR (B,3,32,128) fp32 in [0,1] (ToTensor range, dataset/dataset.py:143-152)."""
+    """LR (B,3,16,64) and HR (B,3,32,128) fp32 in [0,1] (ToTensor range, dataset/dataset.py:143-152).
+    Smooth, text-crop-like content: HR is a random low-frequency field plus a few sharp "strokes" and mild
+    noise; LR is its 2x2 box down-sample (the synthetic-LR recipe of dataset.py:240-254 uses bicubic).
+    White noise would make the TPS resampling step chaotic under any perturbation of the control points."""
     rs = np.random.RandomState(seed + 17)
-    lr = torch.from_numpy(rs.random_sample((B, 3, 16, 64)).astype(np.float32))
-    hr = torch.from_numpy(rs.random_sample((B, 3, 32, 128)).astype(np.float32))
-    return lr, hr
+    yy, xx = np.meshgrid(np.linspace(0, 1, 32), np.linspace(0, 1, 128), indexing="ij")
+    hr = np.zeros((B, 3, 32, 128), dtype=np.float64)
+    for b in range(B):
+        for c in range(3):
+            f = np.zeros_like(yy)
+            for _ in range(6):
+                fx, fy = rs.uniform(0.5, 6.0), rs.uniform(0.3, 2.0)
+                f += rs.uniform(0.2, 1.0) * np.cos(2 * np.pi * (fx * xx + fy * yy) + rs.uniform(0, 2 * np.pi))
+            for _ in range(4):  # vertical / slanted strokes
+                x0, wd, sl = rs.uniform(0.05, 0.95), rs.uniform(0.01, 0.03), rs.uniform(-0.2, 0.2)
+                f += rs.uniform(1.0, 2.0) * np.exp(-((xx - x0 - sl * (yy - 0.5)) / wd) ** 2)
+            f = (f - f.min()) / (f.max() - f.min() + 1e-9)
+            hr[b, c] = np.clip(0.9 * f + 0.05 + 0.01 * rs.standard_normal(f.shape), 0.0, 1.0)
+    lr = hr.reshape(B, 3, 16, 2, 64, 2).mean(axis=(3, 5))
+    return torch.from_numpy(lr.astype(np.float32)), torch.from_numpy(hr.astype(np.float32))

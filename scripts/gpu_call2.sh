@@ -5,7 +5,7 @@ nvidia-smi -L
 run() { echo "=== $*"; timeout 900 "$@" 2>&1 | tail -40; }
 run python -m pytest tests/test_gpu_gemm.py -m gpu -q --timeout 300 -p no:cacheprovider
 run python -m pytest tests/test_gpu_ops.py -m gpu -q --timeout 300 -p no:cacheprovider
-for t in test_eval_forward_vs_golden test_train_forward_backward_vs_oracle test_reference_loop_and_fused_trainer_agree test_dropout_on_matches_oracle_with_same_masks test_full_size_properties; do
+for t in test_eval_forward_vs_golden 'test_train_forward_backward_vs_oracle[False]' 'test_train_forward_backward_vs_oracle[True]' test_reference_loop_and_fused_trainer_agree test_dropout_on_matches_oracle_with_same_masks test_full_size_properties; do
   run python -m pytest "tests/test_gpu_tbsrn.py::$t" -m gpu -q --timeout 600 -p no:cacheprovider
   cp gpurun_out/tbsrn_parity.json gpurun_out/parity_$t.json 2>/dev/null
 done

@@ -10,7 +10,7 @@ from oracle import synth, tbsrn_oracle as O
 
 @pytest.fixture(scope="module")
 def golden():
-    path = synth.GOLDEN_DIR / "tbsrn_b2.pt"
+    path = synth.GOLDEN_DIR / "tbsrn_b4.pt"
     want = (synth.GOLDEN_DIR / "SHA256SUMS").read_text().split()[0]
     assert hashlib.sha256(path.read_bytes()).hexdigest() == want
     return torch.load(path, weights_only=False)
@@ -31,14 +31,14 @@ def test_spec_matches_reference_layout():
 
 
 def test_eval_forward(golden, sd):
-    lr, _ = synth.synth_images(2)
+    lr, _ = synth.synth_images(4)
     with torch.no_grad():
         sr = O.tbsrn_forward(sd, lr, training=False)
     assert torch.allclose(sr, golden["eval_sr"], atol=2e-5, rtol=1e-4)
 
 
 def test_train_step(golden, sd):
-    lr, hr = synth.synth_images(2)
+    lr, hr = synth.synth_images(4)
     new_sd, info = O.train_step(sd, lr, hr, {}, masks=None)
     assert torch.allclose(info["sr"], golden["train_sr"], atol=2e-5, rtol=1e-4)
     assert abs(info["mse"].item() - golden["train_mse"].item()) < 1e-6
@@ -57,12 +57,12 @@ def test_train_step(golden, sd):
 
 
 def test_dropout_mask_changes_output(sd):
-    lr, _ = synth.synth_images(2)
+    lr, _ = synth.synth_images(4)
     g = torch.Generator().manual_seed(0)
     masks = {}
     for i in range(2, 7):
-        masks[f"block{i}.feature_enhancer.attn"] = torch.rand(2, 4, 1024, 1024, generator=g) >= 0.1
-        masks[f"block{i}.feature_enhancer.ffn"] = torch.rand(2, 1024, 128, generator=g) >= 0.1
+        masks[f"block{i}.feature_enhancer.attn"] = torch.rand(4, 4, 1024, 1024, generator=g) >= 0.1
+        masks[f"block{i}.feature_enhancer.ffn"] = torch.rand(4, 1024, 128, generator=g) >= 0.1
     with torch.no_grad():
         a = O.tbsrn_forward(sd, lr, training=True, masks=masks)
         b = O.tbsrn_forward(sd, lr, training=True, masks=None)
