@@ -86,18 +86,30 @@ __global__ void __launch_bounds__(kThreads) bn_stats_kernel(const bf16* __restri
 
 // stats[0]=mean [1]=invstd [2]=scale=gamma*invstd [3]=shift=beta-mean*scale ; running stats updated
 // as nn.BatchNorm does in train mode (momentum 0.1, unbiased variance).
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// second-stage reductions: one WARP per output element (lanes stride over the P partials) so the stage is
+// a handful of microseconds instead of a serial chain of P dependent L2 round trips
 __global__ void bn_finalize_kernel(const float* __restrict__ partial, int P, int C, long T,
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float* __restrict__ running_mean, float* __restrict__ running_var,
                                    long long* __restrict__ nbt, float eps, float momentum,
                                    float* __restrict__ stats) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (c >= C) return;
   double s = 0.0, q = 0.0;
-  for (int p = 0; p < P; ++p) {
+  for (int p = lane; p < P; p += 32) {
     s += partial[(long)p * 2 * C + c];
     q += partial[(long)p * 2 * C + C + c];
   }
+  s = warp_sum_d(s);
+  q = warp_sum_d(q);
+  if (lane != 0) return;
   const double mean = s / (double)T;
   double var = q / (double)T - mean * mean;
   if (var < 0.0) var = 0.0;
@@ -219,13 +231,17 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_reduce_kernel(const bf16* __r
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int P, int C, long T,
                                        float* __restrict__ coef, float* __restrict__ dgamma,
                                        float* __restrict__ dbeta) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (c >= C) return;
   double s = 0.0, q = 0.0;
-  for (int p = 0; p < P; ++p) {
+  for (int p = lane; p < P; p += 32) {
     s += partial[(long)p * 2 * C + c];
     q += partial[(long)p * 2 * C + C + c];
   }
+  s = warp_sum_d(s);
+  q = warp_sum_d(q);
+  if (lane != 0) return;
   coef[c] = (float)(s / (double)T);
   coef[C + c] = (float)(q / (double)T);
   if (dgamma) dgamma[c] = (float)q;
@@ -426,11 +442,13 @@ __global__ void __launch_bounds__(kThreads) colsum_kernel(const bf16* __restrict
 // out[i] = scale * sum_p partial[p*stride + i]   (deterministic second stage of every reduction)
 __global__ void reduce_partials_kernel(const float* __restrict__ partial, int P, long stride, int n,
                                        float* __restrict__ out, float scale) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (i >= n) return;
   double s = 0.0;
-  for (int p = 0; p < P; ++p) s += partial[(long)p * stride + i];
-  out[i] = (float)s * scale;
+  for (int p = lane; p < P; p += 32) s += partial[(long)p * stride + i];
+  s = warp_sum_d(s);
+  if (lane == 0) out[i] = (float)s * scale;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -542,6 +560,15 @@ __global__ void pe_table_kernel(bf16* __restrict__ pe) {
   pe[i] = __float2bfloat16_rn(v);
 }
 
+// grid for reduction passes: at most 2 CTAs per SM so the second stage sums <= 296 partials
+int red_grid(long work_items, int per_block) {
+  long g = (work_items + per_block - 1) / per_block;
+  const long cap = 148L * 2;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
 int ew_grid(long work_items, int per_block) {
   long g = (work_items + per_block - 1) / per_block;
   const long cap = 148L * 8;
@@ -557,7 +584,7 @@ int ew_grid(long work_items, int per_block) {
 // ---------------------------------------------------------------------------------------------
 int bn_partial_blocks(long T, int C) {
   const int rpb = kThreads / (C >> 3);
-  return ew_grid(T, rpb * 4);
+  return red_grid(T, rpb * 4);
 }
 
 int bn_train_stats(const bf16* x, long ld, long T, int C, const float* gamma, const float* beta, float* rm, float* rv,
@@ -567,7 +594,7 @@ int bn_train_stats(const bf16* x, long ld, long T, int C, const float* gamma, co
   const int P = bn_partial_blocks(T, C);
   bn_stats_kernel<<<P, kThreads, 0, s>>>(x, ld, T, C, partial);
   FOCR_LAUNCH_CHECK();
-  bn_finalize_kernel<<<focr_cdiv(C, 128), 128, 0, s>>>(partial, P, C, T, gamma, beta, rm, rv, nbt, eps, momentum,
+  bn_finalize_kernel<<<focr_cdiv(C, 4), 128, 0, s>>>(partial, P, C, T, gamma, beta, rm, rv, nbt, eps, momentum,
                                                         stats);
   FOCR_LAUNCH_CHECK();
   return FOCR_OK;
@@ -597,7 +624,7 @@ int bn_backward(const bf16* dy, long ld_dy, const bf16* x, long ld_x, const floa
   const int P = bn_partial_blocks(T, C);
   bn_bwd_reduce_kernel<<<P, kThreads, 0, s>>>(dy, ld_dy, x, ld_x, stats, T, C, act, partial);
   FOCR_LAUNCH_CHECK();
-  bn_bwd_finalize_kernel<<<focr_cdiv(C, 128), 128, 0, s>>>(partial, P, C, T, coef, dgamma, dbeta);
+  bn_bwd_finalize_kernel<<<focr_cdiv(C, 4), 128, 0, s>>>(partial, P, C, T, coef, dgamma, dbeta);
   FOCR_LAUNCH_CHECK();
   const int rpb = kThreads / (C >> 3);
   bn_bwd_apply_kernel<<<ew_grid(T, rpb * 2), kThreads, 0, s>>>(dy, ld_dy, x, ld_x, stats, coef, dx, ld_dx, T, C, act);
@@ -605,7 +632,7 @@ int bn_backward(const bf16* dy, long ld_dy, const bf16* x, long ld_x, const floa
   return FOCR_OK;
 }
 
-int ln_partial_blocks(long T) { return ew_grid(T, (kThreads / 16) * 8); }
+int ln_partial_blocks(long T) { return red_grid(T, (kThreads / 16) * 8); }
 
 int ln_forward(const bf16* x, const float* a, const float* b, bf16* y, long T, float eps, cudaStream_t s) {
   ProfScope _ps("ln_fwd", s);
@@ -620,14 +647,14 @@ int ln_backward(const bf16* dy, const bf16* x, const float* a, bf16* dx, float* 
   const int P = ln_partial_blocks(T);
   ln_bwd_kernel<<<P, kThreads, 0, s>>>(dy, x, a, dx, partial, T, eps);
   FOCR_LAUNCH_CHECK();
-  reduce_partials_kernel<<<1, 128, 0, s>>>(partial, P, 256, 128, da, 1.f);
+  reduce_partials_kernel<<<32, 128, 0, s>>>(partial, P, 256, 128, da, 1.f);
   FOCR_LAUNCH_CHECK();
-  reduce_partials_kernel<<<1, 128, 0, s>>>(partial + 128, P, 256, 128, db, 1.f);
+  reduce_partials_kernel<<<32, 128, 0, s>>>(partial + 128, P, 256, 128, db, 1.f);
   FOCR_LAUNCH_CHECK();
   return FOCR_OK;
 }
 
-int colsum_partial_blocks(long T, int C) { return ew_grid(T, (kThreads / (C >> 3)) * 8); }
+int colsum_partial_blocks(long T, int C) { return red_grid(T, (kThreads / (C >> 3)) * 8); }
 
 int colsum(const bf16* x, long ld, long T, int C, float* out, float* partial, cudaStream_t s) {
   ProfScope _ps("colsum", s);
@@ -635,7 +662,7 @@ int colsum(const bf16* x, long ld, long T, int C, float* out, float* partial, cu
   const int P = colsum_partial_blocks(T, C);
   colsum_kernel<<<P, kThreads, 0, s>>>(x, ld, T, C, 0, 0, partial);
   FOCR_LAUNCH_CHECK();
-  reduce_partials_kernel<<<focr_cdiv(C, 128), 128, 0, s>>>(partial, P, C, C, out, 1.f);
+  reduce_partials_kernel<<<focr_cdiv(C, 4), 128, 0, s>>>(partial, P, C, C, out, 1.f);
   FOCR_LAUNCH_CHECK();
   return FOCR_OK;
 }
@@ -647,13 +674,13 @@ int colsum2(const bf16* x, long t_outer, long t_inner, long stride_outer, long s
   const int P = colsum_partial_blocks(T, C);
   colsum_kernel<<<P, kThreads, 0, s>>>(x, stride_inner, T, C, t_inner, stride_outer, partial);
   FOCR_LAUNCH_CHECK();
-  reduce_partials_kernel<<<focr_cdiv(C, 128), 128, 0, s>>>(partial, P, C, C, out, 1.f);
+  reduce_partials_kernel<<<focr_cdiv(C, 4), 128, 0, s>>>(partial, P, C, C, out, 1.f);
   FOCR_LAUNCH_CHECK();
   return FOCR_OK;
 }
 
 int reduce_partials(const float* partial, int P, long stride, int n, float* out, float scale, cudaStream_t s) {
-  reduce_partials_kernel<<<focr_cdiv(n, 128), 128, 0, s>>>(partial, P, stride, n, out, scale);
+  reduce_partials_kernel<<<focr_cdiv(n, 4), 128, 0, s>>>(partial, P, stride, n, out, scale);
   FOCR_LAUNCH_CHECK();
   return FOCR_OK;
 }
