@@ -36,7 +36,7 @@ __device__ __forceinline__ float ex2(float x) {
 __device__ __forceinline__ uint32_t ld32(const bf16* p) { return *reinterpret_cast<const uint32_t*>(p); }
 
 __device__ __forceinline__ void load_head_tile(uint32_t sbase, const bf16* g, long ld, int tid) {
-  for (int i = tid; i < kS * 4; i += 256) {
+  for (int i = tid; i < kS * 4; i += (int)blockDim.x) {
     const int row = i >> 2, ch = i & 3;
     cp_async_16(sbase + sw_off(row, ch), g + (long)row * ld + ch * 8, true);
   }
@@ -101,8 +101,8 @@ __device__ __forceinline__ float quad_max(float v) {
 }
 
 // ------------------------------------------------------------------------------------------
-template <bool DROP>
-__global__ void __launch_bounds__(256, 1)
+template <bool DROP, int NW>
+__global__ void __launch_bounds__(NW * 32, 1)
 attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __restrict__ lse2, uint32_t key,
                 uint32_t thresh16, float inv_keep) {
   extern __shared__ __align__(128) uint8_t sm[];
@@ -116,8 +116,8 @@ attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __r
   cp_async_wait<0>();
   __syncthreads();
 
-  for (int qt = 0; qt < kS / 128; ++qt) {
-    const int q0 = qt * 128 + warp * 16;
+  for (int u = warp; u < kS / 16; u += NW) {  // 64 units of 16 query rows, round-robin over the warps
+    const int q0 = u * 16;
     uint32_t qa[2][4];
     load_a_frags(qa, base + (long)(q0 + g) * kLdQkv, kLdQkv, c);
     float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
@@ -199,8 +199,8 @@ attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __r
 
 // ------------------------------------------------------------------------------------------
 // backward pass A: dQ (and D = rowsum(dO o O), written for pass B)
-template <bool DROP>
-__global__ void __launch_bounds__(256, 1)
+template <bool DROP, int NW>
+__global__ void __launch_bounds__(NW * 32, 1)
 attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o_in, const bf16* __restrict__ d_o,
                    const float* __restrict__ lse2, float* __restrict__ dsum, bf16* __restrict__ dqkv, uint32_t key,
                    uint32_t thresh16, float inv_keep) {
@@ -215,8 +215,8 @@ attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o_in, 
   cp_async_wait<0>();
   __syncthreads();
 
-  for (int qt = 0; qt < kS / 128; ++qt) {
-    const int q0 = qt * 128 + warp * 16;
+  for (int u = warp; u < kS / 16; u += NW) {
+    const int q0 = u * 16;
     const long t0 = (long)b * kS + q0 + g;
     uint32_t qa[2][4], da[2][4], oa[2][4];
     load_a_frags(qa, base + (long)(q0 + g) * kLdQkv, kLdQkv, c);
@@ -305,7 +305,7 @@ attn_bwd_dkv_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ d_o, 
   load_head_tile(sQ, base, kLdQkv, tid);
   load_head_tile(sdO, d_o + (long)b * kS * kLdO + h * 32, kLdO, tid);
   cp_async_commit();
-  for (int i = tid; i < kS; i += 256) {
+  for (int i = tid; i < kS; i += (int)blockDim.x) {
     sL[i] = lse2[(long)bh * kS + i];
     sD[i] = dsum[(long)bh * kS + i];
   }
@@ -383,6 +383,11 @@ attn_bwd_dkv_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ d_o, 
   }
 }
 
+// warps per CTA (one CTA per SM: 128 KB of smem).  More resident warps hide the mma.sync / MUFU / ldmatrix
+// latencies of this issue-bound kernel; the register file caps them (65536 / (32 * regs)).
+constexpr int kFwdWarps = 16;  // <= 128 registers
+constexpr int kDqWarps = 13;   // <= 157 registers; 64 units over 13 warps = 5 passes (98 % filled)
+
 template <typename K>
 int set_smem(K kernel, int bytes) {
   FOCR_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
@@ -399,16 +404,16 @@ int attn_forward(const bf16* qkv, bf16* out, float* lse2, int B, uint32_t key, u
   const float inv_keep = 65536.f / (65536.f - (float)thresh16);
   static bool init = false;
   if (!init) {
-    int rc = set_smem(attn_fwd_kernel<true>, smem);
+    int rc = set_smem(attn_fwd_kernel<true, kFwdWarps>, smem);
     if (rc) return rc;
-    rc = set_smem(attn_fwd_kernel<false>, smem);
+    rc = set_smem(attn_fwd_kernel<false, kFwdWarps>, smem);
     if (rc) return rc;
     init = true;
   }
   if (thresh16)
-    attn_fwd_kernel<true><<<B * 4, 256, smem, s>>>(qkv, out, lse2, key, thresh16, inv_keep);
+    attn_fwd_kernel<true, kFwdWarps><<<B * 4, kFwdWarps * 32, smem, s>>>(qkv, out, lse2, key, thresh16, inv_keep);
   else
-    attn_fwd_kernel<false><<<B * 4, 256, smem, s>>>(qkv, out, lse2, key, 0, 1.f);
+    attn_fwd_kernel<false, kFwdWarps><<<B * 4, kFwdWarps * 32, smem, s>>>(qkv, out, lse2, key, 0, 1.f);
   FOCR_LAUNCH_CHECK();
   return FOCR_OK;
 }
@@ -420,9 +425,9 @@ int attn_backward(const bf16* qkv, const bf16* o, const bf16* d_o, const float* 
   const float inv_keep = 65536.f / (65536.f - (float)thresh16);
   static bool init = false;
   if (!init) {
-    int rc = set_smem(attn_bwd_dq_kernel<true>, smem_a);
+    int rc = set_smem(attn_bwd_dq_kernel<true, kDqWarps>, smem_a);
     if (rc) return rc;
-    rc = set_smem(attn_bwd_dq_kernel<false>, smem_a);
+    rc = set_smem(attn_bwd_dq_kernel<false, kDqWarps>, smem_a);
     if (rc) return rc;
     rc = set_smem(attn_bwd_dkv_kernel<true>, smem_b);
     if (rc) return rc;
@@ -433,9 +438,11 @@ int attn_backward(const bf16* qkv, const bf16* o, const bf16* d_o, const float* 
   {
     ProfScope ps("attn_bwd_dq", s);
     if (thresh16)
-      attn_bwd_dq_kernel<true><<<B * 4, 256, smem_a, s>>>(qkv, o, d_o, lse2, dsum, dqkv, key, thresh16, inv_keep);
+      attn_bwd_dq_kernel<true, kDqWarps><<<B * 4, kDqWarps * 32, smem_a, s>>>(qkv, o, d_o, lse2, dsum, dqkv, key,
+                                                                             thresh16, inv_keep);
     else
-      attn_bwd_dq_kernel<false><<<B * 4, 256, smem_a, s>>>(qkv, o, d_o, lse2, dsum, dqkv, key, 0, 1.f);
+      attn_bwd_dq_kernel<false, kDqWarps><<<B * 4, kDqWarps * 32, smem_a, s>>>(qkv, o, d_o, lse2, dsum, dqkv, key, 0,
+                                                                              1.f);
     FOCR_LAUNCH_CHECK();
   }
   {

@@ -312,6 +312,17 @@ int focr_tbsrn_ws_tensor(int B, int srb_nums, const char* name, long long* byte_
   std::string nm(name);
   if (nm == "x_tps") { p = w.x_tps; n = (long)B * 3072; eb = 4; }
   else if (nm == "ctrl") { p = w.ctrl; n = (long)B * 64; eb = 4; }
+  else if (nm.rfind("stn.yact", 0) == 0 || nm.rfind("stn.pool", 0) == 0 || nm.rfind("stn.ypre", 0) == 0) {
+    const int i = atoi(nm.substr(8).c_str());
+    FOCR_REQUIRE(i >= 0 && i < 6, "ws_tensor: bad stn index in %s", name);
+    const tbsrn::StnConv& c = tbsrn::kStn[i];
+    const long M = (long)B * c.h * c.w;
+    if (nm[4] == 'y' && nm[5] == 'a') { p = w.stn_yact[i]; n = M * c.cout; }
+    else if (nm[4] == 'y') { p = w.stn_ypre[i]; n = M * c.npad; }
+    else { p = w.stn_pool[i]; n = (c.pool_h ? M / (2 * c.pool_h) : M) * c.cout; }
+  }
+  else if (nm == "stn.f1") { p = w.f1; n = (long)B * 512; }
+  else if (nm == "stn.f1pre") { p = w.f1pre; n = (long)B * 512; }
   else if (nm == "b1") { p = w.b1; n = T * 64; }
   else if (nm == "s7") { p = w.s7; n = T * 64; }
   else if (nm == "u") { p = w.u; n = Thr * 64; }

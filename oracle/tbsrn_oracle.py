@@ -117,17 +117,25 @@ def srb(sd, pre, x, new_stats, training, masks, taps=None):
 # ---------------------------------------------------------------------------------------------
 # STN head + TPS  (model/stn_head.py:25-99, model/tps_spatial_transformer.py:54-112)
 # ---------------------------------------------------------------------------------------------
-def stn_head(sd, x, new_stats, training, pre="stn_head"):
+def stn_head(sd, x, new_stats, training, pre="stn_head", taps=None):
     pools = {0: (2, 2), 2: (2, 2), 4: (2, 2), 6: (2, 2), 8: ((1, 2), (1, 2))}
     for i in range(0, 11, 2):  # conv3x3_block indices 0,2,4,6,8,10 of the Sequential
         p = f"{pre}.stn_convnet.{i}"
         x = F.conv2d(x, sd[p + ".0.weight"], sd[p + ".0.bias"], padding=1)
+        if taps is not None:
+            taps[f"stn.ypre{i // 2}"] = x.detach()
         x = F.relu(batch_norm_train(x, sd, p + ".1", new_stats, training))
+        if taps is not None:
+            taps[f"stn.yact{i // 2}"] = x.detach()
         if i in pools:
             x = F.max_pool2d(x, kernel_size=pools[i][0], stride=pools[i][1])
     x = x.reshape(x.shape[0], -1)
     f = F.linear(x, sd[pre + ".stn_fc1.0.weight"], sd[pre + ".stn_fc1.0.bias"])
+    if taps is not None:
+        taps["stn.f1pre"] = f.detach()
     f = F.relu(batch_norm_train(f, sd, pre + ".stn_fc1.1", new_stats, training))
+    if taps is not None:
+        taps["stn.f1"] = f.detach()
     c = F.linear(0.1 * f, sd[pre + ".stn_fc2.weight"], sd[pre + ".stn_fc2.bias"])  # stn_head.py:93
     return c.view(-1, 20, 2)
 
@@ -152,7 +160,7 @@ def tbsrn_forward(sd: Dict[str, Tensor], x: Tensor, training: bool = True, stn: 
                   taps: Optional[dict] = None) -> Tensor:
     """TBSRN.forward, model/tbsrn.py:214-226."""
     if stn and training:
-        ctrl = stn_head(sd, x, new_stats, training)
+        ctrl = stn_head(sd, x, new_stats, training, taps=taps)
         x = tps_transform(sd, x, ctrl)
         if taps is not None:
             taps["ctrl"], taps["x_tps"] = ctrl.detach(), x.detach()
