@@ -17,9 +17,9 @@ namespace {
 constexpr int kTileM = 128;
 constexpr int kChunkK = 64;  // bf16 elements = one 128-byte swizzle row
 constexpr int kABytes = kTileM * 128;
-constexpr int kSmemBudget = 192 * 1024;
-constexpr int kStgLd = 36;                          // floats per staged row (32 + pad, 16-byte aligned)
-constexpr int kStgBytes = 4 * 32 * kStgLd * 4;      // one 32x32 fp32 transpose tile per epilogue warp
+// two CTAs per SM: the epilogue (one warp per SM sub-partition and CTA) is latency-bound, a second resident CTA
+// overlaps its TMA/MMA phases with the first one's epilogue
+constexpr int kSmemBudget = 96 * 1024;
 
 template <int BLOCK_N>
 struct TcCfg {
@@ -27,11 +27,11 @@ struct TcCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = kSmemBudget / kStageBytes;
   static constexpr int kTmemCols = 2 * BLOCK_N;  // 2 accumulator stages
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kStgBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 template <int BLOCK_N>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(256, 2)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUtensorMap mA1,
                const __grid_constant__ CUtensorMap mA2, const __grid_constant__ CUtensorMap mA3,
                const __grid_constant__ CUtensorMap mB, const TcGemmParams p) {
@@ -142,7 +142,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
   } else if (warp >= 4) {
     const int ew = warp - 4;  // == warp % 4 : TMEM lane quarter this warp may access
     const int row = ew * 32 + lane;
-    float* stg = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + 256) + ew * 32 * kStgLd;
     int acc = 0;
     uint32_t aphase = 0;
     const int hw = p.H * p.W;
@@ -154,7 +153,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BLOCK_N;
 #pragma unroll 1
       for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-        // ---- phase 1: thread = accumulator row; bias / relu / dropout in fp32, staged to smem -----------------
         uint32_t r[32];
         tmem_ld_32x32b_x32(taddr + c0, r);
         tmem_ld_wait();
@@ -176,51 +174,98 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
         }
-        if (p.drop_thresh16 != 0) {
+        if (p.drop_thresh != 0) {
           const uint32_t c0h = (uint32_t)((mg * p.ldc + n0) >> 1);
 #pragma unroll
           for (int q = 0; q < 16; ++q) {
-            const uint32_t hsh = drop_hash32(p.drop_key, c0h + q);
-            v[2 * q] = (hsh & 0xFFFFu) >= p.drop_thresh16 ? v[2 * q] * p.drop_scale : 0.f;
-            v[2 * q + 1] = (hsh >> 16) >= p.drop_thresh16 ? v[2 * q + 1] * p.drop_scale : 0.f;
+            uint32_t r0, r1;
+            drop_rand2(p.drop_key, c0h + q, r0, r1);
+            v[2 * q] = r0 >= p.drop_thresh ? v[2 * q] * p.drop_scale : 0.f;
+            v[2 * q + 1] = r1 >= p.drop_thresh ? v[2 * q + 1] * p.drop_scale : 0.f;
           }
         }
-        __syncwarp();  // previous chunk's phase-2 reads of the staging tile are done
+        if (p.gate != nullptr) {
+          const uint4* gp = reinterpret_cast<const uint4*>(p.gate + mg * p.ldc + n0);
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<float4*>(stg + lane * kStgLd + j * 4) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        __syncwarp();
-        // ---- phase 2: 4 lanes per row, 8 rows per pass: every global access is a full 64-byte row segment ------
-        const int q8 = (lane & 3) * 8;
+          for (int q = 0; q < 4; ++q) {
+            uint4 gv = gp[q];
+            const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
 #pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          const int rr = it * 8 + (lane >> 2);
-          const long mrow = (long)m * kTileM + ew * 32 + rr;
-          float a[8];
-          {
-            const float4 x0 = *reinterpret_cast<const float4*>(stg + rr * kStgLd + q8);
-            const float4 x1 = *reinterpret_cast<const float4*>(stg + rr * kStgLd + q8 + 4);
-            a[0] = x0.x; a[1] = x0.y; a[2] = x0.z; a[3] = x0.w;
-            a[4] = x1.x; a[5] = x1.y; a[6] = x1.z; a[7] = x1.w;
+            for (int j = 0; j < 4; ++j) {
+              float2 f = unpack_bf16x2(gw[j]);
+              v[q * 8 + 2 * j] = f.x > 0.f ? v[q * 8 + 2 * j] * p.gate_scale : 0.f;
+              v[q * 8 + 2 * j + 1] = f.y > 0.f ? v[q * 8 + 2 * j + 1] * p.gate_scale : 0.f;
+            }
           }
-          const int nn = n0 + q8;
-          if (p.epi == TC_EPI_F32) {
-            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + mrow * p.ldc + nn);
-            op[0] = make_float4(a[0], a[1], a[2], a[3]);
-            op[1] = make_float4(a[4], a[5], a[6], a[7]);
-            continue;
-          }
-          if (p.epi == TC_EPI_PIXSHUF) {  // n = sub*64 + c, sub = 2*i + j -> HR pixel (2h+i, 2w+j)
-            const int sub = nn >> 6, c = nn & 63;
-            const int b = (int)(mrow / hw);
-            const int rem = (int)(mrow - (long)b * hw);
-            const int h = rem / p.W, w = rem - h * p.W;
-            const long hp = ((long)b * 2 * p.H + 2 * h + (sub >> 1)) * (2 * p.W) + 2 * w + (sub & 1);
-            // round the pre-activation to bf16 first so that backward (which re-reads it) differentiates exactly
-            // the function that forward evaluated
+        }
+        if (p.epi == TC_EPI_BF16) {
+          const long off = mg * p.ldc + n0;
+          if (p.prelu_slope != nullptr) {
+            if (p.out2 != nullptr) {
+              uint4* op2 = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out2) + off);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) a[j] = __bfloat162float(__float2bfloat16_rn(a[j]));
+              for (int q = 0; q < 4; ++q) {
+                uint4 o;
+                o.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
+                o.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
+                o.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
+                o.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
+                op2[q] = o;
+              }
+            }
+            const float slope = p.prelu_slope[0];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              // differentiate what was stored: the pre-activation is kept in bf16
+              const float xr = __bfloat162float(__float2bfloat16_rn(v[j]));
+              v[j] = xr > 0.f ? xr : slope * xr;
+            }
+          }
+          if (p.residual != nullptr) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 rv = rp[q];
+              float2 f;
+              f = unpack_bf16x2(rv.x); v[q * 8 + 0] += f.x; v[q * 8 + 1] += f.y;
+              f = unpack_bf16x2(rv.y); v[q * 8 + 2] += f.x; v[q * 8 + 3] += f.y;
+              f = unpack_bf16x2(rv.z); v[q * 8 + 4] += f.x; v[q * 8 + 5] += f.y;
+              f = unpack_bf16x2(rv.w); v[q * 8 + 6] += f.x; v[q * 8 + 7] += f.y;
+            }
+          }
+          uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + off);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 o;
+            o.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
+            o.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
+            o.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
+            o.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
+            op[q] = o;
+          }
+        } else if (p.epi == TC_EPI_F32) {
+          float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + mg * p.ldc + n0);
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            op[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+        } else {  // TC_EPI_PIXSHUF: n = sub*64 + c, sub = 2*i + j -> HR pixel (2h+i, 2w+j)
+          const int sub = n0 >> 6, c = n0 & 63;
+          const int b = (int)(mg / hw);
+          const int rem = (int)(mg - (long)b * hw);
+          const int h = rem / p.W, w = rem - h * p.W;
+          const long hp = ((long)b * 2 * p.H + 2 * h + (sub >> 1)) * (2 * p.W) + 2 * w + (sub & 1);
+          uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + hp * 64 + c);
+          uint4* op2 = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out2) + hp * 64 + c);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
             uint4 o, o2;
+            float a[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              // round the pre-activation to bf16 first so that backward (which re-reads it)
+              // differentiates exactly the function that forward evaluated
+              a[j] = __bfloat162float(__float2bfloat16_rn(v[q * 8 + j]));
+            }
             o.x = pack_bf16x2(a[0], a[1]);
             o.y = pack_bf16x2(a[2], a[3]);
             o.z = pack_bf16x2(a[4], a[5]);
@@ -229,52 +274,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
             o2.y = pack_bf16x2(mish_f(a[2]), mish_f(a[3]));
             o2.z = pack_bf16x2(mish_f(a[4]), mish_f(a[5]));
             o2.w = pack_bf16x2(mish_f(a[6]), mish_f(a[7]));
-            *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + hp * 64 + c) = o;
-            *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out2) + hp * 64 + c) = o2;
-            continue;
+            op[q] = o;
+            op2[q] = o2;
           }
-          const long off = mrow * p.ldc + nn;
-          if (p.gate != nullptr) {
-            const uint4 gv = *reinterpret_cast<const uint4*>(p.gate + off);
-            const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 f = unpack_bf16x2(gw[j]);
-              a[2 * j] = f.x > 0.f ? a[2 * j] * p.gate_scale : 0.f;
-              a[2 * j + 1] = f.y > 0.f ? a[2 * j + 1] * p.gate_scale : 0.f;
-            }
-          }
-          if (p.prelu_slope != nullptr) {
-            if (p.out2 != nullptr) {
-              uint4 o;
-              o.x = pack_bf16x2(a[0], a[1]);
-              o.y = pack_bf16x2(a[2], a[3]);
-              o.z = pack_bf16x2(a[4], a[5]);
-              o.w = pack_bf16x2(a[6], a[7]);
-              *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out2) + off) = o;
-            }
-            const float slope = p.prelu_slope[0];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              // differentiate what was stored: the pre-activation is kept in bf16
-              const float xr = __bfloat162float(__float2bfloat16_rn(a[j]));
-              a[j] = xr > 0.f ? xr : slope * xr;
-            }
-          }
-          if (p.residual != nullptr) {
-            const uint4 rv = *reinterpret_cast<const uint4*>(p.residual + off);
-            float2 f;
-            f = unpack_bf16x2(rv.x); a[0] += f.x; a[1] += f.y;
-            f = unpack_bf16x2(rv.y); a[2] += f.x; a[3] += f.y;
-            f = unpack_bf16x2(rv.z); a[4] += f.x; a[5] += f.y;
-            f = unpack_bf16x2(rv.w); a[6] += f.x; a[7] += f.y;
-          }
-          uint4 o;
-          o.x = pack_bf16x2(a[0], a[1]);
-          o.y = pack_bf16x2(a[2], a[3]);
-          o.z = pack_bf16x2(a[4], a[5]);
-          o.w = pack_bf16x2(a[6], a[7]);
-          *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + off) = o;
         }
       }
       tc_fence_before();
@@ -354,7 +356,7 @@ int launch_impl(const CUtensorMap* am, const CUtensorMap& bm, const TcGemmParams
     attr_set = true;
   }
   const int total = p.m_tiles * p.n_blocks;
-  const int grid = total < num_sms() ? total : num_sms();
+  const int grid = total < 2 * num_sms() ? total : 2 * num_sms();
   tc_gemm_kernel<BLOCK_N><<<grid, 256, Cfg::kSmemBytes, stream>>>(am[0], am[1], am[2], am[3], bm, p);
   FOCR_LAUNCH_CHECK();
   return FOCR_OK;
