@@ -80,42 +80,6 @@ __device__ __forceinline__ void mma_p_m(float (&acc)[4][4], const uint32_t (&pa)
     }
   }
 }
-// 32-wide variants (used by pass B to halve the live accumulator tile and fit more warps per SM)
-__device__ __forceinline__ void mma_a_mt32(float (&acc)[4][4], const uint32_t (&a)[2][4], uint32_t sbase, int row0,
-                                           int lane) {
-#pragma unroll
-  for (int n = 0; n < 4; ++n) {
-    uint32_t r[4];
-    ldmatrix_x4(r, sbase + sw_off(row0 + n * 8 + (lane & 7), lane >> 3));
-    const uint32_t b0[2] = {r[0], r[1]}, b1[2] = {r[2], r[3]};
-    mma_bf16_16816(acc[n], a[0], b0);
-    mma_bf16_16816(acc[n], a[1], b1);
-  }
-}
-__device__ __forceinline__ void mma_p_m32(float (&acc)[4][4], const uint32_t (&pa)[2][4], uint32_t sbase, int row0,
-                                          int lane) {
-#pragma unroll
-  for (int kk = 0; kk < 2; ++kk) {
-    const int row = row0 + kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
-#pragma unroll
-    for (int nd = 0; nd < 4; nd += 2) {
-      uint32_t r[4];
-      ldmatrix_x4_trans(r, sbase + sw_off(row, nd + (lane >> 4)));
-      const uint32_t b0[2] = {r[0], r[1]}, b1[2] = {r[2], r[3]};
-      mma_bf16_16816(acc[nd], pa[kk], b0);
-      mma_bf16_16816(acc[nd + 1], pa[kk], b1);
-    }
-  }
-}
-__device__ __forceinline__ void pack_frags32(uint32_t (&pa)[2][4], const float (&s)[4][4]) {
-#pragma unroll
-  for (int kk = 0; kk < 2; ++kk) {
-    pa[kk][0] = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
-    pa[kk][1] = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
-    pa[kk][2] = pack_bf16x2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
-    pa[kk][3] = pack_bf16x2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
-  }
-}
 __device__ __forceinline__ void pack_frags(uint32_t (&pa)[4][4], const float (&s)[8][4]) {
 #pragma unroll
   for (int kk = 0; kk < 4; ++kk) {
@@ -140,7 +104,7 @@ __device__ __forceinline__ float quad_max(float v) {
 template <bool DROP, int NW>
 __global__ void __launch_bounds__(NW * 32, 1)
 attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __restrict__ lse2, uint32_t key,
-                uint32_t thresh, float inv_keep) {
+                uint32_t thresh16, float inv_keep) {
   extern __shared__ __align__(128) uint8_t sm[];
   const uint32_t sK = smem_u32(sm), sV = sK + kTileBytes;
   const int bh = blockIdx.x, b = bh >> 2, h = bh & 3;
@@ -205,14 +169,11 @@ attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __r
         const uint32_t cb = (uint32_t)(kt * 32 + c);
 #pragma unroll
         for (int n = 0; n < 8; ++n) {
-          uint32_t r0, r1, r2, r3;
-          drop_rand2(key, rb0 + cb + n * 4, r0, r1);
-          drop_rand2(key, rb1 + cb + n * 4, r2, r3);
-          // the 1/(1-p) scale is applied once to the output row (after the loop), not per element
-          s[n][0] = r0 >= thresh ? s[n][0] : 0.f;
-          s[n][1] = r1 >= thresh ? s[n][1] : 0.f;
-          s[n][2] = r2 >= thresh ? s[n][2] : 0.f;
-          s[n][3] = r3 >= thresh ? s[n][3] : 0.f;
+          const uint32_t h0 = drop_hash32(key, rb0 + cb + n * 4), h1 = drop_hash32(key, rb1 + cb + n * 4);
+          s[n][0] = (h0 & 0xFFFFu) >= thresh16 ? s[n][0] * inv_keep : 0.f;
+          s[n][1] = (h0 >> 16) >= thresh16 ? s[n][1] * inv_keep : 0.f;
+          s[n][2] = (h1 & 0xFFFFu) >= thresh16 ? s[n][2] * inv_keep : 0.f;
+          s[n][3] = (h1 >> 16) >= thresh16 ? s[n][3] * inv_keep : 0.f;
         }
       }
       uint32_t pa[4][4];
@@ -221,7 +182,7 @@ attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __r
     }
     l0 = quad_sum(l0);
     l1 = quad_sum(l1);
-    const float i0 = inv_keep / l0, i1 = inv_keep / l1;
+    const float i0 = 1.f / l0, i1 = 1.f / l1;
     bf16* orow0 = out + ((long)b * kS + q0 + g) * kLdO + h * 32;
     bf16* orow1 = orow0 + 8 * kLdO;
 #pragma unroll
@@ -242,7 +203,7 @@ template <bool DROP, int NW>
 __global__ void __launch_bounds__(NW * 32, 1)
 attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o_in, const bf16* __restrict__ d_o,
                    const float* __restrict__ lse2, float* __restrict__ dsum, bf16* __restrict__ dqkv, uint32_t key,
-                   uint32_t thresh, float inv_keep) {
+                   uint32_t thresh16, float inv_keep) {
   extern __shared__ __align__(128) uint8_t sm[];
   const uint32_t sK = smem_u32(sm), sV = sK + kTileBytes;
   const int bh = blockIdx.x, b = bh >> 2, h = bh & 3;
@@ -302,13 +263,11 @@ attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o_in, 
         const float p2 = ex2(fmaf(s[n][2], kScaleLog2, -L1)), p3 = ex2(fmaf(s[n][3], kScaleLog2, -L1));
         float e0 = dp[n][0], e1 = dp[n][1], e2 = dp[n][2], e3 = dp[n][3];
         if (DROP) {
-          uint32_t r0, r1, r2, r3;
-          drop_rand2(key, rb0 + cb + n * 4, r0, r1);
-          drop_rand2(key, rb1 + cb + n * 4, r2, r3);
-          e0 = r0 >= thresh ? e0 * inv_keep : 0.f;
-          e1 = r1 >= thresh ? e1 * inv_keep : 0.f;
-          e2 = r2 >= thresh ? e2 * inv_keep : 0.f;
-          e3 = r3 >= thresh ? e3 * inv_keep : 0.f;
+          const uint32_t h0 = drop_hash32(key, rb0 + cb + n * 4), h1 = drop_hash32(key, rb1 + cb + n * 4);
+          e0 = (h0 & 0xFFFFu) >= thresh16 ? e0 * inv_keep : 0.f;
+          e1 = (h0 >> 16) >= thresh16 ? e1 * inv_keep : 0.f;
+          e2 = (h1 & 0xFFFFu) >= thresh16 ? e2 * inv_keep : 0.f;
+          e3 = (h1 >> 16) >= thresh16 ? e3 * inv_keep : 0.f;
         }
         s[n][0] = p0 * (e0 - D0);
         s[n][1] = p1 * (e1 - D0);
@@ -330,12 +289,11 @@ attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o_in, 
 }
 
 // ------------------------------------------------------------------------------------------
-// backward pass B: dK, dV (warp owns 16 key rows; everything is the transpose of pass A).  The query axis is
-// walked in tiles of 32 so that the live S^T / dP^T tiles stay small enough for NW warps per SM.
-template <bool DROP, int NW>
-__global__ void __launch_bounds__(NW * 32, 1)
+// backward pass B: dK, dV (warp owns 16 key rows; everything is the transpose of pass A)
+template <bool DROP>
+__global__ void __launch_bounds__(256, 1)
 attn_bwd_dkv_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ d_o, const float* __restrict__ lse2,
-                    const float* __restrict__ dsum, bf16* __restrict__ dqkv, uint32_t key, uint32_t thresh,
+                    const float* __restrict__ dsum, bf16* __restrict__ dqkv, uint32_t key, uint32_t thresh16,
                     float inv_keep) {
   extern __shared__ __align__(128) uint8_t sm[];
   const uint32_t sQ = smem_u32(sm), sdO = sQ + kTileBytes;
@@ -354,8 +312,8 @@ attn_bwd_dkv_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ d_o, 
   cp_async_wait<0>();
   __syncthreads();
 
-  for (int u = warp; u < kS / 16; u += NW) {
-    const int kv0 = u * 16;
+  for (int kb = 0; kb < kS / 128; ++kb) {
+    const int kv0 = kb * 128 + warp * 16;
     uint32_t ka[2][4], va[2][4];
     load_a_frags(ka, base + 128 + (long)(kv0 + g) * kLdQkv, kLdQkv, c);
     load_a_frags(va, base + 256 + (long)(kv0 + g) * kLdQkv, kLdQkv, c);
@@ -364,23 +322,23 @@ attn_bwd_dkv_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ d_o, 
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) dk[i][j] = dv[i][j] = 0.f;
-    // element (kv, q): counter = (bh*1024 + q)*512 + kv/2, uniform r0 / r1 for kv even / odd
+    // element (kv, q): counter = (bh*1024 + q)*512 + kv/2, 16-bit lane = kv & 1
     const uint32_t kvh0 = (uint32_t)((kv0 + g) >> 1), kvh1 = (uint32_t)((kv0 + g + 8) >> 1);
-    const bool odd = (kv0 + g) & 1;  // same parity for row g and g+8
+    const int sh = ((kv0 + g) & 1) * 16;  // same parity for row g and g+8
 
 #pragma unroll 1
-    for (int qt = 0; qt < kS / 32; ++qt) {
-      float st[4][4], dpt[4][4];
+    for (int qt = 0; qt < kS / 64; ++qt) {
+      float st[8][4], dpt[8][4];
 #pragma unroll
-      for (int n = 0; n < 4; ++n) {
+      for (int n = 0; n < 8; ++n) {
         st[n][0] = st[n][1] = st[n][2] = st[n][3] = 0.f;
         dpt[n][0] = dpt[n][1] = dpt[n][2] = dpt[n][3] = 0.f;
       }
-      mma_a_mt32(st, ka, sQ, qt * 32, lane);
-      mma_a_mt32(dpt, va, sdO, qt * 32, lane);
+      mma_a_mt(st, ka, sQ, qt * 64, lane);
+      mma_a_mt(dpt, va, sdO, qt * 64, lane);
 #pragma unroll
-      for (int n = 0; n < 4; ++n) {
-        const int q = qt * 32 + n * 8 + 2 * c;
+      for (int n = 0; n < 8; ++n) {
+        const int q = qt * 64 + n * 8 + 2 * c;
         const float2 Lq = *reinterpret_cast<const float2*>(sL + q);
         const float2 Dq = *reinterpret_cast<const float2*>(sD + q);
         const float p0 = ex2(fmaf(st[n][0], kScaleLog2, -Lq.x)), p1 = ex2(fmaf(st[n][1], kScaleLog2, -Lq.y));
@@ -389,15 +347,10 @@ attn_bwd_dkv_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ d_o, 
         float d0 = p0, d1 = p1, d2 = p2, d3 = p3;
         if (DROP) {
           const uint32_t qb0 = (uint32_t)(bh * kS + q) * 512u, qb1 = qb0 + 512u;
-          uint32_t ra, rb;
-          drop_rand2(key, qb0 + kvh0, ra, rb);
-          const bool k0 = (odd ? rb : ra) >= thresh;
-          drop_rand2(key, qb1 + kvh0, ra, rb);
-          const bool k1 = (odd ? rb : ra) >= thresh;
-          drop_rand2(key, qb0 + kvh1, ra, rb);
-          const bool k2 = (odd ? rb : ra) >= thresh;
-          drop_rand2(key, qb1 + kvh1, ra, rb);
-          const bool k3 = (odd ? rb : ra) >= thresh;
+          const bool k0 = ((drop_hash32(key, qb0 + kvh0) >> sh) & 0xFFFFu) >= thresh16;
+          const bool k1 = ((drop_hash32(key, qb1 + kvh0) >> sh) & 0xFFFFu) >= thresh16;
+          const bool k2 = ((drop_hash32(key, qb0 + kvh1) >> sh) & 0xFFFFu) >= thresh16;
+          const bool k3 = ((drop_hash32(key, qb1 + kvh1) >> sh) & 0xFFFFu) >= thresh16;
           e0 = k0 ? e0 * inv_keep : 0.f; d0 = k0 ? p0 * inv_keep : 0.f;
           e1 = k1 ? e1 * inv_keep : 0.f; d1 = k1 ? p1 * inv_keep : 0.f;
           e2 = k2 ? e2 * inv_keep : 0.f; d2 = k2 ? p2 * inv_keep : 0.f;
@@ -412,11 +365,11 @@ attn_bwd_dkv_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ d_o, 
         dpt[n][2] = d2;
         dpt[n][3] = d3;
       }
-      uint32_t pa[2][4];
-      pack_frags32(pa, dpt);
-      mma_p_m32(dv, pa, sdO, qt * 32, lane);
-      pack_frags32(pa, st);
-      mma_p_m32(dk, pa, sQ, qt * 32, lane);
+      uint32_t pa[4][4];
+      pack_frags(pa, dpt);
+      mma_p_m(dv, pa, sdO, qt * 64, lane);
+      pack_frags(pa, st);
+      mma_p_m(dk, pa, sQ, qt * 64, lane);
     }
     bf16* r0 = dqkv + ((long)b * kS + kv0 + g) * kLdQkv + h * 32;
     bf16* r1 = r0 + 8 * kLdQkv;
@@ -433,8 +386,7 @@ attn_bwd_dkv_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ d_o, 
 // warps per CTA (one CTA per SM: 128 KB of smem).  More resident warps hide the mma.sync / MUFU / ldmatrix
 // latencies of this issue-bound kernel; the register file caps them (65536 / (32 * regs)).
 constexpr int kFwdWarps = 16;  // <= 128 registers
-constexpr int kDkvWarps = 16;
-constexpr int kDqWarps = 16;   // <= 157 registers; 64 units over 13 warps = 5 passes (98 % filled)
+constexpr int kDqWarps = 8;   // measured: 8 warps (172 regs, no spills) beats 13/16 warps at the 128-register cap
 
 template <typename K>
 int set_smem(K kernel, int bytes) {
@@ -444,12 +396,12 @@ int set_smem(K kernel, int bytes) {
 
 }  // namespace
 
-// thresh = round(p_drop * 2^32); thresh == 0 disables dropout (eval / parity runs)
-int attn_forward(const bf16* qkv, bf16* out, float* lse2, int B, uint32_t key, uint32_t thresh, cudaStream_t s) {
+// p_drop = thresh16 / 65536; thresh16 == 0 disables dropout (eval / parity runs)
+int attn_forward(const bf16* qkv, bf16* out, float* lse2, int B, uint32_t key, uint32_t thresh16, cudaStream_t s) {
   ProfScope _ps("attn_fwd", s);
   FOCR_REQUIRE(B >= 1 && B <= 1024, "attention: B=%d out of range", B);
   const int smem = 2 * kTileBytes;
-  const float inv_keep = drop_keep_scale(thresh);
+  const float inv_keep = 65536.f / (65536.f - (float)thresh16);
   static bool init = false;
   if (!init) {
     int rc = set_smem(attn_fwd_kernel<true, kFwdWarps>, smem);
@@ -458,8 +410,8 @@ int attn_forward(const bf16* qkv, bf16* out, float* lse2, int B, uint32_t key, u
     if (rc) return rc;
     init = true;
   }
-  if (thresh)
-    attn_fwd_kernel<true, kFwdWarps><<<B * 4, kFwdWarps * 32, smem, s>>>(qkv, out, lse2, key, thresh, inv_keep);
+  if (thresh16)
+    attn_fwd_kernel<true, kFwdWarps><<<B * 4, kFwdWarps * 32, smem, s>>>(qkv, out, lse2, key, thresh16, inv_keep);
   else
     attn_fwd_kernel<false, kFwdWarps><<<B * 4, kFwdWarps * 32, smem, s>>>(qkv, out, lse2, key, 0, 1.f);
   FOCR_LAUNCH_CHECK();
@@ -467,27 +419,27 @@ int attn_forward(const bf16* qkv, bf16* out, float* lse2, int B, uint32_t key, u
 }
 
 int attn_backward(const bf16* qkv, const bf16* o, const bf16* d_o, const float* lse2, float* dsum, bf16* dqkv, int B,
-                  uint32_t key, uint32_t thresh, cudaStream_t s) {
+                  uint32_t key, uint32_t thresh16, cudaStream_t s) {
   FOCR_REQUIRE(B >= 1 && B <= 1024, "attention: B=%d out of range", B);
   const int smem_a = 2 * kTileBytes, smem_b = 2 * kTileBytes + 2 * kS * 4;
-  const float inv_keep = drop_keep_scale(thresh);
+  const float inv_keep = 65536.f / (65536.f - (float)thresh16);
   static bool init = false;
   if (!init) {
     int rc = set_smem(attn_bwd_dq_kernel<true, kDqWarps>, smem_a);
     if (rc) return rc;
     rc = set_smem(attn_bwd_dq_kernel<false, kDqWarps>, smem_a);
     if (rc) return rc;
-    rc = set_smem(attn_bwd_dkv_kernel<true, kDkvWarps>, smem_b);
+    rc = set_smem(attn_bwd_dkv_kernel<true>, smem_b);
     if (rc) return rc;
-    rc = set_smem(attn_bwd_dkv_kernel<false, kDkvWarps>, smem_b);
+    rc = set_smem(attn_bwd_dkv_kernel<false>, smem_b);
     if (rc) return rc;
     init = true;
   }
   {
     ProfScope ps("attn_bwd_dq", s);
-    if (thresh)
+    if (thresh16)
       attn_bwd_dq_kernel<true, kDqWarps><<<B * 4, kDqWarps * 32, smem_a, s>>>(qkv, o, d_o, lse2, dsum, dqkv, key,
-                                                                             thresh, inv_keep);
+                                                                             thresh16, inv_keep);
     else
       attn_bwd_dq_kernel<false, kDqWarps><<<B * 4, kDqWarps * 32, smem_a, s>>>(qkv, o, d_o, lse2, dsum, dqkv, key, 0,
                                                                               1.f);
@@ -495,12 +447,10 @@ int attn_backward(const bf16* qkv, const bf16* o, const bf16* d_o, const float* 
   }
   {
     ProfScope ps("attn_bwd_dkv", s);
-    if (thresh)
-      attn_bwd_dkv_kernel<true, kDkvWarps><<<B * 4, kDkvWarps * 32, smem_b, s>>>(qkv, d_o, lse2, dsum, dqkv, key,
-                                                                               thresh, inv_keep);
+    if (thresh16)
+      attn_bwd_dkv_kernel<true><<<B * 4, 256, smem_b, s>>>(qkv, d_o, lse2, dsum, dqkv, key, thresh16, inv_keep);
     else
-      attn_bwd_dkv_kernel<false, kDkvWarps><<<B * 4, kDkvWarps * 32, smem_b, s>>>(qkv, d_o, lse2, dsum, dqkv, key, 0,
-                                                                                1.f);
+      attn_bwd_dkv_kernel<false><<<B * 4, 256, smem_b, s>>>(qkv, d_o, lse2, dsum, dqkv, key, 0, 1.f);
     FOCR_LAUNCH_CHECK();
   }
   return FOCR_OK;

@@ -99,29 +99,22 @@ __device__ __forceinline__ float mish_grad_f(float x) {
 
 
 // ----------------------------------------------------------------------------------
-// counter-based RNG for dropout.  Attention is ALU-pipe bound, so the generator is built from
-// 32x32->64 multiplies (IMAD.WIDE, FMA pipe) and two xors instead of shift/xor chains:
-//   m = (ctr ^ key) * M0;  h = hi(m) ^ lo(m);  m = h * M1;  r0 = hi(m) ^ lo(m);  r1 = r0 * M2 + A
-// r0 / r1 are the 32-bit uniforms of elements 2*ctr and 2*ctr+1; an element is DROPPED when r < thresh32
-// (thresh32 = round(p * 2^32)).  key = seed ^ f(stream).  numpy twin: oracle/dropout_rng.py.
+// counter-based RNG for dropout: one 32-bit hash (murmur3 finaliser over a Weyl-premixed counter)
+// yields two 16-bit lanes; element 2*ctr + j is DROPPED when lane j < thresh16
+// (thresh16 = round(p * 65536)).  key = seed ^ (stream * golden).  numpy twin: oracle/dropout_rng.py.
 // ----------------------------------------------------------------------------------
-__host__ __device__ __forceinline__ void drop_rand2(uint32_t key, uint32_t ctr, uint32_t& r0, uint32_t& r1) {
-  uint64_t m = (uint64_t)(ctr ^ key) * (uint64_t)0xD2511F53u;
-  const uint32_t h = (uint32_t)(m >> 32) ^ (uint32_t)m;
-  m = (uint64_t)h * (uint64_t)0xCD9E8D57u;
-  r0 = (uint32_t)(m >> 32) ^ (uint32_t)m;
-  r1 = r0 * 0x85EBCA6Bu + 0xC2B2AE35u;
+__host__ __device__ __forceinline__ uint32_t drop_hash32(uint32_t key, uint32_t ctr) {
+  uint32_t h = ctr * 0x9E3779B1u + key;
+  h ^= h >> 16;
+  h *= 0x85EBCA6Bu;
+  h ^= h >> 13;
+  h *= 0xC2B2AE35u;
+  h ^= h >> 16;
+  return h;
 }
 __host__ __device__ __forceinline__ uint32_t drop_key(uint32_t seed, uint32_t stream) {
   return seed ^ (stream * 0x9E3779B9u + 0x7F4A7C15u);
 }
-static inline uint32_t drop_thresh32(float p) {
-  if (p <= 0.f) return 0u;
-  double t = (double)p * 4294967296.0 + 0.5;
-  if (t > 4294967295.0) t = 4294967295.0;
-  return (uint32_t)t;
-}
-static inline float drop_keep_scale(uint32_t thresh32) { return (float)(4294967296.0 / (4294967296.0 - (double)thresh32)); }
 
 // ----------------------------------------------------------------------------------
 // mbarrier

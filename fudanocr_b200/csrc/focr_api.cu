@@ -224,12 +224,12 @@ int focr_layernorm_std_bwd(const void* dy, const void* x, const float* a, void* 
 // ---------------------------------------------------------------------------------------------
 int focr_mha_flash_fwd(const void* qkv, void* out, float* lse2, int B, float p_drop, unsigned seed, unsigned stream_id,
                        void* stream) {
-  const uint32_t th = drop_thresh32(p_drop);
+  const uint32_t th = p_drop > 0.f ? (uint32_t)(p_drop * 65536.0 + 0.5) : 0;
   return attn_forward((const bf16*)qkv, (bf16*)out, lse2, B, drop_key(seed, stream_id), th, (cudaStream_t)stream);
 }
 int focr_mha_flash_bwd(const void* qkv, const void* out, const void* d_out, const float* lse2, float* dsum_ws,
                        void* dqkv, int B, float p_drop, unsigned seed, unsigned stream_id, void* stream) {
-  const uint32_t th = drop_thresh32(p_drop);
+  const uint32_t th = p_drop > 0.f ? (uint32_t)(p_drop * 65536.0 + 0.5) : 0;
   return attn_backward((const bf16*)qkv, (const bf16*)out, (const bf16*)d_out, lse2, dsum_ws, (bf16*)dqkv, B,
                        drop_key(seed, stream_id), th, (cudaStream_t)stream);
 }

@@ -235,7 +235,12 @@ template <typename T>
 T* P(void* const* prm, int i) {
   return reinterpret_cast<T*>(prm[i]);
 }
-uint32_t thresh_of(float p) { return drop_thresh32(p); }
+uint32_t thresh_of(float p) {
+  if (p <= 0.f) return 0;
+  long t = (long)(p * 65536.0 + 0.5);
+  if (t > 65535) t = 65535;
+  return (uint32_t)t;
+}
 
 int prep_weights(const Slots& sl, void* const* prm, Ws& w, bool stn, cudaStream_t s) {
   TRY(pe_table(w.pe, s));
@@ -395,7 +400,7 @@ int forward(const Slots& sl, void* const* prm, const float* x_lr, float* sr_out,
   const long T = w.T;
   const bool use_stn = stn && training;  // tbsrn.py:215
   const uint32_t th = training ? thresh_of(p_drop) : 0;
-  const float keep_scale = drop_keep_scale(th);
+  const float keep_scale = 65536.f / (65536.f - (float)th);
   TRY(prep_weights(sl, prm, w, use_stn, s));
   const float* x_in = x_lr;
   if (use_stn) {
@@ -444,7 +449,7 @@ int forward(const Slots& sl, void* const* prm, const float* x_lr, float* sr_out,
     p.bias = P<float>(prm, sl.srb(i, S_W1B));
     p.out = a.hd;
     p.relu = 1;
-    p.drop_thresh = th;
+    p.drop_thresh16 = th;
     p.drop_scale = keep_scale;
     p.drop_key = drop_key(seed, 2 * i + 1);
     TRY(tok_gemm(a.y1, 128, T, q.w1, 128, p, s));
@@ -506,7 +511,7 @@ int backward(const Slots& sl, void* const* prm, void* const* grd, const float* x
   const int B = w.B, n = sl.srb_nums;
   const long T = w.T, Thr = w.Thr;
   const uint32_t th = thresh_of(p_drop);
-  const float keep_scale = drop_keep_scale(th);
+  const float keep_scale = 65536.f / (65536.f - (float)th);
   // tanh, final 9x9 conv
   TRY(tanh_backward(w.sr, d_sr, w.d_o, (long)B * 3 * 4096, s));
   if (grd[sl.fin_b]) TRY(nchw3_sum(w.d_o, B, 4096, P<float>(grd, sl.fin_b), w.partial, s));

@@ -174,14 +174,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
         }
-        if (p.drop_thresh != 0) {
+        if (p.drop_thresh16 != 0) {
           const uint32_t c0h = (uint32_t)((mg * p.ldc + n0) >> 1);
 #pragma unroll
           for (int q = 0; q < 16; ++q) {
-            uint32_t r0, r1;
-            drop_rand2(p.drop_key, c0h + q, r0, r1);
-            v[2 * q] = r0 >= p.drop_thresh ? v[2 * q] * p.drop_scale : 0.f;
-            v[2 * q + 1] = r1 >= p.drop_thresh ? v[2 * q + 1] * p.drop_scale : 0.f;
+            const uint32_t hsh = drop_hash32(p.drop_key, c0h + q);
+            v[2 * q] = (hsh & 0xFFFFu) >= p.drop_thresh16 ? v[2 * q] * p.drop_scale : 0.f;
+            v[2 * q + 1] = (hsh >> 16) >= p.drop_thresh16 ? v[2 * q + 1] * p.drop_scale : 0.f;
           }
         }
         if (p.gate != nullptr) {

@@ -33,7 +33,7 @@ struct TcGemmParams {
   void* out2;
   const bf16* residual;  // nullptr or [M, ldc]
   // forward dropout applied after relu (PositionwiseFeedForward, tbsrn.py:162-163); 0 = off
-  uint32_t drop_thresh;    // 32-bit threshold, 0 = off
+  uint32_t drop_thresh16;
   float drop_scale;      // 1/(1-p)
   uint32_t drop_key;     // drop_key(seed, stream)
   // backward gate: v = gate[m][n] > 0 ? v * gate_scale : 0  (relu'(.) * dropout mask, read from the

@@ -40,7 +40,9 @@ def synth_state_dict(spec: Dict[str, list], seed: int = 1234, computed: Dict[str
         if key.endswith("stn_fc2.bias"):  # identity control points (stn_head.py:69-86) + small noise
             v = identity_ctrl_points().reshape(-1) + 0.02 * z
         elif key.endswith("stn_fc2.weight"):
-            v = 0.02 * z
+            # the reference initialises this weight to ZERO (stn_head.py:85: identity warp) and Adam moves it by
+            # ~1e-4 per step, so a lightly trained STN has |w| ~ 1e-3; non-zero so the gradient path is exercised
+            v = 0.002 * z
         elif leaf == "running_var":
             v = (0.5 + rs.random_sample(n)).astype(np.float32).reshape(shape)
         elif leaf == "running_mean":
