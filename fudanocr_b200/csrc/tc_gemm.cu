@@ -17,33 +17,47 @@ namespace {
 constexpr int kTileM = 128;
 constexpr int kChunkK = 64;  // bf16 elements = one 128-byte swizzle row
 constexpr int kABytes = kTileM * 128;
-// two CTAs per SM: the epilogue (one warp per SM sub-partition and CTA) is latency-bound, a second resident CTA
-// overlaps its TMA/MMA phases with the first one's epilogue
-constexpr int kSmemBudget = 96 * 1024;
+constexpr int kCdBlk = kTileM * 128;  // one 128-row x 64-column bf16 block, 128-byte swizzled (TMA box)
 
+// One persistent CTA per SM.  Shared memory: K-block ring (A+B per stage), a double-buffered output tile
+// that the epilogue fills and a TMA store drains, and one auxiliary input tile (residual or gate) that the
+// producer prefetches with TMA, so the epilogue warps never touch global memory.
 template <int BLOCK_N>
 struct TcCfg {
   static constexpr int kBBytes = BLOCK_N * 128;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = kSmemBudget / kStageBytes;
+  static constexpr int kStages = BLOCK_N == 128 ? 3 : 6;
+  static constexpr int kCdBytes = (BLOCK_N / 64) * kCdBlk;  // per buffer
+  static constexpr int kOffCd = kStages * kStageBytes;
+  static constexpr int kOffAux = kOffCd + 2 * kCdBytes;
+  static constexpr int kOffBar = kOffAux + 2 * kCdBytes;  // aux tile double-buffered like the output tile
   static constexpr int kTmemCols = 2 * BLOCK_N;  // 2 accumulator stages
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kOffBar + 512 /*barriers*/ + 1024 /*align*/;
 };
 
+// byte offset of (row, 16-byte chunk) inside a 128-byte-swizzled 128x64 bf16 block
+__device__ __forceinline__ uint32_t cd_off(int row, int chunk) { return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4)); }
+
 template <int BLOCK_N>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUtensorMap mA1,
                const __grid_constant__ CUtensorMap mA2, const __grid_constant__ CUtensorMap mA3,
-               const __grid_constant__ CUtensorMap mB, const TcGemmParams p) {
+               const __grid_constant__ CUtensorMap mB, const __grid_constant__ CUtensorMap mC,
+               const __grid_constant__ CUtensorMap mR, const TcGemmParams p) {
   using Cfg = TcCfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::kOffBar);
   uint64_t* empty = full + Cfg::kStages;
   uint64_t* tfull = empty + Cfg::kStages;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* afull = tempty + 2;   // [2] auxiliary (residual / gate) tile landed
+  uint64_t* aempty = afull + 2;   // [2] ... and has been consumed by the 4 epilogue warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty + 2);
+  uint8_t* cd_base = smem + Cfg::kOffCd;
+  uint8_t* aux_base = smem + Cfg::kOffAux;
+  const bool use_aux = p.tma_out && (p.residual != nullptr || p.gate != nullptr);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -65,6 +79,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
       mbar_init(&tfull[a], 1);
       mbar_init(&tempty[a], 4);
     }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&afull[a], 1);
+      mbar_init(&aempty[a], 4);
+    }
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -81,12 +99,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
       const CUtensorMap* amaps[4] = {&mA0, &mA1, &mA2, &mA3};
       int stage = 0;
       uint32_t phase = 0;
+      int ait = 0;
       const int hw = p.H * p.W;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int m = tile / p.n_blocks, nb = tile % p.n_blocks;
         const int p0 = m * kTileM;
         const int b = p0 / hw;
         const int h0 = (p0 - b * hw) / p.W;
+        if (use_aux) {
+          const int ab = ait & 1;
+          mbar_wait(&aempty[ab], ((ait >> 1) & 1) ^ 1);
+          mbar_arrive_expect_tx(&afull[ab], Cfg::kCdBytes);
+          for (int blk = 0; blk < BLOCK_N / 64; ++blk)
+            tma_load_2d(aux_base + ab * Cfg::kCdBytes + blk * kCdBlk, &mR, &afull[ab], nb * BLOCK_N + blk * 64, p0);
+          ++ait;
+        }
         for (int tap = 0; tap < taps; ++tap) {
           const int dy = tap / p.kw - pad_h, dx = tap % p.kw - pad_w;
           for (int ch = 0; ch < p.chunks; ++ch) {
@@ -144,10 +171,101 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
     const int row = ew * 32 + lane;
     int acc = 0;
     uint32_t aphase = 0;
+    int it = 0;
     const int hw = p.H * p.W;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m = tile / p.n_blocks, nb = tile % p.n_blocks;
       const long mg = (long)m * kTileM + row;
+      if (p.tma_out) {
+        // ---- TMEM -> registers -> swizzled smem tile -> TMA store.  No global access from these warps. ------------
+        uint8_t* cd = cd_base + (it & 1) * Cfg::kCdBytes;
+        if (ew == 0 && lane == 0) bulk_wait_read<1>();  // the store issued two tiles ago has finished reading `cd`
+        named_bar_sync(1, 128);
+        mbar_wait(&tfull[acc], aphase);
+        tc_fence_after();
+        const uint8_t* aux = aux_base + (it & 1) * Cfg::kCdBytes;
+        if (use_aux) mbar_wait(&afull[it & 1], (it >> 1) & 1);
+        const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BLOCK_N;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(taddr + c0, r);
+          tmem_ld_wait();
+          if (c0 == BLOCK_N - 32) {  // accumulator fully drained: hand the TMEM stage back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+          }
+          const int n0 = nb * BLOCK_N + c0;
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 bb = *reinterpret_cast<const float4*>(p.bias + n0 + j);
+              v[j] += bb.x;
+              v[j + 1] += bb.y;
+              v[j + 2] += bb.z;
+              v[j + 3] += bb.w;
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          if (p.drop_thresh16 != 0) {
+            const uint32_t c0h = (uint32_t)((mg * p.ldc + n0) >> 1);
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+              const uint32_t hsh = drop_hash32(p.drop_key, c0h + q);
+              v[2 * q] = (hsh & 0xFFFFu) >= p.drop_thresh16 ? v[2 * q] * p.drop_scale : 0.f;
+              v[2 * q + 1] = (hsh >> 16) >= p.drop_thresh16 ? v[2 * q + 1] * p.drop_scale : 0.f;
+            }
+          }
+          const int blk = c0 >> 6, kc = (c0 & 63) >> 3;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t so = (uint32_t)(blk * kCdBlk) + cd_off(row, kc + q);
+            if (use_aux) {
+              const uint4 av = *reinterpret_cast<const uint4*>(aux + so);
+              const uint32_t aw[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 f = unpack_bf16x2(aw[j]);
+                if (p.gate != nullptr) {
+                  v[q * 8 + 2 * j] = f.x > 0.f ? v[q * 8 + 2 * j] * p.gate_scale : 0.f;
+                  v[q * 8 + 2 * j + 1] = f.y > 0.f ? v[q * 8 + 2 * j + 1] * p.gate_scale : 0.f;
+                } else {
+                  v[q * 8 + 2 * j] += f.x;
+                  v[q * 8 + 2 * j + 1] += f.y;
+                }
+              }
+            }
+            uint4 o;
+            o.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
+            o.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
+            o.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
+            o.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
+            *reinterpret_cast<uint4*>(cd + so) = o;
+          }
+        }
+        if (use_aux) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&aempty[it & 1]);
+        }
+        fence_proxy_async();  // make the generic-proxy smem writes visible to the TMA (async proxy)
+        named_bar_sync(1, 128);
+        if (ew == 0 && lane == 0) {
+          for (int blk = 0; blk < BLOCK_N / 64; ++blk)
+            tma_store_2d(&mC, cd + blk * kCdBlk, nb * BLOCK_N + blk * 64, m * kTileM);
+          bulk_commit();
+        }
+        ++it;
+        acc ^= 1;
+        if (acc == 0) aphase ^= 1;
+        continue;
+      }
       mbar_wait(&tfull[acc], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BLOCK_N;
@@ -284,6 +402,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
       acc ^= 1;
       if (acc == 0) aphase ^= 1;
     }
+    if (p.tma_out && ew == 0 && lane == 0) bulk_wait<0>();  // all output tiles are in global memory
   }
 
   tc_fence_before();
@@ -346,7 +465,8 @@ int num_sms() {
 }
 
 template <int BLOCK_N>
-int launch_impl(const CUtensorMap* am, const CUtensorMap& bm, const TcGemmParams& p, cudaStream_t stream) {
+int launch_impl(const CUtensorMap* am, const CUtensorMap& bm, const CUtensorMap& cm, const CUtensorMap& rm,
+                const TcGemmParams& p, cudaStream_t stream) {
   using Cfg = TcCfg<BLOCK_N>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -355,8 +475,8 @@ int launch_impl(const CUtensorMap* am, const CUtensorMap& bm, const TcGemmParams
     attr_set = true;
   }
   const int total = p.m_tiles * p.n_blocks;
-  const int grid = total < 2 * num_sms() ? total : 2 * num_sms();
-  tc_gemm_kernel<BLOCK_N><<<grid, 256, Cfg::kSmemBytes, stream>>>(am[0], am[1], am[2], am[3], bm, p);
+  const int grid = total < num_sms() ? total : num_sms();
+  tc_gemm_kernel<BLOCK_N><<<grid, 256, Cfg::kSmemBytes, stream>>>(am[0], am[1], am[2], am[3], bm, cm, rm, p);
   FOCR_LAUNCH_CHECK();
   return FOCR_OK;
 }
@@ -406,8 +526,25 @@ int tc_gemm_launch(const bf16* const* a_ptrs, int n_amaps, long a_pix_stride, lo
     int rc = make_map(&bm, w, 2, dims, str, box);
     if (rc) return rc;
   }
+  // output / auxiliary tiles through TMA for the plain bf16 epilogue (every hot GEMM); the rare epilogues
+  // (fp32 output, PixelShuffle scatter, PReLU with saved pre-activation) keep direct stores
+  p.tma_out = (p.epi == TC_EPI_BF16 && p.prelu_slope == nullptr) ? 1 : 0;
+  FOCR_REQUIRE(!(p.residual && p.gate), "tc_gemm: residual and gate are mutually exclusive");
+  CUtensorMap cm = bm, rm = bm;
+  if (p.tma_out) {
+    cuuint64_t dims[2] = {(cuuint64_t)p.n_total, (cuuint64_t)p.m_tiles * kTileM};
+    cuuint64_t str[1] = {(cuuint64_t)p.ldc * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)kTileM};
+    int rc = make_map(&cm, p.out, 2, dims, str, box);
+    if (rc) return rc;
+    const void* aux = p.residual ? (const void*)p.residual : (const void*)p.gate;
+    if (aux) {
+      rc = make_map(&rm, aux, 2, dims, str, box);
+      if (rc) return rc;
+    }
+  }
   const char* scope = p.kh * p.kw == 1 ? "tc_linear" : (p.kh == 3 && p.kw == 3 ? "tc_conv3x3" : "tc_conv9tap");
   ProfScope _ps(scope, stream);
-  if (block_n == 128) return launch_impl<128>(am, bm, p, stream);
-  return launch_impl<64>(am, bm, p, stream);
+  if (block_n == 128) return launch_impl<128>(am, bm, cm, rm, p, stream);
+  return launch_impl<64>(am, bm, cm, rm, p, stream);
 }

@@ -42,6 +42,7 @@ struct TcGemmParams {
   float gate_scale;
   // PReLU epilogue (block1, tbsrn.py:180-182): out = x > 0 ? x : slope[0]*x ; out2 (optional) = x
   const float* prelu_slope;
+  int tma_out;  // set by tc_gemm_launch: epilogue goes TMEM -> smem -> TMA store, aux tile prefetched by TMA
 };
 
 int tc_gemm_launch(const bf16* const* a_ptrs, int n_amaps, long a_pix_stride /*elements between pixels*/,
