@@ -560,10 +560,11 @@ __global__ void pe_table_kernel(bf16* __restrict__ pe) {
   pe[i] = __float2bfloat16_rn(v);
 }
 
-// grid for reduction passes: at most 2 CTAs per SM so the second stage sums <= 296 partials
+// grid for reduction passes: 8 CTAs per SM keep enough loads in flight to stream at HBM rate; the second stage is
+// warp-parallel, so summing up to 1184 partials per output costs ~40 loads per lane
 int red_grid(long work_items, int per_block) {
   long g = (work_items + per_block - 1) / per_block;
-  const long cap = 148L * 2;
+  const long cap = 148L * 8;
   if (g > cap) g = cap;
   if (g < 1) g = 1;
   return (int)g;

@@ -14,6 +14,8 @@
 
 namespace {
 
+constexpr int kThreads = 384;   // producer, MMA, TMEM-alloc, spare + 2 x 4 epilogue warps
+constexpr int kEpiThreads = 256;
 constexpr int kTileM = 128;
 constexpr int kChunkK = 64;  // bf16 elements = one 128-byte swizzle row
 constexpr int kABytes = kTileM * 128;
@@ -39,7 +41,7 @@ struct TcCfg {
 __device__ __forceinline__ uint32_t cd_off(int row, int chunk) { return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4)); }
 
 template <int BLOCK_N>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(kThreads, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUtensorMap mA1,
                const __grid_constant__ CUtensorMap mA2, const __grid_constant__ CUtensorMap mA3,
                const __grid_constant__ CUtensorMap mB, const __grid_constant__ CUtensorMap mC,
@@ -77,11 +79,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 4);
+      mbar_init(&tempty[a], kEpiThreads / 32);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&afull[a], 1);
-      mbar_init(&aempty[a], 4);
+      mbar_init(&aempty[a], kEpiThreads / 32);
     }
     fence_mbar_init();
   }
@@ -167,7 +169,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
       }
     }
   } else if (warp >= 4) {
-    const int ew = warp - 4;  // == warp % 4 : TMEM lane quarter this warp may access
+    const int ew = warp & 3;        // TMEM lane quarter this warp may access (warp % 4)
+    const int egrp = (warp - 4) >> 2;  // epilogue group 0 / 1: interleaved 32-column chunks
     const int row = ew * 32 + lane;
     int acc = 0;
     uint32_t aphase = 0;
@@ -179,19 +182,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
       if (p.tma_out) {
         // ---- TMEM -> registers -> swizzled smem tile -> TMA store.  No global access from these warps. ------------
         uint8_t* cd = cd_base + (it & 1) * Cfg::kCdBytes;
-        if (ew == 0 && lane == 0) bulk_wait_read<1>();  // the store issued two tiles ago has finished reading `cd`
-        named_bar_sync(1, 128);
+        if (warp == 4 && lane == 0) bulk_wait_read<1>();  // the store issued two tiles ago has finished reading `cd`
+        named_bar_sync(1, kEpiThreads);
         mbar_wait(&tfull[acc], aphase);
         tc_fence_after();
         const uint8_t* aux = aux_base + (it & 1) * Cfg::kCdBytes;
         if (use_aux) mbar_wait(&afull[it & 1], (it >> 1) & 1);
         const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BLOCK_N;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        for (int c0 = egrp * 32; c0 < BLOCK_N; c0 += 64) {
           uint32_t r[32];
           tmem_ld_32x32b_x32(taddr + c0, r);
           tmem_ld_wait();
-          if (c0 == BLOCK_N - 32) {  // accumulator fully drained: hand the TMEM stage back to the MMA warp
+          if (c0 + 64 >= BLOCK_N) {  // this warp's last chunk: its share of the accumulator is drained
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
@@ -255,8 +258,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
           if (lane == 0) mbar_arrive(&aempty[it & 1]);
         }
         fence_proxy_async();  // make the generic-proxy smem writes visible to the TMA (async proxy)
-        named_bar_sync(1, 128);
-        if (ew == 0 && lane == 0) {
+        named_bar_sync(1, kEpiThreads);
+        if (warp == 4 && lane == 0) {
           for (int blk = 0; blk < BLOCK_N / 64; ++blk)
             tma_store_2d(&mC, cd + blk * kCdBlk, nb * BLOCK_N + blk * 64, m * kTileM);
           bulk_commit();
@@ -270,7 +273,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BLOCK_N;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      for (int c0 = egrp * 32; c0 < BLOCK_N; c0 += 64) {
         uint32_t r[32];
         tmem_ld_32x32b_x32(taddr + c0, r);
         tmem_ld_wait();
@@ -402,7 +405,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
       acc ^= 1;
       if (acc == 0) aphase ^= 1;
     }
-    if (p.tma_out && ew == 0 && lane == 0) bulk_wait<0>();  // all output tiles are in global memory
+    if (p.tma_out && warp == 4 && lane == 0) bulk_wait<0>();  // all output tiles are in global memory
   }
 
   tc_fence_before();
@@ -476,7 +479,7 @@ int launch_impl(const CUtensorMap* am, const CUtensorMap& bm, const CUtensorMap&
   }
   const int total = p.m_tiles * p.n_blocks;
   const int grid = total < num_sms() ? total : num_sms();
-  tc_gemm_kernel<BLOCK_N><<<grid, 256, Cfg::kSmemBytes, stream>>>(am[0], am[1], am[2], am[3], bm, cm, rm, p);
+  tc_gemm_kernel<BLOCK_N><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(am[0], am[1], am[2], am[3], bm, cm, rm, p);
   FOCR_LAUNCH_CHECK();
   return FOCR_OK;
 }
