@@ -58,6 +58,11 @@ _SIGS = {
     "focr_tbsrn_workspace_bytes": (_sz, [_i, _i]),
     "focr_tbsrn_forward": (C.c_int, [_pp, _fp, _fp, _i, _i, _i, _f, _u, _vp, _sz, _vp]),
     "focr_tbsrn_backward": (C.c_int, [_pp, _pp, _fp, _fp, _i, _i, _i, _f, _u, _vp, _sz, _vp]),
+    "focr_crnn_num_slots": (C.c_int, []),
+    "focr_crnn_workspace_bytes": (_sz, [_i]),
+    "focr_bicubic_gray_32x100": (C.c_int, [_fp, _fp, _i, _vp]),
+    "focr_crnn_forward": (C.c_int, [_pp, _fp, _i, _fp, _i, _vp, _sz, _vp]),
+    "focr_ctc_greedy_decode": (C.c_int, [_fp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "focr_prof_enable": (C.c_int, [_i, C.c_char_p]),
     "focr_prof_collect": (C.c_int, [C.c_char_p, _i]),
     "focr_launch_count": (_ll, []),

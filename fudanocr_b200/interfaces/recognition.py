@@ -1,0 +1,43 @@
+"""Evaluation-side helpers of the reference's TextSR loop on the focr engine:
+``parse_crnn_data`` (interfaces/base.py:319-325), ``get_crnn_pred`` (interfaces/super_resolution.py:143-158) and
+``strLabelConverter.decode`` (utils/utils_crnn.py:54-89).  The index arithmetic (argmax, repeat/blank collapse)
+runs on the GPU and returns INT32 arrays; only the final index -> character join happens on the host."""
+from __future__ import annotations
+
+from typing import List, Tuple
+
+import torch
+
+from .. import _lib as L
+
+ALPHABET = "-0123456789abcdefghijklmnopqrstuvwxyz"  # index 0 = CTC blank
+
+
+def parse_crnn_data(imgs_input: torch.Tensor) -> torch.Tensor:
+    x = imgs_input[:, :3].detach().contiguous().float()
+    if not x.is_cuda or tuple(x.shape[1:]) != (3, 32, 128):
+        raise L.FocrError("parse_crnn_data: expected a CUDA (B,3,32,128) tensor")
+    out = torch.empty(x.shape[0], 1, 32, 100, dtype=torch.float32, device=x.device)
+    L.check(L.lib.focr_bicubic_gray_32x100(x.data_ptr(), out.data_ptr(), x.shape[0], L.cur_stream()))
+    return out
+
+
+def ctc_greedy_decode(logits_tbc: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """logits (T,B,C) -> (path (B,T), labels (B,T) padded with -1, lengths (B)), all int32 on the device."""
+    x = logits_tbc.detach().contiguous().float()
+    if not x.is_cuda:
+        raise L.FocrError("ctc_greedy_decode runs on CUDA only")
+    T, B, Cc = x.shape
+    path = torch.empty(B, T, dtype=torch.int32, device=x.device)
+    out = torch.empty(B, T, dtype=torch.int32, device=x.device)
+    ln = torch.empty(B, dtype=torch.int32, device=x.device)
+    L.check(L.lib.focr_ctc_greedy_decode(x.data_ptr(), T, B, Cc, path.data_ptr(), out.data_ptr(), ln.data_ptr(),
+                                         L.cur_stream()))
+    return path, out, ln
+
+
+def get_crnn_pred(outputs_btc: torch.Tensor) -> List[str]:
+    """same call shape as the reference: outputs = crnn_output.permute(1, 0, 2) -> list of strings"""
+    _, out, ln = ctc_greedy_decode(outputs_btc.permute(1, 0, 2))
+    out, ln = out.cpu().tolist(), ln.cpu().tolist()
+    return ["".join(ALPHABET[i] for i in row[:n]) for row, n in zip(out, ln)]

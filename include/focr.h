@@ -91,6 +91,19 @@ int focr_tbsrn_backward(void* const* params, void* const* grads, const float* x_
 int focr_tbsrn_ws_tensor(int B, int srb_nums, const char* name, long long* byte_offset, long long* elems,
                          int* elem_bytes);
 
+/* --- frozen CRNN evaluator + greedy CTC decode (eval pipeline, BASELINE configs[4]) -----------------------------------
+ * STT/model/crnn/crnn.py:25-80 (CRNN(32,1,37,256).forward, eval mode), STT/interfaces/base.py:319-325 (parse_crnn_data:
+ * bicubic (32,100) + gray), STT/interfaces/super_resolution.py:143-158 (get_crnn_pred) and
+ * STT/utils/utils_crnn.py:54-89 (strLabelConverter.decode).  params: HOST array of the 49 state_dict tensors in
+ * state_dict order.  Decode output is INT32 and bit-exact: path (B,T) argmax indices (lowest index on ties), out (B,T)
+ * collapsed label indices padded with -1, len (B). */
+int focr_crnn_num_slots(void);
+size_t focr_crnn_workspace_bytes(int B);
+int focr_bicubic_gray_32x100(const float* images, float* gray, int B, void* stream);
+int focr_crnn_forward(void* const* params, const float* images, int input_is_gray, float* logits, int B, void* ws,
+                      size_t ws_bytes, void* stream);
+int focr_ctc_greedy_decode(const float* logits, int T, int B, int C, int* path, int* out, int* len, void* stream);
+
 /* --- measurement hooks used by bench.py: CUDA-event scopes on the launching stream + launch counter ----------- */
 int focr_prof_enable(int mode /*0 off, 1 all, 2 focus*/, const char* focus_substring);
 int focr_prof_collect(char* buf, int cap); /* lines "scope launches total_ms"; synchronises; clears */
