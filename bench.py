@@ -109,6 +109,19 @@ def algo_work(B: int):
     return w
 
 
+def ncu_traffic(scope: str):
+    """DRAM read+write bytes per launch of the kernel behind `scope`, from the committed `ncu --set full` capture
+    (profiles/r01_dram_traffic_bytes.json, produced by scripts/summarize_profiles.py); None if not captured."""
+    for name in sorted(os.listdir(os.path.join(ROOT, "profiles")), reverse=True):
+        if name.endswith("_dram_traffic_bytes.json"):
+            d = json.load(open(os.path.join(ROOT, "profiles", name)))
+            key = {"tc_linear": "tc_gemm_kernel<128>", "tc_conv3x3": "tc_gemm_kernel<64>"}.get(scope, scope + "_kernel")
+            for k, v in d.items():
+                if k.startswith(key):
+                    return v
+    return None
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -277,7 +290,8 @@ def main():
     step_ms_profiled = sum(v[1] for v in breakdown.values())
     roofline = {
         "kernel": top, "bound": kind, "achieved": achieved, "peak": peak, "unit": unit,
-        "frac": achieved / peak if peak else None, "traffic": None,
+        "frac": achieved / peak if peak else None, "traffic": ncu_traffic(top),
+        "algorithmic_per_launch": (amount / max(cnt / max(K, 1), 1)) if cnt else None,
         "launches_per_step": cnt / max(K, 1), "ms_per_launch": tot_ms / cnt if cnt else None,
         "share_of_step": (breakdown[top][1] / step_ms_profiled) if top in breakdown and step_ms_profiled else None,
         "peak_source": peaks["source"] + (", sustained bf16 figure (kernel timed inside a long step)"
