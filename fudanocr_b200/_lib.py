@@ -66,6 +66,12 @@ _SIGS = {
     "focr_prof_enable": (C.c_int, [_i, C.c_char_p]),
     "focr_prof_collect": (C.c_int, [C.c_char_p, _i]),
     "focr_launch_count": (_ll, []),
+    "focr_tsrn_num_slots": (C.c_int, [_i]),
+    "focr_tsrn_slot_name": (C.c_char_p, [_i, _i]),
+    "focr_tsrn_workspace_bytes": (_sz, [_i, _i]),
+    "focr_tsrn_forward": (C.c_int, [_pp, _fp, _fp, _i, _i, _i, _vp, _sz, _vp]),
+    "focr_tsrn_backward": (C.c_int, [_pp, _pp, _fp, _fp, _i, _i, _i, _vp, _sz, _vp]),
+    "focr_tsrn_ws_tensor": (C.c_int, [_i, _i, C.c_char_p, C.POINTER(_ll), C.POINTER(_ll), C.POINTER(_i)]),
     "focr_tbsrn_ws_tensor": (C.c_int, [_i, _i, C.c_char_p, C.POINTER(_ll), C.POINTER(_ll), C.POINTER(_i)]),
 }
 

@@ -256,55 +256,79 @@ int focr_adam_clip_step(const void* chunks, int n_chunks, float gscale, float ma
 // flags bit0: training (BN batch stats + running update, dropout, STN active), bit1: model has STN.
 // ---------------------------------------------------------------------------------------------
 int focr_tbsrn_num_slots(int srb_nums) { return tbsrn::Slots(srb_nums).count; }
+int focr_tsrn_num_slots(int srb_nums) { return tbsrn::Slots(srb_nums, tbsrn::ARCH_TSRN).count; }
 
-const char* focr_tbsrn_slot_name(int srb_nums, int idx) {
+static const char* slot_name_impl(int srb_nums, int arch, int idx) {
   static thread_local std::vector<std::string> names;
   static thread_local int cached = -1;
-  if (cached != srb_nums) {
-    names = tbsrn::slot_names(srb_nums);
-    cached = srb_nums;
+  const int key = srb_nums * 2 + arch;
+  if (cached != key) {
+    names = tbsrn::slot_names(srb_nums, arch);
+    cached = key;
   }
   if (idx < 0 || idx >= (int)names.size()) return "";
   return names[idx].c_str();
 }
+const char* focr_tbsrn_slot_name(int srb_nums, int idx) { return slot_name_impl(srb_nums, tbsrn::ARCH_TBSRN, idx); }
+const char* focr_tsrn_slot_name(int srb_nums, int idx) { return slot_name_impl(srb_nums, tbsrn::ARCH_TSRN, idx); }
 
-size_t focr_tbsrn_workspace_bytes(int B, int srb_nums) {
+static size_t ws_bytes_impl(int B, int srb_nums, int arch) {
   tbsrn::Ws w;
-  tbsrn::layout(w, B, srb_nums, nullptr);
+  tbsrn::layout(w, B, srb_nums, nullptr, arch);
   return w.total_bytes + 256;
 }
+size_t focr_tbsrn_workspace_bytes(int B, int srb_nums) { return ws_bytes_impl(B, srb_nums, tbsrn::ARCH_TBSRN); }
+size_t focr_tsrn_workspace_bytes(int B, int srb_nums) { return ws_bytes_impl(B, srb_nums, tbsrn::ARCH_TSRN); }
 
 static void* align256(void* p) { return (void*)(((uintptr_t)p + 255) & ~(uintptr_t)255); }
 
-int focr_tbsrn_forward(void* const* params, const float* x_lr, float* sr, int B, int srb_nums, int flags, float p_drop,
-                       unsigned seed, void* ws, size_t ws_bytes, void* stream) {
-  FOCR_REQUIRE(B >= 1 && srb_nums >= 0 && srb_nums <= 16, "tbsrn_forward: B=%d srb_nums=%d", B, srb_nums);
-  FOCR_REQUIRE(!((flags & 1) && (flags & 2)) || B >= 2, "tbsrn_forward: train mode with STN needs B >= 2 (BatchNorm1d)");
+static int forward_impl(int arch, void* const* params, const float* x_lr, float* sr, int B, int srb_nums, int flags,
+                        float p_drop, unsigned seed, void* ws, size_t ws_bytes, void* stream) {
+  FOCR_REQUIRE(B >= 1 && srb_nums >= 0 && srb_nums <= 16, "forward: B=%d srb_nums=%d", B, srb_nums);
+  FOCR_REQUIRE(!((flags & 1) && (flags & 2)) || B >= 2, "forward: train mode with STN needs B >= 2 (BatchNorm1d)");
   tbsrn::Ws w;
-  tbsrn::layout(w, B, srb_nums, align256(ws));
-  FOCR_REQUIRE(ws_bytes >= w.total_bytes + 256, "tbsrn_forward: workspace too small (%zu < %zu)", ws_bytes,
+  tbsrn::layout(w, B, srb_nums, align256(ws), arch);
+  FOCR_REQUIRE(ws_bytes >= w.total_bytes + 256, "forward: workspace too small (%zu < %zu)", ws_bytes,
                w.total_bytes + 256);
-  tbsrn::Slots sl(srb_nums);
+  tbsrn::Slots sl(srb_nums, arch);
   return tbsrn::forward(sl, params, x_lr, sr, w, flags & 1, (flags >> 1) & 1, p_drop, seed, (cudaStream_t)stream);
 }
+static int backward_impl(int arch, void* const* params, void* const* grads, const float* x_lr, const float* d_sr, int B,
+                         int srb_nums, int flags, float p_drop, unsigned seed, void* ws, size_t ws_bytes, void* stream) {
+  FOCR_REQUIRE(flags & 1, "backward: forward must have run in training mode");
+  tbsrn::Ws w;
+  tbsrn::layout(w, B, srb_nums, align256(ws), arch);
+  FOCR_REQUIRE(ws_bytes >= w.total_bytes + 256, "backward: workspace too small");
+  tbsrn::Slots sl(srb_nums, arch);
+  return tbsrn::backward(sl, params, grads, x_lr, d_sr, w, (flags >> 1) & 1, p_drop, seed, (cudaStream_t)stream);
+}
 
+int focr_tbsrn_forward(void* const* params, const float* x_lr, float* sr, int B, int srb_nums, int flags, float p_drop,
+                       unsigned seed, void* ws, size_t ws_bytes, void* stream) {
+  return forward_impl(tbsrn::ARCH_TBSRN, params, x_lr, sr, B, srb_nums, flags, p_drop, seed, ws, ws_bytes, stream);
+}
 int focr_tbsrn_backward(void* const* params, void* const* grads, const float* x_lr, const float* d_sr, int B,
                         int srb_nums, int flags, float p_drop, unsigned seed, void* ws, size_t ws_bytes, void* stream) {
-  FOCR_REQUIRE(flags & 1, "tbsrn_backward: forward must have run in training mode");
-  tbsrn::Ws w;
-  tbsrn::layout(w, B, srb_nums, align256(ws));
-  FOCR_REQUIRE(ws_bytes >= w.total_bytes + 256, "tbsrn_backward: workspace too small");
-  tbsrn::Slots sl(srb_nums);
-  return tbsrn::backward(sl, params, grads, x_lr, d_sr, w, (flags >> 1) & 1, p_drop, seed, (cudaStream_t)stream);
+  return backward_impl(tbsrn::ARCH_TBSRN, params, grads, x_lr, d_sr, B, srb_nums, flags, p_drop, seed, ws, ws_bytes,
+                       stream);
+}
+// TSRN (model/tsrn.py:18-74): same trunk, SRBs with vertical + horizontal BiGRU instead of the FeatureEnhancer
+int focr_tsrn_forward(void* const* params, const float* x_lr, float* sr, int B, int srb_nums, int flags, void* ws,
+                      size_t ws_bytes, void* stream) {
+  return forward_impl(tbsrn::ARCH_TSRN, params, x_lr, sr, B, srb_nums, flags, 0.f, 0, ws, ws_bytes, stream);
+}
+int focr_tsrn_backward(void* const* params, void* const* grads, const float* x_lr, const float* d_sr, int B,
+                       int srb_nums, int flags, void* ws, size_t ws_bytes, void* stream) {
+  return backward_impl(tbsrn::ARCH_TSRN, params, grads, x_lr, d_sr, B, srb_nums, flags, 0.f, 0, ws, ws_bytes, stream);
 }
 
 // Byte offset / element count of a named intermediate inside the workspace (parity debugging):
 // "x_tps","ctrl","b1","s7","u","opre","srb<i>.<c1|a1|c2|f|qkv|o|y1|y2|out>"
-int focr_tbsrn_ws_tensor(int B, int srb_nums, const char* name, long long* byte_offset, long long* elems,
-                         int* elem_bytes) {
+static int ws_tensor_impl(int arch, int B, int srb_nums, const char* name, long long* byte_offset, long long* elems,
+                          int* elem_bytes) {
   tbsrn::Ws w;
   char* base = (char*)4096;
-  tbsrn::layout(w, B, srb_nums, base);
+  tbsrn::layout(w, B, srb_nums, base, arch);
   const long T = w.T, Thr = w.Thr;
   const void* p = nullptr;
   long n = 0;
@@ -343,12 +367,23 @@ int focr_tbsrn_ws_tensor(int B, int srb_nums, const char* name, long long* byte_
     else if (f == "y1") { p = a.y1; n = T * 128; }
     else if (f == "y2") { p = a.y2; n = T * 128; }
     else if (f == "out") { p = a.out; n = T * 64; }
+    else if (f == "r0" && arch == tbsrn::ARCH_TSRN) { p = a.r0; n = T * 64; }
+    else if (f == "o1" && arch == tbsrn::ARCH_TSRN) { p = a.o1; n = T * 64; }
+    if (arch == tbsrn::ARCH_TSRN && (f == "f" || f == "qkv" || f == "o" || f == "y1" || f == "y2")) p = nullptr;
   }
   FOCR_REQUIRE(p != nullptr, "ws_tensor: unknown tensor %s", name);
   *byte_offset = (const char*)p - base;
   *elems = n;
   *elem_bytes = eb;
   return FOCR_OK;
+}
+int focr_tbsrn_ws_tensor(int B, int srb_nums, const char* name, long long* byte_offset, long long* elems,
+                         int* elem_bytes) {
+  return ws_tensor_impl(tbsrn::ARCH_TBSRN, B, srb_nums, name, byte_offset, elems, elem_bytes);
+}
+int focr_tsrn_ws_tensor(int B, int srb_nums, const char* name, long long* byte_offset, long long* elems,
+                        int* elem_bytes) {
+  return ws_tensor_impl(tbsrn::ARCH_TSRN, B, srb_nums, name, byte_offset, elems, elem_bytes);
 }
 
 }  // extern "C"

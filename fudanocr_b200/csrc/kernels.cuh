@@ -86,3 +86,13 @@ int unpack_stn_conv_grad(const float* g, float* dw, int Co, int C, int Kpad, cud
 // optim.cu
 int adam_clip_step(const void* chunks, int n_chunks, float gscale, float max_norm, float lr, float b1, float b2,
                    float eps, long long* step, float* state, float* partial, cudaStream_t s);
+
+// gru.cu
+int gru_prep(const float* wih_f, const float* wih_r, const float* bih_f, const float* bih_r, bf16* w, bf16* wt, float* b,
+             cudaStream_t s);
+int gru_forward(const bf16* xp, const float* whh_f, const float* whh_r, const float* bhh_f, const float* bhh_r, bf16* out,
+                float* hprev32, bf16* hprev16, int B, int vertical, cudaStream_t s);
+int gru_backward(const bf16* xp, const float* whh_f, const float* whh_r, const float* bhh_f, const float* bhh_r,
+                 const float* hprev32, const bf16* dout, bf16* dxp, bf16* dhid, int B, int vertical, cudaStream_t s);
+int gru_unpack_whh(const float* g, float* df, float* dr, cudaStream_t s);
+int linear_wgrad_k64(const bf16* dy, const bf16* x, long T, int N, float* dw, float* tmp, float* partial, cudaStream_t s);

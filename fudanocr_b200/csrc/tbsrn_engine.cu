@@ -16,8 +16,8 @@ namespace tbsrn {
 // ---------------------------------------------------------------------------------------------
 // slot names = reference state_dict keys
 // ---------------------------------------------------------------------------------------------
-std::vector<std::string> slot_names(int n) {
-  Slots sl(n);
+std::vector<std::string> slot_names(int n, int arch) {
+  Slots sl(n, arch);
   std::vector<std::string> v(sl.count);
   v[sl.b1_w] = "block1.0.weight";
   v[sl.b1_b] = "block1.0.bias";
@@ -34,8 +34,25 @@ std::vector<std::string> slot_names(int n) {
       "feature_enhancer.pff.w_1.weight", "feature_enhancer.pff.w_1.bias", "feature_enhancer.pff.w_2.weight",
       "feature_enhancer.pff.w_2.bias", "feature_enhancer.mul_layernorm3.a_2", "feature_enhancer.mul_layernorm3.b_2",
       "feature_enhancer.linear.weight", "feature_enhancer.linear.bias"};
-  for (int b = 0; b < n; ++b)
-    for (int s = 0; s < S_COUNT; ++s) v[sl.srb(b, s)] = "block" + std::to_string(b + 2) + "." + srb_names[s];
+  static const char* gru_names[G_COUNT] = {"conv1.weight", "conv1.bias", "gru.weight_ih_l0", "gru.weight_hh_l0",
+                                            "gru.bias_ih_l0", "gru.bias_hh_l0", "gru.weight_ih_l0_reverse",
+                                            "gru.weight_hh_l0_reverse", "gru.bias_ih_l0_reverse",
+                                            "gru.bias_hh_l0_reverse"};
+  static const char* tsrn_head[7] = {"conv1.weight", "conv1.bias", "bn1.weight", "bn1.bias", "bn1.running_mean",
+                                     "bn1.running_var", "bn1.num_batches_tracked"};
+  static const char* tsrn_mid[7] = {"conv2.weight", "conv2.bias", "bn2.weight", "bn2.bias", "bn2.running_mean",
+                                    "bn2.running_var", "bn2.num_batches_tracked"};
+  for (int b = 0; b < n; ++b) {
+    const std::string pre = "block" + std::to_string(b + 2) + ".";
+    if (arch == ARCH_TSRN) {
+      for (int j = 0; j < 7; ++j) v[sl.srb(b, TS_C1W + j)] = pre + tsrn_head[j];
+      for (int j = 0; j < G_COUNT; ++j) v[sl.srb(b, TS_G1 + j)] = pre + "gru1." + gru_names[j];
+      for (int j = 0; j < 7; ++j) v[sl.srb(b, TS_C2W + j)] = pre + tsrn_mid[j];
+      for (int j = 0; j < G_COUNT; ++j) v[sl.srb(b, TS_G2 + j)] = pre + "gru2." + gru_names[j];
+    } else {
+      for (int s = 0; s < S_COUNT; ++s) v[sl.srb(b, s)] = pre + srb_names[s];
+    }
+  }
   static const char* bn_names[5] = {"weight", "bias", "running_mean", "running_var", "num_batches_tracked"};
   const std::string b7 = "block" + std::to_string(n + 2), b8 = "block" + std::to_string(n + 3);
   v[sl.b7_w] = b7 + ".0.weight";
@@ -79,10 +96,11 @@ struct Bump {
 inline long pad128(long m) { return (m + 127) / 128 * 128; }
 }  // namespace
 
-void layout(Ws& w, int B, int n, void* base) {
+void layout(Ws& w, int B, int n, void* base, int arch) {
   Bump b{reinterpret_cast<char*>(base)};
   w.B = B;
   w.srb_nums = n;
+  w.arch = arch;
   const long T = (long)B * 1024, Thr = (long)B * 4096;
   w.T = T;
   w.Thr = Thr;
@@ -121,11 +139,42 @@ void layout(Ws& w, int B, int n, void* base) {
   w.w_b1d = b.get<bf16>(9 * 4096);
   w.srb.resize(n);
   w.srbw.resize(n);
+  w.gruw.resize(arch == ARCH_TSRN ? 2 * n : 0);
   for (int i = 0; i < n; ++i) {
     SrbWs& s = w.srb[i];
+    SrbW& q = w.srbw[i];
     s.c1 = b.get<bf16>(T * 64);
     s.a1 = b.get<bf16>(T * 64);
     s.c2 = b.get<bf16>(T * 64);
+    s.out = b.get<bf16>(T * 64);
+    s.st1 = b.get<float>(4 * 64);
+    s.st2 = b.get<float>(4 * 64);
+    q.c1f = b.get<bf16>(9 * 4096);
+    q.c1d = b.get<bf16>(9 * 4096);
+    q.c2f = b.get<bf16>(9 * 4096);
+    q.c2d = b.get<bf16>(9 * 4096);
+    if (arch == ARCH_TSRN) {
+      s.r0 = b.get<bf16>(T * 64);
+      s.g1in = b.get<bf16>(T * 64);
+      s.xp1 = b.get<bf16>(T * 192);
+      s.o1 = b.get<bf16>(T * 64);
+      s.hp1b = b.get<bf16>(T * 64);
+      s.hp1 = b.get<float>(T * 64);
+      s.ssum = b.get<bf16>(T * 64);
+      s.g2in = b.get<bf16>(T * 64);
+      s.xp2 = b.get<bf16>(T * 192);
+      s.hp2b = b.get<bf16>(T * 64);
+      s.hp2 = b.get<float>(T * 64);
+      for (int gidx = 0; gidx < 2; ++gidx) {
+        GruW& gw = w.gruw[2 * i + gidx];
+        gw.cw = b.get<bf16>(64 * 64);
+        gw.cwT = b.get<bf16>(64 * 64);
+        gw.wih = b.get<bf16>(192 * 64);
+        gw.wihT = b.get<bf16>(192 * 64);
+        gw.bih = b.get<float>(192);
+      }
+      continue;
+    }
     s.f = b.get<bf16>(T * 128);
     s.qkv = b.get<bf16>(T * 384);
     s.o = b.get<bf16>(T * 128);
@@ -134,15 +183,7 @@ void layout(Ws& w, int B, int n, void* base) {
     s.hd = b.get<bf16>(T * 128);
     s.y2pre = b.get<bf16>(T * 128);
     s.y2 = b.get<bf16>(T * 128);
-    s.out = b.get<bf16>(T * 64);
     s.lse = b.get<float>((long)B * 4 * 1024);
-    s.st1 = b.get<float>(4 * 64);
-    s.st2 = b.get<float>(4 * 64);
-    SrbW& q = w.srbw[i];
-    q.c1f = b.get<bf16>(9 * 4096);
-    q.c1d = b.get<bf16>(9 * 4096);
-    q.c2f = b.get<bf16>(9 * 4096);
-    q.c2d = b.get<bf16>(9 * 4096);
     q.qkv = b.get<bf16>(384 * 128);
     q.qkvT = b.get<bf16>(384 * 128);
     q.wo = b.get<bf16>(128 * 128);
@@ -177,6 +218,8 @@ void layout(Ws& w, int B, int n, void* base) {
   for (int i = 0; i < 5; ++i) w.g64[i] = b.get<bf16>(T * 64);
   for (int i = 0; i < 4; ++i) w.g128[i] = b.get<bf16>(T * 128);
   w.g384 = b.get<bf16>(T * 384);
+  w.gdxp = w.g384;  // TSRN reuses the (T,384) buffer as two (T,192) halves
+  w.gdhid = w.g384 + T * 192;
   w.dsum = b.get<float>((long)B * 4 * 1024);
   w.dx_tps = b.get<float>((long)B * 3 * 1024);
   w.dctrl = b.get<float>((long)B * 40);
@@ -248,10 +291,21 @@ int prep_weights(const Slots& sl, void* const* prm, Ws& w, bool stn, cudaStream_
   TRY(prep_w9(P<float>(prm, sl.b1_w), w.w_b1d, 3, s));
   for (int i = 0; i < sl.srb_nums; ++i) {
     SrbW& q = w.srbw[i];
-    TRY(prep_conv_w_fwd(P<float>(prm, sl.srb(i, S_C1W)), q.c1f, 64, 64, 3, 0, s));
-    TRY(prep_conv_w_dgrad(P<float>(prm, sl.srb(i, S_C1W)), q.c1d, 64, 64, 3, 0, s));
-    TRY(prep_conv_w_fwd(P<float>(prm, sl.srb(i, S_C2W)), q.c2f, 64, 64, 3, 0, s));
-    TRY(prep_conv_w_dgrad(P<float>(prm, sl.srb(i, S_C2W)), q.c2d, 64, 64, 3, 0, s));
+    const int c1w = sl.arch == ARCH_TSRN ? (int)TS_C1W : (int)S_C1W, c2w = sl.arch == ARCH_TSRN ? (int)TS_C2W : (int)S_C2W;
+    TRY(prep_conv_w_fwd(P<float>(prm, sl.srb(i, c1w)), q.c1f, 64, 64, 3, 0, s));
+    TRY(prep_conv_w_dgrad(P<float>(prm, sl.srb(i, c1w)), q.c1d, 64, 64, 3, 0, s));
+    TRY(prep_conv_w_fwd(P<float>(prm, sl.srb(i, c2w)), q.c2f, 64, 64, 3, 0, s));
+    TRY(prep_conv_w_dgrad(P<float>(prm, sl.srb(i, c2w)), q.c2d, 64, 64, 3, 0, s));
+    if (sl.arch == ARCH_TSRN) {
+      for (int gidx = 0; gidx < 2; ++gidx) {
+        const int g0 = sl.srb(i, gidx ? TS_G2 : TS_G1);
+        GruW& gw = w.gruw[2 * i + gidx];
+        TRY(prep_linear_w(P<float>(prm, g0 + G_CW), gw.cw, gw.cwT, 64, 64, 64, 0, s));
+        TRY(gru_prep(P<float>(prm, g0 + G_WIH), P<float>(prm, g0 + G_WIH_R), P<float>(prm, g0 + G_BIH),
+                     P<float>(prm, g0 + G_BIH_R), gw.wih, gw.wihT, gw.bih, s));
+      }
+      continue;
+    }
     for (int j = 0; j < 3; ++j) {
       TRY(prep_linear_w(P<float>(prm, sl.srb(i, S_LQW + 2 * j)), q.qkv + j * 128 * 128, q.qkvT, 128, 128, 384,
                         j * 128, s));
@@ -392,6 +446,118 @@ int stn_backward(const Slots& sl, void* const* prm, void* const* grd, const floa
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
+// TSRN sequence residual block (tsrn.py:77-98, 128-145)
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+// GruBlock forward: gin = conv1x1(x); xp = gin W_ih^T + b_ih (both directions); recurrence -> out (T,64)
+int gru_block_forward(void* const* prm, int g0, const GruW& gw, const bf16* x, bf16* gin, bf16* xp, bf16* out, float* hp32,
+                      bf16* hp16, int vertical, Ws& w, cudaStream_t s) {
+  TcGemmParams p = gp();
+  p.bias = P<float>(prm, g0 + G_CB);
+  p.out = gin;
+  TRY(tok_gemm(x, 64, w.T, gw.cw, 64, p, s));
+  p = gp();
+  p.bias = gw.bih;
+  p.out = xp;
+  TRY(tok_gemm(gin, 64, w.T, gw.wih, 192, p, s));
+  return gru_forward(xp, P<float>(prm, g0 + G_WHH), P<float>(prm, g0 + G_WHH_R), P<float>(prm, g0 + G_BHH),
+                     P<float>(prm, g0 + G_BHH_R), out, hp32, hp16, w.B, vertical, s);
+}
+
+// GruBlock backward: dout (T,64) -> dx (T,64) (+ residual), all parameter gradients of the block
+int gru_block_backward(void* const* prm, void* const* grd, int g0, const GruW& gw, const bf16* x, const bf16* gin,
+                       const bf16* xp, const float* hp32, const bf16* hp16, const bf16* dout, bf16* dgin, bf16* dx,
+                       const bf16* dx_residual, int vertical, Ws& w, cudaStream_t s) {
+  const long T = w.T;
+  TRY(gru_backward(xp, P<float>(prm, g0 + G_WHH), P<float>(prm, g0 + G_WHH_R), P<float>(prm, g0 + G_BHH),
+                   P<float>(prm, g0 + G_BHH_R), hp32, dout, w.gdxp, w.gdhid, w.B, vertical, s));
+  // recurrent weights / biases: dW_hh = dhid^T h_{t-1}
+  float* tmp2 = w.tmpw + 192 * 64;  // second half of the scratch: the [2N][128] intermediate of the k64 trick
+  TRY(linear_wgrad_k64(w.gdhid, hp16, T, 192, w.tmpw, tmp2, w.partial, s));
+  TRY(gru_unpack_whh(w.tmpw, P<float>(grd, g0 + G_WHH), P<float>(grd, g0 + G_WHH_R), s));
+  TRY(colsum(w.gdhid, 192, T, 192, w.tmpb, w.partial, s));
+  if (grd[g0 + G_BHH]) TRY(d2d(grd[g0 + G_BHH], w.tmpb, 96 * 4, s));
+  if (grd[g0 + G_BHH_R]) TRY(d2d(grd[g0 + G_BHH_R], w.tmpb + 96, 96 * 4, s));
+  // input projection
+  TRY(linear_wgrad_k64(w.gdxp, gin, T, 192, w.tmpw, tmp2, w.partial, s));
+  if (grd[g0 + G_WIH]) TRY(d2d(grd[g0 + G_WIH], w.tmpw, 96 * 64 * 4, s));
+  if (grd[g0 + G_WIH_R]) TRY(d2d(grd[g0 + G_WIH_R], w.tmpw + 96 * 64, 96 * 64 * 4, s));
+  TRY(colsum(w.gdxp, 192, T, 192, w.tmpb, w.partial, s));
+  if (grd[g0 + G_BIH]) TRY(d2d(grd[g0 + G_BIH], w.tmpb, 96 * 4, s));
+  if (grd[g0 + G_BIH_R]) TRY(d2d(grd[g0 + G_BIH_R], w.tmpb + 96, 96 * 4, s));
+  TcGemmParams p = gp();
+  p.out = dgin;
+  TRY(tok_gemm(w.gdxp, 192, T, gw.wihT, 64, p, s));
+  // conv1x1
+  if (grd[g0 + G_CW]) TRY(linear_wgrad_k64(dgin, x, T, 64, P<float>(grd, g0 + G_CW), tmp2, w.partial, s));
+  if (grd[g0 + G_CB]) TRY(colsum(dgin, 64, T, 64, P<float>(grd, g0 + G_CB), w.partial, s));
+  p = gp();
+  p.out = dx;
+  p.residual = dx_residual;
+  return tok_gemm(dgin, 64, T, gw.cwT, 64, p, s);
+}
+
+int tsrn_srb_forward(const Slots& sl, void* const* prm, int i, const bf16* x, Ws& w, bool training, cudaStream_t s) {
+  SrbWs& a = w.srb[i];
+  SrbW& q = w.srbw[i];
+  const int B = w.B;
+  const long T = w.T;
+  TcGemmParams p = gp();
+  p.bias = P<float>(prm, sl.srb(i, TS_C1B));
+  p.out = a.c1;
+  TRY(map_conv(x, B, 16, 64, 3, 3, q.c1f, 64, p, s));
+  TRY(bn_fwd_stats(a.c1, 64, T, 64, prm, sl.srb(i, TS_BN1W), training, w, a.st1, s));
+  TRY(bn_apply(a.c1, 64, a.st1, a.a1, 64, T, 64, ACT_MISH, nullptr, 0, nullptr, s));
+  p = gp();
+  p.bias = P<float>(prm, sl.srb(i, TS_C2B));
+  p.out = a.c2;
+  TRY(map_conv(a.a1, B, 16, 64, 3, 3, q.c2f, 64, p, s));
+  TRY(bn_fwd_stats(a.c2, 64, T, 64, prm, sl.srb(i, TS_BN2W), training, w, a.st2, s));
+  TRY(bn_apply(a.c2, 64, a.st2, a.r0, 64, T, 64, ACT_NONE, nullptr, 0, nullptr, s));
+  // gru1 on the transposed map = sequences down the columns (tsrn.py:96)
+  TRY(gru_block_forward(prm, sl.srb(i, TS_G1), w.gruw[2 * i], a.r0, a.g1in, a.xp1, a.o1, a.hp1, a.hp1b, 1, w, s));
+  TRY(add_bf16(x, a.o1, a.ssum, T * 64, s));
+  // gru2(x + residual): sequences along the rows (tsrn.py:98)
+  return gru_block_forward(prm, sl.srb(i, TS_G2), w.gruw[2 * i + 1], a.ssum, a.g2in, a.xp2, a.out, a.hp2, a.hp2b, 0, w, s);
+}
+
+// dout: gradient w.r.t. the SRB output; dx_out receives the gradient w.r.t. its input
+int tsrn_srb_backward(const Slots& sl, void* const* prm, void* const* grd, int i, const bf16* x_in, const bf16* dout,
+                      bf16* dx_out, Ws& w, cudaStream_t s) {
+  SrbWs& a = w.srb[i];
+  SrbW& q = w.srbw[i];
+  const int B = w.B;
+  const long T = w.T;
+  bf16 *dgin = w.g64[3], *dsum = w.g64[4];
+  // gru2: input ssum = x + o1
+  TRY(gru_block_backward(prm, grd, sl.srb(i, TS_G2), w.gruw[2 * i + 1], a.ssum, a.g2in, a.xp2, a.hp2, a.hp2b, dout, dgin,
+                         dsum, nullptr, 0, w, s));
+  // gru1: input r0, its output gradient is dsum (the o1 branch of the sum)
+  bf16* dr0 = w.g128[0];  // (T,64) view of a free (T,128) buffer
+  TRY(gru_block_backward(prm, grd, sl.srb(i, TS_G1), w.gruw[2 * i], a.r0, a.g1in, a.xp1, a.hp1, a.hp1b, dsum, dgin, dr0,
+                         nullptr, 1, w, s));
+  bf16 *dc2 = w.g128[1], *da1 = w.g128[2], *dc1 = w.g128[1];
+  TRY(bn_backward(dr0, 64, a.c2, 64, a.st2, dc2, 64, T, 64, ACT_NONE, P<float>(grd, sl.srb(i, TS_BN2W)),
+                  P<float>(grd, sl.srb(i, TS_BN2B)), w.partial, w.coef, s));
+  if (grd[sl.srb(i, TS_C2W)]) TRY(conv3x3_wgrad(dc2, a.a1, B, 16, 64, 0, P<float>(grd, sl.srb(i, TS_C2W)), w.partial, s));
+  if (grd[sl.srb(i, TS_C2B)]) TRY(colsum(dc2, 64, T, 64, P<float>(grd, sl.srb(i, TS_C2B)), w.partial, s));
+  TcGemmParams p = gp();
+  p.out = da1;
+  TRY(map_conv(dc2, B, 16, 64, 3, 3, q.c2d, 64, p, s));
+  TRY(bn_backward(da1, 64, a.c1, 64, a.st1, dc1, 64, T, 64, ACT_MISH, P<float>(grd, sl.srb(i, TS_BN1W)),
+                  P<float>(grd, sl.srb(i, TS_BN1B)), w.partial, w.coef, s));
+  if (grd[sl.srb(i, TS_C1W)]) TRY(conv3x3_wgrad(dc1, x_in, B, 16, 64, 0, P<float>(grd, sl.srb(i, TS_C1W)), w.partial, s));
+  if (grd[sl.srb(i, TS_C1B)]) TRY(colsum(dc1, 64, T, 64, P<float>(grd, sl.srb(i, TS_C1B)), w.partial, s));
+  p = gp();
+  p.out = dx_out;
+  p.residual = dsum;  // x also feeds gru2 directly through the sum
+  return map_conv(dc1, B, 16, 64, 3, 3, q.c1d, 64, p, s);
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
 int forward(const Slots& sl, void* const* prm, const float* x_lr, float* sr_out, Ws& w, bool training, bool stn,
@@ -421,6 +587,11 @@ int forward(const Slots& sl, void* const* prm, const float* x_lr, float* sr_out,
   for (int i = 0; i < n; ++i) {
     SrbWs& a = w.srb[i];
     SrbW& q = w.srbw[i];
+    if (sl.arch == ARCH_TSRN) {
+      TRY(tsrn_srb_forward(sl, prm, i, x, w, training, s));
+      x = a.out;
+      continue;
+    }
     TcGemmParams p = gp();
     p.bias = P<float>(prm, sl.srb(i, S_C1B));
     p.out = a.c1;
@@ -566,6 +737,13 @@ int backward(const Slots& sl, void* const* prm, void* const* grd, const float* x
     SrbWs& a = w.srb[i];
     SrbW& q = w.srbw[i];
     const bf16* x_in = i > 0 ? w.srb[i - 1].out : w.b1;
+    if (sl.arch == ARCH_TSRN) {
+      TRY(tsrn_srb_backward(sl, prm, grd, i, x_in, dcur, dfree, w, s));
+      bf16* t = dcur;
+      dcur = dfree;
+      dfree = t;
+      continue;
+    }
     bf16 *gA = w.g128[0], *gB = w.g128[1], *gC = w.g128[2];
     TcGemmParams p = gp();
     // out = x + linear(y2)

@@ -17,9 +17,18 @@ enum Srb : int {
   S_LN1A, S_LN1B, S_W1W, S_W1B, S_W2W, S_W2B, S_LN3A, S_LN3B, S_LINW, S_LINB, S_COUNT
 };
 enum Bn : int { BN_W, BN_B, BN_RM, BN_RV, BN_NBT };
+// TSRN's SRB (scene-text-telescope/model/tsrn.py:77-98): conv/BN/mish/conv/BN + vertical BiGRU + horizontal BiGRU
+enum Gru : int { G_CW, G_CB, G_WIH, G_WHH, G_BIH, G_BHH, G_WIH_R, G_WHH_R, G_BIH_R, G_BHH_R, G_COUNT };
+enum TsrnSrb : int {
+  TS_C1W, TS_C1B, TS_BN1W, TS_BN1B, TS_BN1RM, TS_BN1RV, TS_BN1NBT, TS_G1,
+  TS_C2W = TS_G1 + G_COUNT, TS_C2B, TS_BN2W, TS_BN2B, TS_BN2RM, TS_BN2RV, TS_BN2NBT, TS_G2, TS_COUNT = TS_G2 + G_COUNT
+};
+enum Arch : int { ARCH_TBSRN = 0, ARCH_TSRN = 1 };
 
 struct Slots {
   int srb_nums;
+  int arch = ARCH_TBSRN;
+  int srb_stride = S_COUNT;
   int b1_w = 0, b1_b = 1, b1_a = 2;
   int srb0 = 3;
   int b7_w, b7_b, b7_bn;          // bn: +0 w, +1 b, +2 rm, +3 rv, +4 nbt
@@ -28,8 +37,9 @@ struct Slots {
   int fc1_w, fc1_b, bn1d, fc2_w, fc2_b;
   int tps_inv, tps_repr;
   int count;
-  explicit Slots(int n) : srb_nums(n) {
-    int i = srb0 + n * S_COUNT;
+  explicit Slots(int n, int arch_ = ARCH_TBSRN) : srb_nums(n), arch(arch_) {
+    srb_stride = arch == ARCH_TSRN ? (int)TS_COUNT : (int)S_COUNT;
+    int i = srb0 + n * srb_stride;
     b7_w = i++; b7_b = i++; b7_bn = i; i += 5;
     up_w = i++; up_b = i++; fin_w = i++; fin_b = i++;
     stn_conv0 = i; i += 6 * 7;
@@ -37,11 +47,11 @@ struct Slots {
     tps_inv = i++; tps_repr = i++;
     count = i;
   }
-  int srb(int blk, int s) const { return srb0 + blk * S_COUNT + s; }
+  int srb(int blk, int s) const { return srb0 + blk * srb_stride + s; }
   int stn(int conv, int j) const { return stn_conv0 + conv * 7 + j; }
 };
 
-std::vector<std::string> slot_names(int srb_nums);
+std::vector<std::string> slot_names(int srb_nums, int arch = ARCH_TBSRN);
 
 // ---- STN conv geometry ---------------------------------------------------------------------------
 struct StnConv {
@@ -56,6 +66,14 @@ static const StnConv kStn[6] = {
 struct SrbWs {
   bf16 *c1, *a1, *c2, *f, *qkv, *o, *y1pre, *y1, *hd, *y2pre, *y2, *out;
   float *lse, *st1, *st2;  // stats [4][64]
+  // TSRN: r0 = bn2(c2); per GRU block: conv1x1 output gin, projected input xp (T,192), output, saved h_{t-1}
+  bf16 *r0, *g1in, *xp1, *o1, *hp1b, *ssum, *g2in, *xp2, *hp2b;
+  float *hp1, *hp2;
+};
+struct GruW {  // prepared GRU-block weights
+  bf16 *cw, *cwT;      // conv1x1 [64][64] and transpose
+  bf16 *wih, *wihT;    // [192][64], [64][192]
+  float* bih;          // [192]
 };
 struct SrbW {  // prepared bf16 weights
   bf16 *c1f, *c1d, *c2f, *c2d;             // conv fwd / dgrad layouts [9][64][64]
@@ -83,6 +101,9 @@ struct Ws {
   bf16 *w_b1, *w_b1d;  // [9][64][64]
   std::vector<SrbWs> srb;
   std::vector<SrbW> srbw;
+  std::vector<GruW> gruw;  // 2 per SRB (TSRN)
+  bf16 *gdxp, *gdhid;      // (T,192) backward temporaries (TSRN)
+  int arch;
   bf16 *c7, *s7;       // conv7 output, b1 + bn7(c7)
   float* st7;
   bf16 *w7f, *w7d, *wupf, *wupd, *wfin, *wfind;
@@ -114,7 +135,7 @@ struct Ws {
 };
 
 // Carves the layout out of `base` (may be nullptr to only measure).  Deterministic in (B, srb_nums).
-void layout(Ws& w, int B, int srb_nums, void* base);
+void layout(Ws& w, int B, int srb_nums, void* base, int arch = ARCH_TBSRN);
 
 int forward(const Slots& sl, void* const* prm, const float* x_lr, float* sr_out, Ws& w, bool training, bool stn,
             float p_drop, uint32_t seed, cudaStream_t s);

@@ -189,36 +189,39 @@ class _EngineFn(torch.autograd.Function):
         return (None, None) + tuple(grads)
 
 
-class TBSRN(nn.Module):
-    def __init__(self, scale_factor=2, width=128, height=32, STN=True, srb_nums=5, mask=False, hidden_units=32,
-                 input_channel=3):
-        super().__init__()
-        if mask or input_channel != 3:
-            raise NotImplementedError("focr TBSRN: the 4-channel (mask=True) variant is not built; "
-                                      "reference default is mask=False (interfaces/base.py:141-142)")
-        if scale_factor != 2 or hidden_units != 32 or (width, height) != (128, 32):
-            # the reference hard-wires the 16x64 positional encoding and 64 channels (tbsrn.py:83)
-            raise NotImplementedError("focr TBSRN supports scale_factor=2, hidden_units=32, 128x32 only")
-        ch = 2 * hidden_units
-        self.conv = nn.Conv2d(input_channel, 3, 3, 1, 1)  # dead members kept for state_dict parity
-        self.bn = nn.BatchNorm2d(3)
-        self.relu = nn.ReLU()
-        self.block1 = _Seq(nn.Conv2d(3, ch, kernel_size=9, padding=4), nn.PReLU())
-        self.srb_nums = srb_nums
-        for i in range(srb_nums):
-            setattr(self, f"block{i + 2}", _SRB(ch))
-        setattr(self, f"block{srb_nums + 2}", _Seq(nn.Conv2d(ch, ch, kernel_size=3, padding=1), nn.BatchNorm2d(ch)))
-        setattr(self, f"block{srb_nums + 3}", _Seq(_Upsample(ch, 2), nn.Conv2d(ch, 3, kernel_size=9, padding=4)))
-        self.tps_inputsize = [height // scale_factor, width // scale_factor]
-        self.stn = STN
-        if self.stn:
-            self.tps = _TPS(tuple(self.tps_inputsize), 20, (0.05, 0.05))
-            self.stn_head = _STNHead(3, 20)
-        self._slot_names = [L.lib.focr_tbsrn_slot_name(srb_nums, i).decode()
-                            for i in range(L.lib.focr_tbsrn_num_slots(srb_nums))]
+class _SREngineModule(nn.Module):
+    """Shared plumbing of the engine-backed SR networks (TBSRN, TSRN): slot table, workspace, launches."""
+    _ARCH = "tbsrn"
+
+    def _engine_init(self, srb_nums: int):
+        lib = L.lib
+        if self._ARCH == "tsrn":
+            n = lib.focr_tsrn_num_slots(srb_nums)
+            self._slot_names = [lib.focr_tsrn_slot_name(srb_nums, i).decode() for i in range(n)]
+        else:
+            n = lib.focr_tbsrn_num_slots(srb_nums)
+            self._slot_names = [lib.focr_tbsrn_slot_name(srb_nums, i).decode() for i in range(n)]
         self._cache = None   # (slot tensors, pointer table) — invalidated by _apply (.to / .cuda / .float)
         self._ws: Dict[int, torch.Tensor] = {}
-        self._placeholders = None
+
+    def _ws_bytes(self, B: int) -> int:
+        if self._ARCH == "tsrn":
+            return L.lib.focr_tsrn_workspace_bytes(B, self.srb_nums)
+        return L.lib.focr_tbsrn_workspace_bytes(B, self.srb_nums)
+
+    def _c_forward(self, table, x, sr, B, flags, p, seed, ws):
+        if self._ARCH == "tsrn":
+            return L.lib.focr_tsrn_forward(table, x.data_ptr(), sr.data_ptr(), B, self.srb_nums, flags, ws.data_ptr(),
+                                           ws.numel(), L.cur_stream())
+        return L.lib.focr_tbsrn_forward(table, x.data_ptr(), sr.data_ptr(), B, self.srb_nums, flags, p, seed,
+                                        ws.data_ptr(), ws.numel(), L.cur_stream())
+
+    def _c_backward(self, table, gtable, x, d_sr, B, flags, p, seed, ws):
+        if self._ARCH == "tsrn":
+            return L.lib.focr_tsrn_backward(table, gtable, x.data_ptr(), d_sr.data_ptr(), B, self.srb_nums, flags,
+                                            ws.data_ptr(), ws.numel(), L.cur_stream())
+        return L.lib.focr_tbsrn_backward(table, gtable, x.data_ptr(), d_sr.data_ptr(), B, self.srb_nums, flags, p, seed,
+                                         ws.data_ptr(), ws.numel(), L.cur_stream())
 
     # -- plumbing --------------------------------------------------------------------------------
     def _apply(self, fn, *a, **k):
@@ -274,16 +277,16 @@ class TBSRN(nn.Module):
     def _workspace(self, B: int, device) -> torch.Tensor:
         ws = self._ws.get(B)
         if ws is None or ws.device != device:
-            nbytes = L.lib.focr_tbsrn_workspace_bytes(B, self.srb_nums)
+            nbytes = self._ws_bytes(B)
             ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
             self._ws = {B: ws}  # keep one batch size resident
         return ws
 
     def _launch_forward(self, x: torch.Tensor) -> dict:
         if not x.is_cuda:
-            raise L.FocrError("focr TBSRN runs on CUDA (sm_100a) only; move the input to the GPU")
+            raise L.FocrError(f"focr {type(self).__name__} runs on CUDA (sm_100a) only; move the input to the GPU")
         if x.dim() != 4 or tuple(x.shape[1:]) != (3, 16, 64):
-            raise ValueError(f"TBSRN expects (B,3,16,64) LR crops, got {tuple(x.shape)}")
+            raise ValueError(f"{type(self).__name__} expects (B,3,16,64) LR crops, got {tuple(x.shape)}")
         tensors, table = self._slots()
         x = x.detach().contiguous().float()
         B = x.shape[0]
@@ -294,8 +297,7 @@ class TBSRN(nn.Module):
         p = self.dropout_p if training else 0.0
         seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item()) if p > 0 else 0
         with torch.cuda.device(x.device):
-            L.check(L.lib.focr_tbsrn_forward(table, x.data_ptr(), sr.data_ptr(), B, self.srb_nums, flags, p, seed,
-                                             ws.data_ptr(), ws.numel(), L.cur_stream()), "focr_tbsrn_forward")
+            L.check(self._c_forward(table, x, sr, B, flags, p, seed, ws), f"focr_{self._ARCH}_forward")
         return {"x": x, "sr": sr, "ws": ws, "B": B, "flags": flags, "p": p, "seed": seed}
 
     def _launch_backward(self, st: dict, d_sr: torch.Tensor):
@@ -309,9 +311,8 @@ class TBSRN(nn.Module):
         gtable = (C.c_void_p * len(tensors))(*gptr)
         d_sr = d_sr.contiguous().float()
         with torch.cuda.device(d_sr.device):
-            L.check(L.lib.focr_tbsrn_backward(table, gtable, st["x"].data_ptr(), d_sr.data_ptr(), st["B"],
-                                              self.srb_nums, st["flags"], st["p"], st["seed"], st["ws"].data_ptr(),
-                                              st["ws"].numel(), L.cur_stream()), "focr_tbsrn_backward")
+            L.check(self._c_backward(table, gtable, st["x"], d_sr, st["B"], st["flags"], st["p"], st["seed"], st["ws"]),
+                    f"focr_{self._ARCH}_backward")
         return [v.view_as(tensors[i]) for i, v in zip(self._grad_slots, views)]
 
     # -- public API ------------------------------------------------------------------------------
@@ -320,3 +321,32 @@ class TBSRN(nn.Module):
         if self.training and torch.is_grad_enabled():
             return _EngineFn.apply(x, self, *[tensors[i] for i in self._grad_slots])
         return self._launch_forward(x)["sr"]
+
+
+class TBSRN(_SREngineModule):
+    def __init__(self, scale_factor=2, width=128, height=32, STN=True, srb_nums=5, mask=False, hidden_units=32,
+                 input_channel=3):
+        super().__init__()
+        if mask or input_channel != 3:
+            raise NotImplementedError("focr TBSRN: the 4-channel (mask=True) variant is not built; "
+                                      "reference default is mask=False (interfaces/base.py:141-142)")
+        if scale_factor != 2 or hidden_units != 32 or (width, height) != (128, 32):
+            # the reference hard-wires the 16x64 positional encoding and 64 channels (tbsrn.py:83)
+            raise NotImplementedError("focr TBSRN supports scale_factor=2, hidden_units=32, 128x32 only")
+        ch = 2 * hidden_units
+        self.conv = nn.Conv2d(input_channel, 3, 3, 1, 1)  # dead members kept for state_dict parity
+        self.bn = nn.BatchNorm2d(3)
+        self.relu = nn.ReLU()
+        self.block1 = _Seq(nn.Conv2d(3, ch, kernel_size=9, padding=4), nn.PReLU())
+        self.srb_nums = srb_nums
+        for i in range(srb_nums):
+            setattr(self, f"block{i + 2}", _SRB(ch))
+        setattr(self, f"block{srb_nums + 2}", _Seq(nn.Conv2d(ch, ch, kernel_size=3, padding=1), nn.BatchNorm2d(ch)))
+        setattr(self, f"block{srb_nums + 3}", _Seq(_Upsample(ch, 2), nn.Conv2d(ch, 3, kernel_size=9, padding=4)))
+        self.tps_inputsize = [height // scale_factor, width // scale_factor]
+        self.stn = STN
+        if self.stn:
+            self.tps = _TPS(tuple(self.tps_inputsize), 20, (0.05, 0.05))
+            self.stn_head = _STNHead(3, 20)
+        self._engine_init(srb_nums)
+

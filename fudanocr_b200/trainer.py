@@ -19,7 +19,7 @@ import torch
 import torch.distributed as dist
 
 from . import _lib as L
-from .model.tbsrn import TBSRN
+from .model.tbsrn import TBSRN, _SREngineModule
 
 _CHUNK = 65536
 
@@ -27,8 +27,8 @@ _CHUNK = 65536
 class TBSRNTrainer:
     def __init__(self, model: TBSRN, lr: float = 1e-4, betas=(0.5, 0.999), eps: float = 1e-8,
                  max_grad_norm: float = 0.25, loss_scale: float = 100.0, process_group=None):
-        if not isinstance(model, TBSRN):
-            raise TypeError("TBSRNTrainer drives fudanocr_b200.model.tbsrn.TBSRN")
+        if not isinstance(model, _SREngineModule):
+            raise TypeError("TBSRNTrainer drives the engine-backed SR models (fudanocr_b200.model.tbsrn.TBSRN / tsrn.TSRN)")
         self.model = model
         self.lr, self.betas, self.eps = lr, betas, eps
         self.max_grad_norm, self.loss_scale = max_grad_norm, loss_scale
@@ -91,13 +91,11 @@ class TBSRNTrainer:
             seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item()) if p > 0 else 0
         st = L.cur_stream()
         lib = L.lib
-        L.check(lib.focr_tbsrn_forward(self.ptable, images_lr.data_ptr(), self.sr.data_ptr(), B, m.srb_nums, flags, p,
-                                       seed, ws.data_ptr(), ws.numel(), st), "tbsrn_forward")
+        L.check(m._c_forward(self.ptable, images_lr, self.sr, B, flags, p, seed, ws), "sr_forward")
         L.check(lib.focr_mse_loss_grad(self.sr.data_ptr(), images_hr.data_ptr(), self.d_sr.data_ptr(),
                                        self.loss.data_ptr(), self.sr.numel(), self.loss_scale, self.scratch.data_ptr(),
                                        self.scratch.numel(), st), "mse_loss_grad")
-        L.check(lib.focr_tbsrn_backward(self.ptable, self.gtable, images_lr.data_ptr(), self.d_sr.data_ptr(), B,
-                                        m.srb_nums, flags, p, seed, ws.data_ptr(), ws.numel(), st), "tbsrn_backward")
+        L.check(m._c_backward(self.ptable, self.gtable, images_lr, self.d_sr, B, flags, p, seed, ws), "sr_backward")
         gscale = 1.0
         if self.world > 1:
             dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.pg)

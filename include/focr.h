@@ -88,6 +88,17 @@ int focr_tbsrn_forward(void* const* params, const float* x_lr, float* sr, int B,
                        unsigned seed, void* ws, size_t ws_bytes, void* stream);
 int focr_tbsrn_backward(void* const* params, void* const* grads, const float* x_lr, const float* d_sr, int B,
                         int srb_nums, int flags, float p_drop, unsigned seed, void* ws, size_t ws_bytes, void* stream);
+/* TSRN: STT/model/tsrn.py:18-74 (TSRN), :77-98 (RecurrentResidualBlock), :128-145 (GruBlock: conv1x1 + BiGRU(64,32));
+ * same conventions as the TBSRN entry points (slot i = state_dict entry focr_tsrn_slot_name(srb_nums, i)). */
+int focr_tsrn_num_slots(int srb_nums);
+const char* focr_tsrn_slot_name(int srb_nums, int idx);
+size_t focr_tsrn_workspace_bytes(int B, int srb_nums);
+int focr_tsrn_forward(void* const* params, const float* x_lr, float* sr, int B, int srb_nums, int flags, void* ws,
+                      size_t ws_bytes, void* stream);
+int focr_tsrn_backward(void* const* params, void* const* grads, const float* x_lr, const float* d_sr, int B,
+                       int srb_nums, int flags, void* ws, size_t ws_bytes, void* stream);
+int focr_tsrn_ws_tensor(int B, int srb_nums, const char* name, long long* byte_offset, long long* elems,
+                        int* elem_bytes);
 int focr_tbsrn_ws_tensor(int B, int srb_nums, const char* name, long long* byte_offset, long long* elems,
                          int* elem_bytes);
 

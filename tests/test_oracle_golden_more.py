@@ -1,0 +1,56 @@
+"""CPU: the CRNN and TSRN oracle restatements vs golden vectors recorded from the real reference modules."""
+import hashlib
+
+import torch
+
+from oracle import crnn_oracle as C
+from oracle import synth, tbsrn_oracle as O, tsrn_oracle as TS
+
+
+def _load(name):
+    path = synth.GOLDEN_DIR / name
+    sums = dict(reversed(ln.split()) for ln in (synth.GOLDEN_DIR / "SHA256SUMS").read_text().splitlines() if ln.strip())
+    assert hashlib.sha256(path.read_bytes()).hexdigest() == sums[name]
+    return torch.load(path, weights_only=False)
+
+
+def test_crnn_oracle_vs_reference_golden():
+    g = _load("crnn_b2.pt")
+    sd = synth.synth_state_dict(synth.load_spec("crnn"), seed=4321)
+    assert len(sd) == 49
+    gray = C.parse_crnn_data(g["sr"])
+    assert torch.equal(gray, g["gray"])
+    with torch.no_grad():
+        logits = C.crnn_forward(sd, gray)
+    assert torch.allclose(logits, g["logits"], atol=2e-5, rtol=1e-4)
+    assert torch.equal(C.greedy_path(logits), g["path"])
+    assert C.get_crnn_pred(logits.permute(1, 0, 2)) == g["strings"]
+    assert ["".join(C.ALPHABET[i] for i in C.ctc_collapse(p.tolist())) for p in g["path"]] == g["strings"]
+
+
+def test_ctc_collapse_cases():
+    assert C.ctc_collapse([0, 0, 0]) == []
+    assert C.ctc_collapse([3, 3, 3]) == [3]
+    assert C.ctc_collapse([3, 0, 3]) == [3, 3]
+    assert C.ctc_collapse([1, 1, 0, 0, 2, 2, 1]) == [1, 2, 1]
+
+
+def test_tsrn_oracle_vs_reference_golden():
+    g = _load("tsrn_b4.pt")
+    spec = synth.load_spec("tsrn")
+    assert len(spec) == 239
+    sd = synth.synth_state_dict(spec, seed=2468, computed=O.tps_buffers())
+    lr, hr = synth.synth_images(4)
+    with torch.no_grad():
+        assert torch.allclose(TS.tsrn_forward(sd, lr, training=False), g["eval_sr"], atol=2e-5, rtol=1e-4)
+    _, info = TS.train_step(sd, lr, hr, {})
+    assert torch.allclose(info["sr"], g["train_sr"], atol=2e-5, rtol=1e-4)
+    assert abs(info["grad_norm"].item() - g["grad_norm"].item()) < 1e-4 * g["grad_norm"].item()
+    for k, v in g["grads"].items():
+        assert torch.allclose(info["grads"][k], v, atol=1e-5 + 1e-4 * v.abs().max().item(), rtol=1e-3), k
+    gmax = max(g["grad_l2"].values())
+    for k, n in g["grad_l2"].items():
+        if n < 1e-5 * gmax:  # numerically-zero gradients (conv bias before a batch-stat BN) are rounding noise
+            assert info["grads"][k].norm().item() < 1e-4 * gmax, k
+        else:
+            assert abs(info["grads"][k].norm().item() - n) <= 1e-3 * n + 1e-6, k
