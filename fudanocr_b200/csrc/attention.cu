@@ -12,8 +12,13 @@
 //   backward: two passes without atomics -
 //     pass A (dQ)   : warp owns 16 query rows;  dS = P o (dP - D),  dQ = dS K
 //     pass B (dK,dV): warp owns 16 key rows;    works on S^T, dP^T; dV = Pd^T dO, dK = dS^T Q
-// Dropout uses the counter hash of common.cuh keyed on (b,h,q,k) so all three kernels regenerate the
-// same mask.
+// Dropout uses the counter hash of common.cuh keyed on (b,h,q,k).  The hash is ~60 % of the forward's
+// instruction stream, so when the caller provides a keep-bit buffer (1 bit per (b,h,q,k), B x 512 KB) the
+// forward stores its keep decisions in its own fragment layout - word [bh][q/16][k/64][lane], bit
+// 16*(q%16 >= 8) + 2*((k%64)/8) + (k&1), lane = (q%8)*4 + (k%8)/2 - and both backward passes test bits
+// instead of re-hashing (DROP = 2).  Without the buffer the backward regenerates the mask (DROP = 1).
+// The 1/(1-p) factor is folded into the output scales: P.V, dV accumulate kept probabilities unscaled,
+// dS = P o (keep o dP - D (1-p)) / (1-p).
 #include "kernels.cuh"
 
 namespace {
@@ -101,10 +106,10 @@ __device__ __forceinline__ float quad_max(float v) {
 }
 
 // ------------------------------------------------------------------------------------------
-template <bool DROP, int NW>
+template <int DROP, int NW>
 __global__ void __launch_bounds__(NW * 32, 1)
 attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __restrict__ lse2, uint32_t key,
-                uint32_t thresh16, float inv_keep) {
+                uint32_t thresh16, float inv_keep, uint32_t* __restrict__ drop_bits) {
   extern __shared__ __align__(128) uint8_t sm[];
   const uint32_t sK = smem_u32(sm), sV = sK + kTileBytes;
   const int bh = blockIdx.x, b = bh >> 2, h = bh & 3;
@@ -167,14 +172,24 @@ attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __r
       }
       if (DROP) {
         const uint32_t cb = (uint32_t)(kt * 32 + c);
+        uint32_t bits = 0;
 #pragma unroll
         for (int n = 0; n < 8; ++n) {
           const uint32_t h0 = drop_hash32(key, rb0 + cb + n * 4), h1 = drop_hash32(key, rb1 + cb + n * 4);
-          s[n][0] = (h0 & 0xFFFFu) >= thresh16 ? s[n][0] * inv_keep : 0.f;
-          s[n][1] = (h0 >> 16) >= thresh16 ? s[n][1] * inv_keep : 0.f;
-          s[n][2] = (h1 & 0xFFFFu) >= thresh16 ? s[n][2] * inv_keep : 0.f;
-          s[n][3] = (h1 >> 16) >= thresh16 ? s[n][3] * inv_keep : 0.f;
+          const bool k0 = (h0 & 0xFFFFu) >= thresh16, k1 = (h0 >> 16) >= thresh16;
+          const bool k2 = (h1 & 0xFFFFu) >= thresh16, k3 = (h1 >> 16) >= thresh16;
+          s[n][0] = k0 ? s[n][0] : 0.f;
+          s[n][1] = k1 ? s[n][1] : 0.f;
+          s[n][2] = k2 ? s[n][2] : 0.f;
+          s[n][3] = k3 ? s[n][3] : 0.f;
+          if (DROP == 2) {
+            if (k0) bits |= 1u << (2 * n);
+            if (k1) bits |= 2u << (2 * n);
+            if (k2) bits |= 0x10000u << (2 * n);
+            if (k3) bits |= 0x20000u << (2 * n);
+          }
         }
+        if (DROP == 2) drop_bits[(((size_t)bh * 64 + u) * 16 + kt) * 32 + lane] = bits;
       }
       uint32_t pa[4][4];
       pack_frags(pa, s);
@@ -182,7 +197,7 @@ attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __r
     }
     l0 = quad_sum(l0);
     l1 = quad_sum(l1);
-    const float i0 = 1.f / l0, i1 = 1.f / l1;
+    const float i0 = inv_keep / l0, i1 = inv_keep / l1;
     bf16* orow0 = out + ((long)b * kS + q0 + g) * kLdO + h * 32;
     bf16* orow1 = orow0 + 8 * kLdO;
 #pragma unroll
@@ -199,11 +214,11 @@ attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __r
 
 // ------------------------------------------------------------------------------------------
 // backward pass A: dQ (and D = rowsum(dO o O), written for pass B)
-template <bool DROP, int NW>
+template <int DROP, int NW>
 __global__ void __launch_bounds__(NW * 32, 1)
 attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o_in, const bf16* __restrict__ d_o,
                    const float* __restrict__ lse2, float* __restrict__ dsum, bf16* __restrict__ dqkv, uint32_t key,
-                   uint32_t thresh16, float inv_keep) {
+                   uint32_t thresh16, float inv_keep, const uint32_t* __restrict__ drop_bits) {
   extern __shared__ __align__(128) uint8_t sm[];
   const uint32_t sK = smem_u32(sm), sV = sK + kTileBytes;
   const int bh = blockIdx.x, b = bh >> 2, h = bh & 3;
@@ -245,9 +260,19 @@ attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o_in, 
 #pragma unroll
       for (int j = 0; j < 4; ++j) dq[i][j] = 0.f;
     const uint32_t rb0 = (uint32_t)(bh * kS + q0 + g) * 512u, rb1 = rb0 + 8u * 512u;
+    D0 *= 1.f / inv_keep;  // dS = P o (keep o dP - D (1-p)) / (1-p); the 1/(1-p) goes into the final scale
+    D1 *= 1.f / inv_keep;
+    const uint32_t* wb = drop_bits + ((size_t)bh * 64 + u) * 16 * 32 + lane;
+    uint32_t wnext = 0;
+    if (DROP == 2) wnext = __ldg(wb);
 
 #pragma unroll 1
     for (int kt = 0; kt < kS / 64; ++kt) {
+      uint32_t w = 0;
+      if (DROP == 2) {
+        w = wnext;
+        if (kt + 1 < kS / 64) wnext = __ldg(wb + (kt + 1) * 32);
+      }
       float s[8][4], dp[8][4];
 #pragma unroll
       for (int n = 0; n < 8; ++n) {
@@ -262,12 +287,17 @@ attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o_in, 
         const float p0 = ex2(fmaf(s[n][0], kScaleLog2, -L0)), p1 = ex2(fmaf(s[n][1], kScaleLog2, -L0));
         const float p2 = ex2(fmaf(s[n][2], kScaleLog2, -L1)), p3 = ex2(fmaf(s[n][3], kScaleLog2, -L1));
         float e0 = dp[n][0], e1 = dp[n][1], e2 = dp[n][2], e3 = dp[n][3];
-        if (DROP) {
+        if (DROP == 1) {
           const uint32_t h0 = drop_hash32(key, rb0 + cb + n * 4), h1 = drop_hash32(key, rb1 + cb + n * 4);
-          e0 = (h0 & 0xFFFFu) >= thresh16 ? e0 * inv_keep : 0.f;
-          e1 = (h0 >> 16) >= thresh16 ? e1 * inv_keep : 0.f;
-          e2 = (h1 & 0xFFFFu) >= thresh16 ? e2 * inv_keep : 0.f;
-          e3 = (h1 >> 16) >= thresh16 ? e3 * inv_keep : 0.f;
+          e0 = (h0 & 0xFFFFu) >= thresh16 ? e0 : 0.f;
+          e1 = (h0 >> 16) >= thresh16 ? e1 : 0.f;
+          e2 = (h1 & 0xFFFFu) >= thresh16 ? e2 : 0.f;
+          e3 = (h1 >> 16) >= thresh16 ? e3 : 0.f;
+        } else if (DROP == 2) {
+          e0 = (w & (1u << (2 * n))) ? e0 : 0.f;
+          e1 = (w & (2u << (2 * n))) ? e1 : 0.f;
+          e2 = (w & (0x10000u << (2 * n))) ? e2 : 0.f;
+          e3 = (w & (0x20000u << (2 * n))) ? e3 : 0.f;
         }
         s[n][0] = p0 * (e0 - D0);
         s[n][1] = p1 * (e1 - D0);
@@ -280,21 +310,22 @@ attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o_in, 
     }
     bf16* r0 = dqkv + t0 * kLdQkv + h * 32;
     bf16* r1 = r0 + 8 * kLdQkv;
+    const float osc = kScale * inv_keep;
 #pragma unroll
     for (int nd = 0; nd < 4; ++nd) {
-      *reinterpret_cast<uint32_t*>(r0 + nd * 8 + 2 * c) = pack_bf16x2(dq[nd][0] * kScale, dq[nd][1] * kScale);
-      *reinterpret_cast<uint32_t*>(r1 + nd * 8 + 2 * c) = pack_bf16x2(dq[nd][2] * kScale, dq[nd][3] * kScale);
+      *reinterpret_cast<uint32_t*>(r0 + nd * 8 + 2 * c) = pack_bf16x2(dq[nd][0] * osc, dq[nd][1] * osc);
+      *reinterpret_cast<uint32_t*>(r1 + nd * 8 + 2 * c) = pack_bf16x2(dq[nd][2] * osc, dq[nd][3] * osc);
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------
 // backward pass B: dK, dV (warp owns 16 key rows; everything is the transpose of pass A)
-template <bool DROP>
+template <int DROP>
 __global__ void __launch_bounds__(256, 1)
 attn_bwd_dkv_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ d_o, const float* __restrict__ lse2,
                     const float* __restrict__ dsum, bf16* __restrict__ dqkv, uint32_t key, uint32_t thresh16,
-                    float inv_keep) {
+                    float inv_keep, const uint32_t* __restrict__ drop_bits) {
   extern __shared__ __align__(128) uint8_t sm[];
   const uint32_t sQ = smem_u32(sm), sdO = sQ + kTileBytes;
   float* sL = reinterpret_cast<float*>(sm + 2 * kTileBytes);
@@ -307,7 +338,7 @@ attn_bwd_dkv_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ d_o, 
   cp_async_commit();
   for (int i = tid; i < kS; i += (int)blockDim.x) {
     sL[i] = lse2[(long)bh * kS + i];
-    sD[i] = dsum[(long)bh * kS + i];
+    sD[i] = dsum[(long)bh * kS + i] * (1.f / inv_keep);
   }
   cp_async_wait<0>();
   __syncthreads();
@@ -325,6 +356,10 @@ attn_bwd_dkv_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ d_o, 
     // element (kv, q): counter = (bh*1024 + q)*512 + kv/2, 16-bit lane = kv & 1
     const uint32_t kvh0 = (uint32_t)((kv0 + g) >> 1), kvh1 = (uint32_t)((kv0 + g + 8) >> 1);
     const int sh = ((kv0 + g) & 1) * 16;  // same parity for row g and g+8
+    // keep-bit words of the forward's fragment layout (see the file header): q -> (unit, half, lane group), kv -> bit
+    const uint32_t* wb = drop_bits + (size_t)bh * 64 * 16 * 32 + (kv0 >> 6) * 32 + (g >> 1);
+    const int wl0 = (2 * c) * 4, wl1 = (2 * c + 1) * 4;
+    const int shl = 2 * ((kv0 & 63) >> 3) + (g & 1);
 
 #pragma unroll 1
     for (int qt = 0; qt < kS / 64; ++qt) {
@@ -334,8 +369,23 @@ attn_bwd_dkv_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ d_o, 
         st[n][0] = st[n][1] = st[n][2] = st[n][3] = 0.f;
         dpt[n][0] = dpt[n][1] = dpt[n][2] = dpt[n][3] = 0.f;
       }
+      uint32_t wq[4][2];
+      if (DROP == 2) {
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          wq[m][0] = __ldg(wb + (qt * 4 + m) * 16 * 32 + wl0);
+          wq[m][1] = __ldg(wb + (qt * 4 + m) * 16 * 32 + wl1);
+        }
+      }
       mma_a_mt(st, ka, sQ, qt * 64, lane);
       mma_a_mt(dpt, va, sdO, qt * 64, lane);
+      if (DROP == 2) {
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          wq[m][0] >>= shl;
+          wq[m][1] >>= shl;
+        }
+      }
 #pragma unroll
       for (int n = 0; n < 8; ++n) {
         const int q = qt * 64 + n * 8 + 2 * c;
@@ -346,15 +396,25 @@ attn_bwd_dkv_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ d_o, 
         float e0 = dpt[n][0], e1 = dpt[n][1], e2 = dpt[n][2], e3 = dpt[n][3];
         float d0 = p0, d1 = p1, d2 = p2, d3 = p3;
         if (DROP) {
-          const uint32_t qb0 = (uint32_t)(bh * kS + q) * 512u, qb1 = qb0 + 512u;
-          const bool k0 = ((drop_hash32(key, qb0 + kvh0) >> sh) & 0xFFFFu) >= thresh16;
-          const bool k1 = ((drop_hash32(key, qb1 + kvh0) >> sh) & 0xFFFFu) >= thresh16;
-          const bool k2 = ((drop_hash32(key, qb0 + kvh1) >> sh) & 0xFFFFu) >= thresh16;
-          const bool k3 = ((drop_hash32(key, qb1 + kvh1) >> sh) & 0xFFFFu) >= thresh16;
-          e0 = k0 ? e0 * inv_keep : 0.f; d0 = k0 ? p0 * inv_keep : 0.f;
-          e1 = k1 ? e1 * inv_keep : 0.f; d1 = k1 ? p1 * inv_keep : 0.f;
-          e2 = k2 ? e2 * inv_keep : 0.f; d2 = k2 ? p2 * inv_keep : 0.f;
-          e3 = k3 ? e3 * inv_keep : 0.f; d3 = k3 ? p3 * inv_keep : 0.f;
+          bool k0, k1, k2, k3;
+          if (DROP == 1) {
+            const uint32_t qb0 = (uint32_t)(bh * kS + q) * 512u, qb1 = qb0 + 512u;
+            k0 = ((drop_hash32(key, qb0 + kvh0) >> sh) & 0xFFFFu) >= thresh16;
+            k1 = ((drop_hash32(key, qb1 + kvh0) >> sh) & 0xFFFFu) >= thresh16;
+            k2 = ((drop_hash32(key, qb0 + kvh1) >> sh) & 0xFFFFu) >= thresh16;
+            k3 = ((drop_hash32(key, qb1 + kvh1) >> sh) & 0xFFFFu) >= thresh16;
+          } else {
+            const uint32_t w0 = wq[n >> 1][0], w1 = wq[n >> 1][1];
+            const uint32_t b0 = (n & 1) ? 0x10000u : 1u, b2 = (n & 1) ? 0x40000u : 4u;
+            k0 = w0 & b0;
+            k1 = w1 & b0;
+            k2 = w0 & b2;
+            k3 = w1 & b2;
+          }
+          e0 = k0 ? e0 : 0.f; d0 = k0 ? p0 : 0.f;
+          e1 = k1 ? e1 : 0.f; d1 = k1 ? p1 : 0.f;
+          e2 = k2 ? e2 : 0.f; d2 = k2 ? p2 : 0.f;
+          e3 = k3 ? e3 : 0.f; d3 = k3 ? p3 : 0.f;
         }
         st[n][0] = p0 * (e0 - Dq.x);
         st[n][1] = p1 * (e1 - Dq.y);
@@ -373,12 +433,15 @@ attn_bwd_dkv_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ d_o, 
     }
     bf16* r0 = dqkv + ((long)b * kS + kv0 + g) * kLdQkv + h * 32;
     bf16* r1 = r0 + 8 * kLdQkv;
+    const float ksc = kScale * inv_keep;
 #pragma unroll
     for (int nd = 0; nd < 4; ++nd) {
-      *reinterpret_cast<uint32_t*>(r0 + 128 + nd * 8 + 2 * c) = pack_bf16x2(dk[nd][0] * kScale, dk[nd][1] * kScale);
-      *reinterpret_cast<uint32_t*>(r1 + 128 + nd * 8 + 2 * c) = pack_bf16x2(dk[nd][2] * kScale, dk[nd][3] * kScale);
-      *reinterpret_cast<uint32_t*>(r0 + 256 + nd * 8 + 2 * c) = pack_bf16x2(dv[nd][0], dv[nd][1]);
-      *reinterpret_cast<uint32_t*>(r1 + 256 + nd * 8 + 2 * c) = pack_bf16x2(dv[nd][2], dv[nd][3]);
+      *reinterpret_cast<uint32_t*>(r0 + 128 + nd * 8 + 2 * c) = pack_bf16x2(dk[nd][0] * ksc, dk[nd][1] * ksc);
+      *reinterpret_cast<uint32_t*>(r1 + 128 + nd * 8 + 2 * c) = pack_bf16x2(dk[nd][2] * ksc, dk[nd][3] * ksc);
+      *reinterpret_cast<uint32_t*>(r0 + 256 + nd * 8 + 2 * c) =
+          pack_bf16x2(dv[nd][0] * inv_keep, dv[nd][1] * inv_keep);
+      *reinterpret_cast<uint32_t*>(r1 + 256 + nd * 8 + 2 * c) =
+          pack_bf16x2(dv[nd][2] * inv_keep, dv[nd][3] * inv_keep);
     }
   }
 }
@@ -396,61 +459,80 @@ int set_smem(K kernel, int bytes) {
 
 }  // namespace
 
-// p_drop = thresh16 / 65536; thresh16 == 0 disables dropout (eval / parity runs)
-int attn_forward(const bf16* qkv, bf16* out, float* lse2, int B, uint32_t key, uint32_t thresh16, cudaStream_t s) {
+// p_drop = thresh16 / 65536; thresh16 == 0 disables dropout (eval / parity runs).  drop_bits: optional keep-bit
+// buffer of attn_drop_bits_bytes(B) bytes written by the forward and consumed by the backward (may be null).
+size_t attn_drop_bits_bytes(int B) { return (size_t)B * 4 * (kS / 16) * (kS / 64) * 32 * sizeof(uint32_t); }
+
+int attn_forward(const bf16* qkv, bf16* out, float* lse2, int B, uint32_t key, uint32_t thresh16, uint32_t* drop_bits,
+                 cudaStream_t s) {
   ProfScope _ps("attn_fwd", s);
   FOCR_REQUIRE(B >= 1 && B <= 1024, "attention: B=%d out of range", B);
   const int smem = 2 * kTileBytes;
   const float inv_keep = 65536.f / (65536.f - (float)thresh16);
   static bool init = false;
   if (!init) {
-    int rc = set_smem(attn_fwd_kernel<true, kFwdWarps>, smem);
+    int rc = set_smem(attn_fwd_kernel<0, kFwdWarps>, smem);
     if (rc) return rc;
-    rc = set_smem(attn_fwd_kernel<false, kFwdWarps>, smem);
+    rc = set_smem(attn_fwd_kernel<1, kFwdWarps>, smem);
+    if (rc) return rc;
+    rc = set_smem(attn_fwd_kernel<2, kFwdWarps>, smem);
     if (rc) return rc;
     init = true;
   }
-  if (thresh16)
-    attn_fwd_kernel<true, kFwdWarps><<<B * 4, kFwdWarps * 32, smem, s>>>(qkv, out, lse2, key, thresh16, inv_keep);
+  const dim3 grid(B * 4), block(kFwdWarps * 32);
+  if (!thresh16)
+    attn_fwd_kernel<0, kFwdWarps><<<grid, block, smem, s>>>(qkv, out, lse2, key, 0, 1.f, nullptr);
+  else if (!drop_bits)
+    attn_fwd_kernel<1, kFwdWarps><<<grid, block, smem, s>>>(qkv, out, lse2, key, thresh16, inv_keep, nullptr);
   else
-    attn_fwd_kernel<false, kFwdWarps><<<B * 4, kFwdWarps * 32, smem, s>>>(qkv, out, lse2, key, 0, 1.f);
+    attn_fwd_kernel<2, kFwdWarps><<<grid, block, smem, s>>>(qkv, out, lse2, key, thresh16, inv_keep, drop_bits);
   FOCR_LAUNCH_CHECK();
   return FOCR_OK;
 }
 
 int attn_backward(const bf16* qkv, const bf16* o, const bf16* d_o, const float* lse2, float* dsum, bf16* dqkv, int B,
-                  uint32_t key, uint32_t thresh16, cudaStream_t s) {
+                  uint32_t key, uint32_t thresh16, const uint32_t* drop_bits, cudaStream_t s) {
   FOCR_REQUIRE(B >= 1 && B <= 1024, "attention: B=%d out of range", B);
   const int smem_a = 2 * kTileBytes, smem_b = 2 * kTileBytes + 2 * kS * 4;
   const float inv_keep = 65536.f / (65536.f - (float)thresh16);
   static bool init = false;
   if (!init) {
-    int rc = set_smem(attn_bwd_dq_kernel<true, kDqWarps>, smem_a);
+    int rc = set_smem(attn_bwd_dq_kernel<0, kDqWarps>, smem_a);
     if (rc) return rc;
-    rc = set_smem(attn_bwd_dq_kernel<false, kDqWarps>, smem_a);
+    rc = set_smem(attn_bwd_dq_kernel<1, kDqWarps>, smem_a);
     if (rc) return rc;
-    rc = set_smem(attn_bwd_dkv_kernel<true>, smem_b);
+    rc = set_smem(attn_bwd_dq_kernel<2, kDqWarps>, smem_a);
     if (rc) return rc;
-    rc = set_smem(attn_bwd_dkv_kernel<false>, smem_b);
+    rc = set_smem(attn_bwd_dkv_kernel<0>, smem_b);
+    if (rc) return rc;
+    rc = set_smem(attn_bwd_dkv_kernel<1>, smem_b);
+    if (rc) return rc;
+    rc = set_smem(attn_bwd_dkv_kernel<2>, smem_b);
     if (rc) return rc;
     init = true;
   }
+  const dim3 grid(B * 4);
   {
     ProfScope ps("attn_bwd_dq", s);
-    if (thresh16)
-      attn_bwd_dq_kernel<true, kDqWarps><<<B * 4, kDqWarps * 32, smem_a, s>>>(qkv, o, d_o, lse2, dsum, dqkv, key,
-                                                                             thresh16, inv_keep);
+    if (!thresh16)
+      attn_bwd_dq_kernel<0, kDqWarps><<<grid, kDqWarps * 32, smem_a, s>>>(qkv, o, d_o, lse2, dsum, dqkv, key, 0, 1.f,
+                                                                          nullptr);
+    else if (!drop_bits)
+      attn_bwd_dq_kernel<1, kDqWarps><<<grid, kDqWarps * 32, smem_a, s>>>(qkv, o, d_o, lse2, dsum, dqkv, key, thresh16,
+                                                                          inv_keep, nullptr);
     else
-      attn_bwd_dq_kernel<false, kDqWarps><<<B * 4, kDqWarps * 32, smem_a, s>>>(qkv, o, d_o, lse2, dsum, dqkv, key, 0,
-                                                                              1.f);
+      attn_bwd_dq_kernel<2, kDqWarps><<<grid, kDqWarps * 32, smem_a, s>>>(qkv, o, d_o, lse2, dsum, dqkv, key, thresh16,
+                                                                          inv_keep, drop_bits);
     FOCR_LAUNCH_CHECK();
   }
   {
     ProfScope ps("attn_bwd_dkv", s);
-    if (thresh16)
-      attn_bwd_dkv_kernel<true><<<B * 4, 256, smem_b, s>>>(qkv, d_o, lse2, dsum, dqkv, key, thresh16, inv_keep);
+    if (!thresh16)
+      attn_bwd_dkv_kernel<0><<<grid, 256, smem_b, s>>>(qkv, d_o, lse2, dsum, dqkv, key, 0, 1.f, nullptr);
+    else if (!drop_bits)
+      attn_bwd_dkv_kernel<1><<<grid, 256, smem_b, s>>>(qkv, d_o, lse2, dsum, dqkv, key, thresh16, inv_keep, nullptr);
     else
-      attn_bwd_dkv_kernel<false><<<B * 4, 256, smem_b, s>>>(qkv, d_o, lse2, dsum, dqkv, key, 0, 1.f);
+      attn_bwd_dkv_kernel<2><<<grid, 256, smem_b, s>>>(qkv, d_o, lse2, dsum, dqkv, key, thresh16, inv_keep, drop_bits);
     FOCR_LAUNCH_CHECK();
   }
   return FOCR_OK;

@@ -222,16 +222,19 @@ int focr_layernorm_std_bwd(const void* dy, const void* x, const float* a, void* 
 // fused 4-head self-attention over 1024 tokens, d_k = 32.  qkv (B*1024, 384) bf16, out (B*1024,128) bf16,
 // lse2 fp32 (B*4*1024) (log2-domain log-sum-exp, needed by bwd).  p_drop in [0,1): dropout on P.
 // ---------------------------------------------------------------------------------------------
+size_t focr_mha_drop_bits_bytes(int B) { return attn_drop_bits_bytes(B); }
 int focr_mha_flash_fwd(const void* qkv, void* out, float* lse2, int B, float p_drop, unsigned seed, unsigned stream_id,
-                       void* stream) {
+                       void* drop_bits, void* stream) {
   const uint32_t th = p_drop > 0.f ? (uint32_t)(p_drop * 65536.0 + 0.5) : 0;
-  return attn_forward((const bf16*)qkv, (bf16*)out, lse2, B, drop_key(seed, stream_id), th, (cudaStream_t)stream);
+  return attn_forward((const bf16*)qkv, (bf16*)out, lse2, B, drop_key(seed, stream_id), th, (uint32_t*)drop_bits,
+                      (cudaStream_t)stream);
 }
 int focr_mha_flash_bwd(const void* qkv, const void* out, const void* d_out, const float* lse2, float* dsum_ws,
-                       void* dqkv, int B, float p_drop, unsigned seed, unsigned stream_id, void* stream) {
+                       void* dqkv, int B, float p_drop, unsigned seed, unsigned stream_id, const void* drop_bits,
+                       void* stream) {
   const uint32_t th = p_drop > 0.f ? (uint32_t)(p_drop * 65536.0 + 0.5) : 0;
   return attn_backward((const bf16*)qkv, (const bf16*)out, (const bf16*)d_out, lse2, dsum_ws, (bf16*)dqkv, B,
-                       drop_key(seed, stream_id), th, (cudaStream_t)stream);
+                       drop_key(seed, stream_id), th, (const uint32_t*)drop_bits, (cudaStream_t)stream);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -42,9 +42,11 @@ int mish_backward(const bf16* dy, const bf16* x, bf16* dx, long n, cudaStream_t 
 int pe_table(bf16* pe, cudaStream_t s);
 
 // attention.cu
-int attn_forward(const bf16* qkv, bf16* out, float* lse2, int B, uint32_t key, uint32_t thresh16, cudaStream_t s);
+size_t attn_drop_bits_bytes(int B);
+int attn_forward(const bf16* qkv, bf16* out, float* lse2, int B, uint32_t key, uint32_t thresh16, uint32_t* drop_bits,
+                 cudaStream_t s);
 int attn_backward(const bf16* qkv, const bf16* o, const bf16* d_o, const float* lse2, float* dsum, bf16* dqkv, int B,
-                  uint32_t key, uint32_t thresh16, cudaStream_t s);
+                  uint32_t key, uint32_t thresh16, const uint32_t* drop_bits, cudaStream_t s);
 
 // wgrad.cu
 int linear_wgrad_splits(long T, int N);

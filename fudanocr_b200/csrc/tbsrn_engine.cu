@@ -184,6 +184,7 @@ void layout(Ws& w, int B, int n, void* base, int arch) {
     s.y2pre = b.get<bf16>(T * 128);
     s.y2 = b.get<bf16>(T * 128);
     s.lse = b.get<float>((long)B * 4 * 1024);
+    s.dropbits = b.get<uint32_t>((long)(attn_drop_bits_bytes(B) / 4));
     q.qkv = b.get<bf16>(384 * 128);
     q.qkvT = b.get<bf16>(384 * 128);
     q.wo = b.get<bf16>(128 * 128);
@@ -609,7 +610,7 @@ int forward(const Slots& sl, void* const* prm, const float* x_lr, float* sr_out,
     p.bias = q.bqkv;
     p.out = a.qkv;
     TRY(tok_gemm(a.f, 128, T, q.qkv, 384, p, s));
-    TRY(attn_forward(a.qkv, a.o, a.lse, B, drop_key(seed, 2 * i), th, s));
+    TRY(attn_forward(a.qkv, a.o, a.lse, B, drop_key(seed, 2 * i), th, a.dropbits, s));
     p = gp();
     p.bias = P<float>(prm, sl.srb(i, S_LOB));
     p.out = a.y1pre;
@@ -771,7 +772,7 @@ int backward(const Slots& sl, void* const* prm, void* const* grd, const float* x
     p.out = gC;
     TRY(tok_gemm(gB, 128, T, q.woT, 128, p, s));
     TRY(lin_grads(gB, 128, a.o, T, 128, grd, sl.srb(i, S_LOW), sl.srb(i, S_LOB), w, s));
-    TRY(attn_backward(a.qkv, a.o, gC, a.lse, w.dsum, w.g384, B, drop_key(seed, 2 * i), th, s));
+    TRY(attn_backward(a.qkv, a.o, gC, a.lse, w.dsum, w.g384, B, drop_key(seed, 2 * i), th, a.dropbits, s));
     p = gp();
     p.out = gA;
     p.residual = gB;

@@ -66,6 +66,7 @@ static const StnConv kStn[6] = {
 struct SrbWs {
   bf16 *c1, *a1, *c2, *f, *qkv, *o, *y1pre, *y1, *hd, *y2pre, *y2, *out;
   float *lse, *st1, *st2;  // stats [4][64]
+  uint32_t* dropbits;      // attention keep bits, 1 per (b,h,q,k)
   // TSRN: r0 = bn2(c2); per GRU block: conv1x1 output gin, projected input xp (T,192), output, saved h_{t-1}
   bf16 *r0, *g1in, *xp1, *o1, *hp1b, *ssum, *g2in, *xp2, *hp2b;
   float *hp1, *hp2;

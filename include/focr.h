@@ -64,12 +64,16 @@ int focr_layernorm_std_bwd(const void* dy, const void* x, const float* a, void* 
                            float eps, void* ws, size_t ws_bytes, void* stream);
 
 /* --- MultiHeadedAttention core, h = 4, d_k = 32, 1024 tokens: STT/model/tbsrn.py:109-150 ------------------------
- * qkv (B*1024,384) bf16 = [q|k|v]; out (B*1024,128); lse2 fp32 (B*4*1024).  Dropout on P with rate p_drop,
- * mask regenerated in backward from (seed, stream_id). */
+ * qkv (B*1024,384) bf16 = [q|k|v]; out (B*1024,128); lse2 fp32 (B*4*1024).  Dropout on P with rate p_drop; the
+ * keep mask is a counter hash of (seed, stream_id, b, h, q, k).  drop_bits (device, focr_mha_drop_bits_bytes(B)
+ * bytes, or NULL): when given, the forward stores its keep decisions there (1 bit per element) and the backward
+ * reads them instead of re-hashing (the fast path); with NULL the backward regenerates the mask from the seed. */
+size_t focr_mha_drop_bits_bytes(int B);
 int focr_mha_flash_fwd(const void* qkv, void* out, float* lse2, int B, float p_drop, unsigned seed, unsigned stream_id,
-                       void* stream);
+                       void* drop_bits, void* stream);
 int focr_mha_flash_bwd(const void* qkv, const void* out, const void* d_out, const float* lse2, float* dsum_ws,
-                       void* dqkv, int B, float p_drop, unsigned seed, unsigned stream_id, void* stream);
+                       void* dqkv, int B, float p_drop, unsigned seed, unsigned stream_id, const void* drop_bits,
+                       void* stream);
 
 /* --- step body: STT/interfaces/super_resolution.py:69-84, STT/loss/text_focus_loss.py:86, base.py:194-198 ------ */
 int focr_mse_loss_grad(const float* sr, const float* hr, float* d_sr, float* loss, long n, float gscale, void* ws,

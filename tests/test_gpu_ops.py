@@ -114,8 +114,10 @@ def _attn_ref(qkv, B, keep=None, scale_keep=1.0):
     return torch.matmul(p, v).transpose(1, 2).reshape(B * 1024, 128)
 
 
-@pytest.mark.parametrize("B,p_drop", [(2, 0.0), (1, 0.1), (3, 0.0)])
-def test_attention_fwd_bwd(B, p_drop):
+@pytest.mark.parametrize("B,p_drop,use_bits", [(2, 0.0, False), (1, 0.1, False), (3, 0.0, True), (2, 0.1, True)])
+def test_attention_fwd_bwd(B, p_drop, use_bits):
+    """use_bits: the forward stores its keep decisions (1 bit per element) and the backward reads them (the path the
+    engine uses); otherwise the backward regenerates the mask from the seed.  Both must match the numpy twin."""
     L = _L()
     from oracle import dropout_rng as R
     T = B * 1024
@@ -124,10 +126,22 @@ def test_attention_fwd_bwd(B, p_drop):
     out = torch.empty(T, 128, dtype=torch.bfloat16, device=DEV)
     lse = torch.empty(B * 4 * 1024, device=DEV)
     seed, blk = 1234, 3
-    L.check(L.lib.focr_mha_flash_fwd(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, p_drop, seed, 2 * blk,
+    nb = L.lib.focr_mha_drop_bits_bytes(B)
+    assert nb == B * 4 * 1024 * 1024 // 8
+    bits = torch.zeros(nb // 4, dtype=torch.int32, device=DEV) if use_bits else None
+    bp = bits.data_ptr() if use_bits else None
+    L.check(L.lib.focr_mha_flash_fwd(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, p_drop, seed, 2 * blk, bp,
                                      L.cur_stream()))
     _sync(L)
     keep = R.attn_keep_mask(B, seed, blk, p_drop).to(DEV) if p_drop > 0 else None
+    if use_bits and p_drop > 0:
+        # decode the fragment-layout words back to a (B,4,1024,1024) mask: word [bh][q/16][k/64][lane=(q%8)*4+(k%8)/2],
+        # bit 16*((q%16)//8) + 2*((k%64)//8) + (k&1)
+        w = bits.view(B, 4, 64, 16, 8, 4).long() & 0xFFFFFFFF        # [b,h,u,kt,g,c]
+        sh = torch.arange(32, device=DEV).view(2, 8, 2)               # [half, n, j]
+        m = (w[..., None, None, None] >> sh) & 1                      # [b,h,u,kt,g,c,half,n,j]
+        m = m.permute(0, 1, 2, 6, 4, 3, 7, 5, 8).reshape(B, 4, 1024, 1024)   # q=(u,half,g)  k=(kt,n,c,j)
+        assert torch.equal(m.bool(), keep.bool())
     qr = qkv.float().requires_grad_(True)
     ref = _attn_ref(qr, B, keep, R.keep_scale(p_drop))
     assert _rel(out, ref) < 1e-2, _rel(out, ref)
@@ -140,7 +154,7 @@ def test_attention_fwd_bwd(B, p_drop):
     dqkv = torch.empty_like(qkv)
     dsum = torch.empty(B * 4 * 1024, device=DEV)
     L.check(L.lib.focr_mha_flash_bwd(qkv.data_ptr(), out.data_ptr(), d_out.data_ptr(), lse.data_ptr(), dsum.data_ptr(),
-                                     dqkv.data_ptr(), B, p_drop, seed, 2 * blk, L.cur_stream()))
+                                     dqkv.data_ptr(), B, p_drop, seed, 2 * blk, bp, L.cur_stream()))
     _sync(L)
     for i, nm in enumerate("qkv"):
         e = _rel(dqkv[:, i * 128:(i + 1) * 128], qr.grad[:, i * 128:(i + 1) * 128])
@@ -156,7 +170,7 @@ def test_attention_dropout_statistics():
     qkv = _bf(qkv)
     out = torch.empty(B * 1024, 128, dtype=torch.bfloat16, device=DEV)
     lse = torch.empty(B * 4 * 1024, device=DEV)
-    L.check(L.lib.focr_mha_flash_fwd(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, 0.1, 77, 0, L.cur_stream()))
+    L.check(L.lib.focr_mha_flash_fwd(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, 0.1, 77, 0, None, L.cur_stream()))
     _sync(L)
     o = out.float()
     assert abs(o.mean().item() - 1.0) < 2e-3          # unbiased
