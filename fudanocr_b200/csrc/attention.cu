@@ -213,6 +213,51 @@ attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __r
 }
 
 // ------------------------------------------------------------------------------------------
+// Backward kernels.  Both are latency-bound at 2 warps per scheduler (the S -> exp -> dS -> MMA chain is serial
+// inside a warp), so they walk the other sequence dimension in 32-wide steps, software-pipelined by hand: the
+// QK^T / dO V^T MMAs of step i+1 are issued before the softmax arithmetic of step i (two register buffers A/B).
+template <int NT>
+__device__ __forceinline__ void mma_a_mt_t(float (&acc)[NT][4], const uint32_t (&a)[2][4], uint32_t sbase, int row0,
+                                           int lane) {
+#pragma unroll
+  for (int n = 0; n < NT; ++n) {
+    uint32_t r[4];
+    ldmatrix_x4(r, sbase + sw_off(row0 + n * 8 + (lane & 7), lane >> 3));
+    const uint32_t b0[2] = {r[0], r[1]}, b1[2] = {r[2], r[3]};
+    mma_bf16_16816(acc[n], a[0], b0);
+    mma_bf16_16816(acc[n], a[1], b1);
+  }
+}
+template <int KK>
+__device__ __forceinline__ void mma_p_m_t(float (&acc)[4][4], const uint32_t (&pa)[KK][4], uint32_t sbase, int row0,
+                                          int lane) {
+#pragma unroll
+  for (int kk = 0; kk < KK; ++kk) {
+    const int row = row0 + kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+#pragma unroll
+    for (int nd = 0; nd < 4; nd += 2) {
+      uint32_t r[4];
+      ldmatrix_x4_trans(r, sbase + sw_off(row, nd + (lane >> 4)));
+      const uint32_t b0[2] = {r[0], r[1]}, b1[2] = {r[2], r[3]};
+      mma_bf16_16816(acc[nd], pa[kk], b0);
+      mma_bf16_16816(acc[nd + 1], pa[kk], b1);
+    }
+  }
+}
+__device__ __forceinline__ void pack_frags2(uint32_t (&pa)[2][4], const float (&s)[4][4]) {
+#pragma unroll
+  for (int kk = 0; kk < 2; ++kk) {
+    pa[kk][0] = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
+    pa[kk][1] = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
+    pa[kk][2] = pack_bf16x2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+    pa[kk][3] = pack_bf16x2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+  }
+}
+__device__ __forceinline__ void zero44(float (&x)[4][4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) x[i][0] = x[i][1] = x[i][2] = x[i][3] = 0.f;
+}
+
 // backward pass A: dQ (and D = rowsum(dO o O), written for pass B)
 template <int DROP, int NW>
 __global__ void __launch_bounds__(NW * 32, 1)
@@ -253,37 +298,25 @@ attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o_in, 
       dsum[(long)bh * kS + q0 + g] = D0;
       dsum[(long)bh * kS + q0 + g + 8] = D1;
     }
-    const float L0 = lse2[(long)bh * kS + q0 + g], L1 = lse2[(long)bh * kS + q0 + g + 8];
-    float dq[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) dq[i][j] = 0.f;
-    const uint32_t rb0 = (uint32_t)(bh * kS + q0 + g) * 512u, rb1 = rb0 + 8u * 512u;
     D0 *= 1.f / inv_keep;  // dS = P o (keep o dP - D (1-p)) / (1-p); the 1/(1-p) goes into the final scale
     D1 *= 1.f / inv_keep;
+    const float L0 = lse2[(long)bh * kS + q0 + g], L1 = lse2[(long)bh * kS + q0 + g + 8];
+    float dq[4][4];
+    zero44(dq);
+    const uint32_t rb0 = (uint32_t)(bh * kS + q0 + g) * 512u, rb1 = rb0 + 8u * 512u;
     const uint32_t* wb = drop_bits + ((size_t)bh * 64 + u) * 16 * 32 + lane;
-    uint32_t wnext = 0;
-    if (DROP == 2) wnext = __ldg(wb);
 
-#pragma unroll 1
-    for (int kt = 0; kt < kS / 64; ++kt) {
-      uint32_t w = 0;
-      if (DROP == 2) {
-        w = wnext;
-        if (kt + 1 < kS / 64) wnext = __ldg(wb + (kt + 1) * 32);
-      }
-      float s[8][4], dp[8][4];
+    auto compute = [&](float (&s)[4][4], float (&dp)[4][4], int row0) {
+      zero44(s);
+      zero44(dp);
+      mma_a_mt_t<4>(s, qa, sK, row0, lane);
+      mma_a_mt_t<4>(dp, da, sV, row0, lane);
+    };
+    // nb: 0 for the even 32-step of a 64-wide bit word, 4 for the odd one
+    auto process = [&](float (&s)[4][4], float (&dp)[4][4], int row0, uint32_t w, const int nb) {
+      const uint32_t cb = (uint32_t)(row0 >> 1) + c;
 #pragma unroll
-      for (int n = 0; n < 8; ++n) {
-        s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
-        dp[n][0] = dp[n][1] = dp[n][2] = dp[n][3] = 0.f;
-      }
-      mma_a_mt(s, qa, sK, kt * 64, lane);
-      mma_a_mt(dp, da, sV, kt * 64, lane);
-      const uint32_t cb = (uint32_t)(kt * 32 + c);
-#pragma unroll
-      for (int n = 0; n < 8; ++n) {
+      for (int n = 0; n < 4; ++n) {
         const float p0 = ex2(fmaf(s[n][0], kScaleLog2, -L0)), p1 = ex2(fmaf(s[n][1], kScaleLog2, -L0));
         const float p2 = ex2(fmaf(s[n][2], kScaleLog2, -L1)), p3 = ex2(fmaf(s[n][3], kScaleLog2, -L1));
         float e0 = dp[n][0], e1 = dp[n][1], e2 = dp[n][2], e3 = dp[n][3];
@@ -294,19 +327,39 @@ attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o_in, 
           e2 = (h1 & 0xFFFFu) >= thresh16 ? e2 : 0.f;
           e3 = (h1 >> 16) >= thresh16 ? e3 : 0.f;
         } else if (DROP == 2) {
-          e0 = (w & (1u << (2 * n))) ? e0 : 0.f;
-          e1 = (w & (2u << (2 * n))) ? e1 : 0.f;
-          e2 = (w & (0x10000u << (2 * n))) ? e2 : 0.f;
-          e3 = (w & (0x20000u << (2 * n))) ? e3 : 0.f;
+          e0 = (w & (1u << (2 * (n + nb)))) ? e0 : 0.f;
+          e1 = (w & (2u << (2 * (n + nb)))) ? e1 : 0.f;
+          e2 = (w & (0x10000u << (2 * (n + nb)))) ? e2 : 0.f;
+          e3 = (w & (0x20000u << (2 * (n + nb)))) ? e3 : 0.f;
         }
         s[n][0] = p0 * (e0 - D0);
         s[n][1] = p1 * (e1 - D0);
         s[n][2] = p2 * (e2 - D1);
         s[n][3] = p3 * (e3 - D1);
       }
-      uint32_t pa[4][4];
-      pack_frags(pa, s);
-      mma_p_m(dq, pa, sK, kt * 64, lane);
+      uint32_t pa[2][4];
+      pack_frags2(pa, s);
+      mma_p_m_t<2>(dq, pa, sK, row0, lane);
+    };
+
+    float sA[4][4], dA[4][4], sB[4][4], dB[4][4];
+    uint32_t w = 0, w1 = 0, w2 = 0;  // bit words of tiles kt, kt+1, kt+2 (loads run two tiles ahead)
+    if (DROP == 2) {
+      w1 = __ldg(wb);
+      w2 = __ldg(wb + 32);
+    }
+    compute(sA, dA, 0);
+#pragma unroll 1
+    for (int kt = 0; kt < kS / 64; ++kt) {
+      if (DROP == 2) {
+        w = w1;
+        w1 = w2;
+        if (kt + 2 < kS / 64) w2 = __ldg(wb + (kt + 2) * 32);
+      }
+      compute(sB, dB, kt * 64 + 32);
+      process(sA, dA, kt * 64, w, 0);
+      if (kt + 1 < kS / 64) compute(sA, dA, kt * 64 + 64);
+      process(sB, dB, kt * 64 + 32, w, 4);
     }
     bf16* r0 = dqkv + t0 * kLdQkv + h * 32;
     bf16* r1 = r0 + 8 * kLdQkv;
@@ -330,11 +383,22 @@ attn_bwd_dkv_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ d_o, 
   const uint32_t sQ = smem_u32(sm), sdO = sQ + kTileBytes;
   float* sL = reinterpret_cast<float*>(sm + 2 * kTileBytes);
   float* sD = sL + kS;
+  // DROP == 2: keep-bit words of the current 128-key block, all 64 query units x 2 key tiles x 32 lanes, double-buffered
+  uint32_t* sW = reinterpret_cast<uint32_t*>(sD + kS);
   const int bh = blockIdx.x, b = bh >> 2, h = bh & 3;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, c = lane & 3;
   const bf16* base = qkv + (long)b * kS * kLdQkv + h * 32;
+  auto load_bits = [&](int kb) {
+    if (DROP == 2) {
+      const uint32_t dst = smem_u32(sW) + (kb & 1) * 16384;
+      const uint32_t* src = drop_bits + ((size_t)bh * 64 * 16 + 2 * kb) * 32;
+      for (int i = tid; i < 1024; i += 256)
+        cp_async_16(dst + (i >> 4) * 256 + (i & 15) * 16, src + (size_t)(i >> 4) * 512 + (i & 15) * 4, true);
+    }
+  };
   load_head_tile(sQ, base, kLdQkv, tid);
   load_head_tile(sdO, d_o + (long)b * kS * kLdO + h * 32, kLdO, tid);
+  load_bits(0);
   cp_async_commit();
   for (int i = tid; i < kS; i += (int)blockDim.x) {
     sL[i] = lse2[(long)bh * kS + i];
@@ -344,51 +408,45 @@ attn_bwd_dkv_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ d_o, 
   __syncthreads();
 
   for (int kb = 0; kb < kS / 128; ++kb) {
+    if (DROP == 2) {
+      cp_async_wait<0>();
+      __syncthreads();  // this block's bit words landed, and every warp is done with the buffer refilled next
+      if (kb + 1 < kS / 128) load_bits(kb + 1);
+      cp_async_commit();
+    }
     const int kv0 = kb * 128 + warp * 16;
     uint32_t ka[2][4], va[2][4];
     load_a_frags(ka, base + 128 + (long)(kv0 + g) * kLdQkv, kLdQkv, c);
     load_a_frags(va, base + 256 + (long)(kv0 + g) * kLdQkv, kLdQkv, c);
     float dk[4][4], dv[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) dk[i][j] = dv[i][j] = 0.f;
+    zero44(dk);
+    zero44(dv);
     // element (kv, q): counter = (bh*1024 + q)*512 + kv/2, 16-bit lane = kv & 1
     const uint32_t kvh0 = (uint32_t)((kv0 + g) >> 1), kvh1 = (uint32_t)((kv0 + g + 8) >> 1);
     const int sh = ((kv0 + g) & 1) * 16;  // same parity for row g and g+8
     // keep-bit words of the forward's fragment layout (see the file header): q -> (unit, half, lane group), kv -> bit
-    const uint32_t* wb = drop_bits + (size_t)bh * 64 * 16 * 32 + (kv0 >> 6) * 32 + (g >> 1);
+    const uint32_t* wb = sW + (kb & 1) * 4096 + (warp >> 2) * 32 + (g >> 1);
     const int wl0 = (2 * c) * 4, wl1 = (2 * c + 1) * 4;
     const int shl = 2 * ((kv0 & 63) >> 3) + (g & 1);
 
-#pragma unroll 1
-    for (int qt = 0; qt < kS / 64; ++qt) {
-      float st[8][4], dpt[8][4];
-#pragma unroll
-      for (int n = 0; n < 8; ++n) {
-        st[n][0] = st[n][1] = st[n][2] = st[n][3] = 0.f;
-        dpt[n][0] = dpt[n][1] = dpt[n][2] = dpt[n][3] = 0.f;
-      }
-      uint32_t wq[4][2];
+    // step qs covers query rows [qs*32, qs*32+32): two forward units, one pair of bit words each
+    auto compute = [&](float (&st)[4][4], float (&dpt)[4][4], uint32_t (&wq)[2][2], int qs) {
       if (DROP == 2) {
 #pragma unroll
-        for (int m = 0; m < 4; ++m) {
-          wq[m][0] = __ldg(wb + (qt * 4 + m) * 16 * 32 + wl0);
-          wq[m][1] = __ldg(wb + (qt * 4 + m) * 16 * 32 + wl1);
+        for (int m = 0; m < 2; ++m) {
+          wq[m][0] = wb[(qs * 2 + m) * 64 + wl0];
+          wq[m][1] = wb[(qs * 2 + m) * 64 + wl1];
         }
       }
-      mma_a_mt(st, ka, sQ, qt * 64, lane);
-      mma_a_mt(dpt, va, sdO, qt * 64, lane);
-      if (DROP == 2) {
+      zero44(st);
+      zero44(dpt);
+      mma_a_mt_t<4>(st, ka, sQ, qs * 32, lane);
+      mma_a_mt_t<4>(dpt, va, sdO, qs * 32, lane);
+    };
+    auto process = [&](float (&st)[4][4], float (&dpt)[4][4], const uint32_t (&wq)[2][2], int qs) {
 #pragma unroll
-        for (int m = 0; m < 4; ++m) {
-          wq[m][0] >>= shl;
-          wq[m][1] >>= shl;
-        }
-      }
-#pragma unroll
-      for (int n = 0; n < 8; ++n) {
-        const int q = qt * 64 + n * 8 + 2 * c;
+      for (int n = 0; n < 4; ++n) {
+        const int q = qs * 32 + n * 8 + 2 * c;
         const float2 Lq = *reinterpret_cast<const float2*>(sL + q);
         const float2 Dq = *reinterpret_cast<const float2*>(sD + q);
         const float p0 = ex2(fmaf(st[n][0], kScaleLog2, -Lq.x)), p1 = ex2(fmaf(st[n][1], kScaleLog2, -Lq.y));
@@ -404,7 +462,7 @@ attn_bwd_dkv_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ d_o, 
             k2 = ((drop_hash32(key, qb0 + kvh1) >> sh) & 0xFFFFu) >= thresh16;
             k3 = ((drop_hash32(key, qb1 + kvh1) >> sh) & 0xFFFFu) >= thresh16;
           } else {
-            const uint32_t w0 = wq[n >> 1][0], w1 = wq[n >> 1][1];
+            const uint32_t w0 = wq[n >> 1][0] >> shl, w1 = wq[n >> 1][1] >> shl;
             const uint32_t b0 = (n & 1) ? 0x10000u : 1u, b2 = (n & 1) ? 0x40000u : 4u;
             k0 = w0 & b0;
             k1 = w1 & b0;
@@ -425,11 +483,22 @@ attn_bwd_dkv_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ d_o, 
         dpt[n][2] = d2;
         dpt[n][3] = d3;
       }
-      uint32_t pa[4][4];
-      pack_frags(pa, dpt);
-      mma_p_m(dv, pa, sdO, qt * 64, lane);
-      pack_frags(pa, st);
-      mma_p_m(dk, pa, sQ, qt * 64, lane);
+      uint32_t pa[2][4];
+      pack_frags2(pa, dpt);
+      mma_p_m_t<2>(dv, pa, sdO, qs * 32, lane);
+      pack_frags2(pa, st);
+      mma_p_m_t<2>(dk, pa, sQ, qs * 32, lane);
+    };
+
+    float sA[4][4], dA[4][4], sB[4][4], dB[4][4];
+    uint32_t wA[2][2], wB[2][2];
+    compute(sA, dA, wA, 0);
+#pragma unroll 1
+    for (int qs = 0; qs < kS / 32; qs += 2) {
+      compute(sB, dB, wB, qs + 1);
+      process(sA, dA, wA, qs);
+      if (qs + 2 < kS / 32) compute(sA, dA, wA, qs + 2);
+      process(sB, dB, wB, qs + 1);
     }
     bf16* r0 = dqkv + ((long)b * kS + kv0 + g) * kLdQkv + h * 32;
     bf16* r1 = r0 + 8 * kLdQkv;
@@ -493,7 +562,7 @@ int attn_forward(const bf16* qkv, bf16* out, float* lse2, int B, uint32_t key, u
 int attn_backward(const bf16* qkv, const bf16* o, const bf16* d_o, const float* lse2, float* dsum, bf16* dqkv, int B,
                   uint32_t key, uint32_t thresh16, const uint32_t* drop_bits, cudaStream_t s) {
   FOCR_REQUIRE(B >= 1 && B <= 1024, "attention: B=%d out of range", B);
-  const int smem_a = 2 * kTileBytes, smem_b = 2 * kTileBytes + 2 * kS * 4;
+  const int smem_a = 2 * kTileBytes, smem_b = 2 * kTileBytes + 2 * kS * 4 + 2 * 16384;
   const float inv_keep = 65536.f / (65536.f - (float)thresh16);
   static bool init = false;
   if (!init) {
