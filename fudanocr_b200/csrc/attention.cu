@@ -1,24 +1,29 @@
-// Fused self-attention of the TBSRN FeatureEnhancer: h=4 heads, d_k=32, 1024 tokens
-// (scene-text-telescope/model/tbsrn.py:109-150: softmax(QK^T/sqrt(d_k)) -> dropout(0.1) -> PV).
-// The reference materialises P = (B,4,1024,1024) fp32 (4 GiB at B=256); here P never leaves
-// registers.  Input is the packed projection QKV (T,384) bf16 = [q | k | v], head h at columns
+// Fused self-attention of the TBSRN FeatureEnhancer on the 5th-generation tensor cores: h = 4 heads, d_k = 32,
+// 1024 tokens (scene-text-telescope/model/tbsrn.py:109-150: softmax(QK^T/sqrt(d_k)) -> dropout(0.1) -> PV).
+// The reference materialises P = (B,4,1024,1024) fp32 (4 GiB at B = 256); here P only ever exists as 128 x 64 tiles
+// in tensor memory / shared memory.  Input is the packed projection QKV (T,384) bf16 = [q | k | v], head h at columns
 // h*32 of each third; output O (T,128) bf16 in the "concat heads" layout the out-projection reads.
 //
-// d_k = 32 makes the op exp/issue-bound rather than MMA-bound (128 tensor FLOPs per exp), so the
-// kernels are warp-level mma.sync m16n8k16 flash kernels: one CTA per (batch, head) keeps the whole
-// K and V (or Q and dO) of that head in shared memory (2 x 64 KB, XOR-swizzled for ldmatrix) so they
-// are read from HBM exactly once.
-//   forward : warp owns 16 query rows, loops over 16 KV tiles of 64, online softmax
-//   backward: two passes without atomics -
-//     pass A (dQ)   : warp owns 16 query rows;  dS = P o (dP - D),  dQ = dS K
-//     pass B (dK,dV): warp owns 16 key rows;    works on S^T, dP^T; dV = Pd^T dO, dK = dS^T Q
-// Dropout uses the counter hash of common.cuh keyed on (b,h,q,k).  The hash is ~60 % of the forward's
-// instruction stream, so when the caller provides a keep-bit buffer (1 bit per (b,h,q,k), B x 512 KB) the
-// forward stores its keep decisions in its own fragment layout - word [bh][q/16][k/64][lane], bit
-// 16*(q%16 >= 8) + 2*((k%64)/8) + (k&1), lane = (q%8)*4 + (k%8)/2 - and both backward passes test bits
-// instead of re-hashing (DROP = 2).  Without the buffer the backward regenerates the mask (DROP = 1).
-// The 1/(1-p) factor is folded into the output scales: P.V, dV accumulate kept probabilities unscaled,
-// dS = P o (keep o dP - D (1-p)) / (1-p).
+// One CTA per (batch, head), 384 threads:
+//   warp 0      TMA producer (64-byte-swizzled boxes of the [1024][32] head slices)
+//   warp 1, 2   one tcgen05.mma issuing thread per softmax group
+//   warp 3      TMEM allocator
+//   warps 4-7 / 8-11   softmax groups 0 / 1: thread = one query row of a 128-row tile (TMEM lane = row), so row
+//               max / row sum / LSE / D are thread-local scalars and no shuffles are needed
+// Tiles are 128 queries x 64 keys.  S = Q K^T and dP = dO V^T are K-major x K-major MMAs (d_k = 32 = two K steps),
+// accumulators in TMEM; the softmax threads read them with tcgen05.ld, write bf16 P / dS rows into a 128-byte-swizzled
+// shared tile, and the second GEMM of each tile consumes that tile either K-major (P V, dS K) or MN-major (P^T dO,
+// dS^T Q - M = 64 keys) with V / K / dO / Q read in place as MN-major B operands.  The descriptor semantics used
+// here are pinned by tests/test_gpu_umma_layouts.py.
+//   forward   : two passes over the keys per query tile (exact row max first, then exp / sum / PV) - no rescaling of
+//               the TMEM accumulator is ever needed; S is double-buffered in TMEM
+//   backward A: dQ  (query tile outer, key tiles inner; also writes D = rowsum(dO o O))
+//   backward B: dK, dV (64-key block outer, query tiles inner)
+// Dropout: counter hash of common.cuh keyed on (b,h,q,k/2); each 32-bit hash carries two 15-bit lanes, element k
+// is DROPPED when lane (k & 1) < th15 (th15 = round(p * 32768)).  The forward can store its keep decisions, one
+// word per (q, 32 keys): word [bh][k/32][q], bit (k%32)/2 + 16 (k&1); the backward then reads bits instead of
+// re-hashing.  The 1/(1-p) factor is folded into the output scales: P V and dV accumulate kept probabilities
+// unscaled, dS = P o (keep o dP - D (1-p)) / (1-p).
 #include "kernels.cuh"
 
 namespace {
@@ -28,497 +33,681 @@ constexpr int kLdQkv = 384;   // row stride of the packed projection
 constexpr int kLdO = 128;
 constexpr float kScale = 0.17677669529663687f;  // 1/sqrt(32)
 constexpr float kScaleLog2 = kScale * 1.4426950408889634f;
-constexpr int kTileBytes = kS * 64;  // one [1024][32] bf16 head slice
+constexpr int kThreads = 384;
+constexpr int kHeadBytes = kS * 64;  // one [1024][32] bf16 head slice
+constexpr int kQTile = 128 * 64;     // [128][32] bf16
+constexpr int kPTile = 128 * 128;    // [128 q][64 keys] bf16, 128-byte swizzled
 
-__device__ __forceinline__ uint32_t sw_off(int row, int chunk) {
-  return (uint32_t)(row * 64 + (((chunk ^ (row >> 1)) & 3) << 4));
-}
 __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ uint32_t ld32(const bf16* p) { return *reinterpret_cast<const uint32_t*>(p); }
+// byte permute with sign replication: selector nibble 8+i yields 0xFF if the msb of source byte i is set, else 0x00
+__device__ __forceinline__ uint32_t prmt(uint32_t x, uint32_t sel) {
+  uint32_t y;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(y) : "r"(x), "r"(0u), "r"(sel));
+  return y;
+}
+__device__ __forceinline__ uint32_t p_off(int row, int chunk) { return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4)); }
 
-__device__ __forceinline__ void load_head_tile(uint32_t sbase, const bf16* g, long ld, int tid) {
-  for (int i = tid; i < kS * 4; i += (int)blockDim.x) {
-    const int row = i >> 2, ch = i & 3;
-    cp_async_16(sbase + sw_off(row, ch), g + (long)row * ld + ch * 8, true);
-  }
+// operand descriptors: [rows][32] bf16 tiles written by TMA with the 64-byte swizzle (8-row groups 512 B apart) and
+// the [128][64] bf16 P / dS tile with the 128-byte swizzle (8-row groups 1024 B apart).  The same fields serve the
+// K-major and the MN-major reading of a tile; the instruction descriptor says which one is meant.
+__device__ __forceinline__ uint64_t desc_sw64(uint32_t addr) { return umma_desc(addr, 16, 512, 4); }
+__device__ __forceinline__ uint64_t desc_sw128(uint32_t addr) { return umma_desc(addr, 16, 1024, 2); }
+
+// S / dP tile: D[128 x 64] = A[128 x 32] B[64 x 32]^T
+__device__ __forceinline__ void mma_qk(uint32_t tmem_d, uint32_t a_addr, uint32_t b_addr) {
+  constexpr uint32_t idesc = umma_idesc_bf16_ex(128, 64, 0, 0);
+  const uint64_t da = desc_sw64(a_addr), db = desc_sw64(b_addr);
+  tc_mma_bf16(tmem_d, da, db, idesc, 0);
+  tc_mma_bf16(tmem_d, da + 2, db + 2, idesc, 1);
 }
-// A-operand fragments (16 rows x 32 cols, two k-steps) of a row-major bf16 matrix in global memory
-__device__ __forceinline__ void load_a_frags(uint32_t (&a)[2][4], const bf16* row0, long ld, int c) {
-  const bf16* row1 = row0 + 8 * ld;
+// D[128 x 32] (+)= A[128 q x 64 keys] (K-major, sw128) * B[64 keys x 32] (MN-major, sw64)
+__device__ __forceinline__ void mma_pv(uint32_t tmem_d, uint32_t a_addr, uint32_t b_addr, bool acc) {
+  constexpr uint32_t idesc = umma_idesc_bf16_ex(128, 32, 0, 1);
+  const uint64_t da = desc_sw128(a_addr), db = desc_sw64(b_addr);
 #pragma unroll
-  for (int ks = 0; ks < 2; ++ks) {
-    a[ks][0] = ld32(row0 + ks * 16 + 2 * c);
-    a[ks][1] = ld32(row1 + ks * 16 + 2 * c);
-    a[ks][2] = ld32(row0 + ks * 16 + 8 + 2 * c);
-    a[ks][3] = ld32(row1 + ks * 16 + 8 + 2 * c);
-  }
+  for (int ks = 0; ks < 4; ++ks) tc_mma_bf16(tmem_d, da + 2 * ks, db + 64 * ks, idesc, (acc || ks) ? 1u : 0u);
 }
-// acc[8][4] (16 x 64) = A(16x32) * M^T, M = [64 rows of the smem head tile starting at row0][32]
-__device__ __forceinline__ void mma_a_mt(float (&acc)[8][4], const uint32_t (&a)[2][4], uint32_t sbase, int row0,
-                                         int lane) {
+// D[64 keys x 32] (+)= A^T, A = [128 q x 64 keys] tile read MN-major (M = keys), B = [128 q x 32] MN-major
+__device__ __forceinline__ void mma_ptdo(uint32_t tmem_d, uint32_t a_addr, uint32_t b_addr, bool acc) {
+  constexpr uint32_t idesc = umma_idesc_bf16_ex(64, 32, 1, 1);
+  const uint64_t da = desc_sw128(a_addr), db = desc_sw64(b_addr);
 #pragma unroll
-  for (int n = 0; n < 8; ++n) {
-    uint32_t r[4];
-    ldmatrix_x4(r, sbase + sw_off(row0 + n * 8 + (lane & 7), lane >> 3));
-    const uint32_t b0[2] = {r[0], r[1]}, b1[2] = {r[2], r[3]};
-    mma_bf16_16816(acc[n], a[0], b0);
-    mma_bf16_16816(acc[n], a[1], b1);
-  }
-}
-// acc[4][4] (16 x 32) += P(16x64, packed A frags) * M, M = [64 rows starting at row0][32] of the smem tile
-__device__ __forceinline__ void mma_p_m(float (&acc)[4][4], const uint32_t (&pa)[4][4], uint32_t sbase, int row0,
-                                        int lane) {
-#pragma unroll
-  for (int kk = 0; kk < 4; ++kk) {
-    const int row = row0 + kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
-#pragma unroll
-    for (int nd = 0; nd < 4; nd += 2) {
-      uint32_t r[4];
-      ldmatrix_x4_trans(r, sbase + sw_off(row, nd + (lane >> 4)));
-      const uint32_t b0[2] = {r[0], r[1]}, b1[2] = {r[2], r[3]};
-      mma_bf16_16816(acc[nd], pa[kk], b0);
-      mma_bf16_16816(acc[nd + 1], pa[kk], b1);
-    }
-  }
-}
-__device__ __forceinline__ void pack_frags(uint32_t (&pa)[4][4], const float (&s)[8][4]) {
-#pragma unroll
-  for (int kk = 0; kk < 4; ++kk) {
-    pa[kk][0] = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
-    pa[kk][1] = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
-    pa[kk][2] = pack_bf16x2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
-    pa[kk][3] = pack_bf16x2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
-  }
-}
-__device__ __forceinline__ float quad_sum(float v) {
-  v += __shfl_xor_sync(0xffffffffu, v, 1);
-  v += __shfl_xor_sync(0xffffffffu, v, 2);
-  return v;
-}
-__device__ __forceinline__ float quad_max(float v) {
-  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
-  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
-  return v;
+  for (int ks = 0; ks < 8; ++ks) tc_mma_bf16(tmem_d, da + 128 * ks, db + 64 * ks, idesc, (acc || ks) ? 1u : 0u);
 }
 
-// ------------------------------------------------------------------------------------------
-template <int DROP, int NW>
-__global__ void __launch_bounds__(NW * 32, 1)
-attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __restrict__ lse2, uint32_t key,
-                uint32_t thresh16, float inv_keep, uint32_t* __restrict__ drop_bits) {
-  extern __shared__ __align__(128) uint8_t sm[];
-  const uint32_t sK = smem_u32(sm), sV = sK + kTileBytes;
-  const int bh = blockIdx.x, b = bh >> 2, h = bh & 3;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, c = lane & 3;
-  const bf16* base = qkv + (long)b * kS * kLdQkv + h * 32;
-  load_head_tile(sK, base + 128, kLdQkv, tid);
-  load_head_tile(sV, base + 256, kLdQkv, tid);
-  cp_async_commit();
-  cp_async_wait<0>();
-  __syncthreads();
+// keep decisions of 32 consecutive keys of one query row.  x = (hash & 0x7FFF7FFF) + addc has bit 15 / bit 31 set iff
+// the even / odd key of the pair is kept (addc = (0x8000 - th15) * 0x00010001).
+__device__ __forceinline__ uint32_t keep_x(uint32_t key, uint32_t ctr, uint32_t addc) {
+  return (drop_hash32(key, ctr) & 0x7FFF7FFFu) + addc;
+}
+__device__ __forceinline__ uint32_t hash_word(uint32_t key, uint32_t ctr0, uint32_t addc) {
+  uint32_t w = 0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) w = (w >> 1) | (keep_x(key, ctr0 + i, addc) & 0x80008000u);
+  return w;
+}
 
-  for (int u = warp; u < kS / 16; u += NW) {  // 64 units of 16 query rows, round-robin over the warps
-    const int q0 = u * 16;
-    uint32_t qa[2][4];
-    load_a_frags(qa, base + (long)(q0 + g) * kLdQkv, kLdQkv, c);
-    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
-    float o[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
-    const uint32_t rb0 = (uint32_t)(bh * kS + q0 + g) * 512u, rb1 = rb0 + 8u * 512u;
+struct WgBars {      // per softmax group
+  uint64_t a_full;   // per-tile operand(s) of this group landed (TMA)
+  uint64_t a_empty;  // ... and every MMA reading them has completed
+  uint64_t a2_full[2];   // dKV kernel: the K_j / V_j double buffer
+  uint64_t a2_empty[2];
+  uint64_t s_full[2];    // S (and dP) accumulator written
+  uint64_t s_empty[2];   // ... and drained by the 4 softmax warps
+  uint64_t p_full;       // P / dS tile written to shared memory (4 warps)
+  uint64_t p_empty;      // ... and consumed by the second GEMM
+  uint64_t o_full;       // output accumulator (O / dQ / dK,dV) complete
+  uint64_t o_empty;      // ... and drained
+};
+struct Bars {
+  uint64_t res_full;  // the resident head slices landed
+  WgBars wg[2];
+  uint32_t tmem_slot;
+};
 
-#pragma unroll 1
-    for (int kt = 0; kt < kS / 64; ++kt) {
-      float s[8][4];
-#pragma unroll
-      for (int n = 0; n < 8; ++n) s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
-      mma_a_mt(s, qa, sK, kt * 64, lane);
-      float mx0 = s[0][0], mx1 = s[0][2];
-#pragma unroll
-      for (int n = 0; n < 8; ++n) {
-        mx0 = fmaxf(mx0, fmaxf(s[n][0], s[n][1]));
-        mx1 = fmaxf(mx1, fmaxf(s[n][2], s[n][3]));
-      }
-      mx0 = quad_max(mx0);
-      mx1 = quad_max(mx1);
-      const float mn0 = fmaxf(m0, mx0 * kScaleLog2), mn1 = fmaxf(m1, mx1 * kScaleLog2);
-      const float al0 = ex2(m0 - mn0), al1 = ex2(m1 - mn1);
-      m0 = mn0;
-      m1 = mn1;
-      float rs0 = 0.f, rs1 = 0.f;
-#pragma unroll
-      for (int n = 0; n < 8; ++n) {
-        s[n][0] = ex2(fmaf(s[n][0], kScaleLog2, -mn0));
-        s[n][1] = ex2(fmaf(s[n][1], kScaleLog2, -mn0));
-        s[n][2] = ex2(fmaf(s[n][2], kScaleLog2, -mn1));
-        s[n][3] = ex2(fmaf(s[n][3], kScaleLog2, -mn1));
-        rs0 += s[n][0] + s[n][1];
-        rs1 += s[n][2] + s[n][3];
-      }
-      l0 = fmaf(l0, al0, rs0);
-      l1 = fmaf(l1, al1, rs1);
-#pragma unroll
-      for (int nd = 0; nd < 4; ++nd) {
-        o[nd][0] *= al0;
-        o[nd][1] *= al0;
-        o[nd][2] *= al1;
-        o[nd][3] *= al1;
-      }
-      if (DROP) {
-        const uint32_t cb = (uint32_t)(kt * 32 + c);
-        uint32_t bits = 0;
-#pragma unroll
-        for (int n = 0; n < 8; ++n) {
-          const uint32_t h0 = drop_hash32(key, rb0 + cb + n * 4), h1 = drop_hash32(key, rb1 + cb + n * 4);
-          const bool k0 = (h0 & 0xFFFFu) >= thresh16, k1 = (h0 >> 16) >= thresh16;
-          const bool k2 = (h1 & 0xFFFFu) >= thresh16, k3 = (h1 >> 16) >= thresh16;
-          s[n][0] = k0 ? s[n][0] : 0.f;
-          s[n][1] = k1 ? s[n][1] : 0.f;
-          s[n][2] = k2 ? s[n][2] : 0.f;
-          s[n][3] = k3 ? s[n][3] : 0.f;
-          if (DROP == 2) {
-            if (k0) bits |= 1u << (2 * n);
-            if (k1) bits |= 2u << (2 * n);
-            if (k2) bits |= 0x10000u << (2 * n);
-            if (k3) bits |= 0x20000u << (2 * n);
-          }
-        }
-        if (DROP == 2) drop_bits[(((size_t)bh * 64 + u) * 16 + kt) * 32 + lane] = bits;
-      }
-      uint32_t pa[4][4];
-      pack_frags(pa, s);
-      mma_p_m(o, pa, sV, kt * 64, lane);
+__device__ __forceinline__ void init_bars(Bars* bars) {
+  mbar_init(&bars->res_full, 1);
+  for (int g = 0; g < 2; ++g) {
+    WgBars& w = bars->wg[g];
+    mbar_init(&w.a_full, 1);
+    mbar_init(&w.a_empty, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&w.a2_full[i], 1);
+      mbar_init(&w.a2_empty[i], 1);
+      mbar_init(&w.s_full[i], 1);
+      mbar_init(&w.s_empty[i], 4);
     }
-    l0 = quad_sum(l0);
-    l1 = quad_sum(l1);
-    const float i0 = inv_keep / l0, i1 = inv_keep / l1;
-    bf16* orow0 = out + ((long)b * kS + q0 + g) * kLdO + h * 32;
-    bf16* orow1 = orow0 + 8 * kLdO;
-#pragma unroll
-    for (int nd = 0; nd < 4; ++nd) {
-      *reinterpret_cast<uint32_t*>(orow0 + nd * 8 + 2 * c) = pack_bf16x2(o[nd][0] * i0, o[nd][1] * i0);
-      *reinterpret_cast<uint32_t*>(orow1 + nd * 8 + 2 * c) = pack_bf16x2(o[nd][2] * i1, o[nd][3] * i1);
-    }
-    if (c == 0) {
-      lse2[(long)bh * kS + q0 + g] = m0 + log2f(l0);
-      lse2[(long)bh * kS + q0 + g + 8] = m1 + log2f(l1);
-    }
+    mbar_init(&w.p_full, 4);
+    mbar_init(&w.p_empty, 1);
+    mbar_init(&w.o_full, 1);
+    mbar_init(&w.o_empty, 4);
   }
+  fence_mbar_init();
+}
+// one arrival per softmax warp, after every lane's TMEM loads have completed
+__device__ __forceinline__ void warp_release_tmem(uint64_t* bar, int lane) {
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(bar);
+}
+// one arrival per softmax warp, after every lane's shared-memory stores are visible to the tensor-core proxy
+__device__ __forceinline__ void warp_publish_smem(uint64_t* bar, int lane) {
+  fence_proxy_async();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(bar);
+}
+__device__ __forceinline__ void store_chunks4(uint8_t* tile, int row, int chunk0, const uint32_t (&pk)[16]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    *reinterpret_cast<uint4*>(tile + p_off(row, chunk0 + q)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
 }
 
-// ------------------------------------------------------------------------------------------
-// Backward kernels.  Both are latency-bound at 2 warps per scheduler (the S -> exp -> dS -> MMA chain is serial
-// inside a warp), so they walk the other sequence dimension in 32-wide steps, software-pipelined by hand: the
-// QK^T / dO V^T MMAs of step i+1 are issued before the softmax arithmetic of step i (two register buffers A/B).
-template <int NT>
-__device__ __forceinline__ void mma_a_mt_t(float (&acc)[NT][4], const uint32_t (&a)[2][4], uint32_t sbase, int row0,
-                                           int lane) {
-#pragma unroll
-  for (int n = 0; n < NT; ++n) {
-    uint32_t r[4];
-    ldmatrix_x4(r, sbase + sw_off(row0 + n * 8 + (lane & 7), lane >> 3));
-    const uint32_t b0[2] = {r[0], r[1]}, b1[2] = {r[2], r[3]};
-    mma_bf16_16816(acc[n], a[0], b0);
-    mma_bf16_16816(acc[n], a[1], b1);
-  }
-}
-template <int KK>
-__device__ __forceinline__ void mma_p_m_t(float (&acc)[4][4], const uint32_t (&pa)[KK][4], uint32_t sbase, int row0,
-                                          int lane) {
-#pragma unroll
-  for (int kk = 0; kk < KK; ++kk) {
-    const int row = row0 + kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
-#pragma unroll
-    for (int nd = 0; nd < 4; nd += 2) {
-      uint32_t r[4];
-      ldmatrix_x4_trans(r, sbase + sw_off(row, nd + (lane >> 4)));
-      const uint32_t b0[2] = {r[0], r[1]}, b1[2] = {r[2], r[3]};
-      mma_bf16_16816(acc[nd], pa[kk], b0);
-      mma_bf16_16816(acc[nd + 1], pa[kk], b1);
-    }
-  }
-}
-__device__ __forceinline__ void pack_frags2(uint32_t (&pa)[2][4], const float (&s)[4][4]) {
-#pragma unroll
-  for (int kk = 0; kk < 2; ++kk) {
-    pa[kk][0] = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
-    pa[kk][1] = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
-    pa[kk][2] = pack_bf16x2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
-    pa[kk][3] = pack_bf16x2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
-  }
-}
-__device__ __forceinline__ void zero44(float (&x)[4][4]) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) x[i][0] = x[i][1] = x[i][2] = x[i][3] = 0.f;
-}
+// ------------------------------------------------------------------------------------------------------------------
+// forward.  shared: K, V resident (2 x 64 KB); per group a Q tile (8 KB) and a P tile (16 KB).
+// TMEM per group: S[2] (2 x 64 columns), O (32 columns).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kFwdSmem = 2 * kHeadBytes + 2 * (kQTile + kPTile) + 1024 /*barriers*/ + 1024 /*alignment*/;
 
-// backward pass A: dQ (and D = rowsum(dO o O), written for pass B)
-template <int DROP, int NW>
-__global__ void __launch_bounds__(NW * 32, 1)
-attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o_in, const bf16* __restrict__ d_o,
-                   const float* __restrict__ lse2, float* __restrict__ dsum, bf16* __restrict__ dqkv, uint32_t key,
-                   uint32_t thresh16, float inv_keep, const uint32_t* __restrict__ drop_bits) {
-  extern __shared__ __align__(128) uint8_t sm[];
-  const uint32_t sK = smem_u32(sm), sV = sK + kTileBytes;
-  const int bh = blockIdx.x, b = bh >> 2, h = bh & 3;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, c = lane & 3;
-  const bf16* base = qkv + (long)b * kS * kLdQkv + h * 32;
-  load_head_tile(sK, base + 128, kLdQkv, tid);
-  load_head_tile(sV, base + 256, kLdQkv, tid);
-  cp_async_commit();
-  cp_async_wait<0>();
-  __syncthreads();
-
-  for (int u = warp; u < kS / 16; u += NW) {
-    const int q0 = u * 16;
-    const long t0 = (long)b * kS + q0 + g;
-    uint32_t qa[2][4], da[2][4], oa[2][4];
-    load_a_frags(qa, base + (long)(q0 + g) * kLdQkv, kLdQkv, c);
-    load_a_frags(da, d_o + t0 * kLdO + h * 32, kLdO, c);
-    load_a_frags(oa, o_in + t0 * kLdO + h * 32, kLdO, c);
-    float D0 = 0.f, D1 = 0.f;
-#pragma unroll
-    for (int ks = 0; ks < 2; ++ks) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 x = unpack_bf16x2(da[ks][j]), y = unpack_bf16x2(oa[ks][j]);
-        const float v = x.x * y.x + x.y * y.y;
-        if (j & 1) D1 += v; else D0 += v;
-      }
-    }
-    D0 = quad_sum(D0);
-    D1 = quad_sum(D1);
-    if (c == 0) {
-      dsum[(long)bh * kS + q0 + g] = D0;
-      dsum[(long)bh * kS + q0 + g + 8] = D1;
-    }
-    D0 *= 1.f / inv_keep;  // dS = P o (keep o dP - D (1-p)) / (1-p); the 1/(1-p) goes into the final scale
-    D1 *= 1.f / inv_keep;
-    const float L0 = lse2[(long)bh * kS + q0 + g], L1 = lse2[(long)bh * kS + q0 + g + 8];
-    float dq[4][4];
-    zero44(dq);
-    const uint32_t rb0 = (uint32_t)(bh * kS + q0 + g) * 512u, rb1 = rb0 + 8u * 512u;
-    const uint32_t* wb = drop_bits + ((size_t)bh * 64 + u) * 16 * 32 + lane;
-
-    auto compute = [&](float (&s)[4][4], float (&dp)[4][4], int row0) {
-      zero44(s);
-      zero44(dp);
-      mma_a_mt_t<4>(s, qa, sK, row0, lane);
-      mma_a_mt_t<4>(dp, da, sV, row0, lane);
-    };
-    // nb: 0 for the even 32-step of a 64-wide bit word, 4 for the odd one
-    auto process = [&](float (&s)[4][4], float (&dp)[4][4], int row0, uint32_t w, const int nb) {
-      const uint32_t cb = (uint32_t)(row0 >> 1) + c;
-#pragma unroll
-      for (int n = 0; n < 4; ++n) {
-        const float p0 = ex2(fmaf(s[n][0], kScaleLog2, -L0)), p1 = ex2(fmaf(s[n][1], kScaleLog2, -L0));
-        const float p2 = ex2(fmaf(s[n][2], kScaleLog2, -L1)), p3 = ex2(fmaf(s[n][3], kScaleLog2, -L1));
-        float e0 = dp[n][0], e1 = dp[n][1], e2 = dp[n][2], e3 = dp[n][3];
-        if (DROP == 1) {
-          const uint32_t h0 = drop_hash32(key, rb0 + cb + n * 4), h1 = drop_hash32(key, rb1 + cb + n * 4);
-          e0 = (h0 & 0xFFFFu) >= thresh16 ? e0 : 0.f;
-          e1 = (h0 >> 16) >= thresh16 ? e1 : 0.f;
-          e2 = (h1 & 0xFFFFu) >= thresh16 ? e2 : 0.f;
-          e3 = (h1 >> 16) >= thresh16 ? e3 : 0.f;
-        } else if (DROP == 2) {
-          e0 = (w & (1u << (2 * (n + nb)))) ? e0 : 0.f;
-          e1 = (w & (2u << (2 * (n + nb)))) ? e1 : 0.f;
-          e2 = (w & (0x10000u << (2 * (n + nb)))) ? e2 : 0.f;
-          e3 = (w & (0x20000u << (2 * (n + nb)))) ? e3 : 0.f;
-        }
-        s[n][0] = p0 * (e0 - D0);
-        s[n][1] = p1 * (e1 - D0);
-        s[n][2] = p2 * (e2 - D1);
-        s[n][3] = p3 * (e3 - D1);
-      }
-      uint32_t pa[2][4];
-      pack_frags2(pa, s);
-      mma_p_m_t<2>(dq, pa, sK, row0, lane);
-    };
-
-    float sA[4][4], dA[4][4], sB[4][4], dB[4][4];
-    uint32_t w = 0, w1 = 0, w2 = 0;  // bit words of tiles kt, kt+1, kt+2 (loads run two tiles ahead)
-    if (DROP == 2) {
-      w1 = __ldg(wb);
-      w2 = __ldg(wb + 32);
-    }
-    compute(sA, dA, 0);
-#pragma unroll 1
-    for (int kt = 0; kt < kS / 64; ++kt) {
-      if (DROP == 2) {
-        w = w1;
-        w1 = w2;
-        if (kt + 2 < kS / 64) w2 = __ldg(wb + (kt + 2) * 32);
-      }
-      compute(sB, dB, kt * 64 + 32);
-      process(sA, dA, kt * 64, w, 0);
-      if (kt + 1 < kS / 64) compute(sA, dA, kt * 64 + 64);
-      process(sB, dB, kt * 64 + 32, w, 4);
-    }
-    bf16* r0 = dqkv + t0 * kLdQkv + h * 32;
-    bf16* r1 = r0 + 8 * kLdQkv;
-    const float osc = kScale * inv_keep;
-#pragma unroll
-    for (int nd = 0; nd < 4; ++nd) {
-      *reinterpret_cast<uint32_t*>(r0 + nd * 8 + 2 * c) = pack_bf16x2(dq[nd][0] * osc, dq[nd][1] * osc);
-      *reinterpret_cast<uint32_t*>(r1 + nd * 8 + 2 * c) = pack_bf16x2(dq[nd][2] * osc, dq[nd][3] * osc);
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// backward pass B: dK, dV (warp owns 16 key rows; everything is the transpose of pass A)
 template <int DROP>
-__global__ void __launch_bounds__(256, 1)
-attn_bwd_dkv_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ d_o, const float* __restrict__ lse2,
-                    const float* __restrict__ dsum, bf16* __restrict__ dqkv, uint32_t key, uint32_t thresh16,
-                    float inv_keep, const uint32_t* __restrict__ drop_bits) {
-  extern __shared__ __align__(128) uint8_t sm[];
-  const uint32_t sQ = smem_u32(sm), sdO = sQ + kTileBytes;
-  float* sL = reinterpret_cast<float*>(sm + 2 * kTileBytes);
-  float* sD = sL + kS;
-  // DROP == 2: keep-bit words of the current 128-key block, all 64 query units x 2 key tiles x 32 lanes, double-buffered
-  uint32_t* sW = reinterpret_cast<uint32_t*>(sD + kS);
+__global__ void __launch_bounds__(kThreads, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap mQkv, bf16* __restrict__ out, float* __restrict__ lse2, uint32_t key,
+                uint32_t th15, float inv_keep, uint32_t* __restrict__ drop_bits) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sK = smem;
+  uint8_t* sV = smem + kHeadBytes;
+  uint8_t* sQ = smem + 2 * kHeadBytes;             // [2 groups]
+  uint8_t* sP = sQ + 2 * kQTile;                   // [2 groups]
+  Bars* bars = reinterpret_cast<Bars*>(sP + 2 * kPTile);
   const int bh = blockIdx.x, b = bh >> 2, h = bh & 3;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, c = lane & 3;
-  const bf16* base = qkv + (long)b * kS * kLdQkv + h * 32;
-  auto load_bits = [&](int kb) {
-    if (DROP == 2) {
-      const uint32_t dst = smem_u32(sW) + (kb & 1) * 16384;
-      const uint32_t* src = drop_bits + ((size_t)bh * 64 * 16 + 2 * kb) * 32;
-      for (int i = tid; i < 1024; i += 256)
-        cp_async_16(dst + (i >> 4) * 256 + (i & 15) * 16, src + (size_t)(i >> 4) * 512 + (i & 15) * 4, true);
-    }
-  };
-  load_head_tile(sQ, base, kLdQkv, tid);
-  load_head_tile(sdO, d_o + (long)b * kS * kLdO + h * 32, kLdO, tid);
-  load_bits(0);
-  cp_async_commit();
-  for (int i = tid; i < kS; i += (int)blockDim.x) {
-    sL[i] = lse2[(long)bh * kS + i];
-    sD[i] = dsum[(long)bh * kS + i] * (1.f / inv_keep);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) tma_prefetch_desc(&mQkv);
+  if (warp == 1 && lane == 0) init_bars(bars);
+  if (warp == 3) {
+    tmem_alloc(&bars->tmem_slot, 512);
+    tmem_relinquish();
   }
-  cp_async_wait<0>();
+  tc_fence_before();
   __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_slot;
 
-  for (int kb = 0; kb < kS / 128; ++kb) {
-    if (DROP == 2) {
-      cp_async_wait<0>();
-      __syncthreads();  // this block's bit words landed, and every warp is done with the buffer refilled next
-      if (kb + 1 < kS / 128) load_bits(kb + 1);
-      cp_async_commit();
-    }
-    const int kv0 = kb * 128 + warp * 16;
-    uint32_t ka[2][4], va[2][4];
-    load_a_frags(ka, base + 128 + (long)(kv0 + g) * kLdQkv, kLdQkv, c);
-    load_a_frags(va, base + 256 + (long)(kv0 + g) * kLdQkv, kLdQkv, c);
-    float dk[4][4], dv[4][4];
-    zero44(dk);
-    zero44(dv);
-    // element (kv, q): counter = (bh*1024 + q)*512 + kv/2, 16-bit lane = kv & 1
-    const uint32_t kvh0 = (uint32_t)((kv0 + g) >> 1), kvh1 = (uint32_t)((kv0 + g + 8) >> 1);
-    const int sh = ((kv0 + g) & 1) * 16;  // same parity for row g and g+8
-    // keep-bit words of the forward's fragment layout (see the file header): q -> (unit, half, lane group), kv -> bit
-    const uint32_t* wb = sW + (kb & 1) * 4096 + (warp >> 2) * 32 + (g >> 1);
-    const int wl0 = (2 * c) * 4, wl1 = (2 * c + 1) * 4;
-    const int shl = 2 * ((kv0 & 63) >> 3) + (g & 1);
-
-    // step qs covers query rows [qs*32, qs*32+32): two forward units, one pair of bit words each
-    auto compute = [&](float (&st)[4][4], float (&dpt)[4][4], uint32_t (&wq)[2][2], int qs) {
-      if (DROP == 2) {
-#pragma unroll
-        for (int m = 0; m < 2; ++m) {
-          wq[m][0] = wb[(qs * 2 + m) * 64 + wl0];
-          wq[m][1] = wb[(qs * 2 + m) * 64 + wl1];
-        }
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&bars->res_full, 2 * kHeadBytes);
+      for (int i = 0; i < 8; ++i) {
+        tma_load_2d(sK + i * kQTile, &mQkv, &bars->res_full, 128 + h * 32, b * kS + i * 128);
+        tma_load_2d(sV + i * kQTile, &mQkv, &bars->res_full, 256 + h * 32, b * kS + i * 128);
       }
-      zero44(st);
-      zero44(dpt);
-      mma_a_mt_t<4>(st, ka, sQ, qs * 32, lane);
-      mma_a_mt_t<4>(dpt, va, sdO, qs * 32, lane);
-    };
-    auto process = [&](float (&st)[4][4], float (&dpt)[4][4], const uint32_t (&wq)[2][2], int qs) {
-#pragma unroll
-      for (int n = 0; n < 4; ++n) {
-        const int q = qs * 32 + n * 8 + 2 * c;
-        const float2 Lq = *reinterpret_cast<const float2*>(sL + q);
-        const float2 Dq = *reinterpret_cast<const float2*>(sD + q);
-        const float p0 = ex2(fmaf(st[n][0], kScaleLog2, -Lq.x)), p1 = ex2(fmaf(st[n][1], kScaleLog2, -Lq.y));
-        const float p2 = ex2(fmaf(st[n][2], kScaleLog2, -Lq.x)), p3 = ex2(fmaf(st[n][3], kScaleLog2, -Lq.y));
-        float e0 = dpt[n][0], e1 = dpt[n][1], e2 = dpt[n][2], e3 = dpt[n][3];
-        float d0 = p0, d1 = p1, d2 = p2, d3 = p3;
-        if (DROP) {
-          bool k0, k1, k2, k3;
-          if (DROP == 1) {
-            const uint32_t qb0 = (uint32_t)(bh * kS + q) * 512u, qb1 = qb0 + 512u;
-            k0 = ((drop_hash32(key, qb0 + kvh0) >> sh) & 0xFFFFu) >= thresh16;
-            k1 = ((drop_hash32(key, qb1 + kvh0) >> sh) & 0xFFFFu) >= thresh16;
-            k2 = ((drop_hash32(key, qb0 + kvh1) >> sh) & 0xFFFFu) >= thresh16;
-            k3 = ((drop_hash32(key, qb1 + kvh1) >> sh) & 0xFFFFu) >= thresh16;
-          } else {
-            const uint32_t w0 = wq[n >> 1][0] >> shl, w1 = wq[n >> 1][1] >> shl;
-            const uint32_t b0 = (n & 1) ? 0x10000u : 1u, b2 = (n & 1) ? 0x40000u : 4u;
-            k0 = w0 & b0;
-            k1 = w1 & b0;
-            k2 = w0 & b2;
-            k3 = w1 & b2;
+      for (int it = 0; it < 4; ++it)
+        for (int g = 0; g < 2; ++g) {
+          WgBars& w = bars->wg[g];
+          mbar_wait(&w.a_empty, (it & 1) ^ 1);
+          mbar_arrive_expect_tx(&w.a_full, kQTile);
+          tma_load_2d(sQ + g * kQTile, &mQkv, &w.a_full, h * 32, b * kS + (g + 2 * it) * 128);
+        }
+    }
+  } else if (warp == 1 || warp == 2) {
+    if (lane == 0) {
+      const int g = warp - 1;
+      WgBars& w = bars->wg[g];
+      const uint32_t tS = tmem + g * 160, tO = tmem + g * 160 + 128;
+      const uint32_t aQ = smem_u32(sQ + g * kQTile), aP = smem_u32(sP + g * kPTile);
+      const uint32_t aK = smem_u32(sK), aV = smem_u32(sV);
+      mbar_wait(&bars->res_full, 0);
+      uint32_t ns = 0, np = 0;
+      for (int it = 0; it < 4; ++it) {
+        mbar_wait(&w.a_full, it & 1);
+        tc_fence_after();
+        for (int j = 0; j < 32; ++j) {  // 16 key tiles for the max pass, 16 for the exp / PV pass
+          const int sb = ns & 1;
+          mbar_wait(&w.s_empty[sb], ((ns >> 1) & 1) ^ 1);
+          tc_fence_after();
+          mma_qk(tS + sb * 64, aQ, aK + (j & 15) * 4096);
+          tc_commit(&w.s_full[sb]);
+          ++ns;
+          if (j == 31) tc_commit(&w.a_empty);
+          if (j >= 17) {  // P V of key tile j - 17
+            const int jj = j - 17;
+            mbar_wait(&w.p_full, np & 1);
+            tc_fence_after();
+            if (jj == 0) {
+              mbar_wait(&w.o_empty, (it & 1) ^ 1);
+              tc_fence_after();
+            }
+            mma_pv(tO, aP, aV + jj * 4096, jj != 0);
+            tc_commit(&w.p_empty);
+            ++np;
           }
-          e0 = k0 ? e0 : 0.f; d0 = k0 ? p0 : 0.f;
-          e1 = k1 ? e1 : 0.f; d1 = k1 ? p1 : 0.f;
-          e2 = k2 ? e2 : 0.f; d2 = k2 ? p2 : 0.f;
-          e3 = k3 ? e3 : 0.f; d3 = k3 ? p3 : 0.f;
         }
-        st[n][0] = p0 * (e0 - Dq.x);
-        st[n][1] = p1 * (e1 - Dq.y);
-        st[n][2] = p2 * (e2 - Dq.x);
-        st[n][3] = p3 * (e3 - Dq.y);
-        dpt[n][0] = d0;
-        dpt[n][1] = d1;
-        dpt[n][2] = d2;
-        dpt[n][3] = d3;
+        mbar_wait(&w.p_full, np & 1);
+        tc_fence_after();
+        mma_pv(tO, aP, aV + 15 * 4096, true);
+        tc_commit(&w.p_empty);
+        ++np;
+        tc_commit(&w.o_full);
       }
-      uint32_t pa[2][4];
-      pack_frags2(pa, dpt);
-      mma_p_m_t<2>(dv, pa, sdO, qs * 32, lane);
-      pack_frags2(pa, st);
-      mma_p_m_t<2>(dk, pa, sQ, qs * 32, lane);
-    };
-
-    float sA[4][4], dA[4][4], sB[4][4], dB[4][4];
-    uint32_t wA[2][2], wB[2][2];
-    compute(sA, dA, wA, 0);
-#pragma unroll 1
-    for (int qs = 0; qs < kS / 32; qs += 2) {
-      compute(sB, dB, wB, qs + 1);
-      process(sA, dA, wA, qs);
-      if (qs + 2 < kS / 32) compute(sA, dA, wA, qs + 2);
-      process(sB, dB, wB, qs + 1);
     }
-    bf16* r0 = dqkv + ((long)b * kS + kv0 + g) * kLdQkv + h * 32;
-    bf16* r1 = r0 + 8 * kLdQkv;
-    const float ksc = kScale * inv_keep;
+  } else if (warp >= 4) {
+    const int g = (warp - 4) >> 2, quad = warp & 3, row = quad * 32 + lane;
+    WgBars& w = bars->wg[g];
+    const uint32_t tS = tmem + ((uint32_t)(quad * 32) << 16) + g * 160, tO = tS + 128;
+    uint8_t* myP = sP + g * kPTile;
+    const uint32_t addc = (0x8000u - th15) * 0x00010001u;
+    uint32_t ns = 0, np = 0;
+    for (int it = 0; it < 4; ++it) {
+      const int q = (g + 2 * it) * 128 + row;
+      // ---- pass 1: exact row maximum ----
+      float m = -INFINITY;
+      for (int j = 0; j < 16; ++j) {
+        const int sb = ns & 1;
+        mbar_wait(&w.s_full[sb], (ns >> 1) & 1);
+        tc_fence_after();
 #pragma unroll
-    for (int nd = 0; nd < 4; ++nd) {
-      *reinterpret_cast<uint32_t*>(r0 + 128 + nd * 8 + 2 * c) = pack_bf16x2(dk[nd][0] * ksc, dk[nd][1] * ksc);
-      *reinterpret_cast<uint32_t*>(r1 + 128 + nd * 8 + 2 * c) = pack_bf16x2(dk[nd][2] * ksc, dk[nd][3] * ksc);
-      *reinterpret_cast<uint32_t*>(r0 + 256 + nd * 8 + 2 * c) =
-          pack_bf16x2(dv[nd][0] * inv_keep, dv[nd][1] * inv_keep);
-      *reinterpret_cast<uint32_t*>(r1 + 256 + nd * 8 + 2 * c) =
-          pack_bf16x2(dv[nd][2] * inv_keep, dv[nd][3] * inv_keep);
+        for (int hf = 0; hf < 2; ++hf) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(tS + sb * 64 + hf * 32, r);
+          tmem_ld_wait();
+          if (hf == 1) warp_release_tmem(&w.s_empty[sb], lane);
+          float m0 = __uint_as_float(r[0]), m1 = __uint_as_float(r[1]);
+#pragma unroll
+          for (int e = 2; e < 32; e += 2) {
+            m0 = fmaxf(m0, __uint_as_float(r[e]));
+            m1 = fmaxf(m1, __uint_as_float(r[e + 1]));
+          }
+          m = fmaxf(m, fmaxf(m0, m1));
+        }
+        ++ns;
+      }
+      const float mneg = m * kScaleLog2;
+      // ---- pass 2: P = exp2(S c - m c), row sum, dropout, P -> shared ----
+      float l0 = 0.f, l1 = 0.f;
+      const uint32_t rowctr = (uint32_t)(bh * kS + q) * 512u;
+      for (int j = 0; j < 16; ++j) {
+        const int sb = ns & 1;
+        mbar_wait(&w.s_full[sb], (ns >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(tS + sb * 64 + hf * 32, r);
+          tmem_ld_wait();
+          if (hf == 1) warp_release_tmem(&w.s_empty[sb], lane);
+          uint32_t pk[16];
+          uint32_t word = 0;
+          const uint32_t ctr0 = rowctr + (uint32_t)(j * 32 + hf * 16);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float p0 = ex2(fmaf(__uint_as_float(r[2 * i]), kScaleLog2, -mneg));
+            const float p1 = ex2(fmaf(__uint_as_float(r[2 * i + 1]), kScaleLog2, -mneg));
+            l0 += p0;
+            l1 += p1;
+            pk[i] = pack_bf16x2(p0, p1);
+            if (DROP) {
+              const uint32_t x = keep_x(key, ctr0 + i, addc);
+              pk[i] &= prmt(x, 0xBB99u);
+              if (DROP == 2) word = (word >> 1) | (x & 0x80008000u);
+            }
+          }
+          if (hf == 0) mbar_wait(&w.p_empty, (np & 1) ^ 1);  // the P V of the previous tile has read the buffer
+          store_chunks4(myP, row, hf * 4, pk);
+          if (DROP == 2) drop_bits[((size_t)bh * 32 + j * 2 + hf) * kS + q] = word;
+        }
+        warp_publish_smem(&w.p_full, lane);
+        ++np;
+        ++ns;
+      }
+      // ---- epilogue: O / l ----
+      mbar_wait(&w.o_full, it & 1);
+      tc_fence_after();
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(tO, r);
+      tmem_ld_wait();
+      warp_release_tmem(&w.o_empty, lane);
+      const float l = l0 + l1;
+      const float sc = inv_keep / l;
+      uint4* orow = reinterpret_cast<uint4*>(out + ((long)b * kS + q) * kLdO + h * 32);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint4 o;
+        o.x = pack_bf16x2(__uint_as_float(r[8 * c + 0]) * sc, __uint_as_float(r[8 * c + 1]) * sc);
+        o.y = pack_bf16x2(__uint_as_float(r[8 * c + 2]) * sc, __uint_as_float(r[8 * c + 3]) * sc);
+        o.z = pack_bf16x2(__uint_as_float(r[8 * c + 4]) * sc, __uint_as_float(r[8 * c + 5]) * sc);
+        o.w = pack_bf16x2(__uint_as_float(r[8 * c + 6]) * sc, __uint_as_float(r[8 * c + 7]) * sc);
+        orow[c] = o;
+      }
+      lse2[(long)bh * kS + q] = mneg + log2f(l);
     }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 3) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
   }
 }
 
-// warps per CTA (one CTA per SM: 128 KB of smem).  More resident warps hide the mma.sync / MUFU / ldmatrix
-// latencies of this issue-bound kernel; the register file caps them (65536 / (32 * regs)).
-constexpr int kFwdWarps = 16;  // <= 128 registers
-constexpr int kDqWarps = 8;   // measured: 8 warps (172 regs, no spills) beats 13/16 warps at the 128-register cap
+// ------------------------------------------------------------------------------------------------------------------
+// backward, shared by both passes: one 32-key half of a 128 x 64 tile.
+//   P = exp2(S c - L),  dS = P o (keep o dP - D'),  Pd = keep o P   (bf16 pairs)
+// ------------------------------------------------------------------------------------------------------------------
+template <int DROP, bool WITH_P>
+__device__ __forceinline__ void bwd_half(const uint32_t (&rs)[32], const uint32_t (&rd)[32], float L, float Dp,
+                                         uint32_t word, uint32_t (&ds)[16], uint32_t (&pd)[16]) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float p0 = ex2(fmaf(__uint_as_float(rs[2 * i]), kScaleLog2, -L));
+    const float p1 = ex2(fmaf(__uint_as_float(rs[2 * i + 1]), kScaleLog2, -L));
+    float e0 = __uint_as_float(rd[2 * i]), e1 = __uint_as_float(rd[2 * i + 1]);
+    uint32_t pp = 0;
+    if (WITH_P) pp = pack_bf16x2(p0, p1);
+    if (DROP) {
+      const uint32_t x = word << (15 - i);  // bit i -> 15, bit 16+i -> 31
+      e0 = __uint_as_float(rd[2 * i] & prmt(x, 0x9999u));
+      e1 = __uint_as_float(rd[2 * i + 1] & prmt(x, 0xBBBBu));
+      if (WITH_P) pp &= prmt(x, 0xBB99u);
+    }
+    ds[i] = pack_bf16x2(p0 * (e0 - Dp), p1 * (e1 - Dp));
+    if (WITH_P) pd[i] = pp;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// backward pass A: dQ (and D = rowsum(dO o O), written for pass B).
+// shared: K, V resident; per group a Q tile, a dO tile and a dS tile.  TMEM per group: S 64, dP 64, dQ 32 columns.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kDqSmem = 2 * kHeadBytes + 2 * (2 * kQTile + kPTile) + 1024 + 1024;
+
+template <int DROP>
+__global__ void __launch_bounds__(kThreads, 1)
+attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap mQkv, const __grid_constant__ CUtensorMap mDo,
+                   const bf16* __restrict__ o_in, const bf16* __restrict__ d_o, const float* __restrict__ lse2,
+                   float* __restrict__ dsum, bf16* __restrict__ dqkv, uint32_t key, uint32_t th15, float inv_keep,
+                   const uint32_t* __restrict__ drop_bits) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sK = smem;
+  uint8_t* sV = smem + kHeadBytes;
+  uint8_t* sQ = smem + 2 * kHeadBytes;   // [2 groups]
+  uint8_t* sDo = sQ + 2 * kQTile;        // [2 groups]
+  uint8_t* sDs = sDo + 2 * kQTile;       // [2 groups]
+  Bars* bars = reinterpret_cast<Bars*>(sDs + 2 * kPTile);
+  const int bh = blockIdx.x, b = bh >> 2, h = bh & 3;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mQkv);
+    tma_prefetch_desc(&mDo);
+  }
+  if (warp == 1 && lane == 0) init_bars(bars);
+  if (warp == 3) {
+    tmem_alloc(&bars->tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&bars->res_full, 2 * kHeadBytes);
+      for (int i = 0; i < 8; ++i) {
+        tma_load_2d(sK + i * kQTile, &mQkv, &bars->res_full, 128 + h * 32, b * kS + i * 128);
+        tma_load_2d(sV + i * kQTile, &mQkv, &bars->res_full, 256 + h * 32, b * kS + i * 128);
+      }
+      for (int it = 0; it < 4; ++it)
+        for (int g = 0; g < 2; ++g) {
+          WgBars& w = bars->wg[g];
+          mbar_wait(&w.a_empty, (it & 1) ^ 1);
+          mbar_arrive_expect_tx(&w.a_full, 2 * kQTile);
+          tma_load_2d(sQ + g * kQTile, &mQkv, &w.a_full, h * 32, b * kS + (g + 2 * it) * 128);
+          tma_load_2d(sDo + g * kQTile, &mDo, &w.a_full, h * 32, b * kS + (g + 2 * it) * 128);
+        }
+    }
+  } else if (warp == 1 || warp == 2) {
+    if (lane == 0) {
+      const int g = warp - 1;
+      WgBars& w = bars->wg[g];
+      const uint32_t tS = tmem + g * 160, tDp = tS + 64, tDq = tS + 128;
+      const uint32_t aQ = smem_u32(sQ + g * kQTile), aDo = smem_u32(sDo + g * kQTile), aDs = smem_u32(sDs + g * kPTile);
+      const uint32_t aK = smem_u32(sK), aV = smem_u32(sV);
+      mbar_wait(&bars->res_full, 0);
+      uint32_t n = 0;
+      for (int it = 0; it < 4; ++it) {
+        mbar_wait(&w.a_full, it & 1);
+        tc_fence_after();
+        for (int j = 0; j <= 16; ++j) {
+          if (j < 16) {
+            mbar_wait(&w.s_empty[0], (n & 1) ^ 1);
+            tc_fence_after();
+            mma_qk(tS, aQ, aK + j * 4096);
+            mma_qk(tDp, aDo, aV + j * 4096);
+            tc_commit(&w.s_full[0]);
+            if (j == 15) tc_commit(&w.a_empty);
+            ++n;
+          }
+          if (j >= 1) {  // dQ += dS K of key tile j - 1  (its tile counter is n - 2 for j < 16, n - 1 for j == 16)
+            const int jj = j - 1;
+            const uint32_t nn = (j < 16) ? n - 2 : n - 1;
+            mbar_wait(&w.p_full, nn & 1);
+            tc_fence_after();
+            if (jj == 0) {
+              mbar_wait(&w.o_empty, (it & 1) ^ 1);
+              tc_fence_after();
+            }
+            mma_pv(tDq, aDs, aK + jj * 4096, jj != 0);
+            tc_commit(&w.p_empty);
+          }
+        }
+        tc_commit(&w.o_full);
+      }
+    }
+  } else if (warp >= 4) {
+    const int g = (warp - 4) >> 2, quad = warp & 3, row = quad * 32 + lane;
+    WgBars& w = bars->wg[g];
+    const uint32_t tS = tmem + ((uint32_t)(quad * 32) << 16) + g * 160, tDp = tS + 64, tDq = tS + 128;
+    uint8_t* myDs = sDs + g * kPTile;
+    const uint32_t addc = (0x8000u - th15) * 0x00010001u;
+    const float keep_prob = 1.f / inv_keep;
+    uint32_t n = 0;
+    for (int it = 0; it < 4; ++it) {
+      const int q = (g + 2 * it) * 128 + row;
+      const long t = (long)b * kS + q;
+      const float L = lse2[(long)bh * kS + q];
+      float D = 0.f;
+      {
+        const uint4* po = reinterpret_cast<const uint4*>(o_in + t * kLdO + h * 32);
+        const uint4* pd = reinterpret_cast<const uint4*>(d_o + t * kLdO + h * 32);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint4 a = po[c], d = pd[c];
+          const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, dw[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 x = unpack_bf16x2(aw[e]), y = unpack_bf16x2(dw[e]);
+            D = fmaf(x.x, y.x, D);
+            D = fmaf(x.y, y.y, D);
+          }
+        }
+      }
+      dsum[(long)bh * kS + q] = D;
+      const float Dp = D * keep_prob;
+      const uint32_t rowctr = (uint32_t)(bh * kS + q) * 512u;
+      for (int j = 0; j < 16; ++j) {
+        uint32_t wd[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
+        if (DROP == 2) {
+          wd[0] = __ldg(drop_bits + ((size_t)bh * 32 + j * 2) * kS + q);
+          wd[1] = __ldg(drop_bits + ((size_t)bh * 32 + j * 2 + 1) * kS + q);
+        }
+        mbar_wait(&w.s_full[0], n & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          uint32_t rs[32], rd[32];
+          tmem_ld_32x32b_x32(tS + hf * 32, rs);
+          tmem_ld_32x32b_x32(tDp + hf * 32, rd);
+          tmem_ld_wait();
+          if (hf == 1) warp_release_tmem(&w.s_empty[0], lane);
+          if (DROP == 1) wd[hf] = hash_word(key, rowctr + (uint32_t)(j * 32 + hf * 16), addc);
+          uint32_t ds[16], pd[16];
+          bwd_half<DROP, false>(rs, rd, L, Dp, wd[hf], ds, pd);
+          if (hf == 0) mbar_wait(&w.p_empty, (n & 1) ^ 1);
+          store_chunks4(myDs, row, hf * 4, ds);
+        }
+        warp_publish_smem(&w.p_full, lane);
+        ++n;
+      }
+      mbar_wait(&w.o_full, it & 1);
+      tc_fence_after();
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(tDq, r);
+      tmem_ld_wait();
+      warp_release_tmem(&w.o_empty, lane);
+      const float sc = kScale * inv_keep;
+      uint4* drow = reinterpret_cast<uint4*>(dqkv + t * kLdQkv + h * 32);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint4 o;
+        o.x = pack_bf16x2(__uint_as_float(r[8 * c + 0]) * sc, __uint_as_float(r[8 * c + 1]) * sc);
+        o.y = pack_bf16x2(__uint_as_float(r[8 * c + 2]) * sc, __uint_as_float(r[8 * c + 3]) * sc);
+        o.z = pack_bf16x2(__uint_as_float(r[8 * c + 4]) * sc, __uint_as_float(r[8 * c + 5]) * sc);
+        o.w = pack_bf16x2(__uint_as_float(r[8 * c + 6]) * sc, __uint_as_float(r[8 * c + 7]) * sc);
+        drow[c] = o;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 3) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// backward pass B: dK, dV.  shared: Q, dO resident; per group a double-buffered (K_j, V_j) 64-key block, a P tile and
+// a dS tile.  TMEM per group: S 64, dP 64, dK 32, dV 32 columns (the two M = 64 accumulators use lanes
+// (r % 16) + 32 (r / 16)).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kKvBlk = 64 * 64;  // [64 keys][32] bf16
+constexpr int kDkvSmem = 2 * kHeadBytes + 2 * (4 * kKvBlk + 2 * kPTile) + 1024 + 1024;
+
+template <int DROP>
+__global__ void __launch_bounds__(kThreads, 1)
+attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mQkv, const __grid_constant__ CUtensorMap mQkv64,
+                    const __grid_constant__ CUtensorMap mDo, const float* __restrict__ lse2,
+                    const float* __restrict__ dsum, bf16* __restrict__ dqkv, uint32_t key, uint32_t th15, float inv_keep,
+                    const uint32_t* __restrict__ drop_bits) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sDo = smem + kHeadBytes;
+  uint8_t* sKv = smem + 2 * kHeadBytes;   // [2 groups][2 buffers][K_j | V_j]
+  uint8_t* sP = sKv + 2 * 4 * kKvBlk;     // [2 groups]
+  uint8_t* sDs = sP + 2 * kPTile;         // [2 groups]
+  Bars* bars = reinterpret_cast<Bars*>(sDs + 2 * kPTile);
+  const int bh = blockIdx.x, b = bh >> 2, h = bh & 3;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mQkv);
+    tma_prefetch_desc(&mQkv64);
+    tma_prefetch_desc(&mDo);
+  }
+  if (warp == 1 && lane == 0) init_bars(bars);
+  if (warp == 3) {
+    tmem_alloc(&bars->tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&bars->res_full, 2 * kHeadBytes);
+      for (int i = 0; i < 8; ++i) {
+        tma_load_2d(sQ + i * kQTile, &mQkv, &bars->res_full, h * 32, b * kS + i * 128);
+        tma_load_2d(sDo + i * kQTile, &mDo, &bars->res_full, h * 32, b * kS + i * 128);
+      }
+      for (int jt = 0; jt < 8; ++jt)
+        for (int g = 0; g < 2; ++g) {
+          WgBars& w = bars->wg[g];
+          const int kb = jt & 1, j = g + 2 * jt;
+          mbar_wait(&w.a2_empty[kb], ((jt >> 1) & 1) ^ 1);
+          mbar_arrive_expect_tx(&w.a2_full[kb], 2 * kKvBlk);
+          uint8_t* dst = sKv + (g * 2 + kb) * 2 * kKvBlk;
+          tma_load_2d(dst, &mQkv64, &w.a2_full[kb], 128 + h * 32, b * kS + j * 64);
+          tma_load_2d(dst + kKvBlk, &mQkv64, &w.a2_full[kb], 256 + h * 32, b * kS + j * 64);
+        }
+    }
+  } else if (warp == 1 || warp == 2) {
+    if (lane == 0) {
+      const int g = warp - 1;
+      WgBars& w = bars->wg[g];
+      const uint32_t tS = tmem + g * 192, tDp = tS + 64, tDk = tS + 128, tDv = tS + 160;
+      const uint32_t aQ = smem_u32(sQ), aDo = smem_u32(sDo);
+      const uint32_t aP = smem_u32(sP + g * kPTile), aDs = smem_u32(sDs + g * kPTile);
+      mbar_wait(&bars->res_full, 0);
+      uint32_t n = 0;
+      for (int jt = 0; jt < 8; ++jt) {
+        const int kb = jt & 1;
+        const uint32_t aKj = smem_u32(sKv + (g * 2 + kb) * 2 * kKvBlk), aVj = aKj + kKvBlk;
+        mbar_wait(&w.a2_full[kb], (jt >> 1) & 1);
+        tc_fence_after();
+        for (int i = 0; i <= 8; ++i) {
+          if (i < 8) {
+            mbar_wait(&w.s_empty[0], (n & 1) ^ 1);
+            tc_fence_after();
+            mma_qk(tS, aQ + i * kQTile, aKj);
+            mma_qk(tDp, aDo + i * kQTile, aVj);
+            tc_commit(&w.s_full[0]);
+            if (i == 7) tc_commit(&w.a2_empty[kb]);
+            ++n;
+          }
+          if (i >= 1) {  // dV += Pd^T dO, dK += dS^T Q of query tile i - 1
+            const int ii = i - 1;
+            const uint32_t nn = (i < 8) ? n - 2 : n - 1;
+            mbar_wait(&w.p_full, nn & 1);
+            tc_fence_after();
+            if (ii == 0) {
+              mbar_wait(&w.o_empty, (jt & 1) ^ 1);
+              tc_fence_after();
+            }
+            mma_ptdo(tDv, aP, aDo + ii * kQTile, ii != 0);
+            mma_ptdo(tDk, aDs, aQ + ii * kQTile, ii != 0);
+            tc_commit(&w.p_empty);
+          }
+        }
+        tc_commit(&w.o_full);
+      }
+    }
+  } else if (warp >= 4) {
+    const int g = (warp - 4) >> 2, quad = warp & 3, row = quad * 32 + lane;
+    WgBars& w = bars->wg[g];
+    const uint32_t tS = tmem + ((uint32_t)(quad * 32) << 16) + g * 192, tDp = tS + 64, tDk = tS + 128, tDv = tS + 160;
+    uint8_t* myP = sP + g * kPTile;
+    uint8_t* myDs = sDs + g * kPTile;
+    const uint32_t addc = (0x8000u - th15) * 0x00010001u;
+    const float keep_prob = 1.f / inv_keep;
+    uint32_t n = 0;
+    for (int jt = 0; jt < 8; ++jt) {
+      const int j = g + 2 * jt;  // 64-key block
+      for (int i = 0; i < 8; ++i) {
+        const int q = i * 128 + row;
+        const float L = lse2[(long)bh * kS + q];
+        const float Dp = dsum[(long)bh * kS + q] * keep_prob;
+        uint32_t wd[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
+        if (DROP == 2) {
+          wd[0] = __ldg(drop_bits + ((size_t)bh * 32 + j * 2) * kS + q);
+          wd[1] = __ldg(drop_bits + ((size_t)bh * 32 + j * 2 + 1) * kS + q);
+        }
+        const uint32_t rowctr = (uint32_t)(bh * kS + q) * 512u;
+        mbar_wait(&w.s_full[0], n & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          uint32_t rs[32], rd[32];
+          tmem_ld_32x32b_x32(tS + hf * 32, rs);
+          tmem_ld_32x32b_x32(tDp + hf * 32, rd);
+          tmem_ld_wait();
+          if (hf == 1) warp_release_tmem(&w.s_empty[0], lane);
+          if (DROP == 1) wd[hf] = hash_word(key, rowctr + (uint32_t)(j * 32 + hf * 16), addc);
+          uint32_t ds[16], pd[16];
+          bwd_half<DROP, true>(rs, rd, L, Dp, wd[hf], ds, pd);
+          if (hf == 0) mbar_wait(&w.p_empty, (n & 1) ^ 1);
+          store_chunks4(myDs, row, hf * 4, ds);
+          store_chunks4(myP, row, hf * 4, pd);
+        }
+        warp_publish_smem(&w.p_full, lane);
+        ++n;
+      }
+      mbar_wait(&w.o_full, jt & 1);
+      tc_fence_after();
+      uint32_t rk[32], rv[32];
+      tmem_ld_32x32b_x32(tDk, rk);
+      tmem_ld_32x32b_x32(tDv, rv);
+      tmem_ld_wait();
+      warp_release_tmem(&w.o_empty, lane);
+      if (lane < 16) {  // M = 64 accumulator: key row quad*16 + lane lives on TMEM lane quad*32 + lane
+        const long t = (long)b * kS + j * 64 + quad * 16 + lane;
+        const float ksc = kScale * inv_keep;
+        uint4* krow = reinterpret_cast<uint4*>(dqkv + t * kLdQkv + 128 + h * 32);
+        uint4* vrow = reinterpret_cast<uint4*>(dqkv + t * kLdQkv + 256 + h * 32);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint4 o;
+          o.x = pack_bf16x2(__uint_as_float(rk[8 * c + 0]) * ksc, __uint_as_float(rk[8 * c + 1]) * ksc);
+          o.y = pack_bf16x2(__uint_as_float(rk[8 * c + 2]) * ksc, __uint_as_float(rk[8 * c + 3]) * ksc);
+          o.z = pack_bf16x2(__uint_as_float(rk[8 * c + 4]) * ksc, __uint_as_float(rk[8 * c + 5]) * ksc);
+          o.w = pack_bf16x2(__uint_as_float(rk[8 * c + 6]) * ksc, __uint_as_float(rk[8 * c + 7]) * ksc);
+          krow[c] = o;
+          o.x = pack_bf16x2(__uint_as_float(rv[8 * c + 0]) * inv_keep, __uint_as_float(rv[8 * c + 1]) * inv_keep);
+          o.y = pack_bf16x2(__uint_as_float(rv[8 * c + 2]) * inv_keep, __uint_as_float(rv[8 * c + 3]) * inv_keep);
+          o.z = pack_bf16x2(__uint_as_float(rv[8 * c + 4]) * inv_keep, __uint_as_float(rv[8 * c + 5]) * inv_keep);
+          o.w = pack_bf16x2(__uint_as_float(rv[8 * c + 6]) * inv_keep, __uint_as_float(rv[8 * c + 7]) * inv_keep);
+          vrow[c] = o;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 3) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
 
 template <typename K>
 int set_smem(K kernel, int bytes) {
@@ -526,35 +715,50 @@ int set_smem(K kernel, int bytes) {
   return FOCR_OK;
 }
 
+struct AttnDrop {
+  uint32_t th15;
+  float inv_keep;
+};
+AttnDrop drop_params(uint32_t thresh16) {
+  AttnDrop d;
+  d.th15 = (thresh16 + 1) >> 1;  // p * 32768, rounded
+  d.inv_keep = 32768.f / (32768.f - (float)d.th15);
+  return d;
+}
+
 }  // namespace
 
 // p_drop = thresh16 / 65536; thresh16 == 0 disables dropout (eval / parity runs).  drop_bits: optional keep-bit
-// buffer of attn_drop_bits_bytes(B) bytes written by the forward and consumed by the backward (may be null).
-size_t attn_drop_bits_bytes(int B) { return (size_t)B * 4 * (kS / 16) * (kS / 64) * 32 * sizeof(uint32_t); }
+// buffer of attn_drop_bits_bytes(B) bytes written by the forward and consumed by the backward (may be null: the
+// backward then regenerates the mask from the seed).
+size_t attn_drop_bits_bytes(int B) { return (size_t)B * 4 * (kS / 32) * kS * sizeof(uint32_t); }
 
 int attn_forward(const bf16* qkv, bf16* out, float* lse2, int B, uint32_t key, uint32_t thresh16, uint32_t* drop_bits,
                  cudaStream_t s) {
   ProfScope _ps("attn_fwd", s);
   FOCR_REQUIRE(B >= 1 && B <= 1024, "attention: B=%d out of range", B);
-  const int smem = 2 * kTileBytes;
-  const float inv_keep = 65536.f / (65536.f - (float)thresh16);
+  static_assert(sizeof(Bars) <= 1024, "barrier block");
   static bool init = false;
   if (!init) {
-    int rc = set_smem(attn_fwd_kernel<0, kFwdWarps>, smem);
+    int rc = set_smem(attn_fwd_kernel<0>, kFwdSmem);
     if (rc) return rc;
-    rc = set_smem(attn_fwd_kernel<1, kFwdWarps>, smem);
+    rc = set_smem(attn_fwd_kernel<1>, kFwdSmem);
     if (rc) return rc;
-    rc = set_smem(attn_fwd_kernel<2, kFwdWarps>, smem);
+    rc = set_smem(attn_fwd_kernel<2>, kFwdSmem);
     if (rc) return rc;
     init = true;
   }
-  const dim3 grid(B * 4), block(kFwdWarps * 32);
+  CUtensorMap mq;
+  int rc = focr_make_tmap_2d(&mq, qkv, kLdQkv, (unsigned long long)B * kS, kLdQkv * 2, 32, 128, 64);
+  if (rc) return rc;
+  const AttnDrop d = drop_params(thresh16);
+  const dim3 grid(B * 4), block(kThreads);
   if (!thresh16)
-    attn_fwd_kernel<0, kFwdWarps><<<grid, block, smem, s>>>(qkv, out, lse2, key, 0, 1.f, nullptr);
+    attn_fwd_kernel<0><<<grid, block, kFwdSmem, s>>>(mq, out, lse2, key, 0, 1.f, nullptr);
   else if (!drop_bits)
-    attn_fwd_kernel<1, kFwdWarps><<<grid, block, smem, s>>>(qkv, out, lse2, key, thresh16, inv_keep, nullptr);
+    attn_fwd_kernel<1><<<grid, block, kFwdSmem, s>>>(mq, out, lse2, key, d.th15, d.inv_keep, nullptr);
   else
-    attn_fwd_kernel<2, kFwdWarps><<<grid, block, smem, s>>>(qkv, out, lse2, key, thresh16, inv_keep, drop_bits);
+    attn_fwd_kernel<2><<<grid, block, kFwdSmem, s>>>(mq, out, lse2, key, d.th15, d.inv_keep, drop_bits);
   FOCR_LAUNCH_CHECK();
   return FOCR_OK;
 }
@@ -562,46 +766,53 @@ int attn_forward(const bf16* qkv, bf16* out, float* lse2, int B, uint32_t key, u
 int attn_backward(const bf16* qkv, const bf16* o, const bf16* d_o, const float* lse2, float* dsum, bf16* dqkv, int B,
                   uint32_t key, uint32_t thresh16, const uint32_t* drop_bits, cudaStream_t s) {
   FOCR_REQUIRE(B >= 1 && B <= 1024, "attention: B=%d out of range", B);
-  const int smem_a = 2 * kTileBytes, smem_b = 2 * kTileBytes + 2 * kS * 4 + 2 * 16384;
-  const float inv_keep = 65536.f / (65536.f - (float)thresh16);
   static bool init = false;
   if (!init) {
-    int rc = set_smem(attn_bwd_dq_kernel<0, kDqWarps>, smem_a);
+    int rc = set_smem(attn_bwd_dq_kernel<0>, kDqSmem);
     if (rc) return rc;
-    rc = set_smem(attn_bwd_dq_kernel<1, kDqWarps>, smem_a);
+    rc = set_smem(attn_bwd_dq_kernel<1>, kDqSmem);
     if (rc) return rc;
-    rc = set_smem(attn_bwd_dq_kernel<2, kDqWarps>, smem_a);
+    rc = set_smem(attn_bwd_dq_kernel<2>, kDqSmem);
     if (rc) return rc;
-    rc = set_smem(attn_bwd_dkv_kernel<0>, smem_b);
+    rc = set_smem(attn_bwd_dkv_kernel<0>, kDkvSmem);
     if (rc) return rc;
-    rc = set_smem(attn_bwd_dkv_kernel<1>, smem_b);
+    rc = set_smem(attn_bwd_dkv_kernel<1>, kDkvSmem);
     if (rc) return rc;
-    rc = set_smem(attn_bwd_dkv_kernel<2>, smem_b);
+    rc = set_smem(attn_bwd_dkv_kernel<2>, kDkvSmem);
     if (rc) return rc;
     init = true;
   }
-  const dim3 grid(B * 4);
+  CUtensorMap mq, mq64, mdo;
+  int rc = focr_make_tmap_2d(&mq, qkv, kLdQkv, (unsigned long long)B * kS, kLdQkv * 2, 32, 128, 64);
+  if (rc) return rc;
+  rc = focr_make_tmap_2d(&mq64, qkv, kLdQkv, (unsigned long long)B * kS, kLdQkv * 2, 32, 64, 64);
+  if (rc) return rc;
+  rc = focr_make_tmap_2d(&mdo, d_o, kLdO, (unsigned long long)B * kS, kLdO * 2, 32, 128, 64);
+  if (rc) return rc;
+  const AttnDrop d = drop_params(thresh16);
+  const dim3 grid(B * 4), block(kThreads);
   {
     ProfScope ps("attn_bwd_dq", s);
     if (!thresh16)
-      attn_bwd_dq_kernel<0, kDqWarps><<<grid, kDqWarps * 32, smem_a, s>>>(qkv, o, d_o, lse2, dsum, dqkv, key, 0, 1.f,
-                                                                          nullptr);
+      attn_bwd_dq_kernel<0><<<grid, block, kDqSmem, s>>>(mq, mdo, o, d_o, lse2, dsum, dqkv, key, 0, 1.f, nullptr);
     else if (!drop_bits)
-      attn_bwd_dq_kernel<1, kDqWarps><<<grid, kDqWarps * 32, smem_a, s>>>(qkv, o, d_o, lse2, dsum, dqkv, key, thresh16,
-                                                                          inv_keep, nullptr);
+      attn_bwd_dq_kernel<1><<<grid, block, kDqSmem, s>>>(mq, mdo, o, d_o, lse2, dsum, dqkv, key, d.th15, d.inv_keep,
+                                                         nullptr);
     else
-      attn_bwd_dq_kernel<2, kDqWarps><<<grid, kDqWarps * 32, smem_a, s>>>(qkv, o, d_o, lse2, dsum, dqkv, key, thresh16,
-                                                                          inv_keep, drop_bits);
+      attn_bwd_dq_kernel<2><<<grid, block, kDqSmem, s>>>(mq, mdo, o, d_o, lse2, dsum, dqkv, key, d.th15, d.inv_keep,
+                                                         drop_bits);
     FOCR_LAUNCH_CHECK();
   }
   {
     ProfScope ps("attn_bwd_dkv", s);
     if (!thresh16)
-      attn_bwd_dkv_kernel<0><<<grid, 256, smem_b, s>>>(qkv, d_o, lse2, dsum, dqkv, key, 0, 1.f, nullptr);
+      attn_bwd_dkv_kernel<0><<<grid, block, kDkvSmem, s>>>(mq, mq64, mdo, lse2, dsum, dqkv, key, 0, 1.f, nullptr);
     else if (!drop_bits)
-      attn_bwd_dkv_kernel<1><<<grid, 256, smem_b, s>>>(qkv, d_o, lse2, dsum, dqkv, key, thresh16, inv_keep, nullptr);
+      attn_bwd_dkv_kernel<1><<<grid, block, kDkvSmem, s>>>(mq, mq64, mdo, lse2, dsum, dqkv, key, d.th15, d.inv_keep,
+                                                           nullptr);
     else
-      attn_bwd_dkv_kernel<2><<<grid, 256, smem_b, s>>>(qkv, d_o, lse2, dsum, dqkv, key, thresh16, inv_keep, drop_bits);
+      attn_bwd_dkv_kernel<2><<<grid, block, kDkvSmem, s>>>(mq, mq64, mdo, lse2, dsum, dqkv, key, d.th15, d.inv_keep,
+                                                           drop_bits);
     FOCR_LAUNCH_CHECK();
   }
   return FOCR_OK;

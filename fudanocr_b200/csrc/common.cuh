@@ -280,6 +280,25 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
          ((uint32_t)(M >> 4) << 24);
 }
 
+// General UMMA shared-memory operand descriptor (sm_100 version 1).  layout: 0 none, 2 = 128B, 4 = 64B,
+// 6 = 32B swizzle.  K-major operand: SBO = bytes between 8-row groups; MN-major operand: SBO = bytes between
+// 8-deep K groups, LBO = bytes between swizzle atoms along M/N.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                              uint32_t layout) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout << 61;
+  return d;
+}
+// kind::f16 instruction descriptor with explicit operand majors (0 = K-major, 1 = MN-major)
+__host__ __device__ constexpr uint32_t umma_idesc_bf16_ex(int M, int N, int a_mn, int b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
 // ----------------------------------------------------------------------------------
 // legacy-path helpers (mma.sync m16n8k16 bf16, ldmatrix, cp.async) for the kernels whose
 // operand gathers need per-row addressing

@@ -486,6 +486,31 @@ int launch_impl(const CUtensorMap* am, const CUtensorMap& bm, const CUtensorMap&
 
 }  // namespace
 
+int focr_make_tmap_2d(CUtensorMap* out, const void* base, unsigned long long inner, unsigned long long outer,
+                      unsigned long long row_bytes, unsigned box_inner, unsigned box_outer, int swizzle_bytes) {
+  PFN_tmapEncodeTiled enc = get_encode();
+  if (!enc) {
+    focr_set_error("cuTensorMapEncodeTiled entry point unavailable");
+    return FOCR_ERR_CUDA;
+  }
+  const cuuint64_t dims[2] = {inner, outer};
+  const cuuint64_t str[1] = {row_bytes};
+  const cuuint32_t box[2] = {box_inner, box_outer};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128  ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                      : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, str, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    focr_set_error("cuTensorMapEncodeTiled failed (%d) for a %llu x %llu map", (int)r, inner, outer);
+    return FOCR_ERR_CUDA;
+  }
+  return FOCR_OK;
+}
+
 int tc_gemm_block_n(int n_total) {
   if (n_total % 128 == 0) return 128;
   return 64;

@@ -67,13 +67,20 @@ int focr_layernorm_std_bwd(const void* dy, const void* x, const float* a, void* 
  * qkv (B*1024,384) bf16 = [q|k|v]; out (B*1024,128); lse2 fp32 (B*4*1024).  Dropout on P with rate p_drop; the
  * keep mask is a counter hash of (seed, stream_id, b, h, q, k).  drop_bits (device, focr_mha_drop_bits_bytes(B)
  * bytes, or NULL): when given, the forward stores its keep decisions there (1 bit per element) and the backward
- * reads them instead of re-hashing (the fast path); with NULL the backward regenerates the mask from the seed. */
+ * reads them instead of re-hashing (the fast path); with NULL the backward regenerates the mask from the seed.
+ * Bit layout: word [b*4+h][k/32][q] (uint32), key k of the 32-key group at bit (k%32)/2 + 16*(k&1). */
 size_t focr_mha_drop_bits_bytes(int B);
 int focr_mha_flash_fwd(const void* qkv, void* out, float* lse2, int B, float p_drop, unsigned seed, unsigned stream_id,
                        void* drop_bits, void* stream);
 int focr_mha_flash_bwd(const void* qkv, const void* out, const void* d_out, const float* lse2, float* dsum_ws,
                        void* dqkv, int B, float p_drop, unsigned seed, unsigned stream_id, const void* drop_bits,
                        void* stream);
+
+/* tcgen05 operand-descriptor probe (test support for the attention kernels): copies `img` to shared memory, issues
+ * nk MMAs D += A.B with the two 64-bit operand descriptors (start address relative to the image, advanced by
+ * a_step16 / b_step16 16-byte units per step) and dumps the 128-lane x ncols fp32 TMEM accumulator to `out`. */
+int focr_umma_probe(const void* img, int img_bytes, unsigned long long desc_a, unsigned long long desc_b, unsigned idesc,
+                    int nk, unsigned a_step16, unsigned b_step16, float* out, int ncols, void* stream);
 
 /* --- step body: STT/interfaces/super_resolution.py:69-84, STT/loss/text_focus_loss.py:86, base.py:194-198 ------ */
 int focr_mse_loss_grad(const float* sr, const float* hr, float* d_sr, float* loss, long n, float gscale, void* ws,

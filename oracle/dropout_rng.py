@@ -33,10 +33,23 @@ def _keep(key: int, elem_index: np.ndarray, th: int) -> np.ndarray:
     return lane >= np.uint64(th)
 
 
+def thresh15(p: float) -> int:
+    """attention.cu compares 15-bit lanes: th15 = (thresh16 + 1) >> 1"""
+    return (thresh16(p) + 1) >> 1
+
+
 def attn_keep_mask(B: int, seed: int, blk: int, p: float) -> torch.Tensor:
-    """(B,4,1024,1024) bool: element (b,h,q,k) has index ((b*4+h)*1024+q)*1024 + k (attention.cu)."""
+    """(B,4,1024,1024) bool: element (b,h,q,k) has index ((b*4+h)*1024+q)*1024 + k; its hash (counter index >> 1)
+    carries two 15-bit lanes (bits 0-14 for even k, bits 16-30 for odd k); kept iff lane >= th15 (attention.cu)."""
     idx = np.arange(B * 4 * 1024 * 1024, dtype=np.uint64)
-    return torch.from_numpy(_keep(drop_key(seed, 2 * blk), idx, thresh16(p)).reshape(B, 4, 1024, 1024))
+    h = hash32(drop_key(seed, 2 * blk), idx >> np.uint64(1))
+    lane = np.where((idx & np.uint64(1)) == 0, h & np.uint64(0x7FFF), (h >> np.uint64(16)) & np.uint64(0x7FFF))
+    return torch.from_numpy((lane >= np.uint64(thresh15(p))).reshape(B, 4, 1024, 1024))
+
+
+def attn_keep_scale(p: float) -> float:
+    """attention.cu scales kept probabilities by 32768/(32768-th15)"""
+    return 32768.0 / (32768.0 - thresh15(p))
 
 
 def ffn_keep_mask(B: int, seed: int, blk: int, p: float) -> torch.Tensor:

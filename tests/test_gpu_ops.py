@@ -135,15 +135,15 @@ def test_attention_fwd_bwd(B, p_drop, use_bits):
     _sync(L)
     keep = R.attn_keep_mask(B, seed, blk, p_drop).to(DEV) if p_drop > 0 else None
     if use_bits and p_drop > 0:
-        # decode the fragment-layout words back to a (B,4,1024,1024) mask: word [bh][q/16][k/64][lane=(q%8)*4+(k%8)/2],
-        # bit 16*((q%16)//8) + 2*((k%64)//8) + (k&1)
-        w = bits.view(B, 4, 64, 16, 8, 4).long() & 0xFFFFFFFF        # [b,h,u,kt,g,c]
-        sh = torch.arange(32, device=DEV).view(2, 8, 2)               # [half, n, j]
-        m = (w[..., None, None, None] >> sh) & 1                      # [b,h,u,kt,g,c,half,n,j]
-        m = m.permute(0, 1, 2, 6, 4, 3, 7, 5, 8).reshape(B, 4, 1024, 1024)   # q=(u,half,g)  k=(kt,n,c,j)
+        # decode: word [b,h,k/32,q], key k of the group at bit (k%32)//2 + 16*(k&1)
+        w = bits.view(B, 4, 32, 1024).long() & 0xFFFFFFFF             # [b,h,kw,q]
+        kk = torch.arange(32, device=DEV)
+        sh = kk // 2 + 16 * (kk & 1)
+        m = (w[..., None] >> sh) & 1                                   # [b,h,kw,q,kk]
+        m = m.permute(0, 1, 3, 2, 4).reshape(B, 4, 1024, 1024)
         assert torch.equal(m.bool(), keep.bool())
     qr = qkv.float().requires_grad_(True)
-    ref = _attn_ref(qr, B, keep, R.keep_scale(p_drop))
+    ref = _attn_ref(qr, B, keep, R.attn_keep_scale(p_drop))
     assert _rel(out, ref) < 1e-2, _rel(out, ref)
     # log-sum-exp (log2 domain)
     q, k = [qkv.float()[:, i * 128:(i + 1) * 128].view(B, 1024, 4, 32).transpose(1, 2) for i in range(2)]
