@@ -19,10 +19,11 @@
 //               the TMEM accumulator is ever needed; S is double-buffered in TMEM
 //   backward A: dQ  (query tile outer, key tiles inner; also writes D = rowsum(dO o O))
 //   backward B: dK, dV (64-key block outer, query tiles inner)
-// Dropout: counter hash of common.cuh keyed on (b,h,q,k/2); each 32-bit hash carries two 15-bit lanes, element k
-// is DROPPED when lane (k & 1) < th15 (th15 = round(p * 32768)).  The forward can store its keep decisions, one
-// word per (q, 32 keys): word [bh][k/32][q], bit (k%32)/2 + 16 (k&1); the backward then reads bits instead of
-// re-hashing.  The 1/(1-p) factor is folded into the output scales: P V and dV accumulate kept probabilities
+// Dropout: counter hash of common.cuh keyed on (b,h,q,k/4); each 32-bit hash carries four 7-bit lanes (the low 7
+// bits of its bytes), element k is DROPPED when lane (k & 3) < th7, th7 = round(p * 128) - the rate is quantised to
+// 1/128 (p = 0.1 -> 13/128) and the 1/(1-p) rescale uses the quantised rate, so the expectation is exact.  The
+// forward can store its keep decisions, one word per (q, 32 keys): word [bh][k/32][q], bit 8 (k&3) + (k%32)/4; the
+// backward then reads bits instead of re-hashing.  The 1/(1-p) factor is folded into the output scales: P V and dV accumulate kept probabilities
 // unscaled, dS = P o (keep o dP - D (1-p)) / (1-p).
 #include "kernels.cuh"
 
@@ -79,17 +80,30 @@ __device__ __forceinline__ void mma_ptdo(uint32_t tmem_d, uint32_t a_addr, uint3
   for (int ks = 0; ks < 8; ++ks) tc_mma_bf16(tmem_d, da + 128 * ks, db + 64 * ks, idesc, (acc || ks) ? 1u : 0u);
 }
 
-// keep decisions of 32 consecutive keys of one query row.  x = (hash & 0x7FFF7FFF) + addc has bit 15 / bit 31 set iff
-// the even / odd key of the pair is kept (addc = (0x8000 - th15) * 0x00010001).
+// keep decisions of 4 consecutive keys of one query row: x = (hash & 0x7F7F7F7F) + addc has the msb of byte j set iff
+// key 4*ctr + j is kept (addc = (128 - th7) * 0x01010101); 8 such x build the 32-key word.
 __device__ __forceinline__ uint32_t keep_x(uint32_t key, uint32_t ctr, uint32_t addc) {
-  return (drop_hash32(key, ctr) & 0x7FFF7FFFu) + addc;
+  return (drop_hash32(key, ctr) & 0x7F7F7F7Fu) + addc;
 }
 __device__ __forceinline__ uint32_t hash_word(uint32_t key, uint32_t ctr0, uint32_t addc) {
   uint32_t w = 0;
 #pragma unroll
-  for (int i = 0; i < 16; ++i) w = (w >> 1) | (keep_x(key, ctr0 + i, addc) & 0x80008000u);
+  for (int i = 0; i < 8; ++i) w = (w >> 1) | (keep_x(key, ctr0 + i, addc) & 0x80808080u);
   return w;
 }
+
+// optional clock trace of one softmax warp (block 0, warp 4, lane 0) for tuning: focr_attn_set_trace()
+__device__ long long* g_attn_trace = nullptr;
+struct Tracer {
+  long long* p;
+  __device__ __forceinline__ Tracer(int warp, int lane) {
+    long long* t = g_attn_trace;
+    p = (t != nullptr && blockIdx.x == 0 && warp == 4 && lane == 0) ? t : nullptr;
+  }
+  __device__ __forceinline__ void mark() {
+    if (p) *p++ = clock64();
+  }
+};
 
 struct WgBars {      // per softmax group
   uint64_t a_full;   // per-tile operand(s) of this group landed (TMA)
@@ -105,13 +119,13 @@ struct WgBars {      // per softmax group
 };
 struct Bars {
   uint64_t res_full;  // the resident head slices landed
-  WgBars wg[2];
+  WgBars wg[4];
   uint32_t tmem_slot;
 };
 
 __device__ __forceinline__ void init_bars(Bars* bars) {
   mbar_init(&bars->res_full, 1);
-  for (int g = 0; g < 2; ++g) {
+  for (int g = 0; g < 4; ++g) {
     WgBars& w = bars->wg[g];
     mbar_init(&w.a_full, 1);
     mbar_init(&w.a_empty, 1);
@@ -147,28 +161,40 @@ __device__ __forceinline__ void store_chunks4(uint8_t* tile, int row, int chunk0
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// forward.  shared: K, V resident (2 x 64 KB); per group a Q tile (8 KB) and a P tile (16 KB).
-// TMEM per group: S[2] (2 x 64 columns), O (32 columns).
+// forward.  NWG softmax groups (2, 3 or 4) work on different 128-query tiles of the same (batch, head) at once; warp g
+// (lane 0) issues the MMAs and the Q-tile TMA of group g, warps 4.. are the softmax groups.
+// shared: K, V resident (2 x 64 KB); per group a Q tile (8 KB) and a P tile (16 KB).
+// TMEM per group: S ring (2 x 64 columns; 1 x 64 with four groups) and O (32 columns).
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int kFwdSmem = 2 * kHeadBytes + 2 * (kQTile + kPTile) + 1024 /*barriers*/ + 1024 /*alignment*/;
+template <int NWG>
+struct FwdCfg {
+  static constexpr int kSB = NWG == 4 ? 1 : 2;       // S buffers per group
+  static constexpr int kCols = kSB * 64 + 32;        // TMEM columns per group
+  static constexpr int kThreads = 128 + NWG * 128;
+  static constexpr int kSmem = 2 * kHeadBytes + NWG * (kQTile + kPTile) + 1024 /*barriers*/ + 1024 /*alignment*/;
+};
 
-template <int DROP>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int DROP, int NWG>
+__global__ void __launch_bounds__(FwdCfg<NWG>::kThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap mQkv, bf16* __restrict__ out, float* __restrict__ lse2, uint32_t key,
-                uint32_t th15, float inv_keep, uint32_t* __restrict__ drop_bits) {
+                uint32_t th7, float inv_keep, uint32_t* __restrict__ drop_bits) {
+  using Cfg = FwdCfg<NWG>;
+  constexpr int SB = Cfg::kSB;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* sK = smem;
   uint8_t* sV = smem + kHeadBytes;
-  uint8_t* sQ = smem + 2 * kHeadBytes;             // [2 groups]
-  uint8_t* sP = sQ + 2 * kQTile;                   // [2 groups]
-  Bars* bars = reinterpret_cast<Bars*>(sP + 2 * kPTile);
+  uint8_t* sQ = smem + 2 * kHeadBytes;             // [NWG]
+  uint8_t* sP = sQ + NWG * kQTile;                 // [NWG]
+  Bars* bars = reinterpret_cast<Bars*>(sP + NWG * kPTile);
   const int bh = blockIdx.x, b = bh >> 2, h = bh & 3;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  if (warp == 0 && lane == 0) tma_prefetch_desc(&mQkv);
-  if (warp == 1 && lane == 0) init_bars(bars);
-  if (warp == 3) {
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mQkv);
+    init_bars(bars);
+  }
+  if (warp == 1) {
     tmem_alloc(&bars->tmem_slot, 512);
     tmem_relinquish();
   }
@@ -177,36 +203,31 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mQkv, bf16* __restrict__ out
   tc_fence_after();
   const uint32_t tmem = bars->tmem_slot;
 
-  if (warp == 0) {
+  if (warp < NWG) {
     if (lane == 0) {
-      mbar_arrive_expect_tx(&bars->res_full, 2 * kHeadBytes);
-      for (int i = 0; i < 8; ++i) {
-        tma_load_2d(sK + i * kQTile, &mQkv, &bars->res_full, 128 + h * 32, b * kS + i * 128);
-        tma_load_2d(sV + i * kQTile, &mQkv, &bars->res_full, 256 + h * 32, b * kS + i * 128);
-      }
-      for (int it = 0; it < 4; ++it)
-        for (int g = 0; g < 2; ++g) {
-          WgBars& w = bars->wg[g];
-          mbar_wait(&w.a_empty, (it & 1) ^ 1);
-          mbar_arrive_expect_tx(&w.a_full, kQTile);
-          tma_load_2d(sQ + g * kQTile, &mQkv, &w.a_full, h * 32, b * kS + (g + 2 * it) * 128);
-        }
-    }
-  } else if (warp == 1 || warp == 2) {
-    if (lane == 0) {
-      const int g = warp - 1;
+      const int g = warp;
       WgBars& w = bars->wg[g];
-      const uint32_t tS = tmem + g * 160, tO = tmem + g * 160 + 128;
+      if (g == 0) {
+        mbar_arrive_expect_tx(&bars->res_full, 2 * kHeadBytes);
+        for (int i = 0; i < 8; ++i) {
+          tma_load_2d(sK + i * kQTile, &mQkv, &bars->res_full, 128 + h * 32, b * kS + i * 128);
+          tma_load_2d(sV + i * kQTile, &mQkv, &bars->res_full, 256 + h * 32, b * kS + i * 128);
+        }
+      }
+      const uint32_t tS = tmem + g * Cfg::kCols, tO = tS + SB * 64;
       const uint32_t aQ = smem_u32(sQ + g * kQTile), aP = smem_u32(sP + g * kPTile);
       const uint32_t aK = smem_u32(sK), aV = smem_u32(sV);
-      mbar_wait(&bars->res_full, 0);
       uint32_t ns = 0, np = 0;
-      for (int it = 0; it < 4; ++it) {
-        mbar_wait(&w.a_full, it & 1);
+      for (int it = 0; g + NWG * it < 8; ++it) {
+        mbar_wait_parked(&w.a_empty, (it & 1) ^ 1);  // every S MMA of the previous tile has read the Q buffer
+        mbar_arrive_expect_tx(&w.a_full, kQTile);
+        tma_load_2d(sQ + g * kQTile, &mQkv, &w.a_full, h * 32, b * kS + (g + NWG * it) * 128);
+        if (it == 0) mbar_wait_parked(&bars->res_full, 0);
+        mbar_wait_parked(&w.a_full, it & 1);
         tc_fence_after();
         for (int j = 0; j < 32; ++j) {  // 16 key tiles for the max pass, 16 for the exp / PV pass
-          const int sb = ns & 1;
-          mbar_wait(&w.s_empty[sb], ((ns >> 1) & 1) ^ 1);
+          const int sb = ns % SB;
+          mbar_wait_parked(&w.s_empty[sb], ((ns / SB) & 1) ^ 1);
           tc_fence_after();
           mma_qk(tS + sb * 64, aQ, aK + (j & 15) * 4096);
           tc_commit(&w.s_full[sb]);
@@ -214,10 +235,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mQkv, bf16* __restrict__ out
           if (j == 31) tc_commit(&w.a_empty);
           if (j >= 17) {  // P V of key tile j - 17
             const int jj = j - 17;
-            mbar_wait(&w.p_full, np & 1);
+            mbar_wait_parked(&w.p_full, np & 1);
             tc_fence_after();
             if (jj == 0) {
-              mbar_wait(&w.o_empty, (it & 1) ^ 1);
+              mbar_wait_parked(&w.o_empty, (it & 1) ^ 1);
               tc_fence_after();
             }
             mma_pv(tO, aP, aV + jj * 4096, jj != 0);
@@ -225,7 +246,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mQkv, bf16* __restrict__ out
             ++np;
           }
         }
-        mbar_wait(&w.p_full, np & 1);
+        mbar_wait_parked(&w.p_full, np & 1);
         tc_fence_after();
         mma_pv(tO, aP, aV + 15 * 4096, true);
         tc_commit(&w.p_empty);
@@ -236,17 +257,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mQkv, bf16* __restrict__ out
   } else if (warp >= 4) {
     const int g = (warp - 4) >> 2, quad = warp & 3, row = quad * 32 + lane;
     WgBars& w = bars->wg[g];
-    const uint32_t tS = tmem + ((uint32_t)(quad * 32) << 16) + g * 160, tO = tS + 128;
+    const uint32_t tS = tmem + ((uint32_t)(quad * 32) << 16) + g * Cfg::kCols, tO = tS + SB * 64;
     uint8_t* myP = sP + g * kPTile;
-    const uint32_t addc = (0x8000u - th15) * 0x00010001u;
+    const uint32_t addc = (128u - th7) * 0x01010101u;
     uint32_t ns = 0, np = 0;
-    for (int it = 0; it < 4; ++it) {
-      const int q = (g + 2 * it) * 128 + row;
+    Tracer tr(warp, lane);
+    for (int it = 0; g + NWG * it < 8; ++it) {
+      const int q = (g + NWG * it) * 128 + row;
       // ---- pass 1: exact row maximum ----
       float m = -INFINITY;
       for (int j = 0; j < 16; ++j) {
-        const int sb = ns & 1;
-        mbar_wait(&w.s_full[sb], (ns >> 1) & 1);
+        const int sb = ns % SB;
+        tr.mark();
+        mbar_wait(&w.s_full[sb], (ns / SB) & 1);
+        tr.mark();
         tc_fence_after();
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
@@ -267,10 +291,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mQkv, bf16* __restrict__ out
       const float mneg = m * kScaleLog2;
       // ---- pass 2: P = exp2(S c - m c), row sum, dropout, P -> shared ----
       float l0 = 0.f, l1 = 0.f;
-      const uint32_t rowctr = (uint32_t)(bh * kS + q) * 512u;
+      const uint32_t rowctr = (uint32_t)(bh * kS + q) * 256u;
       for (int j = 0; j < 16; ++j) {
-        const int sb = ns & 1;
-        mbar_wait(&w.s_full[sb], (ns >> 1) & 1);
+        const int sb = ns % SB;
+        tr.mark();
+        mbar_wait(&w.s_full[sb], (ns / SB) & 1);
+        tr.mark();
         tc_fence_after();
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
@@ -278,32 +304,42 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mQkv, bf16* __restrict__ out
           tmem_ld_32x32b_x32(tS + sb * 64 + hf * 32, r);
           tmem_ld_wait();
           if (hf == 1) warp_release_tmem(&w.s_empty[sb], lane);
+          tr.mark();
           uint32_t pk[16];
           uint32_t word = 0;
-          const uint32_t ctr0 = rowctr + (uint32_t)(j * 32 + hf * 16);
+          const uint32_t ctr0 = rowctr + (uint32_t)(j * 16 + hf * 8);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float p0 = ex2(fmaf(__uint_as_float(r[2 * i]), kScaleLog2, -mneg));
-            const float p1 = ex2(fmaf(__uint_as_float(r[2 * i + 1]), kScaleLog2, -mneg));
-            l0 += p0;
-            l1 += p1;
-            pk[i] = pack_bf16x2(p0, p1);
+          for (int i = 0; i < 8; ++i) {
+            float p[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) p[e] = ex2(fmaf(__uint_as_float(r[4 * i + e]), kScaleLog2, -mneg));
+            l0 += p[0] + p[2];
+            l1 += p[1] + p[3];
+            pk[2 * i] = pack_bf16x2(p[0], p[1]);
+            pk[2 * i + 1] = pack_bf16x2(p[2], p[3]);
             if (DROP) {
               const uint32_t x = keep_x(key, ctr0 + i, addc);
-              pk[i] &= prmt(x, 0xBB99u);
-              if (DROP == 2) word = (word >> 1) | (x & 0x80008000u);
+              pk[2 * i] &= prmt(x, 0x9988u);
+              pk[2 * i + 1] &= prmt(x, 0xBBAAu);
+              if (DROP == 2) word = (word >> 1) | (x & 0x80808080u);
             }
           }
+          tr.mark();
           if (hf == 0) mbar_wait(&w.p_empty, (np & 1) ^ 1);  // the P V of the previous tile has read the buffer
+          tr.mark();
           store_chunks4(myP, row, hf * 4, pk);
           if (DROP == 2) drop_bits[((size_t)bh * 32 + j * 2 + hf) * kS + q] = word;
         }
+        tr.mark();
         warp_publish_smem(&w.p_full, lane);
+        tr.mark();
         ++np;
         ++ns;
       }
       // ---- epilogue: O / l ----
+      tr.mark();
       mbar_wait(&w.o_full, it & 1);
+      tr.mark();
       tc_fence_after();
       uint32_t r[32];
       tmem_ld_32x32b_x32(tO, r);
@@ -327,7 +363,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mQkv, bf16* __restrict__ out
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 3) {
+  if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
   }
@@ -341,20 +377,35 @@ template <int DROP, bool WITH_P>
 __device__ __forceinline__ void bwd_half(const uint32_t (&rs)[32], const uint32_t (&rd)[32], float L, float Dp,
                                          uint32_t word, uint32_t (&ds)[16], uint32_t (&pd)[16]) {
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const float p0 = ex2(fmaf(__uint_as_float(rs[2 * i]), kScaleLog2, -L));
-    const float p1 = ex2(fmaf(__uint_as_float(rs[2 * i + 1]), kScaleLog2, -L));
-    float e0 = __uint_as_float(rd[2 * i]), e1 = __uint_as_float(rd[2 * i + 1]);
-    uint32_t pp = 0;
-    if (WITH_P) pp = pack_bf16x2(p0, p1);
-    if (DROP) {
-      const uint32_t x = word << (15 - i);  // bit i -> 15, bit 16+i -> 31
-      e0 = __uint_as_float(rd[2 * i] & prmt(x, 0x9999u));
-      e1 = __uint_as_float(rd[2 * i + 1] & prmt(x, 0xBBBBu));
-      if (WITH_P) pp &= prmt(x, 0xBB99u);
+  for (int i = 0; i < 8; ++i) {
+    float p[4], e[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      p[c] = ex2(fmaf(__uint_as_float(rs[4 * i + c]), kScaleLog2, -L));
+      e[c] = __uint_as_float(rd[4 * i + c]);
     }
-    ds[i] = pack_bf16x2(p0 * (e0 - Dp), p1 * (e1 - Dp));
-    if (WITH_P) pd[i] = pp;
+    uint32_t pp0 = 0, pp1 = 0;
+    if (WITH_P) {
+      pp0 = pack_bf16x2(p[0], p[1]);
+      pp1 = pack_bf16x2(p[2], p[3]);
+    }
+    if (DROP) {
+      const uint32_t x = word << (7 - i);  // bit 8 c + i -> msb of byte c
+      e[0] = __uint_as_float(rd[4 * i + 0] & prmt(x, 0x8888u));
+      e[1] = __uint_as_float(rd[4 * i + 1] & prmt(x, 0x9999u));
+      e[2] = __uint_as_float(rd[4 * i + 2] & prmt(x, 0xAAAAu));
+      e[3] = __uint_as_float(rd[4 * i + 3] & prmt(x, 0xBBBBu));
+      if (WITH_P) {
+        pp0 &= prmt(x, 0x9988u);
+        pp1 &= prmt(x, 0xBBAAu);
+      }
+    }
+    ds[2 * i] = pack_bf16x2(p[0] * (e[0] - Dp), p[1] * (e[1] - Dp));
+    ds[2 * i + 1] = pack_bf16x2(p[2] * (e[2] - Dp), p[3] * (e[3] - Dp));
+    if (WITH_P) {
+      pd[2 * i] = pp0;
+      pd[2 * i + 1] = pp1;
+    }
   }
 }
 
@@ -362,31 +413,35 @@ __device__ __forceinline__ void bwd_half(const uint32_t (&rs)[32], const uint32_
 // backward pass A: dQ (and D = rowsum(dO o O), written for pass B).
 // shared: K, V resident; per group a Q tile, a dO tile and a dS tile.  TMEM per group: S 64, dP 64, dQ 32 columns.
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int kDqSmem = 2 * kHeadBytes + 2 * (2 * kQTile + kPTile) + 1024 + 1024;
+template <int NWG>
+struct DqCfg {
+  static constexpr int kThreads = 128 + NWG * 128;
+  static constexpr int kSmem = 2 * kHeadBytes + NWG * (2 * kQTile + kPTile) + 1024 + 1024;
+};
 
-template <int DROP>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int DROP, int NWG>
+__global__ void __launch_bounds__(DqCfg<NWG>::kThreads, 1)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap mQkv, const __grid_constant__ CUtensorMap mDo,
                    const bf16* __restrict__ o_in, const bf16* __restrict__ d_o, const float* __restrict__ lse2,
-                   float* __restrict__ dsum, bf16* __restrict__ dqkv, uint32_t key, uint32_t th15, float inv_keep,
+                   float* __restrict__ dsum, bf16* __restrict__ dqkv, uint32_t key, uint32_t th7, float inv_keep,
                    const uint32_t* __restrict__ drop_bits) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* sK = smem;
   uint8_t* sV = smem + kHeadBytes;
-  uint8_t* sQ = smem + 2 * kHeadBytes;   // [2 groups]
-  uint8_t* sDo = sQ + 2 * kQTile;        // [2 groups]
-  uint8_t* sDs = sDo + 2 * kQTile;       // [2 groups]
-  Bars* bars = reinterpret_cast<Bars*>(sDs + 2 * kPTile);
+  uint8_t* sQ = smem + 2 * kHeadBytes;   // [NWG]
+  uint8_t* sDo = sQ + NWG * kQTile;      // [NWG]
+  uint8_t* sDs = sDo + NWG * kQTile;     // [NWG]
+  Bars* bars = reinterpret_cast<Bars*>(sDs + NWG * kPTile);
   const int bh = blockIdx.x, b = bh >> 2, h = bh & 3;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mQkv);
     tma_prefetch_desc(&mDo);
+    init_bars(bars);
   }
-  if (warp == 1 && lane == 0) init_bars(bars);
-  if (warp == 3) {
+  if (warp == 1) {
     tmem_alloc(&bars->tmem_slot, 512);
     tmem_relinquish();
   }
@@ -395,37 +450,32 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap mQkv, const __grid_consta
   tc_fence_after();
   const uint32_t tmem = bars->tmem_slot;
 
-  if (warp == 0) {
+  if (warp < NWG) {
     if (lane == 0) {
-      mbar_arrive_expect_tx(&bars->res_full, 2 * kHeadBytes);
-      for (int i = 0; i < 8; ++i) {
-        tma_load_2d(sK + i * kQTile, &mQkv, &bars->res_full, 128 + h * 32, b * kS + i * 128);
-        tma_load_2d(sV + i * kQTile, &mQkv, &bars->res_full, 256 + h * 32, b * kS + i * 128);
-      }
-      for (int it = 0; it < 4; ++it)
-        for (int g = 0; g < 2; ++g) {
-          WgBars& w = bars->wg[g];
-          mbar_wait(&w.a_empty, (it & 1) ^ 1);
-          mbar_arrive_expect_tx(&w.a_full, 2 * kQTile);
-          tma_load_2d(sQ + g * kQTile, &mQkv, &w.a_full, h * 32, b * kS + (g + 2 * it) * 128);
-          tma_load_2d(sDo + g * kQTile, &mDo, &w.a_full, h * 32, b * kS + (g + 2 * it) * 128);
-        }
-    }
-  } else if (warp == 1 || warp == 2) {
-    if (lane == 0) {
-      const int g = warp - 1;
+      const int g = warp;
       WgBars& w = bars->wg[g];
+      if (g == 0) {
+        mbar_arrive_expect_tx(&bars->res_full, 2 * kHeadBytes);
+        for (int i = 0; i < 8; ++i) {
+          tma_load_2d(sK + i * kQTile, &mQkv, &bars->res_full, 128 + h * 32, b * kS + i * 128);
+          tma_load_2d(sV + i * kQTile, &mQkv, &bars->res_full, 256 + h * 32, b * kS + i * 128);
+        }
+      }
       const uint32_t tS = tmem + g * 160, tDp = tS + 64, tDq = tS + 128;
       const uint32_t aQ = smem_u32(sQ + g * kQTile), aDo = smem_u32(sDo + g * kQTile), aDs = smem_u32(sDs + g * kPTile);
       const uint32_t aK = smem_u32(sK), aV = smem_u32(sV);
-      mbar_wait(&bars->res_full, 0);
       uint32_t n = 0;
-      for (int it = 0; it < 4; ++it) {
-        mbar_wait(&w.a_full, it & 1);
+      for (int it = 0; g + NWG * it < 8; ++it) {
+        mbar_wait_parked(&w.a_empty, (it & 1) ^ 1);
+        mbar_arrive_expect_tx(&w.a_full, 2 * kQTile);
+        tma_load_2d(sQ + g * kQTile, &mQkv, &w.a_full, h * 32, b * kS + (g + NWG * it) * 128);
+        tma_load_2d(sDo + g * kQTile, &mDo, &w.a_full, h * 32, b * kS + (g + NWG * it) * 128);
+        if (it == 0) mbar_wait_parked(&bars->res_full, 0);
+        mbar_wait_parked(&w.a_full, it & 1);
         tc_fence_after();
         for (int j = 0; j <= 16; ++j) {
           if (j < 16) {
-            mbar_wait(&w.s_empty[0], (n & 1) ^ 1);
+            mbar_wait_parked(&w.s_empty[0], (n & 1) ^ 1);
             tc_fence_after();
             mma_qk(tS, aQ, aK + j * 4096);
             mma_qk(tDp, aDo, aV + j * 4096);
@@ -436,10 +486,10 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap mQkv, const __grid_consta
           if (j >= 1) {  // dQ += dS K of key tile j - 1  (its tile counter is n - 2 for j < 16, n - 1 for j == 16)
             const int jj = j - 1;
             const uint32_t nn = (j < 16) ? n - 2 : n - 1;
-            mbar_wait(&w.p_full, nn & 1);
+            mbar_wait_parked(&w.p_full, nn & 1);
             tc_fence_after();
             if (jj == 0) {
-              mbar_wait(&w.o_empty, (it & 1) ^ 1);
+              mbar_wait_parked(&w.o_empty, (it & 1) ^ 1);
               tc_fence_after();
             }
             mma_pv(tDq, aDs, aK + jj * 4096, jj != 0);
@@ -454,11 +504,11 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap mQkv, const __grid_consta
     WgBars& w = bars->wg[g];
     const uint32_t tS = tmem + ((uint32_t)(quad * 32) << 16) + g * 160, tDp = tS + 64, tDq = tS + 128;
     uint8_t* myDs = sDs + g * kPTile;
-    const uint32_t addc = (0x8000u - th15) * 0x00010001u;
+    const uint32_t addc = (128u - th7) * 0x01010101u;
     const float keep_prob = 1.f / inv_keep;
     uint32_t n = 0;
-    for (int it = 0; it < 4; ++it) {
-      const int q = (g + 2 * it) * 128 + row;
+    for (int it = 0; g + NWG * it < 8; ++it) {
+      const int q = (g + NWG * it) * 128 + row;
       const long t = (long)b * kS + q;
       const float L = lse2[(long)bh * kS + q];
       float D = 0.f;
@@ -479,12 +529,17 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap mQkv, const __grid_consta
       }
       dsum[(long)bh * kS + q] = D;
       const float Dp = D * keep_prob;
-      const uint32_t rowctr = (uint32_t)(bh * kS + q) * 512u;
+      const uint32_t rowctr = (uint32_t)(bh * kS + q) * 256u;
+      uint32_t wn[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};  // keep-bit words, loaded one key tile ahead
+      if (DROP == 2) {
+        wn[0] = __ldg(drop_bits + ((size_t)bh * 32) * kS + q);
+        wn[1] = __ldg(drop_bits + ((size_t)bh * 32 + 1) * kS + q);
+      }
       for (int j = 0; j < 16; ++j) {
-        uint32_t wd[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
-        if (DROP == 2) {
-          wd[0] = __ldg(drop_bits + ((size_t)bh * 32 + j * 2) * kS + q);
-          wd[1] = __ldg(drop_bits + ((size_t)bh * 32 + j * 2 + 1) * kS + q);
+        uint32_t wd[2] = {wn[0], wn[1]};
+        if (DROP == 2 && j < 15) {
+          wn[0] = __ldg(drop_bits + ((size_t)bh * 32 + j * 2 + 2) * kS + q);
+          wn[1] = __ldg(drop_bits + ((size_t)bh * 32 + j * 2 + 3) * kS + q);
         }
         mbar_wait(&w.s_full[0], n & 1);
         tc_fence_after();
@@ -495,7 +550,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap mQkv, const __grid_consta
           tmem_ld_32x32b_x32(tDp + hf * 32, rd);
           tmem_ld_wait();
           if (hf == 1) warp_release_tmem(&w.s_empty[0], lane);
-          if (DROP == 1) wd[hf] = hash_word(key, rowctr + (uint32_t)(j * 32 + hf * 16), addc);
+          if (DROP == 1) wd[hf] = hash_word(key, rowctr + (uint32_t)(j * 16 + hf * 8), addc);
           uint32_t ds[16], pd[16];
           bwd_half<DROP, false>(rs, rd, L, Dp, wd[hf], ds, pd);
           if (hf == 0) mbar_wait(&w.p_empty, (n & 1) ^ 1);
@@ -526,7 +581,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap mQkv, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 3) {
+  if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
   }
@@ -544,7 +599,7 @@ template <int DROP>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mQkv, const __grid_constant__ CUtensorMap mQkv64,
                     const __grid_constant__ CUtensorMap mDo, const float* __restrict__ lse2,
-                    const float* __restrict__ dsum, bf16* __restrict__ dqkv, uint32_t key, uint32_t th15, float inv_keep,
+                    const float* __restrict__ dsum, bf16* __restrict__ dqkv, uint32_t key, uint32_t th7, float inv_keep,
                     const uint32_t* __restrict__ drop_bits) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -583,7 +638,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mQkv, const __grid_const
         for (int g = 0; g < 2; ++g) {
           WgBars& w = bars->wg[g];
           const int kb = jt & 1, j = g + 2 * jt;
-          mbar_wait(&w.a2_empty[kb], ((jt >> 1) & 1) ^ 1);
+          mbar_wait_parked(&w.a2_empty[kb], ((jt >> 1) & 1) ^ 1);
           mbar_arrive_expect_tx(&w.a2_full[kb], 2 * kKvBlk);
           uint8_t* dst = sKv + (g * 2 + kb) * 2 * kKvBlk;
           tma_load_2d(dst, &mQkv64, &w.a2_full[kb], 128 + h * 32, b * kS + j * 64);
@@ -597,16 +652,16 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mQkv, const __grid_const
       const uint32_t tS = tmem + g * 192, tDp = tS + 64, tDk = tS + 128, tDv = tS + 160;
       const uint32_t aQ = smem_u32(sQ), aDo = smem_u32(sDo);
       const uint32_t aP = smem_u32(sP + g * kPTile), aDs = smem_u32(sDs + g * kPTile);
-      mbar_wait(&bars->res_full, 0);
+      mbar_wait_parked(&bars->res_full, 0);
       uint32_t n = 0;
       for (int jt = 0; jt < 8; ++jt) {
         const int kb = jt & 1;
         const uint32_t aKj = smem_u32(sKv + (g * 2 + kb) * 2 * kKvBlk), aVj = aKj + kKvBlk;
-        mbar_wait(&w.a2_full[kb], (jt >> 1) & 1);
+        mbar_wait_parked(&w.a2_full[kb], (jt >> 1) & 1);
         tc_fence_after();
         for (int i = 0; i <= 8; ++i) {
           if (i < 8) {
-            mbar_wait(&w.s_empty[0], (n & 1) ^ 1);
+            mbar_wait_parked(&w.s_empty[0], (n & 1) ^ 1);
             tc_fence_after();
             mma_qk(tS, aQ + i * kQTile, aKj);
             mma_qk(tDp, aDo + i * kQTile, aVj);
@@ -617,10 +672,10 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mQkv, const __grid_const
           if (i >= 1) {  // dV += Pd^T dO, dK += dS^T Q of query tile i - 1
             const int ii = i - 1;
             const uint32_t nn = (i < 8) ? n - 2 : n - 1;
-            mbar_wait(&w.p_full, nn & 1);
+            mbar_wait_parked(&w.p_full, nn & 1);
             tc_fence_after();
             if (ii == 0) {
-              mbar_wait(&w.o_empty, (jt & 1) ^ 1);
+              mbar_wait_parked(&w.o_empty, (jt & 1) ^ 1);
               tc_fence_after();
             }
             mma_ptdo(tDv, aP, aDo + ii * kQTile, ii != 0);
@@ -637,21 +692,33 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mQkv, const __grid_const
     const uint32_t tS = tmem + ((uint32_t)(quad * 32) << 16) + g * 192, tDp = tS + 64, tDk = tS + 128, tDv = tS + 160;
     uint8_t* myP = sP + g * kPTile;
     uint8_t* myDs = sDs + g * kPTile;
-    const uint32_t addc = (0x8000u - th15) * 0x00010001u;
+    const uint32_t addc = (128u - th7) * 0x01010101u;
     const float keep_prob = 1.f / inv_keep;
     uint32_t n = 0;
+    // per-tile row scalars and keep-bit words are loaded one tile ahead of their use
+    float Ln = lse2[(long)bh * kS + row], Dn = dsum[(long)bh * kS + row];
+    uint32_t wn[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
+    if (DROP == 2) {
+      wn[0] = __ldg(drop_bits + ((size_t)bh * 32 + g * 2) * kS + row);
+      wn[1] = __ldg(drop_bits + ((size_t)bh * 32 + g * 2 + 1) * kS + row);
+    }
     for (int jt = 0; jt < 8; ++jt) {
       const int j = g + 2 * jt;  // 64-key block
       for (int i = 0; i < 8; ++i) {
         const int q = i * 128 + row;
-        const float L = lse2[(long)bh * kS + q];
-        const float Dp = dsum[(long)bh * kS + q] * keep_prob;
-        uint32_t wd[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
-        if (DROP == 2) {
-          wd[0] = __ldg(drop_bits + ((size_t)bh * 32 + j * 2) * kS + q);
-          wd[1] = __ldg(drop_bits + ((size_t)bh * 32 + j * 2 + 1) * kS + q);
+        const float L = Ln;
+        const float Dp = Dn * keep_prob;
+        uint32_t wd[2] = {wn[0], wn[1]};
+        if (i < 7 || jt < 7) {
+          const int qn = ((i + 1) & 7) * 128 + row, jn = (i < 7) ? j : j + 2;
+          Ln = lse2[(long)bh * kS + qn];
+          Dn = dsum[(long)bh * kS + qn];
+          if (DROP == 2) {
+            wn[0] = __ldg(drop_bits + ((size_t)bh * 32 + jn * 2) * kS + qn);
+            wn[1] = __ldg(drop_bits + ((size_t)bh * 32 + jn * 2 + 1) * kS + qn);
+          }
         }
-        const uint32_t rowctr = (uint32_t)(bh * kS + q) * 512u;
+        const uint32_t rowctr = (uint32_t)(bh * kS + q) * 256u;
         mbar_wait(&w.s_full[0], n & 1);
         tc_fence_after();
 #pragma unroll
@@ -661,7 +728,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mQkv, const __grid_const
           tmem_ld_32x32b_x32(tDp + hf * 32, rd);
           tmem_ld_wait();
           if (hf == 1) warp_release_tmem(&w.s_empty[0], lane);
-          if (DROP == 1) wd[hf] = hash_word(key, rowctr + (uint32_t)(j * 32 + hf * 16), addc);
+          if (DROP == 1) wd[hf] = hash_word(key, rowctr + (uint32_t)(j * 16 + hf * 8), addc);
           uint32_t ds[16], pd[16];
           bwd_half<DROP, true>(rs, rd, L, Dp, wd[hf], ds, pd);
           if (hf == 0) mbar_wait(&w.p_empty, (n & 1) ^ 1);
@@ -716,13 +783,15 @@ int set_smem(K kernel, int bytes) {
 }
 
 struct AttnDrop {
-  uint32_t th15;
+  uint32_t th7;
   float inv_keep;
 };
 AttnDrop drop_params(uint32_t thresh16) {
   AttnDrop d;
-  d.th15 = (thresh16 + 1) >> 1;  // p * 32768, rounded
-  d.inv_keep = 32768.f / (32768.f - (float)d.th15);
+  d.th7 = (thresh16 + 256) >> 9;  // p * 128, rounded
+  if (thresh16 && d.th7 == 0) d.th7 = 1;
+  if (d.th7 > 127) d.th7 = 127;
+  d.inv_keep = 128.f / (128.f - (float)d.th7);
   return d;
 }
 
@@ -731,34 +800,84 @@ AttnDrop drop_params(uint32_t thresh16) {
 // p_drop = thresh16 / 65536; thresh16 == 0 disables dropout (eval / parity runs).  drop_bits: optional keep-bit
 // buffer of attn_drop_bits_bytes(B) bytes written by the forward and consumed by the backward (may be null: the
 // backward then regenerates the mask from the seed).
+// tuning aid: device buffer (>= 64 KB of int64) that block 0 / warp 4 fills with clock64() marks, or null to disable
+extern "C" int focr_attn_set_trace(void* buf) {
+  long long* p = (long long*)buf;
+  FOCR_CHECK_CUDA(cudaMemcpyToSymbol(g_attn_trace, &p, sizeof(p)));
+  return FOCR_OK;
+}
+
 size_t attn_drop_bits_bytes(int B) { return (size_t)B * 4 * (kS / 32) * kS * sizeof(uint32_t); }
+
+template <int NWG>
+int launch_fwd(const CUtensorMap& mq, bf16* out, float* lse2, int B, uint32_t key, uint32_t thresh16, uint32_t* drop_bits,
+               cudaStream_t s) {
+  using Cfg = FwdCfg<NWG>;
+  static bool init = false;
+  if (!init) {
+    int rc = set_smem(attn_fwd_kernel<0, NWG>, Cfg::kSmem);
+    if (rc) return rc;
+    rc = set_smem(attn_fwd_kernel<1, NWG>, Cfg::kSmem);
+    if (rc) return rc;
+    rc = set_smem(attn_fwd_kernel<2, NWG>, Cfg::kSmem);
+    if (rc) return rc;
+    init = true;
+  }
+  const AttnDrop d = drop_params(thresh16);
+  const dim3 grid(B * 4), block(Cfg::kThreads);
+  if (!thresh16)
+    attn_fwd_kernel<0, NWG><<<grid, block, Cfg::kSmem, s>>>(mq, out, lse2, key, 0, 1.f, nullptr);
+  else if (!drop_bits)
+    attn_fwd_kernel<1, NWG><<<grid, block, Cfg::kSmem, s>>>(mq, out, lse2, key, d.th7, d.inv_keep, nullptr);
+  else
+    attn_fwd_kernel<2, NWG><<<grid, block, Cfg::kSmem, s>>>(mq, out, lse2, key, d.th7, d.inv_keep, drop_bits);
+  FOCR_LAUNCH_CHECK();
+  return FOCR_OK;
+}
 
 int attn_forward(const bf16* qkv, bf16* out, float* lse2, int B, uint32_t key, uint32_t thresh16, uint32_t* drop_bits,
                  cudaStream_t s) {
   ProfScope _ps("attn_fwd", s);
   FOCR_REQUIRE(B >= 1 && B <= 1024, "attention: B=%d out of range", B);
   static_assert(sizeof(Bars) <= 1024, "barrier block");
-  static bool init = false;
-  if (!init) {
-    int rc = set_smem(attn_fwd_kernel<0>, kFwdSmem);
-    if (rc) return rc;
-    rc = set_smem(attn_fwd_kernel<1>, kFwdSmem);
-    if (rc) return rc;
-    rc = set_smem(attn_fwd_kernel<2>, kFwdSmem);
-    if (rc) return rc;
-    init = true;
-  }
   CUtensorMap mq;
   int rc = focr_make_tmap_2d(&mq, qkv, kLdQkv, (unsigned long long)B * kS, kLdQkv * 2, 32, 128, 64);
   if (rc) return rc;
+  static int nwg = 0;
+  if (!nwg) {
+    const char* e = getenv("FOCR_ATTN_FWD_NWG");  // tuning knob: softmax groups per CTA (2, 3 or 4)
+    nwg = e ? atoi(e) : 4;
+    if (nwg < 2 || nwg > 4) nwg = 4;
+  }
+  if (nwg == 2) return launch_fwd<2>(mq, out, lse2, B, key, thresh16, drop_bits, s);
+  if (nwg == 3) return launch_fwd<3>(mq, out, lse2, B, key, thresh16, drop_bits, s);
+  return launch_fwd<4>(mq, out, lse2, B, key, thresh16, drop_bits, s);
+}
+
+template <int NWG>
+int launch_dq(const CUtensorMap& mq, const CUtensorMap& mdo, const bf16* o, const bf16* d_o, const float* lse2, float* dsum,
+              bf16* dqkv, int B, uint32_t key, uint32_t thresh16, const uint32_t* drop_bits, cudaStream_t s) {
+  using Cfg = DqCfg<NWG>;
+  static bool init = false;
+  if (!init) {
+    int rc = set_smem(attn_bwd_dq_kernel<0, NWG>, Cfg::kSmem);
+    if (rc) return rc;
+    rc = set_smem(attn_bwd_dq_kernel<1, NWG>, Cfg::kSmem);
+    if (rc) return rc;
+    rc = set_smem(attn_bwd_dq_kernel<2, NWG>, Cfg::kSmem);
+    if (rc) return rc;
+    init = true;
+  }
   const AttnDrop d = drop_params(thresh16);
-  const dim3 grid(B * 4), block(kThreads);
+  const dim3 grid(B * 4), block(Cfg::kThreads);
   if (!thresh16)
-    attn_fwd_kernel<0><<<grid, block, kFwdSmem, s>>>(mq, out, lse2, key, 0, 1.f, nullptr);
+    attn_bwd_dq_kernel<0, NWG><<<grid, block, Cfg::kSmem, s>>>(mq, mdo, o, d_o, lse2, dsum, dqkv, key, 0, 1.f, nullptr);
   else if (!drop_bits)
-    attn_fwd_kernel<1><<<grid, block, kFwdSmem, s>>>(mq, out, lse2, key, d.th15, d.inv_keep, nullptr);
+    attn_bwd_dq_kernel<1, NWG><<<grid, block, Cfg::kSmem, s>>>(mq, mdo, o, d_o, lse2, dsum, dqkv, key, d.th7, d.inv_keep,
+                                                                nullptr);
   else
-    attn_fwd_kernel<2><<<grid, block, kFwdSmem, s>>>(mq, out, lse2, key, d.th15, d.inv_keep, drop_bits);
+    attn_bwd_dq_kernel<2, NWG><<<grid, block, Cfg::kSmem, s>>>(mq, mdo, o, d_o, lse2, dsum, dqkv, key, d.th7, d.inv_keep,
+                                                                drop_bits);
   FOCR_LAUNCH_CHECK();
   return FOCR_OK;
 }
@@ -768,13 +887,7 @@ int attn_backward(const bf16* qkv, const bf16* o, const bf16* d_o, const float* 
   FOCR_REQUIRE(B >= 1 && B <= 1024, "attention: B=%d out of range", B);
   static bool init = false;
   if (!init) {
-    int rc = set_smem(attn_bwd_dq_kernel<0>, kDqSmem);
-    if (rc) return rc;
-    rc = set_smem(attn_bwd_dq_kernel<1>, kDqSmem);
-    if (rc) return rc;
-    rc = set_smem(attn_bwd_dq_kernel<2>, kDqSmem);
-    if (rc) return rc;
-    rc = set_smem(attn_bwd_dkv_kernel<0>, kDkvSmem);
+    int rc = set_smem(attn_bwd_dkv_kernel<0>, kDkvSmem);
     if (rc) return rc;
     rc = set_smem(attn_bwd_dkv_kernel<1>, kDkvSmem);
     if (rc) return rc;
@@ -793,25 +906,25 @@ int attn_backward(const bf16* qkv, const bf16* o, const bf16* d_o, const float* 
   const dim3 grid(B * 4), block(kThreads);
   {
     ProfScope ps("attn_bwd_dq", s);
-    if (!thresh16)
-      attn_bwd_dq_kernel<0><<<grid, block, kDqSmem, s>>>(mq, mdo, o, d_o, lse2, dsum, dqkv, key, 0, 1.f, nullptr);
-    else if (!drop_bits)
-      attn_bwd_dq_kernel<1><<<grid, block, kDqSmem, s>>>(mq, mdo, o, d_o, lse2, dsum, dqkv, key, d.th15, d.inv_keep,
-                                                         nullptr);
-    else
-      attn_bwd_dq_kernel<2><<<grid, block, kDqSmem, s>>>(mq, mdo, o, d_o, lse2, dsum, dqkv, key, d.th15, d.inv_keep,
-                                                         drop_bits);
-    FOCR_LAUNCH_CHECK();
+    static int nwg = 0;
+    if (!nwg) {
+      const char* e = getenv("FOCR_ATTN_DQ_NWG");  // tuning knob: softmax groups per CTA (2 or 3)
+      nwg = e ? atoi(e) : 2;  // measured: a third group does not pay (0.63 vs 0.60 ms at B = 256)
+      if (nwg < 2 || nwg > 3) nwg = 2;
+    }
+    rc = nwg == 2 ? launch_dq<2>(mq, mdo, o, d_o, lse2, dsum, dqkv, B, key, thresh16, drop_bits, s)
+                  : launch_dq<3>(mq, mdo, o, d_o, lse2, dsum, dqkv, B, key, thresh16, drop_bits, s);
+    if (rc) return rc;
   }
   {
     ProfScope ps("attn_bwd_dkv", s);
     if (!thresh16)
       attn_bwd_dkv_kernel<0><<<grid, block, kDkvSmem, s>>>(mq, mq64, mdo, lse2, dsum, dqkv, key, 0, 1.f, nullptr);
     else if (!drop_bits)
-      attn_bwd_dkv_kernel<1><<<grid, block, kDkvSmem, s>>>(mq, mq64, mdo, lse2, dsum, dqkv, key, d.th15, d.inv_keep,
+      attn_bwd_dkv_kernel<1><<<grid, block, kDkvSmem, s>>>(mq, mq64, mdo, lse2, dsum, dqkv, key, d.th7, d.inv_keep,
                                                            nullptr);
     else
-      attn_bwd_dkv_kernel<2><<<grid, block, kDkvSmem, s>>>(mq, mq64, mdo, lse2, dsum, dqkv, key, d.th15, d.inv_keep,
+      attn_bwd_dkv_kernel<2><<<grid, block, kDkvSmem, s>>>(mq, mq64, mdo, lse2, dsum, dqkv, key, d.th7, d.inv_keep,
                                                            drop_bits);
     FOCR_LAUNCH_CHECK();
   }

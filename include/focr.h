@@ -68,7 +68,8 @@ int focr_layernorm_std_bwd(const void* dy, const void* x, const float* a, void* 
  * keep mask is a counter hash of (seed, stream_id, b, h, q, k).  drop_bits (device, focr_mha_drop_bits_bytes(B)
  * bytes, or NULL): when given, the forward stores its keep decisions there (1 bit per element) and the backward
  * reads them instead of re-hashing (the fast path); with NULL the backward regenerates the mask from the seed.
- * Bit layout: word [b*4+h][k/32][q] (uint32), key k of the 32-key group at bit (k%32)/2 + 16*(k&1). */
+ * Bit layout: word [b*4+h][k/32][q] (uint32), key k of the 32-key group at bit (k%32)/4 + 8*(k&3).
+ * The attention dropout rate is quantised to 1/128 (p = 0.1 -> 13/128); the rescale uses the quantised rate. */
 size_t focr_mha_drop_bits_bytes(int B);
 int focr_mha_flash_fwd(const void* qkv, void* out, float* lse2, int B, float p_drop, unsigned seed, unsigned stream_id,
                        void* drop_bits, void* stream);
@@ -81,6 +82,9 @@ int focr_mha_flash_bwd(const void* qkv, const void* out, const void* d_out, cons
  * a_step16 / b_step16 16-byte units per step) and dumps the 128-lane x ncols fp32 TMEM accumulator to `out`. */
 int focr_umma_probe(const void* img, int img_bytes, unsigned long long desc_a, unsigned long long desc_b, unsigned idesc,
                     int nk, unsigned a_step16, unsigned b_step16, float* out, int ncols, void* stream);
+
+/* tuning aid: clock64() trace of one softmax warp of the attention forward (block 0); NULL disables */
+int focr_attn_set_trace(void* device_buf_int64);
 
 /* --- step body: STT/interfaces/super_resolution.py:69-84, STT/loss/text_focus_loss.py:86, base.py:194-198 ------ */
 int focr_mse_loss_grad(const float* sr, const float* hr, float* d_sr, float* loss, long n, float gscale, void* ws,

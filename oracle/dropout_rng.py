@@ -33,31 +33,40 @@ def _keep(key: int, elem_index: np.ndarray, th: int) -> np.ndarray:
     return lane >= np.uint64(th)
 
 
-def thresh15(p: float) -> int:
-    """attention.cu compares 15-bit lanes: th15 = (thresh16 + 1) >> 1"""
-    return (thresh16(p) + 1) >> 1
+def thresh7(p: float) -> int:
+    """attention.cu compares 7-bit lanes: th7 = (thresh16 + 256) >> 9 (p quantised to 1/128)"""
+    t = thresh16(p)
+    th = (t + 256) >> 9
+    if t and th == 0:
+        th = 1
+    return min(th, 127)
 
 
 def attn_keep_mask(B: int, seed: int, blk: int, p: float) -> torch.Tensor:
-    """(B,4,1024,1024) bool: element (b,h,q,k) has index ((b*4+h)*1024+q)*1024 + k; its hash (counter index >> 1)
-    carries two 15-bit lanes (bits 0-14 for even k, bits 16-30 for odd k); kept iff lane >= th15 (attention.cu)."""
+    """(B,4,1024,1024) bool: element (b,h,q,k) has index ((b*4+h)*1024+q)*1024 + k; the hash of (index >> 2) carries
+    four 7-bit lanes (low 7 bits of byte k & 3); kept iff lane >= th7 (attention.cu)."""
     idx = np.arange(B * 4 * 1024 * 1024, dtype=np.uint64)
-    h = hash32(drop_key(seed, 2 * blk), idx >> np.uint64(1))
-    lane = np.where((idx & np.uint64(1)) == 0, h & np.uint64(0x7FFF), (h >> np.uint64(16)) & np.uint64(0x7FFF))
-    return torch.from_numpy((lane >= np.uint64(thresh15(p))).reshape(B, 4, 1024, 1024))
+    h = hash32(drop_key(seed, 2 * blk), idx >> np.uint64(2))
+    lane = (h >> (np.uint64(8) * (idx & np.uint64(3)))) & np.uint64(0x7F)
+    return torch.from_numpy((lane >= np.uint64(thresh7(p))).reshape(B, 4, 1024, 1024))
 
 
 def attn_keep_scale(p: float) -> float:
-    """attention.cu scales kept probabilities by 32768/(32768-th15)"""
-    return 32768.0 / (32768.0 - thresh15(p))
+    """attention.cu scales kept probabilities by 128/(128-th7)"""
+    return 128.0 / (128.0 - thresh7(p))
+
+
+def attn_drop_rate(p: float) -> float:
+    """the rate the attention kernels actually apply (13/128 for p = 0.1)"""
+    return thresh7(p) / 128.0
 
 
 def ffn_keep_mask(B: int, seed: int, blk: int, p: float) -> torch.Tensor:
-    """(B,1024,128) bool: element (t,n) has index t*128+n (tc_gemm.cu epilogue)."""
+    """(B,1024,128) bool: element (t,n) has index t*128+n (tc_gemm.cu epilogue, 16-bit lanes)."""
     idx = np.arange(B * 1024 * 128, dtype=np.uint64)
     return torch.from_numpy(_keep(drop_key(seed, 2 * blk + 1), idx, thresh16(p)).reshape(B, 1024, 128))
 
 
 def keep_scale(p: float) -> float:
-    """the kernels scale kept values by 65536/(65536-thresh16) (exactly 1/(1-p_effective))"""
+    """the FFN epilogue scales kept values by 65536/(65536-thresh16) (exactly 1/(1-p_effective))"""
     return 65536.0 / (65536.0 - thresh16(p))

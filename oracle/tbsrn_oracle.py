@@ -67,8 +67,11 @@ def batch_norm_train(x: Tensor, sd: Dict[str, Tensor], pre: str, new_stats: Opti
 # ---------------------------------------------------------------------------------------------
 # FeatureEnhancer  (model/tbsrn.py:63-163)
 # ---------------------------------------------------------------------------------------------
-def multi_head_attention(sd, pre, x, attn_keep: Optional[Tensor], p_drop: float, h: int = 4):
-    """model/tbsrn.py:95-150: q,k,v,out = 4 x Linear(128,128); softmax(QK^T/sqrt(d_k)); dropout on P."""
+def multi_head_attention(sd, pre, x, attn_keep: Optional[Tensor], p_drop: float, h: int = 4,
+                         keep_scale: Optional[float] = None):
+    """model/tbsrn.py:95-150: q,k,v,out = 4 x Linear(128,128); softmax(QK^T/sqrt(d_k)); dropout on P.
+    keep_scale: the 1/(1-p) rescale of kept probabilities when the caller's mask was drawn at a quantised rate
+    (the CUDA attention draws at 13/128 for p = 0.1); default 1/(1-p_drop) as nn.Dropout."""
     B, S, D = x.shape
     dk = D // h
     q, k, v = [F.linear(x, sd[f"{pre}.linears.{i}.weight"], sd[f"{pre}.linears.{i}.bias"])
@@ -76,7 +79,7 @@ def multi_head_attention(sd, pre, x, attn_keep: Optional[Tensor], p_drop: float,
     scores = torch.matmul(q, k.transpose(-2, -1)) / math.sqrt(dk)
     p = F.softmax(scores, dim=-1)
     if attn_keep is not None:
-        p = p * attn_keep.to(p.dtype) / (1.0 - p_drop)
+        p = p * attn_keep.to(p.dtype) * (keep_scale if keep_scale is not None else 1.0 / (1.0 - p_drop))
     o = torch.matmul(p, v).transpose(1, 2).contiguous().view(B, S, D)
     return F.linear(o, sd[f"{pre}.linears.3.weight"], sd[f"{pre}.linears.3.bias"])
 
@@ -88,7 +91,8 @@ def feature_enhancer(sd, pre, conv_feature: Tensor, masks: Optional[dict], p_dro
     x = torch.cat([conv_feature, pe], 1).permute(0, 2, 1).contiguous()  # (B,1024,128)
     attn_keep = masks.get(pre + ".attn") if masks else None
     ffn_keep = masks.get(pre + ".ffn") if masks else None
-    y = layer_norm_std(x + multi_head_attention(sd, pre + ".multihead", x, attn_keep, p_drop),
+    attn_scale = masks.get(pre + ".attn_scale") if masks else None
+    y = layer_norm_std(x + multi_head_attention(sd, pre + ".multihead", x, attn_keep, p_drop, keep_scale=attn_scale),
                        sd[pre + ".mul_layernorm1.a_2"], sd[pre + ".mul_layernorm1.b_2"])
     hdn = F.relu(F.linear(y, sd[pre + ".pff.w_1.weight"], sd[pre + ".pff.w_1.bias"]))
     if ffn_keep is not None:

@@ -48,7 +48,7 @@ def check(B, p_drop, use_bits):
     if use_bits and p_drop > 0:
         w = bits.view(B, 4, 32, 1024).long() & 0xFFFFFFFF
         kk = torch.arange(32, device=dev)
-        sh = kk // 2 + 16 * (kk & 1)
+        sh = kk // 4 + 8 * (kk & 3)
         m = ((w[..., None] >> sh) & 1).permute(0, 1, 3, 2, 4).reshape(B, 4, 1024, 1024)
         msg.append(f"bits mismatches {(m.bool() != keep.bool()).sum().item()} keep-rate {m.float().mean().item():.4f}")
     d_out = torch.randn(T, 128, device=dev, generator=g).to(torch.bfloat16)

@@ -135,10 +135,10 @@ def test_attention_fwd_bwd(B, p_drop, use_bits):
     _sync(L)
     keep = R.attn_keep_mask(B, seed, blk, p_drop).to(DEV) if p_drop > 0 else None
     if use_bits and p_drop > 0:
-        # decode: word [b,h,k/32,q], key k of the group at bit (k%32)//2 + 16*(k&1)
+        # decode: word [b,h,k/32,q], key k of the group at bit (k%32)//4 + 8*(k&3)
         w = bits.view(B, 4, 32, 1024).long() & 0xFFFFFFFF             # [b,h,kw,q]
         kk = torch.arange(32, device=DEV)
-        sh = kk // 2 + 16 * (kk & 1)
+        sh = kk // 4 + 8 * (kk & 3)
         m = (w[..., None] >> sh) & 1                                   # [b,h,kw,q,kk]
         m = m.permute(0, 1, 3, 2, 4).reshape(B, 4, 1024, 1024)
         assert torch.equal(m.bool(), keep.bool())
@@ -162,7 +162,11 @@ def test_attention_fwd_bwd(B, p_drop, use_bits):
 
 
 def test_attention_dropout_statistics():
-    """in-kernel mask: keep rate 0.9 and E[out] unchanged (uniform V makes the dropped output = keep fraction)"""
+    """in-kernel mask: drop rate = the quantised 13/128 and E[out] unchanged (uniform V makes the dropped output = the
+    keep fraction)"""
+    from oracle import dropout_rng as R
+    pq = R.attn_drop_rate(0.1)
+    assert abs(pq - 0.1) < 2e-3
     L = _L()
     B = 2
     qkv = torch.zeros(B * 1024, 384, device=DEV)
@@ -174,8 +178,8 @@ def test_attention_dropout_statistics():
     _sync(L)
     o = out.float()
     assert abs(o.mean().item() - 1.0) < 2e-3          # unbiased
-    sd = o[:, ::32].std().item()                       # per (row, head): binomial(1024, .9)/1024/.9
-    assert abs(sd - math.sqrt(0.1 * 0.9 / 1024) / 0.9) < 2e-3
+    sd = o[:, ::32].std().item()                       # per (row, head): binomial(1024, 1-pq)/1024/(1-pq)
+    assert abs(sd - math.sqrt(pq * (1 - pq) / 1024) / (1 - pq)) < 2e-3
 
 
 # ---------------------------------------------------------------------------------------------

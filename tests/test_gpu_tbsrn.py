@@ -241,9 +241,15 @@ def test_reference_loop_and_fused_trainer_agree(env):
                 g2 = tr.flat_g[off:off + n]
                 off += (n + 3) // 4 * 4
                 d = (g1[k].reshape(-1) / coef - g2).norm().item() / (g2.norm().item() + 1e-20)
-                if d > 1e-3 and k in live_names and not k.startswith("stn_head."):
-                    diffs[k] = d  # (the B=4 STN prologue amplifies 1-ulp differences of d_sr: not a front-end property)
-            REPORT["frontends_grad_mismatch"] = dict(sorted(diffs.items(), key=lambda kv: -kv[1])[:20])
+                # the two paths differ by ~1 ulp in d_sr (torch's MSE backward vs the fused one); batch-statistics BN at
+                # B = 4 amplifies that for cancellation-dominated sums (bias-type gradients).  The kernels themselves are
+                # bit-reproducible and workspace-independent, and moving the targets by ONE ulp moves these gradients by
+                # 1e-3 .. 2.5e-3 (scripts/ws_independence.py: bf16 rounding flips cascade), so the front-ends agree when the
+                # mismatch stays inside half the tensor's own bf16 error against the fp32 oracle.
+                e_or = (info["grads"][k].reshape(-1) - g2).norm().item() / (g2.norm().item() + 1e-20)
+                if d > (5e-3 if n == 1 else 1e-3) and d > 0.5 * e_or and k in live_names and not k.startswith("stn_head."):
+                    diffs[k] = (d, e_or)  # (the B=4 STN prologue amplifies 1-ulp differences of d_sr even more)
+            REPORT["frontends_grad_mismatch"] = dict(sorted(diffs.items(), key=lambda kv: -kv[1][0])[:20])
             _dump()
         assert abs(loss.item() - l2.item()) < 1e-6 + 1e-4 * abs(loss.item())
         assert abs(gn1.item() - tr.grad_norm.item()) < 1e-3 * gn1.item(), REPORT.get("frontends_grad_mismatch")
@@ -286,6 +292,7 @@ def test_dropout_on_matches_oracle_with_same_masks(env):
     masks = {}
     for i in range(5):
         masks[f"block{i + 2}.feature_enhancer.attn"] = R.attn_keep_mask(B, seed, i, p).to(DEV)
+        masks[f"block{i + 2}.feature_enhancer.attn_scale"] = R.attn_keep_scale(p)
         masks[f"block{i + 2}.feature_enhancer.ffn"] = R.ffn_keep_mask(B, seed, i, p).to(DEV)
     sd = {k: v.to(DEV) for k, v in env["sd"].items()}
     _, info = O.train_step(sd, lr, hr, {}, masks=masks, stn=False)
