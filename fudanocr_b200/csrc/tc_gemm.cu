@@ -245,6 +245,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
                 }
               }
             }
+            if (p.relu_post) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[q * 8 + j] = fmaxf(v[q * 8 + j], 0.f);
+            }
             uint4 o;
             o.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
             o.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
@@ -520,7 +524,9 @@ int tc_gemm_launch(const bf16* const* a_ptrs, int n_amaps, long a_pix_stride, lo
                    long a_img_stride, int a_channels, int B, const bf16* w, int cin, TcGemmParams p,
                    cudaStream_t stream) {
   FOCR_REQUIRE(n_amaps >= 1 && n_amaps <= 4, "tc_gemm: n_amaps %d", n_amaps);
-  FOCR_REQUIRE(p.W == 64 || p.W == 128, "tc_gemm: W must be 64 or 128 (got %d)", p.W);
+  FOCR_REQUIRE(p.W == 32 || p.W == 64 || p.W == 128, "tc_gemm: W must be 32, 64 or 128 (got %d)", p.W);
+  FOCR_REQUIRE(p.H % (kTileM / p.W) == 0, "tc_gemm: H %d is not a multiple of the %d-row tile", p.H, kTileM / p.W);
+  FOCR_REQUIRE(!p.relu_post || (p.epi == TC_EPI_BF16 && p.prelu_slope == nullptr), "tc_gemm: relu_post needs the bf16 TMA epilogue");
   FOCR_REQUIRE((p.H * p.W) % kTileM == 0, "tc_gemm: H*W must be a multiple of 128");
   FOCR_REQUIRE(cin % 64 == 0 && a_channels % 64 == 0, "tc_gemm: channels must be multiples of 64");
   FOCR_REQUIRE(p.kh >= 1 && p.kw >= 1 && (p.kh & 1) && (p.kw & 1) && p.kh <= 9 && p.kw <= 9, "tc_gemm: taps %dx%d",
