@@ -76,6 +76,13 @@ _SIGS = {
     "focr_tsrn_backward": (C.c_int, [_pp, _pp, _fp, _fp, _i, _i, _i, _vp, _sz, _vp]),
     "focr_tsrn_ws_tensor": (C.c_int, [_i, _i, C.c_char_p, C.POINTER(_ll), C.POINTER(_ll), C.POINTER(_i)]),
     "focr_tbsrn_ws_tensor": (C.c_int, [_i, _i, C.c_char_p, C.POINTER(_ll), C.POINTER(_ll), C.POINTER(_i)]),
+    "focr_strokenet_num_slots": (C.c_int, []),
+    "focr_strokenet_slot_name": (C.c_char_p, [_i, _i]),
+    "focr_strokenet_prepared_bytes": (_sz, [_i]),
+    "focr_strokenet_prepare": (C.c_int, [_pp, _i, _vp, _sz, _vp]),
+    "focr_focus_loss_workspace_bytes": (_sz, [_i, _i]),
+    "focr_focus_loss": (C.c_int, [_vp, _sz, _i, _fp, _fp, _vp, _i, _i, _f, _f, _fp, _fp, _fp, _fp, _vp, _sz, _vp]),
+    "focr_focus_loss_ws_tensor": (C.c_int, [_i, _i, C.c_char_p, C.POINTER(_ll), C.POINTER(_ll), C.POINTER(_i)]),
 }
 
 

@@ -236,13 +236,24 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const float2 f = unpack_bf16x2(aw[j]);
-                if (p.gate != nullptr) {
+                if (p.residual == nullptr) {
                   v[q * 8 + 2 * j] = f.x > 0.f ? v[q * 8 + 2 * j] * p.gate_scale : 0.f;
                   v[q * 8 + 2 * j + 1] = f.y > 0.f ? v[q * 8 + 2 * j + 1] * p.gate_scale : 0.f;
                 } else {
                   v[q * 8 + 2 * j] += f.x;
                   v[q * 8 + 2 * j + 1] += f.y;
                 }
+              }
+            }
+            if (p.residual != nullptr && p.gate != nullptr) {
+              // both a residual (through the TMA-prefetched tile) and a gate: the gate row comes straight from global
+              const uint4 gv = *reinterpret_cast<const uint4*>(p.gate + mg * p.ldc + n0 + q * 8);
+              const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 f = unpack_bf16x2(gw[j]);
+                v[q * 8 + 2 * j] = f.x > 0.f ? v[q * 8 + 2 * j] * p.gate_scale : 0.f;
+                v[q * 8 + 2 * j + 1] = f.y > 0.f ? v[q * 8 + 2 * j + 1] * p.gate_scale : 0.f;
               }
             }
             if (p.relu_post) {
@@ -563,7 +574,7 @@ int tc_gemm_launch(const bf16* const* a_ptrs, int n_amaps, long a_pix_stride, lo
   // output / auxiliary tiles through TMA for the plain bf16 epilogue (every hot GEMM); the rare epilogues
   // (fp32 output, PixelShuffle scatter, PReLU with saved pre-activation) keep direct stores
   p.tma_out = (p.epi == TC_EPI_BF16 && p.prelu_slope == nullptr) ? 1 : 0;
-  FOCR_REQUIRE(!(p.residual && p.gate), "tc_gemm: residual and gate are mutually exclusive");
+  FOCR_REQUIRE(p.tma_out || !(p.residual && p.gate), "tc_gemm: residual + gate needs the bf16 TMA epilogue");
   CUtensorMap cm = bm, rm = bm;
   if (p.tma_out) {
     cuuint64_t dims[2] = {(cuuint64_t)p.n_total, (cuuint64_t)p.m_tiles * kTileM};

@@ -37,7 +37,7 @@ struct TcGemmParams {
   float drop_scale;      // 1/(1-p)
   uint32_t drop_key;     // drop_key(seed, stream)
   // backward gate: v = gate[m][n] > 0 ? v * gate_scale : 0  (relu'(.) * dropout mask, read from the
-  // stored post-dropout activation)
+  // stored post-dropout activation).  With a residual as well the order is (acc + residual) then gate.
   const bf16* gate;
   float gate_scale;
   // PReLU epilogue (block1, tbsrn.py:180-182): out = x > 0 ? x : slope[0]*x ; out2 (optional) = x

@@ -130,6 +130,29 @@ int focr_crnn_forward(void* const* params, const float* images, int input_is_gra
                       size_t ws_bytes, void* stream);
 int focr_ctc_greedy_decode(const float* logits, int T, int B, int C, int* path, int* out, int* len, void* stream);
 
+/* --- stroke-/text-focus loss: the frozen recogniser and the attention-map L1 term -------------------------------------
+ * text-gestalt/loss/stroke_focus_loss.py:83-122 (StrokeFocusLoss.forward), :12-18 (to_gray_tensor),
+ * text-gestalt/loss/transformer_english_decomposition.py:70-168 (ResNet encoder), :276-304 (Decoder), :343-398
+ * (Transformer.forward); scene-text-telescope/loss/transformer.py is the same network with 37 classes.
+ * params: HOST array of focr_strokenet_num_slots() DEVICE pointers, slot i = state_dict entry
+ * focr_strokenet_slot_name(variant, i) (variant 0 text-gestalt key names, 1 scene-text-telescope).  The recogniser is
+ * frozen and in eval mode: focr_strokenet_prepare folds BatchNorm into bf16 conv weights once, into a caller-allocated
+ * blob of focr_strokenet_prepared_bytes(n_class) bytes that every later call borrows.
+ * focr_focus_loss: sr, hr fp32 NCHW (B,3,32,128); text_input int64 (B,T) = the right-shifted label indices the
+ * reference's label encoder builds; losses[3] (device) = {mse + lambda * attention, mse, attention};
+ * d_sr = gscale * d(loss)/d(sr) (MSE and attention terms; gscale = 100 in the reference step body);
+ * map_hr_out / map_sr_out (optional, fp32 (B,16,T,256)) receive the two word-attention maps.  Only the SR branch's
+ * input-gradient chain is evaluated: the reference's unused weight gradients and HR-branch backward are not. */
+int focr_strokenet_num_slots(void);
+const char* focr_strokenet_slot_name(int variant, int idx);
+size_t focr_strokenet_prepared_bytes(int n_class);
+int focr_strokenet_prepare(void* const* params, int n_class, void* prepared, size_t prepared_bytes, void* stream);
+size_t focr_focus_loss_workspace_bytes(int B, int T);
+int focr_focus_loss(const void* prepared, size_t prepared_bytes, int n_class, const float* sr, const float* hr,
+                    const long long* text_input, int B, int T, float lambda, float gscale, float* d_sr, float* losses,
+                    float* map_hr_out, float* map_sr_out, void* ws, size_t ws_bytes, void* stream);
+int focr_focus_loss_ws_tensor(int B, int T, const char* name, long long* byte_offset, long long* elems, int* elem_bytes);
+
 /* --- measurement hooks used by bench.py: CUDA-event scopes on the launching stream + launch counter ----------- */
 int focr_prof_enable(int mode /*0 off, 1 all, 2 focus*/, const char* focus_substring);
 int focr_prof_collect(char* buf, int cap); /* lines "scope launches total_ms"; synchronises; clears */

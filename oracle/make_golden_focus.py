@@ -42,10 +42,29 @@ def main():
     sd = synth.synth_state_dict(spec, seed=777, computed={"pe.pe": FO.positional_encoding(512, 5000)})
     assert torch.equal(sd["pe.pe"], model.state_dict()["pe.pe"])
     model.load_state_dict(sd)
+    # A trained recogniser's BatchNorm running statistics match its activations; random ones do not, and a deep ReLU
+    # stack with mismatched statistics collapses to content-independent features (uniform attention maps, nothing to
+    # test).  Calibrate them the way training would: one train-mode pass of the encoder over a calibration batch with
+    # cumulative averaging (momentum=None), then freeze.  The resulting buffers are stored in the fixture so the tests
+    # rebuild exactly this state dict from (spec, seed) + fixture.
+    _, cal = synth.synth_images(8, seed=11)
+    for m in model.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.reset_running_stats()
+            m.momentum = None
+    model.train()
+    with torch.no_grad():
+        model.encoder(FO.to_gray_tensor(cal))
+    model.eval()
+    bn_stats = {k: v.clone() for k, v in model.state_dict().items()
+                if k.endswith("running_mean") or k.endswith("running_var")}
+    sd.update(bn_stats)
 
     B = 2
-    _, hr = synth.synth_images(B, seed=5)
-    sr = (hr + 0.08 * torch.randn(hr.shape, generator=torch.Generator().manual_seed(3))).clamp(0, 1)
+    lr, hr = synth.synth_images(B, seed=5)
+    # an early-training SR output: the blurry bilinear up-sample of the LR crop plus a little noise
+    sr = torch.nn.functional.interpolate(lr, scale_factor=2, mode="bilinear", align_corners=False)
+    sr = (sr + 0.02 * torch.randn(hr.shape, generator=torch.Generator().manual_seed(3))).clamp(0, 1)
     labels = ["ab3", "Hello"]
     dic = FO.synth_decomposition()
 
@@ -91,7 +110,7 @@ def main():
 
     out = {"hr": hr, "sr": sr, "labels": labels, "length": r_len, "text_input": r_inp, "loss": loss_r.detach(),
            "mse": mse_r.detach(), "attention_loss": att_r.detach(), "map_hr": r_map, "map_sr": info["map_sr"].detach(),
-           "probs_hr": r_probs, "correct_hr": r_corr, "d_sr_total_x100": sr_r.grad, "d_sr_attn_x100": sr_a.grad}
+           "probs_hr": r_probs, "correct_hr": r_corr, "d_sr_total_x100": sr_r.grad, "d_sr_attn_x100": sr_a.grad, "bn_stats": bn_stats}
     torch.save(out, gd / "focus_b2.pt")
     h = hashlib.sha256((gd / "focus_b2.pt").read_bytes()).hexdigest()
     sums = [ln for ln in (gd / "SHA256SUMS").read_text().splitlines() if "focus_b2.pt" not in ln]

@@ -117,3 +117,27 @@ def test_two_rank_gloo_gradient_exchange(tmp_path):
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
         assert "ok" in o
+
+
+def test_focus_loss_dropin_surface():
+    """the frozen recogniser container carries the reference's state_dict; the loss refuses CPU tensors"""
+    import types
+    from fudanocr_b200 import _lib as L
+    from fudanocr_b200.loss.stroke_focus_loss import StrokeFocusLoss
+    from fudanocr_b200.loss.transformer_english_decomposition import Transformer
+    from oracle import synth, focus_oracle as FO
+    spec = synth.load_spec("focus")
+    t = Transformer("tg")
+    assert list(t.state_dict().keys()) == list(spec.keys())
+    assert all(list(v.shape) == spec[k] for k, v in t.state_dict().items())
+    stt = Transformer("stt")
+    assert "embedding_word.lut.weight" in stt.state_dict() and stt.state_dict()["generator_word.proj.weight"].shape[0] == 37
+    sd = {"module." + k: v for k, v in t.state_dict().items()}          # DataParallel-prefixed asset, as shipped
+    crit = StrokeFocusLoss(types.SimpleNamespace(text_focus=True, stroke_lambda=50), decomposition=FO.synth_decomposition(),
+                           transformer_state_dict=sd)
+    assert not any(p.requires_grad for p in crit.transformer.parameters())
+    ln, inp, gt = crit.label_stroke_encoder(["ab3", "Hello"])
+    o_ln, o_inp, o_gt = FO.label_stroke_encoder(["ab3", "Hello"], FO.synth_decomposition())
+    assert torch.equal(ln, o_ln) and torch.equal(inp, o_inp) and torch.equal(gt, o_gt)
+    with pytest.raises(L.FocrError):
+        crit(torch.rand(2, 3, 32, 128), torch.rand(2, 3, 32, 128), ["ab3", "Hello"])

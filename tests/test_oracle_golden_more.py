@@ -54,3 +54,31 @@ def test_tsrn_oracle_vs_reference_golden():
             assert info["grads"][k].norm().item() < 1e-4 * gmax, k
         else:
             assert abs(info["grads"][k].norm().item() - n) <= 1e-3 * n + 1e-6, k
+
+
+def focus_state_dict(g):
+    """(spec, seed 777) synthetic recogniser + the calibrated BatchNorm statistics stored in the fixture"""
+    from oracle import focus_oracle as FO
+    sd = synth.synth_state_dict(synth.load_spec("focus"), seed=777, computed={"pe.pe": FO.positional_encoding(512, 5000)})
+    sd.update(g["bn_stats"])
+    return sd
+
+
+def test_focus_oracle_vs_reference_golden():
+    """stroke-focus loss (text-gestalt): restatement vs outputs of the unmodified reference classes"""
+    from oracle import focus_oracle as FO
+    g = _load("focus_b2.pt")
+    sd = focus_state_dict(g)
+    assert len(sd) == 244
+    dic = FO.synth_decomposition()
+    ln, inp, _ = FO.label_stroke_encoder(g["labels"], dic)
+    assert torch.equal(ln, g["length"]) and torch.equal(inp, g["text_input"])
+    sr = g["sr"].clone().requires_grad_(True)
+    loss, mse, att, info = FO.stroke_focus_loss(sd, sr, g["hr"], g["labels"], dic, 50.0)
+    (loss * 100).backward()
+    assert torch.allclose(info["map_hr"], g["map_hr"], atol=1e-6, rtol=1e-3)
+    assert torch.allclose(info["map_sr"], g["map_sr"], atol=1e-6, rtol=1e-3)
+    assert abs(att.item() - g["attention_loss"].item()) < 1e-4 * g["attention_loss"].item()
+    assert abs(loss.item() - g["loss"].item()) < 1e-4 * g["loss"].item()
+    d = g["d_sr_total_x100"]
+    assert ((sr.grad - d).norm() / d.norm()).item() < 2e-3
