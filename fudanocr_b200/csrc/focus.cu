@@ -987,6 +987,7 @@ int focr_focus_loss_ws_tensor(int B, int T, const char* name, long long* byte_of
   else if (nm == "Q") ptr = w.Q, n = w.Mt * kD;
   else if (nm == "text") ptr = w.text, n = w.Mt * kD;
   else if (nm == "a1") ptr = w.a1, n = (long long)B * 4096 * 64;
+  else if (nm == "a2") ptr = w.a2, n = (long long)B * 1024 * 128;
   else if (nm == "p2") ptr = w.p2, n = (long long)B * 256 * 128;
   else if (nm == "feat") ptr = w.act[t.stages[3].conv], n = (long long)B * kTok * kD;
   else if (nm == "K") ptr = w.Kp, n = (long long)B * kTok * kD;

@@ -34,8 +34,9 @@ class _FocusFn(torch.autograd.Function):
     def forward(ctx, sr, hr, owner, text_input, lam):
         losses, d_sr = owner._run(sr, hr, text_input, lam, 1.0)
         ctx.save_for_backward(d_sr)
-        ctx.mark_non_differentiable(losses[1], losses[2])
-        return losses[0], losses[1], losses[2]
+        loss, mse, att = losses[0].clone(), losses[1].clone(), losses[2].clone()
+        ctx.mark_non_differentiable(mse, att)
+        return loss, mse, att
 
     @staticmethod
     def backward(ctx, g0, g1, g2):

@@ -26,13 +26,17 @@ _CHUNK = 65536
 
 class TBSRNTrainer:
     def __init__(self, model: TBSRN, lr: float = 1e-4, betas=(0.5, 0.999), eps: float = 1e-8,
-                 max_grad_norm: float = 0.25, loss_scale: float = 100.0, process_group=None):
+                 max_grad_norm: float = 0.25, loss_scale: float = 100.0, process_group=None, criterion=None):
         if not isinstance(model, _SREngineModule):
             raise TypeError("TBSRNTrainer drives the engine-backed SR models (fudanocr_b200.model.tbsrn.TBSRN / tsrn.TSRN)")
         self.model = model
         self.lr, self.betas, self.eps = lr, betas, eps
         self.max_grad_norm, self.loss_scale = max_grad_norm, loss_scale
         self.pg = process_group
+        # image_crit of the step body: None = the MSE term alone (text_focus off); otherwise a fudanocr_b200.loss
+        # module with loss_and_grad() (StrokeFocusLoss: text-gestalt/interfaces/super_resolution.py:69, config 3)
+        self.criterion = criterion
+        self.losses: Optional[torch.Tensor] = None
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
         tensors, _ = model._slots()
         self.slots = list(model._grad_slots)
@@ -75,9 +79,11 @@ class TBSRNTrainer:
         if self.world > 1:  # start from identical weights on every rank (rank 0's)
             dist.broadcast(self.flat_p, src=0, group=self.pg)
 
-    def step(self, images_lr: torch.Tensor, images_hr: torch.Tensor, seed: Optional[int] = None) -> torch.Tensor:
-        """One optimisation step on device-resident fp32 NCHW batches.  Returns the (device) MSE loss tensor
-        of this rank's shard; nothing here blocks the host."""
+    def step(self, images_lr: torch.Tensor, images_hr: torch.Tensor, seed: Optional[int] = None,
+             labels=None) -> torch.Tensor:
+        """One optimisation step on device-resident fp32 NCHW batches.  Returns the (device) loss tensor of this
+        rank's shard (MSE, or the criterion's total loss; its parts are in ``self.losses``); nothing here blocks
+        the host."""
         m = self.model
         B = images_lr.shape[0]
         dev = images_lr.device
@@ -92,9 +98,13 @@ class TBSRNTrainer:
         st = L.cur_stream()
         lib = L.lib
         L.check(m._c_forward(self.ptable, images_lr, self.sr, B, flags, p, seed, ws), "sr_forward")
-        L.check(lib.focr_mse_loss_grad(self.sr.data_ptr(), images_hr.data_ptr(), self.d_sr.data_ptr(),
-                                       self.loss.data_ptr(), self.sr.numel(), self.loss_scale, self.scratch.data_ptr(),
-                                       self.scratch.numel(), st), "mse_loss_grad")
+        if self.criterion is None:
+            L.check(lib.focr_mse_loss_grad(self.sr.data_ptr(), images_hr.data_ptr(), self.d_sr.data_ptr(),
+                                           self.loss.data_ptr(), self.sr.numel(), self.loss_scale, self.scratch.data_ptr(),
+                                           self.scratch.numel(), st), "mse_loss_grad")
+        else:
+            self.losses = self.criterion.loss_and_grad(self.sr, images_hr, labels, self.loss_scale, self.d_sr)
+            self.loss = self.losses[0:1]
         L.check(m._c_backward(self.ptable, self.gtable, images_lr, self.d_sr, B, flags, p, seed, ws), "sr_backward")
         gscale = 1.0
         if self.world > 1:

@@ -39,7 +39,7 @@ def main():
     spec = {k: list(v.shape) for k, v in model.state_dict().items()}
     gd = synth.GOLDEN_DIR
     (gd / "focus_spec.json").write_text(json.dumps(spec, indent=0))
-    sd = synth.synth_state_dict(spec, seed=777, computed={"pe.pe": FO.positional_encoding(512, 5000)})
+    sd = FO.synth_recogniser_state_dict(spec)
     assert torch.equal(sd["pe.pe"], model.state_dict()["pe.pe"])
     model.load_state_dict(sd)
     # A trained recogniser's BatchNorm running statistics match its activations; random ones do not, and a deep ReLU
@@ -107,6 +107,11 @@ def main():
     sr_a = sr.clone().requires_grad_(True)
     _, _, att_a, _ = FO.stroke_focus_loss(sd, sr_a, hr, labels, dic, 50.0)
     (att_a * 50.0 * 100).backward()
+
+    # the BatchNorm-folded form of the restatement is the same function
+    with torch.no_grad():
+        m_fold = FO.attention_map(sd, FO.to_gray_tensor(hr), r_inp, FO.Numerics(fold=True))
+    assert torch.allclose(m_fold, r_map, atol=1e-6, rtol=1e-3), (m_fold - r_map).abs().max()
 
     out = {"hr": hr, "sr": sr, "labels": labels, "length": r_len, "text_input": r_inp, "loss": loss_r.detach(),
            "mse": mse_r.detach(), "attention_loss": att_r.detach(), "map_hr": r_map, "map_sr": info["map_sr"].detach(),

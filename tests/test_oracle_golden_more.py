@@ -59,8 +59,7 @@ def test_tsrn_oracle_vs_reference_golden():
 def focus_state_dict(g):
     """(spec, seed 777) synthetic recogniser + the calibrated BatchNorm statistics stored in the fixture"""
     from oracle import focus_oracle as FO
-    sd = synth.synth_state_dict(synth.load_spec("focus"), seed=777, computed={"pe.pe": FO.positional_encoding(512, 5000)})
-    sd.update(g["bn_stats"])
+    sd = FO.synth_recogniser_state_dict(synth.load_spec("focus"), g["bn_stats"])
     return sd
 
 
