@@ -40,6 +40,8 @@ constexpr int kHeads = 16;    // cross / masked attention heads, d_k = 64
 constexpr int kDk = 64;
 constexpr int kTok = 256;     // 8 x 32 encoder positions
 constexpr int kMaxT = 256;    // longest decoder input handled by the text-side kernels
+constexpr int kFF = 2048;     // PositionwiseFeedForward width
+constexpr int kGenPad = 64;   // generator rows padded to one GEMM tile (n_class <= 64)
 
 // ---------------------------------------------------------------------------------------------
 // topology + slots (slot i = reference state_dict entry i)
@@ -174,6 +176,9 @@ struct Prep {
   float *ln1a, *ln1b;
   bf16 *xq, *xk, *xkT;      // cross-attention query / key projections; xkT = [in][out] for the input gradient
   float *xqb, *xkb;
+  // rest of the decoder (recognition term of TextFocusLoss): value / output projections, FFN, generator (padded to 64 rows)
+  bf16 *xv, *xvT, *xo, *xoT, *w1, *w1T, *w2, *w2T, *gen, *genT;
+  float *xvb, *xob, *w1b, *w2b, *genb, *ln2a, *ln2b, *ln3a, *ln3b;
   float* fold_tmp;          // fp32 scratch for the BN fold (largest conv)
   size_t total;
 };
@@ -202,6 +207,16 @@ void prep_layout(Prep& p, int n_class, void* base) {
   for (auto l : lin) *l = b.take<bf16>((size_t)kD * kD);
   float** vec[8] = {&p.mqb, &p.mkb, &p.mvb, &p.mob, &p.ln1a, &p.ln1b, &p.xqb, &p.xkb};
   for (auto l : vec) *l = b.take<float>(kD);
+  bf16** lin2[4] = {&p.xv, &p.xvT, &p.xo, &p.xoT};
+  for (auto l : lin2) *l = b.take<bf16>((size_t)kD * kD);
+  bf16** ffw[4] = {&p.w1, &p.w1T, &p.w2, &p.w2T};
+  for (auto l : ffw) *l = b.take<bf16>((size_t)kD * kFF);
+  p.gen = b.take<bf16>((size_t)kGenPad * kD);
+  p.genT = b.take<bf16>((size_t)kD * kGenPad);
+  float** vec2[7] = {&p.xvb, &p.xob, &p.w2b, &p.ln2a, &p.ln2b, &p.ln3a, &p.ln3b};
+  for (auto l : vec2) *l = b.take<float>(kD);
+  p.w1b = b.take<float>(kFF);
+  p.genb = b.take<float>(kGenPad);
   p.fold_tmp = b.take<float>((size_t)9 * 512 * 1024);
   p.total = (b.off + 255) / 256 * 256;
 }
@@ -218,6 +233,9 @@ struct Ws {
   bf16 *g_a2, *g_p1, *g_a1;
   float* partial;  // [B*16] L1 partials + mse scratch
   float* scal;     // [4]
+  // recognition term (SR branch only)
+  bf16 *Vp, *ctx, *x2, *r2, *hff, *x3, *r3, *dlogits, *dr3, *dx3, *dh, *dr2, *dx2, *dctx;
+  float *logits, *ce_partial;
   size_t total;
 };
 void ws_layout(Ws& w, int B, int T, void* base) {
@@ -242,6 +260,14 @@ void ws_layout(Ws& w, int B, int T, void* base) {
   w.g_a1 = b.take<bf16>((size_t)B * 4096 * 64);
   w.partial = b.take<float>((size_t)B * kHeads + 4096);
   w.scal = b.take<float>(8);
+  w.Vp = b.take<bf16>((size_t)B * kTok * kD);
+  bf16** t1[10] = {&w.ctx, &w.x2, &w.r2, &w.x3, &w.r3, &w.dr3, &w.dx3, &w.dr2, &w.dx2, &w.dctx};
+  for (auto p : t1) *p = b.take<bf16>((size_t)w.Mt * kD);
+  w.hff = b.take<bf16>((size_t)w.Mt * kFF);
+  w.dh = b.take<bf16>((size_t)w.Mt * kFF);
+  w.dlogits = b.take<bf16>((size_t)w.Mt * kGenPad);
+  w.logits = b.take<float>((size_t)w.Mt * kGenPad);
+  w.ce_partial = b.take<float>((size_t)B + 8);
   w.total = (b.off + 255) / 256 * 256;
 }
 
@@ -697,6 +723,263 @@ __global__ void __launch_bounds__(256) xattn_map_bwd_kernel(const float* __restr
     float s = 0.f;
     for (int i = 0; i < 8; ++i) s += red[i];
     l1_partial[blockIdx.x] = s;
+  }
+}
+
+// context rows of the cross-attention: ctx[b,t,h,:] = sum_k P[b,h,t,k] V[b,k,h,:]; one CTA per (sample, head), V head slice in
+// shared memory, one warp per query row, lane owns 2 of the 64 channels   (attention() :26-46, MultiHeadedAttention :57-66)
+__global__ void __launch_bounds__(256) xattn_ctx_kernel(const float* __restrict__ P, const bf16* __restrict__ V,
+                                                        bf16* __restrict__ ctx, int T) {
+  __shared__ uint32_t Vs[kTok * 32];
+  __shared__ float ps[8][kTok];
+  const int b = blockIdx.x / kHeads, h = blockIdx.x % kHeads;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < kTok * 32; i += 256) {
+    const int r = i >> 5, c = i & 31;
+    Vs[i] = *reinterpret_cast<const uint32_t*>(V + ((long)b * kTok + r) * kD + h * kDk + 2 * c);
+  }
+  __syncthreads();
+  for (int t = warp; t < T; t += 8) {
+    const float* pr = P + (((long)b * kHeads + h) * T + t) * kTok;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ps[warp][lane + 32 * j] = pr[lane + 32 * j];
+    __syncwarp();
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < kTok; ++k) {
+      const float2 vf = unpack_bf16x2(Vs[k * 32 + lane]);
+      a0 = fmaf(ps[warp][k], vf.x, a0);
+      a1 = fmaf(ps[warp][k], vf.y, a1);
+    }
+    *reinterpret_cast<uint32_t*>(ctx + ((long)b * T + t) * kD + h * kDk + 2 * lane) = pack_bf16x2(a0, a1);
+    __syncwarp();
+  }
+}
+
+// input gradient of the recogniser's LayerNorm (1024 features, unbiased std, eps on std); warp per row
+//   g = dy * a;  dx = inv (g - mean(g)) - xc inv^2 sum(g xc) / ((n-1) std),  inv = 1/(std+eps), xc = x - mean
+__global__ void ln1024_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ a,
+                                  bf16* __restrict__ dx, long rows, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long row = blockIdx.x * (long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float v[32], g[32];
+  const uint4* xp = reinterpret_cast<const uint4*>(x + row * kD);
+  const uint4* gp = reinterpret_cast<const uint4*>(dy + row * kD);
+  float s = 0.f, sg = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint4 u = xp[lane + 32 * j], w = gp[lane + 32 * j];
+    const uint32_t uw[4] = {u.x, u.y, u.z, u.w}, ww[4] = {w.x, w.y, w.z, w.w};
+    const int c0 = (lane + 32 * j) * 8;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float2 f = unpack_bf16x2(uw[q]), d = unpack_bf16x2(ww[q]);
+      v[j * 8 + 2 * q] = f.x;
+      v[j * 8 + 2 * q + 1] = f.y;
+      g[j * 8 + 2 * q] = d.x * a[c0 + 2 * q];
+      g[j * 8 + 2 * q + 1] = d.y * a[c0 + 2 * q + 1];
+      s += f.x + f.y;
+      sg += g[j * 8 + 2 * q] + g[j * 8 + 2 * q + 1];
+    }
+  }
+  const float mean = warp_sum(s) * (1.f / kD);
+  const float gmean = warp_sum(sg) * (1.f / kD);
+  float ss = 0.f, sgx = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    v[j] -= mean;
+    ss = fmaf(v[j], v[j], ss);
+    sgx = fmaf(g[j], v[j], sgx);
+  }
+  const float sd = sqrtf(warp_sum(ss) * (1.f / (kD - 1)));
+  sgx = warp_sum(sgx);
+  const float inv = 1.f / (sd + eps);
+  const float k2 = sd > 0.f ? inv * inv * sgx / ((kD - 1) * sd) : 0.f;
+  uint4* op = reinterpret_cast<uint4*>(dx + row * kD);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float o[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) o[q] = inv * (g[j * 8 + q] - gmean) - v[j * 8 + q] * k2;
+    uint4 u;
+    u.x = pack_bf16x2(o[0], o[1]);
+    u.y = pack_bf16x2(o[2], o[3]);
+    u.z = pack_bf16x2(o[4], o[5]);
+    u.w = pack_bf16x2(o[6], o[7]);
+    op[lane + 32 * j] = u;
+  }
+}
+
+// weight_cross_entropy (STT/loss/weight_ce_loss.py:36-45) on the valid positions (t < length[b]) of the logits (Mt, 64 pad):
+//   loss_i = -log( w[gt_i][gt_i] e^{p_gt} / sum_j w[gt_i][j] e^{p_j} ), mean over all valid positions; evaluated with
+//   log-sum-exp.  One CTA per sample, one warp per position; writes dlogits = coef * (softmax_w - onehot) (bf16, zero for
+//   invalid rows / padded classes), the packed logits (optional) and the per-sample loss sum.
+__global__ void __launch_bounds__(128) wce_kernel(const float* __restrict__ logits, const long long* __restrict__ length,
+                                                  const long long* __restrict__ gt, const float* __restrict__ table,
+                                                  bf16* __restrict__ dlogits, float* __restrict__ packed,
+                                                  float* __restrict__ partial, int B, int T, int n_class, float lam_gscale) {
+  const int b = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  long long start = 0, total = 0;
+  for (int i = 0; i < B; ++i) {
+    const long long l = length[i];
+    if (i < b) start += l;
+    total += l;
+  }
+  const int len = (int)length[b];
+  const float coef = lam_gscale / (float)total;
+  __shared__ float red[4];
+  float lsum = 0.f;
+  for (int t = warp; t < T; t += 4) {
+    const long row = (long)b * T + t;
+    bf16* dr = dlogits + row * kGenPad;
+    if (t >= len) {
+      dr[lane] = __float2bfloat16_rn(0.f);
+      dr[lane + 32] = __float2bfloat16_rn(0.f);
+      continue;
+    }
+    const int g = (int)gt[start + t];
+    const float* pr = logits + row * kGenPad;
+    float z[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int c = lane + 32 * j;
+      z[j] = c < n_class ? pr[c] + __logf(table[g * n_class + c]) : -INFINITY;
+      if (packed != nullptr && c < n_class) packed[(start + t) * n_class + c] = pr[c];
+    }
+    const float mx = warp_max(fmaxf(z[0], z[1]));
+    const float e0 = __expf(z[0] - mx), e1 = __expf(z[1] - mx);
+    const float Z = warp_sum(e0 + e1);
+    const float zg = __shfl_sync(0xffffffffu, g < 32 ? z[0] : z[1], g & 31);
+    lsum += (mx + __logf(Z)) - zg;
+    const float inv = 1.f / Z;
+    dr[lane] = __float2bfloat16_rn(coef * (e0 * inv - (lane == g ? 1.f : 0.f)));
+    dr[lane + 32] = __float2bfloat16_rn(coef * (e1 * inv - (lane + 32 == g ? 1.f : 0.f)));
+  }
+  if (lane == 0) red[warp] = lsum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    partial[b] = red[0] + red[1] + red[2] + red[3];
+    if (b == 0) partial[B] = (float)total;
+  }
+}
+
+// cross-attention backward with both loss terms: dP = L1-map term + dctx . V^T (recognition term);
+//   dS = P (dP - sum_k dP P) / 8;  dK[b,k,h,:] = sum_t dS[t,k] Q[b,t,h,:];  dV[b,k,h,:] = sum_t P[t,k] dctx[b,t,h,:]
+// one CTA per (sample, head), thread k owns rows k of dK and dV (2 x 64 fp32 accumulators)
+__global__ void __launch_bounds__(256) xattn_full_bwd_kernel(const float* __restrict__ Phr, const float* __restrict__ Psr,
+                                                             const bf16* __restrict__ Q, const bf16* __restrict__ V,
+                                                             const bf16* __restrict__ dctx, bf16* __restrict__ dK,
+                                                             bf16* __restrict__ dV, float* __restrict__ l1_partial, int T,
+                                                             float coef) {
+  extern __shared__ uint32_t sm_dyn[];
+  uint32_t* Vs = sm_dyn;                                         // [256][33] bf16 pairs
+  float* dS = reinterpret_cast<float*>(Vs + kTok * 33);          // [8][256]
+  float* Pm = dS + 8 * kTok;                                     // [8][256]
+  float* qs = Pm + 8 * kTok;                                     // [8][64]
+  float* dcs = qs + 8 * 64;                                      // [8][64]
+  __shared__ float red[8];
+  const int b = blockIdx.x / kHeads, h = blockIdx.x % kHeads;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < kTok * 32; i += 256) {
+    const int r = i >> 5, c = i & 31;
+    Vs[r * 33 + c] = *reinterpret_cast<const uint32_t*>(V + ((long)b * kTok + r) * kD + h * kDk + 2 * c);
+  }
+  float accK[64], accV[64];
+#pragma unroll
+  for (int d = 0; d < 64; ++d) accK[d] = accV[d] = 0.f;
+  float l1 = 0.f;
+  __syncthreads();
+  for (int t0 = 0; t0 < T; t0 += 8) {
+    const int t = t0 + warp;
+    if (t < T) {
+      const long qo = ((long)b * T + t) * kD + h * kDk + 2 * lane;
+      const float2 qf = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(Q + qo));
+      const float2 cf = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dctx + qo));
+      qs[warp * 64 + 2 * lane] = qf.x;
+      qs[warp * 64 + 2 * lane + 1] = qf.y;
+      dcs[warp * 64 + 2 * lane] = cf.x;
+      dcs[warp * 64 + 2 * lane + 1] = cf.y;
+      __syncwarp();
+      const long ro = (((long)b * kHeads + h) * T + t) * kTok;
+      float ps[8], g[8];
+      float dot = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int kk = lane + 32 * j;
+        ps[j] = Psr[ro + kk];
+        const float df = ps[j] - Phr[ro + kk];
+        l1 += fabsf(df);
+        float gg = df > 0.f ? coef : (df < 0.f ? -coef : 0.f);
+#pragma unroll 8
+        for (int d2 = 0; d2 < 32; ++d2) {
+          const float2 vf = unpack_bf16x2(Vs[kk * 33 + d2]);
+          gg = fmaf(dcs[warp * 64 + 2 * d2], vf.x, gg);
+          gg = fmaf(dcs[warp * 64 + 2 * d2 + 1], vf.y, gg);
+        }
+        g[j] = gg;
+        dot = fmaf(gg, ps[j], dot);
+      }
+      dot = warp_sum(dot);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        dS[warp * kTok + lane + 32 * j] = ps[j] * (g[j] - dot) * 0.125f;
+        Pm[warp * kTok + lane + 32 * j] = ps[j];
+      }
+    }
+    __syncthreads();
+    const int nt = min(8, T - t0);
+    for (int tt = 0; tt < nt; ++tt) {
+      const float ds = dS[tt * kTok + threadIdx.x], pv = Pm[tt * kTok + threadIdx.x];
+#pragma unroll
+      for (int d = 0; d < 64; ++d) {
+        accK[d] = fmaf(ds, qs[tt * 64 + d], accK[d]);
+        accV[d] = fmaf(pv, dcs[tt * 64 + d], accV[d]);
+      }
+    }
+    __syncthreads();
+  }
+  uint4* opk = reinterpret_cast<uint4*>(dK + ((long)b * kTok + threadIdx.x) * kD + h * kDk);
+  uint4* opv = reinterpret_cast<uint4*>(dV + ((long)b * kTok + threadIdx.x) * kD + h * kDk);
+#pragma unroll
+  for (int c8 = 0; c8 < 8; ++c8) {
+    uint4 u, w;
+    u.x = pack_bf16x2(accK[c8 * 8 + 0], accK[c8 * 8 + 1]);
+    u.y = pack_bf16x2(accK[c8 * 8 + 2], accK[c8 * 8 + 3]);
+    u.z = pack_bf16x2(accK[c8 * 8 + 4], accK[c8 * 8 + 5]);
+    u.w = pack_bf16x2(accK[c8 * 8 + 6], accK[c8 * 8 + 7]);
+    w.x = pack_bf16x2(accV[c8 * 8 + 0], accV[c8 * 8 + 1]);
+    w.y = pack_bf16x2(accV[c8 * 8 + 2], accV[c8 * 8 + 3]);
+    w.z = pack_bf16x2(accV[c8 * 8 + 4], accV[c8 * 8 + 5]);
+    w.w = pack_bf16x2(accV[c8 * 8 + 6], accV[c8 * 8 + 7]);
+    opk[c8] = u;
+    opv[c8] = w;
+  }
+  l1 = warp_sum(l1);
+  if (lane == 0) red[warp] = l1;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < 8; ++i) s += red[i];
+    l1_partial[blockIdx.x] = s;
+  }
+}
+
+// losses = {mse + la * attention + lc * recognition, mse, attention, recognition}   (single warp)
+__global__ void finish_loss4_kernel(const float* __restrict__ partial, int n, float inv_numel, float la,
+                                    const float* __restrict__ ce_partial, int B, float lc, float* __restrict__ losses) {
+  float s = 0.f, c = 0.f;
+  for (int i = threadIdx.x; i < n; i += 32) s += partial[i];
+  for (int i = threadIdx.x; i < B; i += 32) c += ce_partial[i];
+  s = warp_sum(s);
+  c = warp_sum(c);
+  if (threadIdx.x == 0) {
+    const float att = s * inv_numel;
+    const float rec = c / ce_partial[B];
+    losses[2] = att;
+    losses[3] = rec;
+    losses[0] = losses[1] + la * att + lc * rec;
   }
 }
 
