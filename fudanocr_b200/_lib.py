@@ -82,6 +82,8 @@ _SIGS = {
     "focr_strokenet_prepare": (C.c_int, [_pp, _i, _vp, _sz, _vp]),
     "focr_focus_loss_workspace_bytes": (_sz, [_i, _i]),
     "focr_focus_loss": (C.c_int, [_vp, _sz, _i, _fp, _fp, _vp, _i, _i, _f, _f, _fp, _fp, _fp, _fp, _vp, _sz, _vp]),
+    "focr_text_focus_loss": (C.c_int, [_vp, _sz, _i, _fp, _fp, _vp, _vp, _vp, _fp, _i, _i, _f, _f, _f, _fp, _fp, _fp, _fp, _fp,
+                                       _vp, _sz, _vp]),
     "focr_focus_loss_ws_tensor": (C.c_int, [_i, _i, C.c_char_p, C.POINTER(_ll), C.POINTER(_ll), C.POINTER(_i)]),
 }
 

@@ -177,8 +177,8 @@ struct Prep {
   bf16 *xq, *xk, *xkT;      // cross-attention query / key projections; xkT = [in][out] for the input gradient
   float *xqb, *xkb;
   // rest of the decoder (recognition term of TextFocusLoss): value / output projections, FFN, generator (padded to 64 rows)
-  bf16 *xv, *xvT, *xo, *xoT, *w1, *w1T, *w2, *w2T, *gen, *genT;
-  float *xvb, *xob, *w1b, *w2b, *genb, *ln2a, *ln2b, *ln3a, *ln3b;
+  bf16 *xv, *xvT, *xo, *xoT, *ff1, *ff1T, *ff2, *ff2T, *gen, *genT;
+  float *xvb, *xob, *ff1b, *ff2b, *genb, *ln2a, *ln2b, *ln3a, *ln3b;
   float* fold_tmp;          // fp32 scratch for the BN fold (largest conv)
   size_t total;
 };
@@ -209,13 +209,13 @@ void prep_layout(Prep& p, int n_class, void* base) {
   for (auto l : vec) *l = b.take<float>(kD);
   bf16** lin2[4] = {&p.xv, &p.xvT, &p.xo, &p.xoT};
   for (auto l : lin2) *l = b.take<bf16>((size_t)kD * kD);
-  bf16** ffw[4] = {&p.w1, &p.w1T, &p.w2, &p.w2T};
+  bf16** ffw[4] = {&p.ff1, &p.ff1T, &p.ff2, &p.ff2T};
   for (auto l : ffw) *l = b.take<bf16>((size_t)kD * kFF);
   p.gen = b.take<bf16>((size_t)kGenPad * kD);
   p.genT = b.take<bf16>((size_t)kD * kGenPad);
-  float** vec2[7] = {&p.xvb, &p.xob, &p.w2b, &p.ln2a, &p.ln2b, &p.ln3a, &p.ln3b};
+  float** vec2[7] = {&p.xvb, &p.xob, &p.ff2b, &p.ln2a, &p.ln2b, &p.ln3a, &p.ln3b};
   for (auto l : vec2) *l = b.take<float>(kD);
-  p.w1b = b.take<float>(kFF);
+  p.ff1b = b.take<float>(kFF);
   p.genb = b.take<float>(kGenPad);
   p.fold_tmp = b.take<float>((size_t)9 * 512 * 1024);
   p.total = (b.off + 255) / 256 * 256;
@@ -1084,6 +1084,25 @@ int prepare(void* const* prm, int n_class, Prep& pw, cudaStream_t s) {
   cp(prm[d0 + D_LN1B], pw.ln1b, kD);
   cp(prm[d0 + D_XQ_B], pw.xqb, kD);
   cp(prm[d0 + D_XK_B], pw.xkb, kD);
+  // recognition-term half of the decoder
+  FOCR_REQUIRE(n_class <= kGenPad, "strokenet_prepare: n_class %d > %d", n_class, kGenPad);
+  TRY(prep_linear_w((const float*)prm[d0 + D_XV_W], pw.xv, pw.xvT, kD, kD, kD, 0, s));
+  TRY(prep_linear_w((const float*)prm[d0 + D_XO_W], pw.xo, pw.xoT, kD, kD, kD, 0, s));
+  TRY(prep_linear_w((const float*)prm[d0 + D_W1_W], pw.ff1, pw.ff1T, kFF, kD, kFF, 0, s));
+  TRY(prep_linear_w((const float*)prm[d0 + D_W2_W], pw.ff2, pw.ff2T, kD, kFF, kD, 0, s));
+  FOCR_CHECK_CUDA(cudaMemsetAsync(pw.gen, 0, (size_t)kGenPad * kD * 2, s));
+  FOCR_CHECK_CUDA(cudaMemsetAsync(pw.genT, 0, (size_t)kGenPad * kD * 2, s));
+  FOCR_CHECK_CUDA(cudaMemsetAsync(pw.genb, 0, (size_t)kGenPad * 4, s));
+  TRY(prep_linear_w((const float*)prm[d0 + D_GEN_W], pw.gen, pw.genT, n_class, kD, kGenPad, 0, s));
+  cp(prm[d0 + D_XV_B], pw.xvb, kD);
+  cp(prm[d0 + D_XO_B], pw.xob, kD);
+  cp(prm[d0 + D_W1_B], pw.ff1b, kFF);
+  cp(prm[d0 + D_W2_B], pw.ff2b, kD);
+  cp(prm[d0 + D_GEN_B], pw.genb, n_class);
+  cp(prm[d0 + D_LN2A], pw.ln2a, kD);
+  cp(prm[d0 + D_LN2B], pw.ln2b, kD);
+  cp(prm[d0 + D_LN3A], pw.ln3a, kD);
+  cp(prm[d0 + D_LN3B], pw.ln3b, kD);
   FOCR_CHECK_CUDA(cudaGetLastError());
   return FOCR_OK;
 }
@@ -1172,10 +1191,16 @@ int branch_forward(const Prep& pw, const float* img, int B, int T, Ws& w, float*
 }
 
 // SR-branch input gradient: dK (in w.g[1]) -> tokens -> encoder -> gray -> d_img (accumulated)
-int branch_backward(const Prep& pw, int B, Ws& w, float* d_img, cudaStream_t s) {
+int branch_backward(const Prep& pw, int B, Ws& w, float* d_img, bool with_value_path, cudaStream_t s) {
   const Topo& t = topo();
   const int last = t.stages[3].conv;
   TcGemmParams p = gp();
+  if (with_value_path) {  // dV (in w.g[2]) through the value projection first; added to the key path below
+    p.out = w.g[3];
+    TRY(tok_gemm(w.g[2], kD, (long)B * kTok, pw.xvT, kD, p, s));
+    p = gp();
+    p.residual = w.g[3];
+  }
   p.out = w.g[0];
   p.gate = w.act[last];
   TRY(tok_gemm(w.g[1], kD, (long)B * kTok, pw.xkT, kD, p, s));
@@ -1215,6 +1240,75 @@ int branch_backward(const Prep& pw, int B, Ws& w, float* d_img, cudaStream_t s) 
     conv1_dgrad_kernel<<<B * 32, 128, 0, s>>>(w.g_a1, pw.w1, d_img);
     FOCR_LAUNCH_CHECK();
   }
+  return FOCR_OK;
+}
+
+// rest of Decoder.forward for the SR branch (:296-304) + generator + weighted CE, and its backward down to dctx.
+// Needs w.Kp / w.map_sr of the SR branch.  Leaves dlogits-driven dctx in w.dctx.
+int decoder_tail(const Prep& pw, const long long* length, const long long* text_gt, const float* table, int B, int T,
+                 int n_class, float lam_gscale, float* sr_pred_out, Ws& w, cudaStream_t s) {
+  const Topo& t = topo();
+  const bf16* tokens = w.act[t.stages[3].conv];
+  TcGemmParams p = gp();
+  p.bias = pw.xvb;
+  p.out = w.Vp;
+  TRY(tok_gemm(tokens, kD, (long)B * kTok, pw.xv, kD, p, s));
+  {
+    ProfScope _ps("focus_xattn", s);
+    FOCR_CHECK_CUDA(cudaMemsetAsync(w.ctx, 0, (size_t)w.Mt * kD * 2, s));
+    xattn_ctx_kernel<<<B * kHeads, 256, 0, s>>>(w.map_sr, w.Vp, w.ctx, T);
+    FOCR_LAUNCH_CHECK();
+  }
+  p = gp();
+  p.bias = pw.xob;
+  p.out = w.x2;
+  p.residual = w.query;
+  TRY(tok_gemm(w.ctx, kD, w.Mt, pw.xo, kD, p, s));
+  ln1024_kernel<<<focr_cdiv(w.Mt, 8), 256, 0, s>>>(w.x2, pw.ln2a, pw.ln2b, w.r2, w.Mt, 1e-6f);
+  FOCR_LAUNCH_CHECK();
+  p = gp();
+  p.bias = pw.ff1b;
+  p.out = w.hff;
+  p.relu = 1;
+  TRY(tok_gemm(w.r2, kD, w.Mt, pw.ff1, kFF, p, s));
+  p = gp();
+  p.bias = pw.ff2b;
+  p.out = w.x3;
+  p.residual = w.r2;
+  TRY(tok_gemm(w.hff, kFF, w.Mt, pw.ff2, kD, p, s));
+  ln1024_kernel<<<focr_cdiv(w.Mt, 8), 256, 0, s>>>(w.x3, pw.ln3a, pw.ln3b, w.r3, w.Mt, 1e-6f);
+  FOCR_LAUNCH_CHECK();
+  p = gp();
+  p.bias = pw.genb;
+  p.out = w.logits;
+  p.epi = TC_EPI_F32;
+  TRY(tok_gemm(w.r3, kD, w.Mt, pw.gen, kGenPad, p, s));
+  {
+    ProfScope _ps("focus_wce", s);
+    FOCR_CHECK_CUDA(cudaMemsetAsync(w.dlogits, 0, (size_t)w.Mt * kGenPad * 2, s));
+    wce_kernel<<<B, 128, 0, s>>>(w.logits, length, text_gt, table, w.dlogits, sr_pred_out, w.ce_partial, B, T, n_class,
+                                 lam_gscale);
+    FOCR_LAUNCH_CHECK();
+  }
+  // ---- backward to dctx
+  p = gp();
+  p.out = w.dr3;
+  TRY(tok_gemm(w.dlogits, kGenPad, w.Mt, pw.genT, kD, p, s));
+  ln1024_bwd_kernel<<<focr_cdiv(w.Mt, 8), 256, 0, s>>>(w.dr3, w.x3, pw.ln3a, w.dx3, w.Mt, 1e-6f);
+  FOCR_LAUNCH_CHECK();
+  p = gp();
+  p.out = w.dh;
+  p.gate = w.hff;
+  TRY(tok_gemm(w.dx3, kD, w.Mt, pw.ff2T, kFF, p, s));
+  p = gp();
+  p.out = w.dr2;
+  p.residual = w.dx3;
+  TRY(tok_gemm(w.dh, kFF, w.Mt, pw.ff1T, kD, p, s));
+  ln1024_bwd_kernel<<<focr_cdiv(w.Mt, 8), 256, 0, s>>>(w.dr2, w.x2, pw.ln2a, w.dx2, w.Mt, 1e-6f);
+  FOCR_LAUNCH_CHECK();
+  p = gp();
+  p.out = w.dctx;
+  TRY(tok_gemm(w.dx2, kD, w.Mt, pw.xoT, kD, p, s));
   return FOCR_OK;
 }
 
@@ -1273,6 +1367,14 @@ int focr_focus_loss_ws_tensor(int B, int T, const char* name, long long* byte_of
   else if (nm == "a2") ptr = w.a2, n = (long long)B * 1024 * 128;
   else if (nm == "p2") ptr = w.p2, n = (long long)B * 256 * 128;
   else if (nm == "feat") ptr = w.act[t.stages[3].conv], n = (long long)B * kTok * kD;
+  else if (nm == "logits") ptr = w.logits, n = w.Mt * kGenPad, eb = 4;
+  else if (nm == "ctx") ptr = w.ctx, n = w.Mt * kD;
+  else if (nm == "r2") ptr = w.r2, n = w.Mt * kD;
+  else if (nm == "r3") ptr = w.r3, n = w.Mt * kD;
+  else if (nm == "x2") ptr = w.x2, n = w.Mt * kD;
+  else if (nm == "x3") ptr = w.x3, n = w.Mt * kD;
+  else if (nm == "hff") ptr = w.hff, n = w.Mt * kFF;
+  else if (nm == "V") ptr = w.Vp, n = (long long)B * kTok * kD;
   else if (nm == "K") ptr = w.Kp, n = (long long)B * kTok * kD;
   else if (nm == "map_hr") ptr = w.map_hr, n = (long long)B * kHeads * T * kTok, eb = 4;
   else if (nm == "map_sr") ptr = w.map_sr, n = (long long)B * kHeads * T * kTok, eb = 4;
@@ -1318,7 +1420,55 @@ int focr_focus_loss(const void* prepared, size_t prepared_bytes, int n_class, co
     finish_loss_kernel<<<1, 32, 0, s>>>(w.partial, B * kHeads, (float)(1.0 / numel), lambda, losses);
     FOCR_LAUNCH_CHECK();
   }
-  TRY(branch_backward(pw, B, w, d_sr, s));
+  TRY(branch_backward(pw, B, w, d_sr, false, s));
+  if (map_hr_out)
+    FOCR_CHECK_CUDA(cudaMemcpyAsync(map_hr_out, w.map_hr, (size_t)numel * 4, cudaMemcpyDeviceToDevice, s));
+  if (map_sr_out)
+    FOCR_CHECK_CUDA(cudaMemcpyAsync(map_sr_out, w.map_sr, (size_t)numel * 4, cudaMemcpyDeviceToDevice, s));
+  return FOCR_OK;
+}
+
+// TextFocusLoss.forward with text_focus on (STT/loss/text_focus_loss.py:84-99): mse + lambda_attn * L1(maps) +
+// lambda_ce * weight_cross_entropy(sr logits, text_gt)  (STT/loss/weight_ce_loss.py:36-45), value and gradient.
+int focr_text_focus_loss(const void* prepared, size_t prepared_bytes, int n_class, const float* sr, const float* hr,
+                         const long long* text_input, const long long* length, const long long* text_gt,
+                         const float* weight_table, int B, int T, float lambda_attn, float lambda_ce, float gscale,
+                         float* d_sr, float* losses, float* map_hr_out, float* map_sr_out, float* sr_pred_out, void* ws,
+                         size_t ws_bytes, void* stream) {
+  using namespace strokenet;
+  cudaStream_t s = (cudaStream_t)stream;
+  FOCR_REQUIRE(B >= 1 && T >= 1 && T <= kMaxT, "text_focus_loss: B %d, T %d (T <= %d)", B, T, kMaxT);
+  FOCR_REQUIRE(n_class >= 2 && n_class <= kGenPad, "text_focus_loss: n_class %d", n_class);
+  FOCR_REQUIRE(length && text_gt && weight_table, "text_focus_loss: length / text_gt / weight_table are required");
+  Prep pw;
+  prep_layout(pw, n_class, const_cast<void*>(prepared));
+  FOCR_REQUIRE(prepared && prepared_bytes >= pw.total, "text_focus_loss: prepared blob too small");
+  Ws w;
+  ws_layout(w, B, T, ws);
+  FOCR_REQUIRE(ws && ws_bytes >= w.total, "text_focus_loss: workspace too small (%zu < %zu)", ws_bytes, w.total);
+  const long n = (long)B * 3 * 32 * 128;
+  TRY(focr_mse_loss_grad(sr, hr, d_sr, losses + 1, n, gscale, w.partial, ((size_t)B * kHeads + 4096) * 4, stream));
+  TRY(text_side(pw, text_input, B, T, n_class, w, s));
+  TRY(branch_forward(pw, hr, B, T, w, w.map_hr, s));
+  TRY(branch_forward(pw, sr, B, T, w, w.map_sr, s));
+  TRY(decoder_tail(pw, length, text_gt, weight_table, B, T, n_class, lambda_ce * gscale, sr_pred_out, w, s));
+  const double numel = (double)B * kHeads * T * kTok;
+  {
+    ProfScope _ps("focus_xattn", s);
+    const size_t smem = (size_t)kTok * 33 * 4 + 2 * 8 * kTok * 4 + 2 * 8 * 64 * 4;
+    static bool attr = false;
+    if (!attr) {
+      FOCR_CHECK_CUDA(cudaFuncSetAttribute(xattn_full_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr = true;
+    }
+    xattn_full_bwd_kernel<<<B * kHeads, 256, smem, s>>>(w.map_hr, w.map_sr, w.Q, w.Vp, w.dctx, w.g[1], w.g[2], w.partial, T,
+                                                        (float)((double)lambda_attn * gscale / numel));
+    FOCR_LAUNCH_CHECK();
+    finish_loss4_kernel<<<1, 32, 0, s>>>(w.partial, B * kHeads, (float)(1.0 / numel), lambda_attn, w.ce_partial, B,
+                                         lambda_ce, losses);
+    FOCR_LAUNCH_CHECK();
+  }
+  TRY(branch_backward(pw, B, w, d_sr, true, s));
   if (map_hr_out)
     FOCR_CHECK_CUDA(cudaMemcpyAsync(map_hr_out, w.map_hr, (size_t)numel * 4, cudaMemcpyDeviceToDevice, s));
   if (map_sr_out)

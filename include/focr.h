@@ -151,6 +151,17 @@ size_t focr_focus_loss_workspace_bytes(int B, int T);
 int focr_focus_loss(const void* prepared, size_t prepared_bytes, int n_class, const float* sr, const float* hr,
                     const long long* text_input, int B, int T, float lambda, float gscale, float* d_sr, float* losses,
                     float* map_hr_out, float* map_sr_out, void* ws, size_t ws_bytes, void* stream);
+/* TextFocusLoss.forward (scene-text-telescope/loss/text_focus_loss.py:84-99) = mse + lambda_attn * L1(maps) + lambda_ce *
+ * weight_cross_entropy(sr logits, text_gt) (scene-text-telescope/loss/weight_ce_loss.py:36-45; weight_table fp32
+ * (n_class, n_class) from load_confuse_matrix :10-33).  length (B) and text_gt (sum length) are the int64 tensors of the
+ * reference's label_encoder (:62-81).  losses[4] = {total, mse, attention, recognition}; sr_pred_out (optional, fp32
+ * (sum length, n_class)) receives the packed SR logits.  The full decoder (value path, FFN, LayerNorms, generator) runs for
+ * the SR branch only - the HR branch's logits are never read by the reference either. */
+int focr_text_focus_loss(const void* prepared, size_t prepared_bytes, int n_class, const float* sr, const float* hr,
+                         const long long* text_input, const long long* length, const long long* text_gt,
+                         const float* weight_table, int B, int T, float lambda_attn, float lambda_ce, float gscale,
+                         float* d_sr, float* losses, float* map_hr_out, float* map_sr_out, float* sr_pred_out, void* ws,
+                         size_t ws_bytes, void* stream);
 int focr_focus_loss_ws_tensor(int B, int T, const char* name, long long* byte_offset, long long* elems, int* elem_bytes);
 
 /* --- measurement hooks used by bench.py: CUDA-event scopes on the launching stream + launch counter ----------- */

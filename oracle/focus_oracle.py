@@ -165,7 +165,7 @@ def _mha(sd, pre: str, query: Tensor, key: Tensor, value: Tensor, mask: Optional
         p = p + (nm.teacher[f"{pre}.map"] - p).detach()
     if not need_out:
         return None, p
-    x = nm.a(torch.matmul(p, v).transpose(1, 2).contiguous().view(nb, -1, h * dk))
+    x = nm.act(torch.matmul(p, v).transpose(1, 2).contiguous().view(nb, -1, h * dk), False, key=f"{pre}.ctx")
     return _lin(sd, f"{pre}.linears.3", x, nm), p
 
 
@@ -194,10 +194,11 @@ def decoder(sd, text: Tensor, conv_feature: Tensor, pre: str = "decoder", nm: Nu
     align, amap = _mha(sd, f"{pre}.multihead", result, tokens, tokens, None, nm=nm, need_out=not map_only)
     if map_only:
         return None, amap
-    result = layer_norm_std(result + align, sd[f"{pre}.mul_layernorm2.a_2"], sd[f"{pre}.mul_layernorm2.b_2"])
-    ff = F.linear(F.relu(F.linear(result, sd[f"{pre}.pff.w_1.weight"], sd[f"{pre}.pff.w_1.bias"])),
-                  sd[f"{pre}.pff.w_2.weight"], sd[f"{pre}.pff.w_2.bias"])
-    result = layer_norm_std(result + ff, sd[f"{pre}.mul_layernorm3.a_2"], sd[f"{pre}.mul_layernorm3.b_2"])
+    x2 = nm.act(result + align, False, key=f"{pre}.x2")
+    result = nm.act(layer_norm_std(x2, sd[f"{pre}.mul_layernorm2.a_2"], sd[f"{pre}.mul_layernorm2.b_2"]), False, key=f"{pre}.r2")
+    hidden = nm.act(_lin(sd, f"{pre}.pff.w_1", result, nm), True, key=f"{pre}.pff.w_1")
+    x3 = nm.act(result + _lin(sd, f"{pre}.pff.w_2", hidden, nm), False, key=f"{pre}.x3")
+    result = nm.act(layer_norm_std(x3, sd[f"{pre}.mul_layernorm3.a_2"], sd[f"{pre}.mul_layernorm3.b_2"]), False, key=f"{pre}.r3")
     return result, amap
 
 
@@ -208,12 +209,12 @@ def attention_map(sd, image: Tensor, text_input: Tensor, nm: Numerics = FP32) ->
     return amap
 
 
-def transformer_forward(sd, image: Tensor, text_length: Tensor, text_input: Tensor):
+def transformer_forward(sd, image: Tensor, text_length: Tensor, text_input: Tensor, nm: Numerics = FP32):
     """Transformer.forward with test=False (:356-393) -> (probs_res (sum len, 10), attention map, correct_list)"""
-    feat = resnet_encoder(sd, image)
-    text = text_embedding(sd, text_input)
-    res, amap = decoder(sd, text, feat)
-    logits = F.linear(res, sd["generator_word_with_upperword.proj.weight"], sd["generator_word_with_upperword.proj.bias"])
+    feat = resnet_encoder(sd, image, nm=nm)
+    text = text_embedding(sd, text_input, nm)
+    res, amap = decoder(sd, text, feat, nm=nm)
+    logits = _lin(sd, "generator_word_with_upperword.proj", res, nm)
     rows, correct = [], []
     for i, ln in enumerate(text_length.tolist()):
         r = logits[i, :ln]

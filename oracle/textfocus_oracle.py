@@ -90,15 +90,19 @@ def _rename(sd: Dict[str, Tensor]) -> Dict[str, Tensor]:
 
 
 def text_focus_loss(sd, sr_img: Tensor, hr_img: Tensor, labels: Sequence[str], table: Tensor,
-                    lambda_attn: float = 10.0, lambda_ce: float = 0.0005):
-    """TextFocusLoss.forward with args.text_focus on (:84-99) -> (loss, mse, attention_loss, recognition_loss, info)"""
+                    lambda_attn: float = 10.0, lambda_ce: float = 0.0005, nm: FO.Numerics = FO.FP32,
+                    map_hr: Optional[Tensor] = None):
+    """TextFocusLoss.forward with args.text_focus on (:84-99) -> (loss, mse, attention_loss, recognition_loss, info).
+    nm: numerics mode of the recogniser (focus_oracle.Numerics); map_hr: use this HR attention map instead of computing it"""
     sd = _rename(sd)
     mse = F.mse_loss(sr_img, hr_img)
     labels = [str_filt(s, "lower") + "-" for s in labels]
     length, inp, gt = label_encoder(labels)
     length, inp, gt = length.to(sr_img.device), inp.to(sr_img.device), gt.to(sr_img.device)
-    _, map_hr, _ = FO.transformer_forward(sd, FO.to_gray_tensor(hr_img), length, inp)
-    sr_pred, map_sr, _ = FO.transformer_forward(sd, FO.to_gray_tensor(sr_img), length, inp)
+    if map_hr is None:
+        with torch.no_grad():
+            _, map_hr, _ = FO.transformer_forward(sd, FO.to_gray_tensor(hr_img), length, inp, nm)
+    sr_pred, map_sr, _ = FO.transformer_forward(sd, FO.to_gray_tensor(sr_img), length, inp, nm)
     att = F.l1_loss(map_hr, map_sr)
     rec = weight_cross_entropy(sr_pred, gt, table)
     loss = mse + att * lambda_attn + rec * lambda_ce

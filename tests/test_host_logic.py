@@ -141,3 +141,25 @@ def test_focus_loss_dropin_surface():
     assert torch.equal(ln, o_ln) and torch.equal(inp, o_inp) and torch.equal(gt, o_gt)
     with pytest.raises(L.FocrError):
         crit(torch.rand(2, 3, 32, 128), torch.rand(2, 3, 32, 128), ["ab3", "Hello"])
+
+
+def test_text_focus_loss_dropin_surface():
+    import types
+    from fudanocr_b200 import _lib as L
+    from fudanocr_b200.loss.text_focus_loss import TextFocusLoss, str_filt
+    from fudanocr_b200.loss.transformer_english_decomposition import Transformer
+    from oracle import synth, textfocus_oracle as TF
+    spec = synth.load_spec("textfocus")
+    t = Transformer("stt")
+    assert list(t.state_dict().keys()) == list(spec.keys())
+    assert all(list(v.shape) == spec[k] for k, v in t.state_dict().items())
+    crit = TextFocusLoss(types.SimpleNamespace(text_focus=True), confuse_counts=TF.synth_confuse_counts(),
+                         transformer_state_dict={"module." + k: v for k, v in t.state_dict().items()})
+    assert torch.equal(crit.weight_table, TF.confuse_weight_table(TF.synth_confuse_counts()))
+    labels = ["B200", "text-Focus!", "a"]
+    filt = [str_filt(s, "lower") + "-" for s in labels]
+    assert filt == [TF.str_filt(s, "lower") + "-" for s in labels] == ["b200-", "textfocus-", "a-"]
+    for a, b in zip(crit.label_encoder(filt), TF.label_encoder(filt)):
+        assert torch.equal(a, b)
+    with pytest.raises(L.FocrError):
+        crit(torch.rand(3, 3, 32, 128), torch.rand(3, 3, 32, 128), labels)

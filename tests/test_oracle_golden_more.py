@@ -81,3 +81,25 @@ def test_focus_oracle_vs_reference_golden():
     assert abs(loss.item() - g["loss"].item()) < 1e-4 * g["loss"].item()
     d = g["d_sr_total_x100"]
     assert ((sr.grad - d).norm() / d.norm()).item() < 2e-3
+
+
+def test_textfocus_oracle_vs_reference_golden():
+    """text-focus loss (scene-text-telescope): restatement vs outputs of the unmodified reference modules"""
+    from oracle import focus_oracle as FO, textfocus_oracle as TF
+    g = _load("textfocus_b3.pt")
+    sd = FO.synth_recogniser_state_dict(synth.load_spec("textfocus"), g["bn_stats"], seed=778)
+    table = TF.confuse_weight_table(g["confuse_counts"].numpy())
+    assert torch.equal(table, g["weight_table"])
+    sr = g["sr"].clone().requires_grad_(True)
+    loss, mse, att, rec, info = TF.text_focus_loss(sd, sr, g["hr"], g["labels"], table)
+    (loss * 100).backward()
+    assert torch.equal(info["text_input"], g["text_input"]) and torch.equal(info["text_gt"], g["text_gt"])
+    assert torch.allclose(info["sr_pred"], g["sr_pred"], atol=1e-4, rtol=1e-3)
+    assert abs(rec.item() - g["recognition_loss"].item()) < 1e-4 * g["recognition_loss"].item()
+    assert abs(loss.item() - g["loss"].item()) < 1e-4 * g["loss"].item()
+    d = g["d_sr_total_x100"]
+    assert ((sr.grad - d).norm() / d.norm()).item() < 2e-2
+    # the log-sum-exp form the CUDA kernel uses is the same function
+    lw = torch.log(table[g["text_gt"]])
+    lse = torch.logsumexp(g["sr_pred"] + lw, 1) - (g["sr_pred"] + lw).gather(1, g["text_gt"][:, None])[:, 0]
+    assert abs(lse.mean().item() - g["recognition_loss"].item()) < 1e-5 * g["recognition_loss"].item()
