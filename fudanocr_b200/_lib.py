@@ -44,6 +44,7 @@ _SIGS = {
     "focr_linear_dgrad": (C.c_int, [_vp, _fp, _vp, _l, _i, _i, _vp, _sz, _vp]),
     "focr_linear_wgrad": (C.c_int, [_vp, _vp, _fp, _l, _i, _i, _vp, _sz, _vp]),
     "focr_bias_grad": (C.c_int, [_vp, _fp, _l, _i, _vp, _sz, _vp]),
+    "focr_linear_wgrad_bias": (C.c_int, [_vp, _vp, _fp, _fp, _l, _i, _i, _vp, _sz, _vp]),
     "focr_bn_workspace_bytes": (_sz, []),
     "focr_bn_train_fwd": (C.c_int, [_vp, _fp, _fp, _fp, _fp, _vp, _vp, _fp, _l, _i, _i, _vp, _sz, _vp]),
     "focr_bn_bwd": (C.c_int, [_vp, _vp, _fp, _vp, _fp, _fp, _l, _i, _i, _vp, _sz, _vp]),

@@ -167,6 +167,21 @@ int focr_linear_wgrad(const void* dy, const void* x, float* dw, long M, int K, i
   FOCR_REQUIRE(ws_bytes >= focr_wgrad_workspace_bytes(), "linear_wgrad: workspace too small");
   return linear_wgrad((const bf16*)dy, N, (const bf16*)x, K, M, N, K, dw, 1.f, (float*)ws, (cudaStream_t)stream);
 }
+// weight AND bias gradient in one pass over dY and X (tcgen05 kernel of wgrad_tc.cu when K == 128, N in {64,128,256,384} and
+// M % 64 == 0; the streaming mma.sync kernels otherwise)
+int focr_linear_wgrad_bias(const void* dy, const void* x, float* dw, float* db, long M, int K, int N, void* ws, size_t ws_bytes,
+                           void* stream) {
+  FOCR_REQUIRE(ws_bytes >= focr_wgrad_workspace_bytes(), "linear_wgrad_bias: workspace too small");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (linear_wgrad_tc_supported(M, N, K, N, K) && linear_wgrad_tc_partial_bytes(N) <= ws_bytes)
+    return linear_wgrad_tc((const bf16*)dy, N, (const bf16*)x, K, M, N, dw, db, (float*)ws, s);
+  if (dw) {
+    int rc = linear_wgrad((const bf16*)dy, N, (const bf16*)x, K, M, N, K, dw, 1.f, (float*)ws, s);
+    if (rc) return rc;
+  }
+  if (db) return colsum((const bf16*)dy, N, M, N, db, (float*)ws, s);
+  return FOCR_OK;
+}
 // column sums (bias gradient): out[N] = sum_m x[m][n]
 int focr_bias_grad(const void* dy, float* db, long M, int N, void* ws, size_t ws_bytes, void* stream) {
   FOCR_REQUIRE(ws_bytes >= focr_wgrad_workspace_bytes(), "bias_grad: workspace too small");

@@ -59,6 +59,12 @@ size_t conv3x3_wgrad_partial_bytes(int B, int H, int groups);
 int conv3x3_wgrad(const bf16* dy, const bf16* x, int B, int H, int Co, int shuf, float* dw, float* partial,
                   cudaStream_t s);
 
+// wgrad_tc.cu: tcgen05 weight + bias gradient of a linear layer with K = 128 inputs
+bool linear_wgrad_tc_supported(long T, int N, int K, long ld_dy, long ld_x);
+size_t linear_wgrad_tc_partial_bytes(int N);
+int linear_wgrad_tc(const bf16* dy, long ld_dy, const bf16* x, long ld_x, long T, int N, float* dw, float* db, float* partial,
+                    cudaStream_t s);
+
 // conv9x9.cu
 int im2col_dx(const float* in, bf16* out, int B, int H, int W, int sgn, cudaStream_t s);
 int vgather9(const float* z, const float* bias, float* out, int B, int H, int W, int sgn, cudaStream_t s);

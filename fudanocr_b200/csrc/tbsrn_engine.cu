@@ -672,6 +672,9 @@ int forward(const Slots& sl, void* const* prm, const float* x_lr, float* sr_out,
 namespace {
 int lin_grads(const bf16* dy, long ld_dy, const bf16* x, long T, int N, void* const* grd, int w_slot, int b_slot, Ws& w,
               cudaStream_t s) {
+  if (linear_wgrad_tc_supported(T, N, 128, ld_dy, 128) && linear_wgrad_tc_partial_bytes(N) <= w.partial_bytes &&
+      (grd[w_slot] || grd[b_slot]))  // weight and bias gradient in one pass over dY and X (tcgen05, wgrad_tc.cu)
+    return linear_wgrad_tc(dy, ld_dy, x, 128, T, N, P<float>(grd, w_slot), P<float>(grd, b_slot), w.partial, s);
   if (grd[w_slot]) TRY(linear_wgrad(dy, ld_dy, x, 128, T, N, 128, P<float>(grd, w_slot), 1.f, w.partial, s));
   if (grd[b_slot]) TRY(colsum(dy, ld_dy, T, N, P<float>(grd, b_slot), w.partial, s));
   return FOCR_OK;
@@ -777,8 +780,12 @@ int backward(const Slots& sl, void* const* prm, void* const* grd, const float* x
     p.out = gA;
     p.residual = gB;
     TRY(tok_gemm(w.g384, 384, T, q.qkvT, 128, p, s));
-    TRY(linear_wgrad(w.g384, 384, a.f, 128, T, 384, 128, w.tmpw, 1.f, w.partial, s));
-    TRY(colsum(w.g384, 384, T, 384, w.tmpb, w.partial, s));
+    if (linear_wgrad_tc_supported(T, 384, 128, 384, 128) && linear_wgrad_tc_partial_bytes(384) <= w.partial_bytes) {
+      TRY(linear_wgrad_tc(w.g384, 384, a.f, 128, T, 384, w.tmpw, w.tmpb, w.partial, s));
+    } else {
+      TRY(linear_wgrad(w.g384, 384, a.f, 128, T, 384, 128, w.tmpw, 1.f, w.partial, s));
+      TRY(colsum(w.g384, 384, T, 384, w.tmpb, w.partial, s));
+    }
     for (int j = 0; j < 3; ++j) {
       if (grd[sl.srb(i, S_LQW + 2 * j)]) TRY(d2d(grd[sl.srb(i, S_LQW + 2 * j)], w.tmpw + j * 128 * 128, 128 * 128 * 4, s));
       if (grd[sl.srb(i, S_LQB + 2 * j)]) TRY(d2d(grd[sl.srb(i, S_LQB + 2 * j)], w.tmpb + j * 128, 128 * 4, s));

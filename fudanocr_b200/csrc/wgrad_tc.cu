@@ -1,0 +1,291 @@
+// Weight + bias gradient of nn.Linear on the 5th-generation tensor cores:
+//     dW[n][k] = sum_t dY[t][n] X[t][k]   (K = 128),      db[n] = sum_t dY[t][n]
+// (autograd of the FeatureEnhancer linears, scene-text-telescope/model/tbsrn.py:74,103,158-159).
+//
+// The reduction runs over the token axis (T = B*1024), the outputs are tiny, so this is a streaming kernel that
+// must read dY and X exactly once at HBM speed.  Both operands are consumed AS STORED: a [64 tokens][64 columns]
+// TMA box with the 128-byte swizzle is, read MN-major, a 64-wide slice of dY^T (A operand, M = output features) or
+// of X^T (B operand, N = input features) with the tokens as the MMA K dimension - no transposes, no register
+// staging.  M = 128 / N = 128 operands span two such atoms (LBO = atom stride); the descriptor semantics are pinned
+// by tests/test_gpu_umma_layouts.py.  The bias gradient rides along as one more MMA per step against a constant
+// all-ones B operand (N = 16), so dY is not read a second time.
+//
+// One persistent CTA per SM owns a contiguous range of 64-token tiles:
+//   warp 0: TMA producer (ring of stages, each = N/64 dY atoms + 2 X atoms)      warp 1: MMA issuer
+//   warp 2: TMEM allocator (512 columns: up to 3 x [128 x 128] fp32 + 3 x [128 x 16])
+//   warps 4-7: epilogue - after the last tile, TMEM -> one fp32 partial per CTA.  Second stage in the same launch: grid
+//              barrier, then each CTA sums the <= 148 partials of its slice of dW / db in a fixed order (no atomics on
+//              data: run-to-run reproducible)
+#include "kernels.cuh"
+
+#define TRY_RC(expr)          \
+  do {                        \
+    int _rc = (expr);         \
+    if (_rc != 0) return _rc; \
+  } while (0)
+
+namespace {
+
+constexpr int kTokTile = 64;
+constexpr int kAtomBytes = kTokTile * 128;  // [64 tokens][64 bf16], 128-byte swizzled
+constexpr int kSmemRing = 192 * 1024;
+constexpr int kOnesBytes = 8192;
+constexpr int kThreads = 256;
+constexpr int kBiasCol0 = 384;  // TMEM column of the first bias accumulator
+constexpr int kMaxStages = 8;
+
+__global__ void __launch_bounds__(kThreads, 1)
+linear_wgrad_tc_kernel(const __grid_constant__ CUtensorMap mY, const __grid_constant__ CUtensorMap mX, int n_atoms,
+                       int tiles_total, int stages, float* __restrict__ partial_w, float* __restrict__ partial_b,
+                       float* __restrict__ dw, float* __restrict__ db, unsigned int* __restrict__ sync_ctr, int dbg) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* ones = smem + kSmemRing;
+  uint64_t* full = reinterpret_cast<uint64_t*>(ones + kOnesBytes);
+  uint64_t* empty = full + kMaxStages;
+  uint64_t* done = empty + kMaxStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int N = n_atoms * 64;
+  const int m_blocks = n_atoms >= 2 ? n_atoms / 2 : 1;
+  const int M = n_atoms >= 2 ? 128 : 64;
+  const int stage_bytes = (n_atoms + 2) * kAtomBytes;
+  const int t_begin = (int)((long)tiles_total * blockIdx.x / gridDim.x);
+  const int t_end = (int)((long)tiles_total * (blockIdx.x + 1) / gridDim.x);
+
+  for (int i = threadIdx.x; i < kOnesBytes / 4; i += kThreads) reinterpret_cast<uint32_t*>(ones)[i] = 0x3F803F80u;  // bf16 1.0 x2
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mY);
+    tma_prefetch_desc(&mX);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  fence_proxy_async();  // the ones tile is read by the tensor core (async proxy)
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = t_begin; tile < t_end; ++tile) {
+        mbar_wait_parked(&empty[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&full[stage], (uint32_t)stage_bytes);
+        uint8_t* sy = smem + stage * stage_bytes;
+        uint8_t* sx = sy + n_atoms * kAtomBytes;
+        for (int a = 0; a < n_atoms; ++a) tma_load_2d(sy + a * kAtomBytes, &mY, &full[stage], a * 64, tile * kTokTile);
+        for (int a = 0; a < 2; ++a) tma_load_2d(sx + a * kAtomBytes, &mX, &full[stage], a * 64, tile * kTokTile);
+        if (++stage == stages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_w = umma_idesc_bf16_ex(M, 128, 1, 1);
+      const uint32_t idesc_b = umma_idesc_bf16_ex(M, 16, 1, 1);
+      const uint64_t d_ones = umma_desc(smem_u32(ones), kAtomBytes, 1024, 2);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = t_begin; tile < t_end; ++tile) {
+        mbar_wait_parked(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t sy = smem_u32(smem + stage * stage_bytes);
+        const uint32_t sx = sy + n_atoms * kAtomBytes;
+        const uint64_t db = umma_desc(sx, kAtomBytes, 1024, 2);
+        for (int mb = 0; mb < m_blocks; ++mb) {
+          // M = 128 spans two atoms along M (LBO = atom stride); a single atom uses the pinned LBO = 16
+          const uint64_t da = umma_desc(sy + mb * 2 * kAtomBytes, M == 128 ? kAtomBytes : 16, 1024, 2);
+#pragma unroll
+          for (int ks = 0; ks < kTokTile / 16; ++ks) {
+            const uint32_t acc = (tile > t_begin || ks > 0) ? 1u : 0u;
+            // 16 tokens = 16 rows of 128 bytes = 128 sixteen-byte units along the MMA K dimension
+            if (!(dbg & 1)) tc_mma_bf16(tmem_base + mb * 128, da + 128 * ks, db + 128 * ks, idesc_w, acc);
+            if (!(dbg & 2)) tc_mma_bf16(tmem_base + kBiasCol0 + mb * 16, da + 128 * ks, d_ones, idesc_b, acc);
+          }
+        }
+        tc_commit(&empty[stage]);
+        if (++stage == stages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      tc_commit(done);
+    }
+  } else if (warp >= 4) {
+    const int ew = warp & 3;
+    mbar_wait_parked(done, 0);
+    tc_fence_after();
+    const bool has_work = t_end > t_begin;
+    // M = 128: TMEM lane = row; M = 64: row r sits on lane (r % 16) + 32 (r / 16)
+    const int row_in_block = M == 128 ? ew * 32 + lane : ew * 16 + lane;
+    const bool valid = M == 128 || lane < 16;
+    for (int mb = 0; mb < m_blocks; ++mb) {
+      const int row = mb * 128 + row_in_block;
+      float* out = partial_w + ((long)blockIdx.x * N + row) * 128;
+      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + mb * 128;
+#pragma unroll 1
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(taddr + c0, r);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            float4 v = has_work ? make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
+                                              __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]))
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(out + c0 + 4 * q) = v;
+          }
+        }
+      }
+      uint32_t rb[16];
+      tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(ew * 32) << 16) + kBiasCol0 + mb * 16, rb);
+      tmem_ld_wait();
+      if (valid) partial_b[(long)blockIdx.x * N + row] = has_work ? __uint_as_float(rb[0]) : 0.f;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+  // ---- second stage inside the same launch: grid barrier (all CTAs are co-resident: grid <= #SMs, 1 CTA/SM), then every
+  // CTA sums the gridDim.x partials of its slice of the outputs in a fixed order (deterministic, no atomics on data) ----
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    atomicAdd(&sync_ctr[0], 1u);
+    while (*reinterpret_cast<volatile unsigned int*>(&sync_ctr[0]) < gridDim.x) __nanosleep(64);
+    __threadfence();
+  }
+  __syncthreads();
+  const int P = gridDim.x;
+  const long n_w4 = (long)N * 32;  // float4 outputs
+  if (dw != nullptr && !(dbg & 8)) {
+    // slice of this CTA: float4 outputs [o_begin, o_end); thread = (output o, partial quarter); each thread streams its
+    // quarter of the partials with 8 independent 16-byte loads in flight (bandwidth-, not latency-bound)
+    const long o_begin = n_w4 * blockIdx.x / gridDim.x, o_end = n_w4 * (blockIdx.x + 1) / gridDim.x;
+    const int col = threadIdx.x & 63, part = threadIdx.x >> 6;
+    float4* red = reinterpret_cast<float4*>(smem);
+    const float4* pw4 = reinterpret_cast<const float4*>(partial_w);
+    for (long base = o_begin; base < o_end; base += 64) {
+      const long o = base + col;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (o < o_end) {
+        const int p0 = P * part / 4, p1 = P * (part + 1) / 4;
+        int p = p0;
+        for (; p + 8 <= p1; p += 8) {
+          float4 v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = __ldcg(pw4 + (long)(p + j) * n_w4 + o);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            acc.x += v[j].x;
+            acc.y += v[j].y;
+            acc.z += v[j].z;
+            acc.w += v[j].w;
+          }
+        }
+        for (; p < p1; ++p) {
+          const float4 v = __ldcg(pw4 + (long)p * n_w4 + o);
+          acc.x += v.x;
+          acc.y += v.y;
+          acc.z += v.z;
+          acc.w += v.w;
+        }
+      }
+      red[part * 64 + col] = acc;
+      __syncthreads();
+      if (part == 0 && o < o_end) {
+        const float4 a0 = red[col], a1 = red[64 + col], a2 = red[128 + col], a3 = red[192 + col];
+        reinterpret_cast<float4*>(dw)[o] = make_float4((a0.x + a1.x) + (a2.x + a3.x), (a0.y + a1.y) + (a2.y + a3.y),
+                                                       (a0.z + a1.z) + (a2.z + a3.z), (a0.w + a1.w) + (a2.w + a3.w));
+      }
+      __syncthreads();
+    }
+  }
+  if (db != nullptr) {
+    for (int i = blockIdx.x * kThreads + threadIdx.x; i < N; i += gridDim.x * kThreads) {
+      float acc = 0.f;
+#pragma unroll 8
+      for (int p = 0; p < P; ++p) acc += __ldcg(partial_b + (long)p * N + i);
+      db[i] = acc;
+    }
+  }
+  // self-resetting counters: the last CTA to leave clears both for the next launch
+  if (threadIdx.x == 0) {
+    if (atomicAdd(&sync_ctr[1], 1u) == gridDim.x - 1) {
+      sync_ctr[0] = 0;
+      sync_ctr[1] = 0;
+      __threadfence();
+    }
+  }
+}
+
+__device__ unsigned int g_wgrad_sync[2] = {0u, 0u};
+
+int wg_num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+}  // namespace
+
+bool linear_wgrad_tc_supported(long T, int N, int K, long ld_dy, long ld_x) {
+  return K == 128 && (N == 64 || N == 128 || N == 256 || N == 384) && T % kTokTile == 0 && T >= kTokTile && ld_dy % 8 == 0 &&
+         ld_x % 8 == 0;
+}
+size_t linear_wgrad_tc_partial_bytes(int N) { return (size_t)wg_num_sms() * N * (128 + 1) * 4; }
+
+// dw fp32 [N][128], db fp32 [N] (either may be null); partial: linear_wgrad_tc_partial_bytes(N) bytes
+int linear_wgrad_tc(const bf16* dy, long ld_dy, const bf16* x, long ld_x, long T, int N, float* dw, float* db, float* partial,
+                    cudaStream_t s) {
+  ProfScope _ps("linear_wgrad", s);
+  FOCR_REQUIRE(linear_wgrad_tc_supported(T, N, 128, ld_dy, ld_x), "linear_wgrad_tc: T=%ld N=%d", T, N);
+  CUtensorMap mY, mX;
+  TRY_RC(focr_make_tmap_2d(&mY, dy, (unsigned long long)N, (unsigned long long)T, (unsigned long long)ld_dy * 2, 64, kTokTile, 128));
+  TRY_RC(focr_make_tmap_2d(&mX, x, 128ull, (unsigned long long)T, (unsigned long long)ld_x * 2, 64, kTokTile, 128));
+  const int n_atoms = N / 64;
+  const int tiles = (int)(T / kTokTile);
+  int stages = kSmemRing / ((n_atoms + 2) * kAtomBytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  const int grid = tiles < wg_num_sms() ? tiles : wg_num_sms();
+  const size_t smem = kSmemRing + kOnesBytes + 256 + 1024;
+  static bool attr = false;
+  if (!attr) {
+    FOCR_CHECK_CUDA(cudaFuncSetAttribute(linear_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  float* pw = partial;
+  float* pb = partial + (size_t)grid * N * 128;
+  unsigned int* ctr = nullptr;
+  FOCR_CHECK_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&ctr), g_wgrad_sync));
+  static int dbg = -1;
+  if (dbg < 0) dbg = getenv("FOCR_WGRAD_DEBUG") ? atoi(getenv("FOCR_WGRAD_DEBUG")) : 0;  // tuning aid: bit0 skip W MMAs, bit1 skip bias MMAs
+  if (dbg & 4) stages = 2;
+  linear_wgrad_tc_kernel<<<grid, kThreads, smem, s>>>(mY, mX, n_atoms, tiles, stages, pw, pb, dw, db, ctr, dbg);
+  FOCR_LAUNCH_CHECK();
+  return FOCR_OK;
+}

@@ -47,6 +47,10 @@ int focr_linear_dgrad(const void* dy, const float* w, void* dx, long M, int K, i
 int focr_linear_wgrad(const void* dy, const void* x, float* dw, long M, int K, int N, void* ws, size_t ws_bytes,
                       void* stream);
 int focr_bias_grad(const void* dy, float* db, long M, int N, void* ws, size_t ws_bytes, void* stream);
+/* dw [N][K] and db [N] (either may be NULL) in ONE pass over dy and x: tcgen05 MN-major operands straight from the stored
+ * layouts, bias gradient as an extra MMA against a ones operand (K == 128, N in {64,128,256,384}, M % 64 == 0) */
+int focr_linear_wgrad_bias(const void* dy, const void* x, float* dw, float* db, long M, int K, int N, void* ws,
+                           size_t ws_bytes, void* stream);
 
 /* --- nn.BatchNorm2d in train mode + activation: STT/model/tbsrn.py:233,238,191, stn_head.py:18-21 ----------
  * act: 0 none, 1 mish (tbsrn.py:277-285), 2 relu.  stats: fp32 [4][C] = mean, invstd, scale, shift. */

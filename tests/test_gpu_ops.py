@@ -200,6 +200,37 @@ def test_linear_wgrad_and_bias(M, K, N):
     assert _rel(db, dy.float().sum(0)) < 2e-3
 
 
+@pytest.mark.parametrize("M,N", [(64, 64), (192, 128), (4096, 384), (64 * 301, 128), (64 * 1000, 384), (64 * 149, 64),
+                                 (8192, 256)])
+def test_linear_wgrad_bias_fused_tcgen05(M, N):
+    """one pass over dY and X: tcgen05 MN-major operands + ones-operand bias gradient (csrc/wgrad_tc.cu); covers fewer tiles
+    than CTAs, ragged tile/CTA splits, M = 64 accumulators (N = 64) and 1-3 M blocks"""
+    L = _L()
+    K = 128
+    g = torch.Generator(device=DEV).manual_seed(M + N)
+    dy = _bf(torch.randn(M, N, device=DEV, generator=g))
+    x = _bf(torch.randn(M, K, device=DEV, generator=g) + 0.25)
+    ws = _ws(L.lib.focr_wgrad_workspace_bytes())
+    outs = []
+    for rep in range(2):
+        dw = torch.full((N, K), float("nan"), device=DEV)
+        db = torch.full((N,), float("nan"), device=DEV)
+        L.check(L.lib.focr_linear_wgrad_bias(dy.data_ptr(), x.data_ptr(), dw.data_ptr(), db.data_ptr(), M, K, N, ws.data_ptr(),
+                                             ws.numel(), L.cur_stream()))
+        _sync(L)
+        outs.append((dw, db))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])   # deterministic
+    ref_w, ref_b = dy.double().t() @ x.double(), dy.double().sum(0)
+    assert _rel(outs[0][0], ref_w) < 1e-4, _rel(outs[0][0], ref_w)
+    assert _rel(outs[0][1], ref_b) < 1e-4, _rel(outs[0][1], ref_b)
+    # weight-only / bias-only calls
+    dw = torch.empty(N, K, device=DEV)
+    L.check(L.lib.focr_linear_wgrad_bias(dy.data_ptr(), x.data_ptr(), dw.data_ptr(), 0, M, K, N, ws.data_ptr(), ws.numel(),
+                                         L.cur_stream()))
+    _sync(L)
+    assert torch.equal(dw, outs[0][0])
+
+
 @pytest.mark.parametrize("B,Co,shuf", [(2, 64, 0), (3, 128, 0), (2, 256, 1), (20, 64, 0)])
 def test_conv3x3_wgrad(B, Co, shuf):
     L = _L()

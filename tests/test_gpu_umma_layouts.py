@@ -134,3 +134,32 @@ def test_mn_major_a_m128_two_atoms():
     err = _rel(out[:, :32], ref)
     print("M=128 two-atom MN-major A err", err)
     assert err < 1e-5, err
+
+
+def test_mn_major_both_two_atoms_wgrad():
+    """the linear weight-gradient configuration (csrc/wgrad_tc.cu): A = dY tile [64 t][128 n] and B = X tile [64 t][128 k], each
+    held as two [64][64] 128B-swizzled atoms 8 KB apart and read MN-major (M = N = 128, LBO = atom stride), 4 K steps of 16
+    tokens; plus the bias trick: B = a region of bf16 ones read as an MN-major N = 16 operand"""
+    g = torch.Generator().manual_seed(5)
+    dy = torch.randn(64, 128, generator=g).to(torch.bfloat16)
+    x = torch.randn(64, 128, generator=g).to(torch.bfloat16)
+    img = np.zeros(16384 * 2 + 8192, np.uint8)
+    by, bx = _bf16_bits(dy), _bf16_bits(x)
+    _place(img, 0, by[:, :64].copy(), 128)
+    _place(img, 8192, by[:, 64:].copy(), 128)
+    _place(img, 16384, bx[:, :64].copy(), 128)
+    _place(img, 24576, bx[:, 64:].copy(), 128)
+    img[32768:].view(np.uint16)[:] = 0x3F80
+    ref = dy.float().t() @ x.float()
+    out = _run(img, _desc(0, 8192, 1024, 2), _desc(16384, 8192, 1024, 2), _idesc(128, 128, 1, 1), 4, 128, 128, 128)
+    err = _rel(out, ref)
+    print("wgrad M=N=128 two-atom MN-major err", err)
+    assert err < 1e-5, err
+    out = _run(img, _desc(0, 8192, 1024, 2), _desc(32768, 8192, 1024, 2), _idesc(128, 16, 1, 1), 4, 128, 0, 32)
+    errb = _rel(out[:, 0], dy.float().sum(0))
+    assert errb < 1e-5, errb
+    # N = 64 output features: a single atom, M = 64 (rows on lanes (r % 16) + 32 (r / 16))
+    rows = torch.tensor([(r % 16) + 32 * (r // 16) for r in range(64)])
+    out = _run(img, _desc(0, 16, 1024, 2), _desc(16384, 8192, 1024, 2), _idesc(64, 128, 1, 1), 4, 128, 128, 128)
+    err64 = _rel(out[rows], ref[:64])
+    assert err64 < 1e-5, err64
