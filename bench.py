@@ -232,20 +232,21 @@ def main():
         trainer.step(lr_d, hr_d, seed=it)
     torch.cuda.synchronize()
 
-    # ---- pass 1: per-kernel-family breakdown (all scopes) to find the dominant kernel -----------------------
-    L.lib.focr_prof_enable(1, b"")
+    # ---- pass 1: per-kernel-family breakdown (all scopes, eager launches) to find the dominant kernel --------
+    L.prof_enable(1, b"")
     trainer.step(lr_d, hr_d, seed=1000)
     breakdown = L.prof_collect()
-    L.lib.focr_prof_enable(0, b"")
+    L.prof_enable(0, b"")
     top = max(breakdown.items(), key=lambda kv: kv[1][1])[0] if breakdown else "attn_bwd_dkv"
 
-    # ---- timed region (device-resident inputs); only the dominant kernel carries event scopes ----------------
-    L.lib.focr_prof_enable(2, top.encode())
+    # ---- timed region (device-resident inputs).  The trainer replays the step as CUDA graphs; events inside a
+    # graph cannot be timed, so the dominant kernel's launch duration is taken in pass 3 below ------------------
+    trainer.step(lr_d, hr_d, seed=1001)  # (re)capture outside the timed region
     clocks = ClockSampler(local)
     barrier()
     if rank == 0:
         clocks.start()
-    n0 = L.lib.focr_launch_count()
+    n0 = trainer.kernel_launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for it in range(K):
@@ -253,11 +254,16 @@ def main():
     e1.record()
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
-    launches = int(L.lib.focr_launch_count() - n0)
+    launches = int(trainer.kernel_launches - n0)
     clk = clocks.stop() if rank == 0 else None
-    focus = L.prof_collect()
-    L.lib.focr_prof_enable(0, b"")
     loss_dev = float(trainer.loss.item())
+
+    # ---- pass 3: the same K steps launched eagerly with CUDA-event scopes around the dominant kernel only ------
+    L.prof_enable(2, top.encode())
+    for it in range(K):
+        trainer.step(lr_d, hr_d, seed=2500 + it)
+    focus = L.prof_collect()
+    L.prof_enable(0, b"")
 
     # ---- end to end: host (pinned) inputs -> H2D every step, loss read back every step -----------------------
     barrier()
@@ -296,6 +302,8 @@ def main():
         "share_of_step": (breakdown[top][1] / step_ms_profiled) if top in breakdown and step_ms_profiled else None,
         "peak_source": peaks["source"] + (", sustained bf16 figure (kernel timed inside a long step)"
                                            if kind == "tensor" else ""),
+        "timing": "CUDA events on the launching stream around each launch of the kernel, K eager steps run right after "
+                  "the timed region (the timed region replays the step as CUDA graphs, whose events cannot be timed)",
         "breakdown_ms_per_step": {k: round(v[1], 4) for k, v in sorted(breakdown.items(), key=lambda kv: -kv[1][1])},
     }
     out = {
@@ -305,7 +313,8 @@ def main():
         "config": {"workload": "TBSRN train step (STN on, dropout 0.1, MSE loss x100, clip 0.25, Adam 1e-4), "
                                "LR 16x64 -> HR 32x128, batch 256 per GPU (BASELINE configs[1])",
                    "global_batch": world * B, "parallelism": f"dp{world}",
-                   "l2": "per-step working set (~6 GB of saved activations) >> 126 MB L2; no explicit flush"},
+                   "l2": "per-step working set (~6 GB of saved activations) >> 126 MB L2; no explicit flush",
+                   "launch": "step replayed as 2 CUDA graphs (fwd+loss+bwd | clip+Adam), dropout seed read on device"},
         "e2e": {"value": world * B * K / (ms_e2e * 1e-3), "unit": "images/s",
                 "h2d_bytes_per_step": int(lr_h.numel() * 4 + hr_h.numel() * 4), "d2h_bytes_per_step": 4},
         "gpu_launches": launches, "launches_per_step": launches / max(K, 1),

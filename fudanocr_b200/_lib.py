@@ -61,6 +61,7 @@ _SIGS = {
     "focr_tbsrn_slot_name": (C.c_char_p, [_i, _i]),
     "focr_tbsrn_workspace_bytes": (_sz, [_i, _i]),
     "focr_tbsrn_forward": (C.c_int, [_pp, _fp, _fp, _i, _i, _i, _f, _u, _vp, _sz, _vp]),
+    "focr_tbsrn_forward_devseed": (C.c_int, [_pp, _fp, _fp, _i, _i, _i, _f, _vp, _vp, _sz, _vp]),
     "focr_tbsrn_backward": (C.c_int, [_pp, _pp, _fp, _fp, _i, _i, _i, _f, _u, _vp, _sz, _vp]),
     "focr_crnn_num_slots": (C.c_int, []),
     "focr_crnn_workspace_bytes": (_sz, [_i]),
@@ -112,6 +113,20 @@ def ptr(t) -> int:
 def cur_stream() -> int:
     import torch
     return torch.cuda.current_stream().cuda_stream
+
+
+_PROF_ON = False
+
+
+def prof_enable(mode: int, focus: bytes = b"") -> None:
+    """event scopes on the launching stream (bench.py); while on, the trainer keeps the eager (non-graph) path"""
+    global _PROF_ON
+    _PROF_ON = mode != 0
+    lib.focr_prof_enable(mode, focus)
+
+
+def prof_enabled() -> bool:
+    return _PROF_ON
 
 
 def prof_collect() -> dict:

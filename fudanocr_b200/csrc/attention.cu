@@ -177,8 +177,10 @@ struct FwdCfg {
 template <int DROP, int NWG>
 __global__ void __launch_bounds__(FwdCfg<NWG>::kThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap mQkv, bf16* __restrict__ out, float* __restrict__ lse2, uint32_t key,
-                uint32_t th7, float inv_keep, uint32_t* __restrict__ drop_bits) {
+                uint32_t th7, float inv_keep, uint32_t* __restrict__ drop_bits, const uint32_t* __restrict__ seed_dev) {
   using Cfg = FwdCfg<NWG>;
+  // device-resident seed (CUDA-graph replay): drop_key(seed, stream) = seed ^ f(stream), `key` then carries f(stream)
+  if (DROP != 0 && seed_dev != nullptr) key ^= __ldg(seed_dev);
   constexpr int SB = Cfg::kSB;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -811,7 +813,7 @@ size_t attn_drop_bits_bytes(int B) { return (size_t)B * 4 * (kS / 32) * kS * siz
 
 template <int NWG>
 int launch_fwd(const CUtensorMap& mq, bf16* out, float* lse2, int B, uint32_t key, uint32_t thresh16, uint32_t* drop_bits,
-               cudaStream_t s) {
+               const uint32_t* seed_dev, cudaStream_t s) {
   using Cfg = FwdCfg<NWG>;
   static bool init = false;
   if (!init) {
@@ -826,17 +828,17 @@ int launch_fwd(const CUtensorMap& mq, bf16* out, float* lse2, int B, uint32_t ke
   const AttnDrop d = drop_params(thresh16);
   const dim3 grid(B * 4), block(Cfg::kThreads);
   if (!thresh16)
-    attn_fwd_kernel<0, NWG><<<grid, block, Cfg::kSmem, s>>>(mq, out, lse2, key, 0, 1.f, nullptr);
+    attn_fwd_kernel<0, NWG><<<grid, block, Cfg::kSmem, s>>>(mq, out, lse2, key, 0, 1.f, nullptr, nullptr);
   else if (!drop_bits)
-    attn_fwd_kernel<1, NWG><<<grid, block, Cfg::kSmem, s>>>(mq, out, lse2, key, d.th7, d.inv_keep, nullptr);
+    attn_fwd_kernel<1, NWG><<<grid, block, Cfg::kSmem, s>>>(mq, out, lse2, key, d.th7, d.inv_keep, nullptr, seed_dev);
   else
-    attn_fwd_kernel<2, NWG><<<grid, block, Cfg::kSmem, s>>>(mq, out, lse2, key, d.th7, d.inv_keep, drop_bits);
+    attn_fwd_kernel<2, NWG><<<grid, block, Cfg::kSmem, s>>>(mq, out, lse2, key, d.th7, d.inv_keep, drop_bits, seed_dev);
   FOCR_LAUNCH_CHECK();
   return FOCR_OK;
 }
 
 int attn_forward(const bf16* qkv, bf16* out, float* lse2, int B, uint32_t key, uint32_t thresh16, uint32_t* drop_bits,
-                 cudaStream_t s) {
+                 cudaStream_t s, const uint32_t* seed_dev) {
   ProfScope _ps("attn_fwd", s);
   FOCR_REQUIRE(B >= 1 && B <= 1024, "attention: B=%d out of range", B);
   static_assert(sizeof(Bars) <= 1024, "barrier block");
@@ -849,9 +851,9 @@ int attn_forward(const bf16* qkv, bf16* out, float* lse2, int B, uint32_t key, u
     nwg = e ? atoi(e) : 4;
     if (nwg < 2 || nwg > 4) nwg = 4;
   }
-  if (nwg == 2) return launch_fwd<2>(mq, out, lse2, B, key, thresh16, drop_bits, s);
-  if (nwg == 3) return launch_fwd<3>(mq, out, lse2, B, key, thresh16, drop_bits, s);
-  return launch_fwd<4>(mq, out, lse2, B, key, thresh16, drop_bits, s);
+  if (nwg == 2) return launch_fwd<2>(mq, out, lse2, B, key, thresh16, drop_bits, seed_dev, s);
+  if (nwg == 3) return launch_fwd<3>(mq, out, lse2, B, key, thresh16, drop_bits, seed_dev, s);
+  return launch_fwd<4>(mq, out, lse2, B, key, thresh16, drop_bits, seed_dev, s);
 }
 
 template <int NWG>

@@ -301,7 +301,8 @@ size_t focr_tsrn_workspace_bytes(int B, int srb_nums) { return ws_bytes_impl(B, 
 static void* align256(void* p) { return (void*)(((uintptr_t)p + 255) & ~(uintptr_t)255); }
 
 static int forward_impl(int arch, void* const* params, const float* x_lr, float* sr, int B, int srb_nums, int flags,
-                        float p_drop, unsigned seed, void* ws, size_t ws_bytes, void* stream) {
+                        float p_drop, unsigned seed, void* ws, size_t ws_bytes, void* stream,
+                        const unsigned* seed_dev = nullptr) {
   FOCR_REQUIRE(B >= 1 && srb_nums >= 0 && srb_nums <= 16, "forward: B=%d srb_nums=%d", B, srb_nums);
   FOCR_REQUIRE(!((flags & 1) && (flags & 2)) || B >= 2, "forward: train mode with STN needs B >= 2 (BatchNorm1d)");
   tbsrn::Ws w;
@@ -309,7 +310,7 @@ static int forward_impl(int arch, void* const* params, const float* x_lr, float*
   FOCR_REQUIRE(ws_bytes >= w.total_bytes + 256, "forward: workspace too small (%zu < %zu)", ws_bytes,
                w.total_bytes + 256);
   tbsrn::Slots sl(srb_nums, arch);
-  return tbsrn::forward(sl, params, x_lr, sr, w, flags & 1, (flags >> 1) & 1, p_drop, seed, (cudaStream_t)stream);
+  return tbsrn::forward(sl, params, x_lr, sr, w, flags & 1, (flags >> 1) & 1, p_drop, seed, (cudaStream_t)stream, seed_dev);
 }
 static int backward_impl(int arch, void* const* params, void* const* grads, const float* x_lr, const float* d_sr, int B,
                          int srb_nums, int flags, float p_drop, unsigned seed, void* ws, size_t ws_bytes, void* stream) {
@@ -324,6 +325,13 @@ static int backward_impl(int arch, void* const* params, void* const* grads, cons
 int focr_tbsrn_forward(void* const* params, const float* x_lr, float* sr, int B, int srb_nums, int flags, float p_drop,
                        unsigned seed, void* ws, size_t ws_bytes, void* stream) {
   return forward_impl(tbsrn::ARCH_TBSRN, params, x_lr, sr, B, srb_nums, flags, p_drop, seed, ws, ws_bytes, stream);
+}
+// same as focr_tbsrn_forward with the dropout seed read ON THE DEVICE from *seed_dev when the kernels run: a CUDA graph
+// captured around the step can be replayed with a fresh seed per step (masks are identical to passing that seed by value)
+int focr_tbsrn_forward_devseed(void* const* params, const float* x_lr, float* sr, int B, int srb_nums, int flags,
+                               float p_drop, const unsigned* seed_dev, void* ws, size_t ws_bytes, void* stream) {
+  FOCR_REQUIRE(seed_dev != nullptr, "tbsrn_forward_devseed: seed_dev is NULL");
+  return forward_impl(tbsrn::ARCH_TBSRN, params, x_lr, sr, B, srb_nums, flags, p_drop, 0, ws, ws_bytes, stream, seed_dev);
 }
 int focr_tbsrn_backward(void* const* params, void* const* grads, const float* x_lr, const float* d_sr, int B,
                         int srb_nums, int flags, float p_drop, unsigned seed, void* ws, size_t ws_bytes, void* stream) {

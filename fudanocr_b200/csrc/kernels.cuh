@@ -43,8 +43,10 @@ int pe_table(bf16* pe, cudaStream_t s);
 
 // attention.cu
 size_t attn_drop_bits_bytes(int B);
+// seed_dev (optional): device word XOR-ed into `key` inside the kernel, so a captured CUDA graph can be replayed with a
+// fresh dropout seed per step (key = drop_key(0, stream) in that case)
 int attn_forward(const bf16* qkv, bf16* out, float* lse2, int B, uint32_t key, uint32_t thresh16, uint32_t* drop_bits,
-                 cudaStream_t s);
+                 cudaStream_t s, const uint32_t* seed_dev = nullptr);
 int attn_backward(const bf16* qkv, const bf16* o, const bf16* d_o, const float* lse2, float* dsum, bf16* dqkv, int B,
                   uint32_t key, uint32_t thresh16, const uint32_t* drop_bits, cudaStream_t s);
 

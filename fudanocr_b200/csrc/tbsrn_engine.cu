@@ -562,7 +562,8 @@ int tsrn_srb_backward(const Slots& sl, void* const* prm, void* const* grd, int i
 // forward
 // ---------------------------------------------------------------------------------------------
 int forward(const Slots& sl, void* const* prm, const float* x_lr, float* sr_out, Ws& w, bool training, bool stn,
-            float p_drop, uint32_t seed, cudaStream_t s) {
+            float p_drop, uint32_t seed, cudaStream_t s, const uint32_t* seed_dev) {
+  if (seed_dev != nullptr) seed = 0;  // the kernels XOR the device word into drop_key(0, stream)
   const int B = w.B, n = sl.srb_nums;
   const long T = w.T;
   const bool use_stn = stn && training;  // tbsrn.py:215
@@ -610,7 +611,7 @@ int forward(const Slots& sl, void* const* prm, const float* x_lr, float* sr_out,
     p.bias = q.bqkv;
     p.out = a.qkv;
     TRY(tok_gemm(a.f, 128, T, q.qkv, 384, p, s));
-    TRY(attn_forward(a.qkv, a.o, a.lse, B, drop_key(seed, 2 * i), th, a.dropbits, s));
+    TRY(attn_forward(a.qkv, a.o, a.lse, B, drop_key(seed, 2 * i), th, a.dropbits, s, seed_dev));
     p = gp();
     p.bias = P<float>(prm, sl.srb(i, S_LOB));
     p.out = a.y1pre;
@@ -624,6 +625,7 @@ int forward(const Slots& sl, void* const* prm, const float* x_lr, float* sr_out,
     p.drop_thresh16 = th;
     p.drop_scale = keep_scale;
     p.drop_key = drop_key(seed, 2 * i + 1);
+    p.drop_seed_dev = seed_dev;
     TRY(tok_gemm(a.y1, 128, T, q.w1, 128, p, s));
     p = gp();
     p.bias = P<float>(prm, sl.srb(i, S_W2B));

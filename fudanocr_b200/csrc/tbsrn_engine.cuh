@@ -139,7 +139,7 @@ struct Ws {
 void layout(Ws& w, int B, int srb_nums, void* base, int arch = ARCH_TBSRN);
 
 int forward(const Slots& sl, void* const* prm, const float* x_lr, float* sr_out, Ws& w, bool training, bool stn,
-            float p_drop, uint32_t seed, cudaStream_t s);
+            float p_drop, uint32_t seed, cudaStream_t s, const uint32_t* seed_dev = nullptr);
 int backward(const Slots& sl, void* const* prm, void* const* grd, const float* x_lr, const float* d_sr, Ws& w,
              bool stn, float p_drop, uint32_t seed, cudaStream_t s);
 

@@ -169,6 +169,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
       }
     }
   } else if (warp >= 4) {
+    const uint32_t dkey = p.drop_key ^ ((p.drop_thresh16 != 0 && p.drop_seed_dev != nullptr) ? __ldg(p.drop_seed_dev) : 0u);
     const int ew = warp & 3;        // TMEM lane quarter this warp may access (warp % 4)
     const int egrp = (warp - 4) >> 2;  // epilogue group 0 / 1: interleaved 32-column chunks
     const int row = ew * 32 + lane;
@@ -221,7 +222,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
             const uint32_t c0h = (uint32_t)((mg * p.ldc + n0) >> 1);
 #pragma unroll
             for (int q = 0; q < 16; ++q) {
-              const uint32_t hsh = drop_hash32(p.drop_key, c0h + q);
+              const uint32_t hsh = drop_hash32(dkey, c0h + q);
               v[2 * q] = (hsh & 0xFFFFu) >= p.drop_thresh16 ? v[2 * q] * p.drop_scale : 0.f;
               v[2 * q + 1] = (hsh >> 16) >= p.drop_thresh16 ? v[2 * q + 1] * p.drop_scale : 0.f;
             }
@@ -314,7 +315,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
           const uint32_t c0h = (uint32_t)((mg * p.ldc + n0) >> 1);
 #pragma unroll
           for (int q = 0; q < 16; ++q) {
-            const uint32_t hsh = drop_hash32(p.drop_key, c0h + q);
+            const uint32_t hsh = drop_hash32(dkey, c0h + q);
             v[2 * q] = (hsh & 0xFFFFu) >= p.drop_thresh16 ? v[2 * q] * p.drop_scale : 0.f;
             v[2 * q + 1] = (hsh >> 16) >= p.drop_thresh16 ? v[2 * q + 1] * p.drop_scale : 0.f;
           }

@@ -36,6 +36,7 @@ struct TcGemmParams {
   uint32_t drop_thresh16;
   float drop_scale;      // 1/(1-p)
   uint32_t drop_key;     // drop_key(seed, stream)
+  const uint32_t* drop_seed_dev;  // optional device word XOR-ed into drop_key in the kernel (CUDA-graph replay)
   // backward gate: v = gate[m][n] > 0 ? v * gate_scale : 0  (relu'(.) * dropout mask, read from the
   // stored post-dropout activation).  With a residual as well the order is (acc + residual) then gate.
   const bf16* gate;

@@ -214,8 +214,11 @@ linear_wgrad_tc_kernel(const __grid_constant__ CUtensorMap mY, const __grid_cons
       __syncthreads();
       if (part == 0 && o < o_end) {
         const float4 a0 = red[col], a1 = red[64 + col], a2 = red[128 + col], a3 = red[192 + col];
-        reinterpret_cast<float4*>(dw)[o] = make_float4((a0.x + a1.x) + (a2.x + a3.x), (a0.y + a1.y) + (a2.y + a3.y),
-                                                       (a0.z + a1.z) + (a2.z + a3.z), (a0.w + a1.w) + (a2.w + a3.w));
+        float* d = dw + 4 * o;  // the caller's gradient tensor is only guaranteed 4-byte aligned
+        d[0] = (a0.x + a1.x) + (a2.x + a3.x);
+        d[1] = (a0.y + a1.y) + (a2.y + a3.y);
+        d[2] = (a0.z + a1.z) + (a2.z + a3.z);
+        d[3] = (a0.w + a1.w) + (a2.w + a3.w);
       }
       __syncthreads();
     }
@@ -280,8 +283,8 @@ int linear_wgrad_tc(const bf16* dy, long ld_dy, const bf16* x, long ld_x, long T
   }
   float* pw = partial;
   float* pb = partial + (size_t)grid * N * 128;
-  unsigned int* ctr = nullptr;
-  FOCR_CHECK_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&ctr), g_wgrad_sync));
+  static unsigned int* ctr = nullptr;  // resolved once (outside any stream capture: the first step runs eagerly)
+  if (ctr == nullptr) FOCR_CHECK_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&ctr), g_wgrad_sync));
   static int dbg = -1;
   if (dbg < 0) dbg = getenv("FOCR_WGRAD_DEBUG") ? atoi(getenv("FOCR_WGRAD_DEBUG")) : 0;  // tuning aid: bit0 skip W MMAs, bit1 skip bias MMAs
   if (dbg & 4) stages = 2;

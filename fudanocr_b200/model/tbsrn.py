@@ -209,10 +209,13 @@ class _SREngineModule(nn.Module):
             return L.lib.focr_tsrn_workspace_bytes(B, self.srb_nums)
         return L.lib.focr_tbsrn_workspace_bytes(B, self.srb_nums)
 
-    def _c_forward(self, table, x, sr, B, flags, p, seed, ws):
+    def _c_forward(self, table, x, sr, B, flags, p, seed, ws, seed_dev=None):
         if self._ARCH == "tsrn":
             return L.lib.focr_tsrn_forward(table, x.data_ptr(), sr.data_ptr(), B, self.srb_nums, flags, ws.data_ptr(),
                                            ws.numel(), L.cur_stream())
+        if seed_dev is not None:   # seed read on the device at run time (CUDA-graph replay)
+            return L.lib.focr_tbsrn_forward_devseed(table, x.data_ptr(), sr.data_ptr(), B, self.srb_nums, flags, p,
+                                                    seed_dev.data_ptr(), ws.data_ptr(), ws.numel(), L.cur_stream())
         return L.lib.focr_tbsrn_forward(table, x.data_ptr(), sr.data_ptr(), B, self.srb_nums, flags, p, seed,
                                         ws.data_ptr(), ws.numel(), L.cur_stream())
 

@@ -105,6 +105,11 @@ const char* focr_tbsrn_slot_name(int srb_nums, int idx);
 size_t focr_tbsrn_workspace_bytes(int B, int srb_nums);
 int focr_tbsrn_forward(void* const* params, const float* x_lr, float* sr, int B, int srb_nums, int flags, float p_drop,
                        unsigned seed, void* ws, size_t ws_bytes, void* stream);
+/* focr_tbsrn_forward with the dropout seed read on the device (*seed_dev, uint32) when the kernels run, so that a CUDA
+ * graph captured around the whole step can be replayed with a new seed each step; masks equal those of the by-value seed.
+ * The backward reads the stored keep bits / activations and needs no seed. */
+int focr_tbsrn_forward_devseed(void* const* params, const float* x_lr, float* sr, int B, int srb_nums, int flags,
+                               float p_drop, const unsigned* seed_dev, void* ws, size_t ws_bytes, void* stream);
 int focr_tbsrn_backward(void* const* params, void* const* grads, const float* x_lr, const float* d_sr, int B,
                         int srb_nums, int flags, float p_drop, unsigned seed, void* ws, size_t ws_bytes, void* stream);
 /* TSRN: STT/model/tsrn.py:18-74 (TSRN), :77-98 (RecurrentResidualBlock), :128-145 (GruBlock: conv1x1 + BiGRU(64,32));

@@ -54,10 +54,10 @@ def main():
     for it in range(max(args.warmup, 3)):
         trainer.step(lr, hr, seed=it, labels=labels)
     torch.cuda.synchronize()
-    L.lib.focr_prof_enable(1, b"")
+    L.prof_enable(1, b"")
     trainer.step(lr, hr, seed=99, labels=labels)
     breakdown = L.prof_collect()
-    L.lib.focr_prof_enable(0, b"")
+    L.prof_enable(0, b"")
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()

@@ -223,8 +223,8 @@ def test_linear_wgrad_bias_fused_tcgen05(M, N):
     ref_w, ref_b = dy.double().t() @ x.double(), dy.double().sum(0)
     assert _rel(outs[0][0], ref_w) < 1e-4, _rel(outs[0][0], ref_w)
     assert _rel(outs[0][1], ref_b) < 1e-4, _rel(outs[0][1], ref_b)
-    # weight-only / bias-only calls
-    dw = torch.empty(N, K, device=DEV)
+    # weight-only call into a gradient tensor that is only 4-byte aligned (autograd path: views of one flat buffer)
+    dw = torch.empty(N * K + 1, device=DEV)[1:].view(N, K)
     L.check(L.lib.focr_linear_wgrad_bias(dy.data_ptr(), x.data_ptr(), dw.data_ptr(), 0, M, K, N, ws.data_ptr(), ws.numel(),
                                          L.cur_stream()))
     _sync(L)

@@ -251,7 +251,9 @@ def test_reference_loop_and_fused_trainer_agree(env):
                     diffs[k] = (d, e_or)  # (the B=4 STN prologue amplifies 1-ulp differences of d_sr even more)
             REPORT["frontends_grad_mismatch"] = dict(sorted(diffs.items(), key=lambda kv: -kv[1][0])[:20])
             _dump()
-        assert abs(loss.item() - l2.item()) < 1e-6 + 1e-4 * abs(loss.item())
+        # step 0: same weights, so the two losses are the same number; step 1: after one Adam step (lr * sign(g) per element)
+        # of each front-end - sign flips of numerically-zero gradient elements move the second loss by a few 1e-4 relative
+        assert abs(loss.item() - l2.item()) < 1e-6 + (1e-5 if it == 0 else 5e-4) * abs(loss.item())
         assert abs(gn1.item() - tr.grad_norm.item()) < 1e-3 * gn1.item(), REPORT.get("frontends_grad_mismatch")
         if it == 0:
             assert not REPORT["frontends_grad_mismatch"], REPORT["frontends_grad_mismatch"]
@@ -335,3 +337,33 @@ def test_full_size_properties(env):
     _dump()
     assert losses[0] == losses[1], losses
     assert losses[0][-1] < losses[0][0]
+
+
+def test_graph_replay_is_bit_identical_to_eager(env):
+    """the trainer replays the step as CUDA graphs (device-resident dropout seed, static input buffers): five steps with
+    dropout ON and changing batches must reproduce the eager launches bit for bit - losses, weights, launch count"""
+    from fudanocr_b200.trainer import TBSRNTrainer
+    B = 8
+
+    def run(use_graph):
+        torch.manual_seed(1234)
+        m = _model(env, stn=True)
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.Dropout):
+                mod.p = 0.1
+        tr = TBSRNTrainer(m, use_graph=use_graph)
+        g = torch.Generator(device=DEV).manual_seed(5)
+        losses = []
+        for i in range(5):
+            lr = torch.rand(B, 3, 16, 64, device=DEV, generator=g)
+            hr = torch.rand(B, 3, 32, 128, device=DEV, generator=g)
+            losses.append(tr.step(lr, hr, seed=1000 + i).clone())
+        torch.cuda.synchronize()
+        return torch.cat(losses), tr.flat_p.clone(), tr.kernel_launches, tr._graphs is not None
+
+    l0, p0, n0, g0 = run(False)
+    l1, p1, n1, g1 = run(True)
+    assert g1 and not g0
+    assert torch.equal(l0, l1), (l0, l1)
+    assert torch.equal(p0, p1)
+    assert n0 == n1 and n0 > 0
