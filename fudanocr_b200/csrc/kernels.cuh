@@ -51,8 +51,8 @@ int attn_backward(const bf16* qkv, const bf16* o, const bf16* d_o, const float* 
                   uint32_t key, uint32_t thresh16, const uint32_t* drop_bits, cudaStream_t s);
 
 // wgrad.cu
-int linear_wgrad_splits(long T, int N);
-size_t linear_wgrad_partial_bytes(long T, int N);
+int linear_wgrad_splits(long T, int N, int K = 128);
+size_t linear_wgrad_partial_bytes(long T, int N, int K = 128);
 int linear_wgrad(const bf16* dy, long ld_dy, const bf16* x, long ld_x, long T, int N, int K, float* dw, float scale,
                  float* partial, cudaStream_t s);
 size_t conv9x1_wgrad_partial_bytes(int B, int H, int W);

@@ -24,13 +24,22 @@ constexpr int kCdBlk = kTileM * 128;  // one 128-row x 64-column bf16 block, 128
 // One persistent CTA per SM.  Shared memory: K-block ring (A+B per stage), a double-buffered output tile
 // that the epilogue fills and a TMA store drains, and one auxiliary input tile (residual or gate) that the
 // producer prefetches with TMA, so the epilogue warps never touch global memory.
+// Resident-weights mode (BLOCK_N = 64, one N block, <= 9 K blocks: every 64->64 conv and the 128->64 linear): the whole
+// weight operand (<= 72 KB) is loaded into shared memory ONCE per CTA and the ring carries A tiles only.  The kernel is
+// bound by the L2 -> shared-memory fill rate (a 128-pixel tile needs 9 x 16 KB of shifted A views), so not re-fetching
+// 9 x 8 KB of weights per tile removes a third of that traffic.
+constexpr int kResMaxKb = 9;
 template <int BLOCK_N>
 struct TcCfg {
   static constexpr int kBBytes = BLOCK_N * 128;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = BLOCK_N == 128 ? 3 : 6;
+  static constexpr int kResBytes = kResMaxKb * kBBytes;         // resident weights (BLOCK_N == 64 only)
+  static constexpr int kResStages = 5;                           // A-only ring behind the resident weights
   static constexpr int kCdBytes = (BLOCK_N / 64) * kCdBlk;  // per buffer
-  static constexpr int kOffCd = kStages * kStageBytes;
+  static constexpr int kRingBytes = kStages * kStageBytes;
+  static constexpr int kResRingBytes = kResBytes + kResStages * kABytes;
+  static constexpr int kOffCd = (BLOCK_N == 64 && kResRingBytes > kRingBytes) ? kResRingBytes : kRingBytes;
   static constexpr int kOffAux = kOffCd + 2 * kCdBytes;
   static constexpr int kOffBar = kOffAux + 2 * kCdBytes;  // aux tile double-buffered like the output tile
   static constexpr int kTmemCols = 2 * BLOCK_N;  // 2 accumulator stages
@@ -56,7 +65,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
   uint64_t* tempty = tfull + 2;
   uint64_t* afull = tempty + 2;   // [2] auxiliary (residual / gate) tile landed
   uint64_t* aempty = afull + 2;   // [2] ... and has been consumed by the 4 epilogue warps
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty + 2);
+  uint64_t* bfull = aempty + 2;   // resident weights landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bfull + 1);
+  const bool resident = BLOCK_N == 64 && p.b_resident != 0;
+  uint8_t* ring = smem + (resident ? Cfg::kResBytes : 0);
+  const int stage_bytes = resident ? kABytes : Cfg::kStageBytes;
+  const int n_stages = resident ? Cfg::kResStages : Cfg::kStages;
   uint8_t* cd_base = smem + Cfg::kOffCd;
   uint8_t* aux_base = smem + Cfg::kOffAux;
   const bool use_aux = p.tma_out && (p.residual != nullptr || p.gate != nullptr);
@@ -85,6 +99,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
       mbar_init(&afull[a], 1);
       mbar_init(&aempty[a], kEpiThreads / 32);
     }
+    mbar_init(bfull, 1);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -103,6 +118,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
       uint32_t phase = 0;
       int ait = 0;
       const int hw = p.H * p.W;
+      if (resident) {  // the whole weight operand, once
+        mbar_arrive_expect_tx(bfull, (uint32_t)(nk * Cfg::kBBytes));
+        for (int kb = 0; kb < nk; ++kb)
+          tma_load_2d(smem + kb * Cfg::kBBytes, &mB, bfull, (kb % p.chunks) * kChunkK, (kb / p.chunks) * p.n_total);
+      }
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int m = tile / p.n_blocks, nb = tile % p.n_blocks;
         const int p0 = m * kTileM;
@@ -120,14 +140,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
           const int dy = tap / p.kw - pad_h, dx = tap % p.kw - pad_w;
           for (int ch = 0; ch < p.chunks; ++ch) {
             mbar_wait(&empty[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
-            uint8_t* sa = smem + stage * Cfg::kStageBytes;
+            mbar_arrive_expect_tx(&full[stage], (uint32_t)stage_bytes);
+            uint8_t* sa = ring + stage * stage_bytes;
             const int mi = ch / p.chunks_per_map;
             const int c0 = (ch - mi * p.chunks_per_map) * kChunkK;
             tma_load_4d(sa, amaps[mi], &full[stage], c0, dx, h0 + dy, b);
-            tma_load_2d(sa + kABytes, &mB, &full[stage], ch * kChunkK,
-                        tap * p.n_total + nb * BLOCK_N);
-            if (++stage == Cfg::kStages) {
+            if (!resident)
+              tma_load_2d(sa + kABytes, &mB, &full[stage], ch * kChunkK, tap * p.n_total + nb * BLOCK_N);
+            if (++stage == n_stages) {
               stage = 0;
               phase ^= 1;
             }
@@ -142,6 +162,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
       uint32_t phase = 0;
       int acc = 0;
       uint32_t aphase = 0;
+      if (resident) {
+        mbar_wait(bfull, 0);
+        tc_fence_after();
+      }
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         mbar_wait(&tempty[acc], aphase ^ 1);
         tc_fence_after();
@@ -149,16 +173,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
         for (int kb = 0; kb < nk; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t sa = smem_u32(ring + stage * stage_bytes);
           const uint64_t da = umma_desc_k_sw128(sa);
-          const uint64_t db = umma_desc_k_sw128(sa + kABytes);
+          const uint64_t db = umma_desc_k_sw128(resident ? smem_u32(smem + kb * Cfg::kBBytes) : sa + kABytes);
 #pragma unroll
           for (int k = 0; k < kChunkK / 16; ++k) {
             // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in 16-byte units
             tc_mma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
           }
           tc_commit(&empty[stage]);
-          if (++stage == Cfg::kStages) {
+          if (++stage == n_stages) {
             stage = 0;
             phase ^= 1;
           }
@@ -571,6 +595,12 @@ int tc_gemm_launch(const bf16* const* a_ptrs, int n_amaps, long a_pix_stride, lo
     cuuint32_t box[2] = {64, (cuuint32_t)block_n};
     int rc = make_map(&bm, w, 2, dims, str, box);
     if (rc) return rc;
+  }
+  {
+    static int no_res = -1;
+    if (no_res < 0) no_res = getenv("FOCR_TC_NO_RESIDENT") ? 1 : 0;  // tuning knob
+    p.b_resident = (!no_res && block_n == 64 && p.n_blocks == 1 && p.kh * p.kw * p.chunks <= kResMaxKb &&
+                    p.m_tiles >= 2 * num_sms()) ? 1 : 0;
   }
   // output / auxiliary tiles through TMA for the plain bf16 epilogue (every hot GEMM); the rare epilogues
   // (fp32 output, PixelShuffle scatter, PReLU with saved pre-activation) keep direct stores

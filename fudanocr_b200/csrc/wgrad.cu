@@ -39,6 +39,8 @@ linear_wgrad_kernel(const bf16* __restrict__ dy, long ld_dy, const bf16* __restr
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_blk = blockIdx.x;       // which BN-row block of dW
   const int split = blockIdx.y, nsplit = gridDim.y;
+  x += (long)blockIdx.z * 128;         // which 128-column block of X (K > 128: all blocks in one launch)
+  partial += (long)blockIdx.z * nsplit * n_total * 128;
   const long chunks_total = (T + kLwChunk - 1) / kLwChunk;
   const long c_begin = chunks_total * split / nsplit, c_end = chunks_total * (split + 1) / nsplit;
   const int wn = warp % Cfg::kWarpsN, wk = warp / Cfg::kWarpsN;
@@ -268,21 +270,23 @@ int wg_sms() {
 
 }  // namespace
 
-int linear_wgrad_splits(long T, int N) {
-  const int nblk = (N % 128 == 0) ? N / 128 : N / 64;
+int linear_wgrad_splits(long T, int N, int K) {
+  const int nblk = ((N % 128 == 0) ? N / 128 : N / 64) * (K / 128);
   long chunks = (T + kLwChunk - 1) / kLwChunk;
   long s = wg_sms() / nblk;
   if (s > chunks) s = chunks;
   if (s < 1) s = 1;
   return (int)s;
 }
-size_t linear_wgrad_partial_bytes(long T, int N) { return (size_t)linear_wgrad_splits(T, N) * N * 128 * 4; }
+size_t linear_wgrad_partial_bytes(long T, int N, int K) { return (size_t)linear_wgrad_splits(T, N, K) * N * K * 4; }
 
 // out[r*ld_out + c] = scale * sum_p partial[p*stride + r*128 + c], c < 128
 __global__ void reduce_partials_2d_kernel(const float* __restrict__ partial, int P, long stride, int rows,
                                           float* __restrict__ out, long ld_out, float scale) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * 128) return;
+  partial += (long)blockIdx.y * P * stride;  // K block
+  out += (long)blockIdx.y * 128;
   double s = 0.0;
   for (int p = 0; p < P; ++p) s += partial[(long)p * stride + i];
   out[(long)(i >> 7) * ld_out + (i & 127)] = (float)s * scale;
@@ -293,7 +297,7 @@ int linear_wgrad(const bf16* dy, long ld_dy, const bf16* x, long ld_x, long T, i
                  float* partial, cudaStream_t s) {
   ProfScope _ps("linear_wgrad", s);
   FOCR_REQUIRE(N % 64 == 0 && K % 128 == 0, "linear_wgrad: N=%d K=%d", N, K);
-  const int splits = linear_wgrad_splits(T, N);
+  const int splits = linear_wgrad_splits(T, N, K);
   static bool init = false;
   if (!init) {
     FOCR_CHECK_CUDA(cudaFuncSetAttribute(linear_wgrad_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -302,18 +306,18 @@ int linear_wgrad(const bf16* dy, long ld_dy, const bf16* x, long ld_x, long T, i
                                          LwCfg<64>::kSmemBytes));
     init = true;
   }
-  for (int kb = 0; kb < K / 128; ++kb) {
-    if (N % 128 == 0)
-      linear_wgrad_kernel<128><<<dim3(N / 128, splits), 256, LwCfg<128>::kSmemBytes, s>>>(dy, ld_dy, x + kb * 128,
-                                                                                          ld_x, T, N, partial);
-    else
-      linear_wgrad_kernel<64><<<dim3(N / 64, splits), 256, LwCfg<64>::kSmemBytes, s>>>(dy, ld_dy, x + kb * 128, ld_x,
-                                                                                        T, N, partial);
-    FOCR_LAUNCH_CHECK();
-    reduce_partials_2d_kernel<<<focr_cdiv(N * 128, 256), 256, 0, s>>>(partial, splits, (long)N * 128, N,
-                                                                      dw + kb * 128, K, scale);
-    FOCR_LAUNCH_CHECK();
-  }
+  // one launch covers every (row block, token split, 128-column block of X); one reduction finishes all of dW
+  const int kblocks = K / 128;
+  if (N % 128 == 0)
+    linear_wgrad_kernel<128><<<dim3(N / 128, splits, kblocks), 256, LwCfg<128>::kSmemBytes, s>>>(dy, ld_dy, x, ld_x, T, N,
+                                                                                                partial);
+  else
+    linear_wgrad_kernel<64><<<dim3(N / 64, splits, kblocks), 256, LwCfg<64>::kSmemBytes, s>>>(dy, ld_dy, x, ld_x, T, N,
+                                                                                              partial);
+  FOCR_LAUNCH_CHECK();
+  reduce_partials_2d_kernel<<<dim3(focr_cdiv(N * 128, 256), kblocks), 256, 0, s>>>(partial, splits, (long)N * 128, N, dw, K,
+                                                                                  scale);
+  FOCR_LAUNCH_CHECK();
   return FOCR_OK;
 }
 

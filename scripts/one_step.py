@@ -8,7 +8,7 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 warm = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 torch.manual_seed(1234)
 m = TBSRN().cuda().train()
-tr = TBSRNTrainer(m)
+tr = TBSRNTrainer(m, use_graph=False)  # eager launches: every kernel visible to ncu
 lr = torch.rand(B, 3, 16, 64, device="cuda"); hr = torch.rand(B, 3, 32, 128, device="cuda")
 for i in range(warm):
     tr.step(lr, hr, seed=i)

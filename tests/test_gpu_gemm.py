@@ -25,7 +25,9 @@ def _nhwc(x):  # (B,C,H,W) fp32 -> (B,H,W,C) bf16 contiguous
 
 @pytest.mark.parametrize("B,H,W,Ci,Co,ks", [(2, 16, 64, 64, 64, 3), (3, 16, 64, 64, 64, 1),
                                             (2, 16, 64, 128, 64, 3), (1, 32, 128, 64, 64, 3),
-                                            (2, 16, 64, 64, 128, 3), (2, 16, 64, 64, 256, 3)])
+                                            (2, 16, 64, 64, 128, 3), (2, 16, 64, 64, 256, 3),
+                                            # >= 2 tiles per SM: the resident-weights mode of the 64-wide kernel
+                                            (40, 16, 64, 64, 64, 3), (11, 32, 128, 64, 64, 3), (37, 16, 64, 128, 64, 1)])
 def test_conv_fwd(B, H, W, Ci, Co, ks):
     L = _lib()
     g = torch.Generator(device="cuda").manual_seed(1)
@@ -38,7 +40,9 @@ def test_conv_fwd(B, H, W, Ci, Co, ks):
     L.check(L.lib.focr_conv2d_fwd(xb.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), 0, 0, B, H, W, Ci, Co,
                                   ks, 0, ws.data_ptr(), ws.numel(), L.cur_stream()), "conv2d_fwd")
     L.check(L.lib.focr_sync_check(L.cur_stream()))
-    ref = F.conv2d(xb.float().permute(0, 3, 1, 2), w.to(torch.bfloat16).float(), b, padding=ks // 2)
+    # reference by unfold + matmul: cuDNN spends seconds runtime-compiling fp32 NHWC kernels for the larger shapes
+    cols = F.unfold(xb.float().permute(0, 3, 1, 2).contiguous(), ks, padding=ks // 2)          # (B, Ci*ks*ks, H*W)
+    ref = (w.to(torch.bfloat16).float().reshape(Co, -1) @ cols + b[None, :, None]).view(B, Co, H, W)
     err = _rel(y.permute(0, 3, 1, 2), ref)
     assert err < 1e-2, err
 
