@@ -68,6 +68,8 @@ _SIGS = {
     "focr_bicubic_gray_32x100": (C.c_int, [_fp, _fp, _i, _vp]),
     "focr_crnn_forward": (C.c_int, [_pp, _fp, _i, _fp, _i, _vp, _sz, _vp]),
     "focr_ctc_greedy_decode": (C.c_int, [_fp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "focr_psnr_ssim_workspace_bytes": (_sz, [_i]),
+    "focr_psnr_ssim": (C.c_int, [_fp, _fp, _i, _i, _fp, _fp, _fp, _vp, _sz, _vp]),
     "focr_prof_enable": (C.c_int, [_i, C.c_char_p]),
     "focr_prof_collect": (C.c_int, [C.c_char_p, _i]),
     "focr_launch_count": (_ll, []),

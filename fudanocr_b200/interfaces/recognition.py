@@ -41,3 +41,27 @@ def get_crnn_pred(outputs_btc: torch.Tensor) -> List[str]:
     _, out, ln = ctc_greedy_decode(outputs_btc.permute(1, 0, 2))
     out, ln = out.cpu().tolist(), ln.cpu().tolist()
     return ["".join(ALPHABET[i] for i in row[:n]) for row, n in zip(out, ln)]
+
+
+def str_filt(str_: str, voc_type: str = "lower") -> str:
+    """utils/util.py:12-24 (the comparison key of the accuracy count, super_resolution.py:204)"""
+    import string
+    keep = {"digit": string.digits, "lower": string.digits + string.ascii_lowercase,
+            "upper": string.digits + string.ascii_letters, "all": string.digits + string.ascii_letters + string.punctuation}
+    if voc_type == "lower":
+        str_ = str_.lower()
+    return "".join(c for c in str_ if c in keep[voc_type])
+
+
+def evaluate_batch(model, recognizer, images_lr: torch.Tensor, images_hr: torch.Tensor, label_strs) -> dict:
+    """One iteration of the reference's validation loop (TextSR.eval, interfaces/super_resolution.py:178-207) on the engine:
+    SR forward (eval mode) -> PSNR / SSIM -> bicubic + gray -> CRNN -> greedy CTC decode -> exact-match count.
+    Everything up to the decoded index arrays stays on the device; one D2H copy (indices + the two metric scalars)."""
+    from ..utils.ssim_psnr import psnr_ssim
+    with torch.no_grad():
+        images_sr = model(images_lr)
+        psnr, ssim_avg = psnr_ssim(images_sr, images_hr)
+        logits = recognizer(parse_crnn_data(images_sr[:, :3]))            # (26, B, 37)
+        pred = get_crnn_pred(logits.permute(1, 0, 2).contiguous())
+    n_correct = sum(1 for p, t in zip(pred, label_strs) if p == str_filt(t, "lower"))
+    return {"images_sr": images_sr, "psnr": psnr, "ssim": ssim_avg, "pred": pred, "n_correct": n_correct}

@@ -173,6 +173,14 @@ int focr_text_focus_loss(const void* prepared, size_t prepared_bytes, int n_clas
                          size_t ws_bytes, void* stream);
 int focr_focus_loss_ws_tensor(int B, int T, const char* name, long long* byte_offset, long long* elems, int* elem_bytes);
 
+/* --- evaluation metrics: scene-text-telescope/utils/ssim_psnr.py:9-15 (calculate_psnr), :31-78 (SSIM, window 11, sigma 1.5),
+ * as called per validation batch by interfaces/super_resolution.py:191-192.  img1, img2 fp32 NCHW (B, channels >= 3, 32, 128)
+ * in [0,1] (first 3 channels are used); window: the 121 fp32 taps of create_window (:24-28).  out[0] = PSNR over the batch
+ * (inf when identical), out[1] = mean SSIM; ssim_per_image (optional, B floats) = the size_average=False form. */
+size_t focr_psnr_ssim_workspace_bytes(int B);
+int focr_psnr_ssim(const float* img1, const float* img2, int B, int channels, const float* window, float* out,
+                   float* ssim_per_image, void* ws, size_t ws_bytes, void* stream);
+
 /* --- measurement hooks used by bench.py: CUDA-event scopes on the launching stream + launch counter ----------- */
 int focr_prof_enable(int mode /*0 off, 1 all, 2 focus*/, const char* focus_substring);
 int focr_prof_collect(char* buf, int cap); /* lines "scope launches total_ms"; synchronises; clears */

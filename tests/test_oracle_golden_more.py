@@ -103,3 +103,16 @@ def test_textfocus_oracle_vs_reference_golden():
     lw = torch.log(table[g["text_gt"]])
     lse = torch.logsumexp(g["sr_pred"] + lw, 1) - (g["sr_pred"] + lw).gather(1, g["text_gt"][:, None])[:, 0]
     assert abs(lse.mean().item() - g["recognition_loss"].item()) < 1e-5 * g["recognition_loss"].item()
+
+
+def test_metrics_oracle_vs_reference_golden():
+    """PSNR / SSIM restatement vs values recorded from the unmodified utils/ssim_psnr.py"""
+    from oracle import metrics_oracle as MO
+    g = _load("metrics.pt")
+    for key, rec in g.items():
+        sr, hr = MO.synth_pair(int(key[1:]), rec["seed"])
+        assert abs(float(sr.double().sum() + hr.double().sum()) - rec["checksum"]) < 1e-6 * abs(rec["checksum"])
+        assert torch.allclose(MO.calculate_psnr(sr, hr), rec["psnr"], rtol=1e-5)
+        assert torch.allclose(MO.ssim(sr, hr), rec["ssim"], rtol=1e-5)
+        assert torch.allclose(MO.ssim(sr, hr, 11, False), rec["ssim_per_image"], rtol=1e-5)
+    assert MO.calculate_psnr(hr, hr) == float("inf")
