@@ -50,7 +50,8 @@ __global__ void __launch_bounds__(256) ssim_psnr_kernel(const float* __restrict_
     const float m11 = mu1 * mu1, m22 = mu2 * mu2, m12 = mu1 * mu2;
     const float v1 = s11 - m11, v2 = s22 - m22, v12 = s12 - m12;
     ssim_sum += ((2.f * m12 + C1) * (2.f * v12 + C2)) / ((m11 + m22 + C1) * (v1 + v2 + C2));
-    const float d = sa[(y + kR) * kPW + x + kR] * 255.f - sb[(y + kR) * kPW + x + kR] * 255.f;
+    // img1*255 - img2*255 with each product rounded as in the reference (no FMA contraction: identical images -> exactly 0)
+    const float d = __fsub_rn(__fmul_rn(sa[(y + kR) * kPW + x + kR], 255.f), __fmul_rn(sb[(y + kR) * kPW + x + kR], 255.f));
     se_sum = fmaf(d, d, se_sum);
   }
   ssim_sum = warp_sum(ssim_sum);
