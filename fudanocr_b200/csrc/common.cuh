@@ -86,16 +86,24 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t v) {
 
 // mish(x) = x * tanh(softplus(x)); softplus threshold 20 as in torch (F.softplus).
 // Reference: scene-text-telescope/model/tbsrn.py:277-285.
+// With e = exp(x): tanh(log(1 + e)) = ((1+e)^2 - 1) / ((1+e)^2 + 1) = n / (n + 2), n = e (e + 2): one MUFU.EX2 and one
+// MUFU.RCP instead of exp + log1p + tanh (the train-mode BN backward over a mish layer was compute-bound on those:
+// 144 us against 73 us for the same traffic without the activation).  Above the threshold tanh(x) == 1 in fp32.
 __device__ __forceinline__ float mish_f(float x) {
-  float sp = (x > 20.f) ? x : log1pf(__expf(x));
-  return x * tanhf(sp);
+  const float e = __expf(fminf(x, 20.f));
+  const float n = e * (e + 2.f);
+  const float t = __fdividef(n, n + 2.f);
+  return x > 20.f ? x : x * t;
 }
-// d mish / dx
+// d mish / dx = t + x (1 - t^2) sigmoid(x),  1 - t = 2 / (n + 2)
 __device__ __forceinline__ float mish_grad_f(float x) {
-  float sp = (x > 20.f) ? x : log1pf(__expf(x));
-  float t = tanhf(sp);
-  float sig = 1.f / (1.f + __expf(-x));  // d softplus / dx (== 1 above threshold, sig(20)~1)
-  return t + x * (1.f - t * t) * sig;
+  const float e = __expf(fminf(x, 20.f));
+  const float n = e * (e + 2.f);
+  const float r = __fdividef(1.f, n + 2.f);
+  const float t = n * r;
+  const float omt = 2.f * r;
+  const float sig = __fdividef(e, 1.f + e);
+  return x > 20.f ? 1.f : t + x * omt * (2.f - omt) * sig;
 }
 
 

@@ -11,6 +11,8 @@
 namespace {
 
 constexpr int kThreads = 256;
+constexpr int kLnRows = 4;     // rows per 16-lane group per loop iteration of the LayerNorm forward
+constexpr int kLnBwdRows = 2;  // ... of the backward (4 costs 127 registers and measured 89 us against 66 us for 1)
 
 __device__ __forceinline__ void load8(const bf16* p, float (&v)[8]) {
   const uint4 u = *reinterpret_cast<const uint4*>(p);
@@ -302,33 +304,40 @@ __global__ void __launch_bounds__(kThreads) ln_fwd_kernel(const bf16* __restrict
     av[j] = a[l16 * 8 + j];
     bv[j] = b[l16 * 8 + j];
   }
-  const long rows_per_pass = (long)gridDim.x * (kThreads / 16);
-  // all 16 lanes of a row group take the same trip count (T is a multiple of 16 rows per block pass
-  // is not required: out-of-range rows are predicated, shuffles stay convergent)
-  for (long t0 = (long)blockIdx.x * (kThreads / 16); t0 < T; t0 += rows_per_pass) {
-    const long t = t0 + rl;
-    const bool ok = t < T;
-    float v[8];
-    if (ok) load8(x + t * 128 + l16 * 8, v);
-    else {
+  // kLnRows rows per 16-lane group per iteration: all loads of the iteration are issued before the first shuffle
+  // reduction, so each thread keeps 4 x 16 B in flight (one row at a time streamed at ~3.3 TB/s, half of HBM rate)
+  constexpr int R = kLnRows;
+  const long rows_per_pass = (long)gridDim.x * (kThreads / 16) * R;
+  for (long t0 = (long)blockIdx.x * (kThreads / 16) * R; t0 < T; t0 += rows_per_pass) {
+    float v[R][8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    for (int k = 0; k < R; ++k) {
+      const long t = t0 + rl + k * (kThreads / 16);
+      if (t < T) load8(x + t * 128 + l16 * 8, v[k]);
+      else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[k][j] = 0.f;
+      }
     }
-    float s = 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) s += v[j];
-    const float mean = half_warp_sum(s) * (1.f / 128.f);
-    float q = 0.f;
+    for (int k = 0; k < R; ++k) {
+      const long t = t0 + rl + k * (kThreads / 16);
+      float s = 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      v[j] -= mean;
-      q += v[j] * v[j];
+      for (int j = 0; j < 8; ++j) s += v[k][j];
+      const float mean = half_warp_sum(s) * (1.f / 128.f);
+      float q = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        v[k][j] -= mean;
+        q += v[k][j] * v[k][j];
+      }
+      const float sd = sqrtf(half_warp_sum(q) * (1.f / 127.f));
+      const float inv = 1.f / (sd + eps);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[k][j] = fmaf(av[j] * v[k][j], inv, bv[j]);
+      if (t < T) store8(y + t * 128 + l16 * 8, v[k]);
     }
-    const float sd = sqrtf(half_warp_sum(q) * (1.f / 127.f));
-    const float inv = 1.f / (sd + eps);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = fmaf(av[j] * v[j], inv, bv[j]);
-    if (ok) store8(y + t * 128 + l16 * 8, v);
   }
 }
 
@@ -346,47 +355,54 @@ __global__ void __launch_bounds__(kThreads) ln_bwd_kernel(const bf16* __restrict
     av[j] = a[l16 * 8 + j];
     da[j] = db[j] = 0.f;
   }
-  const long rows_per_pass = (long)gridDim.x * (kThreads / 16);
-  for (long t0 = (long)blockIdx.x * (kThreads / 16); t0 < T; t0 += rows_per_pass) {
-    const long t = t0 + rl;
-    const bool ok = t < T;
-    float v[8], g[8];
-    if (ok) {
-      load8(x + t * 128 + l16 * 8, v);
-      load8(dy + t * 128 + l16 * 8, g);
-    } else {
+  constexpr int R = kLnBwdRows;
+  const long rows_per_pass = (long)gridDim.x * (kThreads / 16) * R;
+  for (long t0 = (long)blockIdx.x * (kThreads / 16) * R; t0 < T; t0 += rows_per_pass) {
+    float v[R][8], g[R][8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = g[j] = 0.f;
+    for (int k = 0; k < R; ++k) {
+      const long t = t0 + rl + k * (kThreads / 16);
+      if (t < T) {
+        load8(x + t * 128 + l16 * 8, v[k]);
+        load8(dy + t * 128 + l16 * 8, g[k]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[k][j] = g[k][j] = 0.f;
+      }
     }
-    float s = 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) s += v[j];
-    const float mean = half_warp_sum(s) * (1.f / 128.f);
-    float q = 0.f, hs = 0.f, hd = 0.f;
+    for (int k = 0; k < R; ++k) {
+      const long t = t0 + rl + k * (kThreads / 16);
+      float s = 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      v[j] -= mean;
-      q += v[j] * v[j];
-      const float h = av[j] * g[j];
-      hs += h;
-      hd += h * v[j];
+      for (int j = 0; j < 8; ++j) s += v[k][j];
+      const float mean = half_warp_sum(s) * (1.f / 128.f);
+      float q = 0.f, hs = 0.f, hd = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        v[k][j] -= mean;
+        q += v[k][j] * v[k][j];
+        const float h = av[j] * g[k][j];
+        hs += h;
+        hd += h * v[k][j];
+      }
+      q = half_warp_sum(q);
+      hs = half_warp_sum(hs);
+      hd = half_warp_sum(hd);
+      const float sigma = sqrtf(q * (1.f / 127.f));
+      const float sp = sigma + eps;
+      const float inv = 1.f / sp;
+      const float hm = hs * (1.f / 128.f);
+      const float k2 = sigma > 0.f ? hd * inv * inv / (127.f * sigma) : 0.f;
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        o[j] = (av[j] * g[k][j] - hm) * inv - v[k][j] * k2;
+        da[j] += g[k][j] * v[k][j] * inv;
+        db[j] += g[k][j];
+      }
+      if (t < T) store8(dx + t * 128 + l16 * 8, o);
     }
-    q = half_warp_sum(q);
-    hs = half_warp_sum(hs);
-    hd = half_warp_sum(hd);
-    const float sigma = sqrtf(q * (1.f / 127.f));
-    const float sp = sigma + eps;
-    const float inv = 1.f / sp;
-    const float hm = hs * (1.f / 128.f);
-    const float k2 = sigma > 0.f ? hd * inv * inv / (127.f * sigma) : 0.f;
-    float o[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      o[j] = (av[j] * g[j] - hm) * inv - v[j] * k2;
-      da[j] += g[j] * v[j] * inv;
-      db[j] += g[j];
-    }
-    if (ok) store8(dx + t * 128 + l16 * 8, o);
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -562,9 +578,18 @@ __global__ void pe_table_kernel(bf16* __restrict__ pe) {
 
 // grid for reduction passes: 8 CTAs per SM keep enough loads in flight to stream at HBM rate; the second stage is
 // warp-parallel, so summing up to 1184 partials per output costs ~40 loads per lane
+int ctas_per_sm() {  // tuning knob FOCR_EW_CTAS_PER_SM (measured at T = 262144: 4 is 5-9 % faster than 8, 16+ slower)
+  static int v = 0;
+  if (v == 0) {
+    const char* e = getenv("FOCR_EW_CTAS_PER_SM");
+    v = e ? atoi(e) : 4;
+    if (v < 1 || v > 32) v = 4;
+  }
+  return v;
+}
 int red_grid(long work_items, int per_block) {
   long g = (work_items + per_block - 1) / per_block;
-  const long cap = 148L * 8;
+  const long cap = 148L * ctas_per_sm();
   if (g > cap) g = cap;
   if (g < 1) g = 1;
   return (int)g;
@@ -572,7 +597,7 @@ int red_grid(long work_items, int per_block) {
 
 int ew_grid(long work_items, int per_block) {
   long g = (work_items + per_block - 1) / per_block;
-  const long cap = 148L * 8;
+  const long cap = 148L * ctas_per_sm();
   if (g > cap) g = cap;
   if (g < 1) g = 1;
   return (int)g;
@@ -633,11 +658,11 @@ int bn_backward(const bf16* dy, long ld_dy, const bf16* x, long ld_x, const floa
   return FOCR_OK;
 }
 
-int ln_partial_blocks(long T) { return red_grid(T, (kThreads / 16) * 8); }
+int ln_partial_blocks(long T) { return red_grid(T, (kThreads / 16) * kLnBwdRows); }
 
 int ln_forward(const bf16* x, const float* a, const float* b, bf16* y, long T, float eps, cudaStream_t s) {
   ProfScope _ps("ln_fwd", s);
-  ln_fwd_kernel<<<ew_grid(T, (kThreads / 16) * 4), kThreads, 0, s>>>(x, a, b, y, T, eps);
+  ln_fwd_kernel<<<ew_grid(T, (kThreads / 16) * kLnRows), kThreads, 0, s>>>(x, a, b, y, T, eps);
   FOCR_LAUNCH_CHECK();
   return FOCR_OK;
 }
