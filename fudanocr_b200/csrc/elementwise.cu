@@ -12,7 +12,7 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kLnRows = 4;     // rows per 16-lane group per loop iteration of the LayerNorm forward
-constexpr int kLnBwdRows = 2;  // ... of the backward (4 costs 127 registers and measured 89 us against 66 us for 1)
+constexpr int kLnBwdRows = 1;  // ... of the backward (2 or 4 rows cost 92 / 127 registers and measured 89 us against 66 us for 1)
 
 __device__ __forceinline__ void load8(const bf16* p, float (&v)[8]) {
   const uint4 u = *reinterpret_cast<const uint4*>(p);
@@ -54,6 +54,7 @@ __global__ void __launch_bounds__(kThreads) bn_stats_kernel(const bf16* __restri
   float s[8], q[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+#pragma unroll 4
   for (long t = (long)blockIdx.x * rpb + rl; t < T; t += (long)gridDim.x * rpb) {
     float v[8];
     load8(x + t * ld + cg * 8, v);
@@ -158,6 +159,7 @@ __global__ void __launch_bounds__(kThreads) bn_apply_kernel(const bf16* __restri
     sc[j] = stats[2 * C + cg * 8 + j];
     sh[j] = stats[3 * C + cg * 8 + j];
   }
+#pragma unroll 4
   for (long t = (long)blockIdx.x * rpb + rl; t < T; t += (long)gridDim.x * rpb) {
     float v[8];
     load8(x + t * ld_x + cg * 8, v);
@@ -195,6 +197,7 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_reduce_kernel(const bf16* __r
     sh[j] = stats[3 * C + cg * 8 + j];
     s[j] = q[j] = 0.f;
   }
+#pragma unroll 4
   for (long t = (long)blockIdx.x * rpb + rl; t < T; t += (long)gridDim.x * rpb) {
     float xv[8], gv[8];
     load8(x + t * ld_x + cg * 8, xv);
@@ -269,6 +272,7 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(const bf16* __re
     c1[j] = coef[cg * 8 + j];
     c2[j] = coef[C + cg * 8 + j];
   }
+#pragma unroll 4
   for (long t = (long)blockIdx.x * rpb + rl; t < T; t += (long)gridDim.x * rpb) {
     float xv[8], gv[8];
     load8(x + t * ld_x + cg * 8, xv);
@@ -434,7 +438,8 @@ __global__ void __launch_bounds__(kThreads) colsum_kernel(const bf16* __restrict
 #pragma unroll
   for (int j = 0; j < 8; ++j) s[j] = 0.f;
   if (rl < rpb) {
-    for (long t = (long)blockIdx.x * rpb + rl; t < T; t += (long)gridDim.x * rpb) {
+  #pragma unroll 4
+  for (long t = (long)blockIdx.x * rpb + rl; t < T; t += (long)gridDim.x * rpb) {
       float v[8];
       const long off = inner > 0 ? (t / inner) * stride_outer + (t % inner) * ld : t * ld;
       load8(x + off + cg * 8, v);
