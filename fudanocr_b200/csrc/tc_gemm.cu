@@ -68,10 +68,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
   uint64_t* bfull = aempty + 2;   // resident weights landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bfull + 1);
   const bool resident = BLOCK_N == 64 && p.b_resident != 0;
+  // Column mode (3x3, 64 -> 64, resident weights, no auxiliary tile): one TMA box of (tile rows + 2) image rows at
+  // horizontal shift dx serves the three taps dy = -1, 0, +1 of that column as 1024-byte-aligned windows of the same
+  // shared-memory tile (window offset = dy * W pixels * 128 B), so a tile needs 3 x (128 + 2W) pixel rows of fills
+  // instead of 9 x 128.  The ring then also takes over the unused auxiliary-tile region.
+  const bool colmode = resident && p.col_mode != 0;
   uint8_t* ring = smem + (resident ? Cfg::kResBytes : 0);
-  const int stage_bytes = resident ? kABytes : Cfg::kStageBytes;
-  const int n_stages = resident ? Cfg::kResStages : Cfg::kStages;
-  uint8_t* cd_base = smem + Cfg::kOffCd;
+  const int col_bytes = (kTileM + 2 * p.W) * 128;
+  const int stage_bytes = colmode ? col_bytes : (resident ? kABytes : Cfg::kStageBytes);
+  int n_stages = resident ? Cfg::kResStages : Cfg::kStages;
+  if (colmode) {
+    n_stages = (Cfg::kOffAux - Cfg::kResBytes) / col_bytes;
+    if (n_stages > Cfg::kStages) n_stages = Cfg::kStages;
+  }
+  uint8_t* cd_base = smem + ((BLOCK_N == 64 && p.b_resident != 0 && p.col_mode != 0) ? Cfg::kOffAux : Cfg::kOffCd);
   uint8_t* aux_base = smem + Cfg::kOffAux;
   const bool use_aux = p.tma_out && (p.residual != nullptr || p.gate != nullptr);
 
@@ -136,6 +146,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
             tma_load_2d(aux_base + ab * Cfg::kCdBytes + blk * kCdBlk, &mR, &afull[ab], nb * BLOCK_N + blk * 64, p0);
           ++ait;
         }
+        if (colmode) {
+          for (int dxi = 0; dxi < 3; ++dxi) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full[stage], (uint32_t)stage_bytes);
+            tma_load_4d(ring + stage * stage_bytes, &mA1, &full[stage], 0, dxi - 1, h0 - 1, b);
+            if (++stage == n_stages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+          continue;
+        }
         for (int tap = 0; tap < taps; ++tap) {
           const int dy = tap / p.kw - pad_h, dx = tap % p.kw - pad_w;
           for (int ch = 0; ch < p.chunks; ++ch) {
@@ -170,6 +192,30 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
         mbar_wait(&tempty[acc], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        if (colmode) {
+          for (int dxi = 0; dxi < 3; ++dxi) {
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(ring + stage * stage_bytes);
+#pragma unroll
+            for (int dyi = 0; dyi < 3; ++dyi) {
+              const uint64_t da = umma_desc_k_sw128(sa + dyi * p.W * 128);
+              const uint64_t db = umma_desc_k_sw128(smem_u32(smem + (dyi * 3 + dxi) * Cfg::kBBytes));
+#pragma unroll
+              for (int k = 0; k < kChunkK / 16; ++k)
+                tc_mma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (dxi | dyi | k) != 0);
+            }
+            tc_commit(&empty[stage]);
+            if (++stage == n_stages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+          tc_commit(&tfull[acc]);
+          acc ^= 1;
+          if (acc == 0) aphase ^= 1;
+          continue;
+        }
         for (int kb = 0; kb < nk; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
@@ -602,6 +648,7 @@ int tc_gemm_launch(const bf16* const* a_ptrs, int n_amaps, long a_pix_stride, lo
     p.b_resident = (!no_res && block_n == 64 && p.n_blocks == 1 && p.kh * p.kw * p.chunks <= kResMaxKb &&
                     p.m_tiles >= 2 * num_sms()) ? 1 : 0;
   }
+  p.col_mode = 0;
   // output / auxiliary tiles through TMA for the plain bf16 epilogue (every hot GEMM); the rare epilogues
   // (fp32 output, PixelShuffle scatter, PReLU with saved pre-activation) keep direct stores
   p.tma_out = (p.epi == TC_EPI_BF16 && p.prelu_slope == nullptr) ? 1 : 0;
@@ -617,6 +664,19 @@ int tc_gemm_launch(const bf16* const* a_ptrs, int n_amaps, long a_pix_stride, lo
     if (aux) {
       rc = make_map(&rm, aux, 2, dims, str, box);
       if (rc) return rc;
+    }
+  }
+  {
+    static int no_col = -1;
+    if (no_col < 0) no_col = getenv("FOCR_TC_NO_COLMODE") ? 1 : 0;  // tuning knob
+    if (!no_col && p.b_resident && p.tma_out && p.kh == 3 && p.kw == 3 && p.chunks == 1 && n_amaps == 1 && !p.residual &&
+        !p.gate) {
+      cuuint64_t dims[4] = {(cuuint64_t)a_channels, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)B};
+      cuuint64_t str[3] = {(cuuint64_t)a_pix_stride * 2, (cuuint64_t)a_row_stride * 2, (cuuint64_t)a_img_stride * 2};
+      cuuint32_t box[4] = {64, (cuuint32_t)p.W, (cuuint32_t)(kTileM / p.W + 2), 1};
+      int rc = make_map(&am[1], a_ptrs[0], 4, dims, str, box);
+      if (rc) return rc;
+      p.col_mode = 1;
     }
   }
   const char* scope = p.kh * p.kw == 1 ? "tc_linear" : (p.kh == 3 && p.kw == 3 ? "tc_conv3x3" : "tc_conv9tap");

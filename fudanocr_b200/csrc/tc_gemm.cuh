@@ -44,6 +44,7 @@ struct TcGemmParams {
   // PReLU epilogue (block1, tbsrn.py:180-182): out = x > 0 ? x : slope[0]*x ; out2 (optional) = x
   const float* prelu_slope;
   int relu_post;  // ReLU applied after the residual add (BasicBlock: relu(bn(conv) + skip))
+  int col_mode;    // set by tc_gemm_launch: 3x3 taps taken column-wise from (rows + 2)-row tiles (see tc_gemm.cu)
   int b_resident;  // set by tc_gemm_launch: whole weight operand resident in shared memory (see tc_gemm.cu)
   int tma_out;  // set by tc_gemm_launch: epilogue goes TMEM -> smem -> TMA store, aux tile prefetched by TMA
 };
