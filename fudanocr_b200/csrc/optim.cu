@@ -20,7 +20,17 @@ __global__ void __launch_bounds__(256) gradsq_kernel(const OptChunk* __restrict_
   __shared__ float red[8];
   const OptChunk c = chunks[blockIdx.x];
   float a = 0.f;
-  for (long long i = threadIdx.x; i < c.n; i += 256) {
+  long long i0 = 0;
+  if ((reinterpret_cast<uintptr_t>(c.g) & 15) == 0) {  // 16-byte aligned chunk: vector loads
+    const float4* g4 = reinterpret_cast<const float4*>(c.g);
+    const long long n4 = c.n >> 2;
+    for (long long i = threadIdx.x; i < n4; i += 256) {
+      const float4 g = g4[i];
+      a += g.x * g.x + g.y * g.y + g.z * g.z + g.w * g.w;
+    }
+    i0 = n4 << 2;
+  }
+  for (long long i = i0 + threadIdx.x; i < c.n; i += 256) {
     const float g = c.g[i];
     a += g * g;
   }
@@ -65,7 +75,37 @@ __global__ void __launch_bounds__(256) adam_kernel(const OptChunk* __restrict__ 
                                                    float b1, float b2, float eps) {
   const OptChunk c = chunks[blockIdx.x];
   const float gs = state[1], step_size = state[2], inv_bc2 = state[3];
-  for (long long i = threadIdx.x; i < c.n; i += 256) {
+  long long i0 = 0;
+  if (((reinterpret_cast<uintptr_t>(c.g) | reinterpret_cast<uintptr_t>(c.p) | reinterpret_cast<uintptr_t>(c.m) |
+        reinterpret_cast<uintptr_t>(c.v)) & 15) == 0) {
+    const float4* g4 = reinterpret_cast<const float4*>(c.g);
+    float4* p4 = reinterpret_cast<float4*>(c.p);
+    float4* m4 = reinterpret_cast<float4*>(c.m);
+    float4* v4 = reinterpret_cast<float4*>(c.v);
+    const long long n4 = c.n >> 2;
+    for (long long i = threadIdx.x; i < n4; i += 256) {
+      const float4 g = g4[i];
+      float4 m = m4[i], v = v4[i], w = p4[i];
+      const float gx = g.x * gs, gy = g.y * gs, gz = g.z * gs, gw = g.w * gs;
+      m.x = b1 * m.x + (1.f - b1) * gx;
+      m.y = b1 * m.y + (1.f - b1) * gy;
+      m.z = b1 * m.z + (1.f - b1) * gz;
+      m.w = b1 * m.w + (1.f - b1) * gw;
+      v.x = b2 * v.x + (1.f - b2) * gx * gx;
+      v.y = b2 * v.y + (1.f - b2) * gy * gy;
+      v.z = b2 * v.z + (1.f - b2) * gz * gz;
+      v.w = b2 * v.w + (1.f - b2) * gw * gw;
+      w.x -= step_size * m.x / (sqrtf(v.x) * inv_bc2 + eps);
+      w.y -= step_size * m.y / (sqrtf(v.y) * inv_bc2 + eps);
+      w.z -= step_size * m.z / (sqrtf(v.z) * inv_bc2 + eps);
+      w.w -= step_size * m.w / (sqrtf(v.w) * inv_bc2 + eps);
+      m4[i] = m;
+      v4[i] = v;
+      p4[i] = w;
+    }
+    i0 = n4 << 2;
+  }
+  for (long long i = i0 + threadIdx.x; i < c.n; i += 256) {
     const float g = c.g[i] * gs;
     const float m = b1 * c.m[i] + (1.f - b1) * g;
     const float v = b2 * c.v[i] + (1.f - b2) * g * g;
