@@ -258,11 +258,17 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(const bf16* __re
                                                                 const bf16* __restrict__ x, long ld_x,
                                                                 const float* __restrict__ stats,
                                                                 const float* __restrict__ coef, bf16* __restrict__ dx,
-                                                                long ld_dx, long T, int C, int act) {
+                                                                long ld_dx, long T, int C, int act,
+                                                                float* __restrict__ colsum_partial) {
+  // colsum_partial (optional): per-CTA column sums of the dx values as stored (bf16-rounded) = the gradient of the bias of
+  // the convolution in front of this BatchNorm, so that tensor is not read again by a separate column-sum pass
+  __shared__ float cred[kThreads][8];
   const int tpr = C >> 3;
   const int rpb = kThreads / tpr;
   const int cg = threadIdx.x % tpr, rl = threadIdx.x / tpr;
-  float mean[8], istd[8], sc[8], sh[8], c1[8], c2[8];
+  float mean[8], istd[8], sc[8], sh[8], c1[8], c2[8], cs[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) cs[j] = 0.f;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     mean[j] = stats[cg * 8 + j];
@@ -282,8 +288,22 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(const bf16* __re
       const float g = gv[j] * act_bwd(fmaf(xv[j], sc[j], sh[j]), act);
       const float xh = (xv[j] - mean[j]) * istd[j];
       gv[j] = sc[j] * (g - c1[j] - xh * c2[j]);
+      cs[j] += __bfloat162float(__float2bfloat16_rn(gv[j]));
     }
     store8(dx + t * ld_dx + cg * 8, gv);
+  }
+  if (colsum_partial != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) cred[threadIdx.x][j] = cs[j];
+    __syncthreads();
+    if (threadIdx.x < tpr) {
+      for (int r = 1; r < rpb; ++r) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cs[j] += cred[threadIdx.x + r * tpr][j];
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) colsum_partial[(long)blockIdx.x * C + cg * 8 + j] = cs[j];
+    }
   }
 }
 
@@ -649,7 +669,7 @@ int bn_apply(const bf16* x, long ld_x, const float* stats, bf16* out, long ld_ou
 }
 
 int bn_backward(const bf16* dy, long ld_dy, const bf16* x, long ld_x, const float* stats, bf16* dx, long ld_dx, long T,
-                int C, int act, float* dgamma, float* dbeta, float* partial, float* coef, cudaStream_t s) {
+                int C, int act, float* dgamma, float* dbeta, float* partial, float* coef, cudaStream_t s, float* dx_colsum) {
   ProfScope _ps("bn_bwd", s);
   FOCR_REQUIRE(C % 8 == 0 && kThreads % (C >> 3) == 0, "bn_backward: unsupported C=%d", C);
   const int P = bn_partial_blocks(T, C);
@@ -658,8 +678,14 @@ int bn_backward(const bf16* dy, long ld_dy, const bf16* x, long ld_x, const floa
   bn_bwd_finalize_kernel<<<focr_cdiv(C, 4), 128, 0, s>>>(partial, P, C, T, coef, dgamma, dbeta);
   FOCR_LAUNCH_CHECK();
   const int rpb = kThreads / (C >> 3);
-  bn_bwd_apply_kernel<<<ew_grid(T, rpb * 2), kThreads, 0, s>>>(dy, ld_dy, x, ld_x, stats, coef, dx, ld_dx, T, C, act);
+  const int G = ew_grid(T, rpb * 2);
+  bn_bwd_apply_kernel<<<G, kThreads, 0, s>>>(dy, ld_dy, x, ld_x, stats, coef, dx, ld_dx, T, C, act,
+                                             dx_colsum ? partial : nullptr);  // `partial` is free again after the finalize
   FOCR_LAUNCH_CHECK();
+  if (dx_colsum) {
+    reduce_partials_kernel<<<focr_cdiv(C, 4), 128, 0, s>>>(partial, G, C, C, dx_colsum, 1.f);
+    FOCR_LAUNCH_CHECK();
+  }
   return FOCR_OK;
 }
 

@@ -21,8 +21,10 @@ int bn_eval_stats(const float* gamma, const float* beta, const float* rm, const 
                   float* stats, cudaStream_t s);
 int bn_apply(const bf16* x, long ld_x, const float* stats, bf16* out, long ld_out, long T, int C, int act,
              const bf16* pe, int pe_rows, const bf16* res, cudaStream_t s);
+// dx_colsum (optional, fp32 [C]): column sums of dx as stored = bias gradient of the conv feeding this BatchNorm
 int bn_backward(const bf16* dy, long ld_dy, const bf16* x, long ld_x, const float* stats, bf16* dx, long ld_dx, long T,
-                int C, int act, float* dgamma, float* dbeta, float* partial, float* coef, cudaStream_t s);
+                int C, int act, float* dgamma, float* dbeta, float* partial, float* coef, cudaStream_t s,
+                float* dx_colsum = nullptr);
 int ln_partial_blocks(long T);
 int ln_forward(const bf16* x, const float* a, const float* b, bf16* y, long T, float eps, cudaStream_t s);
 int ln_backward(const bf16* dy, const bf16* x, const float* a, bf16* dx, float* da, float* db, float* partial, long T,

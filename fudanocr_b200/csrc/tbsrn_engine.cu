@@ -540,16 +540,14 @@ int tsrn_srb_backward(const Slots& sl, void* const* prm, void* const* grd, int i
                          nullptr, 1, w, s));
   bf16 *dc2 = w.g128[1], *da1 = w.g128[2], *dc1 = w.g128[1];
   TRY(bn_backward(dr0, 64, a.c2, 64, a.st2, dc2, 64, T, 64, ACT_NONE, P<float>(grd, sl.srb(i, TS_BN2W)),
-                  P<float>(grd, sl.srb(i, TS_BN2B)), w.partial, w.coef, s));
+                  P<float>(grd, sl.srb(i, TS_BN2B)), w.partial, w.coef, s, P<float>(grd, sl.srb(i, TS_C2B))));
   if (grd[sl.srb(i, TS_C2W)]) TRY(conv3x3_wgrad(dc2, a.a1, B, 16, 64, 0, P<float>(grd, sl.srb(i, TS_C2W)), w.partial, s));
-  if (grd[sl.srb(i, TS_C2B)]) TRY(colsum(dc2, 64, T, 64, P<float>(grd, sl.srb(i, TS_C2B)), w.partial, s));
   TcGemmParams p = gp();
   p.out = da1;
   TRY(map_conv(dc2, B, 16, 64, 3, 3, q.c2d, 64, p, s));
   TRY(bn_backward(da1, 64, a.c1, 64, a.st1, dc1, 64, T, 64, ACT_MISH, P<float>(grd, sl.srb(i, TS_BN1W)),
-                  P<float>(grd, sl.srb(i, TS_BN1B)), w.partial, w.coef, s));
+                  P<float>(grd, sl.srb(i, TS_BN1B)), w.partial, w.coef, s, P<float>(grd, sl.srb(i, TS_C1B))));
   if (grd[sl.srb(i, TS_C1W)]) TRY(conv3x3_wgrad(dc1, x_in, B, 16, 64, 0, P<float>(grd, sl.srb(i, TS_C1W)), w.partial, s));
-  if (grd[sl.srb(i, TS_C1B)]) TRY(colsum(dc1, 64, T, 64, P<float>(grd, sl.srb(i, TS_C1B)), w.partial, s));
   p = gp();
   p.out = dx_out;
   p.residual = dsum;  // x also feeds gru2 directly through the sum
@@ -727,10 +725,9 @@ int backward(const Slots& sl, void* const* prm, void* const* grd, const float* x
   // block7
   bf16* dc7 = w.g64[1];
   TRY(bn_backward(dS, 64, w.c7, 64, w.st7, dc7, 64, T, 64, ACT_NONE, P<float>(grd, sl.b7_bn + BN_W),
-                  P<float>(grd, sl.b7_bn + BN_B), w.partial, w.coef, s));
+                  P<float>(grd, sl.b7_bn + BN_B), w.partial, w.coef, s, P<float>(grd, sl.b7_b)));
   const bf16* x_last = n > 0 ? w.srb[n - 1].out : w.b1;
   if (grd[sl.b7_w]) TRY(conv3x3_wgrad(dc7, x_last, B, 16, 64, 0, P<float>(grd, sl.b7_w), w.partial, s));
-  if (grd[sl.b7_b]) TRY(colsum(dc7, 64, T, 64, P<float>(grd, sl.b7_b), w.partial, s));
   bf16* dcur = w.g64[2];
   {
     TcGemmParams p = gp();
@@ -795,17 +792,15 @@ int backward(const Slots& sl, void* const* prm, void* const* grd, const float* x
     // f = [bn2(c2) | pe]: only the left 64 columns carry gradient
     bf16 *dc2 = w.g64[3], *da1 = w.g64[4];
     TRY(bn_backward(gA, 128, a.c2, 64, a.st2, dc2, 64, T, 64, ACT_NONE, P<float>(grd, sl.srb(i, S_BN2W)),
-                    P<float>(grd, sl.srb(i, S_BN2B)), w.partial, w.coef, s));
+                    P<float>(grd, sl.srb(i, S_BN2B)), w.partial, w.coef, s, P<float>(grd, sl.srb(i, S_C2B))));
     if (grd[sl.srb(i, S_C2W)]) TRY(conv3x3_wgrad(dc2, a.a1, B, 16, 64, 0, P<float>(grd, sl.srb(i, S_C2W)), w.partial, s));
-    if (grd[sl.srb(i, S_C2B)]) TRY(colsum(dc2, 64, T, 64, P<float>(grd, sl.srb(i, S_C2B)), w.partial, s));
     p = gp();
     p.out = da1;
     TRY(map_conv(dc2, B, 16, 64, 3, 3, q.c2d, 64, p, s));
     bf16* dc1 = w.g64[3];
     TRY(bn_backward(da1, 64, a.c1, 64, a.st1, dc1, 64, T, 64, ACT_MISH, P<float>(grd, sl.srb(i, S_BN1W)),
-                    P<float>(grd, sl.srb(i, S_BN1B)), w.partial, w.coef, s));
+                    P<float>(grd, sl.srb(i, S_BN1B)), w.partial, w.coef, s, P<float>(grd, sl.srb(i, S_C1B))));
     if (grd[sl.srb(i, S_C1W)]) TRY(conv3x3_wgrad(dc1, x_in, B, 16, 64, 0, P<float>(grd, sl.srb(i, S_C1W)), w.partial, s));
-    if (grd[sl.srb(i, S_C1B)]) TRY(colsum(dc1, 64, T, 64, P<float>(grd, sl.srb(i, S_C1B)), w.partial, s));
     p = gp();
     p.out = dfree;
     p.residual = dcur;  // the SRB's identity branch
