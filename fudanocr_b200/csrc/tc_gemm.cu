@@ -43,7 +43,8 @@ struct TcCfg {
   static constexpr int kOffAux = kOffCd + 2 * kCdBytes;
   static constexpr int kOffBar = kOffAux + 2 * kCdBytes;  // aux tile double-buffered like the output tile
   static constexpr int kTmemCols = 2 * BLOCK_N;  // 2 accumulator stages
-  static constexpr int kSmemBytes = kOffBar + 512 /*barriers*/ + 1024 /*align*/;
+  static constexpr int kBiasFloats = 384;  // bias vector staged in shared memory when N_total fits (every TBSRN layer)
+  static constexpr int kSmemBytes = kOffBar + 512 /*barriers*/ + kBiasFloats * 4 + 1024 /*align*/;
 };
 
 // byte offset of (row, 16-byte chunk) inside a 128-byte-swizzled 128x64 bf16 block
@@ -84,6 +85,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
   uint8_t* cd_base = smem + ((BLOCK_N == 64 && p.b_resident != 0 && p.col_mode != 0) ? Cfg::kOffAux : Cfg::kOffCd);
   uint8_t* aux_base = smem + Cfg::kOffAux;
   const bool use_aux = p.tma_out && (p.residual != nullptr || p.gate != nullptr);
+  // the epilogue adds the bias to every tile: reading it from global memory costs a long-scoreboard stall per 32-column
+  // chunk (ncu source view: the FADDs behind those loads were the top stall sites of the epilogue warps)
+  float* sbias = reinterpret_cast<float*>(smem + Cfg::kOffBar + 512);
+  const bool bias_in_smem = p.bias != nullptr && p.n_total <= Cfg::kBiasFloats;
+  if (bias_in_smem)
+    for (int i = threadIdx.x; i < p.n_total; i += kThreads) sbias[i] = p.bias[i];
+  const float* bias_src = bias_in_smem ? sbias : p.bias;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -277,7 +285,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
           if (p.bias != nullptr) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-              const float4 bb = *reinterpret_cast<const float4*>(p.bias + n0 + j);
+              const float4 bb = *reinterpret_cast<const float4*>(bias_src + n0 + j);
               v[j] += bb.x;
               v[j + 1] += bb.y;
               v[j + 2] += bb.z;
@@ -370,7 +378,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
         if (p.bias != nullptr) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            float4 bb = *reinterpret_cast<const float4*>(p.bias + n0 + j);
+            float4 bb = *reinterpret_cast<const float4*>(bias_src + n0 + j);
             v[j] += bb.x;
             v[j + 1] += bb.y;
             v[j + 2] += bb.z;
