@@ -70,6 +70,10 @@ _SIGS = {
     "focr_ctc_greedy_decode": (C.c_int, [_fp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "focr_psnr_ssim_workspace_bytes": (_sz, [_i]),
     "focr_psnr_ssim": (C.c_int, [_fp, _fp, _i, _i, _fp, _fp, _fp, _vp, _sz, _vp]),
+    "focr_ctc_loss_workspace_bytes": (_sz, [_i, _i, _i]),
+    "focr_ctc_loss": (C.c_int, [_fp, _i, _i, _i, _vp, _i, _vp, _vp, _i, _i, _i, _f, _fp, _fp, _fp, _vp, _sz, _vp]),
+    "focr_ctc_loss_status": (C.c_int, [_vp, _i, _i, _i, C.POINTER(C.c_int), _vp]),
+    "focr_resize_bicubic_normalize": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _i, _fp, _vp, _vp]),
     "focr_prof_enable": (C.c_int, [_i, C.c_char_p]),
     "focr_prof_collect": (C.c_int, [C.c_char_p, _i]),
     "focr_launch_count": (_ll, []),

@@ -139,6 +139,20 @@ int focr_crnn_forward(void* const* params, const float* images, int input_is_gra
                       size_t ws_bytes, void* stream);
 int focr_ctc_greedy_decode(const float* logits, int T, int B, int C, int* path, int* out, int* len, void* stream);
 
+/* --- CTC forward-backward over the CRNN's raw logits (north_star "CTC forward-backward"; the reference itself never calls a
+ * CTC loss - SURVEY.md D2 - so the contract is torch.nn.functional.ctc_loss(log_softmax(logits, 2), ...) on the (T, B, C)
+ * layout of STT/model/crnn/crnn.py:78-80).  logits fp32 (T,B,C); targets int64 (B,S_max) padded; lengths int64 (B), all on
+ * the DEVICE.  reduction: 0 none, 1 mean (nll_b / max(S_b,1), averaged over B), 2 sum.  nll (B) per-sample negative
+ * log-likelihood (0 for infeasible samples when zero_infinity); loss: scalar for mean / sum (may be NULL for none);
+ * d_logits (T,B,C) = grad_scale * d loss / d logits (for `none`: grad_scale * d nll_b / d logits), or NULL to skip the
+ * backward half.  focr_ctc_loss_status copies the status word of the last call (0 ok, 1 length out of range, 2 label outside
+ * [0, C)) to the host and synchronises the stream. */
+size_t focr_ctc_loss_workspace_bytes(int T, int B, int S_max);
+int focr_ctc_loss(const float* logits, int T, int B, int C, const long long* targets, int S_max, const long long* input_lengths,
+                  const long long* target_lengths, int blank, int reduction, int zero_infinity, float grad_scale, float* nll,
+                  float* loss, float* d_logits, void* ws, size_t ws_bytes, void* stream);
+int focr_ctc_loss_status(const void* ws, int T, int B, int S_max, int* status_host, void* stream);
+
 /* --- stroke-/text-focus loss: the frozen recogniser and the attention-map L1 term -------------------------------------
  * text-gestalt/loss/stroke_focus_loss.py:83-122 (StrokeFocusLoss.forward), :12-18 (to_gray_tensor),
  * text-gestalt/loss/transformer_english_decomposition.py:70-168 (ResNet encoder), :276-304 (Decoder), :343-398
@@ -180,6 +194,14 @@ int focr_focus_loss_ws_tensor(int B, int T, const char* name, long long* byte_of
 size_t focr_psnr_ssim_workspace_bytes(int B);
 int focr_psnr_ssim(const float* img1, const float* img2, int B, int channels, const float* window, float* out,
                    float* ssim_per_image, void* ws, size_t ws_bytes, void* stream);
+
+/* --- input pipeline, device side: resizeNormalize = img.resize((W,H), Image.BICUBIC) + ToTensor, applied per crop by
+ * alignCollate_real (scene-text-telescope/dataset/dataset.py:136-152, :258-270).  Bit-exact with Pillow's 8-bit resampler
+ * (antialiased bicubic a = -0.5, 22-bit fixed-point coefficients, uint8 intermediate).  pixels: packed uint8 RGB crops
+ * (h x w x 3 each); meta: DEVICE int64 [B][3] = {byte offset, h, w}; max_h / max_w: HOST upper bounds of the crop sizes;
+ * out: fp32 (B,3,out_h,out_w) in [0,1]; status: device int set to 1 if a crop exceeded the bounds. */
+int focr_resize_bicubic_normalize(const void* pixels, const long long* meta, int B, int max_h, int max_w, int out_w, int out_h,
+                                  float* out, int* status, void* stream);
 
 /* --- measurement hooks used by bench.py: CUDA-event scopes on the launching stream + launch counter ----------- */
 int focr_prof_enable(int mode /*0 off, 1 all, 2 focus*/, const char* focus_substring);

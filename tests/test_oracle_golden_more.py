@@ -116,3 +116,67 @@ def test_metrics_oracle_vs_reference_golden():
         assert torch.allclose(MO.ssim(sr, hr), rec["ssim"], rtol=1e-5)
         assert torch.allclose(MO.ssim(sr, hr, 11, False), rec["ssim_per_image"], rtol=1e-5)
     assert MO.calculate_psnr(hr, hr) == float("inf")
+
+
+def test_resize_oracle_vs_pillow_golden():
+    """numpy restatement of Pillow's 8-bit bicubic resampler (resizeNormalize, dataset.py:136-152) vs outputs recorded
+    from PIL itself (oracle/make_golden_resize.py) - bit-exact uint8; plus PIL live where importable"""
+    import numpy as np
+    from oracle import resize_oracle as R
+    g = np.load(synth.GOLDEN_DIR / "resize.npz")
+    crops = R.synth_crops(24, seed=7)
+    assert len(g.files) == 2 * len(crops)
+    for size in ((128, 32), (64, 16)):
+        for i, c in enumerate(crops):
+            assert np.array_equal(R.resize_bicubic_u8(c, size), g[f"{size[0]}x{size[1]}_{i}"]), (i, c.shape, size)
+    t = R.resize_normalize(crops[0], (128, 32))
+    assert t.shape == (3, 32, 128) and t.dtype == np.float32 and 0.0 <= t.min() and t.max() <= 1.0
+    # size-preserving resize is the identity (Pillow skips both passes)
+    assert np.array_equal(R.resize_bicubic_u8(crops[-2], (128, 32)), crops[-2])
+    # coefficient rows are normalised: each sums to 2^22 within the rounding of its taps
+    for in_size, out_size in ((200, 64), (9, 16), (33, 32), (1, 16)):
+        bounds, kk = R.precompute_coeffs(in_size, out_size)
+        assert (np.abs(kk.sum(1) - (1 << R.PRECISION_BITS)) <= kk.shape[1]).all()
+        assert (bounds[:, 0] >= 0).all() and (bounds[:, 0] + bounds[:, 1] <= in_size).all()
+    try:
+        from PIL import Image
+    except ImportError:
+        return
+    rs = np.random.RandomState(3)
+    for h, w in ((1, 1), (2, 300), (7, 13), (64, 256), (100, 31)):
+        c = rs.randint(0, 256, size=(h, w, 3)).astype(np.uint8)
+        for size in ((128, 32), (64, 16)):
+            assert np.array_equal(R.resize_bicubic_u8(c, size), np.asarray(Image.fromarray(c, "RGB").resize(size, Image.BICUBIC)))
+
+
+def test_ctc_oracle_vs_torch_golden():
+    """float64 CTC forward-backward restatement vs values recorded from torch.nn.functional.ctc_loss + autograd
+    (oracle/make_golden_ctc.py), plus closed-form cases"""
+    import numpy as np
+    from oracle import ctc_oracle as CO
+    g = np.load(synth.GOLDEN_DIR / "ctc.npz")
+    cases = {"crnn_b8": (26, 8, 37, 12, 1, True), "full_b4": (26, 4, 37, 10, 2, False), "wide_b3": (40, 3, 97, 19, 3, True),
+             "tiny_b5": (3, 5, 5, 2, 4, True)}
+    for name, (T, B, C, S, seed, ragged) in cases.items():
+        logits, targets, il, tl = CO.synth_case(T, B, C, S, seed, ragged)
+        for red in ("mean", "sum", "none"):
+            loss, _, grad = CO.ctc_loss(logits, targets, il, tl, 0, red)
+            assert np.allclose(loss, g[f"{name}/{red}/loss"], rtol=1e-10)
+            assert np.allclose(grad, g[f"{name}/{red}/grad"], rtol=1e-8, atol=1e-12)
+    # T = 1, one label: nll = -log softmax(label)
+    x = np.array([[[0.3, -1.2, 2.0]]], np.float32)
+    loss, nll, grad = CO.ctc_loss(x, np.array([[2]]), [1], [1], 0, "sum")
+    lp = CO.log_softmax(x)[0, 0]
+    assert abs(nll[0] + lp[2]) < 1e-12
+    assert np.allclose(grad[0, 0], np.exp(lp) - np.array([0, 0, 1.0]))
+    # empty target: every frame must be blank
+    x = np.random.RandomState(0).randn(5, 1, 4).astype(np.float32)
+    loss, nll, _ = CO.ctc_loss(x, np.zeros((1, 1), np.int64), [5], [0], 0, "sum")
+    assert abs(nll[0] + CO.log_softmax(x)[:, 0, 0].sum()) < 1e-12
+    # a doubled character needs a blank in between: "aa" in 2 frames is infeasible, in 3 frames has exactly one path
+    x = np.random.RandomState(1).randn(3, 1, 3).astype(np.float32)
+    _, nll2, _ = CO.ctc_loss(x[:2], np.array([[1, 1]]), [2], [2], 0, "sum")
+    assert np.isinf(nll2[0])
+    _, nll3, _ = CO.ctc_loss(x, np.array([[1, 1]]), [3], [2], 0, "sum")
+    lp = CO.log_softmax(x)[:, 0]
+    assert abs(nll3[0] + (lp[0, 1] + lp[1, 0] + lp[2, 1])) < 1e-12
