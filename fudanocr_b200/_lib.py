@@ -73,6 +73,25 @@ _SIGS = {
     "focr_ctc_loss_workspace_bytes": (_sz, [_i, _i, _i]),
     "focr_ctc_loss": (C.c_int, [_fp, _i, _i, _i, _vp, _i, _vp, _vp, _i, _i, _i, _f, _fp, _fp, _fp, _vp, _sz, _vp]),
     "focr_ctc_loss_status": (C.c_int, [_vp, _i, _i, _i, C.POINTER(C.c_int), _vp]),
+    "focr_mha_small_fwd": (C.c_int, [_vp, _l, _vp, _l, _vp, _l, _vp, _l, _fp, _i, _i, _i, _i, _i, _i, _f, _u, _u, _vp]),
+    "focr_mha_small_bwd": (C.c_int, [_vp, _l, _vp, _l, _vp, _l, _vp, _l, _fp, _vp, _l, _vp, _l, _vp, _l, _i, _i, _i, _i, _i, _i,
+                                     _f, _vp]),
+    "focr_layernorm_wide_fwd": (C.c_int, [_vp, _vp, _fp, _fp, _vp, _vp, _l, _i, _f, _vp]),
+    "focr_layernorm_wide_workspace_bytes": (_sz, [_i]),
+    "focr_layernorm_wide_bwd": (C.c_int, [_vp, _vp, _fp, _vp, _fp, _fp, _l, _i, _f, _vp, _sz, _vp]),
+    "focr_text_embed_fwd": (C.c_int, [_vp, _fp, _i, _i, _i, _i, _l, _vp, _f, _u, _u, _vp, _vp]),
+    "focr_text_embed_bwd": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _fp, _vp]),
+    "focr_packed_ce_workspace_bytes": (_sz, [_i]),
+    "focr_packed_ce": (C.c_int, [_fp, _l, _i, _i, _i, _vp, _vp, _f, _fp, _vp, _l, _vp, _sz, _vp]),
+    "focr_dropout": (C.c_int, [_vp, _vp, _l, _f, _u, _u, _vp]),
+    "focr_add_relu": (C.c_int, [_vp, _vp, _vp, _l, _vp]),
+    "focr_relu_bwd": (C.c_int, [_vp, _vp, _vp, _l, _vp]),
+    "focr_maxpool2x2_fwd": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "focr_maxpool2x2_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "focr_adadelta_step": (C.c_int, [_vp, _i, _f, _f, _f, _f, _f, _vp]),
+    "focr_conv3x3_gemm_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "focr_conv3x3_gemm_fwd": (C.c_int, [_vp, _fp, _fp, _fp, _vp, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "focr_conv3x3_gemm_wgrad": (C.c_int, [_vp, _vp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
     "focr_resize_bicubic_normalize": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _i, _fp, _vp, _vp]),
     "focr_prof_enable": (C.c_int, [_i, C.c_char_p]),
     "focr_prof_collect": (C.c_int, [C.c_char_p, _i]),

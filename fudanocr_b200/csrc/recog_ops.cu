@@ -1,0 +1,815 @@
+// Building blocks of the TRAINABLE ResNet + Transformer recognisers:
+//   stroke-level-decomposition/model/transformer.py  (Decoder :289-317, attention :227-241, LayerNorm :244-254,
+//   Embeddings :277-286, PositionalEncoding :168-186, Generator :266-274, BasicBlock :43-73) and train.py:63-77
+//   (CrossEntropyLoss over the packed valid positions, Adadelta(lr 1, rho 0.9)); image-ids-CTR/model/transformer.py and
+//   train.py:63-90 use the same pieces with weight decay 1e-4.
+// Everything here is small next to the 38-conv encoder (which runs on the tcgen05 GEMM): the decoder sees <= B*32 text
+// positions.  The kernels are plain SIMT with fp32 math, one warp per row / CTA per (sample, head), every reduction in a
+// fixed order (bit-reproducible), no atomics.
+//   * decoder attention, masked-self or cross, any d_k <= 256 (h = 4, d_k = 256 here): forward keeps the post-dropout map
+//     the reference returns as 'map'; backward recomputes the softmax and takes the keep mask from the stored map
+//   * the reference's LayerNorm (unbiased std, eps added to the std) for feature widths 512 / 1024 with parameter gradients
+//   * embedding * sqrt(d) concatenated with the (dropped-out) sinusoid table, and its gradient
+//   * cross entropy over the positions t < length[b], mean over the packed total, with the logits gradient
+//   * element-wise dropout, add + ReLU and its backward, 2x2 max-pool wrappers, Adadelta over a chunk table
+#include "kernels.cuh"
+
+#include <cmath>
+#include <string.h>
+
+namespace {
+
+constexpr float kNegInf = -INFINITY;
+
+__device__ __forceinline__ bool keep16(uint32_t key, unsigned long long e, uint32_t th16) {
+  const uint32_t h = drop_hash32(key, (uint32_t)(e >> 1));
+  const uint32_t lane = (e & 1) ? (h >> 16) : (h & 0xFFFFu);
+  return lane >= th16;
+}
+
+__device__ __forceinline__ float ldbf(const bf16* p) { return __bfloat162float(*p); }
+
+// ------------------------------------------------------------------------------------------------------------------
+// decoder attention.  q rows (b*Tq + i) with leading dimension ld_q, head h at columns [h*dk, (h+1)*dk); k / v rows
+// (b*Tk + j).  One CTA per (b, head), 8 warps.  smem: S[Tq][Tk] fp32 (+ second array in the backward).
+// ------------------------------------------------------------------------------------------------------------------
+template <int DKV>  // d_k / 32 elements per lane
+__device__ __forceinline__ void load_row(const bf16* p, int lane, float (&r)[DKV]) {
+#pragma unroll
+  for (int v = 0; v < DKV; ++v) r[v] = ldbf(p + v * 32 + lane);
+}
+
+template <int DKV>
+__device__ void attn_probs(const bf16* __restrict__ q, long ld_q, const bf16* __restrict__ k, long ld_k, int Tq, int Tk,
+                           int causal, float scale, float* __restrict__ S) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int i = warp; i < Tq; i += nw) {
+    float qr[DKV];
+    load_row<DKV>(q + (long)i * ld_q, lane, qr);
+    float* s = S + (long)i * Tk;
+    for (int j = 0; j < Tk; ++j) {
+      float kr[DKV];
+      load_row<DKV>(k + (long)j * ld_k, lane, kr);
+      float a = 0.f;
+#pragma unroll
+      for (int v = 0; v < DKV; ++v) a += qr[v] * kr[v];
+      a = warp_sum(a);
+      if (lane == 0) s[j] = (causal && j > i) ? kNegInf : a * scale;
+    }
+    __syncwarp();
+    float m = kNegInf;
+    for (int j = lane; j < Tk; j += 32) m = fmaxf(m, s[j]);
+    m = warp_max(m);
+    float sum = 0.f;
+    for (int j = lane; j < Tk; j += 32) {
+      const float e = expf(s[j] - m);
+      s[j] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.f / sum;
+    for (int j = lane; j < Tk; j += 32) s[j] *= inv;
+  }
+}
+
+template <int DKV>
+__global__ void __launch_bounds__(256) mha_small_fwd_kernel(const bf16* __restrict__ q, long ld_q, const bf16* __restrict__ k,
+                                                            long ld_k, const bf16* __restrict__ v, long ld_v,
+                                                            bf16* __restrict__ out, long ld_o, float* __restrict__ map,
+                                                            int H, int Tq, int Tk, int causal, float scale, uint32_t key,
+                                                            uint32_t th16, float keep_scale) {
+  extern __shared__ float sm_att[];
+  float* S = sm_att;
+  const int b = blockIdx.x / H, h = blockIdx.x % H;
+  constexpr int dk = DKV * 32;
+  q += (long)b * Tq * ld_q + h * dk;
+  k += (long)b * Tk * ld_k + h * dk;
+  v += (long)b * Tk * ld_v + h * dk;
+  out += (long)b * Tq * ld_o + h * dk;
+  attn_probs<DKV>(q, ld_q, k, ld_k, Tq, Tk, causal, scale, S);
+  __syncthreads();
+  // dropout on P (transformer.py:238-240); the dropped-out map is what the reference returns and multiplies into V
+  float* mp = map + (long)blockIdx.x * Tq * Tk;
+  for (int e = threadIdx.x; e < Tq * Tk; e += blockDim.x) {
+    float p = S[e];
+    if (th16) p = keep16(key, (unsigned long long)blockIdx.x * Tq * Tk + e, th16) ? p * keep_scale : 0.f;
+    S[e] = p;
+    mp[e] = p;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int i = warp; i < Tq; i += nw) {
+    float acc[DKV];
+#pragma unroll
+    for (int c = 0; c < DKV; ++c) acc[c] = 0.f;
+    const float* s = S + (long)i * Tk;
+    for (int j = 0; j < Tk; ++j) {
+      const float p = s[j];
+      if (p == 0.f) continue;  // warp-uniform (s[j] is a broadcast read)
+      float vr[DKV];
+      load_row<DKV>(v + (long)j * ld_v, lane, vr);
+#pragma unroll
+      for (int c = 0; c < DKV; ++c) acc[c] += p * vr[c];
+    }
+#pragma unroll
+    for (int c = 0; c < DKV; ++c) out[(long)i * ld_o + c * 32 + lane] = __float2bfloat16(acc[c]);
+  }
+}
+
+template <int DKV>
+__global__ void __launch_bounds__(256) mha_small_bwd_kernel(const bf16* __restrict__ q, long ld_q, const bf16* __restrict__ k,
+                                                            long ld_k, const bf16* __restrict__ v, long ld_v,
+                                                            const bf16* __restrict__ d_out, long ld_o,
+                                                            const float* __restrict__ map, bf16* __restrict__ dq, long ld_dq,
+                                                            bf16* __restrict__ dk_, long ld_dk, bf16* __restrict__ dv,
+                                                            long ld_dv, int H, int Tq, int Tk, int causal, float scale,
+                                                            float keep_scale) {
+  extern __shared__ float sm_att[];
+  float* P = sm_att;                  // [Tq][Tk] softmax probabilities (pre-dropout), recomputed
+  float* D = sm_att + (long)Tq * Tk;  // [Tq][Tk] dP, then dS
+  const int b = blockIdx.x / H, h = blockIdx.x % H;
+  constexpr int dk = DKV * 32;
+  q += (long)b * Tq * ld_q + h * dk;
+  k += (long)b * Tk * ld_k + h * dk;
+  v += (long)b * Tk * ld_v + h * dk;
+  d_out += (long)b * Tq * ld_o + h * dk;
+  dq += (long)b * Tq * ld_dq + h * dk;
+  dk_ += (long)b * Tk * ld_dk + h * dk;
+  dv += (long)b * Tk * ld_dv + h * dk;
+  const float* mp = map + (long)blockIdx.x * Tq * Tk;
+  attn_probs<DKV>(q, ld_q, k, ld_k, Tq, Tk, causal, scale, P);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  // dP = keep ? (dO . v_j) * keep_scale : 0 ; then dS = P (dP - sum_j P dP) * scale   (rows are warp-private)
+  for (int i = warp; i < Tq; i += nw) {
+    float g[DKV];
+    load_row<DKV>(d_out + (long)i * ld_o, lane, g);
+    float* d = D + (long)i * Tk;
+    const float* p = P + (long)i * Tk;
+    const float* m = mp + (long)i * Tk;
+    for (int j = 0; j < Tk; ++j) {
+      float a = 0.f;
+      if (m[j] != 0.f) {  // warp-uniform
+        float vr[DKV];
+        load_row<DKV>(v + (long)j * ld_v, lane, vr);
+#pragma unroll
+        for (int c = 0; c < DKV; ++c) a += g[c] * vr[c];
+        a = warp_sum(a) * keep_scale;
+      }
+      if (lane == 0) d[j] = a;
+    }
+    __syncwarp();
+    float delta = 0.f;
+    for (int j = lane; j < Tk; j += 32) delta += p[j] * d[j];
+    delta = warp_sum(delta);
+    for (int j = lane; j < Tk; j += 32) d[j] = p[j] * (d[j] - delta) * scale;
+    __syncwarp();
+    // dq_i = sum_j dS_ij k_j
+    float acc[DKV];
+#pragma unroll
+    for (int c = 0; c < DKV; ++c) acc[c] = 0.f;
+    for (int j = 0; j < Tk; ++j) {
+      const float ds = d[j];
+      if (ds == 0.f) continue;
+      float kr[DKV];
+      load_row<DKV>(k + (long)j * ld_k, lane, kr);
+#pragma unroll
+      for (int c = 0; c < DKV; ++c) acc[c] += ds * kr[c];
+    }
+#pragma unroll
+    for (int c = 0; c < DKV; ++c) dq[(long)i * ld_dq + c * 32 + lane] = __float2bfloat16(acc[c]);
+  }
+  __syncthreads();
+  // dk_j = sum_i dS_ij q_i ; dv_j = sum_i map_ij dO_i
+  for (int j = warp; j < Tk; j += nw) {
+    float ak[DKV], av[DKV];
+#pragma unroll
+    for (int c = 0; c < DKV; ++c) ak[c] = av[c] = 0.f;
+    for (int i = 0; i < Tq; ++i) {
+      const float ds = D[(long)i * Tk + j];
+      const float pm = mp[(long)i * Tk + j];
+      if (ds != 0.f) {
+        float qr[DKV];
+        load_row<DKV>(q + (long)i * ld_q, lane, qr);
+#pragma unroll
+        for (int c = 0; c < DKV; ++c) ak[c] += ds * qr[c];
+      }
+      if (pm != 0.f) {
+        float g[DKV];
+        load_row<DKV>(d_out + (long)i * ld_o, lane, g);
+#pragma unroll
+        for (int c = 0; c < DKV; ++c) av[c] += pm * g[c];
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < DKV; ++c) {
+      dk_[(long)j * ld_dk + c * 32 + lane] = __float2bfloat16(ak[c]);
+      dv[(long)j * ld_dv + c * 32 + lane] = __float2bfloat16(av[c]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// LayerNorm of the reference (transformer.py:244-254): a (x - mean) / (std_unbiased + eps) + b over C = NV*256 features.
+// One warp per row; lane l owns the 8-element vectors at columns v*256 + l*8.
+// ------------------------------------------------------------------------------------------------------------------
+template <int NV>
+__device__ __forceinline__ void ld_row_vec(const bf16* row, int lane, float (&x)[NV * 8]) {
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const uint4 u = *reinterpret_cast<const uint4*>(row + v * 256 + lane * 8);
+    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    x[v * 8 + 0] = a.x; x[v * 8 + 1] = a.y; x[v * 8 + 2] = b.x; x[v * 8 + 3] = b.y;
+    x[v * 8 + 4] = c.x; x[v * 8 + 5] = c.y; x[v * 8 + 6] = d.x; x[v * 8 + 7] = d.y;
+  }
+}
+template <int NV>
+__device__ __forceinline__ void st_row_vec(bf16* row, int lane, const float (&x)[NV * 8]) {
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    uint4 u;
+    u.x = pack_bf16x2(x[v * 8 + 0], x[v * 8 + 1]);
+    u.y = pack_bf16x2(x[v * 8 + 2], x[v * 8 + 3]);
+    u.z = pack_bf16x2(x[v * 8 + 4], x[v * 8 + 5]);
+    u.w = pack_bf16x2(x[v * 8 + 6], x[v * 8 + 7]);
+    *reinterpret_cast<uint4*>(row + v * 256 + lane * 8) = u;
+  }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(256) lnw_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ res,
+                                                      const float* __restrict__ a, const float* __restrict__ bb,
+                                                      bf16* __restrict__ sum_out, bf16* __restrict__ y, long T, float eps) {
+  constexpr int C = NV * 256;
+  const int lane = threadIdx.x & 31;
+  const long row0 = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long stride = (long)gridDim.x * (blockDim.x >> 5);
+  for (long r = row0; r < T; r += stride) {
+    float xv[NV * 8];
+    ld_row_vec<NV>(x + r * C, lane, xv);
+    if (res) {  // y = LN(x + res); the bf16-rounded sum is what the backward sees
+      float rv[NV * 8];
+      ld_row_vec<NV>(res + r * C, lane, rv);
+#pragma unroll
+      for (int i = 0; i < NV * 8; ++i) xv[i] = __bfloat162float(__float2bfloat16(xv[i] + rv[i]));
+      if (sum_out) st_row_vec<NV>(sum_out + r * C, lane, xv);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV * 8; ++i) s += xv[i];
+    const float mean = warp_sum(s) * (1.f / C);
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV * 8; ++i) {
+      xv[i] -= mean;
+      ss += xv[i] * xv[i];
+    }
+    const float sd = sqrtf(warp_sum(ss) * (1.f / (C - 1)));
+    const float rr = 1.f / (sd + eps);
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int c = v * 256 + lane * 8 + e;
+        xv[v * 8 + e] = a[c] * xv[v * 8 + e] * rr + bb[c];
+      }
+    st_row_vec<NV>(y + r * C, lane, xv);
+  }
+}
+
+// dx and per-CTA partial sums of (da, db): partial[cta][2][C]
+template <int NV>
+__global__ void __launch_bounds__(256) lnw_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+                                                      const float* __restrict__ a, bf16* __restrict__ dx,
+                                                      float* __restrict__ partial, long T, float eps) {
+  constexpr int C = NV * 256;
+  __shared__ float red[8][64];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long row0 = (long)blockIdx.x * 8 + warp;
+  const long stride = (long)gridDim.x * 8;
+  float da[NV * 8], db[NV * 8];
+#pragma unroll
+  for (int i = 0; i < NV * 8; ++i) da[i] = db[i] = 0.f;
+  for (long r = row0; r < T; r += stride) {
+    float xv[NV * 8], g[NV * 8];
+    ld_row_vec<NV>(x + r * C, lane, xv);
+    ld_row_vec<NV>(dy + r * C, lane, g);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV * 8; ++i) s += xv[i];
+    const float mean = warp_sum(s) * (1.f / C);
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV * 8; ++i) {
+      xv[i] -= mean;
+      ss += xv[i] * xv[i];
+    }
+    const float sd = sqrtf(warp_sum(ss) * (1.f / (C - 1)));
+    const float rr = 1.f / (sd + eps);
+    float sg = 0.f, sgx = 0.f;
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int i = v * 8 + e;
+        const float gy = g[i];
+        da[i] += gy * xv[i] * rr;
+        db[i] += gy;
+        g[i] = gy * a[v * 256 + lane * 8 + e];  // d / d xhat
+        sg += g[i];
+        sgx += g[i] * xv[i];
+      }
+    sg = warp_sum(sg) * (1.f / C);
+    sgx = warp_sum(sgx);
+    // dx_i = r (g_i - mean g) - r^2 (sum_j g_j xc_j) / ((C-1) s) xc_i ; s = 0 only for a constant row (then xc = 0)
+    const float coef = sd > 0.f ? rr * rr * sgx / ((float)(C - 1) * sd) : 0.f;
+#pragma unroll
+    for (int i = 0; i < NV * 8; ++i) g[i] = rr * (g[i] - sg) - coef * xv[i];
+    st_row_vec<NV>(dx + r * C, lane, g);
+  }
+  // cross-warp reduction of the column sums, 64 columns at a time
+  float* out = partial + (long)blockIdx.x * 2 * C;
+  for (int which = 0; which < 2; ++which) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      for (int half = 0; half < 4; ++half) {  // lanes [8*half, 8*half+8) of this vector: 64 columns
+        __syncthreads();
+        if ((lane >> 3) == half) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) red[warp][(lane & 7) * 8 + e] = which ? db[v * 8 + e] : da[v * 8 + e];
+        }
+        __syncthreads();
+        if (threadIdx.x < 64) {
+          float t = 0.f;
+#pragma unroll
+          for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+          out[(long)which * C + v * 256 + half * 64 + threadIdx.x] = t;
+        }
+      }
+    }
+  }
+}
+
+__global__ void lnw_reduce_kernel(const float* __restrict__ partial, int P, int C, float* __restrict__ da,
+                                  float* __restrict__ db) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * C) return;
+  double s = 0.0;
+  for (int p = 0; p < P; ++p) s += partial[(long)p * 2 * C + i];
+  if (i < C) da[i] = (float)s;
+  else db[i - C] = (float)s;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// text embedding (transformer.py:277-286, :168-186, :346-348): out[b,t] = [ lut[idx] * sqrt(E) | dropout(pe[t]) ], E = 512
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void text_embed_pe_kernel(const long long* __restrict__ idx, const float* __restrict__ lut, int vocab, int E,
+                                     long rows, int T, long rows_pad, bf16* __restrict__ out, uint32_t key, uint32_t th16,
+                                     float keep_scale, int* __restrict__ status) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows_pad * 2 * E) return;
+  const long r = i / (2 * E);
+  const int c = (int)(i - r * 2 * E);
+  float val = 0.f;
+  if (r < rows) {
+    if (c < E) {
+      long long t = idx[r];
+      if (t < 0 || t >= vocab) {
+        atomicExch(status, 2);
+        t = 0;
+      }
+      val = lut[t * E + c] * sqrtf((float)E);
+    } else {
+      const int pos = (int)(r % T), cc = c - E;
+      const float div = expf((float)(cc & ~1) * (-logf(10000.f) / (float)E));
+      const float ang = (float)pos * div;
+      val = (cc & 1) ? cosf(ang) : sinf(ang);
+      if (th16) val = keep16(key, (unsigned long long)r * E + cc, th16) ? val * keep_scale : 0.f;
+    }
+  }
+  out[i] = __float2bfloat16(val);
+}
+
+// d_lut[v][c] = sqrt(E) * sum over rows with idx == v of d_out[row][c]   (one thread per (v, c), fixed order)
+__global__ void text_embed_bwd_kernel(const long long* __restrict__ idx, const bf16* __restrict__ d_out, int vocab, int E,
+                                      long rows, float* __restrict__ d_lut) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= vocab * E) return;
+  const int v = i / E, c = i - v * E;
+  float s = 0.f;
+  for (long r = 0; r < rows; ++r)
+    if (idx[r] == v) s += ldbf(d_out + r * 2 * E + c);
+  d_lut[i] = s * sqrtf((float)E);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// cross entropy over the valid positions (transformer.py:361-373 packs rows t < length[b]; train.py:71 takes the mean)
+// logits fp32 [(b*T + t)][ld]; gt packed int64 (sum of lengths).  One CTA per sample, one warp per position.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) packed_ce_kernel(const float* __restrict__ logits, long ld, int B, int T, int C,
+                                                        const long long* __restrict__ length, const long long* __restrict__ gt,
+                                                        float gscale, float* __restrict__ partial, bf16* __restrict__ d_logits,
+                                                        long ld_d, int* __restrict__ status) {
+  __shared__ float wl[4];
+  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  long long off = 0, total = 0;
+  for (int i = 0; i < B; ++i) {
+    long long l = length[i];
+    l = l < 0 ? 0 : (l > T ? T : l);
+    if (i < b) off += l;
+    total += l;
+  }
+  long long len = length[b];
+  if (len < 0 || len > T) {
+    if (threadIdx.x == 0) atomicExch(status, 1);
+    len = len < 0 ? 0 : T;
+  }
+  const float inv_total = total > 0 ? 1.f / (float)total : 0.f;
+  float loss = 0.f;
+  for (int t = warp; t < T; t += 4) {
+    const float* row = logits + ((long)b * T + t) * ld;
+    bf16* drow = d_logits ? d_logits + ((long)b * T + t) * ld_d : nullptr;
+    if (t >= len) {
+      if (drow)
+        for (int c = lane; c < ld_d; c += 32) drow[c] = __float2bfloat16(0.f);
+      continue;
+    }
+    long long g = gt[off + t];
+    if (g < 0 || g >= C) {
+      if (lane == 0) atomicExch(status, 2);
+      g = 0;
+    }
+    float m = kNegInf;
+    for (int c = lane; c < C; c += 32) m = fmaxf(m, row[c]);
+    m = warp_max(m);
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += expf(row[c] - m);
+    s = warp_sum(s);
+    const float lse = m + logf(s);
+    loss += lse - row[g];
+    if (drow)
+      for (int c = lane; c < ld_d; c += 32) {
+        float d = 0.f;
+        if (c < C) d = (expf(row[c] - lse) - (c == (int)g ? 1.f : 0.f)) * gscale * inv_total;
+        drow[c] = __float2bfloat16(d);
+      }
+  }
+  if (lane == 0) wl[warp] = loss;
+  __syncthreads();
+  if (threadIdx.x == 0) partial[b] = (wl[0] + wl[1] + wl[2] + wl[3]) * inv_total;
+}
+
+__global__ void sum_partials_kernel(const float* __restrict__ partial, int n, float* __restrict__ out) {
+  __shared__ double red[256];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) s += partial[i];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = (float)red[0];
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// element-wise pieces
+// ------------------------------------------------------------------------------------------------------------------
+// y = keep ? x * keep_scale : 0 with the mask regenerated from (key, element index): the same call is its own backward
+__global__ void dropout_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, long n, uint32_t key, uint32_t th16,
+                               float keep_scale) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  y[i] = keep16(key, (unsigned long long)i, th16) ? __float2bfloat16(ldbf(x + i) * keep_scale) : __float2bfloat16(0.f);
+}
+// BasicBlock tail (transformer.py:69-71): y = relu(a + b), 8 elements per thread
+__global__ void add_relu_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ y, long n8) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  const uint4 ua = a[i], ub = b[i];
+  const uint32_t* pa = &ua.x;
+  const uint32_t* pb = &ub.x;
+  uint4 o;
+  uint32_t* po = &o.x;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 fa = unpack_bf16x2(pa[e]), fb = unpack_bf16x2(pb[e]);
+    po[e] = pack_bf16x2(fmaxf(fa.x + fb.x, 0.f), fmaxf(fa.y + fb.y, 0.f));
+  }
+  y[i] = o;
+}
+// dx = y > 0 ? dy : 0 (gradient of both summands of add_relu, and of a plain ReLU given its output)
+__global__ void relu_bwd_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ y, uint4* __restrict__ dx, long n8) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  const uint4 ug = dy[i], uy = y[i];
+  const uint32_t* pg = &ug.x;
+  const uint32_t* py = &uy.x;
+  uint4 o;
+  uint32_t* po = &o.x;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 fg = unpack_bf16x2(pg[e]), fy = unpack_bf16x2(py[e]);
+    po[e] = pack_bf16x2(fy.x > 0.f ? fg.x : 0.f, fy.y > 0.f ? fg.y : 0.f);
+  }
+  dx[i] = o;
+}
+
+// Adadelta (torch.optim.Adadelta; stroke-level-decomposition/train.py:32-36 lr 1, rho 0.9; image-ids-CTR adds weight decay)
+struct AdaChunk {
+  float* p;
+  const float* g;
+  float* sq;
+  float* acc;
+  long long n;
+};
+__global__ void __launch_bounds__(256) adadelta_kernel(const AdaChunk* __restrict__ chunks, float gscale, float lr, float rho,
+                                                       float eps, float wd) {
+  const AdaChunk c = chunks[blockIdx.x];
+  for (long long i = threadIdx.x; i < c.n; i += 256) {
+    float w = c.p[i];
+    float g = c.g[i] * gscale;
+    if (wd != 0.f) g += wd * w;
+    const float sq = rho * c.sq[i] + (1.f - rho) * g * g;
+    const float acc = c.acc[i];
+    const float delta = sqrtf(acc + eps) / sqrtf(sq + eps) * g;
+    c.sq[i] = sq;
+    c.acc[i] = rho * acc + (1.f - rho) * delta * delta;
+    c.p[i] = w - lr * delta;
+  }
+}
+
+int egrid(long n, int per) { return (int)((n + per - 1) / per); }
+
+template <int DKV>
+int launch_mha_fwd(const bf16* q, long ld_q, const bf16* k, long ld_k, const bf16* v, long ld_v, bf16* out, long ld_o, float* map,
+                   int B, int H, int Tq, int Tk, int causal, float scale, uint32_t key, uint32_t th16, float ks, size_t smem,
+                   cudaStream_t s) {
+  FOCR_CHECK_CUDA(cudaFuncSetAttribute(mha_small_fwd_kernel<DKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  mha_small_fwd_kernel<DKV><<<B * H, 256, smem, s>>>(q, ld_q, k, ld_k, v, ld_v, out, ld_o, map, H, Tq, Tk, causal, scale, key,
+                                                      th16, ks);
+  FOCR_LAUNCH_CHECK();
+  return FOCR_OK;
+}
+template <int DKV>
+int launch_mha_bwd(const bf16* q, long ld_q, const bf16* k, long ld_k, const bf16* v, long ld_v, const bf16* d_out, long ld_o,
+                   const float* map, bf16* dq, long ld_dq, bf16* dk, long ld_dk, bf16* dv, long ld_dv, int B, int H, int Tq, int Tk,
+                   int causal, float scale, float ks, size_t smem, cudaStream_t s) {
+  FOCR_CHECK_CUDA(cudaFuncSetAttribute(mha_small_bwd_kernel<DKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  mha_small_bwd_kernel<DKV><<<B * H, 256, smem, s>>>(q, ld_q, k, ld_k, v, ld_v, d_out, ld_o, map, dq, ld_dq, dk, ld_dk, dv, ld_dv,
+                                                      H, Tq, Tk, causal, scale, ks);
+  FOCR_LAUNCH_CHECK();
+  return FOCR_OK;
+}
+
+uint32_t th16_of(float p) {
+  if (p <= 0.f) return 0;
+  const long t = (long)(p * 65536.0 + 0.5);
+  return (uint32_t)(t > 65535 ? 65535 : t);
+}
+
+}  // namespace
+
+extern "C" {
+
+// decoder attention core.  q (B*Tq, ld_q) / k, v (B*Tk, ld_k / ld_v) / out (B*Tq, ld_o) bf16, head h at columns h*d_k;
+// map fp32 (B, H, Tq, Tk) = dropout(softmax(q k^T / sqrt(d_k) [+ causal mask])) - the tensor the reference returns.
+int focr_mha_small_fwd(const void* q, long ld_q, const void* k, long ld_k, const void* v, long ld_v, void* out, long ld_o,
+                       float* map, int B, int H, int d_k, int Tq, int Tk, int causal, float p_drop, unsigned seed,
+                       unsigned stream_id, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  FOCR_REQUIRE(q && k && v && out && map, "mha_small_fwd: null pointer");
+  FOCR_REQUIRE(B >= 1 && H >= 1 && Tq >= 1 && Tk >= 1, "mha_small_fwd: B=%d H=%d Tq=%d Tk=%d", B, H, Tq, Tk);
+  FOCR_REQUIRE(d_k == 64 || d_k == 128 || d_k == 256, "mha_small_fwd: d_k %d (64, 128 or 256)", d_k);
+  FOCR_REQUIRE(!causal || Tq == Tk, "mha_small_fwd: the causal mask needs Tq == Tk");
+  FOCR_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "mha_small_fwd: p_drop %f", p_drop);
+  const size_t smem = (size_t)Tq * Tk * 4;
+  FOCR_REQUIRE(smem <= 200 * 1024, "mha_small_fwd: Tq*Tk = %d*%d does not fit shared memory", Tq, Tk);
+  ProfScope _ps("mha_small_fwd", s);
+  const uint32_t th = th16_of(p_drop);
+  const float ks = 65536.f / (65536.f - (float)th);
+  const float scale = 1.f / sqrtf((float)d_k);
+  const uint32_t key = drop_key(seed, stream_id);
+  const bf16 *qq = (const bf16*)q, *kk = (const bf16*)k, *vv = (const bf16*)v;
+  if (d_k == 64) return launch_mha_fwd<2>(qq, ld_q, kk, ld_k, vv, ld_v, (bf16*)out, ld_o, map, B, H, Tq, Tk, causal, scale, key, th, ks, smem, s);
+  if (d_k == 128) return launch_mha_fwd<4>(qq, ld_q, kk, ld_k, vv, ld_v, (bf16*)out, ld_o, map, B, H, Tq, Tk, causal, scale, key, th, ks, smem, s);
+  return launch_mha_fwd<8>(qq, ld_q, kk, ld_k, vv, ld_v, (bf16*)out, ld_o, map, B, H, Tq, Tk, causal, scale, key, th, ks, smem, s);
+}
+
+// gradients of the above w.r.t. q, k, v given d_out and the stored map (its zeros are the dropped positions)
+int focr_mha_small_bwd(const void* q, long ld_q, const void* k, long ld_k, const void* v, long ld_v, const void* d_out, long ld_o,
+                       const float* map, void* dq, long ld_dq, void* dk, long ld_dk, void* dv, long ld_dv, int B, int H, int d_k,
+                       int Tq, int Tk, int causal, float p_drop, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  FOCR_REQUIRE(q && k && v && d_out && map && dq && dk && dv, "mha_small_bwd: null pointer");
+  FOCR_REQUIRE(B >= 1 && H >= 1 && Tq >= 1 && Tk >= 1, "mha_small_bwd: B=%d H=%d Tq=%d Tk=%d", B, H, Tq, Tk);
+  FOCR_REQUIRE(d_k == 64 || d_k == 128 || d_k == 256, "mha_small_bwd: d_k %d (64, 128 or 256)", d_k);
+  FOCR_REQUIRE(!causal || Tq == Tk, "mha_small_bwd: the causal mask needs Tq == Tk");
+  const size_t smem = (size_t)Tq * Tk * 8;
+  FOCR_REQUIRE(smem <= 200 * 1024, "mha_small_bwd: Tq*Tk = %d*%d does not fit shared memory", Tq, Tk);
+  ProfScope _ps("mha_small_bwd", s);
+  const uint32_t th = th16_of(p_drop);
+  const float ks = 65536.f / (65536.f - (float)th);
+  const float scale = 1.f / sqrtf((float)d_k);
+  const bf16 *qq = (const bf16*)q, *kk = (const bf16*)k, *vv = (const bf16*)v, *gg = (const bf16*)d_out;
+  if (d_k == 64) return launch_mha_bwd<2>(qq, ld_q, kk, ld_k, vv, ld_v, gg, ld_o, map, (bf16*)dq, ld_dq, (bf16*)dk, ld_dk, (bf16*)dv, ld_dv, B, H, Tq, Tk, causal, scale, ks, smem, s);
+  if (d_k == 128) return launch_mha_bwd<4>(qq, ld_q, kk, ld_k, vv, ld_v, gg, ld_o, map, (bf16*)dq, ld_dq, (bf16*)dk, ld_dk, (bf16*)dv, ld_dv, B, H, Tq, Tk, causal, scale, ks, smem, s);
+  return launch_mha_bwd<8>(qq, ld_q, kk, ld_k, vv, ld_v, gg, ld_o, map, (bf16*)dq, ld_dq, (bf16*)dk, ld_dk, (bf16*)dv, ld_dv, B, H, Tq, Tk, causal, scale, ks, smem, s);
+}
+
+// y = LN(x [+ res]) over C in {512, 1024} features; sum_out (optional) receives x + res (the tensor the backward needs)
+int focr_layernorm_wide_fwd(const void* x, const void* res, const float* a, const float* b, void* sum_out, void* y, long T, int C,
+                            float eps, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  FOCR_REQUIRE(x && a && b && y && T >= 1, "layernorm_wide_fwd: null pointer / T=%ld", T);
+  FOCR_REQUIRE(C == 512 || C == 1024, "layernorm_wide_fwd: C %d (512 or 1024)", C);
+  ProfScope _ps("ln_wide_fwd", s);
+  long g = (T + 7) / 8;
+  if (g > 148L * 8) g = 148L * 8;
+  if (C == 512)
+    lnw_fwd_kernel<2><<<(int)g, 256, 0, s>>>((const bf16*)x, (const bf16*)res, a, b, (bf16*)sum_out, (bf16*)y, T, eps);
+  else
+    lnw_fwd_kernel<4><<<(int)g, 256, 0, s>>>((const bf16*)x, (const bf16*)res, a, b, (bf16*)sum_out, (bf16*)y, T, eps);
+  FOCR_LAUNCH_CHECK();
+  return FOCR_OK;
+}
+
+size_t focr_layernorm_wide_workspace_bytes(int C) { return (size_t)148 * 2 * 2 * C * sizeof(float); }
+
+int focr_layernorm_wide_bwd(const void* dy, const void* x, const float* a, void* dx, float* da, float* db, long T, int C, float eps,
+                            void* ws, size_t ws_bytes, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  FOCR_REQUIRE(dy && x && a && dx && da && db && ws && T >= 1, "layernorm_wide_bwd: null pointer / T=%ld", T);
+  FOCR_REQUIRE(C == 512 || C == 1024, "layernorm_wide_bwd: C %d (512 or 1024)", C);
+  FOCR_REQUIRE(ws_bytes >= focr_layernorm_wide_workspace_bytes(C), "layernorm_wide_bwd: workspace too small");
+  ProfScope _ps("ln_wide_bwd", s);
+  long g = (T + 7) / 8;
+  if (g > 148L * 2) g = 148L * 2;
+  float* partial = (float*)ws;
+  if (C == 512)
+    lnw_bwd_kernel<2><<<(int)g, 256, 0, s>>>((const bf16*)dy, (const bf16*)x, a, (bf16*)dx, partial, T, eps);
+  else
+    lnw_bwd_kernel<4><<<(int)g, 256, 0, s>>>((const bf16*)dy, (const bf16*)x, a, (bf16*)dx, partial, T, eps);
+  FOCR_LAUNCH_CHECK();
+  lnw_reduce_kernel<<<egrid(2 * C, 256), 256, 0, s>>>(partial, (int)g, C, da, db);
+  FOCR_LAUNCH_CHECK();
+  return FOCR_OK;
+}
+
+// out bf16 (rows_pad, 2E): rows = B*T text positions (row-major b, t), padding rows zero.  status: device int (0 ok, 2 index
+// outside the table).
+int focr_text_embed_fwd(const long long* idx, const float* lut, int vocab, int E, int B, int T, long rows_pad, void* out,
+                        float p_drop, unsigned seed, unsigned stream_id, int* status, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  FOCR_REQUIRE(idx && lut && out && status, "text_embed_fwd: null pointer");
+  FOCR_REQUIRE(vocab >= 1 && E >= 2 && (E & 1) == 0 && B >= 1 && T >= 1 && rows_pad >= (long)B * T, "text_embed_fwd: shape");
+  ProfScope _ps("text_embed", s);
+  const uint32_t th = th16_of(p_drop);
+  FOCR_CHECK_CUDA(cudaMemsetAsync(status, 0, sizeof(int), s));
+  text_embed_pe_kernel<<<egrid(rows_pad * 2 * E, 256), 256, 0, s>>>(idx, lut, vocab, E, (long)B * T, T, rows_pad, (bf16*)out,
+                                                                     drop_key(seed, stream_id), th, 65536.f / (65536.f - (float)th),
+                                                                     status);
+  FOCR_LAUNCH_CHECK();
+  return FOCR_OK;
+}
+int focr_text_embed_bwd(const long long* idx, const void* d_out, int vocab, int E, int B, int T, float* d_lut, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  FOCR_REQUIRE(idx && d_out && d_lut, "text_embed_bwd: null pointer");
+  ProfScope _ps("text_embed_bwd", s);
+  text_embed_bwd_kernel<<<egrid((long)vocab * E, 128), 128, 0, s>>>(idx, (const bf16*)d_out, vocab, E, (long)B * T, d_lut);
+  FOCR_LAUNCH_CHECK();
+  return FOCR_OK;
+}
+
+// loss[0] = mean over the packed valid positions of CE(logits[b,t,:C], gt); d_logits bf16 (B*T, ld_d) = gscale * d loss /
+// d logits (zeros at t >= length[b] and at the padding columns), or NULL.  ws: (B + 1) floats.
+size_t focr_packed_ce_workspace_bytes(int B) { return ((size_t)B + 4) * sizeof(float); }
+int focr_packed_ce(const float* logits, long ld, int B, int T, int C, const long long* length, const long long* gt, float gscale,
+                   float* loss, void* d_logits, long ld_d, void* ws, size_t ws_bytes, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  FOCR_REQUIRE(logits && length && gt && loss && ws, "packed_ce: null pointer");
+  FOCR_REQUIRE(B >= 1 && T >= 1 && C >= 2 && ld >= C && (!d_logits || ld_d >= C), "packed_ce: B=%d T=%d C=%d ld=%ld", B, T, C, ld);
+  FOCR_REQUIRE(ws_bytes >= focr_packed_ce_workspace_bytes(B), "packed_ce: workspace too small");
+  ProfScope _ps("packed_ce", s);
+  float* partial = (float*)ws;
+  int* status = (int*)(partial + B);
+  FOCR_CHECK_CUDA(cudaMemsetAsync(status, 0, sizeof(int), s));
+  packed_ce_kernel<<<B, 128, 0, s>>>(logits, ld, B, T, C, length, gt, gscale, partial, (bf16*)d_logits, ld_d, status);
+  FOCR_LAUNCH_CHECK();
+  sum_partials_kernel<<<1, 256, 0, s>>>(partial, B, loss);
+  FOCR_LAUNCH_CHECK();
+  return FOCR_OK;
+}
+
+int focr_dropout(const void* x, void* y, long n, float p_drop, unsigned seed, unsigned stream_id, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  FOCR_REQUIRE(x && y && n >= 1 && p_drop >= 0.f && p_drop < 1.f, "dropout: bad arguments");
+  const uint32_t th = th16_of(p_drop);
+  dropout_kernel<<<egrid(n, 256), 256, 0, s>>>((const bf16*)x, (bf16*)y, n, drop_key(seed, stream_id), th,
+                                               65536.f / (65536.f - (float)th));
+  FOCR_LAUNCH_CHECK();
+  return FOCR_OK;
+}
+int focr_add_relu(const void* a, const void* b, void* y, long n, void* stream) {
+  FOCR_REQUIRE(a && b && y && n >= 8 && n % 8 == 0, "add_relu: n %ld must be a positive multiple of 8", n);
+  add_relu_kernel<<<egrid(n / 8, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)a, (const uint4*)b, (uint4*)y, n / 8);
+  FOCR_LAUNCH_CHECK();
+  return FOCR_OK;
+}
+int focr_relu_bwd(const void* dy, const void* y, void* dx, long n, void* stream) {
+  FOCR_REQUIRE(dy && y && dx && n >= 8 && n % 8 == 0, "relu_bwd: n %ld must be a positive multiple of 8", n);
+  relu_bwd_kernel<<<egrid(n / 8, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)dy, (const uint4*)y, (uint4*)dx, n / 8);
+  FOCR_LAUNCH_CHECK();
+  return FOCR_OK;
+}
+
+// nn.MaxPool2d((2,2),(2,2)) on an NHWC bf16 map (transformer.py:84,130) and its backward (gradient to the first maximum)
+int focr_maxpool2x2_fwd(const void* x, void* y, int B, int H, int W, int C, void* stream) {
+  FOCR_REQUIRE(x && y && (H & 1) == 0 && (W & 1) == 0 && C % 8 == 0, "maxpool2x2_fwd: H=%d W=%d C=%d", H, W, C);
+  return maxpool_fwd((const bf16*)x, (bf16*)y, B, H, W, C, 2, (cudaStream_t)stream);
+}
+int focr_maxpool2x2_bwd(const void* x, const void* y, const void* dy, void* dx, int B, int H, int W, int C, void* stream) {
+  FOCR_REQUIRE(x && y && dy && dx && (H & 1) == 0 && (W & 1) == 0 && C % 8 == 0, "maxpool2x2_bwd: H=%d W=%d C=%d", H, W, C);
+  return maxpool_bwd((const bf16*)x, (const bf16*)y, (const bf16*)dy, (bf16*)dx, B, H, W, C, 2, (cudaStream_t)stream);
+}
+
+// chunks: device array of n_chunks records {param, grad, square_avg, acc_delta, n} (5 x int64), as focr_adam_clip_step
+int focr_adadelta_step(const void* chunks, int n_chunks, float gscale, float lr, float rho, float eps, float weight_decay,
+                       void* stream) {
+  FOCR_REQUIRE(chunks && n_chunks > 0, "adadelta_step: empty chunk table");
+  ProfScope _ps("adadelta", (cudaStream_t)stream);
+  adadelta_kernel<<<n_chunks, 256, 0, (cudaStream_t)stream>>>((const AdaChunk*)chunks, gscale, lr, rho, eps, weight_decay);
+  FOCR_LAUNCH_CHECK();
+  return FOCR_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// 3x3 convolutions of the recogniser encoder through an explicit im2col (transformer.py:80 conv1 with 3 input channels, and
+// every weight gradient: dW = dY^T col is a plain token GEMM with K = 9 Ci, compute-bound for Ci >= 128).  Forward / input
+// gradient of the 64..1024-channel layers go through the implicit GEMM (focr_conv2d_fwd / _dgrad) instead.
+// ------------------------------------------------------------------------------------------------------------------
+static inline size_t up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+size_t focr_conv3x3_gemm_workspace_bytes(int B, int H, int W, int Ci, int Co) {
+  const size_t M = (size_t)B * H * W, Kp = up((size_t)9 * Ci, 128), Np = up((size_t)Co, 64);
+  return up(M * Kp * 2, 256) + up(Np * Kp * 4, 256) + up(Np * 4, 256) + ((size_t)48 << 20);
+}
+
+// y bf16 (B*H*W, Co) = conv3x3(x) + bias.  x: NHWC bf16 (x_nhwc) or NCHW fp32 (x_nchw), exactly one non-NULL.
+int focr_conv3x3_gemm_fwd(const void* x_nhwc, const float* x_nchw, const float* w, const float* bias, void* y, int B, int H, int W,
+                          int Ci, int Co, void* ws, size_t ws_bytes, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  FOCR_REQUIRE((x_nhwc != nullptr) != (x_nchw != nullptr) && w && y && ws, "conv3x3_gemm_fwd: pointers");
+  const long M = (long)B * H * W;
+  FOCR_REQUIRE(M % 128 == 0 && Co % 64 == 0 && Ci >= 1, "conv3x3_gemm_fwd: B*H*W=%ld (mult. of 128) Co=%d (mult. of 64)", M, Co);
+  FOCR_REQUIRE(ws_bytes >= focr_conv3x3_gemm_workspace_bytes(B, H, W, Ci, Co), "conv3x3_gemm_fwd: workspace too small");
+  const int Kp = (int)up((size_t)9 * Ci, 128);
+  bf16* col = (bf16*)ws;
+  bf16* wb = (bf16*)((char*)ws + up((size_t)M * Kp * 2, 256));
+  int rc = im2col3x3((const bf16*)x_nhwc, x_nchw, col, B, H, W, Ci, Kp, s);
+  if (rc) return rc;
+  rc = prep_stn_conv_w(w, wb, nullptr, Co, Ci, Co, Kp, s);
+  if (rc) return rc;
+  TcGemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.n_total = Co;
+  p.kh = p.kw = 1;
+  p.W = 64;
+  p.H = 2;
+  p.epi = TC_EPI_BF16;
+  p.ldc = Co;
+  p.bias = bias;
+  p.out = y;
+  const bf16* ap[1] = {col};
+  return tc_gemm_launch(ap, 1, Kp, (long)64 * Kp, (long)128 * Kp, Kp, (int)(M / 128), wb, Kp, p, s);
+}
+
+// dw fp32 [Co][Ci][3][3] and db [Co] (either may be NULL) from dy bf16 (B*H*W, Co) and the layer input
+int focr_conv3x3_gemm_wgrad(const void* dy, const void* x_nhwc, const float* x_nchw, float* dw, float* db, int B, int H, int W,
+                            int Ci, int Co, void* ws, size_t ws_bytes, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  FOCR_REQUIRE((x_nhwc != nullptr) != (x_nchw != nullptr) && dy && ws, "conv3x3_gemm_wgrad: pointers");
+  const long M = (long)B * H * W;
+  FOCR_REQUIRE(Co % 64 == 0 && Ci >= 1 && M >= 1, "conv3x3_gemm_wgrad: Co=%d (mult. of 64)", Co);
+  FOCR_REQUIRE(ws_bytes >= focr_conv3x3_gemm_workspace_bytes(B, H, W, Ci, Co), "conv3x3_gemm_wgrad: workspace too small");
+  const int Kp = (int)up((size_t)9 * Ci, 128);
+  bf16* col = (bf16*)ws;
+  float* tmpw = (float*)((char*)ws + up((size_t)M * Kp * 2, 256));
+  float* tmpb = (float*)((char*)tmpw + up((size_t)Co * Kp * 4, 256));
+  float* partial = (float*)((char*)tmpb + up((size_t)Co * 4, 256));
+  FOCR_REQUIRE(linear_wgrad_partial_bytes(M, Co, Kp) <= ((size_t)48 << 20), "conv3x3_gemm_wgrad: partial buffer");
+  int rc;
+  if (dw) {
+    rc = im2col3x3((const bf16*)x_nhwc, x_nchw, col, B, H, W, Ci, Kp, s);
+    if (rc) return rc;
+    rc = linear_wgrad((const bf16*)dy, Co, col, Kp, M, Co, Kp, tmpw, 1.f, partial, s);
+    if (rc) return rc;
+    rc = unpack_stn_conv_grad(tmpw, dw, Co, Ci, Kp, s);
+    if (rc) return rc;
+  }
+  if (db) return colsum((const bf16*)dy, Co, M, Co, db, partial, s);
+  return FOCR_OK;
+}
+
+}  // extern "C"

@@ -614,7 +614,7 @@ int tc_gemm_launch(const bf16* const* a_ptrs, int n_amaps, long a_pix_stride, lo
                    long a_img_stride, int a_channels, int B, const bf16* w, int cin, TcGemmParams p,
                    cudaStream_t stream) {
   FOCR_REQUIRE(n_amaps >= 1 && n_amaps <= 4, "tc_gemm: n_amaps %d", n_amaps);
-  FOCR_REQUIRE(p.W == 32 || p.W == 64 || p.W == 128, "tc_gemm: W must be 32, 64 or 128 (got %d)", p.W);
+  FOCR_REQUIRE(p.W == 16 || p.W == 32 || p.W == 64 || p.W == 128, "tc_gemm: W must be 16, 32, 64 or 128 (got %d)", p.W);
   FOCR_REQUIRE(p.H % (kTileM / p.W) == 0, "tc_gemm: H %d is not a multiple of the %d-row tile", p.H, kTileM / p.W);
   FOCR_REQUIRE(!p.relu_post || (p.epi == TC_EPI_BF16 && p.prelu_slope == nullptr), "tc_gemm: relu_post needs the bf16 TMA epilogue");
   FOCR_REQUIRE((p.H * p.W) % kTileM == 0, "tc_gemm: H*W must be a multiple of 128");

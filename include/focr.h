@@ -23,7 +23,7 @@ const char* focr_last_error(void);
 int focr_version(void);
 int focr_sync_check(void* stream); /* synchronise + surface asynchronous errors (tests only) */
 
-/* --- conv2d 3x3 / 1x1, stride 1, "same" padding, NHWC bf16, Ci and Co multiples of 64, W in {64,128} -------
+/* --- conv2d 3x3 / 1x1, stride 1, "same" padding, NHWC bf16, Ci and Co multiples of 64, W in {16,32,64,128}
  * replaces nn.Conv2d at STT/model/tbsrn.py:190,232,237 (64->64) and :264 (64->256, UpsampleBLock).
  * w: fp32 torch layout [Co][Ci][k][k].  flags bit0 relu; bit1 PixelShuffle(2)+mish epilogue (tbsrn.py:266-273):
  * y = pre-activation (B,2H,2W,64), y2 = mish(y).  residual (optional) is added after the activation. */
@@ -202,6 +202,57 @@ int focr_psnr_ssim(const float* img1, const float* img2, int B, int channels, co
  * out: fp32 (B,3,out_h,out_w) in [0,1]; status: device int set to 1 if a crop exceeded the bounds. */
 int focr_resize_bicubic_normalize(const void* pixels, const long long* meta, int B, int max_h, int max_w, int out_w, int out_h,
                                   float* out, int* status, void* stream);
+
+/* --- building blocks of the TRAINABLE ResNet + Transformer recognisers (SLD = stroke-level-decomposition,
+ * IDS = image-ids-CTR).  All matrices bf16 row-major unless stated; every reduction in a fixed order (bit-reproducible). ---------
+ * focr_mha_small_*: attention() SLD/model/transformer.py:227-241 inside MultiHeadedAttention.forward :205-223, as used by
+ *   Decoder.forward :303-315 (masked self-attention: causal = 1; cross-attention to the image tokens: causal = 0), h heads of
+ *   d_k in {64,128,256}.  q (B*Tq, ld_q), k / v (B*Tk, ld_k / ld_v), out (B*Tq, ld_o); head i at columns [i*d_k, (i+1)*d_k).
+ *   map fp32 (B,H,Tq,Tk) = dropout(softmax(q k^T / sqrt(d_k))) - the 'map' the reference returns; the backward recomputes the
+ *   softmax and reads the keep mask from map's zeros.  Tq*Tk*8 bytes must fit shared memory (200 KB).
+ * focr_layernorm_wide_*: LayerNorm SLD/model/transformer.py:244-254 for 512 / 1024 features, y = LN(x [+ res]); sum_out (optional)
+ *   receives x + res, which the backward takes as its x.  da / db are overwritten.
+ * focr_text_embed_*: Embeddings :277-286 (* sqrt(E)) concatenated with PositionalEncoding :168-186 applied to zeros (:346-348):
+ *   out (rows_pad, 2E), rows = B*T; p_drop acts on the positional half only, as in the reference.
+ * focr_packed_ce: the packing loop :361-373 + nn.CrossEntropyLoss (SLD/train.py:41,71): mean over the positions t < length[b] of
+ *   CE(logits[b,t,:C], gt_packed); logits fp32 (B*T, ld); d_logits bf16 (B*T, ld_d) = gscale * d loss / d logits or NULL.
+ * focr_adadelta_step: torch.optim.Adadelta (SLD/train.py:32-36: lr 1, rho 0.9, eps 1e-6; IDS adds weight_decay 1e-4) over a
+ *   device table of {param, grad, square_avg, acc_delta, n} records (5 x int64 each); grad is scaled by gscale first.
+ * focr_conv3x3_gemm_*: nn.Conv2d(3x3, pad 1) through an explicit im2col: forward for inputs the implicit GEMM does not take
+ *   (3-channel NCHW fp32 image, SLD/model/transformer.py:80), and the weight + bias gradient of ANY 3x3 layer (dW = dY^T col).
+ *   Exactly one of x_nhwc (bf16) / x_nchw (fp32) is non-NULL; Co % 64 == 0; forward needs B*H*W % 128 == 0.
+ * focr_add_relu / focr_relu_bwd: BasicBlock tail :69-71 (out += residual; relu) and its gradient from the stored output.
+ * focr_maxpool2x2_*: nn.MaxPool2d((2,2),(2,2)) :84,130 on NHWC maps; focr_dropout: nn.Dropout with a counter-hash mask - calling
+ *   it on the gradient with the same (seed, stream_id) is its backward. */
+int focr_mha_small_fwd(const void* q, long ld_q, const void* k, long ld_k, const void* v, long ld_v, void* out, long ld_o,
+                       float* map, int B, int H, int d_k, int Tq, int Tk, int causal, float p_drop, unsigned seed,
+                       unsigned stream_id, void* stream);
+int focr_mha_small_bwd(const void* q, long ld_q, const void* k, long ld_k, const void* v, long ld_v, const void* d_out, long ld_o,
+                       const float* map, void* dq, long ld_dq, void* dk, long ld_dk, void* dv, long ld_dv, int B, int H, int d_k,
+                       int Tq, int Tk, int causal, float p_drop, void* stream);
+int focr_layernorm_wide_fwd(const void* x, const void* res, const float* a, const float* b, void* sum_out, void* y, long T, int C,
+                            float eps, void* stream);
+size_t focr_layernorm_wide_workspace_bytes(int C);
+int focr_layernorm_wide_bwd(const void* dy, const void* x, const float* a, void* dx, float* da, float* db, long T, int C, float eps,
+                            void* ws, size_t ws_bytes, void* stream);
+int focr_text_embed_fwd(const long long* idx, const float* lut, int vocab, int E, int B, int T, long rows_pad, void* out,
+                        float p_drop, unsigned seed, unsigned stream_id, int* status, void* stream);
+int focr_text_embed_bwd(const long long* idx, const void* d_out, int vocab, int E, int B, int T, float* d_lut, void* stream);
+size_t focr_packed_ce_workspace_bytes(int B);
+int focr_packed_ce(const float* logits, long ld, int B, int T, int C, const long long* length, const long long* gt, float gscale,
+                   float* loss, void* d_logits, long ld_d, void* ws, size_t ws_bytes, void* stream);
+int focr_dropout(const void* x, void* y, long n, float p_drop, unsigned seed, unsigned stream_id, void* stream);
+int focr_add_relu(const void* a, const void* b, void* y, long n, void* stream);
+int focr_relu_bwd(const void* dy, const void* y, void* dx, long n, void* stream);
+int focr_maxpool2x2_fwd(const void* x, void* y, int B, int H, int W, int C, void* stream);
+int focr_maxpool2x2_bwd(const void* x, const void* y, const void* dy, void* dx, int B, int H, int W, int C, void* stream);
+int focr_adadelta_step(const void* chunks, int n_chunks, float gscale, float lr, float rho, float eps, float weight_decay,
+                       void* stream);
+size_t focr_conv3x3_gemm_workspace_bytes(int B, int H, int W, int Ci, int Co);
+int focr_conv3x3_gemm_fwd(const void* x_nhwc, const float* x_nchw, const float* w, const float* bias, void* y, int B, int H, int W,
+                          int Ci, int Co, void* ws, size_t ws_bytes, void* stream);
+int focr_conv3x3_gemm_wgrad(const void* dy, const void* x_nhwc, const float* x_nchw, float* dw, float* db, int B, int H, int W,
+                            int Ci, int Co, void* ws, size_t ws_bytes, void* stream);
 
 /* --- measurement hooks used by bench.py: CUDA-event scopes on the launching stream + launch counter ----------- */
 int focr_prof_enable(int mode /*0 off, 1 all, 2 focus*/, const char* focus_substring);
