@@ -812,4 +812,16 @@ int focr_conv3x3_gemm_wgrad(const void* dy, const void* x_nhwc, const float* x_n
   return FOCR_OK;
 }
 
+
+// nn.BatchNorm2d in eval mode (running statistics) + activation (0 none, 2 relu) on a (T, C) bf16 matrix: the recogniser under
+// model.eval() (SLD/train.py:88, test-time decode).  stats: fp32 [4][C] scratch.
+int focr_bn_eval_fwd(const void* x, const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                     void* y, float* stats, long T, int C, int act, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  FOCR_REQUIRE(x && gamma && beta && running_mean && running_var && y && stats, "bn_eval_fwd: null pointer");
+  int rc = bn_eval_stats(gamma, beta, running_mean, running_var, 1e-5f, C, stats, s);
+  if (rc) return rc;
+  return bn_apply((const bf16*)x, C, stats, (bf16*)y, C, T, C, act, nullptr, 0, nullptr, s);
+}
+
 }  // extern "C"

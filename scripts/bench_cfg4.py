@@ -1,0 +1,92 @@
+#!/usr/bin/env python
+"""BASELINE configs[3]: stroke-level-decomposition transformer recogniser train step, one process per GPU
+under torchrun.  A step = encoder (40 convs, train-mode BN) + decoder forward, packed cross entropy, backward, gradient
+all-reduce (N > 1), Adadelta.  The reference trains on 32x32 crops (config.py:14, batch 32); BASELINE's 32x320 / batch 512
+variant is not a reference configuration and its 16x160 maps do not tile into the implicit GEMM's 128-pixel
+boxes yet, so this script reports 32x32 at 64 crops per GPU by default.  Not the headline bench (bench.py); prints one JSON
+line with the per-family device-time breakdown."""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--width", type=int, default=32)
+    args = ap.parse_args()
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from fudanocr_b200 import _lib as L
+    from fudanocr_b200.model.transformer import Transformer
+    from fudanocr_b200.trainer_sld import SLDTrainer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(1234)
+    B, K = args.batch, args.steps
+    model = Transformer("stroke").to(dev).train()
+    trainer = SLDTrainer(model)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    image = torch.rand(B, 3, 32, args.width, device=dev, generator=g) * 2 - 1
+    rs = np.random.RandomState(1234 + rank)
+    lens = rs.randint(2, 31, size=B)                                    # stroke strings of 2..30 symbols incl. '$'
+    T = int(lens.max())
+    text_input = torch.zeros(B, T, dtype=torch.long)
+    gt = []
+    for b, n in enumerate(lens):
+        s = rs.randint(1, 6, size=n)
+        s[-1] = 6
+        text_input[b, 1:n] = torch.from_numpy(s[:n - 1])
+        gt.extend(s.tolist())
+    length = torch.from_numpy(lens.astype(np.int64)).to(dev)
+    text_input, text_gt = text_input.to(dev), torch.tensor(gt, dtype=torch.long, device=dev)
+    for _ in range(max(args.warmup, 3)):
+        loss = trainer.step(image, length, text_input, text_gt)
+    torch.cuda.synchronize()
+    L.prof_enable(1, b"")
+    trainer.step(image, length, text_input, text_gt)
+    breakdown = L.prof_collect()
+    L.prof_enable(0, b"")
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n0 = L.lib.focr_launch_count()
+    e0.record()
+    for _ in range(K):
+        loss = trainer.step(image, length, text_input, text_gt)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    if rank == 0:
+        flop = B * 3 * 31.6e9 * (args.width / 32.0)                     # 31.6 GFLOP/img forward at 32x32
+        top = sorted(((k, round(v[1], 3)) for k, v in breakdown.items()), key=lambda kv: -kv[1])[:12]
+        print(json.dumps({"metric": "sld_train_images_per_sec", "value": world * B * K / (ms / 1e3), "unit": "images/s",
+                          "n_gpus": world, "steps": K, "ms_per_step": ms / K, "dtype": "bf16", "data": "synthetic",
+                          "config": {"workload": f"SLD Transformer('stroke') train step, 32x{args.width} crops, batch {B} per GPU, "
+                                                 "CE + Adadelta(lr 1, rho 0.9), dropout 0.1", "T": T},
+                          "tflops_required": flop / (ms / K / 1e3) / 1e12, "launches_per_step": (L.lib.focr_launch_count() - n0) / K,
+                          "final_loss": float(loss), "breakdown_ms_per_step": dict(top)}))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,142 @@
+"""Stroke-level-decomposition recogniser on the engine (fudanocr_b200/model/transformer.py, trainer_sld.py)
+vs the oracle restatement (pinned to the unmodified reference module by tests/golden/sld_b3.pt) on the GPU.
+
+The 40-layer train-mode-BN encoder is ill-conditioned: the oracle itself moves by 1.2e-2 (encoder gradients, relative L2)
+between fp32 and fp64 (measured, tests/test_sld_assembly.py).  bf16 parity is therefore judged the way the TBSRN tests do:
+(a) the decoder and generator - well conditioned - against fp32 within bf16 accuracy; (b) the whole step against the error
+STOCK PyTorch autocast(bf16) makes on the same restatement, measured in the same test; the numbers go to gpurun_out/."""
+import json
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _rel(a, b):
+    return float((a.float() - b.float()).norm() / (b.float().norm() + 1e-30))
+
+
+def _setup():
+    from oracle import sld_oracle as SO, synth
+    from fudanocr_b200.model.transformer import Transformer
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = torch.load(synth.GOLDEN_DIR / "sld_b3.pt", weights_only=False)
+    sd = synth.synth_state_dict(synth.load_spec("sld"), 1234)
+    model = Transformer("stroke")
+    model.load_state_dict(sd, strict=False)
+    model = model.to(DEV)
+    image, strings = SO.synth_batch(g["B"])
+    assert strings == g["strings"]
+    return SO, g, sd, model, image.to(DEV), g["length"].to(DEV), g["text_input"].to(DEV), g["text_gt"].to(DEV)
+
+
+def test_sld_decoder_on_reference_features_and_eval_forward():
+    """teacher-forced: the engine's decoder fed the ORACLE's encoder features (bf16-rounded) must match the fp32 decoder"""
+    SO, g, sd, model, image, length, text_input, text_gt = _setup()
+    dsd = {k: v.to(DEV) for k, v in sd.items()}
+    model.eval()
+    with torch.no_grad():
+        o_logits, o_map, o_conv = SO.forward(dsd, image, text_input, train=False)
+        feat = o_conv.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+        o_logits_tf, o_map_tf, _ = SO.forward(dsd, image, text_input, train=False, conv_feature=feat.float().permute(0, 3, 1, 2))
+        out = model(None, length, text_input, conv_feature=feat.permute(0, 3, 1, 2), test=True)
+        assert _rel(out["pred"], o_logits_tf) < 2e-2, _rel(out["pred"], o_logits_tf)
+        assert (out["map"] - o_map_tf).abs().max().item() < 2e-2 * o_map_tf.max().item()
+        # whole eval forward (running statistics): encoder through 40 bf16 convs
+        full = model(image, length, text_input, test=True)
+        e_conv, e_pred = _rel(full["conv"], o_conv), _rel(full["pred"], o_logits)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            a_logits, _, a_conv = SO.forward(dsd, image, text_input, train=False)
+        s_conv, s_pred = _rel(a_conv, o_conv), _rel(a_logits, o_logits)
+        assert e_conv < max(1.5 * s_conv, 2e-2) and e_pred < max(1.5 * s_pred, 2e-2), (e_conv, s_conv, e_pred, s_pred)
+        assert torch.equal(full["pred"].argmax(2), o_logits.argmax(2)) or e_pred < s_pred * 1.5
+
+
+def test_sld_train_step_vs_oracle_calibrated_against_stock_bf16():
+    SO, g, sd, model, image, length, text_input, text_gt = _setup()
+    from fudanocr_b200.trainer_sld import SLDTrainer
+    model.train()
+    model.dropout_p = 0.0
+    # fp32 oracle and stock autocast(bf16) of the same restatement
+    def run(autocast):
+        osd = {k: v.to(DEV).clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in sd.items()}
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            loss, logits, amap, conv = SO.loss_fn(osd, image, length, text_input, text_gt)
+        loss.float().backward()
+        return loss.detach().float(), {k: v.grad.float() for k, v in osd.items() if v.grad is not None}
+    ref_loss, ref_g = run(False)
+    amp_loss, amp_g = run(True)
+    assert abs(float(ref_loss) - float(g["loss"])) < 1e-3         # the GPU fp32 oracle reproduces the reference's value
+    # engine: fused loss + backward through the reference-loop API
+    loss = model.loss(image, length, text_input, text_gt)
+    loss.backward()
+    eng_g = {k: p.grad.float() for k, p in model.named_parameters() if p.grad is not None}
+    assert set(eng_g) == set(ref_g)
+    report = {"loss": [float(loss), float(ref_loss), float(amp_loss)], "tensors": {}}
+    bad = []
+    for k, r in ref_g.items():
+        if float(r.abs().max()) < 1e-6:      # conv biases ahead of a train-mode BatchNorm: true gradient 0
+            continue
+        e, s = _rel(eng_g[k], r), _rel(amp_g[k], r)
+        report["tensors"][k] = [e, s]
+        well_conditioned = not k.startswith("encoder")
+        if not (e < (3e-2 if well_conditioned else max(1.5 * s, 5e-2))):
+            bad.append((k, e, s))
+    es = sorted(v[0] for v in report["tensors"].values())
+    ss = sorted(v[1] for v in report["tensors"].values())
+    report["median"] = [es[len(es) // 2], ss[len(ss) // 2]]
+    report["worst"] = [es[-1], ss[-1]]
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/sld_parity.json", "w") as f:
+        json.dump(report, f)
+    assert abs(float(loss) - float(ref_loss)) < max(2 * abs(float(amp_loss) - float(ref_loss)), 2e-2 * float(ref_loss))
+    assert not bad, bad[:8]
+    # running statistics follow the reference's update (momentum 0.1, unbiased variance)
+    for k, v in g["running_after"].items():
+        assert _rel(model.state_dict()[k].cpu(), v) < 3e-2, k
+
+
+def test_sld_fused_trainer_step_and_reference_loop_agree():
+    SO, g, sd, model, image, length, text_input, text_gt = _setup()
+    from fudanocr_b200.model.transformer import Transformer
+    from fudanocr_b200.trainer_sld import SLDTrainer
+    model.train()
+    model.dropout_p = 0.0
+    twin = Transformer("stroke")
+    twin.load_state_dict(sd, strict=False)
+    twin = twin.to(DEV).train()
+    twin.dropout_p = 0.0
+    # reference loop, unchanged (train.py:63-77) on the drop-in module
+    opt = torch.optim.Adadelta(twin.parameters(), lr=1.0, rho=0.9)
+    opt.zero_grad()
+    out = twin(image, length, text_input)
+    assert out["pred"].shape == (int(length.sum()), 7)
+    l_ref = torch.nn.CrossEntropyLoss()(out["pred"], text_gt)
+    l_ref.backward()
+    opt.step()
+    # fused trainer
+    tr = SLDTrainer(model)
+    l_fused = tr.step(image, length, text_input, text_gt)
+    torch.cuda.synchronize()
+    assert abs(float(l_fused) - float(l_ref)) < 1e-5 * abs(float(l_ref)) + 1e-6
+    worst = 0.0
+    for (k, a), (_, b) in zip(model.named_parameters(), twin.named_parameters()):
+        worst = max(worst, _rel(a.detach(), b.detach()))
+    # same kernels feed both; they differ only where torch's CE / bf16 cast of its fp32 logits gradient enters
+    assert worst < 2e-2, worst
+    # a second step runs (gradient buffer re-zeroed, state carried) and lowers the loss on the same batch
+    l2 = tr.step(image, length, text_input, text_gt)
+    torch.cuda.synchronize()
+    assert torch.isfinite(l2) and float(l2) < float(l_fused)
+    # dropout on: finite, reproducible masks are covered by the op tests; here only that the path runs
+    model.dropout_p = 0.1
+    l3 = tr.step(image, length, text_input, text_gt)
+    assert torch.isfinite(l3)
+    # no CPU fallback
+    from fudanocr_b200 import _lib as L
+    with pytest.raises(L.FocrError):
+        model(image.cpu(), length, text_input)
