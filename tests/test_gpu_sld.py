@@ -83,8 +83,10 @@ def test_sld_train_step_vs_oracle_calibrated_against_stock_bf16():
             continue
         e, s = _rel(eng_g[k], r), _rel(amp_g[k], r)
         report["tensors"][k] = [e, s]
-        well_conditioned = not k.startswith("encoder")
-        if not (e < (3e-2 if well_conditioned else max(1.5 * s, 5e-2))):
+        # every tensor - the decoder's too, whose inputs are the encoder features - inherits the encoder's bf16 sensitivity
+        # (stock autocast is 7-30 % off in the decoder and ~90 % off in most encoder tensors at this batch size); measured
+        # engine / stock ratio: 0.88 .. 1.19 over the 147 tensors (profiles/r01i_sld_parity.json)
+        if not (e < max(1.5 * s, 5e-2)):
             bad.append((k, e, s))
     es = sorted(v[0] for v in report["tensors"].values())
     ss = sorted(v[1] for v in report["tensors"].values())
@@ -95,6 +97,8 @@ def test_sld_train_step_vs_oracle_calibrated_against_stock_bf16():
         json.dump(report, f)
     assert abs(float(loss) - float(ref_loss)) < max(2 * abs(float(amp_loss) - float(ref_loss)), 2e-2 * float(ref_loss))
     assert not bad, bad[:8]
+    assert report["median"][0] < 1.15 * report["median"][1] + 1e-2, report["median"]
+    assert report["median"][0] < 1.15 * report["median"][1] + 1e-2, report["median"]
     # running statistics follow the reference's update (momentum 0.1, unbiased variance)
     for k, v in g["running_after"].items():
         assert _rel(model.state_dict()[k].cpu(), v) < 3e-2, k
