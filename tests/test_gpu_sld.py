@@ -3,8 +3,10 @@ vs the oracle restatement (pinned to the unmodified reference module by tests/go
 
 The 40-layer train-mode-BN encoder is ill-conditioned: the oracle itself moves by 1.2e-2 (encoder gradients, relative L2)
 between fp32 and fp64 (measured, tests/test_sld_assembly.py).  bf16 parity is therefore judged the way the TBSRN tests do:
-(a) the decoder and generator - well conditioned - against fp32 within bf16 accuracy; (b) the whole step against the error
-STOCK PyTorch autocast(bf16) makes on the same restatement, measured in the same test; the numbers go to gpurun_out/."""
+(a) the decoder and generator teacher-forced on the oracle's encoder features against fp32 within bf16 accuracy; (b) the whole
+step, tensor by tensor, against the error STOCK PyTorch autocast(bf16) makes on the same restatement, measured in the same
+test (report: gpurun_out/sld_parity.json, copy under profiles/); (c) the fused trainer against the unchanged reference loop
+run on the drop-in module.  Kernel-level parity is in tests/test_gpu_recog_ops.py, assembly parity in test_sld_assembly.py."""
 import json
 import os
 
@@ -97,7 +99,6 @@ def test_sld_train_step_vs_oracle_calibrated_against_stock_bf16():
         json.dump(report, f)
     assert abs(float(loss) - float(ref_loss)) < max(2 * abs(float(amp_loss) - float(ref_loss)), 2e-2 * float(ref_loss))
     assert not bad, bad[:8]
-    assert report["median"][0] < 1.15 * report["median"][1] + 1e-2, report["median"]
     assert report["median"][0] < 1.15 * report["median"][1] + 1e-2, report["median"]
     # running statistics follow the reference's update (momentum 0.1, unbiased variance)
     for k, v in g["running_after"].items():
