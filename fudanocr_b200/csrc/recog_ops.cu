@@ -539,6 +539,82 @@ __global__ void __launch_bounds__(256) adadelta_kernel(const AdaChunk* __restric
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// image-ids-CTR head (train.py:71-80): text_pred / ||text_pred||, and the distance term -MSE(text_pred_n, text_features[gt])
+// ------------------------------------------------------------------------------------------------------------------
+// y[r] = x[r] / ||x[r]||_2 (fp32 in, bf16 out), inv[r] = 1 / ||x[r]|| (0 for an all-zero row).  One warp per row.
+__global__ void __launch_bounds__(256) l2norm_fwd_kernel(const float* __restrict__ x, long ld, bf16* __restrict__ y,
+                                                         float* __restrict__ inv, long T, int C) {
+  const int lane = threadIdx.x & 31;
+  const long r = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= T) return;
+  const float* row = x + r * ld;
+  float ss = 0.f;
+  for (int c = lane; c < C; c += 32) ss += row[c] * row[c];
+  ss = warp_sum(ss);
+  const float iv = ss > 0.f ? 1.f / sqrtf(ss) : 0.f;
+  for (int c = lane; c < C; c += 32) y[r * C + c] = __float2bfloat16(row[c] * iv);
+  if (lane == 0) inv[r] = iv;
+}
+// dx = inv (dy - y (dy . y))
+__global__ void __launch_bounds__(256) l2norm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ y,
+                                                         const float* __restrict__ inv, bf16* __restrict__ dx, long ld_dx, long T,
+                                                         int C) {
+  const int lane = threadIdx.x & 31;
+  const long r = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= T) return;
+  float dot = 0.f;
+  for (int c = lane; c < C; c += 32) dot += ldbf(dy + r * C + c) * ldbf(y + r * C + c);
+  dot = warp_sum(dot);
+  const float iv = inv[r];
+  for (int c = lane; c < C; c += 32)
+    dx[r * ld_dx + c] = __float2bfloat16(iv * (ldbf(dy + r * C + c) - ldbf(y + r * C + c) * dot));
+}
+// partial[b] = sum over t < length[b], c of (y[b,t,c] - feats[gt][c])^2 / (total * C); d_y = gscale * 2 (y - feats[gt]) / (total * C)
+__global__ void __launch_bounds__(128) packed_feat_mse_kernel(const bf16* __restrict__ y, int B, int T, int C,
+                                                              const long long* __restrict__ length,
+                                                              const long long* __restrict__ gt, const float* __restrict__ feats,
+                                                              int V, float gscale, float* __restrict__ partial,
+                                                              bf16* __restrict__ d_y, int* __restrict__ status) {
+  __shared__ float wl[4];
+  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  long long off = 0, total = 0;
+  for (int i = 0; i < B; ++i) {
+    long long l = length[i];
+    l = l < 0 ? 0 : (l > T ? T : l);
+    if (i < b) off += l;
+    total += l;
+  }
+  long long len = length[b];
+  len = len < 0 ? 0 : (len > T ? T : len);
+  const float inv_n = total > 0 ? 1.f / ((float)total * (float)C) : 0.f;
+  float acc = 0.f;
+  for (int t = warp; t < T; t += 4) {
+    const long r = (long)b * T + t;
+    if (t >= len) {
+      if (d_y)
+        for (int c = lane; c < C; c += 32) d_y[r * C + c] = __float2bfloat16(0.f);
+      continue;
+    }
+    long long g = gt[off + t];
+    if (g < 0 || g >= V) {
+      if (lane == 0) atomicExch(status, 2);
+      g = 0;
+    }
+    const float* f = feats + g * C;
+    for (int c = lane; c < C; c += 32) {
+      const float d = ldbf(y + r * C + c) - f[c];
+      acc += d * d;
+      if (d_y) d_y[r * C + c] = __float2bfloat16(gscale * 2.f * d * inv_n);
+    }
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) wl[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) partial[b] = (wl[0] + wl[1] + wl[2] + wl[3]) * inv_n;
+}
+
 int egrid(long n, int per) { return (int)((n + per - 1) / per); }
 
 template <int DKV>
@@ -822,6 +898,38 @@ int focr_bn_eval_fwd(const void* x, const float* gamma, const float* beta, const
   int rc = bn_eval_stats(gamma, beta, running_mean, running_var, 1e-5f, C, stats, s);
   if (rc) return rc;
   return bn_apply((const bf16*)x, C, stats, (bf16*)y, C, T, C, act, nullptr, 0, nullptr, s);
+}
+
+
+// image-ids-CTR/train.py:76 - text_pred / text_pred.norm(dim=1, keepdim=True): x fp32 (T, ld) -> y bf16 (T, C), inv fp32 (T)
+int focr_l2norm_rows_fwd(const float* x, long ld, void* y, float* inv, long T, int C, void* stream) {
+  FOCR_REQUIRE(x && y && inv && T >= 1 && C >= 1 && ld >= C, "l2norm_rows_fwd: bad arguments");
+  l2norm_fwd_kernel<<<egrid(T, 8), 256, 0, (cudaStream_t)stream>>>(x, ld, (bf16*)y, inv, T, C);
+  FOCR_LAUNCH_CHECK();
+  return FOCR_OK;
+}
+int focr_l2norm_rows_bwd(const void* dy, const void* y, const float* inv, void* dx, long ld_dx, long T, int C, void* stream) {
+  FOCR_REQUIRE(dy && y && inv && dx && T >= 1 && C >= 1 && ld_dx >= C, "l2norm_rows_bwd: bad arguments");
+  l2norm_bwd_kernel<<<egrid(T, 8), 256, 0, (cudaStream_t)stream>>>((const bf16*)dy, (const bf16*)y, inv, (bf16*)dx, ld_dx, T, C);
+  FOCR_LAUNCH_CHECK();
+  return FOCR_OK;
+}
+// image-ids-CTR/train.py:66-69,79: nn.MSELoss(text_pred_n, text_features[text_gt]) over the packed valid rows.
+// loss[0] = mean squared difference; d_y bf16 (B*T, C) = gscale * d loss / d y (zeros at t >= length[b]) or NULL.  ws: (B + 4) floats.
+int focr_packed_feat_mse(const void* y, int B, int T, int C, const long long* length, const long long* gt, const float* feats, int V,
+                         float gscale, float* loss, void* d_y, void* ws, size_t ws_bytes, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  FOCR_REQUIRE(y && length && gt && feats && loss && ws, "packed_feat_mse: null pointer");
+  FOCR_REQUIRE(B >= 1 && T >= 1 && C >= 1 && V >= 1, "packed_feat_mse: B=%d T=%d C=%d V=%d", B, T, C, V);
+  FOCR_REQUIRE(ws_bytes >= focr_packed_ce_workspace_bytes(B), "packed_feat_mse: workspace too small");
+  float* partial = (float*)ws;
+  int* status = (int*)(partial + B);
+  FOCR_CHECK_CUDA(cudaMemsetAsync(status, 0, sizeof(int), s));
+  packed_feat_mse_kernel<<<B, 128, 0, s>>>((const bf16*)y, B, T, C, length, gt, feats, V, gscale, partial, (bf16*)d_y, status);
+  FOCR_LAUNCH_CHECK();
+  sum_partials_kernel<<<1, 256, 0, s>>>(partial, B, loss);
+  FOCR_LAUNCH_CHECK();
+  return FOCR_OK;
 }
 
 }  // extern "C"

@@ -615,9 +615,13 @@ int tc_gemm_launch(const bf16* const* a_ptrs, int n_amaps, long a_pix_stride, lo
                    cudaStream_t stream) {
   FOCR_REQUIRE(n_amaps >= 1 && n_amaps <= 4, "tc_gemm: n_amaps %d", n_amaps);
   FOCR_REQUIRE(p.W == 16 || p.W == 32 || p.W == 64 || p.W == 128, "tc_gemm: W must be 16, 32, 64 or 128 (got %d)", p.W);
-  FOCR_REQUIRE(p.H % (kTileM / p.W) == 0, "tc_gemm: H %d is not a multiple of the %d-row tile", p.H, kTileM / p.W);
+  // a 128-pixel tile is (128 / W) image rows, or - for maps smaller than one tile (H * W < 128) - several whole images:
+  // the TMA box then extends over the batch dimension, the zero-filled halo still being per image
+  const int tile_rows = (p.H * p.W >= kTileM) ? kTileM / p.W : p.H;
+  const int tile_imgs = kTileM / (p.W * tile_rows);
+  FOCR_REQUIRE(p.H % tile_rows == 0 && tile_imgs * tile_rows * p.W == kTileM && B % tile_imgs == 0,
+               "tc_gemm: a %dx%d map (batch %d) does not tile into 128-pixel boxes", p.H, p.W, B);
   FOCR_REQUIRE(!p.relu_post || (p.epi == TC_EPI_BF16 && p.prelu_slope == nullptr), "tc_gemm: relu_post needs the bf16 TMA epilogue");
-  FOCR_REQUIRE((p.H * p.W) % kTileM == 0, "tc_gemm: H*W must be a multiple of 128");
   FOCR_REQUIRE(cin % 64 == 0 && a_channels % 64 == 0, "tc_gemm: channels must be multiples of 64");
   FOCR_REQUIRE(p.kh >= 1 && p.kw >= 1 && (p.kh & 1) && (p.kw & 1) && p.kh <= 9 && p.kw <= 9, "tc_gemm: taps %dx%d",
                p.kh, p.kw);
@@ -637,7 +641,7 @@ int tc_gemm_launch(const bf16* const* a_ptrs, int n_amaps, long a_pix_stride, lo
     cuuint64_t dims[4] = {(cuuint64_t)a_channels, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)B};
     cuuint64_t str[3] = {(cuuint64_t)a_pix_stride * 2, (cuuint64_t)a_row_stride * 2,
                          (cuuint64_t)a_img_stride * 2};
-    cuuint32_t box[4] = {64, (cuuint32_t)p.W, (cuuint32_t)(kTileM / p.W), 1};
+    cuuint32_t box[4] = {64, (cuuint32_t)p.W, (cuuint32_t)tile_rows, (cuuint32_t)tile_imgs};
     int rc = make_map(&am[i], base, 4, dims, str, box);
     if (rc) return rc;
   }
@@ -678,7 +682,7 @@ int tc_gemm_launch(const bf16* const* a_ptrs, int n_amaps, long a_pix_stride, lo
     static int no_col = -1;
     if (no_col < 0) no_col = getenv("FOCR_TC_NO_COLMODE") ? 1 : 0;  // tuning knob
     if (!no_col && p.b_resident && p.tma_out && p.kh == 3 && p.kw == 3 && p.chunks == 1 && n_amaps == 1 && !p.residual &&
-        !p.gate) {
+        !p.gate && tile_imgs == 1) {
       cuuint64_t dims[4] = {(cuuint64_t)a_channels, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)B};
       cuuint64_t str[3] = {(cuuint64_t)a_pix_stride * 2, (cuuint64_t)a_row_stride * 2, (cuuint64_t)a_img_stride * 2};
       cuuint32_t box[4] = {64, (cuuint32_t)p.W, (cuuint32_t)(kTileM / p.W + 2), 1};

@@ -176,7 +176,7 @@ def linear_fwd(x, w, b, relu=False, fp32_out=False):
     N = w.shape[0]
     y = torch.empty(M, N, dtype=torch.float32 if fp32_out else BF, device=dev)
     ws = _ws(L.lib.focr_linear_workspace_bytes(K, N), dev)
-    _call(L.lib.focr_linear_fwd, "linear_fwd", x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), 0, M, K, N,
+    _call(L.lib.focr_linear_fwd, "linear_fwd", x.data_ptr(), w.data_ptr(), L.ptr(b), y.data_ptr(), 0, M, K, N,
           (1 if relu else 0) | (4 if fp32_out else 0), ws.data_ptr(), ws.numel(), L.cur_stream())
     return y
 
@@ -283,6 +283,37 @@ def packed_ce(logits, B, T, C, length, gt, gscale=1.0, want_grad=True):
     ws = _ws(L.lib.focr_packed_ce_workspace_bytes(B), dev)
     _call(L.lib.focr_packed_ce, "packed_ce", logits.data_ptr(), ld, B, T, C, length.data_ptr(), gt.data_ptr(), float(gscale),
           loss.data_ptr(), L.ptr(d), ld, ws.data_ptr(), ws.numel(), L.cur_stream())
+    return loss[0], d
+
+
+def l2norm_fwd(x):
+    """x fp32 (T, C) -> (y bf16 (T, C) = x / ||x||, inv fp32 (T))"""
+    dev = _dev(x)
+    T, C = x.shape
+    y = torch.empty(T, C, dtype=BF, device=dev)
+    inv = torch.empty(T, dtype=torch.float32, device=dev)
+    _call(L.lib.focr_l2norm_rows_fwd, "l2norm_rows_fwd", x.data_ptr(), x.stride(0), y.data_ptr(), inv.data_ptr(), T, C, L.cur_stream())
+    return y, inv
+
+
+def l2norm_bwd(dy, y, inv):
+    _dev(dy)
+    T, C = y.shape
+    dx = torch.empty(T, C, dtype=BF, device=dy.device)
+    _call(L.lib.focr_l2norm_rows_bwd, "l2norm_rows_bwd", dy.data_ptr(), y.data_ptr(), inv.data_ptr(), dx.data_ptr(), C, T, C,
+          L.cur_stream())
+    return dx
+
+
+def packed_feat_mse(y, B, T, length, gt, feats, gscale=1.0, want_grad=True):
+    """mean over the valid rows (t < length[b]) and columns of (y - feats[gt])^2 -> (loss scalar tensor, d_y bf16 or None)"""
+    dev = _dev(y)
+    C = y.shape[1]
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    d = torch.zeros(y.shape, dtype=BF, device=dev) if want_grad else None
+    ws = _ws(L.lib.focr_packed_ce_workspace_bytes(B), dev)
+    _call(L.lib.focr_packed_feat_mse, "packed_feat_mse", y.data_ptr(), B, T, C, length.data_ptr(), gt.data_ptr(), feats.data_ptr(),
+          feats.shape[0], float(gscale), loss.data_ptr(), L.ptr(d), ws.data_ptr(), ws.numel(), L.cur_stream())
     return loss[0], d
 
 

@@ -123,8 +123,10 @@ class _Linear(Function):
         if ctx.relu:
             dy = ops.relu_bwd(dy, y)
         dx = ops.linear_dgrad(dy, w) if ctx.needs_input_grad[0] else None
-        dw, db = ops.linear_wgrad(dy, x)
-        return dx, dw, db, None, None
+        dw = db = None
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:   # frozen operands (the CLIP text features of image-ids-CTR) skip this
+            dw, db = ops.linear_wgrad(dy, x)
+        return dx, dw, (db if ctx.needs_input_grad[2] else None), None, None
 
 
 class _MHA(Function):
@@ -189,6 +191,36 @@ class _PackedCE(Function):
     @staticmethod
     def forward(ctx, logits, B, T, C, length, gt):
         loss, d = ops.packed_ce(logits, B, T, C, length, gt, 1.0, True)
+        ctx.save_for_backward(d)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (d,) = ctx.saved_tensors
+        return d * g.to(d.dtype), None, None, None, None, None
+
+
+class _L2Norm(Function):
+    """rows of an fp32 matrix scaled to unit length (image-ids-CTR/train.py:76)"""
+
+    @staticmethod
+    def forward(ctx, x):
+        y, inv = ops.l2norm_fwd(x)
+        ctx.save_for_backward(y, inv)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        y, inv = ctx.saved_tensors
+        return ops.l2norm_bwd(_bf(dy).contiguous(), y, inv)
+
+
+class _FeatMSE(Function):
+    """nn.MSELoss(pred_n, text_features[text_gt]) over the packed valid rows (image-ids-CTR/train.py:66-69,79)"""
+
+    @staticmethod
+    def forward(ctx, y, B, T, length, gt, feats):
+        loss, d = ops.packed_feat_mse(y, B, T, length, gt, feats, 1.0, True)
         ctx.save_for_backward(d)
         return loss
 
@@ -266,12 +298,21 @@ class _MultiHeadedAttention(_Container):  # transformer.py:189-223
         self.compress_attention_linear = nn.Linear(h, 1)  # constructed, never used by the reference forward
 
 
-class _LayerNorm(_Container):  # transformer.py:244-254
-    def __init__(self, features, eps=1e-6):
+class _LayerNorm(_Container):  # transformer.py:244-254 (parameters a / b; image-ids-CTR names them a_2 / b_2)
+    def __init__(self, features, eps=1e-6, names=("a", "b")):
         super().__init__()
-        self.a = nn.Parameter(torch.ones(features))
-        self.b = nn.Parameter(torch.zeros(features))
+        self._names = names
+        setattr(self, names[0], nn.Parameter(torch.ones(features)))
+        setattr(self, names[1], nn.Parameter(torch.zeros(features)))
         self.eps = eps
+
+    @property
+    def scale(self):
+        return getattr(self, self._names[0])
+
+    @property
+    def shift(self):
+        return getattr(self, self._names[1])
 
 
 class _PositionwiseFeedForward(_Container):
@@ -288,14 +329,14 @@ class _Generator(_Container):
 
 
 class _Decoder(_Container):  # transformer.py:289-317
-    def __init__(self):
+    def __init__(self, ln_names=("a", "b")):
         super().__init__()
         self.mask_multihead = _MultiHeadedAttention(4, 1024)
-        self.mul_layernorm1 = _LayerNorm(1024)
+        self.mul_layernorm1 = _LayerNorm(1024, names=ln_names)
         self.multihead = _MultiHeadedAttention(4, 1024)
-        self.mul_layernorm2 = _LayerNorm(1024)
+        self.mul_layernorm2 = _LayerNorm(1024, names=ln_names)
         self.pff = _PositionwiseFeedForward(1024, 2048)
-        self.mul_layernorm3 = _LayerNorm(1024)
+        self.mul_layernorm3 = _LayerNorm(1024, names=ln_names)
 
 
 def _pad128(n: int) -> int:
@@ -359,8 +400,9 @@ class Transformer(nn.Module):
     def _lin(self, x, lin: nn.Linear, relu=False):
         return _Linear.apply(x, lin.weight, lin.bias, relu, False)
 
-    def decode(self, feat: torch.Tensor, text_input: torch.Tensor):
-        """feat (B, h, w, 1024) bf16, text_input (B, T) int64 -> (logits fp32 (rows_pad, 64) with rows b*T + t, map (B,4,T,h*w))"""
+    def decode_hidden(self, feat: torch.Tensor, text_input: torch.Tensor):
+        """feat (B, h, w, 1024) bf16, text_input (B, T) int64 -> (decoder output bf16 (rows_pad, 1024) with rows b*T + t,
+        map (B,4,T,h*w)): embedding | PE, then Decoder.forward (transformer.py:346-351, :303-317)"""
         B, T = text_input.shape
         n_tok = feat.shape[1] * feat.shape[2]
         rows_pad = _pad128(B * T)
@@ -372,17 +414,22 @@ class Transformer(nn.Module):
         mm = d.mask_multihead
         q, k, v = (self._lin(x0, mm.linears[i]) for i in range(3))
         a, _ = _MHA.apply(q, k, v, B, mm.h, mm.d_k, T, T, 1, p, seed, 1)
-        r1 = _LN.apply(self._lin(a, mm.linears[3]), x0, d.mul_layernorm1.a, d.mul_layernorm1.b)
+        r1 = _LN.apply(self._lin(a, mm.linears[3]), x0, d.mul_layernorm1.scale, d.mul_layernorm1.shift)
         mh = d.multihead
         img = feat.reshape(B * n_tok, feat.shape[3])
         q2 = self._lin(r1, mh.linears[0])
         k2, v2 = self._lin(img, mh.linears[1]), self._lin(img, mh.linears[2])
         a2, amap = _MHA.apply(q2, k2, v2, B, mh.h, mh.d_k, T, n_tok, 0, p, seed, 2)
-        r2 = _LN.apply(self._lin(a2, mh.linears[3]), r1, d.mul_layernorm2.a, d.mul_layernorm2.b)
+        r2 = _LN.apply(self._lin(a2, mh.linears[3]), r1, d.mul_layernorm2.scale, d.mul_layernorm2.shift)
         hdn = self._lin(r2, d.pff.w_1, relu=True)
         if p > 0:
             hdn = _Dropout.apply(hdn, p, seed, 3)
-        r3 = _LN.apply(self._lin(hdn, d.pff.w_2), r2, d.mul_layernorm3.a, d.mul_layernorm3.b)
+        r3 = _LN.apply(self._lin(hdn, d.pff.w_2), r2, d.mul_layernorm3.scale, d.mul_layernorm3.shift)
+        return r3, amap
+
+    def decode(self, feat: torch.Tensor, text_input: torch.Tensor):
+        """-> (logits fp32 (rows_pad, 64): generator over the 7 symbols padded to one GEMM tile, map)"""
+        r3, amap = self.decode_hidden(feat, text_input)
         g = self.generator_word.proj
         npad = 64 - g.weight.shape[0]
         logits = _Linear.apply(r3, F.pad(g.weight, (0, 0, 0, npad)), F.pad(g.bias, (0, npad)), False, True)

@@ -21,17 +21,17 @@ from .model.transformer import Transformer
 _CHUNK = 65536   # elements per optimizer CTA: ~1100 CTAs for 71.7 M parameters
 
 
-class SLDTrainer:
-    def __init__(self, model: Transformer, lr: float = 1.0, rho: float = 0.9, eps: float = 1e-6, weight_decay: float = 0.0,
-                 process_group=None):
-        if not isinstance(model, Transformer):
-            raise TypeError("SLDTrainer drives fudanocr_b200.model.transformer.Transformer")
+class _FlatAdadeltaTrainer:
+    """parameters, gradients and the two Adadelta states in flat fp32 buffers; autograd accumulates straight into the gradient
+    buffer; `skip` names the parameters the reference forward never touches (their .grad stays None there and its optimiser
+    skips them - which matters once weight decay is on)"""
+
+    def __init__(self, model, skip, lr, rho, eps, weight_decay, process_group):
         self.model = model
         self.lr, self.rho, self.eps, self.weight_decay = lr, rho, eps, weight_decay
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
-        # parameters the reference forward never touches get no gradient there and are skipped by its optimiser
-        self.names = [k for k, _ in model.named_parameters() if "compress_attention_linear" not in k]
+        self.names = [k for k, _ in model.named_parameters() if not any(s in k for s in skip)]
         params = dict(model.named_parameters())
         plist = [params[k] for k in self.names]
         dev = plist[0].device
@@ -63,18 +63,52 @@ class SLDTrainer:
         if self.world > 1:   # start from rank 0's weights on every rank
             dist.broadcast(self.flat_p, src=0, group=self.pg)
 
-    def step(self, image: torch.Tensor, length: torch.Tensor, text_input: torch.Tensor, text_gt: torch.Tensor) -> torch.Tensor:
-        """one optimisation step on device-resident tensors; returns this rank's (device) loss, nothing blocks the host"""
-        m = self.model
-        m.train()
+    def _begin(self):
+        self.model.train()
         self.flat_g.zero_()                                # optimizer.zero_grad()
         for p, g in zip(self.plist, self.grad_views):      # keep .grad pointing into the flat buffer
             if p.grad is not g:
                 p.grad = g
-        loss = m.loss(image, length, text_input, text_gt)
+
+    def _finish(self, loss, lr=None):
         loss.backward()
         if self.world > 1:
             dist.all_reduce(self.flat_g, group=self.pg)    # sum; the mean is taken inside the optimizer kernel
-        ops.adadelta_step(self.chunks, self.chunks.shape[0], 1.0 / self.world, self.lr, self.rho, self.eps, self.weight_decay)
+        ops.adadelta_step(self.chunks, self.chunks.shape[0], 1.0 / self.world, self.lr if lr is None else lr, self.rho, self.eps,
+                          self.weight_decay)
         self.loss = loss.detach()
         return self.loss
+
+
+class SLDTrainer(_FlatAdadeltaTrainer):
+    def __init__(self, model: Transformer, lr: float = 1.0, rho: float = 0.9, eps: float = 1e-6, weight_decay: float = 0.0,
+                 process_group=None):
+        if not isinstance(model, Transformer):
+            raise TypeError("SLDTrainer drives fudanocr_b200.model.transformer.Transformer")
+        super().__init__(model, ("compress_attention_linear",), lr, rho, eps, weight_decay, process_group)
+
+    def step(self, image: torch.Tensor, length: torch.Tensor, text_input: torch.Tensor, text_gt: torch.Tensor) -> torch.Tensor:
+        """one optimisation step on device-resident tensors; returns this rank's (device) loss, nothing blocks the host"""
+        self._begin()
+        return self._finish(self.model.loss(image, length, text_input, text_gt))
+
+
+class IDSTrainer(_FlatAdadeltaTrainer):
+    """image-ids-CTR/train.py:28,63-90: Adadelta(lr, rho 0.9, weight_decay 1e-4) on loss_rec + 0.001 * loss_dis against frozen
+    text features; `lr` may be passed per step (the reference drives it with CosineAnnealingWarmRestarts, train.py:29)"""
+
+    def __init__(self, model, text_features: torch.Tensor, lr: float = 1.0, rho: float = 0.9, eps: float = 1e-6,
+                 weight_decay: float = 1e-4, process_group=None):
+        from .model.ids_transformer import Transformer as IDSTransformer
+        if not isinstance(model, IDSTransformer):
+            raise TypeError("IDSTrainer drives fudanocr_b200.model.ids_transformer.Transformer")
+        super().__init__(model, ("compress_attention_linear", "encoder.layer4"), lr, rho, eps, weight_decay, process_group)
+        self.text_features = text_features.float().contiguous()
+        self.text_features_padded = model.pad_text_features(self.text_features)
+        self.loss_rec = self.loss_dis = None
+
+    def step(self, image, length, text_input, text_gt, lr: Optional[float] = None) -> torch.Tensor:
+        self._begin()
+        loss, rec, dis = self.model.loss(image, length, text_input, text_gt, self.text_features, self.text_features_padded)
+        self.loss_rec, self.loss_dis = rec.detach(), dis.detach()
+        return self._finish(loss, lr)

@@ -251,6 +251,13 @@ int focr_adadelta_step(const void* chunks, int n_chunks, float gscale, float lr,
 /* nn.BatchNorm2d under model.eval() (running statistics) + activation (0 none, 2 relu); stats: fp32 [4][C] scratch */
 int focr_bn_eval_fwd(const void* x, const float* gamma, const float* beta, const float* running_mean, const float* running_var,
                      void* y, float* stats, long T, int C, int act, void* stream);
+/* image-ids-CTR head (IDS/train.py:66-80): row-wise L2 normalisation of the 2048-d predictions (x fp32 (T, ld) -> y bf16 (T, C),
+ * inv fp32 (T) = 1 / norm) with its backward dx = inv (dy - y (dy . y)), and nn.MSELoss(pred_n, text_features[text_gt]) over the
+ * packed valid rows (value, and gscale * gradient w.r.t. y; zeros at t >= length[b]).  ws as focr_packed_ce. */
+int focr_l2norm_rows_fwd(const float* x, long ld, void* y, float* inv, long T, int C, void* stream);
+int focr_l2norm_rows_bwd(const void* dy, const void* y, const float* inv, void* dx, long ld_dx, long T, int C, void* stream);
+int focr_packed_feat_mse(const void* y, int B, int T, int C, const long long* length, const long long* gt, const float* feats, int V,
+                         float gscale, float* loss, void* d_y, void* ws, size_t ws_bytes, void* stream);
 size_t focr_conv3x3_gemm_workspace_bytes(int B, int H, int W, int Ci, int Co);
 int focr_conv3x3_gemm_fwd(const void* x_nhwc, const float* x_nchw, const float* w, const float* bias, void* y, int B, int H, int W,
                           int Ci, int Co, void* ws, size_t ws_bytes, void* stream);

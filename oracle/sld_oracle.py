@@ -89,22 +89,27 @@ def mha(sd, p, query, key, value, mask, h=4, keep=None, keep_scale=1.0):   # tra
     return lin(3, x), p_attn
 
 
+def _ln_params(sd, p):
+    """(a, b) of a LayerNorm: named a / b in stroke-level-decomposition (:247-248), a_2 / b_2 in image-ids-CTR (:253-254)"""
+    return (sd[p + ".a"], sd[p + ".b"]) if p + ".a" in sd else (sd[p + ".a_2"], sd[p + ".b_2"])
+
+
 def decoder(sd, text, conv_feature, drop: Optional[Dict] = None):      # transformer.py:303-317
     d = "decoder."
     T = text.shape[1]
     mask = torch.tril(torch.ones(1, 1, T, T, device=text.device)) != 0     # subsequent_mask :226-229
     ks = drop["scale"] if drop else 1.0
     sa, _ = mha(sd, d + "mask_multihead", text, text, text, mask, keep=drop and drop["self"], keep_scale=ks)
-    result = layer_norm(text + sa, sd[d + "mul_layernorm1.a"], sd[d + "mul_layernorm1.b"])
+    result = layer_norm(text + sa, *_ln_params(sd, d + "mul_layernorm1"))
     b, c, hh, ww = conv_feature.shape
     feat = conv_feature.view(b, c, hh * ww).permute(0, 2, 1).contiguous()
     ca, attention_map = mha(sd, d + "multihead", result, feat, feat, None, keep=drop and drop["cross"], keep_scale=ks)
-    result = layer_norm(result + ca, sd[d + "mul_layernorm2.a"], sd[d + "mul_layernorm2.b"])
+    result = layer_norm(result + ca, *_ln_params(sd, d + "mul_layernorm2"))
     hdn = F.relu(F.linear(result, sd[d + "pff.w_1.weight"], sd[d + "pff.w_1.bias"]))   # :262-263
     if drop:
         hdn = hdn * drop["ffn"] * ks
     ff = F.linear(hdn, sd[d + "pff.w_2.weight"], sd[d + "pff.w_2.bias"])
-    result = layer_norm(result + ff, sd[d + "mul_layernorm3.a"], sd[d + "mul_layernorm3.b"])
+    result = layer_norm(result + ff, *_ln_params(sd, d + "mul_layernorm3"))
     return result, attention_map
 
 

@@ -111,7 +111,7 @@ def dropout(x, p, seed, sid):
 
 
 def linear_fwd(x, w, b, relu=False, fp32_out=False):
-    y = F.linear(x, w, b)
+    y = F.linear(x, w, b)   # b may be None
     return F.relu(y) if relu else y
 
 
@@ -196,6 +196,27 @@ def packed_ce(logits, B, T, C, length, gt, gscale=1.0, want_grad=True):
     with torch.enable_grad():
         x3 = x[:B * T].view(B, T, -1)[:, :, :C]
         loss = F.cross_entropy(torch.cat([x3[b, :int(length[b])] for b in range(B)], 0), gt)
+        if want_grad:
+            (loss * gscale).backward()
+    return loss.detach(), (x.grad if want_grad else None)
+
+
+def l2norm_fwd(x):
+    n = x.norm(dim=1, keepdim=True)
+    inv = torch.where(n > 0, 1.0 / n, torch.zeros_like(n))
+    return x * inv, inv[:, 0]
+
+
+def l2norm_bwd(dy, y, inv):
+    return inv[:, None] * (dy - y * (dy * y).sum(1, keepdim=True))
+
+
+def packed_feat_mse(y, B, T, length, gt, feats, gscale=1.0, want_grad=True):
+    x = y.detach().clone().requires_grad_(True)
+    with torch.enable_grad():
+        x3 = x[:B * T].view(B, T, -1)
+        packed = torch.cat([x3[b, :int(length[b])] for b in range(B)], 0)
+        loss = F.mse_loss(packed, feats[gt])
         if want_grad:
             (loss * gscale).backward()
     return loss.detach(), (x.grad if want_grad else None)

@@ -340,3 +340,85 @@ def test_implicit_conv_on_16x16_maps(B, Ci, Co, flags):
     _sync(L)
     ref_dx = F.conv_transpose2d(dy.float().permute(0, 3, 1, 2), w.to(BF).float(), padding=1)
     assert _rel(dx.permute(0, 3, 1, 2), ref_dx) < 1e-2
+
+
+@pytest.mark.parametrize("B,H,W,Ci,Co", [(8, 2, 16, 512, 1024), (4, 2, 16, 1024, 1024), (3, 4, 32, 256, 512), (2, 8, 64, 128, 256),
+                                         (1, 16, 128, 64, 128)])
+def test_implicit_conv_on_the_ids_encoder_maps(B, H, W, Ci, Co):
+    """image-ids-CTR pools four times (model/transformer.py:126-152): 16x128, 8x64, 4x32 and 2x16 maps; a 2x16 map is a quarter of
+    a 128-pixel tile, so the TMA box spans four images (zero halo still per image)"""
+    L = _lib()
+    g = torch.Generator(device=DEV).manual_seed(H * W + Co)
+    x = torch.randn(B, H, W, Ci, device=DEV, generator=g).to(BF)
+    w = torch.randn(Co, Ci, 3, 3, device=DEV, generator=g) / (9 * Ci) ** 0.5
+    bias = torch.randn(Co, device=DEV, generator=g)
+    y = torch.empty(B, H, W, Co, dtype=BF, device=DEV)
+    ws = _ws(L.lib.focr_conv2d_workspace_bytes(Ci, Co, 3))
+    L.check(L.lib.focr_conv2d_fwd(x.data_ptr(), w.data_ptr(), bias.data_ptr(), y.data_ptr(), 0, 0, B, H, W, Ci, Co, 3, 0,
+                                  ws.data_ptr(), ws.numel(), L.cur_stream()), "conv2d_fwd small map")
+    _sync(L)
+    wr = w.to(BF).float().requires_grad_(True)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wr, bias, padding=1)
+    assert _rel(y.permute(0, 3, 1, 2), ref) < 1e-2
+    dy = torch.randn(B, H, W, Co, device=DEV, generator=g).to(BF)
+    dx = torch.empty(B, H, W, Ci, dtype=BF, device=DEV)
+    L.check(L.lib.focr_conv2d_dgrad(dy.data_ptr(), w.data_ptr(), dx.data_ptr(), B, H, W, Ci, Co, 3, 0, ws.data_ptr(), ws.numel(),
+                                    L.cur_stream()), "conv2d_dgrad small map")
+    _sync(L)
+    assert _rel(dx.permute(0, 3, 1, 2), F.conv_transpose2d(dy.float().permute(0, 3, 1, 2), w.to(BF).float(), padding=1)) < 1e-2
+    ref.backward(dy.float().permute(0, 3, 1, 2))
+    dw, db = torch.empty_like(w), torch.empty_like(bias)
+    ws2 = _ws(L.lib.focr_conv3x3_gemm_workspace_bytes(B, H, W, Ci, Co))
+    L.check(L.lib.focr_conv3x3_gemm_wgrad(dy.data_ptr(), x.data_ptr(), 0, dw.data_ptr(), db.data_ptr(), B, H, W, Ci, Co, ws2.data_ptr(),
+                                          ws2.numel(), L.cur_stream()), "conv3x3_gemm_wgrad small map")
+    _sync(L)
+    assert _rel(dw, wr.grad) < 1e-2
+    # a batch that does not fill whole tiles is refused, not mis-tiled
+    if H * W < 128:
+        assert L.lib.focr_conv2d_fwd(x.data_ptr(), w.data_ptr(), bias.data_ptr(), y.data_ptr(), 0, 0, B - 1, H, W, Ci, Co, 3, 0,
+                                     ws.data_ptr(), ws.numel(), L.cur_stream()) != 0
+
+
+def test_l2norm_rows_and_packed_feature_mse():
+    """image-ids-CTR/train.py:66-80: pred / pred.norm(dim=1), and -MSE(pred_n, text_features[gt]) over the packed valid rows"""
+    L = _lib()
+    g = torch.Generator(device=DEV).manual_seed(12)
+    B, T, C, V = 5, 7, 2048, 300
+    rows_pad = 128
+    x = torch.randn(rows_pad, C, device=DEV, generator=g) * 3
+    x[40] = 0                                                  # an all-zero row must not produce NaN
+    y = torch.empty(rows_pad, C, dtype=BF, device=DEV)
+    inv = torch.empty(rows_pad, device=DEV)
+    L.check(L.lib.focr_l2norm_rows_fwd(x.data_ptr(), C, y.data_ptr(), inv.data_ptr(), rows_pad, C, L.cur_stream()))
+    _sync(L)
+    xr = x.clone().requires_grad_(True)
+    n = xr.norm(dim=1, keepdim=True)
+    ref = xr / torch.where(n > 0, n, torch.ones_like(n))
+    assert _rel(y, ref) < 1e-2 and torch.isfinite(y.float()).all() and (y[40] == 0).all()
+    dy = torch.randn(rows_pad, C, device=DEV, generator=g).to(BF)
+    # reference gradient through the bf16-rounded output the kernel stored
+    yq = y.float()
+    want = inv[:, None] * (dy.float() - yq * (dy.float() * yq).sum(1, keepdim=True))
+    dx = torch.empty(rows_pad, C, dtype=BF, device=DEV)
+    L.check(L.lib.focr_l2norm_rows_bwd(dy.data_ptr(), y.data_ptr(), inv.data_ptr(), dx.data_ptr(), C, rows_pad, C, L.cur_stream()))
+    _sync(L)
+    assert _rel(dx, want) < 1e-2
+    ref.backward(dy.float())
+    assert _rel(dx, xr.grad) < 2e-2
+    # distance term
+    length = torch.tensor([7, 2, 0, 5, 1], device=DEV)
+    gt = torch.randint(0, V, (int(length.sum()),), device=DEV, generator=g)
+    feats = torch.randn(V, C, device=DEV, generator=g) * 0.3
+    loss = torch.empty(1, device=DEV)
+    d = torch.full((rows_pad, C), 3.0, dtype=BF, device=DEV)
+    ws = _ws(L.lib.focr_packed_ce_workspace_bytes(B))
+    L.check(L.lib.focr_packed_feat_mse(y.data_ptr(), B, T, C, length.data_ptr(), gt.data_ptr(), feats.data_ptr(), V, 1.0, loss.data_ptr(),
+                                       d.data_ptr(), ws.data_ptr(), ws.numel(), L.cur_stream()), "packed_feat_mse")
+    _sync(L)
+    yr = y.float().clone().requires_grad_(True)
+    y3 = yr[:B * T].view(B, T, C)
+    packed = torch.cat([y3[b, :int(length[b])] for b in range(B)], 0)
+    ref_l = F.mse_loss(packed, feats[gt])
+    ref_l.backward()
+    assert abs(float(loss) - float(ref_l.detach())) < 1e-5 * float(ref_l.detach())
+    assert _rel(d[:B * T], yr.grad[:B * T]) < 1e-2 and (d[:B * T].float()[yr.grad[:B * T] == 0] == 0).all()
