@@ -20,6 +20,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--width", type=int, default=32)
+    ap.add_argument("--model", choices=("sld", "ids"), default="sld",
+                    help="ids: image-ids-CTR recogniser (SURVEY A22), 32x256 crops, CLIP-feature similarity loss, weight decay 1e-4")
     args = ap.parse_args()
     import numpy as np
     import torch
@@ -37,18 +39,28 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(1234)
     B, K = args.batch, args.steps
-    model = Transformer("stroke").to(dev).train()
-    trainer = SLDTrainer(model)
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    image = torch.rand(B, 3, 32, args.width, device=dev, generator=g) * 2 - 1
     rs = np.random.RandomState(1234 + rank)
-    lens = rs.randint(2, 31, size=B)                                    # stroke strings of 2..30 symbols incl. '$'
+    ids = args.model == "ids"
+    if ids:
+        from fudanocr_b200.model.ids_transformer import Transformer as IDSTransformer, N_CLASS
+        from fudanocr_b200.trainer_sld import IDSTrainer
+        args.width = 256 if args.width == 32 else args.width
+        model = IDSTransformer().to(dev).train()
+        feats = torch.randn(N_CLASS, 2048, device=dev, generator=g) * 0.3
+        trainer = IDSTrainer(model, feats)
+        lens, hi, last = rs.randint(2, 26, size=B), N_CLASS - 1, N_CLASS - 1   # 1..25 characters + END
+    else:
+        model = Transformer("stroke").to(dev).train()
+        trainer = SLDTrainer(model)
+        lens, hi, last = rs.randint(2, 31, size=B), 6, 6                   # stroke strings of 2..30 symbols incl. '$'
+    image = torch.rand(B, 3, 32, args.width, device=dev, generator=g) * 2 - 1
     T = int(lens.max())
     text_input = torch.zeros(B, T, dtype=torch.long)
     gt = []
     for b, n in enumerate(lens):
-        s = rs.randint(1, 6, size=n)
-        s[-1] = 6
+        s = rs.randint(1, hi, size=n)
+        s[-1] = last
         text_input[b, 1:n] = torch.from_numpy(s[:n - 1])
         gt.extend(s.tolist())
     length = torch.from_numpy(lens.astype(np.int64)).to(dev)
@@ -78,12 +90,15 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     if rank == 0:
-        flop = B * 3 * 31.6e9 * (args.width / 32.0)                     # 31.6 GFLOP/img forward at 32x32
+        # forward 31.6 GFLOP/img (SLD, 32x32), 18.2 GFLOP/img (IDS, 32x256)
+        flop = B * 3 * (18.2e9 * args.width / 256.0 if ids else 31.6e9 * args.width / 32.0)
         top = sorted(((k, round(v[1], 3)) for k, v in breakdown.items()), key=lambda kv: -kv[1])[:12]
-        print(json.dumps({"metric": "sld_train_images_per_sec", "value": world * B * K / (ms / 1e3), "unit": "images/s",
+        print(json.dumps({"metric": f"{args.model}_train_images_per_sec", "value": world * B * K / (ms / 1e3), "unit": "images/s",
                           "n_gpus": world, "steps": K, "ms_per_step": ms / K, "dtype": "bf16", "data": "synthetic",
-                          "config": {"workload": f"SLD Transformer('stroke') train step, 32x{args.width} crops, batch {B} per GPU, "
-                                                 "CE + Adadelta(lr 1, rho 0.9), dropout 0.1", "T": T},
+                          "config": {"workload": (f"IDS Transformer train step, 32x{args.width} crops, batch {B} per GPU, similarity CE + 0.001 * "
+                                                  "distance term, Adadelta(lr 1, rho 0.9, wd 1e-4), dropout 0.1") if ids else
+                                                 (f"SLD Transformer('stroke') train step, 32x{args.width} crops, batch {B} per GPU, "
+                                                  "CE + Adadelta(lr 1, rho 0.9), dropout 0.1"), "T": T},
                           "tflops_required": flop / (ms / K / 1e3) / 1e12, "launches_per_step": (L.lib.focr_launch_count() - n0) / K,
                           "final_loss": float(loss), "breakdown_ms_per_step": dict(top)}))
 

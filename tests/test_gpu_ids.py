@@ -106,9 +106,16 @@ def test_ids_eval_forward_fused_trainer_and_reference_loop():
     torch.cuda.synchronize()
     # the reference loop normalises / multiplies in fp32 torch ops, the fused path in bf16 kernels: 1e-3 on the loss value
     assert abs(float(l_fused) - float(l_ref.detach())) < 2e-3 * abs(float(l_ref.detach()))
+    # both took the same step: Adadelta's first update is ~3e-3 * sign(g) per weight, so a wiring difference would show as O(0.1)
+    worst = 0.0
+    for (k, a), (_, b) in zip(model.named_parameters(), twin.named_parameters()):
+        worst = max(worst, _rel(a.detach(), b.detach()))
+    assert worst < 2e-2, worst
+    # (no monotonicity claim: at lr 1 that first step overshoots on a repeated 4-crop batch - measured 8.29 -> 22.1 here, while
+    # the batch-64 run of scripts/bench_cfg4.py --model ids goes 8.3 -> 6.65 in nine steps)
     l2 = tr.step(image, length, text_input, text_gt, lr=0.5)
     torch.cuda.synchronize()
-    assert torch.isfinite(l2) and float(l2) < float(l_fused)
+    assert torch.isfinite(l2)
     model.dropout_p = 0.1
     assert torch.isfinite(tr.step(image, length, text_input, text_gt))
     names = set(tr.names)

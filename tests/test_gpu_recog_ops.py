@@ -404,7 +404,8 @@ def test_l2norm_rows_and_packed_feature_mse():
     _sync(L)
     assert _rel(dx, want) < 1e-2
     ref.backward(dy.float())
-    assert _rel(dx, xr.grad) < 2e-2
+    live = torch.arange(rows_pad, device=DEV) != 40     # the guarded zero row has no meaningful reference gradient
+    assert _rel(dx[live], xr.grad[live]) < 2e-2 and (dx[40] == 0).all()
     # distance term
     length = torch.tensor([7, 2, 0, 5, 1], device=DEV)
     gt = torch.randint(0, V, (int(length.sum()),), device=DEV, generator=g)
