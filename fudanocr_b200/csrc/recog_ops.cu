@@ -390,16 +390,48 @@ __global__ void text_embed_pe_kernel(const long long* __restrict__ idx, const fl
   out[i] = __float2bfloat16(val);
 }
 
-// d_lut[v][c] = sqrt(E) * sum over rows with idx == v of d_out[row][c]   (one thread per (v, c), fixed order)
-__global__ void text_embed_bwd_kernel(const long long* __restrict__ idx, const bf16* __restrict__ d_out, int vocab, int E,
-                                      long rows, float* __restrict__ d_lut) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= vocab * E) return;
-  const int v = i / E, c = i - v * E;
-  float s = 0.f;
-  for (long r = 0; r < rows; ++r)
-    if (idx[r] == v) s += ldbf(d_out + r * 2 * E + c);
-  d_lut[i] = s * sqrtf((float)E);
+// d_lut[v][c] = sqrt(E) * sum over rows with idx == v of d_out[row][c].  One CTA per table entry v: warp 0 compacts the matching
+// rows IN ORDER (ballot + popc) into shared memory, chunk by chunk, then every thread sums its columns over that list - fixed
+// order, no atomics, and a 4303-entry table (image-ids-CTR) costs 4303 x rows comparisons instead of 4303 x 512 x rows.
+constexpr int kEmbChunk = 2048;
+__global__ void __launch_bounds__(128) text_embed_bwd_kernel(const long long* __restrict__ idx, const bf16* __restrict__ d_out,
+                                                             int vocab, int E, long rows, float* __restrict__ d_lut) {
+  __shared__ int list[kEmbChunk];
+  __shared__ int count;
+  const int v = blockIdx.x, lane = threadIdx.x & 31;
+  float acc[8];                                      // columns threadIdx.x + 128 * j, j < E / 128 (E <= 1024)
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (long r0 = 0; r0 < rows; r0 += kEmbChunk) {
+    const int n = (int)((rows - r0) < kEmbChunk ? (rows - r0) : kEmbChunk);
+    if (threadIdx.x < 32) {
+      int cnt = 0;
+      for (int i = 0; i < n; i += 32) {
+        const bool hit = (i + lane < n) && idx[r0 + i + lane] == v;
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (hit) list[cnt + __popc(m & ((1u << lane) - 1))] = i + lane;
+        cnt += __popc(m);
+      }
+      if (lane == 0) count = cnt;
+    }
+    __syncthreads();
+    const int cnt = count;
+    for (int k = 0; k < cnt; ++k) {
+      const bf16* row = d_out + (r0 + list[k]) * 2 * E;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = threadIdx.x + 128 * j;
+        if (c < E) acc[j] += ldbf(row + c);
+      }
+    }
+    __syncthreads();
+  }
+  const float sc = sqrtf((float)E);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = threadIdx.x + 128 * j;
+    if (c < E) d_lut[(long)v * E + c] = acc[j] * sc;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -752,7 +784,8 @@ int focr_text_embed_bwd(const long long* idx, const void* d_out, int vocab, int 
   cudaStream_t s = (cudaStream_t)stream;
   FOCR_REQUIRE(idx && d_out && d_lut, "text_embed_bwd: null pointer");
   ProfScope _ps("text_embed_bwd", s);
-  text_embed_bwd_kernel<<<egrid((long)vocab * E, 128), 128, 0, s>>>(idx, (const bf16*)d_out, vocab, E, (long)B * T, d_lut);
+  FOCR_REQUIRE(vocab >= 1 && E >= 1 && E <= 1024, "text_embed_bwd: vocab=%d E=%d (E <= 1024)", vocab, E);
+  text_embed_bwd_kernel<<<vocab, 128, 0, s>>>(idx, (const bf16*)d_out, vocab, E, (long)B * T, d_lut);
   FOCR_LAUNCH_CHECK();
   return FOCR_OK;
 }

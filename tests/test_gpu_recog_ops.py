@@ -187,6 +187,17 @@ def test_text_embed_fwd_bwd():
     _sync(L)
     ref = torch.zeros(vocab, E, device=DEV).index_add_(0, idx.reshape(-1), d_out[:B * T, :E].float()) * math.sqrt(E)
     assert _rel(d_lut, ref) < 1e-5
+    # a large table with many rows (image-ids-CTR: 4303 entries; more rows than one compaction chunk), repeated indices
+    V2, B2, T2 = 4303, 96, 25
+    idx2 = torch.randint(0, V2, (B2, T2), device=DEV, generator=g)
+    idx2[:, 0] = 0
+    idx2[::3, 5] = 17
+    d2 = torch.randn(_pad := ((B2 * T2 + 127) // 128 * 128), 2 * E, device=DEV, generator=g).to(BF)
+    d_lut2 = torch.empty(V2, E, device=DEV)
+    L.check(L.lib.focr_text_embed_bwd(idx2.data_ptr(), d2.data_ptr(), V2, E, B2, T2, d_lut2.data_ptr(), L.cur_stream()))
+    _sync(L)
+    ref2 = torch.zeros(V2, E, device=DEV).index_add_(0, idx2.reshape(-1), d2[:B2 * T2, :E].float()) * math.sqrt(E)
+    assert _rel(d_lut2, ref2) < 1e-5
     # an index outside the table is flagged, not dereferenced
     bad = idx.clone()
     bad[0, 0] = vocab + 3
