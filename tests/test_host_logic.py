@@ -163,3 +163,79 @@ def test_text_focus_loss_dropin_surface():
         assert torch.equal(a, b)
     with pytest.raises(L.FocrError):
         crit(torch.rand(3, 3, 32, 128), torch.rand(3, 3, 32, 128), labels)
+
+
+SLD_WORKER = textwrap.dedent("""
+    import ctypes, os, sys, numpy as np, torch, torch.distributed as dist
+    sys.path.insert(0, %r); sys.path.insert(0, os.path.join(%r, "tests"))
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%%s" %% sys.argv[1], rank=int(sys.argv[2]), world_size=2)
+    rank = dist.get_rank()
+    torch.set_num_threads(3)
+    import _recog_mock as M
+    from fudanocr_b200.model import recog_ops as ops
+    for name in dir(M):
+        if not name.startswith("_") and callable(getattr(M, name)) and hasattr(ops, name) and name != "install":
+            setattr(ops, name, getattr(M, name))
+    ops.BF = torch.float32
+    ops.require_cuda = lambda t: None
+    def view(ptr, n):
+        return np.ctypeslib.as_array((ctypes.c_float * n).from_address(ptr))
+    def adadelta(table, n_chunks, gscale, lr, rho, eps, wd):            # host twin of adadelta_kernel over the same chunk table
+        for p, g, sq, acc, n in table.tolist():
+            P, G, S, A = view(p, n), view(g, n) * np.float32(gscale), view(sq, n), view(acc, n)
+            if wd:
+                G = G + np.float32(wd) * P
+            S[:] = rho * S + (1 - rho) * G * G
+            d = np.sqrt(A + eps) / np.sqrt(S + eps) * G
+            A[:] = rho * A + (1 - rho) * d * d
+            P[:] = P - lr * d
+    ops.adadelta_step = adadelta
+    from oracle import sld_oracle as SO, synth
+    from fudanocr_b200.interfaces.parallel import shard_batch
+    from fudanocr_b200.model.transformer import Transformer
+    from fudanocr_b200.trainer_sld import SLDTrainer
+    model = Transformer("stroke")
+    sd = synth.synth_state_dict(synth.load_spec("sld"), 1234 + rank)     # ranks start DIFFERENT: the trainer must broadcast rank 0's
+    model.load_state_dict(sd, strict=False)
+    model.dropout_p = 0.0
+    image, strings = SO.synth_batch(4)
+    img, strs = shard_batch([image, strings], rank, 2)
+    length, text_input, text_gt = SO.converter_stroke(strs)
+    tr = SLDTrainer(model)
+    assert tr.world == 2
+    before = tr.flat_p.clone()
+    sums = [torch.zeros(1, dtype=torch.float64) for _ in range(2)]
+    dist.all_gather(sums, before.double().sum().reshape(1))
+    assert sums[0] == sums[1]                                           # identical start after the broadcast
+    loss = tr.step(img, length, text_input, text_gt)
+    losses = [torch.zeros(1) for _ in range(2)]
+    dist.all_gather(losses, loss.reshape(1).float())
+    assert losses[0] != losses[1]                                       # different shards
+    for buf in (tr.flat_g, tr.flat_p):                                  # one summed gradient, one identical step on every rank
+        got = [torch.zeros(1, dtype=torch.float64) for _ in range(2)]
+        dist.all_gather(got, buf.double().abs().sum().reshape(1))
+        assert got[0] == got[1], got
+    assert not torch.equal(before, tr.flat_p) and torch.isfinite(tr.flat_p).all()
+    assert dict(model.named_parameters())["generator_word.proj.weight"].data_ptr() >= tr.flat_p.data_ptr()
+    dist.destroy_process_group()
+    print("ok", rank)
+""")
+
+
+def test_two_rank_gloo_recogniser_trainer(tmp_path):
+    """the data-parallel step of the trainable recognisers (trainer_sld.py) on 2 gloo ranks: SLDTrainer itself, with the kernel
+    wrappers swapped for the CPU stand-ins of tests/_recog_mock.py (test infrastructure) - broadcast of rank 0's weights, one
+    summed flat gradient, identical Adadelta step on both ranks"""
+    script = tmp_path / "sld_worker.py"
+    script.write_text(SLD_WORKER % (ROOT, ROOT))
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    procs = [subprocess.Popen([sys.executable, str(script), str(port), str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+        assert "ok" in o
