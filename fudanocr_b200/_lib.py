@@ -93,6 +93,8 @@ _SIGS = {
     "focr_l2norm_rows_fwd": (C.c_int, [_fp, _l, _vp, _fp, _l, _i, _vp]),
     "focr_l2norm_rows_bwd": (C.c_int, [_vp, _vp, _fp, _vp, _l, _l, _i, _vp]),
     "focr_packed_feat_mse": (C.c_int, [_vp, _i, _i, _i, _vp, _vp, _fp, _i, _f, _fp, _vp, _vp, _sz, _vp]),
+    "focr_conv3x3_wgrad_tc_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "focr_conv3x3_wgrad_tc": (C.c_int, [_vp, _vp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
     "focr_conv3x3_gemm_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "focr_conv3x3_gemm_fwd": (C.c_int, [_vp, _fp, _fp, _fp, _vp, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
     "focr_conv3x3_gemm_wgrad": (C.c_int, [_vp, _vp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _vp, _sz, _vp]),

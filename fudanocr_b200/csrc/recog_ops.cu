@@ -647,6 +647,26 @@ __global__ void __launch_bounds__(128) packed_feat_mse_kernel(const bf16* __rest
   if (threadIdx.x == 0) partial[b] = (wl[0] + wl[1] + wl[2] + wl[3]) * inv_n;
 }
 
+
+// dst[c][r] = src[r][c] for a row-major bf16 matrix (rows x cols, leading dimension ld_src) - 32 x 32 tiles through shared memory
+__global__ void __launch_bounds__(256) transpose_bf16_kernel(const bf16* __restrict__ src, long ld_src, long rows, long cols,
+                                                             bf16* __restrict__ dst, long ld_dst) {
+  __shared__ bf16 tile[32][34];
+  const long c0 = (long)blockIdx.x * 32, r0 = (long)blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long r = r0 + ty + 8 * i, c = c0 + tx;
+    tile[ty + 8 * i][tx] = (r < rows && c < cols) ? src[r * ld_src + c] : __float2bfloat16(0.f);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long c = c0 + ty + 8 * i, r = r0 + tx;
+    if (c < cols && r < rows) dst[c * ld_dst + r] = tile[tx][ty + 8 * i];
+  }
+}
+
 int egrid(long n, int per) { return (int)((n + per - 1) / per); }
 
 template <int DKV>
@@ -962,6 +982,63 @@ int focr_packed_feat_mse(const void* y, int B, int T, int C, const long long* le
   FOCR_LAUNCH_CHECK();
   sum_partials_kernel<<<1, 256, 0, s>>>(partial, B, loss);
   FOCR_LAUNCH_CHECK();
+  return FOCR_OK;
+}
+
+
+// Weight + bias gradient of a 3x3 convolution on the tcgen05 GEMM:  dW[Co][9 Ci] = dY^T (Co x M) . col (M x 9 Ci), the pixel
+// dimension M = B*H*W being the contraction.  Both operands are brought to K-major form by explicit transposes (dY^T: Co x M,
+// col^T: 9Ci x M) so that the same TMA / tcgen05 kernel that runs the forward GEMMs applies, fp32 accumulation in TMEM over all
+// of M, fp32 output.  Co % 128 == 0 and M % 128 == 0 (the 64-channel stem keeps the streaming kernel).
+size_t focr_conv3x3_wgrad_tc_workspace_bytes(int B, int H, int W, int Ci, int Co) {
+  const size_t M = (size_t)B * H * W, Kp = up((size_t)9 * Ci, 128);
+  return 2 * up(M * Kp * 2, 256) + up((size_t)Co * M * 2, 256) + up((size_t)Co * Kp * 4, 256) + up((size_t)Co * 4, 256) + ((size_t)16 << 20);
+}
+int focr_conv3x3_wgrad_tc(const void* dy, const void* x_nhwc, const float* x_nchw, float* dw, float* db, int B, int H, int W, int Ci,
+                          int Co, void* ws, size_t ws_bytes, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  FOCR_REQUIRE((x_nhwc != nullptr) != (x_nchw != nullptr) && dy && dw && ws, "conv3x3_wgrad_tc: pointers");
+  const long M = (long)B * H * W;
+  FOCR_REQUIRE(Co % 128 == 0 && M % 128 == 0 && Ci >= 1, "conv3x3_wgrad_tc: Co=%d (mult. of 128), B*H*W=%ld (mult. of 128)", Co, M);
+  FOCR_REQUIRE(ws_bytes >= focr_conv3x3_wgrad_tc_workspace_bytes(B, H, W, Ci, Co), "conv3x3_wgrad_tc: workspace too small");
+  const int Kp = (int)up((size_t)9 * Ci, 128);
+  char* base = (char*)ws;
+  bf16* col = (bf16*)base;
+  base += up((size_t)M * Kp * 2, 256);
+  bf16* colT = (bf16*)base;
+  base += up((size_t)M * Kp * 2, 256);
+  bf16* dyT = (bf16*)base;
+  base += up((size_t)Co * M * 2, 256);
+  float* tmpw = (float*)base;
+  base += up((size_t)Co * Kp * 4, 256);
+  float* partial = (float*)(base + up((size_t)Co * 4, 256));
+  int rc = im2col3x3((const bf16*)x_nhwc, x_nchw, col, B, H, W, Ci, Kp, s);
+  if (rc) return rc;
+  {
+    ProfScope _ps("wgrad_transpose", s);
+    transpose_bf16_kernel<<<dim3(Kp / 32, (unsigned)(M / 32)), 256, 0, s>>>(col, Kp, M, Kp, colT, M);
+    FOCR_LAUNCH_CHECK();
+    transpose_bf16_kernel<<<dim3(Co / 32, (unsigned)(M / 32)), 256, 0, s>>>((const bf16*)dy, Co, M, Co, dyT, M);
+    FOCR_LAUNCH_CHECK();
+  }
+  TcGemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.n_total = Kp;
+  p.kh = p.kw = 1;
+  p.W = 64;
+  p.H = 2;
+  p.epi = TC_EPI_F32;
+  p.ldc = Kp;
+  p.out = tmpw;
+  const bf16* ap[1] = {dyT};
+  {
+    ProfScope _ps("conv_wgrad_tc", s);
+    rc = tc_gemm_launch(ap, 1, M, (long)64 * M, (long)128 * M, (int)M, Co / 128, colT, (int)M, p, s);
+    if (rc) return rc;
+  }
+  rc = unpack_stn_conv_grad(tmpw, dw, Co, Ci, Kp, s);
+  if (rc) return rc;
+  if (db) return colsum((const bf16*)dy, Co, M, Co, db, partial, s);
   return FOCR_OK;
 }
 

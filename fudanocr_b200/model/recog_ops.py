@@ -4,11 +4,15 @@ enqueues the kernels on the current stream and returns tensors; none of them com
 bf16: feature maps NHWC (B, H, W, C), token matrices (rows, C).  CUDA tensors only - there is no CPU path."""
 from __future__ import annotations
 
+import os
+
 import torch
 
 from .. import _lib as L
 
 BF = torch.bfloat16
+# weight gradients of the encoder convs on the tcgen05 GEMM (transposed operands) instead of the streaming mma.sync kernel
+TC_WGRAD = os.environ.get("FOCR_TC_WGRAD", "0") == "1"
 
 
 def _dev(t):
@@ -78,11 +82,18 @@ def conv_dgrad(dy, w):
 
 
 def conv_wgrad(dy, x, w_shape):
+    """dW, db of a 3x3 convolution from dy (B,H,W,Co) and the layer input x (B,H,W,Ci): im2col, then dW = dY^T col on the tcgen05
+    GEMM (focr_conv3x3_wgrad_tc: Co % 128 == 0 and B*H*W % 128 == 0) or on the streaming mma.sync kernel (the 64-channel stem)"""
     dev = _dev(dy)
     B, H, W, Ci = x.shape
     Co = w_shape[0]
     dw = torch.empty(w_shape, dtype=torch.float32, device=dev)
     db = torch.empty(Co, dtype=torch.float32, device=dev)
+    if TC_WGRAD and Co % 128 == 0 and (B * H * W) % 128 == 0:
+        ws = _ws(L.lib.focr_conv3x3_wgrad_tc_workspace_bytes(B, H, W, Ci, Co), dev)
+        _call(L.lib.focr_conv3x3_wgrad_tc, "conv3x3_wgrad_tc", dy.data_ptr(), x.data_ptr(), 0, dw.data_ptr(), db.data_ptr(), B, H, W,
+              Ci, Co, ws.data_ptr(), ws.numel(), L.cur_stream())
+        return dw, db
     ws = _ws(L.lib.focr_conv3x3_gemm_workspace_bytes(B, H, W, Ci, Co), dev)
     _call(L.lib.focr_conv3x3_gemm_wgrad, "conv3x3_gemm_wgrad", dy.data_ptr(), x.data_ptr(), 0, dw.data_ptr(), db.data_ptr(), B, H, W,
           Ci, Co, ws.data_ptr(), ws.numel(), L.cur_stream())

@@ -248,6 +248,11 @@ int focr_maxpool2x2_fwd(const void* x, void* y, int B, int H, int W, int C, void
 int focr_maxpool2x2_bwd(const void* x, const void* y, const void* dy, void* dx, int B, int H, int W, int C, void* stream);
 int focr_adadelta_step(const void* chunks, int n_chunks, float gscale, float lr, float rho, float eps, float weight_decay,
                        void* stream);
+/* weight + bias gradient of a 3x3 convolution on the tcgen05 GEMM: dW = dY^T . col with the pixel dimension as the contraction, both
+ * operands transposed to K-major form first (Co % 128 == 0, B*H*W % 128 == 0); same arguments as focr_conv3x3_gemm_wgrad */
+size_t focr_conv3x3_wgrad_tc_workspace_bytes(int B, int H, int W, int Ci, int Co);
+int focr_conv3x3_wgrad_tc(const void* dy, const void* x_nhwc, const float* x_nchw, float* dw, float* db, int B, int H, int W, int Ci,
+                          int Co, void* ws, size_t ws_bytes, void* stream);
 /* nn.BatchNorm2d under model.eval() (running statistics) + activation (0 none, 2 relu); stats: fp32 [4][C] scratch */
 int focr_bn_eval_fwd(const void* x, const float* gamma, const float* beta, const float* running_mean, const float* running_var,
                      void* y, float* stats, long T, int C, int act, void* stream);

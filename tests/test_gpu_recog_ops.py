@@ -434,3 +434,24 @@ def test_l2norm_rows_and_packed_feature_mse():
     ref_l.backward()
     assert abs(float(loss) - float(ref_l.detach())) < 1e-5 * float(ref_l.detach())
     assert _rel(d[:B * T], yr.grad[:B * T]) < 1e-2 and (d[:B * T].float()[yr.grad[:B * T] == 0] == 0).all()
+
+
+@pytest.mark.parametrize("B,H,W,Ci,Co", [(8, 16, 16, 128, 256), (2, 16, 16, 512, 1024), (4, 2, 16, 1024, 1024), (2, 8, 64, 128, 256),
+                                         (1, 16, 128, 64, 128)])
+def test_conv_wgrad_on_tcgen05(B, H, W, Ci, Co):
+    """dW = dY^T col with the pixel dimension as the GEMM's K (both operands transposed to K-major, fp32 accumulation in TMEM)"""
+    L = _lib()
+    g = torch.Generator(device=DEV).manual_seed(B * 7 + Co)
+    x = torch.randn(B, H, W, Ci, device=DEV, generator=g).to(BF)
+    dy = torch.randn(B, H, W, Co, device=DEV, generator=g).to(BF)
+    w = torch.zeros(Co, Ci, 3, 3, device=DEV, requires_grad=True)
+    F.conv2d(x.float().permute(0, 3, 1, 2), w, None, padding=1).backward(dy.float().permute(0, 3, 1, 2))
+    dw, db = torch.empty(Co, Ci, 3, 3, device=DEV), torch.empty(Co, device=DEV)
+    ws = _ws(L.lib.focr_conv3x3_wgrad_tc_workspace_bytes(B, H, W, Ci, Co))
+    L.check(L.lib.focr_conv3x3_wgrad_tc(dy.data_ptr(), x.data_ptr(), 0, dw.data_ptr(), db.data_ptr(), B, H, W, Ci, Co, ws.data_ptr(),
+                                        ws.numel(), L.cur_stream()), "conv3x3_wgrad_tc")
+    _sync(L)
+    assert _rel(dw, w.grad) < 1e-2
+    assert _rel(db, dy.float().sum((0, 1, 2))) < 1e-3
+    assert L.lib.focr_conv3x3_wgrad_tc(dy.data_ptr(), x.data_ptr(), 0, dw.data_ptr(), db.data_ptr(), B, H, W, Ci, 64, ws.data_ptr(),
+                                       ws.numel(), L.cur_stream()) != 0        # 64 output channels: refused (streaming kernel's case)
