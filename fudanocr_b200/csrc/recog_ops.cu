@@ -667,6 +667,47 @@ __global__ void __launch_bounds__(256) transpose_bf16_kernel(const bf16* __restr
   }
 }
 
+
+// colT[k][m] = x[pixel m shifted by tap(k)][channel(k)], k = tap * C + c  (the transpose of the im2col matrix, written directly):
+// one CTA turns a [64 pixels][64 channels] window of x (16-byte loads along the channels) into 64 rows x 128 bytes of colT through a
+// transposing shared-memory tile.  C % 64 == 0, so a 64-wide block of k lies inside one tap; blocks past 9C are the zero padding.
+__global__ void __launch_bounds__(256) im2col3x3_t_kernel(const bf16* __restrict__ x, bf16* __restrict__ colT, int B, int H, int W, int C,
+                                                          long M) {
+  __shared__ __align__(16) bf16 tile[64][72];
+  const long m0 = (long)blockIdx.x * 64;
+  const int k0 = blockIdx.y * 64;
+  const int t = threadIdx.x;
+  if (k0 < 9 * C) {
+    const int tap = k0 / C, c0 = k0 - tap * C;
+    const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+    const int i = t & 63;
+    const long m = m0 + i;
+    const int w = (int)(m % W), h = (int)((m / W) % H);
+    const long b = m / ((long)W * H);
+    const int hh = h + dy, ww = w + dx;
+    const bool ok = hh >= 0 && hh < H && ww >= 0 && ww < W;
+    const bf16* src = x + ((b * H + (ok ? hh : 0)) * W + (ok ? ww : 0)) * C + c0;
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+      const int v = (t >> 6) + 4 * pass;
+      uint4 u = make_uint4(0, 0, 0, 0);
+      if (ok) u = *reinterpret_cast<const uint4*>(src + v * 8);
+      const bf16* e = reinterpret_cast<const bf16*>(&u);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) tile[v * 8 + q][i] = e[q];
+    }
+  } else {
+    for (int q = t; q < 64 * 72; q += 256) (&tile[0][0])[q] = __float2bfloat16(0.f);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    const int idx = t + 256 * pass;
+    const int c = idx >> 3, j = idx & 7;
+    *reinterpret_cast<uint4*>(colT + (long)(k0 + c) * M + m0 + j * 8) = *reinterpret_cast<const uint4*>(&tile[c][j * 8]);
+  }
+}
+
 int egrid(long n, int per) { return (int)((n + per - 1) / per); }
 
 template <int DKV>
@@ -992,19 +1033,18 @@ int focr_packed_feat_mse(const void* y, int B, int T, int C, const long long* le
 // of M, fp32 output.  Co % 128 == 0 and M % 128 == 0 (the 64-channel stem keeps the streaming kernel).
 size_t focr_conv3x3_wgrad_tc_workspace_bytes(int B, int H, int W, int Ci, int Co) {
   const size_t M = (size_t)B * H * W, Kp = up((size_t)9 * Ci, 128);
-  return 2 * up(M * Kp * 2, 256) + up((size_t)Co * M * 2, 256) + up((size_t)Co * Kp * 4, 256) + up((size_t)Co * 4, 256) + ((size_t)16 << 20);
+  return up(M * Kp * 2, 256) + up((size_t)Co * M * 2, 256) + up((size_t)Co * Kp * 4, 256) + up((size_t)Co * 4, 256) + ((size_t)16 << 20);
 }
 int focr_conv3x3_wgrad_tc(const void* dy, const void* x_nhwc, const float* x_nchw, float* dw, float* db, int B, int H, int W, int Ci,
                           int Co, void* ws, size_t ws_bytes, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
-  FOCR_REQUIRE((x_nhwc != nullptr) != (x_nchw != nullptr) && dy && dw && ws, "conv3x3_wgrad_tc: pointers");
+  FOCR_REQUIRE(x_nhwc != nullptr && x_nchw == nullptr && dy && dw && ws, "conv3x3_wgrad_tc: pointers (NHWC bf16 input only)");
   const long M = (long)B * H * W;
-  FOCR_REQUIRE(Co % 128 == 0 && M % 128 == 0 && Ci >= 1, "conv3x3_wgrad_tc: Co=%d (mult. of 128), B*H*W=%ld (mult. of 128)", Co, M);
+  FOCR_REQUIRE(Co % 128 == 0 && M % 128 == 0 && Ci % 64 == 0 && Ci >= 64,
+               "conv3x3_wgrad_tc: Co=%d (mult. of 128), Ci=%d (mult. of 64), B*H*W=%ld (mult. of 128)", Co, Ci, M);
   FOCR_REQUIRE(ws_bytes >= focr_conv3x3_wgrad_tc_workspace_bytes(B, H, W, Ci, Co), "conv3x3_wgrad_tc: workspace too small");
   const int Kp = (int)up((size_t)9 * Ci, 128);
   char* base = (char*)ws;
-  bf16* col = (bf16*)base;
-  base += up((size_t)M * Kp * 2, 256);
   bf16* colT = (bf16*)base;
   base += up((size_t)M * Kp * 2, 256);
   bf16* dyT = (bf16*)base;
@@ -1012,11 +1052,10 @@ int focr_conv3x3_wgrad_tc(const void* dy, const void* x_nhwc, const float* x_nch
   float* tmpw = (float*)base;
   base += up((size_t)Co * Kp * 4, 256);
   float* partial = (float*)(base + up((size_t)Co * 4, 256));
-  int rc = im2col3x3((const bf16*)x_nhwc, x_nchw, col, B, H, W, Ci, Kp, s);
-  if (rc) return rc;
+  int rc;
   {
-    ProfScope _ps("wgrad_transpose", s);
-    transpose_bf16_kernel<<<dim3(Kp / 32, (unsigned)(M / 32)), 256, 0, s>>>(col, Kp, M, Kp, colT, M);
+    ProfScope _ps("wgrad_operands", s);
+    im2col3x3_t_kernel<<<dim3((unsigned)(M / 64), Kp / 64), 256, 0, s>>>((const bf16*)x_nhwc, colT, B, H, W, Ci, M);
     FOCR_LAUNCH_CHECK();
     transpose_bf16_kernel<<<dim3(Co / 32, (unsigned)(M / 32)), 256, 0, s>>>((const bf16*)dy, Co, M, Co, dyT, M);
     FOCR_LAUNCH_CHECK();

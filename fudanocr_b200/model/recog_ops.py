@@ -12,7 +12,7 @@ from .. import _lib as L
 
 BF = torch.bfloat16
 # weight gradients of the encoder convs on the tcgen05 GEMM (transposed operands) instead of the streaming mma.sync kernel
-TC_WGRAD = os.environ.get("FOCR_TC_WGRAD", "0") == "1"
+TC_WGRAD = os.environ.get("FOCR_TC_WGRAD", "1") == "1"   # tuning knob: 0 = streaming kernel everywhere
 
 
 def _dev(t):
@@ -89,7 +89,7 @@ def conv_wgrad(dy, x, w_shape):
     Co = w_shape[0]
     dw = torch.empty(w_shape, dtype=torch.float32, device=dev)
     db = torch.empty(Co, dtype=torch.float32, device=dev)
-    if TC_WGRAD and Co % 128 == 0 and (B * H * W) % 128 == 0:
+    if TC_WGRAD and Co % 128 == 0 and Ci % 64 == 0 and (B * H * W) % 128 == 0:
         ws = _ws(L.lib.focr_conv3x3_wgrad_tc_workspace_bytes(B, H, W, Ci, Co), dev)
         _call(L.lib.focr_conv3x3_wgrad_tc, "conv3x3_wgrad_tc", dy.data_ptr(), x.data_ptr(), 0, dw.data_ptr(), db.data_ptr(), B, H, W,
               Ci, Co, ws.data_ptr(), ws.numel(), L.cur_stream())
