@@ -89,6 +89,12 @@ def main():
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+    ranks_identical = None
+    if world > 1:   # every rank must have taken the identical step: compare a checksum of the flat parameter buffer
+        chk = trainer.flat_p.double().abs().sum().reshape(1)
+        got = [torch.zeros_like(chk) for _ in range(world)]
+        dist.all_gather(got, chk)
+        ranks_identical = all(bool(g == got[0]) for g in got)
     if rank == 0:
         # forward 31.6 GFLOP/img (SLD, 32x32), 18.2 GFLOP/img (IDS, 32x256)
         flop = B * 3 * (18.2e9 * args.width / 256.0 if ids else 31.6e9 * args.width / 32.0)
@@ -100,7 +106,7 @@ def main():
                                                  (f"SLD Transformer('stroke') train step, 32x{args.width} crops, batch {B} per GPU, "
                                                   "CE + Adadelta(lr 1, rho 0.9), dropout 0.1"), "T": T},
                           "tflops_required": flop / (ms / K / 1e3) / 1e12, "launches_per_step": (L.lib.focr_launch_count() - n0) / K,
-                          "final_loss": float(loss), "breakdown_ms_per_step": dict(top)}))
+                          "final_loss": float(loss), "ranks_identical": ranks_identical, "breakdown_ms_per_step": dict(top)}))
 
 
 if __name__ == "__main__":
