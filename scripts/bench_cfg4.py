@@ -107,6 +107,8 @@ def main():
                                                   "CE + Adadelta(lr 1, rho 0.9), dropout 0.1"), "T": T},
                           "tflops_required": flop / (ms / K / 1e3) / 1e12, "launches_per_step": (L.lib.focr_launch_count() - n0) / K,
                           "final_loss": float(loss), "ranks_identical": ranks_identical, "breakdown_ms_per_step": dict(top)}))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
