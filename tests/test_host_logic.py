@@ -239,3 +239,43 @@ def test_two_rank_gloo_recogniser_trainer(tmp_path):
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
         assert "ok" in o
+
+
+def test_collate_host_side_packing_and_no_cpu_fallback():
+    """host half of the device-side collate (fudanocr_b200/dataset): ragged crops -> one packed uint8 buffer + (offset, h, w)
+    records; without a CUDA device the collate refuses instead of falling back to Pillow"""
+    import numpy as np
+    from fudanocr_b200 import _lib as L
+    from fudanocr_b200.dataset import dataset as D
+    rs = np.random.RandomState(0)
+    crops = [rs.randint(0, 256, size=(h, w, 3)).astype(np.uint8) for h, w in ((5, 7), (1, 1), (32, 128))]
+    buf, meta, max_h, max_w = D.pack_crops(crops)
+    assert (max_h, max_w) == (32, 128) and meta.shape == (3, 3) and meta.dtype == torch.int64
+    assert meta[:, 0].tolist() == [0, 5 * 7 * 3, 5 * 7 * 3 + 3] and buf.numel() == 5 * 7 * 3 + 3 + 32 * 128 * 3
+    for (off, h, w), c in zip(meta.tolist(), crops):
+        assert np.array_equal(buf.numpy()[off:off + h * w * 3].reshape(h, w, 3), c)
+    # non-contiguous views and torch tensors are accepted; wrong dtypes / ranks / empty crops are not
+    D.pack_crops([crops[2][::2, ::2], torch.from_numpy(crops[0])])
+    for bad in (np.zeros((4, 4), np.uint8), np.zeros((4, 4, 3), np.float32), np.zeros((0, 4, 3), np.uint8)):
+        with pytest.raises(ValueError):
+            D.pack_crops([bad])
+    with pytest.raises(NotImplementedError):
+        D.alignCollate_real(mask=True)
+    if not torch.cuda.is_available():
+        with pytest.raises(L.FocrError):
+            D.resize_normalize_batch(crops, (128, 32))
+        with pytest.raises(L.FocrError):
+            D.alignCollate_real(imgH=32, imgW=128, down_sample_scale=2)([(crops[0], crops[1], "a")])
+
+
+def test_ctc_loss_host_side_argument_handling():
+    """torch.nn.CTCLoss call forms: 1-D concatenated targets are re-padded on the host; CPU tensors are refused"""
+    from fudanocr_b200 import _lib as L
+    from fudanocr_b200.loss import ctc_loss as C
+    padded = C._pad_targets(torch.tensor([3, 4, 5, 9, 1, 1]), torch.tensor([3, 0, 1, 2]))
+    assert padded.tolist() == [[3, 4, 5], [0, 0, 0], [9, 0, 0], [1, 1, 0]]
+    assert C._pad_targets(torch.tensor([], dtype=torch.long), torch.tensor([0, 0])).shape == (2, 1)
+    with pytest.raises(ValueError):
+        C.CTCLoss(reduction="median")
+    with pytest.raises(L.FocrError):
+        C.ctc_loss(torch.zeros(4, 2, 5), torch.ones(2, 2, dtype=torch.long), [4, 4], [2, 2])
