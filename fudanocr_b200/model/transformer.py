@@ -368,6 +368,9 @@ class Transformer(nn.Module):
     def _bn(self, x, bn: nn.BatchNorm2d, act: int):
         if self.training:
             return _BNTrain.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked, act)
+        if torch.is_grad_enabled() and x.requires_grad:
+            raise RuntimeError("focr Transformer: backward through eval-mode BatchNorm is not built (the reference evaluates under "
+                               "torch.no_grad(), stroke-level-decomposition/train.py:80); call model.train() or wrap in no_grad")
         return ops.bn_eval_fwd(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, act)
 
     def _block(self, x, blk: _BasicBlock):
