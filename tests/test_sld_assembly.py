@@ -87,3 +87,41 @@ def test_fused_loss_equals_reference_loop_and_eval_contract(monkeypatch):
         ev2 = model(None, g["length"], g["text_input"], conv_feature=ev["conv"], test=True)
         assert torch.equal(ev2["pred"], ev["pred"])
         assert set(model(image, None, None).keys()) == {"conv"}
+
+
+def test_assembled_model_with_dropout_on_matches_oracle_with_the_rng_twin_masks(monkeypatch):
+    """dropout ON: the four dropout sites of the recogniser (positional half of the embedding, masked self-attention map,
+    cross-attention map, FFN hidden) draw their keep-masks from the counter hash of csrc/common.cuh with element indices
+    (b*T+t)*512+c / ((b*4+h)*Tq+i)*Tk+j / row*2048+c and streams 0..3; the oracle fed the numpy twin's masks
+    (oracle/dropout_rng.py) must agree with the assembled model - the kernels themselves are checked against the same twin on
+    the B200 (tests/test_gpu_recog_ops.py)"""
+    import numpy as np
+    from oracle import dropout_rng as R
+    model, g, image = _setup(monkeypatch)
+    model.train()
+    p = model.dropout_p
+    assert p == 0.1
+    B, T = g["text_input"].shape
+    seed = (model._seed * 1103515245 + 12345) & 0x7FFFFFFF          # the value decode_hidden() will draw next
+    rows_pad = (B * T + 127) // 128 * 128
+
+    def keep(n, sid):
+        return torch.from_numpy(R._keep(R.drop_key(seed, sid), np.arange(n, dtype=np.uint64), R.thresh16(p))).float()
+    drop = {"scale": R.keep_scale(p),
+            "pe": keep(B * T * 512, 0).view(B, T, 512),
+            "self": keep(B * 4 * T * T, 1).view(B, 4, T, T),
+            "cross": keep(B * 4 * T * 256, 2).view(B, 4, T, 256),
+            "ffn": keep(rows_pad * 2048, 3).view(rows_pad, 2048)[:B * T].view(B, T, 2048)}
+    sd = synth.synth_state_dict(synth.load_spec("sld"), 1234)
+    osd = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in sd.items()}
+    o_loss, o_logits, o_map, _ = SO.loss_fn(osd, image, g["length"], g["text_input"], g["text_gt"], drop)
+    o_loss.backward()
+    loss = model.loss(image, g["length"], g["text_input"], g["text_gt"])
+    assert model._seed == seed
+    assert abs(float(loss) - float(o_loss)) < 1e-4 * float(o_loss)
+    assert abs(float(o_loss) - float(g["loss"])) > 1e-4              # the masks did change the result
+    loss.backward()
+    for k in ("generator_word.proj.weight", "decoder.pff.w_1.weight", "decoder.multihead.linears.1.weight",
+              "decoder.mask_multihead.linears.0.weight", "embedding_word.lut.weight", "decoder.mul_layernorm2.a"):
+        a, b = dict(model.named_parameters())[k].grad, osd[k].grad
+        assert float((a - b).norm() / b.norm()) < 2e-3, k
