@@ -279,3 +279,16 @@ def test_ctc_loss_host_side_argument_handling():
         C.CTCLoss(reduction="median")
     with pytest.raises(L.FocrError):
         C.ctc_loss(torch.zeros(4, 2, 5), torch.ones(2, 2, dtype=torch.long), [4, 4], [2, 2])
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/focr.h is the drop-in boundary: it must compile as C99 (no C++ / torch types in any signature)"""
+    import shutil
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "t.c"
+    src.write_text('#include "focr.h"\nint main(void) { return focr_version() > 0 ? 0 : 1; }\n')
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
