@@ -14,12 +14,64 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+def cpu_baseline(kind: str, batch: int = 8, steps: int = 2):
+    """the reference's own CPU path for this step, timed on the host cores: the oracle restatement (oracle/sld_oracle.py /
+    ids_oracle.py, pinned to the unmodified reference modules) - forward, loss, backward, Adadelta - torch CPU fp32, all threads.
+    The one place outside tests/ where oracle/ may run (bench `cpu_baseline` leg); a reported baseline, not a target."""
+    import time
+    import torch
+    from oracle import ids_oracle as IO, sld_oracle as SO, synth
+    torch.set_num_threads(os.cpu_count())
+    ids = kind == "ids"
+    sd = synth.synth_state_dict(synth.load_spec("ids" if ids else "sld"), 1234)
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items() if v.is_floating_point() and "running" not in k}
+    state = {k: (torch.zeros_like(v), torch.zeros_like(v)) for k, v in params.items()}
+    full = dict(sd)
+    full.update(params)
+    if ids:
+        image, labels = IO.synth_batch(batch)
+        length, text_input, text_gt = IO.converter(labels)
+        feats = IO.synth_text_features()
+    else:
+        image, strings = SO.synth_batch(batch)
+        length, text_input, text_gt = SO.converter_stroke(strings)
+
+    def step():
+        for v in params.values():
+            v.grad = None
+        stats = {}
+        if ids:
+            loss = IO.loss_fn(full, image, length, text_input, text_gt, feats, stats)[0]
+        else:
+            loss = SO.loss_fn(full, image, length, text_input, text_gt, None, stats)[0]
+        loss.backward()
+        with torch.no_grad():
+            for k, v in params.items():
+                if v.grad is None:
+                    continue
+                p2, sq, acc = SO.adadelta_update(v, v.grad, *state[k], wd=1e-4 if ids else 0.0)
+                v.copy_(p2)
+                state[k] = (sq, acc)
+            for k, v in stats.items():
+                full[k] = v
+        return float(loss)
+    step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": batch / dt, "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"oracle {kind} train step (torch CPU fp32, {os.cpu_count()} threads), batch {batch}, {steps} timed steps "
+                      f"({dt:.2f} s/step)"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--width", type=int, default=32)
+    ap.add_argument("--cpu-baseline", action="store_true", help="also time the oracle's CPU step on rank 0 (adds ~20-60 s)")
     ap.add_argument("--model", choices=("sld", "ids"), default="sld",
                     help="ids: image-ids-CTR recogniser (SURVEY A22), 32x256 crops, CLIP-feature similarity loss, weight decay 1e-4")
     args = ap.parse_args()
@@ -106,7 +158,8 @@ def main():
                                                  (f"SLD Transformer('stroke') train step, 32x{args.width} crops, batch {B} per GPU, "
                                                   "CE + Adadelta(lr 1, rho 0.9), dropout 0.1"), "T": T},
                           "tflops_required": flop / (ms / K / 1e3) / 1e12, "launches_per_step": (L.lib.focr_launch_count() - n0) / K,
-                          "final_loss": float(loss), "ranks_identical": ranks_identical, "breakdown_ms_per_step": dict(top)}))
+                          "final_loss": float(loss), "ranks_identical": ranks_identical, "breakdown_ms_per_step": dict(top),
+                          "cpu_baseline": cpu_baseline(args.model) if args.cpu_baseline else None}))
     if world > 1:
         dist.destroy_process_group()
 
