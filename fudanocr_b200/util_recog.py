@@ -1,0 +1,86 @@
+"""Label encoders of the trainable recognisers - host-side mirrors of ``util.converter`` of stroke-level-decomposition
+(util.py:90-116) and image-ids-CTR (util.py:101-127).  The reference builds its three tensors ON the GPU one element at a time from
+Python (a device write + sync per character); here they are assembled on the host with numpy and uploaded once, non-blocking.
+Same results, same return order: ``(length, text_input, text_gt, labels)``.
+
+  text_input[i, 0] = 0 (start) and text_input[i, j + 1] = index of the j-th symbol, for all but the last symbol;
+  text_gt = the symbols of all samples, concatenated (image-ids-CTR forces the last symbol of each sample to 'END').
+"""
+from __future__ import annotations
+
+from typing import Dict, Mapping, Optional, Sequence
+
+import numpy as np
+import torch
+
+ALPHABET_STROKE = "<12345$"                                            # stroke-level-decomposition/util.py:14
+
+
+def load_stroke_table(path: str) -> Dict[str, str]:
+    """data/decompose-stroke-3755.txt -> {character: stroke string}  (stroke-level-decomposition/util.py:26-30)"""
+    table = {}
+    with open(path, "r", encoding="utf-8") as f:
+        for line in f:
+            word, _, strokes = line.split()
+            table[word] = strokes.strip()
+    return table
+
+
+def _assemble(symbols: Sequence[Sequence[int]], device):
+    B = len(symbols)
+    length = np.array([len(s) for s in symbols], np.int64)
+    if B == 0 or length.min() < 1:
+        raise ValueError("converter: every label needs at least one symbol")
+    T = int(length.max())
+    text_input = np.zeros((B, T), np.int64)
+    for i, s in enumerate(symbols):
+        text_input[i, 1:len(s)] = s[:-1]
+    text_gt = np.concatenate([np.asarray(s, np.int64) for s in symbols])
+    out = [torch.from_numpy(a) for a in (length, text_input, text_gt)]
+    if device is not None:
+        out = [t.pin_memory().to(device, non_blocking=True) if torch.cuda.is_available() else t.to(device) for t in out]
+    return out
+
+
+def converter_sld(mode: str, label: Sequence[str], character_to_strokelist: Optional[Mapping[str, str]] = None,
+                  alp2num_character: Optional[Mapping[str, int]] = None, device="cuda"):
+    """stroke-level-decomposition/util.py:90-116.  mode 'stroke': label[i][0] is decomposed through `character_to_strokelist`
+    and terminated by '$'; mode 'character': the label string itself over `alp2num_character`."""
+    if mode == "stroke":
+        if character_to_strokelist is None:
+            raise ValueError("converter_sld('stroke', ...) needs the character -> stroke table")
+        strings = [character_to_strokelist[i[0]] + "$" for i in label]
+        a2n = {c: i for i, c in enumerate(ALPHABET_STROKE)}
+    elif mode == "character":
+        if alp2num_character is None:
+            raise ValueError("converter_sld('character', ...) needs alp2num_character")
+        strings, a2n = [i for i in label], alp2num_character
+    else:
+        raise ValueError(f"unknown mode {mode!r}")
+    length, text_input, text_gt = _assemble([[a2n[c] for c in s] for s in strings], device)
+    return length, text_input, text_gt, label
+
+
+def converter_ids(label: Sequence[str], alp2num_character: Mapping[str, int], device="cuda"):
+    """image-ids-CTR/util.py:101-127: the last position of every label stands for 'END' in the target (whatever character the
+    string carries there), and is never fed to the decoder"""
+    end = alp2num_character["END"]
+    symbols = []
+    for s in label:
+        idx = [alp2num_character[c] for c in s[:-1]]
+        symbols.append(idx + [end])
+    length, text_input, text_gt = _assemble(symbols, device)
+    return length, text_input, text_gt, label
+
+
+def cosine_warm_restarts_lr(epoch: int, base_lr: float = 1.0, T_0: int = 10, T_mult: int = 1, eta_min: float = 0.0) -> float:
+    """learning rate of torch.optim.lr_scheduler.CosineAnnealingWarmRestarts(optimizer, T_0=10, T_mult=1) after `epoch` calls of
+    scheduler.step() (image-ids-CTR/train.py:29): the value to pass as ``IDSTrainer.step(..., lr=...)``"""
+    import math
+    if T_mult == 1:
+        t_cur, t_i = epoch % T_0, T_0
+    else:
+        n = int(math.log(epoch / T_0 * (T_mult - 1) + 1, T_mult)) if epoch >= T_0 else 0
+        t_cur = epoch - T_0 * (T_mult ** n - 1) // (T_mult - 1)
+        t_i = T_0 * T_mult ** n
+    return eta_min + (base_lr - eta_min) * (1 + math.cos(math.pi * t_cur / t_i)) / 2

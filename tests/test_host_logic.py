@@ -292,3 +292,44 @@ def test_header_is_plain_c(tmp_path):
     r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_label_converters_match_the_reference_semantics():
+    """fudanocr_b200/util_recog.py vs the oracle restatements of util.converter (both pinned to the unmodified reference
+    converters inside oracle/make_golden_sld.py / make_golden_ids.py)"""
+    from fudanocr_b200 import util_recog as U
+    from oracle import ids_oracle as IO, sld_oracle as SO
+    table = {"甲": "25112", "乙": "5", "丙": "12534"}
+    labels = [["甲"], ["乙"], ["丙"], ["乙"]]
+    length, text_input, text_gt, back = U.converter_sld("stroke", labels, table, device=None)
+    o_len, o_in, o_gt = SO.converter_stroke([table[l[0]] + "$" for l in labels])
+    assert torch.equal(length, o_len) and torch.equal(text_input, o_in) and torch.equal(text_gt, o_gt) and back is labels
+    assert text_input[:, 0].eq(0).all() and text_gt[5] == 6            # start column, '$' closes the first sample
+    a2n = {"START": 0, "天": 1, "地": 2, "人": 3, "END": 4}
+    strings = ["天地#", "人#", "地人天#"]
+    length, text_input, text_gt, _ = U.converter_ids(strings, a2n, device=None)
+    import oracle.ids_oracle as _io
+    old = _io.N_CLASS
+    _io.N_CLASS = 5                                                    # the oracle writes END as N_CLASS - 1
+    try:
+        o_len, o_in, o_gt = IO.converter([[a2n[c] for c in s[:-1]] + [0] for s in strings])
+    finally:
+        _io.N_CLASS = old
+    assert torch.equal(length, o_len) and torch.equal(text_input, o_in) and torch.equal(text_gt, o_gt)
+    assert text_gt.tolist() == [1, 2, 4, 3, 4, 2, 3, 1, 4]
+    with pytest.raises(ValueError):
+        U.converter_sld("stroke", labels, None, device=None)
+    with pytest.raises(KeyError):
+        U.converter_sld("stroke", [["丁"]], table, device=None)
+
+
+def test_cosine_warm_restarts_matches_torch_scheduler():
+    from fudanocr_b200.util_recog import cosine_warm_restarts_lr
+    for T_0, T_mult in ((10, 1), (3, 2)):
+        p = torch.nn.Parameter(torch.zeros(1))
+        opt = torch.optim.Adadelta([p], lr=1.0, rho=0.9, weight_decay=1e-4)
+        sch = torch.optim.lr_scheduler.CosineAnnealingWarmRestarts(opt, T_0=T_0, T_mult=T_mult)
+        for epoch in range(0, 45):
+            assert abs(opt.param_groups[0]["lr"] - cosine_warm_restarts_lr(epoch, 1.0, T_0, T_mult)) < 1e-9, (T_0, T_mult, epoch)
+            opt.step()
+            sch.step()
