@@ -84,3 +84,35 @@ def cosine_warm_restarts_lr(epoch: int, base_lr: float = 1.0, T_0: int = 10, T_m
         t_cur = epoch - T_0 * (T_mult ** n - 1) // (T_mult - 1)
         t_i = T_0 * T_mult ** n
     return eta_min + (base_lr - eta_min) * (1 + math.cos(math.pi * t_cur / t_i)) / 2
+
+
+@torch.no_grad()
+def greedy_decode_sld(model, image: torch.Tensor, max_length: int = 30):
+    """The autoregressive test-time loop of stroke-level-decomposition/train.py:110-121 on the drop-in module: encoder once
+    (features re-entered through ``conv_feature``), then per step the decoder on the growing prefix, arg-max of the last position.
+    Returns (pred (B, max_length + 1) int64 with the start symbol 0 in column 0, prob (B, max_length) fp32 = the winning softmax
+    probability of each step, sequences (list of B index lists cut after the first '$' = last alphabet entry, start dropped),
+    overall_prob (B) = product of the step probabilities up to the cut, train.py:123-137)."""
+    B = image.shape[0]
+    dev = image.device
+    pred = torch.zeros(B, 1, dtype=torch.long, device=dev)
+    prob = torch.zeros(B, max_length, dtype=torch.float32, device=dev)
+    feats = None
+    for i in range(max_length):
+        length = torch.full((B,), i + 1, dtype=torch.long, device=dev)
+        result = model(image, length, pred, conv_feature=feats, test=True)
+        last = torch.softmax(result["pred"][:, -1, :].float(), 1)
+        p, now = last.max(1)
+        prob[:, i] = p
+        pred = torch.cat((pred, now.view(-1, 1)), 1)
+        feats = result["conv"]
+    end = model.word_n_class - 1
+    pred_h, prob_h = pred.cpu(), prob.cpu()
+    sequences, overall = [], []
+    for b in range(B):
+        row = pred_h[b].tolist()
+        cut = next((j for j in range(max_length) if row[j] == end), max_length - 1)     # train.py:126-131 scans columns 0..max-1
+        kept = row[:cut + 1]
+        sequences.append(kept[1:])
+        overall.append(float(torch.prod(prob_h[b, :max(len(kept) - 1, 0)])))
+    return pred, prob, sequences, overall

@@ -125,3 +125,36 @@ def test_assembled_model_with_dropout_on_matches_oracle_with_the_rng_twin_masks(
               "decoder.mask_multihead.linears.0.weight", "embedding_word.lut.weight", "decoder.mul_layernorm2.a"):
         a, b = dict(model.named_parameters())[k].grad, osd[k].grad
         assert float((a - b).norm() / b.norm()) < 2e-3, k
+
+
+def test_greedy_decode_follows_the_reference_test_loop(monkeypatch):
+    """util_recog.greedy_decode_sld on the (mock-backed) drop-in module vs the loop of train.py:110-137 written out on the oracle"""
+    from fudanocr_b200.util_recog import greedy_decode_sld
+    model, g, image = _setup(monkeypatch)
+    model.eval()
+    sd = synth.synth_state_dict(synth.load_spec("sld"), 1234)
+    max_length = 5
+    pred, prob, seqs, overall = greedy_decode_sld(model, image, max_length)
+    # reference loop on the oracle
+    B = image.shape[0]
+    with torch.no_grad():
+        o_pred = torch.zeros(B, 1, dtype=torch.long)
+        o_prob = torch.zeros(B, max_length)
+        feats = None
+        for i in range(max_length):
+            prediction, _, feats = SO.forward(sd, image, o_pred, train=False, conv_feature=feats)
+            now_pred = torch.max(torch.softmax(prediction, 2), 2)[1]
+            o_prob[:, i] = torch.max(torch.softmax(prediction, 2), 2)[0][:, -1]
+            o_pred = torch.cat((o_pred, now_pred[:, -1].view(-1, 1)), 1)
+    assert torch.equal(pred, o_pred) and torch.allclose(prob, o_prob, rtol=1e-4, atol=1e-6)
+    for b in range(B):
+        now = []
+        for j in range(max_length):
+            now.append(int(o_pred[b][j]))
+            if int(o_pred[b][j]) == 6:
+                break
+        assert seqs[b] == now[1:]
+        op = 1.0
+        for j in range(len(now) - 1):
+            op *= float(o_prob[b][j])
+        assert abs(overall[b] - op) < 1e-6
