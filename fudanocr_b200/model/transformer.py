@@ -25,11 +25,17 @@ from . import recog_ops as ops
 ALPHABET_STROKE = "<12345$"  # stroke-level-decomposition/util.py:14
 
 
-def get_alphabet(mode: str) -> str:
-    if mode != "stroke":
-        raise NotImplementedError("focr Transformer: mode 'stroke' (config.py:5); the 3755-class character mode needs a "
-                                  "generator wider than one 64-column tile")
-    return ALPHABET_STROKE
+def get_alphabet(mode: str, alphabet=None):
+    """util.get_alphabet (stroke-level-decomposition/util.py:119-123): the 7 stroke symbols, or - mode 'character' - the caller's
+    character alphabet ('<' + the 3755 GB2312 level-1 characters + '$' in the reference, util.py:21: data, not code, so it is
+    passed in rather than restated here)"""
+    if mode == "stroke":
+        return ALPHABET_STROKE
+    if mode == "character":
+        if alphabet is None:
+            raise ValueError("focr Transformer(mode='character') needs alphabet=<the character alphabet of util.py:21>")
+        return alphabet
+    raise ValueError(f"unknown mode {mode!r} (config.py:5: 'character' / 'stroke')")
 
 
 def _bf(t):
@@ -348,10 +354,10 @@ class Transformer(nn.Module):
 
     DROPOUT = 0.1  # transformer.py:292,295,297,326 and PositionwiseFeedForward default
 
-    def __init__(self, mode: str = "stroke"):
+    def __init__(self, mode: str = "stroke", alphabet=None):
         super().__init__()
         self.mode = mode
-        self.word_n_class = len(get_alphabet(mode))
+        self.word_n_class = len(get_alphabet(mode, alphabet))
         self.embedding_word = _Embeddings(512, self.word_n_class)
         self.pe = _PositionalEncoding(512)
         self.encoder = _ResNet(3, [3, 4, 6, 3])
@@ -431,10 +437,11 @@ class Transformer(nn.Module):
         return r3, amap
 
     def decode(self, feat: torch.Tensor, text_input: torch.Tensor):
-        """-> (logits fp32 (rows_pad, 64): generator over the 7 symbols padded to one GEMM tile, map)"""
+        """-> (logits fp32 (rows_pad, n_class padded to a GEMM tile): generator over the alphabet, map)"""
         r3, amap = self.decode_hidden(feat, text_input)
         g = self.generator_word.proj
-        npad = 64 - g.weight.shape[0]
+        n = g.weight.shape[0]
+        npad = (-n) % (64 if n <= 64 else 128)     # one 64-column tile for the stroke alphabet, 128-column tiles beyond
         logits = _Linear.apply(r3, F.pad(g.weight, (0, 0, 0, npad)), F.pad(g.bias, (0, npad)), False, True)
         return logits, amap
 

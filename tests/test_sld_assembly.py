@@ -158,3 +158,36 @@ def test_greedy_decode_follows_the_reference_test_loop(monkeypatch):
         for j in range(len(now) - 1):
             op *= float(o_prob[b][j])
         assert abs(overall[b] - op) < 1e-6
+
+
+def test_character_mode_assembles_with_a_wide_generator(monkeypatch):
+    """mode 'character' (config.py:5): the generator / embedding span the caller's alphabet (3757 symbols in the reference); checked
+    here with a 300-symbol alphabet against the oracle on the same weights (loss and the generator / embedding gradients)"""
+    import _recog_mock
+    _recog_mock.install(monkeypatch)
+    from fudanocr_b200.model.transformer import Transformer
+    alphabet = "<" + "".join(chr(0x4e00 + i) for i in range(298)) + "$"
+    model = Transformer("character", alphabet=alphabet)
+    assert model.word_n_class == 300 and model.generator_word.proj.weight.shape == (300, 1024)
+    assert model.embedding_word.lut.weight.shape == (300, 512)
+    with __import__("pytest").raises(ValueError):
+        Transformer("character")
+    spec = dict(synth.load_spec("sld"))
+    spec["embedding_word.lut.weight"], spec["generator_word.proj.weight"], spec["generator_word.proj.bias"] = [300, 512], [300, 1024], [300]
+    sd = synth.synth_state_dict(spec, 99)
+    model.load_state_dict(sd, strict=False)
+    model.train()
+    model.dropout_p = 0.0
+    image, _ = SO.synth_batch(2)
+    length = torch.tensor([2, 2])                                    # character mode: one character + '$' (train.py:93-96)
+    text_input = torch.tensor([[0, 17], [0, 250]])
+    text_gt = torch.tensor([17, 299, 250, 299])
+    loss = model.loss(image, length, text_input, text_gt)
+    osd = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in sd.items()}
+    o_loss, *_ = SO.loss_fn(osd, image, length, text_input, text_gt)
+    assert abs(float(loss) - float(o_loss)) < 1e-4 * float(o_loss)
+    loss.backward()
+    o_loss.backward()
+    for k in ("generator_word.proj.weight", "generator_word.proj.bias", "embedding_word.lut.weight"):
+        a, b = dict(model.named_parameters())[k].grad, osd[k].grad
+        assert float((a - b).norm() / b.norm()) < 2e-3, k
