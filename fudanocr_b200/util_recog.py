@@ -116,3 +116,27 @@ def greedy_decode_sld(model, image: torch.Tensor, max_length: int = 30):
         sequences.append(kept[1:])
         overall.append(float(torch.prod(prob_h[b, :max(len(kept) - 1, 0)])))
     return pred, prob, sequences, overall
+
+
+@torch.no_grad()
+def greedy_decode_ids(model, image: torch.Tensor, text_features: torch.Tensor, max_length: int):
+    """The test-time loop of image-ids-CTR/train.py:118-134 on the drop-in module: per step the last position's 2048-d prediction
+    is L2-normalised and matched against the text features; arg-max / winning softmax probability as in the reference.
+    Returns (pred (B, max_length + 1) int64 with the start symbol in column 0, prob (B, max_length) fp32)."""
+    B = image.shape[0]
+    dev = image.device
+    tf = text_features.to(dev).float()
+    pred = torch.zeros(B, 1, dtype=torch.long, device=dev)
+    prob = torch.zeros(B, max_length, dtype=torch.float32, device=dev)
+    feats = None
+    for i in range(max_length):
+        length = torch.full((B,), i + 1, dtype=torch.long, device=dev)
+        result = model(image, length, pred, conv_feature=feats, test=True)
+        prediction = result["pred"][:, -1, :].float()
+        prediction = prediction / prediction.norm(dim=1, keepdim=True)
+        sm = torch.softmax(prediction @ tf.t(), 1)
+        p, now = sm.max(1)
+        prob[:, i] = p
+        pred = torch.cat((pred, now.view(-1, 1)), 1)
+        feats = result["conv"]
+    return pred, prob

@@ -75,3 +75,27 @@ def test_ids_forward_contract(monkeypatch):
         assert torch.allclose(ev["pred"][:, :, ::8], g["eval_pred_sample"], rtol=1e-3, atol=1e-3)
         ev2 = model(None, g["length"], g["text_input"], conv_feature=ev["conv"], test=True)
         assert torch.equal(ev2["pred"], ev["pred"])
+
+
+def test_ids_greedy_decode_follows_the_reference_test_loop(monkeypatch):
+    """util_recog.greedy_decode_ids on the (mock-backed) drop-in module vs the loop of train.py:118-134 written out on the oracle"""
+    from fudanocr_b200.util_recog import greedy_decode_ids
+    model, g, image, tf = _setup(monkeypatch)
+    model.eval()
+    sd = synth.synth_state_dict(synth.load_spec("ids"), 4321)
+    max_length = 3
+    pred, prob = greedy_decode_ids(model, image, tf, max_length)
+    B = image.shape[0]
+    with torch.no_grad():
+        o_pred = torch.zeros(B, 1, dtype=torch.long)
+        o_prob = torch.zeros(B, max_length)
+        feats = None
+        for i in range(max_length):
+            out, _, feats = IO.forward(sd, image, o_pred, train=False, conv_feature=feats)
+            prediction = out[:, -1:, :].squeeze()
+            prediction = prediction / prediction.norm(dim=1, keepdim=True)
+            prediction = prediction @ tf.t()
+            now_pred = torch.max(torch.softmax(prediction, 1), 1)[1]
+            o_prob[:, i] = torch.max(torch.softmax(prediction, 1), 1)[0]
+            o_pred = torch.cat((o_pred, now_pred.view(-1, 1)), 1)
+    assert torch.equal(pred, o_pred) and torch.allclose(prob, o_prob, rtol=1e-3, atol=1e-6)
