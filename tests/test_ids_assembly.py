@@ -99,3 +99,16 @@ def test_ids_greedy_decode_follows_the_reference_test_loop(monkeypatch):
             o_prob[:, i] = torch.max(torch.softmax(prediction, 1), 1)[0]
             o_pred = torch.cat((o_pred, now_pred.view(-1, 1)), 1)
     assert torch.equal(pred, o_pred) and torch.allclose(prob, o_prob, rtol=1e-3, atol=1e-6)
+
+
+def test_ids_checkpoint_round_trip_under_the_data_parallel_wrapper():
+    """image-ids-CTR saves / resumes the nn.DataParallel-wrapped model (train.py:23-27,100): 'module.'-prefixed keys"""
+    from fudanocr_b200.interfaces.parallel import DataParallel
+    from fudanocr_b200.model.ids_transformer import Transformer
+    spec = synth.load_spec("ids")
+    a, b = DataParallel(Transformer(40)), DataParallel(Transformer(40))
+    keys = [k for k in a.state_dict().keys() if k != "module.pe.pe"]
+    assert keys == ["module." + k for k in spec.keys()]
+    b.load_state_dict(a.state_dict())
+    assert all(torch.equal(v, b.state_dict()[k]) for k, v in a.state_dict().items())
+    assert a.module.word_n_class == 40 and len(list(a.parameters())) == len(list(a.module.parameters()))
