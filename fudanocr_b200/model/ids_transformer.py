@@ -58,9 +58,9 @@ class Transformer(_SLDTransformer):
     def encode(self, image: torch.Tensor) -> torch.Tensor:
         """(B, 3, 32, 256) fp32 -> (B, 2, 16, 1024) bf16 NHWC (ResNet.forward, :126-152: conv-bn-relu-pool, conv-bn-relu, then three
         [pool, BasicBlocks, conv-bn-relu] stages)"""
-        ops.require_cuda(image)
         if image.dim() != 4 or image.shape[1] != 3 or image.shape[2] % 16 or image.shape[3] % 16:
             raise ValueError(f"focr IDS Transformer: image must be (B,3,H,W) with H and W multiples of 16, got {tuple(image.shape)}")
+        ops.require_cuda(image)
         e = self.encoder
         x = _ConvFirst.apply(image.float().contiguous(), e.conv1.weight, e.conv1.bias)
         x = _MaxPool.apply(self._bn(x, e.bn1, ops.ACT_RELU))

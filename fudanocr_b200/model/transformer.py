@@ -389,10 +389,10 @@ class Transformer(nn.Module):
 
     def encode(self, image: torch.Tensor) -> torch.Tensor:
         """(B, 3, H, W) fp32 -> (B, H/2, W/2, 1024) bf16 NHWC feature map (ResNet.forward, transformer.py:126-164)"""
-        ops.require_cuda(image)
         if image.dim() != 4 or image.shape[1] != 3 or image.shape[2] % 2 or image.shape[3] // 2 not in (16, 32, 64, 128):
             raise ValueError(f"focr Transformer: image must be (B,3,H,W) with even H and W in {{32,64,128,256}}, got "
                              f"{tuple(image.shape)}")
+        ops.require_cuda(image)
         e = self.encoder
         x = _ConvFirst.apply(image.float().contiguous(), e.conv1.weight, e.conv1.bias)
         x = _MaxPool.apply(self._bn(x, e.bn1, ops.ACT_RELU))

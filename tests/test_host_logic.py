@@ -333,3 +333,35 @@ def test_cosine_warm_restarts_matches_torch_scheduler():
             assert abs(opt.param_groups[0]["lr"] - cosine_warm_restarts_lr(epoch, 1.0, T_0, T_mult)) < 1e-9, (T_0, T_mult, epoch)
             opt.step()
             sch.step()
+
+
+def test_recogniser_ops_have_no_cpu_fallback():
+    """every kernel wrapper of the trainable recognisers refuses CPU tensors (the product path never computes in torch)"""
+    from fudanocr_b200 import _lib as L
+    from fudanocr_b200.model import recog_ops as ops
+    from fudanocr_b200.model.transformer import Transformer
+    from fudanocr_b200.model.ids_transformer import Transformer as IDSTransformer
+    bf = torch.bfloat16
+    x = torch.zeros(2, 16, 16, 64, dtype=bf)
+    w, b = torch.zeros(64, 64, 3, 3), torch.zeros(64)
+    tok = torch.zeros(128, 1024, dtype=bf)
+    calls = [
+        lambda: ops.conv_fwd(x, w, b), lambda: ops.conv_dgrad(x, w), lambda: ops.conv_wgrad(x, x, (64, 64, 3, 3)),
+        lambda: ops.conv_first_fwd(torch.zeros(2, 3, 32, 32), torch.zeros(64, 3, 3, 3), b),
+        lambda: ops.bn_train_fwd(x, b, b, b.clone(), b.clone(), torch.zeros((), dtype=torch.long), 2),
+        lambda: ops.bn_eval_fwd(x, b, b, b, b, 0), lambda: ops.add_relu(x, x), lambda: ops.relu_bwd(x, x), lambda: ops.maxpool_fwd(x),
+        lambda: ops.dropout(x, 0.1, 1, 2), lambda: ops.linear_fwd(tok, torch.zeros(64, 1024), b),
+        lambda: ops.linear_dgrad(tok, torch.zeros(1024, 64)), lambda: ops.linear_wgrad(tok, tok),
+        lambda: ops.mha_fwd(tok, tok, tok, 2, 4, 256, 8, 8, 1, 0.0, 0, 0),
+        lambda: ops.ln_fwd(tok, tok, torch.ones(1024), torch.zeros(1024)),
+        lambda: ops.embed_fwd(torch.zeros(2, 4, dtype=torch.long), torch.zeros(7, 512), 128, 0.0, 0, 0),
+        lambda: ops.packed_ce(torch.zeros(128, 64), 2, 4, 7, torch.tensor([4, 4]), torch.zeros(8, dtype=torch.long)),
+        lambda: ops.l2norm_fwd(torch.zeros(128, 2048)),
+        lambda: Transformer("stroke")(torch.zeros(2, 3, 32, 32), torch.tensor([2, 2]), torch.zeros(2, 2, dtype=torch.long)),
+        lambda: IDSTransformer(20)(torch.zeros(4, 3, 32, 256), torch.tensor([2] * 4), torch.zeros(4, 2, dtype=torch.long)),
+    ]
+    for i, c in enumerate(calls):
+        with pytest.raises(L.FocrError):
+            c()
+    with pytest.raises(ValueError):
+        Transformer("stroke").encode(torch.zeros(2, 3, 32, 320))      # 16 x 160 maps: not tiled yet (DESIGN.md)
