@@ -1,31 +1,49 @@
 #!/usr/bin/env python
-"""bench.py — TBSRN training throughput on the focr sm_100a engine (BASELINE.json configs[1]:
-"TBSRN train step bf16, batch 256 synthetic TextZoom-shaped crops, 1xB200").
+"""bench.py - training / evaluation throughput of the focr sm_100a engine on the BASELINE.json configurations.
 
-    python bench.py --gpus N --steps K --warmup W            # this repo (one process per GPU under torchrun)
-    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host CPU cores
+    python bench.py --gpus N --steps K --warmup W                      # headline: BASELINE configs[1] (TBSRN train, b256)
+    python bench.py --config {2,3,4,5} [--scaling {weak,strong}] ...   # BASELINE configs[1..4] (1-based: --config 2 = configs[1])
+    python bench.py --impl reference [--config C] --steps K --warmup W # the reference algorithm on the host CPU cores
 
-A step = forward + MSE loss (x100) + backward + clip_grad_norm_(0.25) + Adam on one batch of 256 synthetic
-16x64 -> 32x128 crops per GPU (weak scaling: the global batch is 256*N), dropout ON (p = 0.1), STN ON,
-random-init weights of the reference architecture, bf16 tensor-core compute with fp32 accumulation and
-fp32 master weights/optimizer.  Prints ONE JSON line on rank 0.
+    --config 2  TBSRN train step (STN on, dropout 0.1, MSE x100, clip 0.25, Adam), 256 crops / GPU          [default]
+    --config 3  text-gestalt TSRN + StrokeFocusLoss(lambda 50) train step, 32 crops / GPU (global 256 on 8 GPUs)
+    --config 4  stroke-level-decomposition Transformer('stroke') train step (CE + Adadelta), 64 crops / GPU (global 512 on 8)
+    --config 5  joint TBSRN -> CRNN + greedy CTC evaluation pipeline, 128 crops / GPU (global 1024 on 8)
+
+`--scaling weak` keeps the per-GPU batch above as N grows; `--scaling strong` splits BASELINE's GLOBAL batch (256 / 256 / 512 /
+1024) over the N ranks.  The default run (config 2, weak) additionally times the strong-scaling point of config 2 (global 256
+split over N) and reports it under "strong_scaling" in the same JSON line.  One process per GPU under torchrun; rank 0 prints
+ONE JSON line.
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
+import random
 import statistics
+import string
 import subprocess
 import sys
 import threading
 import time
+import types
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-BATCH = 256
-METRIC = "tbsrn_train_images_per_sec"
+WEAK_BATCH = {2: 256, 3: 32, 4: 64, 5: 128}        # crops per GPU
+GLOBAL_BATCH = {2: 256, 3: 256, 4: 512, 5: 1024}   # BASELINE.json's batch (strong scaling splits it over the ranks)
+METRIC = {2: "tbsrn_train_images_per_sec", 3: "tsrn_strokefocus_train_images_per_sec",
+          4: "sld_train_images_per_sec", 5: "tbsrn_crnn_eval_images_per_sec"}
+WORKLOAD = {
+    2: "TBSRN train step (STN on, dropout 0.1, MSE loss x100, clip 0.25, Adam 1e-4), LR 16x64 -> HR 32x128 (BASELINE configs[1])",
+    3: "TSRN (STN) + StrokeFocusLoss(lambda 50) train step (frozen recogniser: HR fwd, SR fwd, SR input-gradient chain), "
+       "clip 0.25, Adam (BASELINE configs[2])",
+    4: "stroke-level-decomposition Transformer('stroke') train step, 32x32 crops (the reference's size; 32x320 per "
+       "--width 320), CE + Adadelta(lr 1, rho 0.9), dropout 0.1 (BASELINE configs[3])",
+    5: "TBSRN eval -> PSNR/SSIM -> bicubic+gray -> CRNN -> greedy CTC decode, strings on the host (BASELINE configs[4])",
+}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -83,35 +101,9 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-# algorithmic work per STEP of each kernel family at per-GPU batch B (FLOP = 2*MAC; bytes = compulsory traffic)
-def algo_work(B: int):
-    T, Thr = B * 1024, B * 4096
-    g = 2.0 * 1024 * 1024 * 32  # one 1024x1024x32 GEMM
-    lin_fwd = 2.0 * T * 128 * (384 + 128 + 128 + 128 + 64)
-    w = {
-        "attn_fwd": ("tensor", 5 * B * 4 * 2 * g),
-        "attn_bwd_dq": ("tensor", 5 * B * 4 * 3 * g),
-        "attn_bwd_dkv": ("tensor", 5 * B * 4 * 4 * g),
-        "tc_conv3x3": ("tensor", 2.0 * T * 576 * (11 * 64 + 256) + 2.0 * T * 576 * 11 * 64 + 2.0 * T * 2304 * 64),
-        "tc_linear": ("tensor", 5 * 2 * lin_fwd),  # forward + input-gradient GEMMs (STN GEMMs are noise)
-        "tc_conv9tap": ("tensor", 2.0 * T * 576 * 64 * 2 + 2.0 * Thr * 576 * 64 * 2),
-        "linear_wgrad": ("tensor", 5 * lin_fwd),
-        "conv3x3_wgrad": ("tensor", 2.0 * T * 576 * (11 * 64 + 256)),
-        "conv9x1_wgrad": ("tensor", 2.0 * T * 576 * 64 + 2.0 * Thr * 576 * 64),
-        # HBM-bound families: bytes read + written once
-        "bn_stats": ("hbm", 11 * T * 64 * 2.0),
-        "bn_apply": ("hbm", (5 * (2 * T * 64 * 2 + T * 64 * 2 + T * 128 * 2) + 3 * T * 64 * 2.0)),
-        "bn_bwd": ("hbm", 11 * 5 * T * 64 * 2.0),
-        "ln_fwd": ("hbm", 10 * 2 * T * 128 * 2.0),
-        "ln_bwd": ("hbm", 10 * 3 * T * 128 * 2.0),
-        "colsum": ("hbm", 5 * (T * 2.0 * (384 + 128 * 3 + 64 + 64 * 2)) + 3 * T * 64 * 2.0),
-    }
-    return w
-
-
 def ncu_traffic(scope: str):
-    """DRAM read+write bytes per launch of the kernel behind `scope`, from the committed `ncu --set full` capture
-    (profiles/r01_dram_traffic_bytes.json, produced by scripts/summarize_profiles.py); None if not captured."""
+    """DRAM read+write bytes per launch of the kernel behind `scope`, from the newest committed `ncu --set full` digest
+    (profiles/*_dram_traffic_bytes.json, produced by scripts/summarize_profiles.py); None if not captured."""
     for name in sorted(os.listdir(os.path.join(ROOT, "profiles")), reverse=True):
         if name.endswith("_dram_traffic_bytes.json"):
             d = json.load(open(os.path.join(ROOT, "profiles", name)))
@@ -128,54 +120,375 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="focr", choices=["focr", "reference"])
-    ap.add_argument("--batch", type=int, default=BATCH, help=argparse.SUPPRESS)
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5],
+                    help="BASELINE.json configuration, 1-based (2 = configs[1], the headline)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--batch", type=int, default=0, help=argparse.SUPPRESS)   # per-GPU override (tuning runs)
+    ap.add_argument("--width", type=int, default=32, help="config 4: crop width (32 = reference, 320 = BASELINE variant)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-strong-point", action="store_true", help="config 2: skip the extra strong-scaling measurement")
     return ap.parse_args()
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_oracle_rate(batch: int, steps: int, warmup: int):
-    """The reference algorithm (oracle restatement of the STT step body, pinned to the real modules by
-    tests/golden) on the host CPU cores: images/s on a bounded sample of the workload."""
-    import torch
-    from oracle import synth, tbsrn_oracle as O
-    # torch's CPU kernels stop scaling (and then regress) past a few dozen threads at these tensor sizes:
-    # use up to 32 of the host cores and report the number actually used
-    cores = min(os.cpu_count() or 1, 32)
-    torch.set_num_threads(cores)
-    sd = synth.synth_state_dict(synth.load_spec("tbsrn"), 1234, O.tps_buffers())
-    lr, hr = synth.synth_images(batch)
-    g = torch.Generator().manual_seed(0)
-    st = {}
-    times = []
-    for it in range(warmup + steps):
-        masks = {}
-        for i in range(5):  # dropout on, as in training
-            masks[f"block{i + 2}.feature_enhancer.attn"] = torch.rand(batch, 4, 1024, 1024, generator=g) >= 0.1
-            masks[f"block{i + 2}.feature_enhancer.ffn"] = torch.rand(batch, 1024, 128, generator=g) >= 0.1
-        t0 = time.perf_counter()
-        sd, _ = O.train_step(sd, lr, hr, st, masks=masks)
-        dt = time.perf_counter() - t0
-        if it >= warmup:
-            times.append(dt)
-    return batch * len(times) / sum(times), cores, sum(times) / len(times)
+# Workloads.  Each: build() -> state; step(i) enqueues one step on device-resident inputs; step_e2e(i) copies the step's
+# inputs from pinned host memory first and reads the step's scalar result back; algo_work() = algorithmic FLOP / bytes per
+# STEP of each kernel family at the per-GPU batch (FLOP = 2 MAC; bytes = compulsory traffic), for the roofline line.
+# ------------------------------------------------------------------------------------------------
+class TBSRNTrain:
+    cfg, dtype = 2, "bf16"
+
+    def __init__(self, B, dev, rank, args):
+        import torch
+        from fudanocr_b200.model.tbsrn import TBSRN
+        from fudanocr_b200.trainer import TBSRNTrainer
+        self.B, self.torch = B, torch
+        torch.manual_seed(1234)  # yaml manualSeed (config/super_resolution.yaml:24); same init on every rank
+        self.model = TBSRN().to(dev)
+        self.model.train()
+        self.trainer = TBSRNTrainer(self.model)
+        g = torch.Generator(device=dev).manual_seed(1234 + rank)
+        self.lr = torch.rand(B, 3, 16, 64, device=dev, generator=g)
+        self.hr = torch.rand(B, 3, 32, 128, device=dev, generator=g)
+        self.lr_h, self.hr_h = self.lr.cpu().pin_memory(), self.hr.cpu().pin_memory()
+        self.h2d, self.d2h = int(self.lr_h.numel() * 4 + self.hr_h.numel() * 4), 4
+        self.extra = {"l2": "per-step working set (~6 GB of saved activations at batch 256) >> 126 MB L2; no explicit flush",
+                      "launch": "step replayed as CUDA graphs (fwd+loss+bwd [+ all-reduce] + clip+Adam), dropout seed read "
+                                "on device"}
+
+    def step(self, i):
+        return self.trainer.step(self.lr, self.hr, seed=i)
+
+    def step_e2e(self, i):
+        self.lr.copy_(self.lr_h, non_blocking=True)
+        self.hr.copy_(self.hr_h, non_blocking=True)
+        loss = self.trainer.step(self.lr, self.hr, seed=i)
+        return loss.cpu()  # the scalar a user logs every step (super_resolution.py:74-76)
+
+    def result(self):
+        return {"final_loss": float(self.trainer.loss.item())}
+
+    def algo_work(self):
+        B = self.B
+        T, Thr = B * 1024, B * 4096
+        g = 2.0 * 1024 * 1024 * 32  # one 1024x1024x32 GEMM
+        lin_fwd = 2.0 * T * 128 * (384 + 128 + 128 + 128 + 64)
+        return {
+            "attn_fwd": ("tensor", 5 * B * 4 * 2 * g),
+            "attn_bwd": ("tensor", 5 * B * 4 * 5 * g),      # single pass: S, dP, dV, dK, dQ
+            "attn_bwd_dq": ("tensor", 5 * B * 4 * 3 * g),
+            "attn_bwd_dkv": ("tensor", 5 * B * 4 * 4 * g),
+            "tc_conv3x3": ("tensor", 2.0 * T * 576 * (11 * 64 + 256) + 2.0 * T * 576 * 11 * 64 + 2.0 * T * 2304 * 64),
+            "tc_linear": ("tensor", 5 * 2 * lin_fwd),  # forward + input-gradient GEMMs (STN GEMMs are noise)
+            "tc_conv9tap": ("tensor", 2.0 * T * 576 * 64 * 2 + 2.0 * Thr * 576 * 64 * 2),
+            "linear_wgrad": ("tensor", 5 * lin_fwd),
+            "conv3x3_wgrad": ("tensor", 2.0 * T * 576 * (11 * 64 + 256)),
+            "conv9x1_wgrad": ("tensor", 2.0 * T * 576 * 64 + 2.0 * Thr * 576 * 64),
+            # HBM-bound families: bytes read + written once
+            "bn_stats": ("hbm", 11 * T * 64 * 2.0),
+            "bn_apply": ("hbm", (5 * (2 * T * 64 * 2 + T * 64 * 2 + T * 128 * 2) + 3 * T * 64 * 2.0)),
+            "bn_bwd": ("hbm", 11 * 5 * T * 64 * 2.0),
+            "ln_fwd": ("hbm", 10 * 2 * T * 128 * 2.0),
+            "ln_bwd": ("hbm", 10 * 3 * T * 128 * 2.0),
+            # bias gradients of the convs that keep a separate column sum (the linears' ride in linear_wgrad, BatchNorm'd
+            # convs need none): block1 9x9 (T x 64), the up-sampling conv (T x 256), the output conv (Thr x 3 padded to 64)
+            "colsum": ("hbm", 2.0 * (T * 64 + T * 256 + Thr * 64)),
+        }
+
+    @staticmethod
+    def cpu_rate(batch, steps, warmup):
+        import torch
+        from oracle import synth, tbsrn_oracle as O
+        # torch's CPU kernels stop scaling (and then regress) past a few dozen threads at these tensor sizes:
+        # use up to 32 of the host cores and report the number actually used
+        cores = min(os.cpu_count() or 1, 32)
+        torch.set_num_threads(cores)
+        sd = synth.synth_state_dict(synth.load_spec("tbsrn"), 1234, O.tps_buffers())
+        lr, hr = synth.synth_images(batch)
+        g = torch.Generator().manual_seed(0)
+        st, times = {}, []
+        for it in range(warmup + steps):
+            masks = {}
+            for i in range(5):  # dropout on, as in training
+                masks[f"block{i + 2}.feature_enhancer.attn"] = torch.rand(batch, 4, 1024, 1024, generator=g) >= 0.1
+                masks[f"block{i + 2}.feature_enhancer.ffn"] = torch.rand(batch, 1024, 128, generator=g) >= 0.1
+            t0 = time.perf_counter()
+            sd, _ = O.train_step(sd, lr, hr, st, masks=masks)
+            if it >= warmup:
+                times.append(time.perf_counter() - t0)
+        return batch * len(times) / sum(times), cores, sum(times) / len(times), \
+            f"oracle TBSRN train_step (torch CPU fp32, {cores} threads)"
+    CPU_BATCH = 16
 
 
+class TSRNFocus:
+    cfg, dtype = 3, "bf16"
+
+    def __init__(self, B, dev, rank, args):
+        import torch
+        from fudanocr_b200.loss.stroke_focus_loss import StrokeFocusLoss
+        from fudanocr_b200.loss.transformer_english_decomposition import Transformer
+        from fudanocr_b200.model.tsrn import TSRN
+        from fudanocr_b200.trainer import TBSRNTrainer
+        self.B, self.torch = B, torch
+        torch.manual_seed(1234)
+        self.model = TSRN(STN=True).to(dev)
+        self.model.train()
+        # synthetic stand-ins for the git-ignored assets: random-init recogniser, 1-4 strokes per character
+        chars = string.digits + string.ascii_lowercase + string.ascii_uppercase
+        dic = {c: "".join(str(1 + (i * 3 + 5 * k) % 9) for k in range(1 + (i * 7) % 4)) for i, c in enumerate(chars)}
+        crit = StrokeFocusLoss(types.SimpleNamespace(text_focus=True, stroke_lambda=50), decomposition=dic,
+                               transformer_state_dict=Transformer("tg").state_dict()).to(dev)
+        self.trainer = TBSRNTrainer(self.model, criterion=crit)
+        g = torch.Generator(device=dev).manual_seed(1234 + rank)
+        self.lr = torch.rand(B, 3, 16, 64, device=dev, generator=g)
+        self.hr = torch.rand(B, 3, 32, 128, device=dev, generator=g)
+        self.lr_h, self.hr_h = self.lr.cpu().pin_memory(), self.hr.cpu().pin_memory()
+        rnd = random.Random(1234 + rank)
+        self.labels = ["".join(rnd.choice(string.digits + string.ascii_lowercase) for _ in range(rnd.randint(1, 12)))
+                       for _ in range(B)]
+        self.h2d, self.d2h = int(self.lr_h.numel() * 4 + self.hr_h.numel() * 4), 12
+        self.extra = {"labels": "random [0-9a-z] strings of 1-12 characters, encoded to stroke sequences on the host every step",
+                      "l2": "working set (recogniser activations, 2 branches) >> 126 MB L2; no explicit flush"}
+
+    def step(self, i):
+        return self.trainer.step(self.lr, self.hr, seed=i, labels=self.labels)
+
+    def step_e2e(self, i):
+        self.lr.copy_(self.lr_h, non_blocking=True)
+        self.hr.copy_(self.hr_h, non_blocking=True)
+        self.trainer.step(self.lr, self.hr, seed=i, labels=self.labels)
+        return self.trainer.losses.cpu()
+
+    def result(self):
+        return {"losses": [float(x) for x in self.trainer.losses.cpu()]}
+
+    def algo_work(self):
+        B = self.B
+        T = B * 1024
+        enc = 25.52e9  # recogniser encoder forward per image and branch; HR fwd + SR fwd + SR dgrad
+        return {
+            "tc_conv3x3": ("tensor", B * 3 * enc + 2.0 * T * 576 * (11 * 64 + 256) + 2.0 * T * 576 * 11 * 64 + 2.0 * T * 2304 * 64),
+            "tc_linear": ("tensor", B * 3 * 1.2e9 + 3 * 10 * 2.0 * T * 64 * (64 + 96)),
+            "linear_wgrad": ("tensor", 10 * 2.0 * T * 64 * (64 + 96)),
+            "conv3x3_wgrad": ("tensor", 2.0 * T * 576 * (11 * 64 + 256)),
+            "gru_fwd": ("tensor", 10 * 2.0 * T * 2 * 3 * 32 * 32),
+            "gru_bwd": ("tensor", 10 * 4.0 * T * 2 * 3 * 32 * 32),
+        }
+
+    @staticmethod
+    def cpu_rate(batch, steps, warmup):
+        """oracle restatement of the config-3 step on the host, exactly what the reference executes: TSRN forward, the
+        stroke-focus loss through the frozen recogniser under autograd (both branches, text-gestalt
+        loss/stroke_focus_loss.py:83-118), x100, backward, clip 0.25, Adam"""
+        import torch
+        from oracle import focus_oracle as FO, synth, tbsrn_oracle as O, tsrn_oracle as TO
+        cores = min(os.cpu_count() or 1, 32)
+        torch.set_num_threads(cores)
+        sd = synth.synth_state_dict(synth.load_spec("tsrn"), 1234, O.tps_buffers())
+        net = FO.synth_recogniser_state_dict(synth.load_spec("focus"))
+        dic = FO.synth_decomposition()
+        lr, hr = synth.synth_images(batch)
+        rnd = random.Random(7)
+        labels = ["".join(rnd.choice(string.digits + string.ascii_lowercase) for _ in range(rnd.randint(1, 12)))
+                  for _ in range(batch)]
+        float_keys = [k for k, v in sd.items() if v.is_floating_point() and not O.is_buffer(k)]
+        opt, times = {}, []
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            leaf = {k: (sd[k].detach().clone().requires_grad_(True) if k in float_keys else sd[k]) for k in sd}
+            new_stats = {}
+            sr = TO.tsrn_forward(leaf, lr, training=True, stn=True, new_stats=new_stats)
+            loss = FO.stroke_focus_loss(net, sr, hr, labels, dic, 50.0)[0]
+            (loss * 100).backward()
+            grads = {k: leaf[k].grad for k in float_keys if leaf[k].grad is not None}
+            clipped, _ = O.clip_grad_norm(grads)
+            sd = dict(sd)
+            sd.update(O.adam_step({k: sd[k] for k in float_keys}, clipped, opt))
+            sd.update(new_stats)
+            if it >= warmup:
+                times.append(time.perf_counter() - t0)
+        return batch * len(times) / sum(times), cores, sum(times) / len(times), \
+            f"oracle TSRN + stroke-focus train step (torch CPU fp32, {cores} threads)"
+    CPU_BATCH = 4
+
+
+class SLDTrain:
+    cfg, dtype = 4, "bf16"
+
+    def __init__(self, B, dev, rank, args):
+        import numpy as np
+        import torch
+        from fudanocr_b200.model.transformer import Transformer
+        from fudanocr_b200.trainer_sld import SLDTrainer
+        self.B, self.torch, self.width = B, torch, args.width
+        torch.manual_seed(1234)
+        g = torch.Generator(device=dev).manual_seed(1234 + rank)
+        rs = np.random.RandomState(1234 + rank)
+        self.model = Transformer("stroke").to(dev).train()
+        self.trainer = SLDTrainer(self.model)
+        lens = rs.randint(2, 31, size=B)                   # stroke strings of 2..30 symbols incl. '$'
+        self.image = torch.rand(B, 3, 32, args.width, device=dev, generator=g) * 2 - 1
+        T = int(lens.max())
+        text_input = torch.zeros(B, T, dtype=torch.long)
+        gt = []
+        for b, n in enumerate(lens):
+            s = rs.randint(1, 6, size=n)
+            s[-1] = 6
+            text_input[b, 1:n] = torch.from_numpy(s[:n - 1])
+            gt.extend(s.tolist())
+        self.length_h = torch.from_numpy(lens.astype(np.int64)).pin_memory()
+        self.text_input_h = text_input.pin_memory()
+        self.text_gt_h = torch.tensor(gt, dtype=torch.long).pin_memory()
+        self.image_h = self.image.cpu().pin_memory()
+        self.length, self.text_input, self.text_gt = self.length_h.to(dev), self.text_input_h.to(dev), self.text_gt_h.to(dev)
+        self.h2d = int(self.image_h.numel() * 4 + (self.length_h.numel() + self.text_input_h.numel() + self.text_gt_h.numel()) * 8)
+        self.d2h = 4
+        self.extra = {"T": T, "crop": f"32x{args.width}",
+                      "l2": "working set (40 saved conv inputs per image) >> 126 MB L2; no explicit flush"}
+
+    def step(self, i):
+        return self.trainer.step(self.image, self.length, self.text_input, self.text_gt)
+
+    def step_e2e(self, i):
+        self.image.copy_(self.image_h, non_blocking=True)
+        self.length.copy_(self.length_h, non_blocking=True)
+        self.text_input.copy_(self.text_input_h, non_blocking=True)
+        self.text_gt.copy_(self.text_gt_h, non_blocking=True)
+        return self.trainer.step(self.image, self.length, self.text_input, self.text_gt).cpu()
+
+    def result(self):
+        return {"final_loss": float(self.trainer.loss)}
+
+    def algo_work(self):
+        fwd = self.B * 30.24e9 * self.width / 32.0   # SURVEY appendix A: encoder convs per image (forward)
+        return {"tc_conv3x3": ("tensor", 2 * fwd), "tc_linear": ("tensor", 2 * fwd), "conv_wgrad_tc": ("tensor", fwd),
+                "wgrad_operands": ("hbm", self.B * self.width / 32.0 * 73e6), "adadelta": ("hbm", 71.7e6 * 28)}
+
+    @staticmethod
+    def cpu_rate(batch, steps, warmup):
+        sys.path.insert(0, os.path.join(ROOT, "scripts"))
+        import bench_cfg4
+        r = bench_cfg4.cpu_baseline("sld", batch=batch, steps=steps)
+        sec = batch / r["value"]
+        return r["value"], r["cores"], sec, "oracle SLD train step (torch CPU fp32, all host threads)"
+    CPU_BATCH = 8
+
+
+class EvalPipeline:
+    cfg, dtype = 5, "bf16"
+
+    def __init__(self, B, dev, rank, args):
+        import torch
+        from fudanocr_b200.interfaces.recognition import evaluate_batch
+        from fudanocr_b200.model.crnn import CRNN
+        from fudanocr_b200.model.tbsrn import TBSRN
+        self.B, self.torch, self.evaluate_batch = B, torch, evaluate_batch
+        torch.manual_seed(1234)
+        self.model = TBSRN().to(dev).eval()
+        self.crnn = CRNN(32, 1, 37, 256).to(dev).eval()
+        g = torch.Generator(device=dev).manual_seed(1234 + rank)
+        self.lr = torch.rand(B, 3, 16, 64, device=dev, generator=g)
+        self.hr = torch.rand(B, 3, 32, 128, device=dev, generator=g)
+        self.lr_h, self.hr_h = self.lr.cpu().pin_memory(), self.hr.cpu().pin_memory()
+        rnd = random.Random(rank)
+        self.labels = ["".join(rnd.choice(string.ascii_lowercase) for _ in range(rnd.randint(1, 12))) for _ in range(B)]
+        self.h2d, self.d2h = int(self.lr_h.numel() * 4 + self.hr_h.numel() * 4), B * 26 * 4 + 8
+        self.out = None
+        self.extra = {"note": "forward only, no collective: ranks own disjoint shards; decoded strings are built on the host "
+                              "inside every step (value and e2e)"}
+
+    def step(self, i):
+        self.out = self.evaluate_batch(self.model, self.crnn, self.lr, self.hr, self.labels)
+        return self.out
+
+    def step_e2e(self, i):
+        self.lr.copy_(self.lr_h, non_blocking=True)
+        self.hr.copy_(self.hr_h, non_blocking=True)
+        self.out = self.evaluate_batch(self.model, self.crnn, self.lr, self.hr, self.labels)
+        return self.out
+
+    def result(self):
+        return {"psnr": float(self.out["psnr"]), "ssim": float(self.out["ssim"])}
+
+    def algo_work(self):
+        B = self.B
+        T = B * 1024
+        g = 2.0 * 1024 * 1024 * 32
+        return {"attn_fwd": ("tensor", 5 * B * 4 * 2 * g),
+                "tc_conv3x3": ("tensor", 2.0 * T * 576 * (11 * 64 + 256) + B * 1.27e9),
+                "tc_linear": ("tensor", 5 * 2.0 * T * 128 * (384 + 128 + 128 + 128 + 64) + B * 0.14e9),
+                "tc_conv9tap": ("tensor", 2.0 * T * 576 * 64 + 2.0 * B * 4096 * 576 * 64)}
+
+    @staticmethod
+    def cpu_rate(batch, steps, warmup):
+        """oracle restatement of TextSR.eval's batch body on the host (interfaces/super_resolution.py:178-207): SR forward
+        (eval), bicubic + gray, CRNN forward, greedy CTC decode to strings"""
+        import torch
+        from oracle import crnn_oracle as CO, synth, tbsrn_oracle as O
+        cores = min(os.cpu_count() or 1, 32)
+        torch.set_num_threads(cores)
+        sd = synth.synth_state_dict(synth.load_spec("tbsrn"), 1234, O.tps_buffers())
+        csd = synth.synth_state_dict(synth.load_spec("crnn"), 99)
+        lr, _ = synth.synth_images(batch)
+        times = []
+        with torch.no_grad():
+            for it in range(warmup + steps):
+                t0 = time.perf_counter()
+                sr = O.tbsrn_forward(sd, lr, training=False)
+                logits = CO.crnn_forward(csd, CO.parse_crnn_data(sr[:, :3]))
+                CO.get_crnn_pred(logits.permute(1, 0, 2))
+                if it >= warmup:
+                    times.append(time.perf_counter() - t0)
+        return batch * len(times) / sum(times), cores, sum(times) / len(times), \
+            f"oracle TBSRN eval + CRNN + greedy decode (torch CPU fp32, {cores} threads)"
+    CPU_BATCH = 32
+
+
+WORKLOADS = {2: TBSRNTrain, 3: TSRNFocus, 4: SLDTrain, 5: EvalPipeline}
+
+
+def config_dict(cfg, B, world, scaling, extra=None):
+    d = {"workload": WORKLOAD[cfg], "baseline_config": cfg, "per_gpu_batch": B, "global_batch": world * B,
+         "parallelism": f"dp{world}", "scaling_mode": scaling}
+    if extra:
+        d.update(extra)
+    return d
+
+
+def per_gpu_batch(args, world):
+    if args.batch:
+        return args.batch
+    if args.scaling == "strong":
+        if GLOBAL_BATCH[args.config] % world:
+            raise SystemExit(f"global batch {GLOBAL_BATCH[args.config]} does not split over {world} ranks")
+        return GLOBAL_BATCH[args.config] // world
+    return WEAK_BATCH[args.config]
+
+
+# ------------------------------------------------------------------------------------------------
 def run_reference(args):
+    """The reference arm: the reference's own algorithm for this path (the oracle restatement, pinned to the unmodified modules
+    by tests/golden - the reference package itself cannot travel to the GPU box) on the host cores.  Every step is a bounded
+    sample of the workload (CPU_BATCH crops); `steps`, `warmup` and `ms_per_step` are what was actually run and measured."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    b = 16
-    rate, cores, sec = cpu_oracle_rate(b, max(1, min(args.steps, 3)), 1 if args.warmup else 0)
+    W = WORKLOADS[args.config]
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    b = W.CPU_BATCH
+    steps = max(1, min(args.steps, 3))
+    warm = 1 if args.warmup else 0
+    rate, cores, sec, what = W.cpu_rate(b, steps, warm)
     out = {
-        "impl": "reference", "metric": METRIC, "value": rate, "unit": "images/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3 * BATCH / b, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "TBSRN train step (STN on, MSE loss x100, clip 0.25, Adam), 16x64->32x128, batch 256/GPU",
-                   "sample": f"batch {b} per step on the host CPU"},
+        "impl": "reference", "metric": METRIC[args.config], "value": rate, "unit": "images/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_dict(args.config, per_gpu_batch(args, world), world, args.scaling),
+        "requested": {"steps": args.steps, "warmup": args.warmup},
         "cpu_baseline": {"value": rate, "unit": "images/s", "cores": cores, "kind": "port",
-                         "sample": f"oracle train_step (torch CPU fp32, {cores} threads), batch {b}, "
-                                   f"{max(1, min(args.steps, 3))} timed steps"},
+                         "sample": f"{what}, {b} crops per step, {steps} timed step(s) after {warm} warm-up "
+                                   f"({sec:.2f} s/step); host-side only, no GPU"},
         "e2e": {"value": rate, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -183,6 +496,27 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
+def timed(torch, dist, world, dev, fn, K):
+    """K calls of fn(i) bracketed by barrier + synchronize on both sides; CUDA-event time, max over ranks (ms)"""
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        fn(i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
@@ -191,8 +525,6 @@ def main():
     import torch
     import torch.distributed as dist
     from fudanocr_b200 import _lib as L
-    from fudanocr_b200.model.tbsrn import TBSRN
-    from fudanocr_b200.trainer import TBSRNTrainer
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -205,85 +537,72 @@ def main():
         os.environ.setdefault("NCCL_IB_DISABLE", "1")   # single node: NVLink / NVSwitch only
         os.environ.setdefault("NCCL_P2P_LEVEL", "NVL")
         dist.init_process_group("nccl", device_id=dev)
-    B, K, W = args.batch, args.steps, max(args.warmup, 0)
+    cfg, K, W = args.config, args.steps, max(args.warmup, 3)
+    B = per_gpu_batch(args, world)
+    wl = WORKLOADS[cfg](B, dev, rank, args)
 
-    torch.manual_seed(1234)  # yaml manualSeed (config/super_resolution.yaml:24); same init on every rank
-    model = TBSRN().to(dev)
-    model.train()
-    trainer = TBSRNTrainer(model)
-    g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    lr_d = torch.rand(B, 3, 16, 64, device=dev, generator=g)
-    hr_d = torch.rand(B, 3, 32, 128, device=dev, generator=g)
-    lr_h, hr_h = lr_d.cpu().pin_memory(), hr_d.cpu().pin_memory()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(ms: float) -> float:
-        if world == 1:
-            return ms
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    for it in range(max(W, 3)):
-        trainer.step(lr_d, hr_d, seed=it)
+    for it in range(W):
+        wl.step(it)
     torch.cuda.synchronize()
 
     # ---- pass 1: per-kernel-family breakdown (all scopes, eager launches) to find the dominant kernel --------
     L.prof_enable(1, b"")
-    trainer.step(lr_d, hr_d, seed=1000)
+    wl.step(1000)
     breakdown = L.prof_collect()
     L.prof_enable(0, b"")
-    top = max(breakdown.items(), key=lambda kv: kv[1][1])[0] if breakdown else "attn_bwd_dkv"
+    work = wl.algo_work()
+    ranked = sorted(breakdown.items(), key=lambda kv: -kv[1][1])
+    top = ranked[0][0] if ranked else "attn_bwd"
 
-    # ---- timed region (device-resident inputs).  The trainer replays the step as CUDA graphs; events inside a
-    # graph cannot be timed, so the dominant kernel's launch duration is taken in pass 3 below ------------------
-    trainer.step(lr_d, hr_d, seed=1001)  # (re)capture outside the timed region
+    # ---- timed region (device-resident inputs).  Graph replays cannot be timed per kernel, so the dominant kernel's launch
+    # duration is taken in pass 3 below --------------------------------------------------------------------------------
+    wl.step(1001)  # (re)capture outside the timed region
+    wl.step(1002)
     clocks = ClockSampler(local)
-    barrier()
     if rank == 0:
         clocks.start()
-    n0 = trainer.kernel_launches
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for it in range(K):
-        trainer.step(lr_d, hr_d, seed=2000 + it)
-    e1.record()
-    barrier()
-    ms = max_over_ranks(e0.elapsed_time(e1))
-    launches = int(trainer.kernel_launches - n0)
+    n0 = L.lib.focr_launch_count()
+    g0 = getattr(getattr(wl, "trainer", None), "kernel_launches", None)
+    ms = timed(torch, dist, world, dev, lambda i: wl.step(2000 + i), K)
+    if g0 is not None:   # graph replays do not pass through the launch counter: the trainer counts the replayed nodes
+        launches = int(wl.trainer.kernel_launches - g0)
+    else:
+        launches = int(L.lib.focr_launch_count() - n0)
     clk = clocks.stop() if rank == 0 else None
-    loss_dev = float(trainer.loss.item())
+    res = wl.result()
 
     # ---- pass 3: the same K steps launched eagerly with CUDA-event scopes around the dominant kernel only ------
     L.prof_enable(2, top.encode())
     for it in range(K):
-        trainer.step(lr_d, hr_d, seed=2500 + it)
+        wl.step(2500 + it)
     focus = L.prof_collect()
     L.prof_enable(0, b"")
 
-    # ---- end to end: host (pinned) inputs -> H2D every step, loss read back every step -----------------------
-    barrier()
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2.record()
-    for it in range(K):
-        lr_d.copy_(lr_h, non_blocking=True)
-        hr_d.copy_(hr_h, non_blocking=True)
-        loss = trainer.step(lr_d, hr_d, seed=3000 + it)
-        _ = loss.cpu()  # the scalar a user logs every step (super_resolution.py:74-76)
-    e3.record()
-    barrier()
-    ms_e2e = max_over_ranks(e2.elapsed_time(e3))
+    # ---- end to end: host (pinned) inputs -> H2D every step, the step's scalar result read back every step ----
+    wl.step_e2e(2999)
+    ms_e2e = timed(torch, dist, world, dev, lambda i: wl.step_e2e(3000 + i), K)
+
+    # ---- config 2, N > 1: the strong-scaling point (BASELINE's global batch 256 split over the ranks) ---------
+    strong = None
+    if cfg == 2 and args.scaling == "weak" and world > 1 and not args.no_strong_point and GLOBAL_BATCH[2] % world == 0:
+        try:
+            Bs = GLOBAL_BATCH[2] // world
+            ws = TBSRNTrain(Bs, dev, rank, args)
+            for it in range(4):
+                ws.step(it)
+            ms_s = timed(torch, dist, world, dev, lambda i: ws.step(4000 + i), K)
+            strong = {"global_batch": GLOBAL_BATCH[2], "per_gpu_batch": Bs, "value": world * Bs * K / (ms_s * 1e-3),
+                      "unit": "images/s", "ms_per_step": ms_s / K, "steps": K,
+                      "note": "same step, BASELINE's global batch 256 split over the ranks (SURVEY 8(d) strong scaling)"}
+            del ws
+        except Exception as ex:   # the extra point must never take the headline number down with it
+            strong = {"error": str(ex)[:200]}
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     peaks = load_peaks()
-    work = algo_work(B)
     kind, amount = work.get(top, ("tensor", 0.0))
     cnt, tot_ms = focus.get(top, (0, 0.0))
     per_step_ms = tot_ms / max(K, 1)
@@ -294,6 +613,12 @@ def main():
         achieved = amount / (per_step_ms * 1e-3) / 1e9 if per_step_ms else 0.0
         peak, unit = peaks["hbm_gbs"], "GB/s"
     step_ms_profiled = sum(v[1] for v in breakdown.values())
+    fam = {}
+    for k, v in ranked:   # per-family fractions of the respective measured peak, from the pass-1 scopes
+        if k in work and v[1] > 0:
+            kd, am = work[k]
+            pk = peaks["tf_sustained"] * 1e12 if kd == "tensor" else peaks["hbm_gbs"] * 1e9
+            fam[k] = round(am / (v[1] * 1e-3) / pk, 4)
     roofline = {
         "kernel": top, "bound": kind, "achieved": achieved, "peak": peak, "unit": unit,
         "frac": achieved / peak if peak else None, "traffic": ncu_traffic(top),
@@ -303,29 +628,29 @@ def main():
         "peak_source": peaks["source"] + (", sustained bf16 figure (kernel timed inside a long step)"
                                            if kind == "tensor" else ""),
         "timing": "CUDA events on the launching stream around each launch of the kernel, K eager steps run right after "
-                  "the timed region (the timed region replays the step as CUDA graphs, whose events cannot be timed)",
-        "breakdown_ms_per_step": {k: round(v[1], 4) for k, v in sorted(breakdown.items(), key=lambda kv: -kv[1][1])},
+                  "the timed region (graph replays cannot be timed per kernel)",
+        "breakdown_ms_per_step": {k: round(v[1], 4) for k, v in ranked},
+        "family_frac_of_peak": fam,
     }
     out = {
-        "metric": METRIC, "value": world * B * K / (ms * 1e-3), "unit": "images/s", "n_gpus": world, "steps": K,
-        "warmup": max(W, 3), "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "TBSRN train step (STN on, dropout 0.1, MSE loss x100, clip 0.25, Adam 1e-4), "
-                               "LR 16x64 -> HR 32x128, batch 256 per GPU (BASELINE configs[1])",
-                   "global_batch": world * B, "parallelism": f"dp{world}",
-                   "l2": "per-step working set (~6 GB of saved activations) >> 126 MB L2; no explicit flush",
-                   "launch": "step replayed as 2 CUDA graphs (fwd+loss+bwd | clip+Adam), dropout seed read on device"},
+        "metric": METRIC[cfg], "value": world * B * K / (ms * 1e-3), "unit": "images/s", "n_gpus": world, "steps": K,
+        "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+        "dtype": wl.dtype, "data": "synthetic",
+        "config": config_dict(cfg, B, world, args.scaling, wl.extra),
         "e2e": {"value": world * B * K / (ms_e2e * 1e-3), "unit": "images/s",
-                "h2d_bytes_per_step": int(lr_h.numel() * 4 + hr_h.numel() * 4), "d2h_bytes_per_step": 4},
+                "h2d_bytes_per_step": wl.h2d, "d2h_bytes_per_step": wl.d2h},
         "gpu_launches": launches, "launches_per_step": launches / max(K, 1),
-        "clocks": clk, "roofline": roofline, "final_loss": loss_dev,
+        "clocks": clk, "roofline": roofline,
     }
+    out.update(res)
+    if strong is not None:
+        out["strong_scaling"] = strong
     if world == 1 and not args.no_cpu_baseline:
         try:
-            rate, cores, sec = cpu_oracle_rate(16, 2, 1)
+            Wc = WORKLOADS[cfg]
+            rate, cores, sec, what = Wc.cpu_rate(Wc.CPU_BATCH, 2, 1)
             out["cpu_baseline"] = {"value": rate, "unit": "images/s", "cores": cores, "kind": "port",
-                                   "sample": f"oracle train_step (torch CPU fp32, {cores} threads), batch 16, "
-                                             f"2 timed steps ({sec:.1f} s/step)"}
+                                   "sample": f"{what}, batch {Wc.CPU_BATCH}, 2 timed steps ({sec:.1f} s/step)"}
         except Exception as ex:  # the baseline leg must never take the GPU number down with it
             out["cpu_baseline"] = {"value": None, "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
                                    "sample": f"failed: {ex}"}

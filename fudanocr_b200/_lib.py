@@ -54,7 +54,11 @@ _SIGS = {
     "focr_mha_flash_fwd": (C.c_int, [_vp, _vp, _fp, _i, _f, _u, _u, _vp, _vp]),
     "focr_mha_flash_bwd": (C.c_int, [_vp, _vp, _vp, _fp, _fp, _vp, _i, _f, _u, _u, _vp, _vp]),
     "focr_umma_probe": (C.c_int, [_vp, _i, C.c_ulonglong, C.c_ulonglong, _u, _i, _u, _u, _vp, _i, _vp]),
-    "focr_attn_set_trace": (C.c_int, [_vp]),
+    "focr_attn_set_force_exact": (C.c_int, [_i]),
+    "focr_weight_cross_entropy_workspace_bytes": (_sz, [_l]),
+    "focr_weight_cross_entropy": (C.c_int, [_fp, _vp, _fp, _fp, _fp, _vp, _l, _i, _vp, _sz, _vp]),
+    "focr_to_gray": (C.c_int, [_fp, _fp, _l, _i, _l, _vp]),
+    "focr_to_gray_bwd": (C.c_int, [_fp, _fp, _l, _i, _l, _vp]),
     "focr_mse_loss_grad": (C.c_int, [_fp, _fp, _fp, _fp, _l, _f, _vp, _sz, _vp]),
     "focr_adam_clip_step": (C.c_int, [_vp, _i, _f, _f, _f, _f, _f, _f, _vp, _fp, _vp, _sz, _vp]),
     "focr_tbsrn_num_slots": (C.c_int, [_i]),

@@ -15,16 +15,25 @@
 // shared tile, and the second GEMM of each tile consumes that tile either K-major (P V, dS K) or MN-major (P^T dO,
 // dS^T Q - M = 64 keys) with V / K / dO / Q read in place as MN-major B operands.  The descriptor semantics used
 // here are pinned by tests/test_gpu_umma_layouts.py.
-//   forward   : two passes over the keys per query tile (exact row max first, then exp / sum / PV) - no rescaling of
-//               the TMEM accumulator is ever needed; S is double-buffered in TMEM
+//   forward   : one pass over the keys per query tile with the Cauchy-Schwarz bound as the softmax shift (see below);
+//               no rescaling of the TMEM accumulator is ever needed
 //   backward A: dQ  (query tile outer, key tiles inner; also writes D = rowsum(dO o O))
 //   backward B: dK, dV (64-key block outer, query tiles inner)
-// Dropout: counter hash of common.cuh keyed on (b,h,q,k/4); each 32-bit hash carries four 7-bit lanes (the low 7
-// bits of its bytes), element k is DROPPED when lane (k & 3) < th7, th7 = round(p * 128) - the rate is quantised to
-// 1/128 (p = 0.1 -> 13/128) and the 1/(1-p) rescale uses the quantised rate, so the expectation is exact.  The
-// forward can store its keep decisions, one word per (q, 32 keys): word [bh][k/32][q], bit 8 (k&3) + (k%32)/4; the
-// backward then reads bits instead of re-hashing.  The 1/(1-p) factor is folded into the output scales: P V and dV accumulate kept probabilities
-// unscaled, dS = P o (keep o dP - D (1-p)) / (1-p).
+// Dropout (nn.Dropout(0.1) on P, tbsrn.py:146-147): the keep decisions of 32 consecutive keys of one query row are
+// ONE 32-bit word built bit-sliced: 12 counter-based random words (six 4-round Philox-2x32 calls keyed on (seed, layer),
+// counter = ((b,h,q) * 32 + k/32) * 8 + call) plus three rotated copies feed the 15 levels of the binary expansion of
+// th15 = round(p * 2^15) through r = bit ? (w | r) : (w & r), which leaves every bit of r set with probability exactly
+// th15 / 32768 (p = 0.1 -> 3277 / 32768 = 0.100006; the 1/(1-p) rescale uses that rate, so the expectation is exact).
+// No per-element compare, no word assembly: ~1.8 instructions per element, 60 % of them on the FMA pipe (IMAD.WIDE).
+// Element k of the group sits at bit 8 (k & 3) + (k % 32) / 4, so that `word << (7 - i)` puts the four decisions of
+// elements 4i .. 4i+3 into the byte sign bits that prmt replicates into bf16-pair masks.  The forward can store the words
+// ([bh][k/32][q], 1 bit per element); the backward then reads them instead of regenerating.  numpy twin:
+// oracle/dropout_rng.py:attn_keep_mask.  The 1/(1-p) factor is folded into the output scales: P V and dV accumulate
+// kept probabilities unscaled, dS = P o (keep o dP - D (1-p)) / (1-p).
+// Softmax shift: softmax is shift-invariant, so the forward does not search the row maximum.  |s_ij| <= |q_i| max_j |k_j|
+// (Cauchy-Schwarz) gives a per-row upper bound that is used as the shift; a CTA whose bound is so loose that exp2 could
+// leave the fp32 normal range (2 * bound * log2(e) / sqrt(d_k) > 100, i.e. logits beyond +-35) takes the exact two-pass
+// route (row maximum first) instead - a CTA-uniform branch.
 #include "kernels.cuh"
 
 namespace {
@@ -58,6 +67,38 @@ __device__ __forceinline__ uint32_t p_off(int row, int chunk) { return (uint32_t
 __device__ __forceinline__ uint64_t desc_sw64(uint32_t addr) { return umma_desc(addr, 16, 512, 4); }
 __device__ __forceinline__ uint64_t desc_sw128(uint32_t addr) { return umma_desc(addr, 16, 1024, 2); }
 
+// tcgen05.st: each thread of the warp writes 32 consecutive 32-bit columns of its TMEM lane
+__device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand is read from tensor memory (row m on lane m, bf16 pairs (k, k+1) packed
+// in 32-bit column k / 2 - exactly what tcgen05.st.32x32b of packed pairs leaves there)
+__device__ __forceinline__ void tc_mma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// O[128 x 32] (+)= P[128 q x 64 keys] (tensor memory, 32 packed columns) * V[64 keys x 32] (MN-major, sw64)
+__device__ __forceinline__ void mma_pv_ts(uint32_t tmem_d, uint32_t tmem_p, uint32_t b_addr, bool acc) {
+  constexpr uint32_t idesc = umma_idesc_bf16_ex(128, 32, 0, 1);
+  const uint64_t db = desc_sw64(b_addr);
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) tc_mma_bf16_ts(tmem_d, tmem_p + 8 * ks, db + 64 * ks, idesc, (acc || ks) ? 1u : 0u);
+}
+
 // S / dP tile: D[128 x 64] = A[128 x 32] B[64 x 32]^T
 __device__ __forceinline__ void mma_qk(uint32_t tmem_d, uint32_t a_addr, uint32_t b_addr) {
   constexpr uint32_t idesc = umma_idesc_bf16_ex(128, 64, 0, 0);
@@ -80,30 +121,93 @@ __device__ __forceinline__ void mma_ptdo(uint32_t tmem_d, uint32_t a_addr, uint3
   for (int ks = 0; ks < 8; ++ks) tc_mma_bf16(tmem_d, da + 128 * ks, db + 64 * ks, idesc, (acc || ks) ? 1u : 0u);
 }
 
-// keep decisions of 4 consecutive keys of one query row: x = (hash & 0x7F7F7F7F) + addc has the msb of byte j set iff
-// key 4*ctr + j is kept (addc = (128 - th7) * 0x01010101); 8 such x build the 32-key word.
-__device__ __forceinline__ uint32_t keep_x(uint32_t key, uint32_t ctr, uint32_t addc) {
-  return (drop_hash32(key, ctr) & 0x7F7F7F7Fu) + addc;
+// ---- dropout keep words (see the header): bit-sliced Bernoulli(th15 / 32768) over Philox-2x32-4 words ----------------
+constexpr uint32_t kPhiloxM = 0xD256D193u;
+constexpr uint32_t kPhiloxW = 0x9E3779B9u;
+constexpr uint32_t kTh15P01 = 3277u;  // round(0.1 * 32768): the reference's attention dropout rate, compile-time path
+struct DropKeys {
+  uint32_t r0, k0, k1, k2, k3;
+};
+__device__ __forceinline__ DropKeys drop_keys(uint32_t key) {
+  DropKeys d;
+  d.r0 = key;
+  d.k0 = key * 0x85EBCA6Bu + 0x1B873593u;
+  d.k1 = d.k0 + kPhiloxW;
+  d.k2 = d.k1 + kPhiloxW;
+  d.k3 = d.k2 + kPhiloxW;
+  return d;
 }
-__device__ __forceinline__ uint32_t hash_word(uint32_t key, uint32_t ctr0, uint32_t addc) {
-  uint32_t w = 0;
+__device__ __forceinline__ void philox_round(uint32_t& l, uint32_t& r, uint32_t k) {
+  const uint64_t p = (uint64_t)l * kPhiloxM;  // IMAD.WIDE.U32 (FMA pipe)
+  l = (uint32_t)(p >> 32) ^ k ^ r;            // one LOP3
+  r = (uint32_t)p;
+}
+__device__ __forceinline__ void philox4(uint32_t ctr, const DropKeys& dk, uint32_t& l, uint32_t& r) {
+  l = ctr;
+  r = dk.r0;
+  philox_round(l, r, dk.k0);
+  philox_round(l, r, dk.k1);
+  philox_round(l, r, dk.k2);
+  philox_round(l, r, dk.k3);
+}
+// keep word of keys [32 kw, 32 kw + 32) of row `rowid` = (b*4+h)*1024 + q.  TH15 != 0: compile-time threshold.
+// `zero`: six words that are 0 at run time but that the compiler cannot prove so (see the forward kernel) - they pin
+// each Philox call behind a chosen point of the caller's instruction stream.
+template <uint32_t TH15>
+__device__ __forceinline__ uint32_t keep_word32(uint32_t rowid, uint32_t kw, const DropKeys& dk, uint32_t th15,
+                                                const uint32_t (&zero)[6]) {
+  const uint32_t ctr0 = (rowid * 32u + kw) * 8u;
+  uint32_t w[15];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) w = (w >> 1) | (keep_x(key, ctr0 + i, addc) & 0x80808080u);
-  return w;
+  for (int c = 0; c < 6; ++c) philox4(ctr0 + c + zero[c], dk, w[2 * c], w[2 * c + 1]);
+  w[12] = __funnelshift_l(w[0], w[0], 7);   // levels 13-15 decide with probability <= 2^-12: rotated copies will do
+  w[13] = __funnelshift_l(w[1], w[1], 13);
+  w[14] = __funnelshift_l(w[2], w[2], 22);
+  uint32_t r = 0;  // bit set <=> the 15-bit uniform of that position is < th15 <=> DROPPED
+#pragma unroll
+  for (int i = 14; i >= 0; --i) {
+    if (TH15 != 0) {
+      r = ((TH15 >> (14 - i)) & 1u) ? (w[i] | r) : (w[i] & r);
+    } else {
+      const uint32_t m = 0u - ((th15 >> (14 - i)) & 1u);
+      r = (w[i] & r) | (m & (w[i] | r));  // MAJ(w, r, m): one LOP3
+    }
+  }
+  return ~r;
+}
+template <uint32_t TH15>
+__device__ __forceinline__ uint32_t keep_word32(uint32_t rowid, uint32_t kw, const DropKeys& dk, uint32_t th15) {
+  const uint32_t zero[6] = {0, 0, 0, 0, 0, 0};
+  return keep_word32<TH15>(rowid, kw, dk, th15, zero);
+}
+__device__ __forceinline__ uint32_t keep_word(uint32_t rowid, uint32_t kw, const DropKeys& dk, uint32_t th15) {
+  return th15 == kTh15P01 ? keep_word32<kTh15P01>(rowid, kw, dk, th15) : keep_word32<0>(rowid, kw, dk, th15);
 }
 
-// optional clock trace of one softmax warp (block 0, warp 4, lane 0) for tuning: focr_attn_set_trace()
-__device__ long long* g_attn_trace = nullptr;
-struct Tracer {
-  long long* p;
-  __device__ __forceinline__ Tracer(int warp, int lane) {
-    long long* t = g_attn_trace;
-    p = (t != nullptr && blockIdx.x == 0 && warp == 4 && lane == 0) ? t : nullptr;
-  }
-  __device__ __forceinline__ void mark() {
-    if (p) *p++ = clock64();
-  }
-};
+// packed fp32 pairs (sm_100: FFMA2 / FADD2 / FMUL2 issue one instruction for two lanes)
+__device__ __forceinline__ uint64_t f2_pack(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
 
 struct WgBars {      // per softmax group
   uint64_t a_full;   // per-tile operand(s) of this group landed (TMA)
@@ -161,42 +265,98 @@ __device__ __forceinline__ void store_chunks4(uint8_t* tile, int row, int chunk0
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// forward.  NWG softmax groups (2, 3 or 4) work on different 128-query tiles of the same (batch, head) at once; warp g
-// (lane 0) issues the MMAs and the Q-tile TMA of group g, warps 4.. are the softmax groups.
-// shared: K, V resident (2 x 64 KB); per group a Q tile (8 KB) and a P tile (16 KB).
-// TMEM per group: S ring (2 x 64 columns; 1 x 64 with four groups) and O (32 columns).
+// forward.  NWG softmax groups (2 or 3) work on different 128-query tiles of the same (batch, head) at once; warp g
+// (lane 0) issues the MMAs and the Q-tile TMA of group g, warps 4.. are the softmax groups (thread = query row).
+// shared: K, V resident (2 x 64 KB); per group two Q tiles (2 x 8 KB).
+// TMEM per group (160 columns): two S buffers of 64 fp32 columns and O (32).  P never touches shared memory: once a
+// thread has pulled its S row into registers it writes the bf16 probabilities back over the first 32 columns of the
+// SAME buffer (tcgen05.st) and the P V MMA takes its A operand from tensor memory.  With two buffers the softmax loop
+// has no wait on the tensor pipe in steady state: S_{j+1} is computed while tile j is in the exponentials, and the
+// buffer of tile j is only overwritten by S_{j+2}, which the issuing thread enqueues after P_j V_j (in-order pipe).
+// Barriers per group: s_full[2] (MMA -> softmax: S written), p_full[2] (softmax -> MMA: S drained, P in place),
+// o_full / o_empty, q_full[2] / q_empty[2].
 // ------------------------------------------------------------------------------------------------------------------
+struct FwdGroupBars {
+  uint64_t q_full[2], q_empty[2];
+  uint64_t s_full[2], p_full[2];
+  uint64_t o_full, o_empty;
+};
+struct FwdBars {
+  uint64_t res_full;   // the resident head slices landed
+  uint64_t flag_full;  // max |k|^2 / max |q|^2 of this (batch, head) reduced (one arrival per softmax warp)
+  FwdGroupBars wg[3];
+  uint32_t tmem_slot;
+  uint32_t kmax_bits, qmax_bits;  // fp32 bit patterns (non-negative, so unsigned max orders them)
+};
 template <int NWG>
 struct FwdCfg {
-  static constexpr int kSB = NWG == 4 ? 1 : 2;       // S buffers per group
-  static constexpr int kCols = kSB * 64 + 32;        // TMEM columns per group
+  static constexpr int kCols = 160;  // TMEM columns per group
   static constexpr int kThreads = 128 + NWG * 128;
-  static constexpr int kSmem = 2 * kHeadBytes + NWG * (kQTile + kPTile) + 1024 /*barriers*/ + 1024 /*alignment*/;
+  static constexpr int kSmem = 2 * kHeadBytes + NWG * 2 * kQTile + 1024 /*barriers*/ + 1024 /*alignment*/;
 };
 
-template <int DROP, int NWG>
+// |x|^2 of one 64-byte row of bf16 (chunk order is irrelevant, so swizzled shared rows can be read in place)
+__device__ __forceinline__ float row_sumsq(const uint4* p) {
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const uint4 v = p[c];
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 x = unpack_bf16x2(w[e]);
+      s0 = fmaf(x.x, x.x, s0);
+      s1 = fmaf(x.y, x.y, s1);
+    }
+  }
+  return s0 + s1;
+}
+// Bound route of the forward.  shift_i = max(m32_i, bound_i - kShiftSpan), m32_i = the largest score among the first 32
+// keys (a lower bound of the row maximum): exp2(s - shift) <= 2^kShiftSpan never overflows, and the largest term is >= 1
+// unless the true maximum sits more than kShiftSpan below the bound - impossible while bound <= kFastBound (scores lie in
+// [-bound, bound]: 2 * 110 - 100 = 120 < 126).  Log2 units; 110 is |q||k|/sqrt(d_k) = 76 nats.
+constexpr float kShiftSpan = 100.f;
+constexpr float kFastBound = 110.f;
+
+// TH15C: compile-time dropout threshold (kTh15P01 for the reference's p = 0.1; 0 = read th15 at run time).  A run-time
+// choice inside the loop would split the keep-word generator from the exponentials into separate basic blocks.
+template <int DROP, int NWG, uint32_t TH15C>
 __global__ void __launch_bounds__(FwdCfg<NWG>::kThreads, 1)
-attn_fwd_kernel(const __grid_constant__ CUtensorMap mQkv, bf16* __restrict__ out, float* __restrict__ lse2, uint32_t key,
-                uint32_t th7, float inv_keep, uint32_t* __restrict__ drop_bits, const uint32_t* __restrict__ seed_dev) {
+attn_fwd_kernel(const __grid_constant__ CUtensorMap mQkv, const bf16* __restrict__ qkv, bf16* __restrict__ out,
+                float* __restrict__ lse2, uint32_t key, uint32_t th15, float inv_keep, uint32_t* __restrict__ drop_bits,
+                const uint32_t* __restrict__ seed_dev, int force_exact) {
   using Cfg = FwdCfg<NWG>;
   // device-resident seed (CUDA-graph replay): drop_key(seed, stream) = seed ^ f(stream), `key` then carries f(stream)
   if (DROP != 0 && seed_dev != nullptr) key ^= __ldg(seed_dev);
-  constexpr int SB = Cfg::kSB;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* sK = smem;
   uint8_t* sV = smem + kHeadBytes;
-  uint8_t* sQ = smem + 2 * kHeadBytes;             // [NWG]
-  uint8_t* sP = sQ + NWG * kQTile;                 // [NWG]
-  Bars* bars = reinterpret_cast<Bars*>(sP + NWG * kPTile);
+  uint8_t* sQ = smem + 2 * kHeadBytes;  // [NWG][2]
+  FwdBars* bars = reinterpret_cast<FwdBars*>(sQ + NWG * 2 * kQTile);
   const int bh = blockIdx.x, b = bh >> 2, h = bh & 3;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mQkv);
-    init_bars(bars);
+    mbar_init(&bars->res_full, 1);
+    mbar_init(&bars->flag_full, NWG * 4);
+    bars->kmax_bits = 0;
+    bars->qmax_bits = 0;
+    for (int g = 0; g < NWG; ++g) {
+      FwdGroupBars& w = bars->wg[g];
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&w.q_full[i], 1);
+        mbar_init(&w.q_empty[i], 1);
+        mbar_init(&w.s_full[i], 1);
+        mbar_init(&w.p_full[i], 4);
+      }
+      mbar_init(&w.o_full, 1);
+      mbar_init(&w.o_empty, 4);
+    }
+    fence_mbar_init();
   }
-  if (warp == 1) {
+  if (warp == 3) {
     tmem_alloc(&bars->tmem_slot, 512);
     tmem_relinquish();
   }
@@ -204,11 +364,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mQkv, bf16* __restrict__ out
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = bars->tmem_slot;
+  const int nq = (8 - 1 - (warp < NWG ? warp : ((warp - 4) >> 2))) / NWG + 1;  // query tiles of this group: g, g + NWG, ..
 
   if (warp < NWG) {
     if (lane == 0) {
       const int g = warp;
-      WgBars& w = bars->wg[g];
+      FwdGroupBars& w = bars->wg[g];
       if (g == 0) {
         mbar_arrive_expect_tx(&bars->res_full, 2 * kHeadBytes);
         for (int i = 0; i < 8; ++i) {
@@ -216,138 +377,186 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mQkv, bf16* __restrict__ out
           tma_load_2d(sV + i * kQTile, &mQkv, &bars->res_full, 256 + h * 32, b * kS + i * 128);
         }
       }
-      const uint32_t tS = tmem + g * Cfg::kCols, tO = tS + SB * 64;
-      const uint32_t aQ = smem_u32(sQ + g * kQTile), aP = smem_u32(sP + g * kPTile);
+      auto load_q = [&](int it) {
+        mbar_arrive_expect_tx(&w.q_full[it & 1], kQTile);
+        tma_load_2d(sQ + (g * 2 + (it & 1)) * kQTile, &mQkv, &w.q_full[it & 1], h * 32, b * kS + (g + NWG * it) * 128);
+      };
+      load_q(0);
+      const uint32_t tS = tmem + g * Cfg::kCols, tO = tS + 128;
       const uint32_t aK = smem_u32(sK), aV = smem_u32(sV);
-      uint32_t ns = 0, np = 0;
-      for (int it = 0; g + NWG * it < 8; ++it) {
-        mbar_wait_parked(&w.a_empty, (it & 1) ^ 1);  // every S MMA of the previous tile has read the Q buffer
-        mbar_arrive_expect_tx(&w.a_full, kQTile);
-        tma_load_2d(sQ + g * kQTile, &mQkv, &w.a_full, h * 32, b * kS + (g + NWG * it) * 128);
-        if (it == 0) mbar_wait_parked(&bars->res_full, 0);
-        mbar_wait_parked(&w.a_full, it & 1);
+      mbar_wait_parked(&bars->res_full, 0);
+      mbar_wait_parked(&bars->flag_full, 0);
+      const float kmax2 = __uint_as_float(*(volatile uint32_t*)&bars->kmax_bits);
+      const float qmax2 = __uint_as_float(*(volatile uint32_t*)&bars->qmax_bits);
+      const bool fast = !force_exact && sqrtf(qmax2 * kmax2) * kScaleLog2 <= kFastBound;
+      const int npass = fast ? 1 : 2;  // the exact route runs a row-maximum pass over the keys first
+      const int per_q = npass * 16, total = nq * per_q;
+      // tile t = (query tile it, pass, key tile j); S of tile t goes to buffer t & 1.  retire(t): wait until the softmax
+      // group has drained S_t (and, in the exp pass, written P_t over it), then enqueue P_t V_j.
+      auto retire = [&](int t) {
+        const int it = t / per_q, r = t - it * per_q, j = r & 15;
+        mbar_wait_parked(&w.p_full[t & 1], (t >> 1) & 1);
+        if (r < per_q - 16) return;  // row-maximum pass: nothing to multiply
         tc_fence_after();
-        for (int j = 0; j < 32; ++j) {  // 16 key tiles for the max pass, 16 for the exp / PV pass
-          const int sb = ns % SB;
-          mbar_wait_parked(&w.s_empty[sb], ((ns / SB) & 1) ^ 1);
+        if (j == 0) {
+          mbar_wait_parked(&w.o_empty, (it & 1) ^ 1);  // O of the previous query tile drained
           tc_fence_after();
-          mma_qk(tS + sb * 64, aQ, aK + (j & 15) * 4096);
-          tc_commit(&w.s_full[sb]);
-          ++ns;
-          if (j == 31) tc_commit(&w.a_empty);
-          if (j >= 17) {  // P V of key tile j - 17
-            const int jj = j - 17;
-            mbar_wait_parked(&w.p_full, np & 1);
-            tc_fence_after();
-            if (jj == 0) {
-              mbar_wait_parked(&w.o_empty, (it & 1) ^ 1);
-              tc_fence_after();
-            }
-            mma_pv(tO, aP, aV + jj * 4096, jj != 0);
-            tc_commit(&w.p_empty);
-            ++np;
-          }
         }
-        mbar_wait_parked(&w.p_full, np & 1);
+        mma_pv_ts(tO, tS + (t & 1) * 64, aV + j * 4096, j != 0);
+        if (j == 15) tc_commit(&w.o_full);
+      };
+      for (int t = 0; t < total; ++t) {
+        const int it = t / per_q, r = t - it * per_q, j = r & 15;
+        if (r == 0) {
+          if (it + 1 < nq) {  // prefetch the next Q tile into the other buffer (its last reader: query tile it - 1)
+            if (it >= 1) mbar_wait_parked(&w.q_empty[(it + 1) & 1], ((it - 1) >> 1) & 1);
+            load_q(it + 1);
+          }
+          mbar_wait_parked(&w.q_full[it & 1], (it >> 1) & 1);
+        }
         tc_fence_after();
-        mma_pv(tO, aP, aV + 15 * 4096, true);
-        tc_commit(&w.p_empty);
-        ++np;
-        tc_commit(&w.o_full);
+        mma_qk(tS + (t & 1) * 64, smem_u32(sQ + (g * 2 + (it & 1)) * kQTile), aK + j * 4096);
+        tc_commit(&w.s_full[t & 1]);
+        if (r == per_q - 1) tc_commit(&w.q_empty[it & 1]);
+        if (t >= 1) retire(t - 1);
       }
+      retire(total - 1);
     }
   } else if (warp >= 4) {
     const int g = (warp - 4) >> 2, quad = warp & 3, row = quad * 32 + lane;
-    WgBars& w = bars->wg[g];
-    const uint32_t tS = tmem + ((uint32_t)(quad * 32) << 16) + g * Cfg::kCols, tO = tS + SB * 64;
-    uint8_t* myP = sP + g * kPTile;
-    const uint32_t addc = (128u - th7) * 0x01010101u;
-    uint32_t ns = 0, np = 0;
-    Tracer tr(warp, lane);
-    for (int it = 0; g + NWG * it < 8; ++it) {
+    FwdGroupBars& w = bars->wg[g];
+    const uint32_t tS = tmem + ((uint32_t)(quad * 32) << 16) + g * Cfg::kCols, tO = tS + 128;
+    const DropKeys dk = drop_keys(key);
+    // ---- prologue: max |k|^2 over the resident keys, max |q|^2 over the queries of this (batch, head) ----
+    float kmax2 = 0.f, qmax2 = 0.f;
+    mbar_wait(&bars->res_full, 0);
+    for (int k = (int)threadIdx.x - 128; k < kS; k += NWG * 128) {
+      kmax2 = fmaxf(kmax2, row_sumsq(reinterpret_cast<const uint4*>(sK + (k >> 7) * kQTile + (k & 127) * 64)));
+      qmax2 = fmaxf(qmax2, row_sumsq(reinterpret_cast<const uint4*>(qkv + ((long)b * kS + k) * kLdQkv + h * 32)));
+    }
+    kmax2 = warp_max(kmax2);
+    qmax2 = warp_max(qmax2);
+    if (lane == 0) {
+      atomicMax(&bars->kmax_bits, __float_as_uint(kmax2));
+      atomicMax(&bars->qmax_bits, __float_as_uint(qmax2));
+      mbar_arrive(&bars->flag_full);
+    }
+    mbar_wait(&bars->flag_full, 0);
+    kmax2 = __uint_as_float(*(volatile uint32_t*)&bars->kmax_bits);
+    qmax2 = __uint_as_float(*(volatile uint32_t*)&bars->qmax_bits);
+    const bool fast = !force_exact && sqrtf(qmax2 * kmax2) * kScaleLog2 <= kFastBound;
+    const uint64_t c2 = f2_pack(kScaleLog2, kScaleLog2);
+    uint32_t t = 0;  // S tiles consumed by this group (both passes), same count as the issuing thread's
+    for (int it = 0; it < nq; ++it) {
       const int q = (g + NWG * it) * 128 + row;
-      // ---- pass 1: exact row maximum ----
-      float m = -INFINITY;
-      for (int j = 0; j < 16; ++j) {
-        const int sb = ns % SB;
-        tr.mark();
-        mbar_wait(&w.s_full[sb], (ns / SB) & 1);
-        tr.mark();
-        tc_fence_after();
-#pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          uint32_t r[32];
-          tmem_ld_32x32b_x32(tS + sb * 64 + hf * 32, r);
+      float mneg;
+      if (fast) {
+        // upper bound of this row's scaled scores: |q_i| max_j |k_j| / sqrt(d_k) (log2 units), less the span; the
+        // shift itself is fixed below from the first 32 scores
+        mbar_wait(&w.q_full[it & 1], (it >> 1) & 1);
+        const float qn2 = row_sumsq(reinterpret_cast<const uint4*>(sQ + (g * 2 + (it & 1)) * kQTile + row * 64));
+        mneg = sqrtf(qn2 * kmax2) * kScaleLog2 - kShiftSpan;
+      } else {
+        // ---- exact route, pass 1: row maximum ----
+        float m = -INFINITY;
+        for (int j = 0; j < 16; ++j, ++t) {
+          mbar_wait(&w.s_full[t & 1], (t >> 1) & 1);
+          tc_fence_after();
+          uint32_t r0[32], r1[32];
+          tmem_ld_32x32b_x32(tS + (t & 1) * 64, r0);
+          tmem_ld_32x32b_x32(tS + (t & 1) * 64 + 32, r1);
           tmem_ld_wait();
-          if (hf == 1) warp_release_tmem(&w.s_empty[sb], lane);
-          float m0 = __uint_as_float(r[0]), m1 = __uint_as_float(r[1]);
+          warp_release_tmem(&w.p_full[t & 1], lane);
+          float m0 = fmaxf(__uint_as_float(r0[0]), __uint_as_float(r1[0]));
+          float m1 = fmaxf(__uint_as_float(r0[1]), __uint_as_float(r1[1]));
 #pragma unroll
           for (int e = 2; e < 32; e += 2) {
-            m0 = fmaxf(m0, __uint_as_float(r[e]));
-            m1 = fmaxf(m1, __uint_as_float(r[e + 1]));
+            m0 = fmaxf(m0, fmaxf(__uint_as_float(r0[e]), __uint_as_float(r1[e])));
+            m1 = fmaxf(m1, fmaxf(__uint_as_float(r0[e + 1]), __uint_as_float(r1[e + 1])));
           }
           m = fmaxf(m, fmaxf(m0, m1));
         }
-        ++ns;
+        mneg = m * kScaleLog2;
       }
-      const float mneg = m * kScaleLog2;
-      // ---- pass 2: P = exp2(S c - m c), row sum, dropout, P -> shared ----
-      float l0 = 0.f, l1 = 0.f;
-      const uint32_t rowctr = (uint32_t)(bh * kS + q) * 256u;
-      for (int j = 0; j < 16; ++j) {
-        const int sb = ns % SB;
-        tr.mark();
-        mbar_wait(&w.s_full[sb], (ns / SB) & 1);
-        tr.mark();
+      // ---- P = exp2(S c - shift), row sum, dropout, P -> tensor memory ----
+      uint64_t nm2 = f2_pack(-mneg, -mneg);
+      uint64_t l01 = f2_pack(0.f, 0.f), l23 = l01;
+      const uint32_t rowid = (uint32_t)(bh * kS + q);
+      // keep words of tile j + 1 are generated INSIDE the exponential block of tile j: the generator is integer work on
+      // the ALU / FMA pipes, the exponentials queue on the MUFU pipe, and a warp issues in order - interleaved in one
+      // instruction stream each fills the other's issue gaps.  Left alone the scheduler hoists the whole generator in
+      // front of the exponentials (it has no inputs to wait for), so each Philox call's counter gets `p * 0.0f` of one
+      // of the tile's probabilities added: +0 at run time, but a true dependency that spreads the twelve calls over the
+      // sixty-four exponentials.
+      uint32_t kwn[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
+      if (DROP) {
+        kwn[0] = keep_word32<TH15C>(rowid, 0, dk, th15);
+        kwn[1] = keep_word32<TH15C>(rowid, 1, dk, th15);
+      }
+      for (int j = 0; j < 16; ++j, ++t) {
+        const uint32_t kwd[2] = {kwn[0], kwn[1]};
+        mbar_wait(&w.s_full[t & 1], (t >> 1) & 1);
         tc_fence_after();
+        uint32_t r[2][32];
+        tmem_ld_32x32b_x32(tS + (t & 1) * 64, r[0]);
+        tmem_ld_32x32b_x32(tS + (t & 1) * 64 + 32, r[1]);
+        tmem_ld_wait();
+        if (fast && j == 0) {  // shift = max(largest of the first 32 scores, bound - span)
+          float m0 = __uint_as_float(r[0][0]), m1 = __uint_as_float(r[0][1]);
+#pragma unroll
+          for (int e = 2; e < 32; e += 2) {
+            m0 = fmaxf(m0, __uint_as_float(r[0][e]));
+            m1 = fmaxf(m1, __uint_as_float(r[0][e + 1]));
+          }
+          mneg = fmaxf(mneg, fmaxf(m0, m1) * kScaleLog2);
+          nm2 = f2_pack(-mneg, -mneg);
+        }
+        uint32_t pk[32];
+        uint32_t zero[2][6];
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
-          uint32_t r[32];
-          tmem_ld_32x32b_x32(tS + sb * 64 + hf * 32, r);
-          tmem_ld_wait();
-          if (hf == 1) warp_release_tmem(&w.s_empty[sb], lane);
-          tr.mark();
-          uint32_t pk[16];
-          uint32_t word = 0;
-          const uint32_t ctr0 = rowctr + (uint32_t)(j * 16 + hf * 8);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            float p[4];
+            float x[4], p[4];
+            f2_unpack(f2_fma(f2_pack(__uint_as_float(r[hf][4 * i]), __uint_as_float(r[hf][4 * i + 1])), c2, nm2), x[0], x[1]);
+            f2_unpack(f2_fma(f2_pack(__uint_as_float(r[hf][4 * i + 2]), __uint_as_float(r[hf][4 * i + 3])), c2, nm2), x[2],
+                      x[3]);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) p[e] = ex2(fmaf(__uint_as_float(r[4 * i + e]), kScaleLog2, -mneg));
-            l0 += p[0] + p[2];
-            l1 += p[1] + p[3];
-            pk[2 * i] = pack_bf16x2(p[0], p[1]);
-            pk[2 * i + 1] = pack_bf16x2(p[2], p[3]);
+            for (int e = 0; e < 4; ++e) p[e] = ex2(x[e]);
+            l01 = f2_add(l01, f2_pack(p[0], p[1]));
+            l23 = f2_add(l23, f2_pack(p[2], p[3]));
+            uint32_t a0 = pack_bf16x2(p[0], p[1]), a1 = pack_bf16x2(p[2], p[3]);
             if (DROP) {
-              const uint32_t x = keep_x(key, ctr0 + i, addc);
-              pk[2 * i] &= prmt(x, 0x9988u);
-              pk[2 * i + 1] &= prmt(x, 0xBBAAu);
-              if (DROP == 2) word = (word >> 1) | (x & 0x80808080u);
+              const uint32_t x8 = kwd[hf] << (7 - i);  // bit 8 c + i -> sign of byte c
+              a0 &= prmt(x8, 0x9988u);
+              a1 &= prmt(x8, 0xBBAAu);
             }
+            pk[hf * 16 + 2 * i] = a0;
+            pk[hf * 16 + 2 * i + 1] = a1;
+            // twelve anchors over the sixteen groups of four exponentials (skipping i = 3 and i = 7)
+            if (DROP && (i & 3) != 3) zero[(hf * 6 + i - (i >> 2)) / 6][(hf * 6 + i - (i >> 2)) % 6] = __float_as_uint(p[0] * 0.0f);
           }
-          tr.mark();
-          if (hf == 0) mbar_wait(&w.p_empty, (np & 1) ^ 1);  // the P V of the previous tile has read the buffer
-          tr.mark();
-          store_chunks4(myP, row, hf * 4, pk);
-          if (DROP == 2) drop_bits[((size_t)bh * 32 + j * 2 + hf) * kS + q] = word;
+          if (DROP == 2) drop_bits[((size_t)bh * 32 + j * 2 + hf) * kS + q] = kwd[hf];
         }
-        tr.mark();
-        warp_publish_smem(&w.p_full, lane);
-        tr.mark();
-        ++np;
-        ++ns;
+        if (DROP) {  // (words 32, 33 of the last tile are never used)
+          kwn[0] = keep_word32<TH15C>(rowid, 2 * j + 2, dk, th15, zero[0]);
+          kwn[1] = keep_word32<TH15C>(rowid, 2 * j + 3, dk, th15, zero[1]);
+        }
+        tmem_st_32x32b_x32(tS + (t & 1) * 64, pk);  // over the S columns this thread has just consumed
+        tmem_st_wait();
+        warp_release_tmem(&w.p_full[t & 1], lane);
       }
       // ---- epilogue: O / l ----
-      tr.mark();
       mbar_wait(&w.o_full, it & 1);
-      tr.mark();
       tc_fence_after();
       uint32_t r[32];
       tmem_ld_32x32b_x32(tO, r);
       tmem_ld_wait();
       warp_release_tmem(&w.o_empty, lane);
-      const float l = l0 + l1;
+      float la, lb, lc, ld;
+      f2_unpack(l01, la, lb);
+      f2_unpack(l23, lc, ld);
+      const float l = (la + lb) + (lc + ld);
       const float sc = inv_keep / l;
       uint4* orow = reinterpret_cast<uint4*>(out + ((long)b * kS + q) * kLdO + h * 32);
 #pragma unroll
@@ -365,7 +574,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mQkv, bf16* __restrict__ out
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 3) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
   }
@@ -425,7 +634,7 @@ template <int DROP, int NWG>
 __global__ void __launch_bounds__(DqCfg<NWG>::kThreads, 1)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap mQkv, const __grid_constant__ CUtensorMap mDo,
                    const bf16* __restrict__ o_in, const bf16* __restrict__ d_o, const float* __restrict__ lse2,
-                   float* __restrict__ dsum, bf16* __restrict__ dqkv, uint32_t key, uint32_t th7, float inv_keep,
+                   float* __restrict__ dsum, bf16* __restrict__ dqkv, uint32_t key, uint32_t th15, float inv_keep,
                    const uint32_t* __restrict__ drop_bits) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -506,7 +715,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap mQkv, const __grid_consta
     WgBars& w = bars->wg[g];
     const uint32_t tS = tmem + ((uint32_t)(quad * 32) << 16) + g * 160, tDp = tS + 64, tDq = tS + 128;
     uint8_t* myDs = sDs + g * kPTile;
-    const uint32_t addc = (128u - th7) * 0x01010101u;
+    const DropKeys dk = drop_keys(key);
     const float keep_prob = 1.f / inv_keep;
     uint32_t n = 0;
     for (int it = 0; g + NWG * it < 8; ++it) {
@@ -531,7 +740,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap mQkv, const __grid_consta
       }
       dsum[(long)bh * kS + q] = D;
       const float Dp = D * keep_prob;
-      const uint32_t rowctr = (uint32_t)(bh * kS + q) * 256u;
+      const uint32_t rowid = (uint32_t)(bh * kS + q);
       uint32_t wn[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};  // keep-bit words, loaded one key tile ahead
       if (DROP == 2) {
         wn[0] = __ldg(drop_bits + ((size_t)bh * 32) * kS + q);
@@ -552,7 +761,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap mQkv, const __grid_consta
           tmem_ld_32x32b_x32(tDp + hf * 32, rd);
           tmem_ld_wait();
           if (hf == 1) warp_release_tmem(&w.s_empty[0], lane);
-          if (DROP == 1) wd[hf] = hash_word(key, rowctr + (uint32_t)(j * 16 + hf * 8), addc);
+          if (DROP == 1) wd[hf] = keep_word(rowid, (uint32_t)(2 * j + hf), dk, th15);
           uint32_t ds[16], pd[16];
           bwd_half<DROP, false>(rs, rd, L, Dp, wd[hf], ds, pd);
           if (hf == 0) mbar_wait(&w.p_empty, (n & 1) ^ 1);
@@ -601,7 +810,7 @@ template <int DROP>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mQkv, const __grid_constant__ CUtensorMap mQkv64,
                     const __grid_constant__ CUtensorMap mDo, const float* __restrict__ lse2,
-                    const float* __restrict__ dsum, bf16* __restrict__ dqkv, uint32_t key, uint32_t th7, float inv_keep,
+                    const float* __restrict__ dsum, bf16* __restrict__ dqkv, uint32_t key, uint32_t th15, float inv_keep,
                     const uint32_t* __restrict__ drop_bits) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -694,7 +903,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mQkv, const __grid_const
     const uint32_t tS = tmem + ((uint32_t)(quad * 32) << 16) + g * 192, tDp = tS + 64, tDk = tS + 128, tDv = tS + 160;
     uint8_t* myP = sP + g * kPTile;
     uint8_t* myDs = sDs + g * kPTile;
-    const uint32_t addc = (128u - th7) * 0x01010101u;
+    const DropKeys dk = drop_keys(key);
     const float keep_prob = 1.f / inv_keep;
     uint32_t n = 0;
     // per-tile row scalars and keep-bit words are loaded one tile ahead of their use
@@ -720,7 +929,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mQkv, const __grid_const
             wn[1] = __ldg(drop_bits + ((size_t)bh * 32 + jn * 2 + 1) * kS + qn);
           }
         }
-        const uint32_t rowctr = (uint32_t)(bh * kS + q) * 256u;
+        const uint32_t rowid = (uint32_t)(bh * kS + q);
         mbar_wait(&w.s_full[0], n & 1);
         tc_fence_after();
 #pragma unroll
@@ -730,7 +939,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mQkv, const __grid_const
           tmem_ld_32x32b_x32(tDp + hf * 32, rd);
           tmem_ld_wait();
           if (hf == 1) warp_release_tmem(&w.s_empty[0], lane);
-          if (DROP == 1) wd[hf] = hash_word(key, rowctr + (uint32_t)(j * 16 + hf * 8), addc);
+          if (DROP == 1) wd[hf] = keep_word(rowid, (uint32_t)(2 * j + hf), dk, th15);
           uint32_t ds[16], pd[16];
           bwd_half<DROP, true>(rs, rd, L, Dp, wd[hf], ds, pd);
           if (hf == 0) mbar_wait(&w.p_empty, (n & 1) ^ 1);
@@ -785,15 +994,15 @@ int set_smem(K kernel, int bytes) {
 }
 
 struct AttnDrop {
-  uint32_t th7;
+  uint32_t th15;
   float inv_keep;
 };
 AttnDrop drop_params(uint32_t thresh16) {
   AttnDrop d;
-  d.th7 = (thresh16 + 256) >> 9;  // p * 128, rounded
-  if (thresh16 && d.th7 == 0) d.th7 = 1;
-  if (d.th7 > 127) d.th7 = 127;
-  d.inv_keep = 128.f / (128.f - (float)d.th7);
+  d.th15 = (thresh16 + 1) >> 1;  // p * 2^15, rounded (p = 0.1 -> 3277)
+  if (thresh16 && d.th15 == 0) d.th15 = 1;
+  if (d.th15 > 32767) d.th15 = 32767;
+  d.inv_keep = 32768.f / (32768.f - (float)d.th15);
   return d;
 }
 
@@ -802,37 +1011,51 @@ AttnDrop drop_params(uint32_t thresh16) {
 // p_drop = thresh16 / 65536; thresh16 == 0 disables dropout (eval / parity runs).  drop_bits: optional keep-bit
 // buffer of attn_drop_bits_bytes(B) bytes written by the forward and consumed by the backward (may be null: the
 // backward then regenerates the mask from the seed).
-// tuning aid: device buffer (>= 64 KB of int64) that block 0 / warp 4 fills with clock64() marks, or null to disable
-extern "C" int focr_attn_set_trace(void* buf) {
-  long long* p = (long long*)buf;
-  FOCR_CHECK_CUDA(cudaMemcpyToSymbol(g_attn_trace, &p, sizeof(p)));
+size_t attn_drop_bits_bytes(int B) { return (size_t)B * 4 * (kS / 32) * kS * sizeof(uint32_t); }
+
+// test knob: 1 forces the exact two-pass route of the forward (row maximum first) regardless of the score bound
+static int g_attn_force_exact = 0;
+extern "C" int focr_attn_set_force_exact(int on) {
+  g_attn_force_exact = on ? 1 : 0;
   return FOCR_OK;
 }
 
-size_t attn_drop_bits_bytes(int B) { return (size_t)B * 4 * (kS / 32) * kS * sizeof(uint32_t); }
-
 template <int NWG>
-int launch_fwd(const CUtensorMap& mq, bf16* out, float* lse2, int B, uint32_t key, uint32_t thresh16, uint32_t* drop_bits,
-               const uint32_t* seed_dev, cudaStream_t s) {
+int launch_fwd(const CUtensorMap& mq, const bf16* qkv, bf16* out, float* lse2, int B, uint32_t key, uint32_t thresh16,
+               uint32_t* drop_bits, const uint32_t* seed_dev, cudaStream_t s) {
   using Cfg = FwdCfg<NWG>;
   static bool init = false;
   if (!init) {
-    int rc = set_smem(attn_fwd_kernel<0, NWG>, Cfg::kSmem);
+    int rc = set_smem(attn_fwd_kernel<0, NWG, 0>, Cfg::kSmem);
     if (rc) return rc;
-    rc = set_smem(attn_fwd_kernel<1, NWG>, Cfg::kSmem);
+    rc = set_smem(attn_fwd_kernel<1, NWG, 0>, Cfg::kSmem);
     if (rc) return rc;
-    rc = set_smem(attn_fwd_kernel<2, NWG>, Cfg::kSmem);
+    rc = set_smem(attn_fwd_kernel<2, NWG, 0>, Cfg::kSmem);
+    if (rc) return rc;
+    rc = set_smem(attn_fwd_kernel<1, NWG, kTh15P01>, Cfg::kSmem);
+    if (rc) return rc;
+    rc = set_smem(attn_fwd_kernel<2, NWG, kTh15P01>, Cfg::kSmem);
     if (rc) return rc;
     init = true;
   }
   const AttnDrop d = drop_params(thresh16);
   const dim3 grid(B * 4), block(Cfg::kThreads);
+  const int fe = g_attn_force_exact;
+  const bool p01 = d.th15 == kTh15P01;
   if (!thresh16)
-    attn_fwd_kernel<0, NWG><<<grid, block, Cfg::kSmem, s>>>(mq, out, lse2, key, 0, 1.f, nullptr, nullptr);
+    attn_fwd_kernel<0, NWG, 0><<<grid, block, Cfg::kSmem, s>>>(mq, qkv, out, lse2, key, 0, 1.f, nullptr, nullptr, fe);
+  else if (!drop_bits && p01)
+    attn_fwd_kernel<1, NWG, kTh15P01><<<grid, block, Cfg::kSmem, s>>>(mq, qkv, out, lse2, key, d.th15, d.inv_keep, nullptr,
+                                                                      seed_dev, fe);
   else if (!drop_bits)
-    attn_fwd_kernel<1, NWG><<<grid, block, Cfg::kSmem, s>>>(mq, out, lse2, key, d.th7, d.inv_keep, nullptr, seed_dev);
+    attn_fwd_kernel<1, NWG, 0><<<grid, block, Cfg::kSmem, s>>>(mq, qkv, out, lse2, key, d.th15, d.inv_keep, nullptr, seed_dev,
+                                                               fe);
+  else if (p01)
+    attn_fwd_kernel<2, NWG, kTh15P01><<<grid, block, Cfg::kSmem, s>>>(mq, qkv, out, lse2, key, d.th15, d.inv_keep, drop_bits,
+                                                                      seed_dev, fe);
   else
-    attn_fwd_kernel<2, NWG><<<grid, block, Cfg::kSmem, s>>>(mq, out, lse2, key, d.th7, d.inv_keep, drop_bits, seed_dev);
+    attn_fwd_kernel<2, NWG, 0><<<grid, block, Cfg::kSmem, s>>>(mq, qkv, out, lse2, key, d.th15, d.inv_keep, drop_bits,
+                                                               seed_dev, fe);
   FOCR_LAUNCH_CHECK();
   return FOCR_OK;
 }
@@ -841,19 +1064,11 @@ int attn_forward(const bf16* qkv, bf16* out, float* lse2, int B, uint32_t key, u
                  cudaStream_t s, const uint32_t* seed_dev) {
   ProfScope _ps("attn_fwd", s);
   FOCR_REQUIRE(B >= 1 && B <= 1024, "attention: B=%d out of range", B);
-  static_assert(sizeof(Bars) <= 1024, "barrier block");
+  static_assert(sizeof(Bars) <= 1024 && sizeof(FwdBars) <= 1024, "barrier block");
   CUtensorMap mq;
   int rc = focr_make_tmap_2d(&mq, qkv, kLdQkv, (unsigned long long)B * kS, kLdQkv * 2, 32, 128, 64);
   if (rc) return rc;
-  static int nwg = 0;
-  if (!nwg) {
-    const char* e = getenv("FOCR_ATTN_FWD_NWG");  // tuning knob: softmax groups per CTA (2, 3 or 4)
-    nwg = e ? atoi(e) : 4;
-    if (nwg < 2 || nwg > 4) nwg = 4;
-  }
-  if (nwg == 2) return launch_fwd<2>(mq, out, lse2, B, key, thresh16, drop_bits, seed_dev, s);
-  if (nwg == 3) return launch_fwd<3>(mq, out, lse2, B, key, thresh16, drop_bits, seed_dev, s);
-  return launch_fwd<4>(mq, out, lse2, B, key, thresh16, drop_bits, seed_dev, s);
+  return launch_fwd<3>(mq, qkv, out, lse2, B, key, thresh16, drop_bits, seed_dev, s);  // 3 groups x 160 TMEM columns
 }
 
 template <int NWG>
@@ -875,10 +1090,10 @@ int launch_dq(const CUtensorMap& mq, const CUtensorMap& mdo, const bf16* o, cons
   if (!thresh16)
     attn_bwd_dq_kernel<0, NWG><<<grid, block, Cfg::kSmem, s>>>(mq, mdo, o, d_o, lse2, dsum, dqkv, key, 0, 1.f, nullptr);
   else if (!drop_bits)
-    attn_bwd_dq_kernel<1, NWG><<<grid, block, Cfg::kSmem, s>>>(mq, mdo, o, d_o, lse2, dsum, dqkv, key, d.th7, d.inv_keep,
+    attn_bwd_dq_kernel<1, NWG><<<grid, block, Cfg::kSmem, s>>>(mq, mdo, o, d_o, lse2, dsum, dqkv, key, d.th15, d.inv_keep,
                                                                 nullptr);
   else
-    attn_bwd_dq_kernel<2, NWG><<<grid, block, Cfg::kSmem, s>>>(mq, mdo, o, d_o, lse2, dsum, dqkv, key, d.th7, d.inv_keep,
+    attn_bwd_dq_kernel<2, NWG><<<grid, block, Cfg::kSmem, s>>>(mq, mdo, o, d_o, lse2, dsum, dqkv, key, d.th15, d.inv_keep,
                                                                 drop_bits);
   FOCR_LAUNCH_CHECK();
   return FOCR_OK;
@@ -923,10 +1138,10 @@ int attn_backward(const bf16* qkv, const bf16* o, const bf16* d_o, const float* 
     if (!thresh16)
       attn_bwd_dkv_kernel<0><<<grid, block, kDkvSmem, s>>>(mq, mq64, mdo, lse2, dsum, dqkv, key, 0, 1.f, nullptr);
     else if (!drop_bits)
-      attn_bwd_dkv_kernel<1><<<grid, block, kDkvSmem, s>>>(mq, mq64, mdo, lse2, dsum, dqkv, key, d.th7, d.inv_keep,
+      attn_bwd_dkv_kernel<1><<<grid, block, kDkvSmem, s>>>(mq, mq64, mdo, lse2, dsum, dqkv, key, d.th15, d.inv_keep,
                                                            nullptr);
     else
-      attn_bwd_dkv_kernel<2><<<grid, block, kDkvSmem, s>>>(mq, mq64, mdo, lse2, dsum, dqkv, key, d.th7, d.inv_keep,
+      attn_bwd_dkv_kernel<2><<<grid, block, kDkvSmem, s>>>(mq, mq64, mdo, lse2, dsum, dqkv, key, d.th15, d.inv_keep,
                                                            drop_bits);
     FOCR_LAUNCH_CHECK();
   }

@@ -23,8 +23,33 @@ from .transformer_english_decomposition import TG_ALPHABET, Transformer
 __all__ = ["StrokeFocusLoss", "to_gray_tensor"]
 
 
-def to_gray_tensor(tensor: torch.Tensor) -> torch.Tensor:  # stroke_focus_loss.py:12-18 (kept for API parity)
-    raise RuntimeError("to_gray_tensor is fused into the focr recogniser stem (conv1_fwd_kernel); it is not a torch op here")
+class _ToGray(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, t):
+        if not t.is_cuda:
+            raise L.FocrError("to_gray_tensor runs on CUDA tensors only (no CPU fallback)")
+        if t.dim() != 4 or t.shape[1] < 3:
+            raise ValueError(f"to_gray_tensor expects (B, >=3, H, W), got {tuple(t.shape)}")
+        x = t.detach().float().contiguous()
+        b, c, h, w = x.shape
+        out = torch.empty(b, 1, h, w, dtype=torch.float32, device=x.device)
+        L.check(L.lib.focr_to_gray(x.data_ptr(), out.data_ptr(), b, c, h * w, L.cur_stream()), "to_gray")
+        ctx.shape = (b, c, h, w)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        b, c, h, w = ctx.shape
+        g = g.float().contiguous()
+        d = torch.empty(b, c, h, w, dtype=torch.float32, device=g.device)
+        L.check(L.lib.focr_to_gray_bwd(g.data_ptr(), d.data_ptr(), b, c, h * w, L.cur_stream()), "to_gray_bwd")
+        return d
+
+
+def to_gray_tensor(tensor: torch.Tensor) -> torch.Tensor:
+    """0.299 R + 0.587 G + 0.114 B, (B, >=3, H, W) -> (B, 1, H, W)  (stroke_focus_loss.py:12-18; inside the fused loss the same
+    arithmetic is part of the recogniser stem, conv1_fwd_kernel)"""
+    return _ToGray.apply(tensor)
 
 
 class _FocusFn(torch.autograd.Function):

@@ -1,6 +1,7 @@
-"""Weight table of the confusion-weighted cross entropy — host-side half of ``loss.weight_ce_loss`` of scene-text-telescope
-(scene-text-telescope/loss/weight_ce_loss.py:10-33).  The loss itself (``weight_cross_entropy``, :36-45) runs inside
-``focr_text_focus_loss`` (wce_kernel, csrc/focus.cu); calling it from Python is not a product path."""
+"""``loss.weight_ce_loss`` of scene-text-telescope on the focr engine (scene-text-telescope/loss/weight_ce_loss.py): the
+weight table built on the host (:10-33) and ``weight_cross_entropy(pred, gt)`` (:36-45) as a CUDA autograd function.  Inside
+``TextFocusLoss`` the same arithmetic runs fused in ``focr_text_focus_loss`` (wce_kernel, csrc/focus.cu); this module-level
+callable exists because the reference exports it.  No CPU fallback."""
 from __future__ import annotations
 
 import pickle
@@ -35,5 +36,49 @@ def load_confuse_matrix(path: str = "./dataset/mydata/confuse.pkl") -> torch.Ten
     return confuse_weight_table(np.asarray(data, dtype=np.float64))
 
 
-def weight_cross_entropy(pred, gt):
-    raise RuntimeError("weight_cross_entropy is fused into focr_text_focus_loss (wce_kernel); use TextFocusLoss")
+weight_table = None   # the reference builds it at import from ./dataset/mydata/confuse.pkl (:35); here on first use
+
+
+def set_weight_table(table: torch.Tensor) -> None:
+    """install a (C, C) weight table (e.g. ``confuse_weight_table(counts)``) instead of reading confuse.pkl"""
+    global weight_table
+    weight_table = table.detach().float().contiguous()
+
+
+class _WeightCE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, gt, table):
+        from .. import _lib as L
+        if not pred.is_cuda:
+            raise L.FocrError("weight_cross_entropy runs on CUDA tensors only (no CPU fallback)")
+        p = pred.detach().float().contiguous()
+        g = gt.to(device=p.device, dtype=torch.long).contiguous()
+        n, c = p.shape
+        if table.shape != (c, c):
+            raise ValueError(f"weight table {tuple(table.shape)} does not match {c} classes")
+        loss = torch.empty(1, dtype=torch.float32, device=p.device)
+        d_pred = torch.empty_like(p)
+        status = torch.zeros(1, dtype=torch.int32, device=p.device)
+        ws = torch.empty(L.lib.focr_weight_cross_entropy_workspace_bytes(n), dtype=torch.uint8, device=p.device)
+        L.check(L.lib.focr_weight_cross_entropy(p.data_ptr(), g.data_ptr(), table.data_ptr(), loss.data_ptr(), d_pred.data_ptr(),
+                                                status.data_ptr(), n, c, ws.data_ptr(), ws.numel(), L.cur_stream()),
+                "weight_cross_entropy")
+        if int(status.item()):   # the reference's weight_table[gt] raises IndexError on such labels
+            raise IndexError("weight_cross_entropy: target index out of range")
+        ctx.save_for_backward(d_pred)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        (d_pred,) = ctx.saved_tensors
+        return d_pred * g, None, None
+
+
+def weight_cross_entropy(pred: torch.Tensor, gt: torch.Tensor) -> torch.Tensor:
+    """-mean_i log(w[gt_i, gt_i] e^{pred_i, gt_i} / sum_j w[gt_i, j] e^{pred_ij})  (weight_ce_loss.py:36-45)"""
+    global weight_table
+    if weight_table is None:
+        set_weight_table(load_confuse_matrix())
+    if weight_table.device != pred.device:
+        weight_table = weight_table.to(pred.device)
+    return _WeightCE.apply(pred, gt, weight_table)

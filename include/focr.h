@@ -69,11 +69,13 @@ int focr_layernorm_std_bwd(const void* dy, const void* x, const float* a, void* 
 
 /* --- MultiHeadedAttention core, h = 4, d_k = 32, 1024 tokens: STT/model/tbsrn.py:109-150 ------------------------
  * qkv (B*1024,384) bf16 = [q|k|v]; out (B*1024,128); lse2 fp32 (B*4*1024).  Dropout on P with rate p_drop; the
- * keep mask is a counter hash of (seed, stream_id, b, h, q, k).  drop_bits (device, focr_mha_drop_bits_bytes(B)
+ * keep mask is a counter-based generator keyed on (seed, stream_id, b, h, q, k).  drop_bits (device, focr_mha_drop_bits_bytes(B)
  * bytes, or NULL): when given, the forward stores its keep decisions there (1 bit per element) and the backward
  * reads them instead of re-hashing (the fast path); with NULL the backward regenerates the mask from the seed.
  * Bit layout: word [b*4+h][k/32][q] (uint32), key k of the 32-key group at bit (k%32)/4 + 8*(k&3).
- * The attention dropout rate is quantised to 1/128 (p = 0.1 -> 13/128); the rescale uses the quantised rate. */
+ * The rate is held to 2^-15 (p = 0.1 -> 3277/32768 = 0.100006); the 1/(1-p) rescale uses that rate, so E[out] is exact.
+ * The forward shifts the softmax by a per-row upper bound of the scores (|q_i| max_j |k_j| / sqrt(d_k)) instead of the
+ * row maximum and falls back to the exact two-pass route per (batch, head) when that bound is too loose for fp32. */
 size_t focr_mha_drop_bits_bytes(int B);
 int focr_mha_flash_fwd(const void* qkv, void* out, float* lse2, int B, float p_drop, unsigned seed, unsigned stream_id,
                        void* drop_bits, void* stream);
@@ -87,8 +89,8 @@ int focr_mha_flash_bwd(const void* qkv, const void* out, const void* d_out, cons
 int focr_umma_probe(const void* img, int img_bytes, unsigned long long desc_a, unsigned long long desc_b, unsigned idesc,
                     int nk, unsigned a_step16, unsigned b_step16, float* out, int ncols, void* stream);
 
-/* tuning aid: clock64() trace of one softmax warp of the attention forward (block 0); NULL disables */
-int focr_attn_set_trace(void* device_buf_int64);
+/* test support: on != 0 forces the exact (row-maximum) route of the attention forward for every (batch, head) */
+int focr_attn_set_force_exact(int on);
 
 /* --- step body: STT/interfaces/super_resolution.py:69-84, STT/loss/text_focus_loss.py:86, base.py:194-198 ------ */
 int focr_mse_loss_grad(const float* sr, const float* hr, float* d_sr, float* loss, long n, float gscale, void* ws,
@@ -186,6 +188,20 @@ int focr_text_focus_loss(const void* prepared, size_t prepared_bytes, int n_clas
                          float* d_sr, float* losses, float* map_hr_out, float* map_sr_out, float* sr_pred_out, void* ws,
                          size_t ws_bytes, void* stream);
 int focr_focus_loss_ws_tensor(int B, int T, const char* name, long long* byte_offset, long long* elems, int* elem_bytes);
+
+/* Stand-alone forms of the two helpers the reference exports next to its focus losses (code importing them keeps working on
+ * CUDA tensors; the fused losses above carry their own copies):
+ * weight_cross_entropy(pred, gt) scene-text-telescope/loss/weight_ce_loss.py:36-45: pred fp32 (N, C) logits, gt int64 (N),
+ * table fp32 (C, C) = load_confuse_matrix(); loss[0] = -(1/N) sum_i log(w[g_i][g_i] e^{p_i,g_i} / sum_j w[g_i][j] e^{p_ij}) by
+ * log-sum-exp; d_pred (optional, fp32 (N, C)) = d loss / d pred; status (optional, int32[1]) is set to 1 when a gt index lies
+ * outside [0, C) (torch indexing raises there).
+ * to_gray_tensor(t) scene-text-telescope/loss/text_focus_loss.py:16-21 (text-gestalt/loss/stroke_focus_loss.py:12-18):
+ * img fp32 NCHW (B, C >= 3, H, W) -> gray (B, 1, H, W) = 0.299 R + 0.587 G + 0.114 B; _bwd writes d_img (channels >= 3: zero). */
+size_t focr_weight_cross_entropy_workspace_bytes(long N);
+int focr_weight_cross_entropy(const float* pred, const long long* gt, const float* table, float* loss, float* d_pred,
+                              int* status, long N, int C, void* ws, size_t ws_bytes, void* stream);
+int focr_to_gray(const float* img, float* gray, long B, int C, long HW, void* stream);
+int focr_to_gray_bwd(const float* d_gray, float* d_img, long B, int C, long HW, void* stream);
 
 /* --- evaluation metrics: scene-text-telescope/utils/ssim_psnr.py:9-15 (calculate_psnr), :31-78 (SSIM, window 11, sigma 1.5),
  * as called per validation batch by interfaces/super_resolution.py:191-192.  img1, img2 fp32 NCHW (B, channels >= 3, 32, 128)

@@ -33,32 +33,71 @@ def _keep(key: int, elem_index: np.ndarray, th: int) -> np.ndarray:
     return lane >= np.uint64(th)
 
 
-def thresh7(p: float) -> int:
-    """attention.cu compares 7-bit lanes: th7 = (thresh16 + 256) >> 9 (p quantised to 1/128)"""
+# ---- attention dropout: bit-sliced Bernoulli(th15 / 32768) over Philox-2x32-4 words (attention.cu: keep_word32) ----
+PHILOX_M = np.uint64(0xD256D193)
+PHILOX_W = 0x9E3779B9
+
+
+def thresh15(p: float) -> int:
+    """attention.cu: th15 = (thresh16 + 1) >> 1 = round(p * 2^15) (p = 0.1 -> 3277)"""
     t = thresh16(p)
-    th = (t + 256) >> 9
+    th = (t + 1) >> 1
     if t and th == 0:
         th = 1
-    return min(th, 127)
+    return min(th, 32767)
+
+
+def philox4(ctr: np.ndarray, key: int):
+    """four rounds of Philox-2x32: (L, R) <- (hi(L * M) ^ k_r ^ R, lo(L * M)), k_r = key * 0x85EBCA6B + 0x1B873593 + r W"""
+    L = ctr.astype(np.uint64) & M32
+    R = np.full_like(L, key & 0xFFFFFFFF)
+    k = (key * 0x85EBCA6B + 0x1B873593) & 0xFFFFFFFF
+    for _ in range(4):
+        prod = L * PHILOX_M
+        L = (prod >> np.uint64(32)) ^ np.uint64(k) ^ R
+        R = prod & M32
+        k = (k + PHILOX_W) & 0xFFFFFFFF
+    return L, R
+
+
+def _rotl(x: np.ndarray, r: int) -> np.ndarray:
+    return ((x << np.uint64(r)) | (x >> np.uint64(32 - r))) & M32
+
+
+def attn_keep_words(rowid: np.ndarray, kw: np.ndarray, key: int, th15: int) -> np.ndarray:
+    """keep word (uint32 in a uint64 array) of keys [32 kw, 32 kw + 32) of row `rowid` = (b*4+h)*1024 + q"""
+    ctr0 = ((rowid.astype(np.uint64) * np.uint64(32) + kw.astype(np.uint64)) * np.uint64(8)) & M32
+    w = []
+    for c in range(6):
+        L, R = philox4((ctr0 + np.uint64(c)) & M32, key)
+        w += [L, R]
+    w += [_rotl(w[0], 7), _rotl(w[1], 13), _rotl(w[2], 22)]
+    r = np.zeros_like(ctr0)
+    for i in range(14, -1, -1):
+        r = (w[i] | r) if (th15 >> (14 - i)) & 1 else (w[i] & r)
+    return (~r) & M32
 
 
 def attn_keep_mask(B: int, seed: int, blk: int, p: float) -> torch.Tensor:
-    """(B,4,1024,1024) bool: element (b,h,q,k) has index ((b*4+h)*1024+q)*1024 + k; the hash of (index >> 2) carries
-    four 7-bit lanes (low 7 bits of byte k & 3); kept iff lane >= th7 (attention.cu)."""
-    idx = np.arange(B * 4 * 1024 * 1024, dtype=np.uint64)
-    h = hash32(drop_key(seed, 2 * blk), idx >> np.uint64(2))
-    lane = (h >> (np.uint64(8) * (idx & np.uint64(3)))) & np.uint64(0x7F)
-    return torch.from_numpy((lane >= np.uint64(thresh7(p))).reshape(B, 4, 1024, 1024))
+    """(B,4,1024,1024) bool keep mask of attention layer `blk`: key k of a 32-key group sits at bit 8 (k & 3) + (k % 32) // 4
+    of the group's keep word (attention.cu)."""
+    rowid = np.arange(B * 4 * 1024, dtype=np.uint64)[:, None]
+    kw = np.arange(32, dtype=np.uint64)[None, :]
+    words = attn_keep_words(rowid, kw, drop_key(seed, 2 * blk), thresh15(p))       # [B*4*1024, 32]
+    kk = np.arange(32, dtype=np.uint64)
+    sh = kk // np.uint64(4) + np.uint64(8) * (kk & np.uint64(3))
+    m = (words[:, :, None] >> sh[None, None, :]) & np.uint64(1)                      # [rows, kw, kk]
+    return torch.from_numpy(m.astype(bool).reshape(B, 4, 1024, 1024))
 
 
 def attn_keep_scale(p: float) -> float:
-    """attention.cu scales kept probabilities by 128/(128-th7)"""
-    return 128.0 / (128.0 - thresh7(p))
+    """attention.cu scales kept probabilities by 32768/(32768-th15) (exactly 1/(1-rate))"""
+    return 32768.0 / (32768.0 - thresh15(p))
 
 
 def attn_drop_rate(p: float) -> float:
-    """the rate the attention kernels actually apply (13/128 for p = 0.1)"""
-    return thresh7(p) / 128.0
+    """the rate the attention kernels actually apply (3277/32768 = 0.100006 for p = 0.1)"""
+    return thresh15(p) / 32768.0
 
 
 def ffn_keep_mask(B: int, seed: int, blk: int, p: float) -> torch.Tensor:

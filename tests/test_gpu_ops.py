@@ -114,15 +114,21 @@ def _attn_ref(qkv, B, keep=None, scale_keep=1.0):
     return torch.matmul(p, v).transpose(1, 2).reshape(B * 1024, 128)
 
 
-@pytest.mark.parametrize("B,p_drop,use_bits", [(2, 0.0, False), (1, 0.1, False), (3, 0.0, True), (2, 0.1, True)])
-def test_attention_fwd_bwd(B, p_drop, use_bits):
+@pytest.mark.parametrize("B,p_drop,use_bits,exact,gain", [(2, 0.0, False, 0, 1.2), (1, 0.1, False, 0, 1.2),
+                                                          (3, 0.0, True, 0, 1.2), (2, 0.1, True, 0, 1.2),
+                                                          (2, 0.1, True, 1, 1.2), (1, 0.0, False, 0, 6.0),
+                                                          (1, 0.1, True, 0, 2.5)])
+def test_attention_fwd_bwd(B, p_drop, use_bits, exact, gain):
     """use_bits: the forward stores its keep decisions (1 bit per element) and the backward reads them (the path the
-    engine uses); otherwise the backward regenerates the mask from the seed.  Both must match the numpy twin."""
+    engine uses); otherwise the backward regenerates the mask from the seed.  Both must match the numpy twin.
+    exact = 1 forces the forward's two-pass (row maximum) route; gain = 6 makes the Cauchy-Schwarz score bound so loose
+    (logits up to +-100) that the kernel must take that route by itself; gain = 2.5 is a peaked softmax on the bound route."""
     L = _L()
     from oracle import dropout_rng as R
+    L.check(L.lib.focr_attn_set_force_exact(exact))
     T = B * 1024
     g = torch.Generator(device=DEV).manual_seed(B)
-    qkv = _bf(torch.randn(T, 384, device=DEV, generator=g) * 1.2)
+    qkv = _bf(torch.randn(T, 384, device=DEV, generator=g) * gain)
     out = torch.empty(T, 128, dtype=torch.bfloat16, device=DEV)
     lse = torch.empty(B * 4 * 1024, device=DEV)
     seed, blk = 1234, 3
@@ -133,6 +139,7 @@ def test_attention_fwd_bwd(B, p_drop, use_bits):
     L.check(L.lib.focr_mha_flash_fwd(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, p_drop, seed, 2 * blk, bp,
                                      L.cur_stream()))
     _sync(L)
+    L.check(L.lib.focr_attn_set_force_exact(0))
     keep = R.attn_keep_mask(B, seed, blk, p_drop).to(DEV) if p_drop > 0 else None
     if use_bits and p_drop > 0:
         # decode: word [b,h,k/32,q], key k of the group at bit (k%32)//4 + 8*(k&3)
@@ -148,7 +155,7 @@ def test_attention_fwd_bwd(B, p_drop, use_bits):
     # log-sum-exp (log2 domain)
     q, k = [qkv.float()[:, i * 128:(i + 1) * 128].view(B, 1024, 4, 32).transpose(1, 2) for i in range(2)]
     lse_ref = torch.logsumexp(torch.matmul(q, k.transpose(-2, -1)) / math.sqrt(32), -1) / math.log(2.0)
-    assert torch.allclose(lse.view(B, 4, 1024), lse_ref, atol=2e-2)
+    assert torch.allclose(lse.view(B, 4, 1024), lse_ref, atol=2e-2, rtol=1e-4)
     d_out = _bf(torch.randn(T, 128, device=DEV, generator=g))
     ref.backward(d_out.float())
     dqkv = torch.empty_like(qkv)
@@ -161,12 +168,40 @@ def test_attention_fwd_bwd(B, p_drop, use_bits):
         assert e < 2e-2, (nm, e)
 
 
+def test_attention_shift_clamp_adversarial_first_keys():
+    """forward on the bound route with the softmax shift pinned by the clamp: the first 32 keys of every row score
+    -a^2/sqrt(32) and all others +a^2/sqrt(32) with a^2 c = 104 log2 units, so the first-keys estimate is 208 below the
+    row maximum and shift = bound - 100; the row sum must neither overflow nor vanish."""
+    L = _L()
+    B, T = 1, 1024
+    a = math.sqrt(104.0 / (1.4426950408889634 / math.sqrt(32)))
+    u = torch.ones(32, device=DEV) * (a / math.sqrt(32))
+    qkv = torch.zeros(T, 384, device=DEV)
+    g = torch.Generator(device=DEV).manual_seed(5)
+    for h in range(4):
+        qkv[:, h * 32:(h + 1) * 32] = u
+        qkv[:, 128 + h * 32:128 + (h + 1) * 32] = u
+        qkv[:32, 128 + h * 32:128 + (h + 1) * 32] = -u
+    qkv[:, 256:] = torch.randn(T, 128, device=DEV, generator=g)
+    qkv = _bf(qkv)
+    out = torch.empty(T, 128, dtype=torch.bfloat16, device=DEV)
+    lse = torch.empty(4 * 1024, device=DEV)
+    L.check(L.lib.focr_mha_flash_fwd(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, 0.0, 0, 0, None, L.cur_stream()))
+    _sync(L)
+    ref = _attn_ref(qkv.float(), B)
+    assert torch.isfinite(out.float()).all() and torch.isfinite(lse).all()
+    assert _rel(out, ref) < 1e-2
+    q, k = [qkv.float()[:, i * 128:(i + 1) * 128].view(B, 1024, 4, 32).transpose(1, 2) for i in range(2)]
+    lse_ref = torch.logsumexp(torch.matmul(q, k.transpose(-2, -1)) / math.sqrt(32), -1) / math.log(2.0)
+    assert torch.allclose(lse.view(B, 4, 1024), lse_ref, atol=2e-2, rtol=1e-4)
+
+
 def test_attention_dropout_statistics():
-    """in-kernel mask: drop rate = the quantised 13/128 and E[out] unchanged (uniform V makes the dropped output = the
-    keep fraction)"""
+    """in-kernel mask: drop rate = 3277/32768 (p = 0.1 to 2^-15) and E[out] unchanged (uniform V makes the dropped
+    output = the keep fraction)"""
     from oracle import dropout_rng as R
     pq = R.attn_drop_rate(0.1)
-    assert abs(pq - 0.1) < 2e-3
+    assert abs(pq - 0.1) < 1e-5
     L = _L()
     B = 2
     qkv = torch.zeros(B * 1024, 384, device=DEV)
