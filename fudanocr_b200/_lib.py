@@ -52,9 +52,11 @@ _SIGS = {
     "focr_layernorm_std_bwd": (C.c_int, [_vp, _vp, _fp, _vp, _fp, _fp, _l, _f, _vp, _sz, _vp]),
     "focr_mha_drop_bits_bytes": (_sz, [_i]),
     "focr_mha_flash_fwd": (C.c_int, [_vp, _vp, _fp, _i, _f, _u, _u, _vp, _vp]),
-    "focr_mha_flash_bwd": (C.c_int, [_vp, _vp, _vp, _fp, _fp, _vp, _i, _f, _u, _u, _vp, _vp]),
+    "focr_mha_bwd_workspace_bytes": (_sz, [_i]),
+    "focr_mha_flash_bwd": (C.c_int, [_vp, _vp, _vp, _fp, _vp, _sz, _vp, _i, _f, _u, _u, _vp, _vp]),
     "focr_umma_probe": (C.c_int, [_vp, _i, C.c_ulonglong, C.c_ulonglong, _u, _i, _u, _u, _vp, _i, _vp]),
     "focr_attn_set_force_exact": (C.c_int, [_i]),
+    "focr_attn_set_bwd_two_pass": (C.c_int, [_i]),
     "focr_weight_cross_entropy_workspace_bytes": (_sz, [_l]),
     "focr_weight_cross_entropy": (C.c_int, [_fp, _vp, _fp, _fp, _fp, _vp, _l, _i, _vp, _sz, _vp]),
     "focr_to_gray": (C.c_int, [_fp, _fp, _l, _i, _l, _vp]),

@@ -73,13 +73,16 @@ int focr_layernorm_std_bwd(const void* dy, const void* x, const float* a, void* 
  * bytes, or NULL): when given, the forward stores its keep decisions there (1 bit per element) and the backward
  * reads them instead of re-hashing (the fast path); with NULL the backward regenerates the mask from the seed.
  * Bit layout: word [b*4+h][k/32][q] (uint32), key k of the 32-key group at bit (k%32)/4 + 8*(k&3).
+ * The backward is ONE kernel (S and dP evaluated once per tile: five GEMMs, one exponential per element); ws
+ * (focr_mha_bwd_workspace_bytes(B) bytes, device) holds D = rowsum(dO o O) and a per-SM fp32 scratch for dK / dV partials.
  * The rate is held to 2^-15 (p = 0.1 -> 3277/32768 = 0.100006); the 1/(1-p) rescale uses that rate, so E[out] is exact.
  * The forward shifts the softmax by a per-row upper bound of the scores (|q_i| max_j |k_j| / sqrt(d_k)) instead of the
  * row maximum and falls back to the exact two-pass route per (batch, head) when that bound is too loose for fp32. */
 size_t focr_mha_drop_bits_bytes(int B);
 int focr_mha_flash_fwd(const void* qkv, void* out, float* lse2, int B, float p_drop, unsigned seed, unsigned stream_id,
                        void* drop_bits, void* stream);
-int focr_mha_flash_bwd(const void* qkv, const void* out, const void* d_out, const float* lse2, float* dsum_ws,
+size_t focr_mha_bwd_workspace_bytes(int B);
+int focr_mha_flash_bwd(const void* qkv, const void* out, const void* d_out, const float* lse2, void* ws, size_t ws_bytes,
                        void* dqkv, int B, float p_drop, unsigned seed, unsigned stream_id, const void* drop_bits,
                        void* stream);
 
@@ -91,6 +94,8 @@ int focr_umma_probe(const void* img, int img_bytes, unsigned long long desc_a, u
 
 /* test support: on != 0 forces the exact (row-maximum) route of the attention forward for every (batch, head) */
 int focr_attn_set_force_exact(int on);
+/* test support: on != 0 selects the two-kernel attention backward (dQ pass + dK/dV pass) instead of the single-pass kernel */
+int focr_attn_set_bwd_two_pass(int on);
 
 /* --- step body: STT/interfaces/super_resolution.py:69-84, STT/loss/text_focus_loss.py:86, base.py:194-198 ------ */
 int focr_mse_loss_grad(const float* sr, const float* hr, float* d_sr, float* loss, long n, float gscale, void* ws,

@@ -10,12 +10,12 @@ st = L.cur_stream()
 res = []
 for rep in range(6):
     out = torch.zeros(T, 128, dtype=torch.bfloat16, device=dev); lse = torch.zeros(B * 4096, device=dev)
-    dqkv = torch.zeros_like(qkv); dsum = torch.zeros(B * 4096, device=dev)
+    dqkv = torch.zeros_like(qkv); bws = torch.empty(L.lib.focr_mha_bwd_workspace_bytes(B), dtype=torch.uint8, device='cuda')
     bits = torch.zeros(L.lib.focr_mha_drop_bits_bytes(B) // 4, dtype=torch.int32, device=dev)
     p = 0.1 if rep >= 3 else 0.0
     bp = bits.data_ptr() if p > 0 else None
     L.check(L.lib.focr_mha_flash_fwd(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, p, 5, 2, bp, st))
-    L.check(L.lib.focr_mha_flash_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), dsum.data_ptr(), dqkv.data_ptr(), B, p, 5, 2, bp, st))
+    L.check(L.lib.focr_mha_flash_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), bws.data_ptr(), bws.numel(), dqkv.data_ptr(), B, p, 5, 2, bp, st))
     torch.cuda.synchronize()
     res.append((out.clone(), lse.clone(), dqkv.clone()))
 for a, b in ((0, 1), (1, 2), (3, 4), (4, 5)):

@@ -54,8 +54,8 @@ def check(B, p_drop, use_bits):
     d_out = torch.randn(T, 128, device=dev, generator=g).to(torch.bfloat16)
     ref.backward(d_out.float())
     dqkv = torch.zeros_like(qkv)
-    dsum = torch.zeros(B * 4096, device=dev)
-    L.check(L.lib.focr_mha_flash_bwd(qkv.data_ptr(), out.data_ptr(), d_out.data_ptr(), lse.data_ptr(), dsum.data_ptr(),
+    bws = torch.empty(L.lib.focr_mha_bwd_workspace_bytes(B), dtype=torch.uint8, device=dev)
+    L.check(L.lib.focr_mha_flash_bwd(qkv.data_ptr(), out.data_ptr(), d_out.data_ptr(), lse.data_ptr(), bws.data_ptr(), bws.numel(),
                                      dqkv.data_ptr(), B, p_drop, 1234, 6, bp, st))
     L.check(L.lib.focr_sync_check(st))
     for i, nm in enumerate("qkv"):
@@ -74,7 +74,7 @@ def timing(B=256, reps=5):
     lse = torch.empty(B * 4096, device=dev)
     dout = torch.randn(T, 128, device=dev).to(torch.bfloat16)
     dqkv = torch.empty_like(qkv)
-    dsum = torch.empty(B * 4096, device=dev)
+    bws = torch.empty(L.lib.focr_mha_bwd_workspace_bytes(B), dtype=torch.uint8, device=dev)
     bits = torch.empty(L.lib.focr_mha_drop_bits_bytes(B) // 4, dtype=torch.int32, device=dev)
     st = L.cur_stream()
     for p, bp, tag in ((0.0, None, "no dropout"), (0.1, bits.data_ptr(), "dropout 0.1 + keep bits"), (0.1, None, "dropout 0.1 re-hash")):
@@ -84,7 +84,7 @@ def timing(B=256, reps=5):
             ev[0].record()
             L.check(L.lib.focr_mha_flash_fwd(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, p, 1, 0, bp, st))
             ev[1].record()
-            L.check(L.lib.focr_mha_flash_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), dsum.data_ptr(),
+            L.check(L.lib.focr_mha_flash_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), bws.data_ptr(), bws.numel(),
                                              dqkv.data_ptr(), B, p, 1, 0, bp, st))
             ev[2].record()
             torch.cuda.synchronize()
@@ -95,7 +95,7 @@ def timing(B=256, reps=5):
     L.lib.focr_prof_enable(1, None)
     for r in range(3):
         L.check(L.lib.focr_mha_flash_fwd(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, 0.1, 1, 0, bits.data_ptr(), st))
-        L.check(L.lib.focr_mha_flash_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), dsum.data_ptr(),
+        L.check(L.lib.focr_mha_flash_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), bws.data_ptr(), bws.numel(),
                                          dqkv.data_ptr(), B, 0.1, 1, 0, bits.data_ptr(), st))
     print({k: (c, round(ms / c, 4)) for k, (c, ms) in L.prof_collect().items()}, flush=True)
 

@@ -8,7 +8,7 @@ dev = "cuda"
 def ws(n): return torch.empty(int(n), dtype=torch.uint8, device=dev)
 qkv = (torch.randn(T, 384, device=dev) * 1.0).to(torch.bfloat16)
 out = torch.empty(T, 128, dtype=torch.bfloat16, device=dev); lse = torch.empty(B * 4096, device=dev)
-dout = torch.randn(T, 128, device=dev).to(torch.bfloat16); dqkv = torch.empty_like(qkv); dsum = torch.empty(B * 4096, device=dev)
+dout = torch.randn(T, 128, device=dev).to(torch.bfloat16); dqkv = torch.empty_like(qkv); bws = torch.empty(L.lib.focr_mha_bwd_workspace_bytes(B), dtype=torch.uint8, device='cuda')
 x128 = torch.randn(T, 128, device=dev).to(torch.bfloat16)
 w = torch.randn(384, 128, device=dev) / 11; b = torch.randn(384, device=dev)
 y = torch.empty(T, 384, dtype=torch.bfloat16, device=dev)
@@ -20,7 +20,7 @@ bits = torch.empty(L.lib.focr_mha_drop_bits_bytes(B) // 4, dtype=torch.int32, de
 st = L.cur_stream()
 for rep in range(2):
     L.check(L.lib.focr_mha_flash_fwd(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, 0.1, 1, 0, bits.data_ptr(), st))
-    L.check(L.lib.focr_mha_flash_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), dsum.data_ptr(), dqkv.data_ptr(), B, 0.1, 1, 0, bits.data_ptr(), st))
+    L.check(L.lib.focr_mha_flash_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), bws.data_ptr(), bws.numel(), dqkv.data_ptr(), B, 0.1, 1, 0, bits.data_ptr(), st))
     L.check(L.lib.focr_linear_fwd(x128.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), 0, T, 128, 384, 0, wsl.data_ptr(), wsl.numel(), st))
     L.check(L.lib.focr_conv2d_fwd(x64.data_ptr(), wc.data_ptr(), bc.data_ptr(), yc.data_ptr(), 0, 0, B, 16, 64, 64, 64, 3, 0, wsc.data_ptr(), wsc.numel(), st))
     L.check(L.lib.focr_linear_wgrad(y.data_ptr(), x128.data_ptr(), dw.data_ptr(), T, 128, 384, wsg.data_ptr(), wsg.numel(), st))

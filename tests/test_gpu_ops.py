@@ -117,15 +117,18 @@ def _attn_ref(qkv, B, keep=None, scale_keep=1.0):
 @pytest.mark.parametrize("B,p_drop,use_bits,exact,gain", [(2, 0.0, False, 0, 1.2), (1, 0.1, False, 0, 1.2),
                                                           (3, 0.0, True, 0, 1.2), (2, 0.1, True, 0, 1.2),
                                                           (2, 0.1, True, 1, 1.2), (1, 0.0, False, 0, 6.0),
-                                                          (1, 0.1, True, 0, 2.5)])
+                                                          (1, 0.1, True, 0, 2.5), (2, 0.1, True, 2, 1.2),
+                                                          (1, 0.1, False, 2, 1.2)])
 def test_attention_fwd_bwd(B, p_drop, use_bits, exact, gain):
     """use_bits: the forward stores its keep decisions (1 bit per element) and the backward reads them (the path the
     engine uses); otherwise the backward regenerates the mask from the seed.  Both must match the numpy twin.
-    exact = 1 forces the forward's two-pass (row maximum) route; gain = 6 makes the Cauchy-Schwarz score bound so loose
+    exact = 1 forces the forward's two-pass (row maximum) route, exact = 2 the two-kernel backward (the default is the
+    single-pass kernel); gain = 6 makes the Cauchy-Schwarz score bound so loose
     (logits up to +-100) that the kernel must take that route by itself; gain = 2.5 is a peaked softmax on the bound route."""
     L = _L()
     from oracle import dropout_rng as R
-    L.check(L.lib.focr_attn_set_force_exact(exact))
+    L.check(L.lib.focr_attn_set_force_exact(1 if exact == 1 else 0))
+    L.check(L.lib.focr_attn_set_bwd_two_pass(1 if exact == 2 else 0))
     T = B * 1024
     g = torch.Generator(device=DEV).manual_seed(B)
     qkv = _bf(torch.randn(T, 384, device=DEV, generator=g) * gain)
@@ -159,10 +162,11 @@ def test_attention_fwd_bwd(B, p_drop, use_bits, exact, gain):
     d_out = _bf(torch.randn(T, 128, device=DEV, generator=g))
     ref.backward(d_out.float())
     dqkv = torch.empty_like(qkv)
-    dsum = torch.empty(B * 4 * 1024, device=DEV)
-    L.check(L.lib.focr_mha_flash_bwd(qkv.data_ptr(), out.data_ptr(), d_out.data_ptr(), lse.data_ptr(), dsum.data_ptr(),
+    bws = torch.empty(L.lib.focr_mha_bwd_workspace_bytes(B), dtype=torch.uint8, device=DEV)
+    L.check(L.lib.focr_mha_flash_bwd(qkv.data_ptr(), out.data_ptr(), d_out.data_ptr(), lse.data_ptr(), bws.data_ptr(), bws.numel(),
                                      dqkv.data_ptr(), B, p_drop, seed, 2 * blk, bp, L.cur_stream()))
     _sync(L)
+    L.check(L.lib.focr_attn_set_bwd_two_pass(0))
     for i, nm in enumerate("qkv"):
         e = _rel(dqkv[:, i * 128:(i + 1) * 128], qr.grad[:, i * 128:(i + 1) * 128])
         assert e < 2e-2, (nm, e)
