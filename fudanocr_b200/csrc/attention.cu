@@ -1000,117 +1000,107 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mQkv, const __grid_const
 // backward, single pass: dQ, dK, dV of one (batch, head) from ONE evaluation of S and dP per 128 x 64 tile (five GEMMs per
 // tile instead of the seven of the two-kernel form above, one exponential per element instead of two, one read of the
 // keep bits instead of two).
-//   loop order: 64-key block outer, query tile inner (as the dK/dV kernel); dK_j, dV_j live in TMEM for the block, and dQ
-//   of EVERY query tile of the sweep stays in TMEM across all key blocks.  512 TMEM columns hold two groups x (S 64, dP 64,
-//   dK 32, dV 32) + four dQ tiles, so the 1024 queries are taken in two sweeps of 512; the dK/dV partials of the first
-//   sweep wait in an fp32 scratch slot owned by this SM (L2-resident: 256 KB per SM) and are folded in by the second.
-//   warp 0      TMA producer (per sweep: Q, dO of the sweep's 512 queries; per key block: K_j, V_j, double-buffered)
-//   warps 1, 3  one tcgen05.mma issuing thread per group; the dQ accumulators, which both add into, are zeroed by the
-//               softmax warps and only ever accumulated
-//   warp 2      TMEM allocator
-//   warps 4-19  two softmax groups (key blocks j = g, g + 2, ..) of eight warps: thread = (query row, 32-column half of
-//               the tile); the backward has no row reductions, so the halves never talk to each other
-//   shared: Q, dO of the sweep (64 KB), K_j / V_j 2 x 2 x 8 KB, and per group TWO P and TWO dS tiles (128 KB), so that a
-//   tile's stores never wait for the MMAs that read the previous one.
+//   loop order: 64-key block outer, the eight query tiles inner.  TMEM (448 columns): S 64, dP 64, dK_j 32, dV_j 32 and
+//   dQ of ALL eight query tiles (256), which accumulates across the sixteen key blocks and is drained once at the end.
+//   There is ONE S / dP buffer: a softmax thread pulls its 32 + 32 values into registers and releases the buffer at
+//   once, so the MMAs of tile n + 1 run while tile n is in the exponentials; the two softmax groups take alternate tiles
+//   (ping-pong through one buffer), each with its own P / dS tile pair in shared memory.
+//   warp 0      TMEM allocator, then TMA producer (Q, dO resident: 128 KB; K_j, V_j double-buffered)
+//   warps 1-3   three tcgen05.mma issuing threads (S + dP + dQ | dV | dK: 8 of the tile's 24 MMAs each)
+//   warps 4-19  two softmax groups of eight warps: thread = (query row, 32-column half of the tile); the backward has no
+//               row reductions, so the halves never talk to each other.  Group 1 (which owns the last tile of a block)
+//               drains dK_j / dV_j.
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int kFusedThreads = 128 + 2 * 256;
-constexpr int kSweepBytes = 4 * kQTile;  // [512][32] bf16
-constexpr int kFusedSmem = 2 * kSweepBytes + 2 * (4 * kKvBlk) + 2 * 2 * 2 * kPTile + 1024 + 1024;
-constexpr size_t kDkvSlotBytes = (size_t)16 * 64 * 64 * sizeof(float);  // per SM: 16 key blocks x 64 keys x (dK 32 | dV 32)
+constexpr int kFusedSmem = 2 * kHeadBytes + 2 * (2 * kKvBlk) + 2 * 2 * kPTile + 1024 + 1024;
 
-struct FusedGroupBars {
-  uint64_t kv_full[2], kv_empty[2];  // K_j / V_j double buffer
-  uint64_t s_full, s_empty;          // S and dP written / drained (8 warps)
-  uint64_t p_full[2], p_empty[2];    // P and dS tiles written (8 warps) / consumed by dV, dK, dQ
-  uint64_t o_full, o_empty;          // dK_j, dV_j complete / drained (8 warps)
-};
 struct FusedBars {
-  uint64_t q_full;             // Q, dO of the sweep landed
-  uint64_t dq_full, dq_ready;  // every MMA of the sweep complete (both issuers) / dQ accumulators zeroed (16 warps)
-  FusedGroupBars wg[2];
+  uint64_t res_full;                 // Q, dO landed
+  uint64_t kv_full[2], kv_empty[2];  // K_j / V_j double buffer
+  uint64_t s_full[2], s_empty;       // S and dP written, per group: a barrier two groups took turns on would let the
+                                     // faster one pass on the other's phase / pulled into registers (8 warps)
+  uint64_t p_full[2], p_empty[2];    // per group: P and dS tiles written (8 warps) / consumed by dV, dK, dQ
+  uint64_t o_full, o_empty;          // dK_j, dV_j complete / drained (8 warps)
+  uint64_t dq_full;                  // every MMA complete
   uint32_t tmem_slot;
 };
 
+// one lane of a converged warp (the MMA-issuing warps run their loops warp-wide so that tile indices, shared-memory
+// addresses and descriptors stay in uniform registers; only the tcgen05 instructions themselves are predicated)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
-// one 16-key quarter of a thread's row: P = exp2(S c - L), dS = P o (keep o dP - D'), Pd = keep o P (bf16 pairs);
-// `word` carries the keep bits of the thread's 32 keys, element e at bit 8 (e & 3) + e / 4
+// four keys of a thread's row: P = exp2(S c - L), dS = P o (keep o dP - D'), Pd = keep o P (bf16 pairs).  x8: the keep
+// word shifted so that the sign bit of byte c is the decision of key c
 template <int DROP>
-__device__ __forceinline__ void bwd_quarter(const uint32_t (&rs)[16], const uint32_t (&rd)[16], float L, float Dp,
-                                            uint32_t word, int qt, uint32_t (&ds)[8], uint32_t (&pd)[8]) {
-  const uint64_t c2 = f2_pack(kScaleLog2, kScaleLog2), nl2 = f2_pack(-L, -L), nd2 = f2_pack(-Dp, -Dp);
+__device__ __forceinline__ void bwd_four(const uint32_t* rs, const uint32_t* rd, uint64_t c2, uint64_t nl2, uint64_t nd2,
+                                         uint32_t x8, uint32_t* ds, uint32_t* pd) {
+  float x[4], p[4];
+  f2_unpack(f2_fma(f2_pack(__uint_as_float(rs[0]), __uint_as_float(rs[1])), c2, nl2), x[0], x[1]);
+  f2_unpack(f2_fma(f2_pack(__uint_as_float(rs[2]), __uint_as_float(rs[3])), c2, nl2), x[2], x[3]);
 #pragma unroll
-  for (int ii = 0; ii < 4; ++ii) {
-    float x[4], p[4];
-    f2_unpack(f2_fma(f2_pack(__uint_as_float(rs[4 * ii]), __uint_as_float(rs[4 * ii + 1])), c2, nl2), x[0], x[1]);
-    f2_unpack(f2_fma(f2_pack(__uint_as_float(rs[4 * ii + 2]), __uint_as_float(rs[4 * ii + 3])), c2, nl2), x[2], x[3]);
-#pragma unroll
-    for (int c = 0; c < 4; ++c) p[c] = ex2(x[c]);
-    uint32_t e[4] = {rd[4 * ii], rd[4 * ii + 1], rd[4 * ii + 2], rd[4 * ii + 3]};
-    uint32_t pp0 = pack_bf16x2(p[0], p[1]), pp1 = pack_bf16x2(p[2], p[3]);
-    if (DROP) {
-      const uint32_t x8 = word << (7 - (4 * qt + ii));  // bit 8 c + i -> sign of byte c
-      e[0] &= prmt(x8, 0x8888u);
-      e[1] &= prmt(x8, 0x9999u);
-      e[2] &= prmt(x8, 0xAAAAu);
-      e[3] &= prmt(x8, 0xBBBBu);
-      pp0 &= prmt(x8, 0x9988u);
-      pp1 &= prmt(x8, 0xBBAAu);
-    }
-    float t0, t1, t2, t3;
-    f2_unpack(f2_mul(f2_pack(p[0], p[1]), f2_add(f2_pack(__uint_as_float(e[0]), __uint_as_float(e[1])), nd2)), t0, t1);
-    f2_unpack(f2_mul(f2_pack(p[2], p[3]), f2_add(f2_pack(__uint_as_float(e[2]), __uint_as_float(e[3])), nd2)), t2, t3);
-    ds[2 * ii] = pack_bf16x2(t0, t1);
-    ds[2 * ii + 1] = pack_bf16x2(t2, t3);
-    pd[2 * ii] = pp0;
-    pd[2 * ii + 1] = pp1;
+  for (int c = 0; c < 4; ++c) p[c] = ex2(x[c]);
+  uint32_t e[4] = {rd[0], rd[1], rd[2], rd[3]};
+  uint32_t pp0 = pack_bf16x2(p[0], p[1]), pp1 = pack_bf16x2(p[2], p[3]);
+  if (DROP) {
+    e[0] &= prmt(x8, 0x8888u);
+    e[1] &= prmt(x8, 0x9999u);
+    e[2] &= prmt(x8, 0xAAAAu);
+    e[3] &= prmt(x8, 0xBBBBu);
+    pp0 &= prmt(x8, 0x9988u);
+    pp1 &= prmt(x8, 0xBBAAu);
   }
+  float t0, t1, t2, t3;
+  f2_unpack(f2_mul(f2_pack(p[0], p[1]), f2_add(f2_pack(__uint_as_float(e[0]), __uint_as_float(e[1])), nd2)), t0, t1);
+  f2_unpack(f2_mul(f2_pack(p[2], p[3]), f2_add(f2_pack(__uint_as_float(e[2]), __uint_as_float(e[3])), nd2)), t2, t3);
+  ds[0] = pack_bf16x2(t0, t1);
+  ds[1] = pack_bf16x2(t2, t3);
+  pd[0] = pp0;
+  pd[1] = pp1;
 }
 
 template <int DROP>
-__global__ void __launch_bounds__(kFusedThreads, 1)
+__global__ void __launch_bounds__(kFusedThreads, 1)  // 20 warps, five per scheduler -> 96 registers
 attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap mQkv, const __grid_constant__ CUtensorMap mQkv64,
                       const __grid_constant__ CUtensorMap mDo, const bf16* __restrict__ o_in, const bf16* __restrict__ d_o,
-                      const float* __restrict__ lse2, float* __restrict__ dsum, bf16* __restrict__ dqkv,
-                      float* __restrict__ scratch, int nslots, uint32_t key, uint32_t th15, float inv_keep,
+                      const float* __restrict__ lse2, bf16* __restrict__ dqkv, uint32_t key, uint32_t th15, float inv_keep,
                       const uint32_t* __restrict__ drop_bits) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint8_t* sQ = smem;                        // [4 tiles]
-  uint8_t* sDo = smem + kSweepBytes;         // [4 tiles]
-  uint8_t* sKv = smem + 2 * kSweepBytes;     // [2 groups][2 buffers][K_j | V_j]
-  uint8_t* sP = sKv + 2 * 4 * kKvBlk;        // [2 groups][2 buffers]
-  uint8_t* sDs = sP + 2 * 2 * kPTile;        // [2 groups][2 buffers]
-  FusedBars* bars = reinterpret_cast<FusedBars*>(sDs + 2 * 2 * kPTile);
+  uint8_t* sQ = smem;                        // [8 tiles]
+  uint8_t* sDo = smem + kHeadBytes;          // [8 tiles]
+  uint8_t* sKv = smem + 2 * kHeadBytes;      // [2 buffers][K_j | V_j]
+  uint8_t* sP = sKv + 2 * 2 * kKvBlk;        // [2 groups]
+  uint8_t* sDs = sP + 2 * kPTile;            // [2 groups]
+  FusedBars* bars = reinterpret_cast<FusedBars*>(sDs + 2 * kPTile);
   const int bh = blockIdx.x, b = bh >> 2, h = bh & 3;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 1 && lane == 0) {
     tma_prefetch_desc(&mQkv);
     tma_prefetch_desc(&mQkv64);
     tma_prefetch_desc(&mDo);
-  }
-  if (warp == 1 && lane == 0) {
-    mbar_init(&bars->q_full, 1);
-    mbar_init(&bars->dq_full, 2);
-    mbar_init(&bars->dq_ready, 16);
-    for (int g = 0; g < 2; ++g) {
-      FusedGroupBars& w = bars->wg[g];
-      for (int i = 0; i < 2; ++i) {
-        mbar_init(&w.kv_full[i], 1);
-        mbar_init(&w.kv_empty[i], 1);
-        mbar_init(&w.p_full[i], 8);
-        mbar_init(&w.p_empty[i], 1);
-      }
-      mbar_init(&w.s_full, 1);
-      mbar_init(&w.s_empty, 8);
-      mbar_init(&w.o_full, 1);
-      mbar_init(&w.o_empty, 8);
+    mbar_init(&bars->res_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars->kv_full[i], 1);
+      mbar_init(&bars->kv_empty[i], 1);
+      mbar_init(&bars->p_full[i], 8);
+      mbar_init(&bars->p_empty[i], 3);  // the three issuing threads
     }
+    mbar_init(&bars->s_full[0], 1);
+    mbar_init(&bars->s_full[1], 1);
+    mbar_init(&bars->s_empty, 8);
+    mbar_init(&bars->o_full, 2);  // dV and dK issuers
+    mbar_init(&bars->o_empty, 8);
+    mbar_init(&bars->dq_full, 1);
     fence_mbar_init();
   }
-  if (warp == 2) {
+  if (warp == 0) {
     tmem_alloc(&bars->tmem_slot, 512);
     tmem_relinquish();
   }
@@ -1118,226 +1108,194 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap mQkv, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = bars->tmem_slot;
-  // tile n of a group = (sweep, key-block round t = 0..15 over both sweeps, query tile i): n = 4 t + i, t = 8 sweep + jt,
-  // key block j = g + 2 jt
+  // tile n = 8 jt + i: key block jt (64 keys), query tile i; softmax group n & 1; S / dP at TMEM columns 0 / 64, dK 128,
+  // dV 160, dQ_i 192 + 32 i
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int t = 0; t < 16; ++t) {
-        const int sw = t >> 3, jt = t & 7, kb = t & 1;
-        for (int g = 0; g < 2; ++g) {
-          FusedGroupBars& w = bars->wg[g];
-          const int j = g + 2 * jt;
-          mbar_wait_parked(&w.kv_empty[kb], ((t >> 1) & 1) ^ 1);
-          mbar_arrive_expect_tx(&w.kv_full[kb], 2 * kKvBlk);
-          uint8_t* dst = sKv + (g * 2 + kb) * 2 * kKvBlk;
-          tma_load_2d(dst, &mQkv64, &w.kv_full[kb], 128 + h * 32, b * kS + j * 64);
-          tma_load_2d(dst + kKvBlk, &mQkv64, &w.kv_full[kb], 256 + h * 32, b * kS + j * 64);
-        }
-        if (jt == 0) {
-          // the sweep's Q and dO: the second sweep overwrites the first, so every MMA of the first must be complete
-          if (sw == 1) mbar_wait_parked(&bars->dq_full, 0);
-          mbar_arrive_expect_tx(&bars->q_full, 2 * kSweepBytes);
-          for (int i = 0; i < 4; ++i) {
-            tma_load_2d(sQ + i * kQTile, &mQkv, &bars->q_full, h * 32, b * kS + sw * 512 + i * 128);
-            tma_load_2d(sDo + i * kQTile, &mDo, &bars->q_full, h * 32, b * kS + sw * 512 + i * 128);
-          }
-        }
+      mbar_arrive_expect_tx(&bars->res_full, 2 * kHeadBytes);
+      for (int i = 0; i < 8; ++i) {
+        tma_load_2d(sQ + i * kQTile, &mQkv, &bars->res_full, h * 32, b * kS + i * 128);
+        tma_load_2d(sDo + i * kQTile, &mDo, &bars->res_full, h * 32, b * kS + i * 128);
+      }
+      for (int jt = 0; jt < 16; ++jt) {
+        const int kb = jt & 1;
+        mbar_wait_parked(&bars->kv_empty[kb], ((jt >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&bars->kv_full[kb], 2 * kKvBlk);
+        uint8_t* dst = sKv + kb * 2 * kKvBlk;
+        tma_load_2d(dst, &mQkv64, &bars->kv_full[kb], 128 + h * 32, b * kS + jt * 64);
+        tma_load_2d(dst + kKvBlk, &mQkv64, &bars->kv_full[kb], 256 + h * 32, b * kS + jt * 64);
       }
     }
-  } else if (warp == 1 || warp == 3) {
-    if (lane == 0) {
-      // one issuing thread per group.  Its events alternate strictly - S drained (tile n) -> issue S / dP of tile n + 1;
-      // P / dS written (tile n) -> issue the three products of tile n - so blocking waits in program order never sit on
-      // the wrong barrier.  The dQ accumulators receive products from BOTH threads: they are zeroed by the softmax warps
-      // and every dQ MMA accumulates, so the order in which the tensor pipe takes the two streams does not matter.
-      const int g = warp >> 1;
-      FusedGroupBars& w = bars->wg[g];
-      const uint32_t tS = tmem + g * 192, tDp = tS + 64, tDk = tS + 128, tDv = tS + 160;
-      const uint32_t aQ = smem_u32(sQ), aDo = smem_u32(sDo);
-      auto issue_s = [&](int n) {
-        const int t = n >> 2, i = n & 3, kb = t & 1;
-        if ((n & 31) == 0) mbar_wait_parked(&bars->q_full, t >> 3);
-        if (i == 0) mbar_wait_parked(&w.kv_full[kb], (t >> 1) & 1);
-        mbar_wait_parked(&w.s_empty, (n & 1) ^ 1);
-        const uint32_t aKj = smem_u32(sKv + (g * 2 + kb) * 2 * kKvBlk), aVj = aKj + kKvBlk;
-        tc_fence_after();
+  } else if (warp == 1) {
+    // issuing warp 1 of 3: S = Q_i K_j^T, dP = dO_i V_j^T of tile n + 1 and dQ_i += dS K_j of tile n (8 MMAs per tile).
+    // One thread issuing all 24 MMAs of a tile was the bottleneck of this kernel (~2000 cycles of dependent integer work
+    // per tile); every accumulator has exactly one issuing warp, so no ordering between the three is needed.
+    const uint32_t tS = tmem, tDp = tmem + 64, tDq = tmem + 192;
+    const uint32_t aQ = smem_u32(sQ), aDo = smem_u32(sDo), aKv = smem_u32(sKv), aDs0 = smem_u32(sDs);
+    mbar_wait_parked(&bars->res_full, 0);
+    auto issue_s = [&](int n) {
+      const int jt = n >> 3, i = n & 7, kb = jt & 1;
+      if (i == 0) mbar_wait_parked(&bars->kv_full[kb], (jt >> 1) & 1);
+      mbar_wait_parked(&bars->s_empty, (n & 1) ^ 1);  // tile n - 1 has been pulled into registers
+      const uint32_t aKj = aKv + kb * 2 * kKvBlk, aVj = aKj + kKvBlk;
+      tc_fence_after();
+      if (elect_one()) {
         mma_qk(tS, aQ + i * kQTile, aKj);
         mma_qk(tDp, aDo + i * kQTile, aVj);
-        tc_commit(&w.s_full);
-      };
-      issue_s(0);
-      for (int n = 0; n < 64; ++n) {
-        const int t = n >> 2, i = n & 3, kb = t & 1, buf = n & 1;
-        // S / dP of the next tile first (its inputs are ready as soon as the softmax warps have pulled tile n into
-        // registers), except across the sweep boundary, where Q / dO are reloaded only after this sweep's last product
-        if (n + 1 < 64 && ((n + 1) & 31) != 0) issue_s(n + 1);
-        mbar_wait_parked(&w.p_full[buf], (n >> 1) & 1);
-        if (i == 0) mbar_wait_parked(&w.o_empty, (t & 1) ^ 1);          // dK, dV of the previous block drained
-        if ((n & 31) == 0) mbar_wait_parked(&bars->dq_ready, n >> 5);   // dQ accumulators zeroed for this sweep
-        const uint32_t aKj = smem_u32(sKv + (g * 2 + kb) * 2 * kKvBlk);
-        const uint32_t aP = smem_u32(sP + (g * 2 + buf) * kPTile), aDs = smem_u32(sDs + (g * 2 + buf) * kPTile);
-        tc_fence_after();
-        mma_ptdo(tDv, aP, aDo + i * kQTile, i != 0);
-        mma_ptdo(tDk, aDs, aQ + i * kQTile, i != 0);
-        mma_pv(tmem + 384 + 32 * i, aDs, aKj, true);
-        tc_commit(&w.p_empty[buf]);
-        if (i == 3) {
-          tc_commit(&w.o_full);
-          tc_commit(&w.kv_empty[kb]);
-        }
-        if ((n & 31) == 31) {
-          tc_commit(&bars->dq_full);  // this group's last product of the sweep (the barrier counts both groups)
-          if (n + 1 < 64) issue_s(n + 1);
-        }
+        tc_commit(&bars->s_full[n & 1]);
       }
+      __syncwarp();
+    };
+    issue_s(0);
+    for (int n = 0; n < 128; ++n) {
+      const int jt = n >> 3, i = n & 7, kb = jt & 1, g = n & 1;
+      if (n + 1 < 128) issue_s(n + 1);
+      mbar_wait_parked(&bars->p_full[g], (n >> 1) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        mma_pv(tDq + 32 * i, aDs0 + g * kPTile, aKv + kb * 2 * kKvBlk, jt != 0);
+        tc_commit(&bars->p_empty[g]);
+        if (i == 7) tc_commit(&bars->kv_empty[kb]);
+        if (n == 127) tc_commit(&bars->dq_full);
+      }
+      __syncwarp();
     }
-  } else if (warp >= 4) {
-    const int g = (warp - 4) >> 3, wi = (warp - 4) & 7, quad = wi & 3, half = wi >> 2, row = quad * 32 + lane;
-    FusedGroupBars& w = bars->wg[g];
-    const uint32_t tS = tmem + ((uint32_t)(quad * 32) << 16) + g * 192 + 32 * half, tDp = tS + 64;
-    const uint32_t tDkv = tmem + ((uint32_t)(quad * 32) << 16) + g * 192 + 128 + 32 * half;  // half 0 drains dK, half 1 dV
+  } else if (warp == 2 || warp == 3) {
+    // issuing warps 2, 3: dV_j += Pd^T dO_i (warp 2) / dK_j += dS^T Q_i (warp 3), 8 MMAs per tile each
+    const bool is_v = warp == 2;
+    const uint32_t tD = tmem + (is_v ? 160 : 128);
+    const uint32_t aB = smem_u32(is_v ? sDo : sQ);
+    const uint32_t aA0 = smem_u32(is_v ? sP : sDs);
+    mbar_wait_parked(&bars->res_full, 0);
+    for (int n = 0; n < 128; ++n) {
+      const int jt = n >> 3, i = n & 7, g = n & 1;
+      mbar_wait_parked(&bars->p_full[g], (n >> 1) & 1);
+      if (i == 0) mbar_wait_parked(&bars->o_empty, (jt & 1) ^ 1);  // dK, dV of the previous block drained
+      tc_fence_after();
+      if (elect_one()) {
+        mma_ptdo(tD, aA0 + g * kPTile, aB + i * kQTile, i != 0);
+        tc_commit(&bars->p_empty[g]);
+        if (i == 7) tc_commit(&bars->o_full);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int g = (warp - 4) >> 3, half = ((warp - 4) >> 2) & 1, quad = warp & 3, row = quad * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    const uint32_t tS = tmem + lane_base + 32 * half, tDp = tS + 64;
+    const uint32_t tDkv = tmem + lane_base + 128 + 32 * half;  // half 0 drains dK, half 1 dV
     const DropKeys dk = drop_keys(key);
     const float keep_prob = 1.f / inv_keep;
-    uint32_t smid;
-    asm("mov.u32 %0, %%smid;" : "=r"(smid));
-    if (smid >= (uint32_t)nslots) {
-      printf("focr: attention backward scratch has %d slots, SM id %u\n", nslots, smid);
-      __trap();
+    const uint32_t aP = smem_u32(sP + g * kPTile), aDs = smem_u32(sDs + g * kPTile);
+    const uint64_t c2 = f2_pack(kScaleLog2, kScaleLog2);
+    // this thread's four query rows (tiles i = g, g + 2, g + 4, g + 6): L and D' = keep_prob * rowsum(dO o O)
+    float Lr[4], Dr[4];
+#pragma unroll
+    for (int ii = 0; ii < 4; ++ii) {
+      const int q = (g + 2 * ii) * 128 + row;
+      const long tk = (long)b * kS + q;
+      const uint4* po = reinterpret_cast<const uint4*>(o_in + tk * kLdO + h * 32);
+      const uint4* pdo = reinterpret_cast<const uint4*>(d_o + tk * kLdO + h * 32);
+      float D = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const uint4 a = po[c], d = pdo[c];
+        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, dw[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 x = unpack_bf16x2(aw[e]), y = unpack_bf16x2(dw[e]);
+          D = fmaf(x.x, y.x, D);
+          D = fmaf(x.y, y.y, D);
+        }
+      }
+      Dr[ii] = D * keep_prob;
+      Lr[ii] = lse2[(long)bh * kS + q];
     }
-    float* slot = scratch + (size_t)smid * (kDkvSlotBytes / sizeof(float));
-    const uint32_t aP0 = smem_u32(sP + g * 2 * kPTile), aDs0 = smem_u32(sDs + g * 2 * kPTile);
-    // this thread's share of the dQ accumulators: query tiles 2g, 2g + 1 of the sweep, 16 of the 32 columns
-    const uint32_t tDq = tmem + ((uint32_t)(quad * 32) << 16) + 384 + 64 * g + 16 * half;
-    auto zero_dq = [&]() {
-      const uint32_t z[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-      tmem_st_32x32b_x16(tDq, z);
-      tmem_st_32x32b_x16(tDq + 32, z);
-      tmem_st_wait();
-      warp_release_tmem(&bars->dq_ready, lane);
-    };
-    zero_dq();
-    for (int sw = 0; sw < 2; ++sw) {
-      // D = rowsum(dO o O) of this thread's four query rows of the sweep (every half / group computes its own copy)
-      for (int i = 0; i < 4; ++i) {
-        const int q = sw * 512 + i * 128 + row;
-        const long tk = (long)b * kS + q;
-        const uint4* po = reinterpret_cast<const uint4*>(o_in + tk * kLdO + h * 32);
-        const uint4* pd = reinterpret_cast<const uint4*>(d_o + tk * kLdO + h * 32);
-        float D = 0.f;
+    uint32_t wn = 0xFFFFFFFFu;  // keep bits, loaded one tile ahead
+    if (DROP == 2) wn = __ldg(drop_bits + ((size_t)bh * 32 + half) * kS + g * 128 + row);
+    for (int jt = 0; jt < 16; ++jt) {
+#pragma unroll
+      for (int ii = 0; ii < 4; ++ii) {
+        const int i = g + 2 * ii, n = 8 * jt + i, m = n >> 1;  // m: this group's tile count
+        const int q = i * 128 + row;
+        uint32_t word = wn;
+        if (DROP == 2 && (ii < 3 || jt < 15)) {
+          const int qn = (g + 2 * ((ii + 1) & 3)) * 128 + row, jn = ii < 3 ? jt : jt + 1;
+          wn = __ldg(drop_bits + ((size_t)bh * 32 + jn * 2 + half) * kS + qn);
+        }
+        if (DROP == 1) word = keep_word((uint32_t)(bh * kS + q), (uint32_t)(2 * jt + half), dk, th15);
+        mbar_wait(&bars->s_full[g], m & 1);
+        tc_fence_after();
+        uint32_t rs[32], rd[32];
+        tmem_ld_32x32b_x32(tS, rs);
+        tmem_ld_32x32b_x32(tDp, rd);
+        tmem_ld_wait();
+        warp_release_tmem(&bars->s_empty, lane);  // the buffer is free for tile n + 1 while this tile is in registers
+        const uint64_t nl2 = f2_pack(-Lr[ii], -Lr[ii]), nd2 = f2_pack(-Dr[ii], -Dr[ii]);
+        uint32_t ds[16], pd[16];
+#pragma unroll
+        for (int k4 = 0; k4 < 8; ++k4)
+          bwd_four<DROP>(rs + 4 * k4, rd + 4 * k4, c2, nl2, nd2, word << (7 - k4), ds + 2 * k4, pd + 2 * k4);
+        mbar_wait(&bars->p_empty[g], (m & 1) ^ 1);  // the products of this group's previous tile have read the tiles
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          const uint4 a = po[c], d = pd[c];
-          const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, dw[4] = {d.x, d.y, d.z, d.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float2 x = unpack_bf16x2(aw[e]), y = unpack_bf16x2(dw[e]);
-            D = fmaf(x.x, y.x, D);
-            D = fmaf(x.y, y.y, D);
-          }
+          const uint32_t off = p_off(row, 4 * half + c);
+          st_shared_v4(aDs + off, ds[4 * c], ds[4 * c + 1], ds[4 * c + 2], ds[4 * c + 3]);
+          st_shared_v4(aP + off, pd[4 * c], pd[4 * c + 1], pd[4 * c + 2], pd[4 * c + 3]);
         }
-        dsum[(long)bh * kS + q] = D;  // identical value from all four threads that own this row
+        warp_publish_smem(&bars->p_full[g], lane);
       }
-      // row scalars and keep bits are loaded one tile ahead of their use
-      float Ln = lse2[(long)bh * kS + sw * 512 + row], Dn = dsum[(long)bh * kS + sw * 512 + row];
-      uint32_t wn = 0xFFFFFFFFu;
-      if (DROP == 2) wn = __ldg(drop_bits + ((size_t)bh * 32 + g * 2 + half) * kS + sw * 512 + row);
-      for (int jt = 0; jt < 8; ++jt) {
-        const int t = sw * 8 + jt, j = g + 2 * jt;
-        for (int i = 0; i < 4; ++i) {
-          const int n = 4 * t + i, buf = n & 1;
-          const int q = sw * 512 + i * 128 + row;
-          const float L = Ln, Dp = Dn * keep_prob;
-          uint32_t word = wn;
-          if (i < 3 || jt < 7) {
-            const int qn = sw * 512 + ((i + 1) & 3) * 128 + row, jn = (i < 3) ? j : j + 2;
-            Ln = lse2[(long)bh * kS + qn];
-            Dn = dsum[(long)bh * kS + qn];
-            if (DROP == 2) wn = __ldg(drop_bits + ((size_t)bh * 32 + jn * 2 + half) * kS + qn);
-          }
-          if (DROP == 1) word = keep_word(( uint32_t)(bh * kS + q), (uint32_t)(2 * j + half), dk, th15);
-          mbar_wait(&w.s_full, n & 1);
-          tc_fence_after();
-          uint32_t ds[2][8], pd[2][8];
-#pragma unroll
-          for (int qt = 0; qt < 2; ++qt) {
-            uint32_t rs[16], rd[16];
-            tmem_ld_32x32b_x16(tS + 16 * qt, rs);
-            tmem_ld_32x32b_x16(tDp + 16 * qt, rd);
-            tmem_ld_wait();
-            if (qt == 1) warp_release_tmem(&w.s_empty, lane);
-            bwd_quarter<DROP>(rs, rd, L, Dp, word, qt, ds[qt], pd[qt]);
-          }
-          mbar_wait(&w.p_empty[buf], ((n >> 1) & 1) ^ 1);  // the products of tile n - 2 have read this buffer
-#pragma unroll
-          for (int qt = 0; qt < 2; ++qt)
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-              const uint32_t off = buf * kPTile + p_off(row, 4 * half + 2 * qt + c);
-              st_shared_v4(aDs0 + off, ds[qt][4 * c], ds[qt][4 * c + 1], ds[qt][4 * c + 2], ds[qt][4 * c + 3]);
-              st_shared_v4(aP0 + off, pd[qt][4 * c], pd[qt][4 * c + 1], pd[qt][4 * c + 2], pd[qt][4 * c + 3]);
-            }
-          warp_publish_smem(&w.p_full[buf], lane);
-        }
+      if (g == 1) {
         // ---- dK_j (half 0) / dV_j (half 1): M = 64 accumulators, key row quad*16 + lane on TMEM lane quad*32 + lane ----
-        mbar_wait(&w.o_full, t & 1);
+        mbar_wait(&bars->o_full, jt & 1);
         tc_fence_after();
         uint32_t r[32];
         tmem_ld_32x32b_x32(tDkv, r);
         tmem_ld_wait();
-        warp_release_tmem(&w.o_empty, lane);
+        warp_release_tmem(&bars->o_empty, lane);
         if (lane < 16) {
-          const int kr = quad * 16 + lane;
-          float4* part = reinterpret_cast<float4*>(slot + ((size_t)(j * 64 + kr) * 64 + 32 * half));
-          if (sw == 0) {
+          const float sc = half == 0 ? kScale * inv_keep : inv_keep;
+          uint4* dst = reinterpret_cast<uint4*>(dqkv + ((long)b * kS + jt * 64 + quad * 16 + lane) * kLdQkv + 128 + 128 * half +
+                                                h * 32);
 #pragma unroll
-            for (int c = 0; c < 8; ++c)
-              part[c] = make_float4(__uint_as_float(r[4 * c]), __uint_as_float(r[4 * c + 1]), __uint_as_float(r[4 * c + 2]),
-                                    __uint_as_float(r[4 * c + 3]));
-          } else {
-            const float sc = half == 0 ? kScale * inv_keep : inv_keep;
-            uint4* dst = reinterpret_cast<uint4*>(dqkv + ((long)b * kS + j * 64 + kr) * kLdQkv + 128 + 128 * half + h * 32);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              const float4 a = part[2 * c], bb = part[2 * c + 1];
-              uint4 o;
-              o.x = pack_bf16x2((__uint_as_float(r[8 * c + 0]) + a.x) * sc, (__uint_as_float(r[8 * c + 1]) + a.y) * sc);
-              o.y = pack_bf16x2((__uint_as_float(r[8 * c + 2]) + a.z) * sc, (__uint_as_float(r[8 * c + 3]) + a.w) * sc);
-              o.z = pack_bf16x2((__uint_as_float(r[8 * c + 4]) + bb.x) * sc, (__uint_as_float(r[8 * c + 5]) + bb.y) * sc);
-              o.w = pack_bf16x2((__uint_as_float(r[8 * c + 6]) + bb.z) * sc, (__uint_as_float(r[8 * c + 7]) + bb.w) * sc);
-              dst[c] = o;
-            }
+          for (int c = 0; c < 4; ++c) {
+            uint4 o;
+            o.x = pack_bf16x2(__uint_as_float(r[8 * c + 0]) * sc, __uint_as_float(r[8 * c + 1]) * sc);
+            o.y = pack_bf16x2(__uint_as_float(r[8 * c + 2]) * sc, __uint_as_float(r[8 * c + 3]) * sc);
+            o.z = pack_bf16x2(__uint_as_float(r[8 * c + 4]) * sc, __uint_as_float(r[8 * c + 5]) * sc);
+            o.w = pack_bf16x2(__uint_as_float(r[8 * c + 6]) * sc, __uint_as_float(r[8 * c + 7]) * sc);
+            dst[c] = o;
           }
         }
       }
-      // ---- dQ of the sweep: group g drains query tiles 2g, 2g + 1; each half its 16 of the 32 columns ----
-      mbar_wait(&bars->dq_full, sw);
-      tc_fence_after();
+    }
+    // ---- dQ: group g drains query tiles g, g + 2, g + 4, g + 6; each half its 16 of the 32 columns ----
+    mbar_wait(&bars->dq_full, 0);
+    tc_fence_after();
 #pragma unroll
-      for (int ii = 0; ii < 2; ++ii) {
-        const int i = 2 * g + ii;
-        uint32_t r[16];
-        tmem_ld_32x32b_x16(tDq + 32 * ii, r);
-        tmem_ld_wait();
-        const float sc = kScale * inv_keep;
-        uint4* dst = reinterpret_cast<uint4*>(dqkv + ((long)b * kS + sw * 512 + i * 128 + row) * kLdQkv + h * 32 + 16 * half);
+    for (int ii = 0; ii < 4; ++ii) {
+      const int i = g + 2 * ii;
+      uint32_t r[16];
+      tmem_ld_32x32b_x16(tmem + lane_base + 192 + 32 * i + 16 * half, r);
+      tmem_ld_wait();
+      const float sc = kScale * inv_keep;
+      uint4* dst = reinterpret_cast<uint4*>(dqkv + ((long)b * kS + i * 128 + row) * kLdQkv + h * 32 + 16 * half);
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint4 o;
-          o.x = pack_bf16x2(__uint_as_float(r[8 * c + 0]) * sc, __uint_as_float(r[8 * c + 1]) * sc);
-          o.y = pack_bf16x2(__uint_as_float(r[8 * c + 2]) * sc, __uint_as_float(r[8 * c + 3]) * sc);
-          o.z = pack_bf16x2(__uint_as_float(r[8 * c + 4]) * sc, __uint_as_float(r[8 * c + 5]) * sc);
-          o.w = pack_bf16x2(__uint_as_float(r[8 * c + 6]) * sc, __uint_as_float(r[8 * c + 7]) * sc);
-          dst[c] = o;
-        }
+      for (int c = 0; c < 2; ++c) {
+        uint4 o;
+        o.x = pack_bf16x2(__uint_as_float(r[8 * c + 0]) * sc, __uint_as_float(r[8 * c + 1]) * sc);
+        o.y = pack_bf16x2(__uint_as_float(r[8 * c + 2]) * sc, __uint_as_float(r[8 * c + 3]) * sc);
+        o.z = pack_bf16x2(__uint_as_float(r[8 * c + 4]) * sc, __uint_as_float(r[8 * c + 5]) * sc);
+        o.w = pack_bf16x2(__uint_as_float(r[8 * c + 6]) * sc, __uint_as_float(r[8 * c + 7]) * sc);
+        dst[c] = o;
       }
-      if (sw == 0) zero_dq();
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
   }
@@ -1461,17 +1419,8 @@ int launch_dq(const CUtensorMap& mq, const CUtensorMap& mdo, const bf16* o, cons
   return FOCR_OK;
 }
 
-// fp32 scratch of the single-pass backward: one 256 KB slot per SM for the first sweep's dK / dV partials
-size_t attn_bwd_scratch_bytes() {
-  int dev = 0, sms = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
-    sms = 160;  // B200: 148 (size query without a device: upper bound)
-  return (size_t)sms * kDkvSlotBytes;
-}
-
-static int attn_backward_fused(const bf16* qkv, const bf16* o, const bf16* d_o, const float* lse2, float* dsum, bf16* dqkv,
-                               int B, uint32_t key, uint32_t thresh16, const uint32_t* drop_bits, void* scratch,
-                               size_t scratch_bytes, cudaStream_t s) {
+static int attn_backward_fused(const bf16* qkv, const bf16* o, const bf16* d_o, const float* lse2, bf16* dqkv, int B,
+                               uint32_t key, uint32_t thresh16, const uint32_t* drop_bits, cudaStream_t s) {
   ProfScope ps("attn_bwd", s);
   static_assert(sizeof(FusedBars) <= 1024, "barrier block");
   static bool init = false;
@@ -1484,7 +1433,6 @@ static int attn_backward_fused(const bf16* qkv, const bf16* o, const bf16* d_o, 
     if (rc) return rc;
     init = true;
   }
-  const int nslots = (int)(scratch_bytes / kDkvSlotBytes);
   CUtensorMap mq, mq64, mdo;
   int rc = focr_make_tmap_2d(&mq, qkv, kLdQkv, (unsigned long long)B * kS, kLdQkv * 2, 32, 128, 64);
   if (rc) return rc;
@@ -1494,36 +1442,29 @@ static int attn_backward_fused(const bf16* qkv, const bf16* o, const bf16* d_o, 
   if (rc) return rc;
   const AttnDrop d = drop_params(thresh16);
   const dim3 grid(B * 4), block(kFusedThreads);
-  float* sc = (float*)scratch;
   if (!thresh16)
-    attn_bwd_fused_kernel<0><<<grid, block, kFusedSmem, s>>>(mq, mq64, mdo, o, d_o, lse2, dsum, dqkv, sc, nslots, key, 0, 1.f,
-                                                             nullptr);
+    attn_bwd_fused_kernel<0><<<grid, block, kFusedSmem, s>>>(mq, mq64, mdo, o, d_o, lse2, dqkv, key, 0, 1.f, nullptr);
   else if (!drop_bits)
-    attn_bwd_fused_kernel<1><<<grid, block, kFusedSmem, s>>>(mq, mq64, mdo, o, d_o, lse2, dsum, dqkv, sc, nslots, key, d.th15,
-                                                             d.inv_keep, nullptr);
+    attn_bwd_fused_kernel<1><<<grid, block, kFusedSmem, s>>>(mq, mq64, mdo, o, d_o, lse2, dqkv, key, d.th15, d.inv_keep,
+                                                             nullptr);
   else
-    attn_bwd_fused_kernel<2><<<grid, block, kFusedSmem, s>>>(mq, mq64, mdo, o, d_o, lse2, dsum, dqkv, sc, nslots, key, d.th15,
-                                                             d.inv_keep, drop_bits);
+    attn_bwd_fused_kernel<2><<<grid, block, kFusedSmem, s>>>(mq, mq64, mdo, o, d_o, lse2, dqkv, key, d.th15, d.inv_keep,
+                                                             drop_bits);
   FOCR_LAUNCH_CHECK();
   return FOCR_OK;
 }
 
-// scratch (attn_bwd_scratch_bytes() bytes, or null): with it the single-pass kernel runs; without it (or with
-// FOCR_ATTN_BWD=2pass in the environment) the two-kernel form (dQ pass, then dK / dV pass)
+// The single-pass kernel is the default; FOCR_ATTN_BWD=2pass in the environment (or focr_attn_set_bwd_two_pass) selects the
+// two-kernel form (dQ pass, then dK / dV pass; `dsum` carries D = rowsum(dO o O) between them).
 int attn_backward(const bf16* qkv, const bf16* o, const bf16* d_o, const float* lse2, float* dsum, bf16* dqkv, int B,
-                  uint32_t key, uint32_t thresh16, const uint32_t* drop_bits, cudaStream_t s, void* scratch,
-                  size_t scratch_bytes) {
+                  uint32_t key, uint32_t thresh16, const uint32_t* drop_bits, cudaStream_t s) {
   FOCR_REQUIRE(B >= 1 && B <= 1024, "attention: B=%d out of range", B);
   static int env_two_pass = -1;
   if (env_two_pass < 0) {
     const char* e = getenv("FOCR_ATTN_BWD");
     env_two_pass = (e != nullptr && strcmp(e, "2pass") == 0) ? 1 : 0;
   }
-  if (scratch != nullptr && !env_two_pass && !g_attn_bwd_two_pass) {
-    FOCR_REQUIRE(scratch_bytes >= attn_bwd_scratch_bytes(), "attention backward: scratch of %zu bytes, need %zu", scratch_bytes,
-                 attn_bwd_scratch_bytes());
-    return attn_backward_fused(qkv, o, d_o, lse2, dsum, dqkv, B, key, thresh16, drop_bits, scratch, scratch_bytes, s);
-  }
+  if (!env_two_pass && !g_attn_bwd_two_pass) return attn_backward_fused(qkv, o, d_o, lse2, dqkv, B, key, thresh16, drop_bits, s);
   static bool init = false;
   if (!init) {
     int rc = set_smem(attn_bwd_dkv_kernel<0>, kDkvSmem);

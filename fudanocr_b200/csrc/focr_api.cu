@@ -244,21 +244,16 @@ int focr_mha_flash_fwd(const void* qkv, void* out, float* lse2, int B, float p_d
   return attn_forward((const bf16*)qkv, (bf16*)out, lse2, B, drop_key(seed, stream_id), th, (uint32_t*)drop_bits,
                       (cudaStream_t)stream);
 }
-// ws: focr_mha_bwd_workspace_bytes(B) bytes = D = rowsum(dO o O) per (b, h, q) + the fp32 dK / dV scratch of the single-pass
-// kernel (one 256 KB slot per SM)
-size_t focr_mha_bwd_workspace_bytes(int B) {
-  return (((size_t)B * 4 * 1024 * sizeof(float) + 255) & ~(size_t)255) + attn_bwd_scratch_bytes();
-}
+// ws: focr_mha_bwd_workspace_bytes(B) bytes (D = rowsum(dO o O) per (b, h, q); only the two-kernel form uses it)
+size_t focr_mha_bwd_workspace_bytes(int B) { return ((size_t)B * 4 * 1024 * sizeof(float) + 255) & ~(size_t)255; }
 int focr_mha_flash_bwd(const void* qkv, const void* out, const void* d_out, const float* lse2, void* ws, size_t ws_bytes,
                        void* dqkv, int B, float p_drop, unsigned seed, unsigned stream_id, const void* drop_bits,
                        void* stream) {
   const uint32_t th = p_drop > 0.f ? (uint32_t)(p_drop * 65536.0 + 0.5) : 0;
   FOCR_REQUIRE(ws != nullptr && ws_bytes >= focr_mha_bwd_workspace_bytes(B), "mha_flash_bwd: workspace of %zu bytes, need %zu",
                ws_bytes, focr_mha_bwd_workspace_bytes(B));
-  const size_t dsum_bytes = ((size_t)B * 4 * 1024 * sizeof(float) + 255) & ~(size_t)255;
   return attn_backward((const bf16*)qkv, (const bf16*)out, (const bf16*)d_out, lse2, (float*)ws, (bf16*)dqkv, B,
-                       drop_key(seed, stream_id), th, (const uint32_t*)drop_bits, (cudaStream_t)stream, (char*)ws + dsum_bytes,
-                       ws_bytes - dsum_bytes);
+                       drop_key(seed, stream_id), th, (const uint32_t*)drop_bits, (cudaStream_t)stream);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -49,10 +49,8 @@ size_t attn_drop_bits_bytes(int B);
 // fresh dropout seed per step (key = drop_key(0, stream) in that case)
 int attn_forward(const bf16* qkv, bf16* out, float* lse2, int B, uint32_t key, uint32_t thresh16, uint32_t* drop_bits,
                  cudaStream_t s, const uint32_t* seed_dev = nullptr);
-size_t attn_bwd_scratch_bytes();
 int attn_backward(const bf16* qkv, const bf16* o, const bf16* d_o, const float* lse2, float* dsum, bf16* dqkv, int B,
-                  uint32_t key, uint32_t thresh16, const uint32_t* drop_bits, cudaStream_t s, void* scratch = nullptr,
-                  size_t scratch_bytes = 0);
+                  uint32_t key, uint32_t thresh16, const uint32_t* drop_bits, cudaStream_t s);
 
 // wgrad.cu
 int linear_wgrad_splits(long T, int N, int K = 128);

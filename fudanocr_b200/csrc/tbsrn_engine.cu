@@ -222,7 +222,6 @@ void layout(Ws& w, int B, int n, void* base, int arch) {
   w.gdxp = w.g384;  // TSRN reuses the (T,384) buffer as two (T,192) halves
   w.gdhid = w.g384 + T * 192;
   w.dsum = b.get<float>((long)B * 4 * 1024);
-  w.attn_scratch = b.get<uint8_t>((long)attn_bwd_scratch_bytes());
   w.dx_tps = b.get<float>((long)B * 3 * 1024);
   w.dctrl = b.get<float>((long)B * 40);
   w.dctrl_b = b.get<bf16>(Bp * 64);
@@ -775,8 +774,7 @@ int backward(const Slots& sl, void* const* prm, void* const* grd, const float* x
     p.out = gC;
     TRY(tok_gemm(gB, 128, T, q.woT, 128, p, s));
     TRY(lin_grads(gB, 128, a.o, T, 128, grd, sl.srb(i, S_LOW), sl.srb(i, S_LOB), w, s));
-    TRY(attn_backward(a.qkv, a.o, gC, a.lse, w.dsum, w.g384, B, drop_key(seed, 2 * i), th, a.dropbits, s, w.attn_scratch,
-                      attn_bwd_scratch_bytes()));
+    TRY(attn_backward(a.qkv, a.o, gC, a.lse, w.dsum, w.g384, B, drop_key(seed, 2 * i), th, a.dropbits, s));
     p = gp();
     p.out = gA;
     p.residual = gB;

@@ -121,7 +121,6 @@ struct Ws {
   bf16* g128[4];       // (T,128)
   bf16* g384;          // (T,384)
   float* dsum;         // (B*4*1024)
-  uint8_t* attn_scratch;  // attn_bwd_scratch_bytes(): dK / dV partials of the single-pass attention backward
   float* dx_tps;       // (B,3,16,64)
   float* dctrl;        // (B,40)
   bf16* dctrl_b;       // (Bpad,64)

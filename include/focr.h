@@ -73,8 +73,9 @@ int focr_layernorm_std_bwd(const void* dy, const void* x, const float* a, void* 
  * bytes, or NULL): when given, the forward stores its keep decisions there (1 bit per element) and the backward
  * reads them instead of re-hashing (the fast path); with NULL the backward regenerates the mask from the seed.
  * Bit layout: word [b*4+h][k/32][q] (uint32), key k of the 32-key group at bit (k%32)/4 + 8*(k&3).
- * The backward is ONE kernel (S and dP evaluated once per tile: five GEMMs, one exponential per element); ws
- * (focr_mha_bwd_workspace_bytes(B) bytes, device) holds D = rowsum(dO o O) and a per-SM fp32 scratch for dK / dV partials.
+ * The backward is ONE kernel (S and dP evaluated once per tile: five GEMMs, one exponential per element, dQ of all 1024
+ * queries accumulating in tensor memory); ws (focr_mha_bwd_workspace_bytes(B) bytes, device) is only touched by the two-kernel
+ * form kept for comparison (focr_attn_set_bwd_two_pass).
  * The rate is held to 2^-15 (p = 0.1 -> 3277/32768 = 0.100006); the 1/(1-p) rescale uses that rate, so E[out] is exact.
  * The forward shifts the softmax by a per-row upper bound of the scores (|q_i| max_j |k_j| / sqrt(d_k)) instead of the
  * row maximum and falls back to the exact two-pass route per (batch, head) when that bound is too loose for fp32. */
