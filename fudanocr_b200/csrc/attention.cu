@@ -438,7 +438,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mQkv, const bf16* __restrict
     const DropKeys dk = drop_keys(key);
     // ---- prologue: max |k|^2 over the resident keys, max |q|^2 over the queries of this (batch, head) ----
     float kmax2 = 0.f, qmax2 = 0.f;
-    mbar_wait(&bars->res_full, 0);
+    mbar_wait_parked(&bars->res_full, 0);
     for (int k = (int)threadIdx.x - 128; k < kS; k += NWG * 128) {
       kmax2 = fmaxf(kmax2, row_sumsq(reinterpret_cast<const uint4*>(sK + (k >> 7) * kQTile + (k & 127) * 64)));
       qmax2 = fmaxf(qmax2, row_sumsq(reinterpret_cast<const uint4*>(qkv + ((long)b * kS + k) * kLdQkv + h * 32)));
@@ -450,7 +450,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mQkv, const bf16* __restrict
       atomicMax(&bars->qmax_bits, __float_as_uint(qmax2));
       mbar_arrive(&bars->flag_full);
     }
-    mbar_wait(&bars->flag_full, 0);
+    mbar_wait_parked(&bars->flag_full, 0);
     kmax2 = __uint_as_float(*(volatile uint32_t*)&bars->kmax_bits);
     qmax2 = __uint_as_float(*(volatile uint32_t*)&bars->qmax_bits);
     const bool fast = !force_exact && sqrtf(qmax2 * kmax2) * kScaleLog2 <= kFastBound;
@@ -462,14 +462,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mQkv, const bf16* __restrict
       if (fast) {
         // upper bound of this row's scaled scores: |q_i| max_j |k_j| / sqrt(d_k) (log2 units), less the span; the
         // shift itself is fixed below from the first 32 scores
-        mbar_wait(&w.q_full[it & 1], (it >> 1) & 1);
+        mbar_wait_parked(&w.q_full[it & 1], (it >> 1) & 1);
         const float qn2 = row_sumsq(reinterpret_cast<const uint4*>(sQ + (g * 2 + (it & 1)) * kQTile + row * 64));
         mneg = sqrtf(qn2 * kmax2) * kScaleLog2 - kShiftSpan;
       } else {
         // ---- exact route, pass 1: row maximum ----
         float m = -INFINITY;
         for (int j = 0; j < 16; ++j, ++t) {
-          mbar_wait(&w.s_full[t & 1], (t >> 1) & 1);
+          mbar_wait_parked(&w.s_full[t & 1], (t >> 1) & 1);
           tc_fence_after();
           uint32_t r0[32], r1[32];
           tmem_ld_32x32b_x32(tS + (t & 1) * 64, r0);
@@ -504,7 +504,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mQkv, const bf16* __restrict
       }
       for (int j = 0; j < 16; ++j, ++t) {
         const uint32_t kwd[2] = {kwn[0], kwn[1]};
-        mbar_wait(&w.s_full[t & 1], (t >> 1) & 1);
+        mbar_wait_parked(&w.s_full[t & 1], (t >> 1) & 1);
         tc_fence_after();
         uint32_t r[2][32];
         tmem_ld_32x32b_x32(tS + (t & 1) * 64, r[0]);
@@ -556,7 +556,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mQkv, const bf16* __restrict
         warp_release_tmem(&w.p_full[t & 1], lane);
       }
       // ---- epilogue: O / l ----
-      mbar_wait(&w.o_full, it & 1);
+      mbar_wait_parked(&w.o_full, it & 1);
       tc_fence_after();
       uint32_t r[32];
       tmem_ld_32x32b_x32(tO, r);
@@ -1006,7 +1006,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mQkv, const __grid_const
 //   once, so the MMAs of tile n + 1 run while tile n is in the exponentials; the two softmax groups take alternate tiles
 //   (ping-pong through one buffer), each with its own P / dS tile pair in shared memory.
 //   warp 0      TMEM allocator, then TMA producer (Q, dO resident: 128 KB; K_j, V_j double-buffered)
-//   warps 1-3   three tcgen05.mma issuing threads (S + dP + dQ | dV | dK: 8 of the tile's 24 MMAs each)
+//   warps 1-3   three tcgen05.mma issuing warps (S + dP, running one tile ahead | dV + dQ | dK)
 //   warps 4-19  two softmax groups of eight warps: thread = (query row, 32-column half of the tile); the backward has no
 //               row reductions, so the halves never talk to each other.  Group 1 (which owns the last tile of a block)
 //               drains dK_j / dV_j.
@@ -1088,9 +1088,9 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap mQkv, const __grid_con
     mbar_init(&bars->res_full, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars->kv_full[i], 1);
-      mbar_init(&bars->kv_empty[i], 1);
+      mbar_init(&bars->kv_empty[i], 2);  // S / dP issuer and dQ issuer
       mbar_init(&bars->p_full[i], 8);
-      mbar_init(&bars->p_empty[i], 3);  // the three issuing threads
+      mbar_init(&bars->p_empty[i], 2);   // dV + dQ issuer and dK issuer
     }
     mbar_init(&bars->s_full[0], 1);
     mbar_init(&bars->s_full[1], 1);
@@ -1128,13 +1128,15 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap mQkv, const __grid_con
       }
     }
   } else if (warp == 1) {
-    // issuing warp 1 of 3: S = Q_i K_j^T, dP = dO_i V_j^T of tile n + 1 and dQ_i += dS K_j of tile n (8 MMAs per tile).
-    // One thread issuing all 24 MMAs of a tile was the bottleneck of this kernel (~2000 cycles of dependent integer work
-    // per tile); every accumulator has exactly one issuing warp, so no ordering between the three is needed.
-    const uint32_t tS = tmem, tDp = tmem + 64, tDq = tmem + 192;
-    const uint32_t aQ = smem_u32(sQ), aDo = smem_u32(sDo), aKv = smem_u32(sKv), aDs0 = smem_u32(sDs);
+    // issuing warp 1 of 3: S = Q_i K_j^T, dP = dO_i V_j^T, one tile ahead of the softmax groups.  It waits for nothing but
+    // the S / dP buffer (and K_j / V_j), so the next tile of a group is in tensor memory long before the group has finished
+    // its current one.  (One thread issuing all 24 MMAs of a tile was the bottleneck of the first version of this kernel:
+    // ~2000 cycles of dependent integer work per tile.  Every accumulator has exactly one issuing warp, so no ordering
+    // between the three warps is needed.)
+    const uint32_t tS = tmem, tDp = tmem + 64;
+    const uint32_t aQ = smem_u32(sQ), aDo = smem_u32(sDo), aKv = smem_u32(sKv);
     mbar_wait_parked(&bars->res_full, 0);
-    auto issue_s = [&](int n) {
+    for (int n = 0; n < 128; ++n) {
       const int jt = n >> 3, i = n & 7, kb = jt & 1;
       if (i == 0) mbar_wait_parked(&bars->kv_full[kb], (jt >> 1) & 1);
       mbar_wait_parked(&bars->s_empty, (n & 1) ^ 1);  // tile n - 1 has been pulled into registers
@@ -1144,39 +1146,32 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap mQkv, const __grid_con
         mma_qk(tS, aQ + i * kQTile, aKj);
         mma_qk(tDp, aDo + i * kQTile, aVj);
         tc_commit(&bars->s_full[n & 1]);
-      }
-      __syncwarp();
-    };
-    issue_s(0);
-    for (int n = 0; n < 128; ++n) {
-      const int jt = n >> 3, i = n & 7, kb = jt & 1, g = n & 1;
-      if (n + 1 < 128) issue_s(n + 1);
-      mbar_wait_parked(&bars->p_full[g], (n >> 1) & 1);
-      tc_fence_after();
-      if (elect_one()) {
-        mma_pv(tDq + 32 * i, aDs0 + g * kPTile, aKv + kb * 2 * kKvBlk, jt != 0);
-        tc_commit(&bars->p_empty[g]);
         if (i == 7) tc_commit(&bars->kv_empty[kb]);
-        if (n == 127) tc_commit(&bars->dq_full);
       }
       __syncwarp();
     }
   } else if (warp == 2 || warp == 3) {
-    // issuing warps 2, 3: dV_j += Pd^T dO_i (warp 2) / dK_j += dS^T Q_i (warp 3), 8 MMAs per tile each
+    // issuing warps 2, 3: dV_j += Pd^T dO_i and dQ_i += dS K_j (warp 2, 12 MMAs per tile) / dK_j += dS^T Q_i (warp 3, 8)
     const bool is_v = warp == 2;
-    const uint32_t tD = tmem + (is_v ? 160 : 128);
+    const uint32_t tD = tmem + (is_v ? 160 : 128), tDq = tmem + 192;
     const uint32_t aB = smem_u32(is_v ? sDo : sQ);
     const uint32_t aA0 = smem_u32(is_v ? sP : sDs);
+    const uint32_t aKv = smem_u32(sKv), aDs0 = smem_u32(sDs);
     mbar_wait_parked(&bars->res_full, 0);
     for (int n = 0; n < 128; ++n) {
-      const int jt = n >> 3, i = n & 7, g = n & 1;
+      const int jt = n >> 3, i = n & 7, g = n & 1, kb = jt & 1;
       mbar_wait_parked(&bars->p_full[g], (n >> 1) & 1);
       if (i == 0) mbar_wait_parked(&bars->o_empty, (jt & 1) ^ 1);  // dK, dV of the previous block drained
       tc_fence_after();
       if (elect_one()) {
         mma_ptdo(tD, aA0 + g * kPTile, aB + i * kQTile, i != 0);
+        if (is_v) mma_pv(tDq + 32 * i, aDs0 + g * kPTile, aKv + kb * 2 * kKvBlk, jt != 0);
         tc_commit(&bars->p_empty[g]);
-        if (i == 7) tc_commit(&bars->o_full);
+        if (i == 7) {
+          tc_commit(&bars->o_full);
+          if (is_v) tc_commit(&bars->kv_empty[kb]);
+        }
+        if (is_v && n == 127) tc_commit(&bars->dq_full);
       }
       __syncwarp();
     }
@@ -1225,7 +1220,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap mQkv, const __grid_con
           wn = __ldg(drop_bits + ((size_t)bh * 32 + jn * 2 + half) * kS + qn);
         }
         if (DROP == 1) word = keep_word((uint32_t)(bh * kS + q), (uint32_t)(2 * jt + half), dk, th15);
-        mbar_wait(&bars->s_full[g], m & 1);
+        mbar_wait_parked(&bars->s_full[g], m & 1);
         tc_fence_after();
         uint32_t rs[32], rd[32];
         tmem_ld_32x32b_x32(tS, rs);
@@ -1237,7 +1232,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap mQkv, const __grid_con
 #pragma unroll
         for (int k4 = 0; k4 < 8; ++k4)
           bwd_four<DROP>(rs + 4 * k4, rd + 4 * k4, c2, nl2, nd2, word << (7 - k4), ds + 2 * k4, pd + 2 * k4);
-        mbar_wait(&bars->p_empty[g], (m & 1) ^ 1);  // the products of this group's previous tile have read the tiles
+        mbar_wait_parked(&bars->p_empty[g], (m & 1) ^ 1);  // the products of this group's previous tile have read the tiles
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const uint32_t off = p_off(row, 4 * half + c);
@@ -1248,7 +1243,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap mQkv, const __grid_con
       }
       if (g == 1) {
         // ---- dK_j (half 0) / dV_j (half 1): M = 64 accumulators, key row quad*16 + lane on TMEM lane quad*32 + lane ----
-        mbar_wait(&bars->o_full, jt & 1);
+        mbar_wait_parked(&bars->o_full, jt & 1);
         tc_fence_after();
         uint32_t r[32];
         tmem_ld_32x32b_x32(tDkv, r);
@@ -1271,7 +1266,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap mQkv, const __grid_con
       }
     }
     // ---- dQ: group g drains query tiles g, g + 2, g + 4, g + 6; each half its 16 of the 32 columns ----
-    mbar_wait(&bars->dq_full, 0);
+    mbar_wait_parked(&bars->dq_full, 0);
     tc_fence_after();
 #pragma unroll
     for (int ii = 0; ii < 4; ++ii) {
