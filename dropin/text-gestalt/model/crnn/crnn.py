@@ -1,0 +1,3 @@
+"""model.crnn.crnn of text-gestalt (model/crnn/crnn.py) on the focr engine"""
+from fudanocr_b200.model.crnn.crnn import *  # noqa: F401,F403
+from fudanocr_b200.model.crnn.crnn import CRNN  # noqa: F401

@@ -142,6 +142,21 @@ def check(rc: int, what: str = "focr call") -> None:
         raise FocrError(f"{what} failed ({rc}): {lib.focr_last_error().decode()}")
 
 
+_STATUS_CHECKS = __import__("os").environ.get("FOCR_CHECK_STATUS", "0") not in ("", "0")
+
+
+def set_status_checks(on: bool) -> None:
+    """Opt-in debug mode: after kernels that report bad indices / lengths through a device status word (text embedding,
+    CTC loss, crop resize) read the word back (one host synchronisation per call) and raise like torch does.  Off by default:
+    a training step never blocks the host.  Also enabled by FOCR_CHECK_STATUS=1 in the environment."""
+    global _STATUS_CHECKS
+    _STATUS_CHECKS = bool(on)
+
+
+def status_checks() -> bool:
+    return _STATUS_CHECKS
+
+
 def ptr(t) -> int:
     """Raw device pointer of a torch tensor (0 for None)."""
     return 0 if t is None else t.data_ptr()

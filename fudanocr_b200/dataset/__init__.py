@@ -1,1 +1,2 @@
-from .dataset import alignCollate_real, alignCollate_syn, resizeNormalize, resize_normalize_batch  # noqa: F401
+from .dataset import (alignCollate_real, alignCollate_syn, finish_collate, hostCollate_real, hostCollate_syn,  # noqa: F401
+                      pack_crops, resizeNormalize, resize_normalize_batch)

@@ -17,7 +17,8 @@ import torch
 
 from .. import _lib as L
 
-__all__ = ["resizeNormalize", "alignCollate_syn", "alignCollate_real", "resize_normalize_batch", "pack_crops"]
+__all__ = ["resizeNormalize", "alignCollate_syn", "alignCollate_real", "resize_normalize_batch", "pack_crops",
+           "hostCollate_real", "hostCollate_syn", "finish_collate"]
 
 
 def _as_u8_hwc(img) -> np.ndarray:
@@ -46,8 +47,8 @@ def pack_crops(images: Sequence) -> Tuple[torch.Tensor, torch.Tensor, int, int]:
         meta[i] = (off, a.shape[0], a.shape[1])
         off += a.size
     buf = torch.empty(max(off, 1), dtype=torch.uint8)
-    if torch.cuda.is_available():
-        buf = buf.pin_memory()
+    if torch.cuda.is_available() and torch.utils.data.get_worker_info() is None:
+        buf = buf.pin_memory()   # (a forked DataLoader worker must not create a CUDA context: finish_collate pins instead)
     flat = buf.numpy()
     for (o, h, w), a in zip(meta, arrs):
         flat[o:o + a.size] = a.reshape(-1)
@@ -59,6 +60,11 @@ def pack_crops(images: Sequence) -> Tuple[torch.Tensor, torch.Tensor, int, int]:
 def resize_normalize_batch(images: Sequence, size: Tuple[int, int], device=None, packed=None) -> torch.Tensor:
     """[resizeNormalize(size)(im) for im in images] stacked: (B, 3, size[1], size[0]) fp32 in [0, 1] on `device`.
     `packed` = a (device pixels, device meta, max_h, max_w) tuple re-uses an upload (HR and LR from the same crops)."""
+    if torch.utils.data.get_worker_info() is not None:
+        raise L.FocrError(
+            "focr collate was called inside a DataLoader worker process: CUDA cannot be (re)initialised in a forked worker. "
+            "Use num_workers=0 with alignCollate_real / alignCollate_syn, or keep the workers and give the loader "
+            "hostCollate_real / hostCollate_syn (pack the crops in the worker) and call finish_collate(batch) in the main process.")
     if not torch.cuda.is_available():
         raise L.FocrError("focr collate runs on a CUDA device only (no CPU fallback)")
     dev = torch.device("cuda" if device is None else device)
@@ -71,10 +77,12 @@ def resize_normalize_batch(images: Sequence, size: Tuple[int, int], device=None,
     pix, meta_d, max_h, max_w = packed
     B = meta_d.shape[0]
     out = torch.empty(B, 3, oh, ow, dtype=torch.float32, device=dev)
-    status = torch.empty(1, dtype=torch.int32, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
         L.check(L.lib.focr_resize_bicubic_normalize(pix.data_ptr(), meta_d.data_ptr(), B, max_h, max_w, ow, oh, out.data_ptr(),
                                                     status.data_ptr(), L.cur_stream()), "resize_bicubic_normalize")
+    if L.status_checks() and int(status.item()):
+        raise ValueError("resize_bicubic_normalize: a crop exceeds the kernel's shared-memory budget (its output was left zero)")
     return out
 
 
@@ -132,3 +140,50 @@ class alignCollate_real(alignCollate_syn):
         images_HR = resize_normalize_batch(images_HR, (self.imgW, self.imgH))
         images_lr = resize_normalize_batch(images_lr, (self.imgW // s, self.imgH // s))
         return images_HR, images_lr, label_strs
+
+
+# ---- worker-safe split: the host half runs inside DataLoader workers (no CUDA), the device half in the main process -------------
+class hostCollate_real(object):
+    """collate_fn for DataLoaders with num_workers > 0 (the reference's loaders use 8, interfaces/base.py:103-108): packs the
+    ragged HR / LR crops of a batch into two uint8 buffers + meta tables and touches no CUDA API; `finish_collate` turns
+    the result into the (images_HR, images_lr, label_strs) triple of alignCollate_real in the main process"""
+    kind = "real"
+
+    def __init__(self, imgH=64, imgW=256, down_sample_scale=4, keep_ratio=False, min_ratio=1, mask=False):
+        if mask:
+            raise NotImplementedError("focr collate: mask=True (4-channel input) is not supported")
+        self.imgH, self.imgW, self.down_sample_scale = imgH, imgW, down_sample_scale
+
+    def __call__(self, batch):
+        images_HR, images_lr, label_strs = zip(*batch)
+        return {"kind": self.kind, "hr": pack_crops(images_HR), "lr": pack_crops(images_lr), "labels": label_strs,
+                "size": (self.imgW, self.imgH), "scale": self.down_sample_scale}
+
+
+class hostCollate_syn(hostCollate_real):
+    """host half of alignCollate_syn: the single crop list travels; both resamples run on the device in finish_collate"""
+    kind = "syn"
+
+    def __call__(self, batch):
+        images, label_strs = zip(*batch)
+        return {"kind": self.kind, "hr": [_as_u8_hwc(im) for im in images], "labels": label_strs,
+                "size": (self.imgW, self.imgH), "scale": self.down_sample_scale}
+
+
+def finish_collate(batch: dict, device=None):
+    """device half (main process): -> (images_HR, images_lr, label_strs) exactly as alignCollate_real / alignCollate_syn"""
+    W, H = batch["size"]
+    s = batch["scale"]
+    if batch["kind"] == "syn":
+        hr, lr, labels = alignCollate_syn(H, W, s)([(im, lab) for im, lab in zip(batch["hr"], batch["labels"])])
+        return hr, lr, labels
+    dev = torch.device("cuda" if device is None else device)
+
+    def up(packed):
+        buf, meta, mh, mw = packed
+        if not buf.is_pinned():
+            buf = buf.pin_memory()
+        return buf.to(dev, non_blocking=True), meta.to(dev, non_blocking=True), mh, mw
+    hr = resize_normalize_batch(None, (W, H), dev, packed=up(batch["hr"]))
+    lr = resize_normalize_batch(None, (W // s, H // s), dev, packed=up(batch["lr"]))
+    return hr, lr, batch["labels"]

@@ -51,10 +51,17 @@ class _CTCFn(torch.autograd.Function):
             L.check(L.lib.focr_ctc_loss(x.data_ptr(), T, B, Cn, targets.data_ptr(), S_max, input_lengths.data_ptr(),
                                         target_lengths.data_ptr(), blank, reduction, int(zero_infinity), 1.0, nll.data_ptr(),
                                         loss.data_ptr(), grad.data_ptr(), ws.data_ptr(), ws.numel(), L.cur_stream()), "ctc_loss")
+        if L.status_checks():   # F.ctc_loss raises on out-of-range lengths / labels; the kernel reports them in a status word
+            import ctypes as C
+            st = C.c_int(0)
+            L.check(L.lib.focr_ctc_loss_status(ws.data_ptr(), T, B, S_max, C.byref(st), L.cur_stream()), "ctc_loss_status")
+            if st.value == 1:
+                raise ValueError("ctc_loss: an input / target length is out of range")
+            if st.value == 2:
+                raise ValueError(f"ctc_loss: a target label lies outside [0, {Cn})")
         ctx.save_for_backward(grad)
         ctx.reduction = reduction
         ctx.in_dtype = logits.dtype
-        ctx.ws = (ws, T, B, S_max)
         return nll if reduction == 0 else loss[0]
 
     @staticmethod
@@ -80,6 +87,10 @@ def ctc_loss(log_probs: torch.Tensor, targets: torch.Tensor, input_lengths: Unio
     B = log_probs.shape[1]
     if il.numel() != B or tl.numel() != B:
         raise ValueError("input_lengths / target_lengths must have one entry per batch element")
+    if not il.is_cuda and (int(il.min()) < 0 or int(il.max()) > log_probs.shape[0]):
+        raise ValueError(f"input_lengths must lie in [0, {log_probs.shape[0]}]")
+    if not tl.is_cuda and int(tl.min()) < 0:
+        raise ValueError("target_lengths must be non-negative")
     if targets.dim() == 1:
         targets = _pad_targets(targets, tl.cpu())
     elif targets.dim() != 2 or targets.shape[0] != B:

@@ -270,9 +270,11 @@ def embed_fwd(idx, lut, rows_pad, p, seed, sid):
     B, T = idx.shape
     vocab, E = lut.shape
     out = torch.empty(rows_pad, 2 * E, dtype=BF, device=dev)
-    status = torch.empty(1, dtype=torch.int32, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
     _call(L.lib.focr_text_embed_fwd, "text_embed_fwd", idx.data_ptr(), lut.data_ptr(), vocab, E, B, T, rows_pad, out.data_ptr(),
           float(p), int(seed), int(sid), status.data_ptr(), L.cur_stream())
+    if L.status_checks() and int(status.item()):   # nn.Embedding raises IndexError on such an index
+        raise IndexError(f"text_embed_fwd: token index outside [0, {vocab}) (the kernel maps it to row 0)")
     return out
 
 

@@ -12,6 +12,7 @@ pointers to ``focr_tbsrn_forward`` / ``focr_tbsrn_backward`` (include/focr.h) th
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 import math
 from typing import Dict, List
 
@@ -172,10 +173,14 @@ class _TPS(_Holder):  # model/tps_spatial_transformer.py:54-95 (buffers only)
 # ---------------------------------------------------------------------------------------------
 # autograd bridge
 # ---------------------------------------------------------------------------------------------
+class _FwdState(dict):
+    """state of one engine forward (a dict that can be weakly referenced)"""
+
+
 class _EngineFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, model, *params):
-        st = model._launch_forward(x)
+        st = model._launch_forward(x, pending=True)
         ctx.model, ctx.st = model, st
         ctx.set_materialize_grads(False)
         return st["sr"]
@@ -203,6 +208,9 @@ class _SREngineModule(nn.Module):
             self._slot_names = [lib.focr_tbsrn_slot_name(srb_nums, i).decode() for i in range(n)]
         self._cache = None   # (slot tensors, pointer table) — invalidated by _apply (.to / .cuda / .float)
         self._ws: Dict[int, torch.Tensor] = {}
+        self._ws_gen = 0
+        self._ws_stamp: Dict[int, int] = {}   # arena address -> generation of the forward whose activations it holds
+        self._ws_owner: Dict[int, "weakref.ref"] = {}   # arena address -> forward state whose backward is still pending
 
     def _ws_bytes(self, B: int) -> int:
         if self._ARCH == "tsrn":
@@ -270,8 +278,11 @@ class _SREngineModule(nn.Module):
                                   f"(got {t.dtype} on {t.device}); there is no CPU path")
             tensors.append(t)
         table = (C.c_void_p * len(tensors))(*[0 if t is None else t.data_ptr() for t in tensors])
+        # every nn.Parameter slot, whatever its requires_grad flag says right now: the reference's eval() switches the flag
+        # off on all parameters and the train loop switches it back on (interfaces/super_resolution.py:166-170, :61-62) -
+        # a cache keyed on the flag would be empty forever if the first forward happened while frozen
         grad_slots = [i for i, t in enumerate(tensors)
-                      if t is not None and isinstance(t, nn.Parameter) and t.requires_grad
+                      if t is not None and isinstance(t, nn.Parameter)
                       and (self.stn or not self._slot_names[i].startswith("stn_head."))]
         self._cache = (tensors, table)
         self._grad_slots = grad_slots
@@ -285,7 +296,21 @@ class _SREngineModule(nn.Module):
             self._ws = {B: ws}  # keep one batch size resident
         return ws
 
-    def _launch_forward(self, x: torch.Tensor) -> dict:
+    def _forward_workspace(self, B: int, device):
+        """workspace for one forward.  The arena holds the activations the backward reads, so a forward whose backward is
+        still pending OWNS its arena: a second forward of the same batch size before that backward (two micro-batches summed
+        into one loss, a validation forward between forward and backward) gets a fresh arena instead of overwriting it.
+        Ownership is a weak reference to the forward's state (held by its autograd node): a forward whose graph was dropped
+        without a backward releases its arena by itself.  Returns (arena, generation stamp)."""
+        ws = self._workspace(B, device)
+        owner = self._ws_owner.get(ws.data_ptr())
+        if owner is not None and owner() is not None:
+            ws = torch.empty(ws.numel(), dtype=torch.uint8, device=device)   # not cached: dies with its autograd node
+        self._ws_gen += 1
+        self._ws_stamp[ws.data_ptr()] = self._ws_gen
+        return ws, self._ws_gen
+
+    def _launch_forward(self, x: torch.Tensor, pending: bool = False) -> dict:
         if not x.is_cuda:
             raise L.FocrError(f"focr {type(self).__name__} runs on CUDA (sm_100a) only; move the input to the GPU")
         if x.dim() != 4 or tuple(x.shape[1:]) != (3, 16, 64):
@@ -293,7 +318,7 @@ class _SREngineModule(nn.Module):
         tensors, table = self._slots()
         x = x.detach().contiguous().float()
         B = x.shape[0]
-        ws = self._workspace(B, x.device)
+        ws, gen = self._forward_workspace(B, x.device)
         sr = torch.empty(B, 3, 32, 128, dtype=torch.float32, device=x.device)
         training = bool(self.training)
         flags = (1 if training else 0) | (2 if self.stn else 0)
@@ -301,9 +326,18 @@ class _SREngineModule(nn.Module):
         seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item()) if p > 0 else 0
         with torch.cuda.device(x.device):
             L.check(self._c_forward(table, x, sr, B, flags, p, seed, ws), f"focr_{self._ARCH}_forward")
-        return {"x": x, "sr": sr, "ws": ws, "B": B, "flags": flags, "p": p, "seed": seed}
+        st = _FwdState(x=x, sr=sr, ws=ws, gen=gen, B=B, flags=flags, p=p, seed=seed)
+        if pending:
+            self._ws_owner[ws.data_ptr()] = weakref.ref(st)
+        else:
+            self._ws_owner.pop(ws.data_ptr(), None)
+        return st
 
     def _launch_backward(self, st: dict, d_sr: torch.Tensor):
+        if self._ws_stamp.get(st["ws"].data_ptr()) != st["gen"]:
+            raise L.FocrError("the activations of this forward have been overwritten by a later forward of the same batch size "
+                              "(backward called twice on one forward?); run forward again before backward")
+        self._ws_owner.pop(st["ws"].data_ptr(), None)   # the arena is free for the next forward
         tensors, table = self._slots()
         sizes = [tensors[i].numel() for i in self._grad_slots]
         flat = torch.empty(sum(sizes), dtype=torch.float32, device=d_sr.device)

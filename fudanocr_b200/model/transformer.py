@@ -368,7 +368,8 @@ class Transformer(nn.Module):
             if p.dim() > 1:
                 nn.init.xavier_uniform_(p)
         self.dropout_p = self.DROPOUT
-        self._seed = 0x5EED
+        # dropout stream: follows torch.manual_seed (reproducible runs); the trainers mix the rank in (reseed_dropout)
+        self._seed = (0x5EED ^ int(torch.initial_seed())) & 0x7FFFFFFF
 
     # -- encoder ------------------------------------------------------------------------------------------------------
     def _bn(self, x, bn: nn.BatchNorm2d, act: int):

@@ -39,6 +39,7 @@ class TBSRNTrainer:
         self.criterion = criterion
         self.losses: Optional[torch.Tensor] = None
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.rank = dist.get_rank(process_group) if self.world > 1 else 0
         tensors, _ = model._slots()
         self.slots = list(model._grad_slots)
         params = [tensors[i] for i in self.slots]
@@ -77,9 +78,9 @@ class TBSRNTrainer:
         self.d_sr: Optional[torch.Tensor] = None
         self.sr: Optional[torch.Tensor] = None
         self.kernel_launches = 0
-        # The step is ~600 short launches: replaying it as CUDA graphs removes the launch gaps (measured 24.0 -> 22.8
-        # ms/step at batch 256).  Two graphs, [forward + loss + backward] and [clip + Adam], with the data-parallel
-        # all-reduce between them; the dropout seed lives in a device word the kernels read at run time, the batch in
+        # The step is ~500 short launches: replaying it as a CUDA graph removes the launch gaps (measured 24.0 -> 22.8
+        # ms/step at batch 256).  One graph: [forward + loss + backward -> gradient all-reduce -> clip + Adam] (see
+        # _capture); the dropout seed lives in a device word the kernels read at run time, the batch in
         # static input buffers.  Captured lazily per batch size after one eager step (which also sets every kernel
         # attribute); a criterion with host-side label encoding keeps the eager path.
         self.use_graph = bool(use_graph)
@@ -120,8 +121,32 @@ class TBSRNTrainer:
             self._lr_in.copy_(self._last_lr)
             self._hr_in.copy_(self._last_hr)
         torch.cuda.current_stream().wait_stream(side)
-        g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        # ONE graph for the whole step: forward + loss + backward, the gradient all-reduce (NCCL collectives can be
+        # captured: the exchange becomes a graph node between the last backward kernel and the optimizer instead of an
+        # eager call wedged between two replays - at 32 crops per GPU that gap was ~13x the wire time), clip + Adam.
+        # FOCR_GRAPH_NCCL=0, or a capture that NCCL refuses, falls back to two graphs with the collective between them.
+        import os
         n0 = L.lib.focr_launch_count()
+        one = self.world == 1 or os.environ.get("FOCR_GRAPH_NCCL", "1") != "0"
+        if one:
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._fwd_loss_bwd(self._lr_in, self._hr_in, B, flags, p, 0, ws, None, use_seed_dev)
+                    if self.world > 1:
+                        dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.pg)
+                    self._optimizer()
+                self._graph_launches = int(L.lib.focr_launch_count() - n0)   # kernel nodes replayed per step
+                self._graphs = (g,)
+                return
+            except Exception as ex:   # noqa: BLE001 - keep training on the two-graph path
+                if self.world == 1:
+                    raise
+                import warnings
+                warnings.warn(f"focr: NCCL all-reduce could not be captured into the step graph ({ex}); using two graphs")
+                torch.cuda.synchronize()
+                n0 = L.lib.focr_launch_count()
+        g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
         with torch.cuda.graph(g1):
             self._fwd_loss_bwd(self._lr_in, self._hr_in, B, flags, p, 0, ws, None, use_seed_dev)
         with torch.cuda.graph(g2):
@@ -146,6 +171,8 @@ class TBSRNTrainer:
         p = m.dropout_p
         if seed is None:
             seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item()) if p > 0 else 0
+        if self.world > 1 and p > 0:   # replicas draw independent dropout masks, as nn.DataParallel's do
+            seed ^= (self.rank * 0x9E3779B1) & 0x7FFFFFFF
         key = (B, flags, p, ws.data_ptr())
         graphable = (self.use_graph and self.criterion is None and not L.prof_enabled() and images_lr.is_contiguous()
                      and images_hr.is_contiguous() and images_lr.dtype == torch.float32 and images_hr.dtype == torch.float32)
@@ -157,9 +184,10 @@ class TBSRNTrainer:
             self._lr_in.copy_(images_lr, non_blocking=True)
             self._hr_in.copy_(images_hr, non_blocking=True)
             self._graphs[0].replay()
-            if self.world > 1:
-                dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.pg)
-            self._graphs[1].replay()
+            if len(self._graphs) == 2:
+                if self.world > 1:
+                    dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.pg)
+                self._graphs[1].replay()
             self.kernel_launches += self._graph_launches
             return self.loss
         if self._graph_key != key:

@@ -62,6 +62,9 @@ class _FlatAdadeltaTrainer:
         self.loss: Optional[torch.Tensor] = None
         if self.world > 1:   # start from rank 0's weights on every rank
             dist.broadcast(self.flat_p, src=0, group=self.pg)
+            rank = dist.get_rank(self.pg)
+            if hasattr(model, "_seed"):   # replicas draw independent dropout masks, as nn.DataParallel's do
+                model._seed = (model._seed ^ (rank * 0x9E3779B1)) & 0x7FFFFFFF
 
     def _begin(self):
         self.model.train()
