@@ -362,7 +362,9 @@ class SLDTrain:
 
     def algo_work(self):
         fwd = self.B * 30.24e9 * self.width / 32.0   # encoder convs per image (forward)
-        return {"tc_conv3x3": ("tensor", 2 * fwd), "tc_linear": ("tensor", 2 * fwd), "conv_wgrad_tc": ("tensor", fwd),
+        # tc_conv3x3: implicit-GEMM forward + input-gradient convs; tc_linear: every 1x1-shaped GEMM = the weight-gradient GEMMs
+        # (dW = dY^T col, K = pixels: the same 30.2 GFLOP/img) + the decoder linears (~1 GFLOP/img fwd + bwd)
+        return {"tc_conv3x3": ("tensor", 2 * fwd), "tc_linear": ("tensor", fwd + self.B * 1.0e9), "conv_wgrad_tc": ("tensor", fwd),
                 "wgrad_operands": ("hbm", self.B * self.width / 32.0 * 73e6), "adadelta": ("hbm", 71.7e6 * 28)}
 
     @staticmethod
@@ -415,9 +417,11 @@ class EvalPipeline:
         B = self.B
         T = B * 1024
         g = 2.0 * 1024 * 1024 * 32
+        # tc_linear: the FeatureEnhancer linears + the CRNN, whose convs run as im2col GEMMs (1.27 GFLOP/img) and whose LSTM input
+        # projections are GEMMs too (0.14 GFLOP/img)
         return {"attn_fwd": ("tensor", 5 * B * 4 * 2 * g),
-                "tc_conv3x3": ("tensor", 2.0 * T * 576 * (11 * 64 + 256) + B * 1.27e9),
-                "tc_linear": ("tensor", 5 * 2.0 * T * 128 * (384 + 128 + 128 + 128 + 64) + B * 0.14e9),
+                "tc_conv3x3": ("tensor", 2.0 * T * 576 * (11 * 64 + 256)),
+                "tc_linear": ("tensor", 5 * 2.0 * T * 128 * (384 + 128 + 128 + 128 + 64) + B * 1.41e9),
                 "tc_conv9tap": ("tensor", 2.0 * T * 576 * 64 + 2.0 * B * 4096 * 576 * 64)}
 
     @staticmethod
@@ -533,6 +537,11 @@ def main():
         raise SystemExit("bench.py (focr arm) needs a B200: there is no CPU fallback for the CUDA engine")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # stdout carries exactly ONE line (the JSON): NCCL announces its version on fd 1 at the first collective, so fd 1 points at
+    # stderr until the result is printed
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         os.environ.setdefault("NCCL_IB_DISABLE", "1")   # single node: NVLink / NVSwitch only
         os.environ.setdefault("NCCL_P2P_LEVEL", "NVL")
@@ -598,10 +607,20 @@ def main():
         except Exception as ex:   # the extra point must never take the headline number down with it
             strong = {"error": str(ex)[:200]}
 
-    if rank != 0:
+    def finish(line=None):
+        """print the line on the real stdout and leave.  The step graph holds captured NCCL work: tearing the process group
+        down under it can block forever, and nothing after this point needs an orderly shutdown, so every rank syncs and exits"""
+        torch.cuda.synchronize()
         if world > 1:
-            dist.destroy_process_group()
-        return
+            dist.barrier()
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        if line is not None:
+            os.write(1, (line + "\n").encode())
+        os._exit(0)
+
+    if rank != 0:
+        finish()
     peaks = load_peaks()
     kind, amount = work.get(top, ("tensor", 0.0))
     cnt, tot_ms = focus.get(top, (0, 0.0))
@@ -654,9 +673,7 @@ def main():
         except Exception as ex:  # the baseline leg must never take the GPU number down with it
             out["cpu_baseline"] = {"value": None, "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
                                    "sample": f"failed: {ex}"}
-    print(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
+    finish(json.dumps(out))
 
 
 if __name__ == "__main__":

@@ -57,6 +57,10 @@ _SIGS = {
     "focr_umma_probe": (C.c_int, [_vp, _i, C.c_ulonglong, C.c_ulonglong, _u, _i, _u, _u, _vp, _i, _vp]),
     "focr_attn_set_force_exact": (C.c_int, [_i]),
     "focr_attn_set_bwd_two_pass": (C.c_int, [_i]),
+    "focr_recog_decode_prepared_bytes": (_sz, [_i, _i, _i]),
+    "focr_recog_decode_prepare": (C.c_int, [_pp, _i, _i, _fp, _i, _vp, _sz, _vp]),
+    "focr_recog_decode_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "focr_recog_decode": (C.c_int, [_vp, _sz, _i, _i, _i, _vp, _i, _i, _i, _vp, _fp, _vp, _sz, _vp]),
     "focr_weight_cross_entropy_workspace_bytes": (_sz, [_l]),
     "focr_weight_cross_entropy": (C.c_int, [_fp, _vp, _fp, _fp, _fp, _vp, _l, _i, _vp, _sz, _vp]),
     "focr_to_gray": (C.c_int, [_fp, _fp, _l, _i, _l, _vp]),

@@ -140,3 +140,79 @@ def greedy_decode_ids(model, image: torch.Tensor, text_features: torch.Tensor, m
         pred = torch.cat((pred, now.view(-1, 1)), 1)
         feats = result["conv"]
     return pred, prob
+
+
+# ---- KV-cached decode (csrc/decode.cu): the same loops, one launch sequence on the device, one read-back -------------------------
+def _decoder_param_table(model):
+    """the 29 fp32 tensors focr_recog_decode_prepare takes, in its order"""
+    d = model.decoder
+    t = [model.embedding_word.lut.weight]
+    for lin in d.mask_multihead.linears:
+        t += [lin.weight, lin.bias]
+    t += [d.mul_layernorm1.scale, d.mul_layernorm1.shift]
+    for lin in d.multihead.linears:
+        t += [lin.weight, lin.bias]
+    t += [d.mul_layernorm2.scale, d.mul_layernorm2.shift, d.pff.w_1.weight, d.pff.w_1.bias, d.pff.w_2.weight, d.pff.w_2.bias,
+          d.mul_layernorm3.scale, d.mul_layernorm3.shift, model.generator_word.proj.weight, model.generator_word.proj.bias]
+    return [x.detach().float().contiguous() for x in t]
+
+
+@torch.no_grad()
+def _cached_decode(model, image: torch.Tensor, max_length: int, text_features: Optional[torch.Tensor]):
+    import ctypes as C
+    from . import _lib as L
+    if not image.is_cuda:
+        raise L.FocrError("focr decode runs on CUDA tensors only (no CPU fallback)")
+    was_training = model.training
+    model.eval()
+    try:
+        feat = model.encode(image)                                   # (B, h, w, 1024) bf16, encoder once
+    finally:
+        model.train(was_training)
+    B, n_tok = feat.shape[0], feat.shape[1] * feat.shape[2]
+    dev = image.device
+    rows = B * n_tok
+    rows_pad = (rows + 127) // 128 * 128
+    f2 = feat.reshape(rows, 1024)
+    if rows_pad != rows:
+        f2 = torch.cat([f2, torch.zeros(rows_pad - rows, 1024, dtype=f2.dtype, device=dev)], 0)
+    f2 = f2.contiguous()
+    params = _decoder_param_table(model)
+    vocab = params[0].shape[0]
+    n_out = params[27].shape[0]
+    tf = None if text_features is None else text_features.to(dev).float().contiguous()
+    n_feat = 0 if tf is None else tf.shape[0]
+    table = (C.c_void_p * len(params))(*[p.data_ptr() for p in params])
+    blob = torch.empty(L.lib.focr_recog_decode_prepared_bytes(vocab, n_out, n_feat), dtype=torch.uint8, device=dev)
+    st = L.cur_stream()
+    with torch.cuda.device(dev):
+        L.check(L.lib.focr_recog_decode_prepare(table, vocab, n_out, None if tf is None else tf.data_ptr(), n_feat, blob.data_ptr(),
+                                                blob.numel(), st), "recog_decode_prepare")
+        ws = torch.empty(L.lib.focr_recog_decode_workspace_bytes(B, n_tok, max_length, n_out, n_feat), dtype=torch.uint8, device=dev)
+        pred = torch.empty(B, max_length + 1, dtype=torch.long, device=dev)
+        prob = torch.empty(B, max_length, dtype=torch.float32, device=dev)
+        L.check(L.lib.focr_recog_decode(blob.data_ptr(), blob.numel(), vocab, n_out, n_feat, f2.data_ptr(), B, n_tok, max_length,
+                                        pred.data_ptr(), prob.data_ptr(), ws.data_ptr(), ws.numel(), st), "recog_decode")
+    return pred, prob
+
+
+def greedy_decode_sld_cached(model, image: torch.Tensor, max_length: int = 30):
+    """`greedy_decode_sld` with the decoder run incrementally on the device (K / V caches, arg-max and end bookkeeping in kernels):
+    same return values.  stroke-level-decomposition/train.py:110-137."""
+    pred, prob = _cached_decode(model, image, max_length, None)
+    end = model.word_n_class - 1
+    pred_h, prob_h = pred.cpu(), prob.cpu()                          # the one read-back
+    sequences, overall = [], []
+    for b in range(pred_h.shape[0]):
+        row = pred_h[b].tolist()
+        cut = next((j for j in range(max_length) if row[j] == end), max_length - 1)
+        kept = row[:cut + 1]
+        sequences.append(kept[1:])
+        overall.append(float(torch.prod(prob_h[b, :max(len(kept) - 1, 0)])))
+    return pred, prob, sequences, overall
+
+
+def greedy_decode_ids_cached(model, image: torch.Tensor, text_features: torch.Tensor, max_length: int):
+    """`greedy_decode_ids` on the KV-cached device loop: (pred (B, max_length + 1), prob (B, max_length)).
+    image-ids-CTR/train.py:118-134."""
+    return _cached_decode(model, image, max_length, text_features)

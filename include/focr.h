@@ -209,6 +209,25 @@ int focr_weight_cross_entropy(const float* pred, const long long* gt, const floa
 int focr_to_gray(const float* img, float* gray, long B, int C, long HW, void* stream);
 int focr_to_gray_bwd(const float* d_gray, float* d_img, long B, int C, long HW, void* stream);
 
+/* --- KV-cached greedy test-time decode of the ResNet + Transformer recognisers ------------------------------
+ * replaces the loops stroke-level-decomposition/train.py:110-121 and image-ids-CTR/train.py:118-134, which re-run the whole
+ * decoder (SLD/model/transformer.py:303-317) on the growing prefix for each of max_length steps.  Here the cross-attention K / V
+ * of the image tokens are projected once, self-attention K / V are cached per emitted position, and every step runs the decoder
+ * layer on the ONE new position, arg-max (lowest index on ties) and its softmax probability included; nothing visits the host
+ * until the (B, T_max + 1) token matrix is read back.
+ * params: HOST array of 29 DEVICE fp32 pointers - 0 embedding table (vocab,512); 1-8 masked self-attention linears q,k,v,out
+ * (weight (1024,1024), bias each); 9,10 LayerNorm-1 scale, shift; 11-18 cross-attention linears; 19,20 LayerNorm-2; 21-24 FFN
+ * w_1 (2048,1024), b_1, w_2 (1024,2048), b_2; 25,26 LayerNorm-3; 27,28 generator weight (n_out,1024), bias.
+ * text_features: NULL (SLD: the generator scores are the class scores) or fp32 (n_feat, n_out) (IDS: the generator output is
+ * L2-normalised and matched against them).  feat: bf16, B*n_tok rows zero-padded to a multiple of 128, 1024 columns (the encoder's
+ * NHWC map).  pred int64 (B, T_max+1): column 0 = start symbol 0; prob fp32 (B, T_max) = winning softmax probability per step. */
+size_t focr_recog_decode_prepared_bytes(int vocab, int n_out, int n_feat);
+int focr_recog_decode_prepare(void* const* params, int vocab, int n_out, const float* text_features, int n_feat, void* blob,
+                              size_t blob_bytes, void* stream);
+size_t focr_recog_decode_workspace_bytes(int B, int n_tok, int T_max, int n_out, int n_feat);
+int focr_recog_decode(const void* blob, size_t blob_bytes, int vocab, int n_out, int n_feat, const void* feat, int B, int n_tok,
+                      int T_max, long long* pred, float* prob, void* ws, size_t ws_bytes, void* stream);
+
 /* --- evaluation metrics: scene-text-telescope/utils/ssim_psnr.py:9-15 (calculate_psnr), :31-78 (SSIM, window 11, sigma 1.5),
  * as called per validation batch by interfaces/super_resolution.py:191-192.  img1, img2 fp32 NCHW (B, channels >= 3, 32, 128)
  * in [0,1] (first 3 channels are used); window: the 121 fp32 taps of create_window (:24-28).  out[0] = PSNR over the batch

@@ -122,5 +122,50 @@ def main():
           f"worst oracle-vs-reference gradient error {worst:.2e}, {(gd / 'ids_b4.pt').stat().st_size / 1e6:.1f} MB")
 
 
+def main_b32():
+    """the same reference module and train.py:71-80 arithmetic at batch 32: loss terms, every gradient norm, 256-element samples"""
+    torch.manual_seed(0)
+    torch.set_num_threads(os.cpu_count())
+    Transformer, util = load_reference()
+    model = Transformer()
+    gd = synth.GOLDEN_DIR
+    sd = synth.synth_state_dict(synth.load_spec("ids"), 4321)
+    model.load_state_dict(sd, strict=False)
+    for m in model.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    B = 32
+    image, labels = IO.synth_batch(B)
+    length, text_input, text_gt = IO.converter(labels)
+    text_features = IO.synth_text_features()
+    model.train()
+    result = model(image, length, text_input)
+    reg = torch.cat([text_features[item].unsqueeze(0) for item in text_gt], dim=0)
+    text_pred = result["pred"]
+    text_pred = text_pred / text_pred.norm(dim=1, keepdim=True)
+    final_res = text_pred @ text_features.t()
+    loss_rec = torch.nn.CrossEntropyLoss()(final_res, text_gt)
+    loss_dis = -torch.nn.MSELoss()(text_pred, reg)
+    loss = loss_rec + 0.001 * loss_dis
+    model.zero_grad()
+    loss.backward()
+    ref_grads = {k: p.grad for k, p in model.named_parameters()}
+    golden = {
+        "B": B, "labels": labels, "length": length, "text_input": text_input, "text_gt": text_gt,
+        "image_checksum": float(image.double().sum()), "loss": loss.detach(), "loss_rec": loss_rec.detach(),
+        "loss_dis": loss_dis.detach(),
+        "grad_norms": {k: (g.norm() if g is not None else None) for k, g in ref_grads.items()},
+        "grad_samples": {k: g.reshape(-1)[::max(g.numel() // 256, 1)][:256].clone() for k, g in ref_grads.items() if g is not None},
+    }
+    torch.save(golden, gd / "ids_b32.pt")
+    h = hashlib.sha256((gd / "ids_b32.pt").read_bytes()).hexdigest()
+    sums = [ln for ln in (gd / "SHA256SUMS").read_text().splitlines() if "ids_b32.pt" not in ln]
+    (gd / "SHA256SUMS").write_text("\n".join(sums + [f"{h}  ids_b32.pt"]) + "\n")
+    print(f"ids b32 golden: loss {float(loss.detach()):.6f}, {(gd / 'ids_b32.pt').stat().st_size / 1e6:.2f} MB")
+
+
 if __name__ == "__main__":
-    main()
+    if "--b32" in sys.argv:
+        main_b32()
+    else:
+        main()

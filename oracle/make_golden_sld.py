@@ -121,5 +121,44 @@ def main():
           f"{(gd / 'sld_b3.pt').stat().st_size / 1e6:.1f} MB")
 
 
+def main_b32():
+    """the same reference module at batch 32 (BatchNorm over 8192 positions per channel: the conditioning the GPU whole-step
+    test needs); records the loss, every gradient norm and 256-element samples of every gradient"""
+    torch.manual_seed(0)
+    torch.set_num_threads(os.cpu_count())
+    Transformer, util = load_reference()
+    model = Transformer("stroke")
+    gd = synth.GOLDEN_DIR
+    sd = synth.synth_state_dict(synth.load_spec("sld"), 1234)
+    model.load_state_dict(sd, strict=False)
+    for m in model.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    B = 32
+    image, strings = SO.synth_batch(B)
+    length, text_input, text_gt = SO.converter_stroke(strings)
+    model.train()
+    out = model(image, length, text_input)
+    loss = torch.nn.CrossEntropyLoss()(out["pred"], text_gt)
+    model.zero_grad()
+    loss.backward()
+    ref_grads = {k: p.grad for k, p in model.named_parameters()}
+    golden = {
+        "B": B, "strings": strings, "length": length, "text_input": text_input, "text_gt": text_gt,
+        "image_checksum": float(image.double().sum()), "loss": loss.detach(), "pred_norm": out["pred"].detach().norm(),
+        "conv_norm": out["conv"].detach().norm(),
+        "grad_norms": {k: (g.norm() if g is not None else None) for k, g in ref_grads.items()},
+        "grad_samples": {k: g.reshape(-1)[::max(g.numel() // 256, 1)][:256].clone() for k, g in ref_grads.items() if g is not None},
+    }
+    torch.save(golden, gd / "sld_b32.pt")
+    h = hashlib.sha256((gd / "sld_b32.pt").read_bytes()).hexdigest()
+    sums = [ln for ln in (gd / "SHA256SUMS").read_text().splitlines() if "sld_b32.pt" not in ln]
+    (gd / "SHA256SUMS").write_text("\n".join(sums + [f"{h}  sld_b32.pt"]) + "\n")
+    print(f"sld b32 golden: loss {float(loss):.6f}, {(gd / 'sld_b32.pt').stat().st_size / 1e6:.2f} MB")
+
+
 if __name__ == "__main__":
-    main()
+    if "--b32" in sys.argv:
+        main_b32()
+    else:
+        main()

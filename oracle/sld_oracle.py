@@ -45,17 +45,23 @@ def basic_block(sd, p, x, train, stats_out=None):                      # transfo
     return F.relu(out + res)
 
 
-def encoder(sd, image, train=True, stats_out=None):                    # transformer.py:126-164
+def encoder(sd, image, train=True, stats_out=None, taps=None):         # transformer.py:126-164
+    """taps (optional dict): receives (input, output) of every stage - 'stem' (conv1 + bn1 + relu + pool), 'conv2', each
+    BasicBlock 'layerL.i' and each transition conv 'layerL_conv' - for teacher-forced per-stage tests"""
     e = "encoder."
-    x = F.relu(_bn(sd, e + "bn1", _conv(sd, e + "conv1", image), train, stats_out))
-    x = F.max_pool2d(x, (2, 2), (2, 2))
-    x = F.relu(_bn(sd, e + "bn2", _conv(sd, e + "conv2", x), train, stats_out))
+
+    def tap(name, xin, xout):
+        if taps is not None:
+            taps[name] = (xin.detach(), xout.detach())
+        return xout
+    x = tap("stem", image, F.max_pool2d(F.relu(_bn(sd, e + "bn1", _conv(sd, e + "conv1", image), train, stats_out)), (2, 2), (2, 2)))
+    x = tap("conv2", x, F.relu(_bn(sd, e + "bn2", _conv(sd, e + "conv2", x), train, stats_out)))
     for name, n, _, _ in LAYERS:
         for i in range(n):
-            x = basic_block(sd, f"{e}{name}.{i}", x, train, stats_out)
+            x = tap(f"{name}.{i}", x, basic_block(sd, f"{e}{name}.{i}", x, train, stats_out))
         tail = name + ("_conv2" if name == "layer4" else "_conv")
         bn = name + ("_conv2_bn" if name == "layer4" else "_bn")
-        x = F.relu(_bn(sd, e + bn, _conv(sd, e + tail, x), train, stats_out))
+        x = tap(tail, x, F.relu(_bn(sd, e + bn, _conv(sd, e + tail, x), train, stats_out)))
     return x
 
 
