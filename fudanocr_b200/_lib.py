@@ -86,6 +86,9 @@ _SIGS = {
     "focr_mha_small_fwd": (C.c_int, [_vp, _l, _vp, _l, _vp, _l, _vp, _l, _fp, _i, _i, _i, _i, _i, _i, _f, _u, _u, _vp]),
     "focr_mha_small_bwd": (C.c_int, [_vp, _l, _vp, _l, _vp, _l, _vp, _l, _fp, _vp, _l, _vp, _l, _vp, _l, _i, _i, _i, _i, _i, _i,
                                      _f, _vp]),
+    "focr_mha_small_bwd_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "focr_mha_small_bwd_ws": (C.c_int, [_vp, _l, _vp, _l, _vp, _l, _vp, _l, _fp, _vp, _l, _vp, _l, _vp, _l, _i, _i, _i, _i, _i, _i,
+                                        _f, _vp, _sz, _vp]),
     "focr_layernorm_wide_fwd": (C.c_int, [_vp, _vp, _fp, _fp, _vp, _vp, _l, _i, _f, _vp]),
     "focr_layernorm_wide_workspace_bytes": (_sz, [_i]),
     "focr_layernorm_wide_bwd": (C.c_int, [_vp, _vp, _fp, _vp, _fp, _fp, _l, _i, _f, _vp, _sz, _vp]),

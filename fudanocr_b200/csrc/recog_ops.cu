@@ -39,14 +39,15 @@ __device__ __forceinline__ void load_row(const bf16* p, int lane, float (&r)[DKV
   for (int v = 0; v < DKV; ++v) r[v] = ldbf(p + v * 32 + lane);
 }
 
+// rows [i0, i1) of softmax(q k^T * scale [+ causal mask]) into S (row i at S + (i - i0) * Tk), one warp per row
 template <int DKV>
-__device__ void attn_probs(const bf16* __restrict__ q, long ld_q, const bf16* __restrict__ k, long ld_k, int Tq, int Tk,
+__device__ void attn_probs(const bf16* __restrict__ q, long ld_q, const bf16* __restrict__ k, long ld_k, int i0, int i1, int Tk,
                            int causal, float scale, float* __restrict__ S) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int i = warp; i < Tq; i += nw) {
+  for (int i = i0 + warp; i < i1; i += nw) {
     float qr[DKV];
     load_row<DKV>(q + (long)i * ld_q, lane, qr);
-    float* s = S + (long)i * Tk;
+    float* s = S + (long)(i - i0) * Tk;
     for (int j = 0; j < Tk; ++j) {
       float kr[DKV];
       load_row<DKV>(k + (long)j * ld_k, lane, kr);
@@ -86,7 +87,7 @@ __global__ void __launch_bounds__(256) mha_small_fwd_kernel(const bf16* __restri
   k += (long)b * Tk * ld_k + h * dk;
   v += (long)b * Tk * ld_v + h * dk;
   out += (long)b * Tq * ld_o + h * dk;
-  attn_probs<DKV>(q, ld_q, k, ld_k, Tq, Tk, causal, scale, S);
+  attn_probs<DKV>(q, ld_q, k, ld_k, 0, Tq, Tk, causal, scale, S);
   __syncthreads();
   // dropout on P (transformer.py:238-240); the dropped-out map is what the reference returns and multiplies into V
   float* mp = map + (long)blockIdx.x * Tq * Tk;
@@ -137,7 +138,7 @@ __global__ void __launch_bounds__(256) mha_small_bwd_kernel(const bf16* __restri
   dk_ += (long)b * Tk * ld_dk + h * dk;
   dv += (long)b * Tk * ld_dv + h * dk;
   const float* mp = map + (long)blockIdx.x * Tq * Tk;
-  attn_probs<DKV>(q, ld_q, k, ld_k, Tq, Tk, causal, scale, P);
+  attn_probs<DKV>(q, ld_q, k, ld_k, 0, Tq, Tk, causal, scale, P);
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   // dP = keep ? (dO . v_j) * keep_scale : 0 ; then dS = P (dP - sum_j P dP) * scale   (rows are warp-private)
@@ -201,6 +202,178 @@ __global__ void __launch_bounds__(256) mha_small_bwd_kernel(const bf16* __restri
         for (int c = 0; c < DKV; ++c) av[c] += pm * g[c];
       }
     }
+#pragma unroll
+    for (int c = 0; c < DKV; ++c) {
+      dk_[(long)j * ld_dk + c * 32 + lane] = __float2bfloat16(ak[c]);
+      dv[(long)j * ld_dv + c * 32 + lane] = __float2bfloat16(av[c]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// The same attention for key counts whose (Tq, Tk) score tile does not fit shared memory (the 2 560 image tokens of 32 x 320
+// crops): the grid also splits the query rows, kMhaRows (one per warp) per CTA, and the backward runs in two launches - a row
+// pass (P, dP, dS, dq; dS goes to a workspace) and a key pass (dk, dv from the dS / map columns staged in shared memory).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kMhaRows = 8;
+constexpr int kMhaKeyBlk = 32;
+
+template <int DKV>
+__global__ void __launch_bounds__(256) mha_rows_fwd_kernel(const bf16* __restrict__ q, long ld_q, const bf16* __restrict__ k,
+                                                           long ld_k, const bf16* __restrict__ v, long ld_v,
+                                                           bf16* __restrict__ out, long ld_o, float* __restrict__ map,
+                                                           int H, int Tq, int Tk, int causal, float scale, uint32_t key,
+                                                           uint32_t th16, float keep_scale) {
+  extern __shared__ float sm_att[];
+  float* S = sm_att;
+  const int b = blockIdx.x / H, h = blockIdx.x % H;
+  const int i0 = blockIdx.y * kMhaRows, i1 = min(Tq, i0 + kMhaRows);
+  constexpr int dk = DKV * 32;
+  q += (long)b * Tq * ld_q + h * dk;
+  k += (long)b * Tk * ld_k + h * dk;
+  v += (long)b * Tk * ld_v + h * dk;
+  out += (long)b * Tq * ld_o + h * dk;
+  attn_probs<DKV>(q, ld_q, k, ld_k, i0, i1, Tk, causal, scale, S);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = i0 + warp;          // rows are warp-private from here on (blockDim.x / 32 == kMhaRows)
+  if (i >= i1) return;
+  __syncwarp();
+  float* s = S + (long)warp * Tk;
+  float* mp = map + ((long)blockIdx.x * Tq + i) * Tk;
+  for (int j = lane; j < Tk; j += 32) {
+    float p = s[j];
+    if (th16) p = keep16(key, ((unsigned long long)blockIdx.x * Tq + i) * Tk + j, th16) ? p * keep_scale : 0.f;
+    s[j] = p;
+    mp[j] = p;
+  }
+  __syncwarp();
+  float acc[DKV];
+#pragma unroll
+  for (int c = 0; c < DKV; ++c) acc[c] = 0.f;
+  for (int j = 0; j < Tk; ++j) {
+    const float p = s[j];
+    if (p == 0.f) continue;  // warp-uniform
+    float vr[DKV];
+    load_row<DKV>(v + (long)j * ld_v, lane, vr);
+#pragma unroll
+    for (int c = 0; c < DKV; ++c) acc[c] += p * vr[c];
+  }
+#pragma unroll
+  for (int c = 0; c < DKV; ++c) out[(long)i * ld_o + c * 32 + lane] = __float2bfloat16(acc[c]);
+}
+
+template <int DKV>
+__global__ void __launch_bounds__(256) mha_rows_bwd_kernel(const bf16* __restrict__ q, long ld_q, const bf16* __restrict__ k,
+                                                           long ld_k, const bf16* __restrict__ v, long ld_v,
+                                                           const bf16* __restrict__ d_out, long ld_o,
+                                                           const float* __restrict__ map, bf16* __restrict__ dq, long ld_dq,
+                                                           float* __restrict__ ds_out, int H, int Tq, int Tk, int causal,
+                                                           float scale, float keep_scale) {
+  extern __shared__ float sm_att[];
+  float* P = sm_att;                          // [kMhaRows][Tk] softmax probabilities (pre-dropout), recomputed
+  float* D = sm_att + (long)kMhaRows * Tk;    // [kMhaRows][Tk] dP, then dS
+  const int b = blockIdx.x / H, h = blockIdx.x % H;
+  const int i0 = blockIdx.y * kMhaRows, i1 = min(Tq, i0 + kMhaRows);
+  constexpr int dk = DKV * 32;
+  q += (long)b * Tq * ld_q + h * dk;
+  k += (long)b * Tk * ld_k + h * dk;
+  v += (long)b * Tk * ld_v + h * dk;
+  d_out += (long)b * Tq * ld_o + h * dk;
+  dq += (long)b * Tq * ld_dq + h * dk;
+  attn_probs<DKV>(q, ld_q, k, ld_k, i0, i1, Tk, causal, scale, P);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = i0 + warp;
+  if (i >= i1) return;
+  __syncwarp();
+  float g[DKV];
+  load_row<DKV>(d_out + (long)i * ld_o, lane, g);
+  float* d = D + (long)warp * Tk;
+  const float* p = P + (long)warp * Tk;
+  const float* m = map + ((long)blockIdx.x * Tq + i) * Tk;
+  for (int j = 0; j < Tk; ++j) {
+    float a = 0.f;
+    if (m[j] != 0.f) {  // warp-uniform
+      float vr[DKV];
+      load_row<DKV>(v + (long)j * ld_v, lane, vr);
+#pragma unroll
+      for (int c = 0; c < DKV; ++c) a += g[c] * vr[c];
+      a = warp_sum(a) * keep_scale;
+    }
+    if (lane == 0) d[j] = a;
+  }
+  __syncwarp();
+  float delta = 0.f;
+  for (int j = lane; j < Tk; j += 32) delta += p[j] * d[j];
+  delta = warp_sum(delta);
+  float* dso = ds_out + ((long)blockIdx.x * Tq + i) * Tk;
+  for (int j = lane; j < Tk; j += 32) {
+    const float x = p[j] * (d[j] - delta) * scale;
+    d[j] = x;
+    dso[j] = x;
+  }
+  __syncwarp();
+  float acc[DKV];
+#pragma unroll
+  for (int c = 0; c < DKV; ++c) acc[c] = 0.f;
+  for (int j = 0; j < Tk; ++j) {
+    const float ds = d[j];
+    if (ds == 0.f) continue;
+    float kr[DKV];
+    load_row<DKV>(k + (long)j * ld_k, lane, kr);
+#pragma unroll
+    for (int c = 0; c < DKV; ++c) acc[c] += ds * kr[c];
+  }
+#pragma unroll
+  for (int c = 0; c < DKV; ++c) dq[(long)i * ld_dq + c * 32 + lane] = __float2bfloat16(acc[c]);
+}
+
+// dk_j = sum_i dS_ij q_i ; dv_j = sum_i map_ij dO_i for the kMhaKeyBlk keys of blockIdx.y, one warp per key at a time
+template <int DKV>
+__global__ void __launch_bounds__(256) mha_keys_bwd_kernel(const bf16* __restrict__ q, long ld_q, const bf16* __restrict__ d_out,
+                                                           long ld_o, const float* __restrict__ map,
+                                                           const float* __restrict__ ds, bf16* __restrict__ dk_, long ld_dk,
+                                                           bf16* __restrict__ dv, long ld_dv, int H, int Tq, int Tk) {
+  extern __shared__ float sm_att[];
+  float* sD = sm_att;                           // [Tq][kMhaKeyBlk]
+  float* sM = sm_att + (long)Tq * kMhaKeyBlk;   // [Tq][kMhaKeyBlk]
+  const int b = blockIdx.x / H, h = blockIdx.x % H;
+  const int j0 = blockIdx.y * kMhaKeyBlk;
+  constexpr int dk = DKV * 32;
+  q += (long)b * Tq * ld_q + h * dk;
+  d_out += (long)b * Tq * ld_o + h * dk;
+  dk_ += (long)b * Tk * ld_dk + h * dk;
+  dv += (long)b * Tk * ld_dv + h * dk;
+  const float* mp = map + (long)blockIdx.x * Tq * Tk;
+  const float* dp = ds + (long)blockIdx.x * Tq * Tk;
+  for (int e = threadIdx.x; e < Tq * kMhaKeyBlk; e += blockDim.x) {
+    const int i = e / kMhaKeyBlk, jj = e % kMhaKeyBlk;
+    const bool in = j0 + jj < Tk;
+    sD[e] = in ? dp[(long)i * Tk + j0 + jj] : 0.f;
+    sM[e] = in ? mp[(long)i * Tk + j0 + jj] : 0.f;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int jj = warp; jj < kMhaKeyBlk && j0 + jj < Tk; jj += nw) {
+    float ak[DKV], av[DKV];
+#pragma unroll
+    for (int c = 0; c < DKV; ++c) ak[c] = av[c] = 0.f;
+    for (int i = 0; i < Tq; ++i) {
+      const float x = sD[i * kMhaKeyBlk + jj];
+      const float pm = sM[i * kMhaKeyBlk + jj];
+      if (x != 0.f) {
+        float qr[DKV];
+        load_row<DKV>(q + (long)i * ld_q, lane, qr);
+#pragma unroll
+        for (int c = 0; c < DKV; ++c) ak[c] += x * qr[c];
+      }
+      if (pm != 0.f) {
+        float g[DKV];
+        load_row<DKV>(d_out + (long)i * ld_o, lane, g);
+#pragma unroll
+        for (int c = 0; c < DKV; ++c) av[c] += pm * g[c];
+      }
+    }
+    const int j = j0 + jj;
 #pragma unroll
     for (int c = 0; c < DKV; ++c) {
       dk_[(long)j * ld_dk + c * 32 + lane] = __float2bfloat16(ak[c]);
@@ -731,6 +904,44 @@ int launch_mha_bwd(const bf16* q, long ld_q, const bf16* k, long ld_k, const bf1
   return FOCR_OK;
 }
 
+template <int DKV>
+int launch_mha_rows_fwd(const bf16* q, long ld_q, const bf16* k, long ld_k, const bf16* v, long ld_v, bf16* out, long ld_o,
+                        float* map, int B, int H, int Tq, int Tk, int causal, float scale, uint32_t key, uint32_t th16, float ks,
+                        cudaStream_t s) {
+  const size_t smem = (size_t)kMhaRows * Tk * 4;
+  FOCR_REQUIRE(smem <= 200 * 1024, "mha_small_fwd: %d keys do not fit the row-split kernel's shared memory", Tk);
+  FOCR_CHECK_CUDA(cudaFuncSetAttribute(mha_rows_fwd_kernel<DKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  mha_rows_fwd_kernel<DKV><<<dim3(B * H, (Tq + kMhaRows - 1) / kMhaRows), kMhaRows * 32, smem, s>>>(
+      q, ld_q, k, ld_k, v, ld_v, out, ld_o, map, H, Tq, Tk, causal, scale, key, th16, ks);
+  FOCR_LAUNCH_CHECK();
+  return FOCR_OK;
+}
+template <int DKV>
+int launch_mha_rows_bwd(const bf16* q, long ld_q, const bf16* k, long ld_k, const bf16* v, long ld_v, const bf16* d_out, long ld_o,
+                        const float* map, bf16* dq, long ld_dq, bf16* dk, long ld_dk, bf16* dv, long ld_dv, float* ds, int B, int H,
+                        int Tq, int Tk, int causal, float scale, float ks, cudaStream_t s) {
+  const size_t smem = (size_t)kMhaRows * Tk * 8;
+  FOCR_REQUIRE(smem <= 200 * 1024, "mha_small_bwd: %d keys do not fit the row-split kernel's shared memory", Tk);
+  FOCR_CHECK_CUDA(cudaFuncSetAttribute(mha_rows_bwd_kernel<DKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  mha_rows_bwd_kernel<DKV><<<dim3(B * H, (Tq + kMhaRows - 1) / kMhaRows), kMhaRows * 32, smem, s>>>(
+      q, ld_q, k, ld_k, v, ld_v, d_out, ld_o, map, dq, ld_dq, ds, H, Tq, Tk, causal, scale, ks);
+  FOCR_LAUNCH_CHECK();
+  const size_t smem2 = (size_t)Tq * kMhaKeyBlk * 8;
+  FOCR_REQUIRE(smem2 <= 200 * 1024, "mha_small_bwd: Tq = %d too long for the key pass", Tq);
+  FOCR_CHECK_CUDA(cudaFuncSetAttribute(mha_keys_bwd_kernel<DKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  mha_keys_bwd_kernel<DKV><<<dim3(B * H, (Tk + kMhaKeyBlk - 1) / kMhaKeyBlk), 256, smem2, s>>>(q, ld_q, d_out, ld_o, map, ds, dk,
+                                                                                                ld_dk, dv, ld_dv, H, Tq, Tk);
+  FOCR_LAUNCH_CHECK();
+  return FOCR_OK;
+}
+
+// the single-CTA kernels keep the whole (Tq, Tk) tile in shared memory; beyond that the row-split pair takes over
+bool mha_fits_one_cta(int Tq, int Tk, int bytes_per_score) {
+  static int force_rows = -1;
+  if (force_rows < 0) force_rows = getenv("FOCR_MHA_ROWS") ? 1 : 0;   // test / tuning knob: always the row-split kernels
+  return !force_rows && (size_t)Tq * Tk * bytes_per_score <= 200 * 1024;
+}
+
 uint32_t th16_of(float p) {
   if (p <= 0.f) return 0;
   const long t = (long)(p * 65536.0 + 0.5);
@@ -753,37 +964,64 @@ int focr_mha_small_fwd(const void* q, long ld_q, const void* k, long ld_k, const
   FOCR_REQUIRE(!causal || Tq == Tk, "mha_small_fwd: the causal mask needs Tq == Tk");
   FOCR_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "mha_small_fwd: p_drop %f", p_drop);
   const size_t smem = (size_t)Tq * Tk * 4;
-  FOCR_REQUIRE(smem <= 200 * 1024, "mha_small_fwd: Tq*Tk = %d*%d does not fit shared memory", Tq, Tk);
   ProfScope _ps("mha_small_fwd", s);
   const uint32_t th = th16_of(p_drop);
   const float ks = 65536.f / (65536.f - (float)th);
   const float scale = 1.f / sqrtf((float)d_k);
   const uint32_t key = drop_key(seed, stream_id);
   const bf16 *qq = (const bf16*)q, *kk = (const bf16*)k, *vv = (const bf16*)v;
+  if (!mha_fits_one_cta(Tq, Tk, 4)) {
+    if (d_k == 64) return launch_mha_rows_fwd<2>(qq, ld_q, kk, ld_k, vv, ld_v, (bf16*)out, ld_o, map, B, H, Tq, Tk, causal, scale, key, th, ks, s);
+    if (d_k == 128) return launch_mha_rows_fwd<4>(qq, ld_q, kk, ld_k, vv, ld_v, (bf16*)out, ld_o, map, B, H, Tq, Tk, causal, scale, key, th, ks, s);
+    return launch_mha_rows_fwd<8>(qq, ld_q, kk, ld_k, vv, ld_v, (bf16*)out, ld_o, map, B, H, Tq, Tk, causal, scale, key, th, ks, s);
+  }
   if (d_k == 64) return launch_mha_fwd<2>(qq, ld_q, kk, ld_k, vv, ld_v, (bf16*)out, ld_o, map, B, H, Tq, Tk, causal, scale, key, th, ks, smem, s);
   if (d_k == 128) return launch_mha_fwd<4>(qq, ld_q, kk, ld_k, vv, ld_v, (bf16*)out, ld_o, map, B, H, Tq, Tk, causal, scale, key, th, ks, smem, s);
   return launch_mha_fwd<8>(qq, ld_q, kk, ld_k, vv, ld_v, (bf16*)out, ld_o, map, B, H, Tq, Tk, causal, scale, key, th, ks, smem, s);
 }
 
+// bytes of workspace focr_mha_small_bwd_ws needs: the dS tile (B, H, Tq, Tk) fp32 of the row-split backward, 0 when the whole
+// score tile of a (sample, head) fits one CTA's shared memory
+size_t focr_mha_small_bwd_workspace_bytes(int B, int H, int Tq, int Tk) {
+  if (mha_fits_one_cta(Tq, Tk, 8)) return 0;
+  return (size_t)B * H * Tq * Tk * 4;
+}
+
 // gradients of the above w.r.t. q, k, v given d_out and the stored map (its zeros are the dropped positions)
-int focr_mha_small_bwd(const void* q, long ld_q, const void* k, long ld_k, const void* v, long ld_v, const void* d_out, long ld_o,
-                       const float* map, void* dq, long ld_dq, void* dk, long ld_dk, void* dv, long ld_dv, int B, int H, int d_k,
-                       int Tq, int Tk, int causal, float p_drop, void* stream) {
+int focr_mha_small_bwd_ws(const void* q, long ld_q, const void* k, long ld_k, const void* v, long ld_v, const void* d_out, long ld_o,
+                          const float* map, void* dq, long ld_dq, void* dk, long ld_dk, void* dv, long ld_dv, int B, int H, int d_k,
+                          int Tq, int Tk, int causal, float p_drop, void* ws, size_t ws_bytes, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   FOCR_REQUIRE(q && k && v && d_out && map && dq && dk && dv, "mha_small_bwd: null pointer");
   FOCR_REQUIRE(B >= 1 && H >= 1 && Tq >= 1 && Tk >= 1, "mha_small_bwd: B=%d H=%d Tq=%d Tk=%d", B, H, Tq, Tk);
   FOCR_REQUIRE(d_k == 64 || d_k == 128 || d_k == 256, "mha_small_bwd: d_k %d (64, 128 or 256)", d_k);
   FOCR_REQUIRE(!causal || Tq == Tk, "mha_small_bwd: the causal mask needs Tq == Tk");
   const size_t smem = (size_t)Tq * Tk * 8;
-  FOCR_REQUIRE(smem <= 200 * 1024, "mha_small_bwd: Tq*Tk = %d*%d does not fit shared memory", Tq, Tk);
   ProfScope _ps("mha_small_bwd", s);
   const uint32_t th = th16_of(p_drop);
   const float ks = 65536.f / (65536.f - (float)th);
   const float scale = 1.f / sqrtf((float)d_k);
   const bf16 *qq = (const bf16*)q, *kk = (const bf16*)k, *vv = (const bf16*)v, *gg = (const bf16*)d_out;
+  if (!mha_fits_one_cta(Tq, Tk, 8)) {
+    FOCR_REQUIRE(ws != nullptr && ws_bytes >= focr_mha_small_bwd_workspace_bytes(B, H, Tq, Tk),
+                 "mha_small_bwd: Tq*Tk = %d*%d needs a %zu-byte workspace (focr_mha_small_bwd_workspace_bytes)", Tq, Tk,
+                 focr_mha_small_bwd_workspace_bytes(B, H, Tq, Tk));
+    float* ds = (float*)ws;
+    if (d_k == 64) return launch_mha_rows_bwd<2>(qq, ld_q, kk, ld_k, vv, ld_v, gg, ld_o, map, (bf16*)dq, ld_dq, (bf16*)dk, ld_dk, (bf16*)dv, ld_dv, ds, B, H, Tq, Tk, causal, scale, ks, s);
+    if (d_k == 128) return launch_mha_rows_bwd<4>(qq, ld_q, kk, ld_k, vv, ld_v, gg, ld_o, map, (bf16*)dq, ld_dq, (bf16*)dk, ld_dk, (bf16*)dv, ld_dv, ds, B, H, Tq, Tk, causal, scale, ks, s);
+    return launch_mha_rows_bwd<8>(qq, ld_q, kk, ld_k, vv, ld_v, gg, ld_o, map, (bf16*)dq, ld_dq, (bf16*)dk, ld_dk, (bf16*)dv, ld_dv, ds, B, H, Tq, Tk, causal, scale, ks, s);
+  }
   if (d_k == 64) return launch_mha_bwd<2>(qq, ld_q, kk, ld_k, vv, ld_v, gg, ld_o, map, (bf16*)dq, ld_dq, (bf16*)dk, ld_dk, (bf16*)dv, ld_dv, B, H, Tq, Tk, causal, scale, ks, smem, s);
   if (d_k == 128) return launch_mha_bwd<4>(qq, ld_q, kk, ld_k, vv, ld_v, gg, ld_o, map, (bf16*)dq, ld_dq, (bf16*)dk, ld_dk, (bf16*)dv, ld_dv, B, H, Tq, Tk, causal, scale, ks, smem, s);
   return launch_mha_bwd<8>(qq, ld_q, kk, ld_k, vv, ld_v, gg, ld_o, map, (bf16*)dq, ld_dq, (bf16*)dk, ld_dk, (bf16*)dv, ld_dv, B, H, Tq, Tk, causal, scale, ks, smem, s);
+}
+
+// the same without a workspace: score tiles that fit one CTA only
+int focr_mha_small_bwd(const void* q, long ld_q, const void* k, long ld_k, const void* v, long ld_v, const void* d_out, long ld_o,
+                       const float* map, void* dq, long ld_dq, void* dk, long ld_dk, void* dv, long ld_dv, int B, int H, int d_k,
+                       int Tq, int Tk, int causal, float p_drop, void* stream) {
+  return focr_mha_small_bwd_ws(q, ld_q, k, ld_k, v, ld_v, d_out, ld_o, map, dq, ld_dq, dk, ld_dk, dv, ld_dv, B, H, d_k, Tq, Tk, causal,
+                               p_drop, nullptr, 0, stream);
 }
 
 // y = LN(x [+ res]) over C in {512, 1024} features; sum_out (optional) receives x + res (the tensor the backward needs)

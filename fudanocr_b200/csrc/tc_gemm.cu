@@ -144,14 +144,25 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int m = tile / p.n_blocks, nb = tile % p.n_blocks;
         const int p0 = m * kTileM;
-        const int b = p0 / hw;
-        const int h0 = (p0 - b * hw) / p.W;
+        int b = p0 / hw;
+        int h0 = (p0 - b * hw) / p.W;
+        int w0 = 0;
+        if (p.wblocks > 1) {  // bw x (128 / bw)-pixel boxes, wblocks side by side
+          b = m / p.tiles_per_img;
+          const int r = m - b * p.tiles_per_img;
+          h0 = (r / p.wblocks) * (kTileM / p.bw);
+          w0 = (r % p.wblocks) * p.bw;
+        }
         if (use_aux) {
           const int ab = ait & 1;
           mbar_wait(&aempty[ab], ((ait >> 1) & 1) ^ 1);
           mbar_arrive_expect_tx(&afull[ab], Cfg::kCdBytes);
-          for (int blk = 0; blk < BLOCK_N / 64; ++blk)
-            tma_load_2d(aux_base + ab * Cfg::kCdBytes + blk * kCdBlk, &mR, &afull[ab], nb * BLOCK_N + blk * 64, p0);
+          for (int blk = 0; blk < BLOCK_N / 64; ++blk) {
+            if (p.wblocks > 1)
+              tma_load_4d(aux_base + ab * Cfg::kCdBytes + blk * kCdBlk, &mR, &afull[ab], nb * BLOCK_N + blk * 64, w0, h0, b);
+            else
+              tma_load_2d(aux_base + ab * Cfg::kCdBytes + blk * kCdBlk, &mR, &afull[ab], nb * BLOCK_N + blk * 64, p0);
+          }
           ++ait;
         }
         if (colmode) {
@@ -174,7 +185,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
             uint8_t* sa = ring + stage * stage_bytes;
             const int mi = ch / p.chunks_per_map;
             const int c0 = (ch - mi * p.chunks_per_map) * kChunkK;
-            tma_load_4d(sa, amaps[mi], &full[stage], c0, dx, h0 + dy, b);
+            tma_load_4d(sa, amaps[mi], &full[stage], c0, w0 + dx, h0 + dy, b);
             if (!resident)
               tma_load_2d(sa + kABytes, &mB, &full[stage], ch * kChunkK, tap * p.n_total + nb * BLOCK_N);
             if (++stage == n_stages) {
@@ -257,7 +268,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
     const int hw = p.H * p.W;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m = tile / p.n_blocks, nb = tile % p.n_blocks;
-      const long mg = (long)m * kTileM + row;
+      long mg = (long)m * kTileM + row;
+      int tb = 0, th0 = 0, tw0 = 0;
+      if (p.wblocks > 1) {  // true pixel index of this thread's row inside a bw-wide box
+        tb = m / p.tiles_per_img;
+        const int r = m - tb * p.tiles_per_img;
+        th0 = (r / p.wblocks) * (kTileM / p.bw);
+        tw0 = (r % p.wblocks) * p.bw;
+        mg = ((long)tb * p.H + th0 + row / p.bw) * p.W + tw0 + row % p.bw;
+      }
       if (p.tma_out) {
         // ---- TMEM -> registers -> swizzled smem tile -> TMA store.  No global access from these warps. ------------
         uint8_t* cd = cd_base + (it & 1) * Cfg::kCdBytes;
@@ -354,8 +373,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
         fence_proxy_async();  // make the generic-proxy smem writes visible to the TMA (async proxy)
         named_bar_sync(1, kEpiThreads);
         if (warp == 4 && lane == 0) {
-          for (int blk = 0; blk < BLOCK_N / 64; ++blk)
-            tma_store_2d(&mC, cd + blk * kCdBlk, nb * BLOCK_N + blk * 64, m * kTileM);
+          for (int blk = 0; blk < BLOCK_N / 64; ++blk) {
+            if (p.wblocks > 1)
+              tma_store_4d(&mC, cd + blk * kCdBlk, nb * BLOCK_N + blk * 64, tw0, th0, tb);
+            else
+              tma_store_2d(&mC, cd + blk * kCdBlk, nb * BLOCK_N + blk * 64, m * kTileM);
+          }
           bulk_commit();
         }
         ++it;
@@ -614,13 +637,29 @@ int tc_gemm_launch(const bf16* const* a_ptrs, int n_amaps, long a_pix_stride, lo
                    long a_img_stride, int a_channels, int B, const bf16* w, int cin, TcGemmParams p,
                    cudaStream_t stream) {
   FOCR_REQUIRE(n_amaps >= 1 && n_amaps <= 4, "tc_gemm: n_amaps %d", n_amaps);
-  FOCR_REQUIRE(p.W == 16 || p.W == 32 || p.W == 64 || p.W == 128, "tc_gemm: W must be 16, 32, 64 or 128 (got %d)", p.W);
   // a 128-pixel tile is (128 / W) image rows, or - for maps smaller than one tile (H * W < 128) - several whole images:
-  // the TMA box then extends over the batch dimension, the zero-filled halo still being per image
-  const int tile_rows = (p.H * p.W >= kTileM) ? kTileM / p.W : p.H;
-  const int tile_imgs = kTileM / (p.W * tile_rows);
-  FOCR_REQUIRE(p.H % tile_rows == 0 && tile_imgs * tile_rows * p.W == kTileM && B % tile_imgs == 0,
+  // the TMA box then extends over the batch dimension, the zero-filled halo still being per image.  Widths that are not
+  // one of 16 / 32 / 64 / 128 (the 16 x 160 maps of the 32 x 320 recogniser crops) are cut into bw-wide boxes of 128 / bw rows.
+  int bw = p.W;
+  if (!(p.W == 16 || p.W == 32 || p.W == 64 || p.W == 128)) {
+    bw = 0;
+    for (int c = 128; c >= 16; c >>= 1)
+      if (p.W % c == 0 && p.H % (kTileM / c) == 0) {
+        bw = c;
+        break;
+      }
+    FOCR_REQUIRE(bw != 0, "tc_gemm: a %dx%d map does not tile into 128-pixel boxes (W must be a multiple of 16 / 32 / 64 / 128 "
+                 "with H a multiple of 8 / 4 / 2 / 1)", p.H, p.W);
+  }
+  p.bw = bw;
+  p.wblocks = p.W / bw;
+  const int tile_rows = (p.H * bw >= kTileM) ? kTileM / bw : p.H;
+  const int tile_imgs = kTileM / (bw * tile_rows);
+  FOCR_REQUIRE(p.H % tile_rows == 0 && tile_imgs * tile_rows * bw == kTileM && B % tile_imgs == 0,
                "tc_gemm: a %dx%d map (batch %d) does not tile into 128-pixel boxes", p.H, p.W, B);
+  p.tiles_per_img = p.wblocks * (p.H / tile_rows);
+  FOCR_REQUIRE(p.wblocks == 1 || (p.epi == TC_EPI_BF16 && p.prelu_slope == nullptr && tile_imgs == 1),
+               "tc_gemm: %d-wide maps need the bf16 TMA epilogue", p.W);
   FOCR_REQUIRE(!p.relu_post || (p.epi == TC_EPI_BF16 && p.prelu_slope == nullptr), "tc_gemm: relu_post needs the bf16 TMA epilogue");
   FOCR_REQUIRE(cin % 64 == 0 && a_channels % 64 == 0, "tc_gemm: channels must be multiples of 64");
   FOCR_REQUIRE(p.kh >= 1 && p.kw >= 1 && (p.kh & 1) && (p.kw & 1) && p.kh <= 9 && p.kw <= 9, "tc_gemm: taps %dx%d",
@@ -641,7 +680,7 @@ int tc_gemm_launch(const bf16* const* a_ptrs, int n_amaps, long a_pix_stride, lo
     cuuint64_t dims[4] = {(cuuint64_t)a_channels, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)B};
     cuuint64_t str[3] = {(cuuint64_t)a_pix_stride * 2, (cuuint64_t)a_row_stride * 2,
                          (cuuint64_t)a_img_stride * 2};
-    cuuint32_t box[4] = {64, (cuuint32_t)p.W, (cuuint32_t)tile_rows, (cuuint32_t)tile_imgs};
+    cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)tile_rows, (cuuint32_t)tile_imgs};
     int rc = make_map(&am[i], base, 4, dims, str, box);
     if (rc) return rc;
   }
@@ -666,7 +705,18 @@ int tc_gemm_launch(const bf16* const* a_ptrs, int n_amaps, long a_pix_stride, lo
   p.tma_out = (p.epi == TC_EPI_BF16 && p.prelu_slope == nullptr) ? 1 : 0;
   FOCR_REQUIRE(p.tma_out || !(p.residual && p.gate), "tc_gemm: residual + gate needs the bf16 TMA epilogue");
   CUtensorMap cm = bm, rm = bm;
-  if (p.tma_out) {
+  if (p.tma_out && p.wblocks > 1) {  // output / auxiliary tiles are bw x tile_rows boxes of the (B, H, W, ldc) map
+    cuuint64_t dims[4] = {(cuuint64_t)p.n_total, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)B};
+    cuuint64_t str[3] = {(cuuint64_t)p.ldc * 2, (cuuint64_t)p.W * p.ldc * 2, (cuuint64_t)p.H * p.W * p.ldc * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)tile_rows, 1};
+    int rc = make_map(&cm, p.out, 4, dims, str, box);
+    if (rc) return rc;
+    const void* aux = p.residual ? (const void*)p.residual : (const void*)p.gate;
+    if (aux) {
+      rc = make_map(&rm, aux, 4, dims, str, box);
+      if (rc) return rc;
+    }
+  } else if (p.tma_out) {
     cuuint64_t dims[2] = {(cuuint64_t)p.n_total, (cuuint64_t)p.m_tiles * kTileM};
     cuuint64_t str[1] = {(cuuint64_t)p.ldc * 2};
     cuuint32_t box[2] = {64, (cuuint32_t)kTileM};
@@ -682,7 +732,7 @@ int tc_gemm_launch(const bf16* const* a_ptrs, int n_amaps, long a_pix_stride, lo
     static int no_col = -1;
     if (no_col < 0) no_col = getenv("FOCR_TC_NO_COLMODE") ? 1 : 0;  // tuning knob
     if (!no_col && p.b_resident && p.tma_out && p.kh == 3 && p.kw == 3 && p.chunks == 1 && n_amaps == 1 && !p.residual &&
-        !p.gate && tile_imgs == 1) {
+        !p.gate && tile_imgs == 1 && p.wblocks == 1) {
       cuuint64_t dims[4] = {(cuuint64_t)a_channels, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)B};
       cuuint64_t str[3] = {(cuuint64_t)a_pix_stride * 2, (cuuint64_t)a_row_stride * 2, (cuuint64_t)a_img_stride * 2};
       cuuint32_t box[4] = {64, (cuuint32_t)p.W, (cuuint32_t)(kTileM / p.W + 2), 1};

@@ -47,6 +47,9 @@ struct TcGemmParams {
   int col_mode;    // set by tc_gemm_launch: 3x3 taps taken column-wise from (rows + 2)-row tiles (see tc_gemm.cu)
   int b_resident;  // set by tc_gemm_launch: whole weight operand resident in shared memory (see tc_gemm.cu)
   int tma_out;  // set by tc_gemm_launch: epilogue goes TMEM -> smem -> TMA store, aux tile prefetched by TMA
+  // set by tc_gemm_launch: maps whose width is not a power of two up to 128 (the 16 x 160 maps of 32 x 320 crops) are cut into
+  // boxes of bw x (128 / bw) pixels, wblocks = W / bw of them side by side; wblocks == 1 is the row-contiguous tiling
+  int bw, wblocks, tiles_per_img;
 };
 
 int tc_gemm_launch(const bf16* const* a_ptrs, int n_amaps, long a_pix_stride /*elements between pixels*/,

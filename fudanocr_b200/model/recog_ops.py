@@ -235,9 +235,10 @@ def mha_bwd(q, k, v, d_out, amap, B, H, dk, Tq, Tk, causal, p):
     dq = torch.zeros(q.shape[0], H * dk, dtype=BF, device=dev)
     dk_ = torch.zeros(k.shape[0], H * dk, dtype=BF, device=dev)
     dv = torch.zeros(v.shape[0], H * dk, dtype=BF, device=dev)
-    _call(L.lib.focr_mha_small_bwd, "mha_small_bwd", q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0),
+    ws = _ws(L.lib.focr_mha_small_bwd_workspace_bytes(B, H, Tq, Tk), dev)
+    _call(L.lib.focr_mha_small_bwd_ws, "mha_small_bwd", q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0),
           d_out.data_ptr(), d_out.stride(0), amap.data_ptr(), dq.data_ptr(), dq.stride(0), dk_.data_ptr(), dk_.stride(0),
-          dv.data_ptr(), dv.stride(0), B, H, dk, Tq, Tk, int(causal), float(p), L.cur_stream())
+          dv.data_ptr(), dv.stride(0), B, H, dk, Tq, Tk, int(causal), float(p), ws.data_ptr(), ws.numel(), L.cur_stream())
     return dq, dk_, dv
 
 

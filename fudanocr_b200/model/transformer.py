@@ -43,6 +43,14 @@ def _bf(t):
 
 
 # ---- autograd nodes: bodies are kernel calls ----------------------------------------------------------------------------
+def _map_tiles(h: int, w: int) -> bool:
+    """can the implicit-GEMM convs (csrc/tc_gemm.cu: tc_gemm_launch) cut an (h, w) map into 128-pixel boxes?"""
+    if w in (16, 32, 64, 128):
+        rows = min(128 // w, h)
+        return h % rows == 0
+    return any(w % c == 0 and h % (128 // c) == 0 for c in (128, 64, 32, 16))
+
+
 class _ConvFirst(Function):
     @staticmethod
     def forward(ctx, x, w, b):
@@ -390,8 +398,10 @@ class Transformer(nn.Module):
 
     def encode(self, image: torch.Tensor) -> torch.Tensor:
         """(B, 3, H, W) fp32 -> (B, H/2, W/2, 1024) bf16 NHWC feature map (ResNet.forward, transformer.py:126-164)"""
-        if image.dim() != 4 or image.shape[1] != 3 or image.shape[2] % 2 or image.shape[3] // 2 not in (16, 32, 64, 128):
-            raise ValueError(f"focr Transformer: image must be (B,3,H,W) with even H and W in {{32,64,128,256}}, got "
+        if image.dim() != 4 or image.shape[1] != 3 or image.shape[2] % 2 or image.shape[3] % 2 or \
+                not _map_tiles(image.shape[2] // 2, image.shape[3] // 2):
+            raise ValueError(f"focr Transformer: image must be (B,3,H,W) whose (H/2, W/2) feature map cuts into 128-pixel TMA boxes "
+                             f"(W/2 in {{16,32,64,128}}, or a multiple of 32 / 64 with H/2 a multiple of 4 / 2 - e.g. 32x320), got "
                              f"{tuple(image.shape)}")
         ops.require_cuda(image)
         e = self.encoder

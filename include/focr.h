@@ -271,6 +271,12 @@ int focr_mha_small_fwd(const void* q, long ld_q, const void* k, long ld_k, const
 int focr_mha_small_bwd(const void* q, long ld_q, const void* k, long ld_k, const void* v, long ld_v, const void* d_out, long ld_o,
                        const float* map, void* dq, long ld_dq, void* dk, long ld_dk, void* dv, long ld_dv, int B, int H, int d_k,
                        int Tq, int Tk, int causal, float p_drop, void* stream);
+/* key counts whose (Tq, Tk) score tile exceeds one CTA's shared memory (2 560 image tokens of 32 x 320 crops): the backward
+ * splits into a row pass and a key pass and needs a (B, H, Tq, Tk) fp32 workspace; ..._workspace_bytes is 0 otherwise */
+size_t focr_mha_small_bwd_workspace_bytes(int B, int H, int Tq, int Tk);
+int focr_mha_small_bwd_ws(const void* q, long ld_q, const void* k, long ld_k, const void* v, long ld_v, const void* d_out, long ld_o,
+                          const float* map, void* dq, long ld_dq, void* dk, long ld_dk, void* dv, long ld_dv, int B, int H, int d_k,
+                          int Tq, int Tk, int causal, float p_drop, void* ws, size_t ws_bytes, void* stream);
 int focr_layernorm_wide_fwd(const void* x, const void* res, const float* a, const float* b, void* sum_out, void* y, long T, int C,
                             float eps, void* stream);
 size_t focr_layernorm_wide_workspace_bytes(int C);

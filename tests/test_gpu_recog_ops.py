@@ -54,8 +54,11 @@ def _mha_ref(q, k, v, B, H, dk, Tq, Tk, causal, keep=None, ks=1.0):
 
 
 @pytest.mark.parametrize("B,H,dk,Tq,Tk,causal", [(3, 4, 256, 17, 17, 1), (3, 4, 256, 17, 256, 0), (2, 16, 64, 9, 40, 0),
-                                                 (2, 8, 128, 31, 31, 1), (1, 4, 256, 1, 1, 1)])
+                                                 (2, 8, 128, 31, 31, 1), (1, 4, 256, 1, 1, 1),
+                                                 (2, 4, 256, 23, 2560, 0), (1, 4, 64, 300, 300, 1), (1, 2, 128, 9, 2561, 0)])
 def test_mha_small_fwd_bwd_no_dropout(B, H, dk, Tq, Tk, causal):
+    """the last three cases exceed one CTA's shared-memory score tile (2 560 = the image tokens of 32 x 320 crops): row-split
+    forward, row pass + key pass backward with a dS workspace"""
     L = _lib()
     g = torch.Generator(device=DEV).manual_seed(B * 100 + Tq)
     D = H * dk
@@ -75,20 +78,29 @@ def test_mha_small_fwd_bwd_no_dropout(B, H, dk, Tq, Tk, causal):
     dq = torch.empty(B * Tq, D, dtype=BF, device=DEV)
     dkv = torch.empty(B * Tk, 2 * D, dtype=BF, device=DEV)
     dk_, dv = dkv[:, :D], dkv[:, D:]
-    L.check(L.lib.focr_mha_small_bwd(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0),
-                                     d_out.data_ptr(), d_out.stride(0), amap.data_ptr(), dq.data_ptr(), dq.stride(0),
-                                     dk_.data_ptr(), dk_.stride(0), dv.data_ptr(), dv.stride(0), B, H, dk, Tq, Tk, causal, 0.0,
-                                     L.cur_stream()), "mha_small_bwd")
+    nws = L.lib.focr_mha_small_bwd_workspace_bytes(B, H, Tq, Tk)
+    assert (nws > 0) == (Tq * Tk * 8 > 200 * 1024)
+    ws = _ws(nws)
+    L.check(L.lib.focr_mha_small_bwd_ws(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0),
+                                        d_out.data_ptr(), d_out.stride(0), amap.data_ptr(), dq.data_ptr(), dq.stride(0),
+                                        dk_.data_ptr(), dk_.stride(0), dv.data_ptr(), dv.stride(0), B, H, dk, Tq, Tk, causal, 0.0,
+                                        ws.data_ptr(), ws.numel(), L.cur_stream()), "mha_small_bwd")
     _sync(L)
+    if nws:  # the no-workspace entry refuses what it cannot do
+        assert L.lib.focr_mha_small_bwd(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0),
+                                        d_out.data_ptr(), d_out.stride(0), amap.data_ptr(), dq.data_ptr(), dq.stride(0),
+                                        dk_.data_ptr(), dk_.stride(0), dv.data_ptr(), dv.stride(0), B, H, dk, Tq, Tk, causal, 0.0,
+                                        L.cur_stream()) != 0
     assert _rel(dq, qr.grad) < 1e-2
     assert _rel(dk_, kr.grad) < 1e-2
     assert _rel(dv, vr.grad) < 1e-2
 
 
-def test_mha_small_dropout_mask_is_the_oracle_rng_and_gradients_follow_it():
+@pytest.mark.parametrize("Tk", [256, 2560])
+def test_mha_small_dropout_mask_is_the_oracle_rng_and_gradients_follow_it(Tk):
     from oracle import dropout_rng as R
     L = _lib()
-    B, H, dk, Tq, Tk, p, seed, sid = 2, 4, 256, 13, 256, 0.1, 99, 5
+    B, H, dk, Tq, p, seed, sid = 2, 4, 256, 13, 0.1, 99, 5
     D = H * dk
     g = torch.Generator(device=DEV).manual_seed(5)
     q = torch.randn(B * Tq, D, device=DEV, generator=g).to(BF)
@@ -106,9 +118,10 @@ def test_mha_small_dropout_mask_is_the_oracle_rng_and_gradients_follow_it():
     d_out = torch.randn(B * Tq, D, device=DEV, generator=g).to(BF)
     o_ref.backward(d_out.float())
     dq, dk_, dv = (torch.empty_like(t) for t in (q, k, v))
-    L.check(L.lib.focr_mha_small_bwd(q.data_ptr(), D, k.data_ptr(), D, v.data_ptr(), D, d_out.data_ptr(), D, amap.data_ptr(),
-                                     dq.data_ptr(), D, dk_.data_ptr(), D, dv.data_ptr(), D, B, H, dk, Tq, Tk, 0, p,
-                                     L.cur_stream()), "mha_small_bwd")
+    ws = _ws(L.lib.focr_mha_small_bwd_workspace_bytes(B, H, Tq, Tk))
+    L.check(L.lib.focr_mha_small_bwd_ws(q.data_ptr(), D, k.data_ptr(), D, v.data_ptr(), D, d_out.data_ptr(), D, amap.data_ptr(),
+                                        dq.data_ptr(), D, dk_.data_ptr(), D, dv.data_ptr(), D, B, H, dk, Tq, Tk, 0, p,
+                                        ws.data_ptr(), ws.numel(), L.cur_stream()), "mha_small_bwd")
     _sync(L)
     assert _rel(dq, qr.grad) < 1e-2 and _rel(dk_, kr.grad) < 1e-2 and _rel(dv, vr.grad) < 1e-2
     # argument errors are codes, not crashes
@@ -354,10 +367,12 @@ def test_implicit_conv_on_16x16_maps(B, Ci, Co, flags):
 
 
 @pytest.mark.parametrize("B,H,W,Ci,Co", [(8, 2, 16, 512, 1024), (4, 2, 16, 1024, 1024), (3, 4, 32, 256, 512), (2, 8, 64, 128, 256),
-                                         (1, 16, 128, 64, 128)])
+                                         (1, 16, 128, 64, 128), (3, 16, 160, 64, 128), (2, 16, 160, 256, 512), (1, 8, 96, 128, 128),
+                                         (2, 4, 320, 64, 64)])
 def test_implicit_conv_on_the_ids_encoder_maps(B, H, W, Ci, Co):
     """image-ids-CTR pools four times (model/transformer.py:126-152): 16x128, 8x64, 4x32 and 2x16 maps; a 2x16 map is a quarter of
-    a 128-pixel tile, so the TMA box spans four images (zero halo still per image)"""
+    a 128-pixel tile, so the TMA box spans four images (zero halo still per image).  16x160 (the maps of 32x320 crops, BASELINE
+    configs[3]) and other widths that are not a power of two are cut into 32- / 64-pixel-wide boxes of 4 / 2 rows."""
     L = _lib()
     g = torch.Generator(device=DEV).manual_seed(H * W + Co)
     x = torch.randn(B, H, W, Ci, device=DEV, generator=g).to(BF)
@@ -436,8 +451,26 @@ def test_l2norm_rows_and_packed_feature_mse():
     assert _rel(d[:B * T], yr.grad[:B * T]) < 1e-2 and (d[:B * T].float()[yr.grad[:B * T] == 0] == 0).all()
 
 
+def test_implicit_conv_160_wide_with_residual_tile():
+    """the auxiliary (residual) tile of a 16x160 map travels through the same 32x4-pixel TMA boxes as the output"""
+    L = _lib()
+    B, H, W, Ci, Co = 2, 16, 160, 128, 128
+    g = torch.Generator(device=DEV).manual_seed(160)
+    x = torch.randn(B, H, W, Ci, device=DEV, generator=g).to(BF)
+    res = torch.randn(B, H, W, Co, device=DEV, generator=g).to(BF)
+    w = torch.randn(Co, Ci, 3, 3, device=DEV, generator=g) / (9 * Ci) ** 0.5
+    bias = torch.randn(Co, device=DEV, generator=g)
+    y = torch.empty(B, H, W, Co, dtype=BF, device=DEV)
+    ws = _ws(L.lib.focr_conv2d_workspace_bytes(Ci, Co, 3))
+    L.check(L.lib.focr_conv2d_fwd(x.data_ptr(), w.data_ptr(), bias.data_ptr(), y.data_ptr(), 0, res.data_ptr(), B, H, W, Ci, Co, 3, 0,
+                                  ws.data_ptr(), ws.numel(), L.cur_stream()), "conv2d_fwd W=160 + residual")
+    _sync(L)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.to(BF).float(), bias, padding=1) + res.float().permute(0, 3, 1, 2)
+    assert _rel(y.permute(0, 3, 1, 2), ref) < 1e-2
+
+
 @pytest.mark.parametrize("B,H,W,Ci,Co", [(8, 16, 16, 128, 256), (2, 16, 16, 512, 1024), (4, 2, 16, 1024, 1024), (2, 8, 64, 128, 256),
-                                         (1, 16, 128, 64, 128)])
+                                         (1, 16, 128, 64, 128), (2, 16, 160, 128, 256)])
 def test_conv_wgrad_on_tcgen05(B, H, W, Ci, Co):
     """dW = dY^T col with the pixel dimension as the GEMM's K (both operands transposed to K-major, fp32 accumulation in TMEM)"""
     L = _lib()
