@@ -362,19 +362,23 @@ class SLDTrain:
 
     def algo_work(self):
         fwd = self.B * 30.24e9 * self.width / 32.0   # encoder convs per image (forward)
-        # tc_conv3x3: implicit-GEMM forward + input-gradient convs; tc_linear: every 1x1-shaped GEMM = the weight-gradient GEMMs
-        # (dW = dY^T col, K = pixels: the same 30.2 GFLOP/img) + the decoder linears (~1 GFLOP/img fwd + bwd)
-        return {"tc_conv3x3": ("tensor", 2 * fwd), "tc_linear": ("tensor", fwd + self.B * 1.0e9), "conv_wgrad_tc": ("tensor", fwd),
+        # tc_conv3x3: implicit-GEMM forward + input-gradient convs; conv_wgrad_tc: the weight-gradient GEMMs (dW = dY^T col,
+        # K = pixels: the same 30.2 GFLOP/img) with their operand preparation inside the scope; tc_linear: stem + decoder linears
+        # (K / V projections of every image token: 2 x 2 x 1024^2 FLOP per token, fwd + dgrad)
+        tok = self.B * 16 * self.width / 2
+        return {"tc_conv3x3": ("tensor", 2 * fwd), "tc_linear": ("tensor", 2 * tok * 4 * 1024 * 1024 + self.B * 1.0e9),
+                "conv_wgrad_tc": ("tensor", fwd),
                 "wgrad_operands": ("hbm", self.B * self.width / 32.0 * 73e6), "adadelta": ("hbm", 71.7e6 * 28)}
 
     @staticmethod
     def cpu_rate(batch, steps, warmup):
         sys.path.insert(0, os.path.join(ROOT, "scripts"))
         import bench_cfg4
-        r = bench_cfg4.cpu_baseline("sld", batch=batch, steps=steps)
+        r = bench_cfg4.cpu_baseline("sld", batch=batch, steps=steps, width=SLDTrain.WIDTH)
         sec = batch / r["value"]
-        return r["value"], r["cores"], sec, "oracle SLD train step (torch CPU fp32, all host threads)"
+        return r["value"], r["cores"], sec, f"oracle SLD train step on 32x{SLDTrain.WIDTH} crops (torch CPU fp32, all host threads)"
     CPU_BATCH = 8
+    WIDTH = 32      # set from --width by main()
 
 
 class EvalPipeline:
@@ -523,6 +527,7 @@ def timed(torch, dist, world, dev, fn, K):
 
 def main():
     args = parse_args()
+    SLDTrain.WIDTH = args.width
     if args.impl == "reference":
         run_reference(args)
         return

@@ -20,6 +20,9 @@ std::vector<cudaEvent_t> g_pool;
 int g_mode = 0;            // 0 off, 1 all scopes, 2 only scopes whose name contains g_focus
 std::string g_focus;
 long long g_launches = 0;
+int g_depth = 0;           // open recorded scopes: a scope opened inside another one (the GEMM inside conv_wgrad_tc) is not recorded,
+                           // so the per-family times add up to the step instead of counting the inner launches twice
+void* const kNested = reinterpret_cast<void*>(~static_cast<uintptr_t>(0));
 
 cudaEvent_t get_event() {
   if (!g_pool.empty()) {
@@ -40,6 +43,12 @@ bool prof_begin(const char* name, cudaStream_t s, void** tok) {
   if (g_mode == 0) return false;
   if (g_mode == 2 && std::string(name).find(g_focus) == std::string::npos) return false;
   std::lock_guard<std::mutex> lk(g_mu);
+  if (g_depth > 0) {
+    ++g_depth;
+    *tok = kNested;
+    return true;
+  }
+  ++g_depth;
   Rec r{name, get_event(), get_event()};
   cudaEventRecord(r.a, s);
   g_recs.push_back(r);
@@ -49,6 +58,8 @@ bool prof_begin(const char* name, cudaStream_t s, void** tok) {
 void prof_end(void* tok, cudaStream_t s) {
   if (!tok) return;
   std::lock_guard<std::mutex> lk(g_mu);
+  if (g_depth > 0) --g_depth;
+  if (tok == kNested) return;
   const size_t i = reinterpret_cast<size_t>(tok) - 1;
   if (i < g_recs.size()) cudaEventRecord(g_recs[i].b, s);
 }
@@ -58,6 +69,7 @@ extern "C" {
 int focr_prof_enable(int mode, const char* focus) {
   std::lock_guard<std::mutex> lk(g_mu);
   g_mode = mode;
+  g_depth = 0;
   g_focus = focus ? focus : "";
   return 0;
 }

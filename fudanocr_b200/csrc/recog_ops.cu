@@ -33,10 +33,67 @@ __device__ __forceinline__ float ldbf(const bf16* p) { return __bfloat162float(*
 // decoder attention.  q rows (b*Tq + i) with leading dimension ld_q, head h at columns [h*dk, (h+1)*dk); k / v rows
 // (b*Tk + j).  One CTA per (b, head), 8 warps.  smem: S[Tq][Tk] fp32 (+ second array in the backward).
 // ------------------------------------------------------------------------------------------------------------------
+// lane l owns the DKV consecutive elements [l * DKV, (l + 1) * DKV) of a head row: ONE 4- / 8- / 16-byte load per row and lane
+// (the first version gave lane l the elements v * 32 + l: eight 2-byte loads per row, and the key loops were bound by their latency)
 template <int DKV>  // d_k / 32 elements per lane
 __device__ __forceinline__ void load_row(const bf16* p, int lane, float (&r)[DKV]) {
+  static_assert(DKV == 2 || DKV == 4 || DKV == 8, "d_k in {64, 128, 256}");
+  uint32_t w[DKV / 2];
+  if constexpr (DKV == 2) {
+    w[0] = *reinterpret_cast<const uint32_t*>(p + lane * 2);
+  } else if constexpr (DKV == 4) {
+    const uint2 u = *reinterpret_cast<const uint2*>(p + lane * 4);
+    w[0] = u.x; w[1] = u.y;
+  } else {
+    const uint4 u = *reinterpret_cast<const uint4*>(p + lane * 8);
+    w[0] = u.x; w[1] = u.y; w[2] = u.z; w[3] = u.w;
+  }
 #pragma unroll
-  for (int v = 0; v < DKV; ++v) r[v] = ldbf(p + v * 32 + lane);
+  for (int v = 0; v < DKV / 2; ++v) {
+    const float2 f = unpack_bf16x2(w[v]);
+    r[2 * v] = f.x;
+    r[2 * v + 1] = f.y;
+  }
+}
+template <int DKV>
+__device__ __forceinline__ void store_row(bf16* p, int lane, const float (&r)[DKV]) {
+  uint32_t w[DKV / 2];
+#pragma unroll
+  for (int v = 0; v < DKV / 2; ++v) w[v] = pack_bf16x2(r[2 * v], r[2 * v + 1]);
+  if constexpr (DKV == 2) {
+    *reinterpret_cast<uint32_t*>(p + lane * 2) = w[0];
+  } else if constexpr (DKV == 4) {
+    *reinterpret_cast<uint2*>(p + lane * 4) = make_uint2(w[0], w[1]);
+  } else {
+    *reinterpret_cast<uint4*>(p + lane * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+// a[u] = x . row(j + u) for four consecutive rows, summed over the warp; the four row loads are issued before any of the math
+template <int DKV>
+__device__ __forceinline__ void dot_rows4(const bf16* __restrict__ base, long ld, int lane, const float (&x)[DKV], float (&a)[4]) {
+  float r[4][DKV];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) load_row<DKV>(base + (long)u * ld, lane, r[u]);
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    a[u] = 0.f;
+#pragma unroll
+    for (int v = 0; v < DKV; ++v) a[u] += x[v] * r[u][v];
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) a[u] = warp_sum(a[u]);
+}
+// acc += sum_u c[u] * row(j + u) for four consecutive rows
+template <int DKV>
+__device__ __forceinline__ void axpy_rows4(const bf16* __restrict__ base, long ld, int lane, const float (&c)[4], float (&acc)[DKV]) {
+  float r[4][DKV];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) load_row<DKV>(base + (long)u * ld, lane, r[u]);
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int v = 0; v < DKV; ++v) acc[v] += c[u] * r[u][v];
 }
 
 // rows [i0, i1) of softmax(q k^T * scale [+ causal mask]) into S (row i at S + (i - i0) * Tk), one warp per row
@@ -48,7 +105,16 @@ __device__ void attn_probs(const bf16* __restrict__ q, long ld_q, const bf16* __
     float qr[DKV];
     load_row<DKV>(q + (long)i * ld_q, lane, qr);
     float* s = S + (long)(i - i0) * Tk;
-    for (int j = 0; j < Tk; ++j) {
+    int j = 0;
+    for (; j + 4 <= Tk; j += 4) {  // four key rows in flight: the loop is bound by the latency of the row loads otherwise
+      float a[4];
+      dot_rows4<DKV>(k + (long)j * ld_k, ld_k, lane, qr, a);
+      if (lane == 0) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) s[j + u] = (causal && j + u > i) ? kNegInf : a[u] * scale;
+      }
+    }
+    for (; j < Tk; ++j) {
       float kr[DKV];
       load_row<DKV>(k + (long)j * ld_k, lane, kr);
       float a = 0.f;
@@ -104,16 +170,19 @@ __global__ void __launch_bounds__(256) mha_small_fwd_kernel(const bf16* __restri
 #pragma unroll
     for (int c = 0; c < DKV; ++c) acc[c] = 0.f;
     const float* s = S + (long)i * Tk;
-    for (int j = 0; j < Tk; ++j) {
+    int j = 0;
+    for (; j + 4 <= Tk; j += 4) {
+      const float c4[4] = {s[j], s[j + 1], s[j + 2], s[j + 3]};
+      axpy_rows4<DKV>(v + (long)j * ld_v, ld_v, lane, c4, acc);
+    }
+    for (; j < Tk; ++j) {
       const float p = s[j];
-      if (p == 0.f) continue;  // warp-uniform (s[j] is a broadcast read)
       float vr[DKV];
       load_row<DKV>(v + (long)j * ld_v, lane, vr);
 #pragma unroll
       for (int c = 0; c < DKV; ++c) acc[c] += p * vr[c];
     }
-#pragma unroll
-    for (int c = 0; c < DKV; ++c) out[(long)i * ld_o + c * 32 + lane] = __float2bfloat16(acc[c]);
+    store_row<DKV>(out + (long)i * ld_o, lane, acc);
   }
 }
 
@@ -148,16 +217,23 @@ __global__ void __launch_bounds__(256) mha_small_bwd_kernel(const bf16* __restri
     float* d = D + (long)i * Tk;
     const float* p = P + (long)i * Tk;
     const float* m = mp + (long)i * Tk;
-    for (int j = 0; j < Tk; ++j) {
-      float a = 0.f;
-      if (m[j] != 0.f) {  // warp-uniform
-        float vr[DKV];
-        load_row<DKV>(v + (long)j * ld_v, lane, vr);
+    int j = 0;
+    for (; j + 4 <= Tk; j += 4) {
+      float a[4];
+      dot_rows4<DKV>(v + (long)j * ld_v, ld_v, lane, g, a);
+      if (lane == 0) {
 #pragma unroll
-        for (int c = 0; c < DKV; ++c) a += g[c] * vr[c];
-        a = warp_sum(a) * keep_scale;
+        for (int u = 0; u < 4; ++u) d[j + u] = m[j + u] != 0.f ? a[u] * keep_scale : 0.f;
       }
-      if (lane == 0) d[j] = a;
+    }
+    for (; j < Tk; ++j) {
+      float vr[DKV];
+      load_row<DKV>(v + (long)j * ld_v, lane, vr);
+      float a = 0.f;
+#pragma unroll
+      for (int c = 0; c < DKV; ++c) a += g[c] * vr[c];
+      a = warp_sum(a) * keep_scale;
+      if (lane == 0) d[j] = m[j] != 0.f ? a : 0.f;
     }
     __syncwarp();
     float delta = 0.f;
@@ -169,16 +245,18 @@ __global__ void __launch_bounds__(256) mha_small_bwd_kernel(const bf16* __restri
     float acc[DKV];
 #pragma unroll
     for (int c = 0; c < DKV; ++c) acc[c] = 0.f;
-    for (int j = 0; j < Tk; ++j) {
+    for (j = 0; j + 4 <= Tk; j += 4) {
+      const float c4[4] = {d[j], d[j + 1], d[j + 2], d[j + 3]};
+      axpy_rows4<DKV>(k + (long)j * ld_k, ld_k, lane, c4, acc);
+    }
+    for (; j < Tk; ++j) {
       const float ds = d[j];
-      if (ds == 0.f) continue;
       float kr[DKV];
       load_row<DKV>(k + (long)j * ld_k, lane, kr);
 #pragma unroll
       for (int c = 0; c < DKV; ++c) acc[c] += ds * kr[c];
     }
-#pragma unroll
-    for (int c = 0; c < DKV; ++c) dq[(long)i * ld_dq + c * 32 + lane] = __float2bfloat16(acc[c]);
+    store_row<DKV>(dq + (long)i * ld_dq, lane, acc);
   }
   __syncthreads();
   // dk_j = sum_i dS_ij q_i ; dv_j = sum_i map_ij dO_i
@@ -202,11 +280,8 @@ __global__ void __launch_bounds__(256) mha_small_bwd_kernel(const bf16* __restri
         for (int c = 0; c < DKV; ++c) av[c] += pm * g[c];
       }
     }
-#pragma unroll
-    for (int c = 0; c < DKV; ++c) {
-      dk_[(long)j * ld_dk + c * 32 + lane] = __float2bfloat16(ak[c]);
-      dv[(long)j * ld_dv + c * 32 + lane] = __float2bfloat16(av[c]);
-    }
+    store_row<DKV>(dk_ + (long)j * ld_dk, lane, ak);
+    store_row<DKV>(dv + (long)j * ld_dv, lane, av);
   }
 }
 
@@ -250,16 +325,19 @@ __global__ void __launch_bounds__(256) mha_rows_fwd_kernel(const bf16* __restric
   float acc[DKV];
 #pragma unroll
   for (int c = 0; c < DKV; ++c) acc[c] = 0.f;
-  for (int j = 0; j < Tk; ++j) {
+  int j = 0;
+  for (; j + 4 <= Tk; j += 4) {
+    const float c4[4] = {s[j], s[j + 1], s[j + 2], s[j + 3]};
+    axpy_rows4<DKV>(v + (long)j * ld_v, ld_v, lane, c4, acc);
+  }
+  for (; j < Tk; ++j) {
     const float p = s[j];
-    if (p == 0.f) continue;  // warp-uniform
     float vr[DKV];
     load_row<DKV>(v + (long)j * ld_v, lane, vr);
 #pragma unroll
     for (int c = 0; c < DKV; ++c) acc[c] += p * vr[c];
   }
-#pragma unroll
-  for (int c = 0; c < DKV; ++c) out[(long)i * ld_o + c * 32 + lane] = __float2bfloat16(acc[c]);
+  store_row<DKV>(out + (long)i * ld_o, lane, acc);
 }
 
 template <int DKV>
@@ -290,16 +368,23 @@ __global__ void __launch_bounds__(256) mha_rows_bwd_kernel(const bf16* __restric
   float* d = D + (long)warp * Tk;
   const float* p = P + (long)warp * Tk;
   const float* m = map + ((long)blockIdx.x * Tq + i) * Tk;
-  for (int j = 0; j < Tk; ++j) {
-    float a = 0.f;
-    if (m[j] != 0.f) {  // warp-uniform
-      float vr[DKV];
-      load_row<DKV>(v + (long)j * ld_v, lane, vr);
+  int j = 0;
+  for (; j + 4 <= Tk; j += 4) {
+    float a[4];
+    dot_rows4<DKV>(v + (long)j * ld_v, ld_v, lane, g, a);
+    if (lane == 0) {
 #pragma unroll
-      for (int c = 0; c < DKV; ++c) a += g[c] * vr[c];
-      a = warp_sum(a) * keep_scale;
+      for (int u = 0; u < 4; ++u) d[j + u] = m[j + u] != 0.f ? a[u] * keep_scale : 0.f;
     }
-    if (lane == 0) d[j] = a;
+  }
+  for (; j < Tk; ++j) {
+    float vr[DKV];
+    load_row<DKV>(v + (long)j * ld_v, lane, vr);
+    float a = 0.f;
+#pragma unroll
+    for (int c = 0; c < DKV; ++c) a += g[c] * vr[c];
+    a = warp_sum(a) * keep_scale;
+    if (lane == 0) d[j] = m[j] != 0.f ? a : 0.f;
   }
   __syncwarp();
   float delta = 0.f;
@@ -315,16 +400,18 @@ __global__ void __launch_bounds__(256) mha_rows_bwd_kernel(const bf16* __restric
   float acc[DKV];
 #pragma unroll
   for (int c = 0; c < DKV; ++c) acc[c] = 0.f;
-  for (int j = 0; j < Tk; ++j) {
+  for (j = 0; j + 4 <= Tk; j += 4) {
+    const float c4[4] = {d[j], d[j + 1], d[j + 2], d[j + 3]};
+    axpy_rows4<DKV>(k + (long)j * ld_k, ld_k, lane, c4, acc);
+  }
+  for (; j < Tk; ++j) {
     const float ds = d[j];
-    if (ds == 0.f) continue;
     float kr[DKV];
     load_row<DKV>(k + (long)j * ld_k, lane, kr);
 #pragma unroll
     for (int c = 0; c < DKV; ++c) acc[c] += ds * kr[c];
   }
-#pragma unroll
-  for (int c = 0; c < DKV; ++c) dq[(long)i * ld_dq + c * 32 + lane] = __float2bfloat16(acc[c]);
+  store_row<DKV>(dq + (long)i * ld_dq, lane, acc);
 }
 
 // dk_j = sum_i dS_ij q_i ; dv_j = sum_i map_ij dO_i for the kMhaKeyBlk keys of blockIdx.y, one warp per key at a time
@@ -336,6 +423,8 @@ __global__ void __launch_bounds__(256) mha_keys_bwd_kernel(const bf16* __restric
   extern __shared__ float sm_att[];
   float* sD = sm_att;                           // [Tq][kMhaKeyBlk]
   float* sM = sm_att + (long)Tq * kMhaKeyBlk;   // [Tq][kMhaKeyBlk]
+  bf16* sQ = reinterpret_cast<bf16*>(sM + (long)Tq * kMhaKeyBlk);   // [Tq][dk]: every key of the block walks all query rows
+  bf16* sG = sQ + (long)Tq * DKV * 32;                               // [Tq][dk] dO rows
   const int b = blockIdx.x / H, h = blockIdx.x % H;
   const int j0 = blockIdx.y * kMhaKeyBlk;
   constexpr int dk = DKV * 32;
@@ -351,6 +440,11 @@ __global__ void __launch_bounds__(256) mha_keys_bwd_kernel(const bf16* __restric
     sD[e] = in ? dp[(long)i * Tk + j0 + jj] : 0.f;
     sM[e] = in ? mp[(long)i * Tk + j0 + jj] : 0.f;
   }
+  for (int e = threadIdx.x; e < Tq * dk; e += blockDim.x) {
+    const int i = e / dk, c = e % dk;
+    sQ[e] = q[(long)i * ld_q + c];
+    sG[e] = d_out[(long)i * ld_o + c];
+  }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   for (int jj = warp; jj < kMhaKeyBlk && j0 + jj < Tk; jj += nw) {
@@ -362,23 +456,20 @@ __global__ void __launch_bounds__(256) mha_keys_bwd_kernel(const bf16* __restric
       const float pm = sM[i * kMhaKeyBlk + jj];
       if (x != 0.f) {
         float qr[DKV];
-        load_row<DKV>(q + (long)i * ld_q, lane, qr);
+        load_row<DKV>(sQ + (long)i * dk, lane, qr);
 #pragma unroll
         for (int c = 0; c < DKV; ++c) ak[c] += x * qr[c];
       }
       if (pm != 0.f) {
         float g[DKV];
-        load_row<DKV>(d_out + (long)i * ld_o, lane, g);
+        load_row<DKV>(sG + (long)i * dk, lane, g);
 #pragma unroll
         for (int c = 0; c < DKV; ++c) av[c] += pm * g[c];
       }
     }
     const int j = j0 + jj;
-#pragma unroll
-    for (int c = 0; c < DKV; ++c) {
-      dk_[(long)j * ld_dk + c * 32 + lane] = __float2bfloat16(ak[c]);
-      dv[(long)j * ld_dv + c * 32 + lane] = __float2bfloat16(av[c]);
-    }
+    store_row<DKV>(dk_ + (long)j * ld_dk, lane, ak);
+    store_row<DKV>(dv + (long)j * ld_dv, lane, av);
   }
 }
 
@@ -926,7 +1017,7 @@ int launch_mha_rows_bwd(const bf16* q, long ld_q, const bf16* k, long ld_k, cons
   mha_rows_bwd_kernel<DKV><<<dim3(B * H, (Tq + kMhaRows - 1) / kMhaRows), kMhaRows * 32, smem, s>>>(
       q, ld_q, k, ld_k, v, ld_v, d_out, ld_o, map, dq, ld_dq, ds, H, Tq, Tk, causal, scale, ks);
   FOCR_LAUNCH_CHECK();
-  const size_t smem2 = (size_t)Tq * kMhaKeyBlk * 8;
+  const size_t smem2 = (size_t)Tq * kMhaKeyBlk * 8 + (size_t)Tq * DKV * 32 * 2 * 2;
   FOCR_REQUIRE(smem2 <= 200 * 1024, "mha_small_bwd: Tq = %d too long for the key pass", Tq);
   FOCR_CHECK_CUDA(cudaFuncSetAttribute(mha_keys_bwd_kernel<DKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   mha_keys_bwd_kernel<DKV><<<dim3(B * H, (Tk + kMhaKeyBlk - 1) / kMhaKeyBlk), 256, smem2, s>>>(q, ld_q, d_out, ld_o, map, ds, dk,
@@ -962,6 +1053,8 @@ int focr_mha_small_fwd(const void* q, long ld_q, const void* k, long ld_k, const
   FOCR_REQUIRE(B >= 1 && H >= 1 && Tq >= 1 && Tk >= 1, "mha_small_fwd: B=%d H=%d Tq=%d Tk=%d", B, H, Tq, Tk);
   FOCR_REQUIRE(d_k == 64 || d_k == 128 || d_k == 256, "mha_small_fwd: d_k %d (64, 128 or 256)", d_k);
   FOCR_REQUIRE(!causal || Tq == Tk, "mha_small_fwd: the causal mask needs Tq == Tk");
+  FOCR_REQUIRE((ld_q | ld_k | ld_v | ld_o) % 8 == 0 && (((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)out) & 15) == 0,
+               "mha_small_fwd: rows must be 16-byte aligned (leading dimensions multiples of 8 elements)");
   FOCR_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "mha_small_fwd: p_drop %f", p_drop);
   const size_t smem = (size_t)Tq * Tk * 4;
   ProfScope _ps("mha_small_fwd", s);
@@ -996,6 +1089,9 @@ int focr_mha_small_bwd_ws(const void* q, long ld_q, const void* k, long ld_k, co
   FOCR_REQUIRE(B >= 1 && H >= 1 && Tq >= 1 && Tk >= 1, "mha_small_bwd: B=%d H=%d Tq=%d Tk=%d", B, H, Tq, Tk);
   FOCR_REQUIRE(d_k == 64 || d_k == 128 || d_k == 256, "mha_small_bwd: d_k %d (64, 128 or 256)", d_k);
   FOCR_REQUIRE(!causal || Tq == Tk, "mha_small_bwd: the causal mask needs Tq == Tk");
+  FOCR_REQUIRE((ld_q | ld_k | ld_v | ld_o | ld_dq | ld_dk | ld_dv) % 8 == 0 &&
+                   (((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)d_out | (uintptr_t)dq | (uintptr_t)dk | (uintptr_t)dv) & 15) == 0,
+               "mha_small_bwd: rows must be 16-byte aligned (leading dimensions multiples of 8 elements)");
   const size_t smem = (size_t)Tq * Tk * 8;
   ProfScope _ps("mha_small_bwd", s);
   const uint32_t th = th16_of(p_drop);

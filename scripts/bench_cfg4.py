@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def cpu_baseline(kind: str, batch: int = 8, steps: int = 2):
+def cpu_baseline(kind: str, batch: int = 8, steps: int = 2, width: int = 32):
     """the reference's own CPU path for this step, timed on the host cores: the oracle restatement (oracle/sld_oracle.py /
     ids_oracle.py, pinned to the unmodified reference modules) - forward, loss, backward, Adadelta - torch CPU fp32, all threads.
     The one place outside tests/ where oracle/ may run (bench `cpu_baseline` leg); a reported baseline, not a target."""
@@ -34,6 +34,8 @@ def cpu_baseline(kind: str, batch: int = 8, steps: int = 2):
         feats = IO.synth_text_features()
     else:
         image, strings = SO.synth_batch(batch)
+        if width != 32:   # 32 x width crops: width / 32 synthetic squares side by side
+            image = torch.cat([image] + [SO.synth_batch(batch, seed=1234 + 17 * i)[0] for i in range(1, width // 32)], dim=3)
         length, text_input, text_gt = SO.converter_stroke(strings)
 
     def step():
