@@ -21,6 +21,18 @@ namespace {
 
 constexpr float kNegInf = -INFINITY;
 
+// Dropout epoch: a device word XOR-ed into every dropout key of this file.  0 (the default) leaves the keys as the host passed
+// them - the masks the oracle twin (oracle/dropout_rng.py) reproduces.  A training step replayed as a CUDA graph has its seed
+// arguments frozen at capture time; the trainer then launches recog_epoch_advance_kernel at the head of every replay, so each
+// step draws fresh masks, and the backward kernels of the same replay see the same word.
+__device__ uint32_t g_recog_epoch = 0u;
+__global__ void recog_epoch_advance_kernel() {
+  uint32_t x = g_recog_epoch + 0x9E3779B9u;
+  x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
+  g_recog_epoch = x | 1u;
+}
+__global__ void recog_epoch_set_kernel(uint32_t v) { g_recog_epoch = v; }
+
 __device__ __forceinline__ bool keep16(uint32_t key, unsigned long long e, uint32_t th16) {
   const uint32_t h = drop_hash32(key, (uint32_t)(e >> 1));
   const uint32_t lane = (e & 1) ? (h >> 16) : (h & 0xFFFFu);
@@ -159,7 +171,7 @@ __global__ void __launch_bounds__(256) mha_small_fwd_kernel(const bf16* __restri
   float* mp = map + (long)blockIdx.x * Tq * Tk;
   for (int e = threadIdx.x; e < Tq * Tk; e += blockDim.x) {
     float p = S[e];
-    if (th16) p = keep16(key, (unsigned long long)blockIdx.x * Tq * Tk + e, th16) ? p * keep_scale : 0.f;
+    if (th16) p = keep16(key ^ g_recog_epoch, (unsigned long long)blockIdx.x * Tq * Tk + e, th16) ? p * keep_scale : 0.f;
     S[e] = p;
     mp[e] = p;
   }
@@ -315,9 +327,10 @@ __global__ void __launch_bounds__(256) mha_rows_fwd_kernel(const bf16* __restric
   __syncwarp();
   float* s = S + (long)warp * Tk;
   float* mp = map + ((long)blockIdx.x * Tq + i) * Tk;
+  const uint32_t epoch = g_recog_epoch;
   for (int j = lane; j < Tk; j += 32) {
     float p = s[j];
-    if (th16) p = keep16(key, ((unsigned long long)blockIdx.x * Tq + i) * Tk + j, th16) ? p * keep_scale : 0.f;
+    if (th16) p = keep16(key ^ epoch, ((unsigned long long)blockIdx.x * Tq + i) * Tk + j, th16) ? p * keep_scale : 0.f;
     s[j] = p;
     mp[j] = p;
   }
@@ -648,7 +661,7 @@ __global__ void text_embed_pe_kernel(const long long* __restrict__ idx, const fl
       const float div = expf((float)(cc & ~1) * (-logf(10000.f) / (float)E));
       const float ang = (float)pos * div;
       val = (cc & 1) ? cosf(ang) : sinf(ang);
-      if (th16) val = keep16(key, (unsigned long long)r * E + cc, th16) ? val * keep_scale : 0.f;
+      if (th16) val = keep16(key ^ g_recog_epoch, (unsigned long long)r * E + cc, th16) ? val * keep_scale : 0.f;
     }
   }
   out[i] = __float2bfloat16(val);
@@ -776,7 +789,7 @@ __global__ void dropout_kernel(const bf16* __restrict__ x, bf16* __restrict__ y,
                                float keep_scale) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  y[i] = keep16(key, (unsigned long long)i, th16) ? __float2bfloat16(ldbf(x + i) * keep_scale) : __float2bfloat16(0.f);
+  y[i] = keep16(key ^ g_recog_epoch, (unsigned long long)i, th16) ? __float2bfloat16(ldbf(x + i) * keep_scale) : __float2bfloat16(0.f);
 }
 // BasicBlock tail (transformer.py:69-71): y = relu(a + b), 8 elements per thread
 __global__ void add_relu_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ y, long n8) {
@@ -1042,6 +1055,18 @@ uint32_t th16_of(float p) {
 }  // namespace
 
 extern "C" {
+
+// dropout epoch of the recogniser kernels (see g_recog_epoch): set it (0 = keys exactly as passed), or advance it on the device
+int focr_recog_epoch_set(unsigned value, void* stream) {
+  recog_epoch_set_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(value);
+  FOCR_LAUNCH_CHECK();
+  return FOCR_OK;
+}
+int focr_recog_epoch_advance(void* stream) {
+  recog_epoch_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>();
+  FOCR_LAUNCH_CHECK();
+  return FOCR_OK;
+}
 
 // decoder attention core.  q (B*Tq, ld_q) / k, v (B*Tk, ld_k / ld_v) / out (B*Tq, ld_o) bf16, head h at columns h*d_k;
 // map fp32 (B, H, Tq, Tk) = dropout(softmax(q k^T / sqrt(d_k) [+ causal mask])) - the tensor the reference returns.

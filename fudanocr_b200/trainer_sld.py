@@ -15,10 +15,12 @@ from typing import Optional
 import torch
 import torch.distributed as dist
 
+from . import _lib as L
 from .model import recog_ops as ops
 from .model.transformer import Transformer
 
 _CHUNK = 65536   # elements per optimizer CTA: ~1100 CTAs for 71.7 M parameters
+_T_BUCKET = 8    # graph replay: the text length is padded up to a multiple of this, so a training run needs <= 4 graphs
 
 
 class _FlatAdadeltaTrainer:
@@ -26,8 +28,17 @@ class _FlatAdadeltaTrainer:
     buffer; `skip` names the parameters the reference forward never touches (their .grad stays None there and its optimiser
     skips them - which matters once weight decay is on)"""
 
-    def __init__(self, model, skip, lr, rho, eps, weight_decay, process_group):
+    def __init__(self, model, skip, lr, rho, eps, weight_decay, process_group, use_graph=True):
         self.model = model
+        # The step - ~780 kernel launches issued from Python through autograd - is replayed as ONE CUDA graph per input shape
+        # (forward, loss, backward, the gradient all-reduce, Adadelta): the first step with a new shape runs eagerly (it also
+        # sets every kernel attribute), the second is captured, later ones are a copy into static buffers + one graph launch.
+        # Seeds are frozen at capture time, so the graph advances the kernels' dropout epoch on the device (focr.h).
+        self.use_graph = bool(use_graph)
+        self._graphs = {}        # shape key -> (graph, static inputs, static outputs)
+        self._seen = {}          # shape key -> eager steps done
+        self._pool = None
+        self.kernel_launches = 0   # launches of focr kernels issued (eager) or replayed (graph nodes) by step()
         self.lr, self.rho, self.eps, self.weight_decay = lr, rho, eps, weight_decay
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
@@ -82,18 +93,87 @@ class _FlatAdadeltaTrainer:
         self.loss = loss.detach()
         return self.loss
 
+    # ---- graph replay -----------------------------------------------------------------------------------------------------------
+    def _graphable(self, image, lr):
+        return (self.use_graph and lr is None and image.is_cuda and not L.prof_enabled() and not L.status_checks()
+                and not torch.cuda.is_current_stream_capturing())
+
+    @staticmethod
+    def _pad_text(length, text_input, text_gt):
+        """static-shape form of the label tensors: T padded to a multiple of _T_BUCKET (positions t >= length[b] carry the start
+        symbol 0, exactly like the columns the reference's converter leaves untouched; the decoder is causal and the loss only
+        reads t < length[b], so the padded step computes the same loss and gradients), text_gt padded to B * T entries"""
+        B, T = text_input.shape
+        Tb = (T + _T_BUCKET - 1) // _T_BUCKET * _T_BUCKET
+        return B, T, Tb
+
+    def _run_graph(self, image, length, text_input, text_gt, body):
+        """body(image, length, text_input, text_gt) -> tuple of device scalars (total loss first); runs one eager step per new
+        shape, then captures, then replays.  Returns the tuple of (static) outputs."""
+        B, T, Tb = self._pad_text(length, text_input, text_gt)
+        key = (tuple(image.shape), image.dtype, Tb, getattr(self.model, "dropout_p", None))   # what the captured launches bake in
+        ent = self._graphs.get(key)
+        if ent is None:
+            if self._seen.get(key, 0) < 1:            # first step of this shape: eager (also the kernels' lazy initialisation)
+                self._seen[key] = 1
+                self._begin()
+                return None
+            dev = image.device
+            st_image = torch.empty_like(image, memory_format=torch.contiguous_format)
+            st_len = torch.zeros(B, dtype=torch.long, device=dev)
+            st_in = torch.zeros(B, Tb, dtype=torch.long, device=dev)
+            st_gt = torch.zeros(B * Tb, dtype=torch.long, device=dev)
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                st_image.copy_(image)
+            torch.cuda.current_stream().wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            if self._pool is None:
+                self._pool = torch.cuda.graph_pool_handle()    # graphs of different shapes replay one at a time: one pool
+            st_len.copy_(length)
+            st_in[:, :T].copy_(text_input)
+            st_gt[:text_gt.numel()].copy_(text_gt)
+            n0 = L.lib.focr_launch_count()
+            with torch.cuda.graph(g, pool=self._pool):
+                L.check(L.lib.focr_recog_epoch_advance(L.cur_stream()), "recog_epoch_advance")
+                self._begin()
+                outs = body(st_image, st_len, st_in, st_gt)
+            ent = (g, (st_image, st_len, st_in, st_gt), outs, int(L.lib.focr_launch_count() - n0))
+            self._graphs[key] = ent
+        g, (st_image, st_len, st_in, st_gt), outs, n_nodes = ent
+        self.kernel_launches += n_nodes
+        st_image.copy_(image, non_blocking=True)
+        st_len.copy_(length, non_blocking=True)
+        if Tb != T:
+            st_in.zero_()
+        st_in[:, :T].copy_(text_input, non_blocking=True)
+        st_gt[:text_gt.numel()].copy_(text_gt, non_blocking=True)
+        g.replay()
+        return outs
+
 
 class SLDTrainer(_FlatAdadeltaTrainer):
     def __init__(self, model: Transformer, lr: float = 1.0, rho: float = 0.9, eps: float = 1e-6, weight_decay: float = 0.0,
-                 process_group=None):
+                 process_group=None, use_graph: bool = True):
         if not isinstance(model, Transformer):
             raise TypeError("SLDTrainer drives fudanocr_b200.model.transformer.Transformer")
-        super().__init__(model, ("compress_attention_linear",), lr, rho, eps, weight_decay, process_group)
+        super().__init__(model, ("compress_attention_linear",), lr, rho, eps, weight_decay, process_group, use_graph)
 
     def step(self, image: torch.Tensor, length: torch.Tensor, text_input: torch.Tensor, text_gt: torch.Tensor) -> torch.Tensor:
         """one optimisation step on device-resident tensors; returns this rank's (device) loss, nothing blocks the host"""
-        self._begin()
-        return self._finish(self.model.loss(image, length, text_input, text_gt))
+        if self._graphable(image, None):
+            outs = self._run_graph(image, length, text_input, text_gt,
+                                   lambda im, ln, ti, gt: (self._finish(self.model.loss(im, ln, ti, gt)),))
+            if outs is not None:
+                self.loss = outs[0]
+                return self.loss
+        else:
+            self._begin()
+        n0 = L.lib.focr_launch_count()
+        out = self._finish(self.model.loss(image, length, text_input, text_gt))
+        self.kernel_launches += int(L.lib.focr_launch_count() - n0)
+        return out
 
 
 class IDSTrainer(_FlatAdadeltaTrainer):
@@ -101,17 +181,29 @@ class IDSTrainer(_FlatAdadeltaTrainer):
     text features; `lr` may be passed per step (the reference drives it with CosineAnnealingWarmRestarts, train.py:29)"""
 
     def __init__(self, model, text_features: torch.Tensor, lr: float = 1.0, rho: float = 0.9, eps: float = 1e-6,
-                 weight_decay: float = 1e-4, process_group=None):
+                 weight_decay: float = 1e-4, process_group=None, use_graph: bool = True):
         from .model.ids_transformer import Transformer as IDSTransformer
         if not isinstance(model, IDSTransformer):
             raise TypeError("IDSTrainer drives fudanocr_b200.model.ids_transformer.Transformer")
-        super().__init__(model, ("compress_attention_linear", "encoder.layer4"), lr, rho, eps, weight_decay, process_group)
+        super().__init__(model, ("compress_attention_linear", "encoder.layer4"), lr, rho, eps, weight_decay, process_group,
+                         use_graph)
         self.text_features = text_features.float().contiguous()
         self.text_features_padded = model.pad_text_features(self.text_features)
         self.loss_rec = self.loss_dis = None
 
     def step(self, image, length, text_input, text_gt, lr: Optional[float] = None) -> torch.Tensor:
-        self._begin()
-        loss, rec, dis = self.model.loss(image, length, text_input, text_gt, self.text_features, self.text_features_padded)
-        self.loss_rec, self.loss_dis = rec.detach(), dis.detach()
-        return self._finish(loss, lr)
+        """`lr` given per step (a scheduler value is a host number baked into the optimiser launch) keeps the eager path"""
+        def body(im, ln, ti, gt):
+            loss, rec, dis = self.model.loss(im, ln, ti, gt, self.text_features, self.text_features_padded)
+            return self._finish(loss, lr), rec.detach(), dis.detach()
+        if self._graphable(image, lr):
+            outs = self._run_graph(image, length, text_input, text_gt, body)
+            if outs is not None:
+                self.loss, self.loss_rec, self.loss_dis = outs
+                return self.loss
+        else:
+            self._begin()
+        n0 = L.lib.focr_launch_count()
+        self.loss, self.loss_rec, self.loss_dis = body(image, length, text_input, text_gt)
+        self.kernel_launches += int(L.lib.focr_launch_count() - n0)
+        return self.loss

@@ -265,6 +265,11 @@ int focr_resize_bicubic_normalize(const void* pixels, const long long* meta, int
  * focr_add_relu / focr_relu_bwd: BasicBlock tail :69-71 (out += residual; relu) and its gradient from the stored output.
  * focr_maxpool2x2_*: nn.MaxPool2d((2,2),(2,2)) :84,130 on NHWC maps; focr_dropout: nn.Dropout with a counter-hash mask - calling
  *   it on the gradient with the same (seed, stream_id) is its backward. */
+/* dropout epoch: a device word XOR-ed into every dropout key of the recogniser kernels (attention map, positional-encoding and
+ * FFN dropout).  0 = keys exactly as passed (default).  A step replayed as a CUDA graph freezes its seed arguments; the trainer
+ * captures focr_recog_epoch_advance at the head of the step so that every replay draws fresh masks (nn.Dropout's behaviour). */
+int focr_recog_epoch_set(unsigned value, void* stream);
+int focr_recog_epoch_advance(void* stream);
 int focr_mha_small_fwd(const void* q, long ld_q, const void* k, long ld_k, const void* v, long ld_v, void* out, long ld_o,
                        float* map, int B, int H, int d_k, int Tq, int Tk, int causal, float p_drop, unsigned seed,
                        unsigned stream_id, void* stream);

@@ -147,6 +147,53 @@ def test_sld_fused_trainer_step_and_reference_loop_agree():
         model(image.cpu(), length, text_input)
 
 
+def test_sld_graph_replay_follows_the_eager_trajectory_and_dropout_epoch_advances():
+    """SLDTrainer replays the step as one CUDA graph per input shape (first step eager, second captured): with dropout off the
+    graph trajectory must equal the eager one (text length 5 is padded to the bucket of 8 inside the graph: same loss, same
+    gradients); the dropout epoch the graph advances changes the masks of a fixed (seed, stream) and 0 restores them"""
+    SO, g, sd, model, image, length, text_input, text_gt = _setup()
+    from fudanocr_b200 import _lib as L
+    from fudanocr_b200.model import recog_ops as ops
+    from fudanocr_b200.model.transformer import Transformer
+    from fudanocr_b200.trainer_sld import SLDTrainer
+    twin = Transformer("stroke")
+    twin.load_state_dict(sd, strict=False)
+    twin = twin.to(DEV)
+    for m in (model, twin):
+        m.train()
+        m.dropout_p = 0.0
+    assert text_input.shape[1] % 8 != 0                      # the padding path is exercised
+    eager, graph = SLDTrainer(twin, use_graph=False), SLDTrainer(model, use_graph=True)
+    for it in range(4):
+        le = eager.step(image, length, text_input, text_gt)
+        lg = graph.step(image, length, text_input, text_gt)
+        torch.cuda.synchronize()
+        # (row order of the decoder's token matrix changes with the padding: reductions differ in the last bits, and Adadelta's
+        # first steps are sign-like, so the two runs agree to rounding noise, not bit for bit)
+        assert abs(float(le) - float(lg)) < 2e-3 * abs(float(le)) + 1e-6, (it, float(le), float(lg))
+    assert len(graph._graphs) == 1 and graph.kernel_launches > 4 * 300
+    worst = max(_rel(a.detach(), b.detach()) for (_, a), (_, b) in zip(model.named_parameters(), twin.named_parameters()))
+    assert worst < 5e-2, worst
+    # a changed dropout rate is a new graph key, not a stale replay
+    model.dropout_p = 0.1
+    l5 = graph.step(image, length, text_input, text_gt)
+    l6 = graph.step(image, length, text_input, text_gt)
+    l7 = graph.step(image, length, text_input, text_gt)
+    torch.cuda.synchronize()
+    assert len(graph._graphs) == 2 and all(torch.isfinite(x) for x in (l5, l6, l7))
+    # the epoch word: same (seed, stream) -> different mask after an advance, the original mask again at epoch 0
+    x = torch.ones(1 << 16, dtype=torch.bfloat16, device=DEV)
+    L.check(L.lib.focr_recog_epoch_set(0, L.cur_stream()))
+    m0 = ops.dropout(x, 0.1, 1234, 3)
+    L.check(L.lib.focr_recog_epoch_advance(L.cur_stream()))
+    m1 = ops.dropout(x, 0.1, 1234, 3)
+    L.check(L.lib.focr_recog_epoch_set(0, L.cur_stream()))
+    m2 = ops.dropout(x, 0.1, 1234, 3)
+    torch.cuda.synchronize()
+    assert torch.equal(m0, m2) and not torch.equal(m0, m1)
+    assert abs(float((m1 == 0).float().mean()) - 0.1) < 0.01
+
+
 # ---- batch 32: the conditioned regime (BatchNorm over 8192 positions per channel) ----------------------------------------------------
 def _setup_b32():
     from oracle import sld_oracle as SO, synth

@@ -364,4 +364,6 @@ def test_recogniser_ops_have_no_cpu_fallback():
         with pytest.raises(L.FocrError):
             c()
     with pytest.raises(ValueError):
-        Transformer("stroke").encode(torch.zeros(2, 3, 32, 320))      # 16 x 160 maps: not tiled yet
+        Transformer("stroke").encode(torch.zeros(2, 3, 32, 72))       # 16 x 36 maps do not cut into 128-pixel TMA boxes
+    with pytest.raises(L.FocrError):
+        Transformer("stroke").encode(torch.zeros(2, 3, 32, 320))      # 16 x 160 maps tile (32 x 4 boxes); CPU tensors still refused
