@@ -1025,13 +1025,6 @@ struct FusedBars {
   uint32_t tmem_slot;
 };
 
-// one lane of a converged warp (the MMA-issuing warps run their loops warp-wide so that tile indices, shared-memory
-// addresses and descriptors stay in uniform registers; only the tcgen05 instructions themselves are predicated)
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
-  return pred != 0;
-}
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }

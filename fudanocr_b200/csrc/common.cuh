@@ -353,6 +353,13 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_b
   d |= (uint64_t)layout << 61;
   return d;
 }
+// one lane of a converged warp (the MMA-issuing warps run their loops warp-wide so that tile indices, shared-memory
+// addresses and descriptors stay in uniform registers; only the tcgen05 instructions themselves are predicated)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 // kind::f16 instruction descriptor with explicit operand majors (0 = K-major, 1 = MN-major)
 __host__ __device__ constexpr uint32_t umma_idesc_bf16_ex(int M, int N, int a_mn, int b_mn) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |

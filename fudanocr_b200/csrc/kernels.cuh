@@ -66,6 +66,11 @@ int conv3x3_wgrad(const bf16* dy, const bf16* x, int B, int H, int Co, int shuf,
 // wgrad_tc.cu: tcgen05 weight + bias gradient of a linear layer with K = 128 inputs
 bool linear_wgrad_tc_supported(long T, int N, int K, long ld_dy, long ld_x);
 size_t linear_wgrad_tc_partial_bytes(int N);
+// wgrad_tc.cu: tcgen05 weight gradient of a 3x3 conv between 64-channel maps of width 64 (two taps stacked along M)
+bool conv3x3_wgrad_tc_supported(int H, int W);
+size_t conv3x3_wgrad_tc_partial_bytes();
+int conv3x3_wgrad_tc(const bf16* dy, long dy_pix, long dy_row, long dy_img, const bf16* x, int B, int H, int co_mul, int co_add,
+                     float* dw, float* partial, cudaStream_t s);
 int linear_wgrad_tc(const bf16* dy, long ld_dy, const bf16* x, long ld_x, long T, int N, float* dw, float* db, float* partial,
                     cudaStream_t s);
 

@@ -628,6 +628,15 @@ int focr_make_tmap_2d(CUtensorMap* out, const void* base, unsigned long long inn
   return FOCR_OK;
 }
 
+// 4-D bf16 NHWC map {channels, W, H, B} with element strides and a 128-byte-swizzled box (shared with wgrad_tc.cu)
+int focr_make_tmap_4d(CUtensorMap* out, const void* base, const unsigned long long dims[4], const unsigned long long strides_bytes[3],
+                      const unsigned box[4]) {
+  cuuint64_t d[4] = {dims[0], dims[1], dims[2], dims[3]};
+  cuuint64_t st[3] = {strides_bytes[0], strides_bytes[1], strides_bytes[2]};
+  cuuint32_t bx[4] = {box[0], box[1], box[2], box[3]};
+  return make_map(out, base, 4, d, st, bx);
+}
+
 int tc_gemm_block_n(int n_total) {
   if (n_total % 128 == 0) return 128;
   return 64;

@@ -59,5 +59,7 @@ int tc_gemm_launch(const bf16* const* a_ptrs, int n_amaps, long a_pix_stride /*e
 
 // 2-D bf16 tensor map {inner, outer} with row stride `row_bytes`, box {box_inner, box_outer} and a 32/64/128-byte
 // swizzle (shared with the attention kernels).
+int focr_make_tmap_4d(CUtensorMap* out, const void* base, const unsigned long long dims[4], const unsigned long long strides_bytes[3],
+                      const unsigned box[4]);
 int focr_make_tmap_2d(CUtensorMap* out, const void* base, unsigned long long inner, unsigned long long outer,
                       unsigned long long row_bytes, unsigned box_inner, unsigned box_outer, int swizzle_bytes);

@@ -254,6 +254,164 @@ int wg_num_sms() {
   return n;
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Weight gradient of a 3x3 convolution between two 64-channel NHWC maps of width 64 on the same tensor cores:
+//     dW[tap][ci][co] = sum_pixels X[p + tap][ci] * dY[p][co]            (autograd of nn.Conv2d, tbsrn.py:232,237; tsrn.py:80-86)
+// A = X (MN-major: the channel row of a pixel is 128 contiguous bytes, pixels are the MMA K dimension), B = dY (same).
+// A tile is two image rows (128 pixels).  X arrives as three TMA boxes of (2 + 2) rows x 64 pixels, one per horizontal shift
+// dx (zero-filled halo); the three vertical taps of a shift are 8 KB-aligned windows of the same box (64 pixels x 128 B per
+// row).  Two taps are STACKED along M: the descriptor's leading-dimension offset is simply the byte distance between the two
+// windows (8 KB for vertically adjacent taps, the box stride for horizontally adjacent ones), so five M = 128 accumulators of
+// 64 columns hold the nine 64 x 64 products (the last pair repeats a tap; its first half is ignored).
+//   pair 0..2: taps (dy -1, dx) over (dy 0, dx), dx = -1, 0, +1      pair 3: (dy +1, dx -1) over (dy +1, dx 0)
+//   pair 4   : (dy 0, dx +1) [ignored] over (dy +1, dx +1)
+// One persistent CTA per SM walks a contiguous range of tiles; partial[cta][tap][co][ci] fp32, summed by a second kernel.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kCvXBox = 4 * 64 * 128;            // one dx box: 4 rows x 64 pixels x 128 B
+constexpr int kCvYTile = 128 * 128;              // dY tile: 128 pixels x 128 B
+constexpr int kCvStage = 3 * kCvXBox + kCvYTile; // 112 KB
+constexpr int kCvStages = 2;
+constexpr int kCvThreads = 256;
+
+__global__ void __launch_bounds__(kCvThreads, 1)
+conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap mX, const __grid_constant__ CUtensorMap mY, int tiles_total,
+                        int tiles_per_img, float* __restrict__ partial) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kCvStages * kCvStage);
+  uint64_t* empty = full + kCvStages;
+  uint64_t* done = empty + kCvStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t_begin = (int)((long)tiles_total * blockIdx.x / gridDim.x);
+  const int t_end = (int)((long)tiles_total * (blockIdx.x + 1) / gridDim.x);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mX);
+    tma_prefetch_desc(&mY);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kCvStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = t_begin; tile < t_end; ++tile) {
+        const int b = tile / tiles_per_img, h0 = (tile - b * tiles_per_img) * 2;
+        mbar_wait_parked(&empty[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&full[stage], (uint32_t)kCvStage);
+        uint8_t* st = smem + stage * kCvStage;
+        for (int dxi = 0; dxi < 3; ++dxi) tma_load_4d(st + dxi * kCvXBox, &mX, &full[stage], 0, dxi - 1, h0 - 1, b);
+        tma_load_4d(st + 3 * kCvXBox, &mY, &full[stage], 0, 0, h0, b);
+        if (++stage == kCvStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // warp-uniform issue loop, one elected lane per instruction (no per-lane predication in the loop body)
+    constexpr uint32_t idesc = umma_idesc_bf16_ex(128, 64, 1, 1);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = t_begin; tile < t_end; ++tile) {
+      mbar_wait_parked(&full[stage], phase);
+      tc_fence_after();
+      const uint32_t st = smem_u32(smem + stage * kCvStage);
+      const uint64_t db = umma_desc(st + 3 * kCvXBox, 16, 1024, 2);
+      // window of tap (dy, dx): box dx + 1, rows (dy + 1) .. (dy + 2) of the 4-row box
+      const uint32_t a0[5] = {st + 0 * kCvXBox, st + 1 * kCvXBox, st + 2 * kCvXBox, st + 0 * kCvXBox + 2 * 8192,
+                              st + 2 * kCvXBox + 8192};
+      const uint32_t lbo[5] = {8192, 8192, 8192, (uint32_t)kCvXBox, 8192};
+      const uint32_t acc = tile > t_begin ? 1u : 0u;
+      if (elect_one()) {
+#pragma unroll
+        for (int pr = 0; pr < 5; ++pr) {
+          const uint64_t da = umma_desc(a0[pr], lbo[pr], 1024, 2);
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)  // 16 pixels = 16 rows of 128 bytes = 128 sixteen-byte units
+            tc_mma_bf16(tmem_base + pr * 64, da + 128 * ks, db + 128 * ks, idesc, acc | (ks > 0 ? 1u : 0u));
+        }
+        tc_commit(&empty[stage]);
+      }
+      __syncwarp();
+      if (++stage == kCvStages) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+    if (elect_one()) tc_commit(done);
+    __syncwarp();
+  } else if (warp >= 4) {
+    const int ew = warp & 3;
+    mbar_wait_parked(done, 0);
+    tc_fence_after();
+    const bool has_work = t_end > t_begin;
+    const int row = ew * 32 + lane;            // TMEM lane: rows 0-63 = first tap of the pair, 64-127 = second
+    const int half = row >> 6, ci = row & 63;
+    // tap index (dy + 1) * 3 + (dx + 1) of each pair's two halves; -1 = ignored
+    const int tap_of[5][2] = {{0, 3}, {1, 4}, {2, 5}, {6, 7}, {-1, 8}};
+    float* out = partial + (long)blockIdx.x * 9 * 4096;
+#pragma unroll 1
+    for (int pr = 0; pr < 5; ++pr) {
+      const int tap = tap_of[pr][half];
+      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + pr * 64;
+#pragma unroll 1
+      for (int c0 = 0; c0 < 64; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(taddr + c0, r);
+        tmem_ld_wait();
+        if (tap >= 0) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)   // [tap][co][ci]: the 32 lanes of a warp write 32 consecutive ci
+            out[(long)tap * 4096 + (c0 + j) * 64 + ci] = has_work ? __uint_as_float(r[j]) : 0.f;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// dW[co][ci][tap] (torch layout [Co][64][3][3], Co = 64 * groups) = sum_cta partial[cta][tap][co][ci]
+__global__ void conv3x3_wgrad_tc_reduce_kernel(const float* __restrict__ partial, int P, int co_mul, int co_add,
+                                               float* __restrict__ dw) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 9 * 4096) return;
+  double s = 0.0;
+  int p = 0;
+  for (; p + 8 <= P; p += 8) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = __ldcg(partial + (long)(p + u) * 9 * 4096 + i);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) s += v[u];
+  }
+  for (; p < P; ++p) s += __ldcg(partial + (long)p * 9 * 4096 + i);
+  const int ci = i & 63, co = (i >> 6) & 63, tap = i >> 12;
+  dw[((long)(co * co_mul + co_add) * 64 + ci) * 9 + tap] = (float)s;
+}
+
 }  // namespace
 
 bool linear_wgrad_tc_supported(long T, int N, int K, long ld_dy, long ld_x) {
@@ -289,6 +447,48 @@ int linear_wgrad_tc(const bf16* dy, long ld_dy, const bf16* x, long ld_x, long T
   if (dbg < 0) dbg = getenv("FOCR_WGRAD_DEBUG") ? atoi(getenv("FOCR_WGRAD_DEBUG")) : 0;  // tuning aid: bit0 skip W MMAs, bit1 skip bias MMAs
   if (dbg & 4) stages = 2;
   linear_wgrad_tc_kernel<<<grid, kThreads, smem, s>>>(mY, mX, n_atoms, tiles, stages, pw, pb, dw, db, ctr, dbg);
+  FOCR_LAUNCH_CHECK();
+  return FOCR_OK;
+}
+
+// ---- 3x3 conv weight gradient (64 -> 64 channels per group, W = 64 maps) -----------------------------------------------------------
+bool conv3x3_wgrad_tc_supported(int H, int W) {
+  static int off = -1;
+  if (off < 0) off = getenv("FOCR_CONV_WGRAD_LEGACY") ? 1 : 0;   // tuning / cross-check knob: keep the mma.sync kernel
+  return !off && W == 64 && H % 2 == 0 && H >= 2;
+}
+size_t conv3x3_wgrad_tc_partial_bytes() { return (size_t)wg_num_sms() * 9 * 4096 * 4; }
+
+// x (B, H, 64, 64) NHWC bf16; dy: 64-channel map addressed through element strides (dy_pix, dy_row, dy_img) - a plain NHWC
+// map, or one sub-pixel plane of the PixelShuffle layout; dw fp32 torch layout: element (co * co_mul + co_add, ci, tap)
+int conv3x3_wgrad_tc(const bf16* dy, long dy_pix, long dy_row, long dy_img, const bf16* x, int B, int H, int co_mul, int co_add,
+                     float* dw, float* partial, cudaStream_t s) {
+  FOCR_REQUIRE(conv3x3_wgrad_tc_supported(H, 64), "conv3x3_wgrad_tc: H=%d", H);
+  CUtensorMap mX, mY;
+  {
+    const unsigned long long dims[4] = {64, 64, (unsigned long long)H, (unsigned long long)B};
+    const unsigned long long str[3] = {64 * 2, 64 * 64 * 2, (unsigned long long)H * 64 * 64 * 2};
+    const unsigned box[4] = {64, 64, 4, 1};
+    TRY_RC(focr_make_tmap_4d(&mX, x, dims, str, box));
+  }
+  {
+    const unsigned long long dims[4] = {64, 64, (unsigned long long)H, (unsigned long long)B};
+    const unsigned long long str[3] = {(unsigned long long)dy_pix * 2, (unsigned long long)dy_row * 2, (unsigned long long)dy_img * 2};
+    const unsigned box[4] = {64, 64, 2, 1};
+    TRY_RC(focr_make_tmap_4d(&mY, dy, dims, str, box));
+  }
+  const int tiles_per_img = H / 2;
+  const int tiles = B * tiles_per_img;
+  const int grid = tiles < wg_num_sms() ? tiles : wg_num_sms();
+  const size_t smem = (size_t)kCvStages * kCvStage + 256 + 1024;
+  static bool attr = false;
+  if (!attr) {
+    FOCR_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  conv3x3_wgrad_tc_kernel<<<grid, kCvThreads, smem, s>>>(mX, mY, tiles, tiles_per_img, partial);
+  FOCR_LAUNCH_CHECK();
+  conv3x3_wgrad_tc_reduce_kernel<<<focr_cdiv(9 * 4096, 256), 256, 0, s>>>(partial, grid, co_mul, co_add, dw);
   FOCR_LAUNCH_CHECK();
   return FOCR_OK;
 }

@@ -270,7 +270,7 @@ def test_linear_wgrad_bias_fused_tcgen05(M, N):
     assert torch.equal(dw, outs[0][0])
 
 
-@pytest.mark.parametrize("B,Co,shuf", [(2, 64, 0), (3, 128, 0), (2, 256, 1), (20, 64, 0)])
+@pytest.mark.parametrize("B,Co,shuf", [(2, 64, 0), (3, 128, 0), (2, 256, 1), (20, 64, 0), (37, 64, 0), (256, 64, 0), (33, 256, 1)])
 def test_conv3x3_wgrad(B, Co, shuf):
     L = _L()
     H, W = 16, 64
