@@ -108,6 +108,49 @@ def test_train_forward_backward_vs_oracle(env, stn, B):
     assert abs(gn - info["grad_norm"].item()) < 0.03 * info["grad_norm"].item()
 
 
+@pytest.mark.parametrize("stn", [False, True])
+def test_train_forward_backward_conditioned_absolute(env, stn):
+    """north_star's 1e-2 bf16 contract asserted absolutely in train mode, at weights conditioned by 50 deterministic Adam steps of
+    the fp32 oracle (see tests/test_gpu_tbsrn.py::test_train_forward_backward_conditioned_absolute for the reasoning)"""
+    TS, synth = env["TS"], env["synth"]
+    B = 32
+    lr, hr = synth.synth_images(B)
+    lr, hr = lr.to(DEV), hr.to(DEV)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    det, bench_ = torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark
+    torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark = True, False
+    try:
+        sd = {k: v.to(DEV) for k, v in env["sd"].items()}
+        state = {}
+        for _ in range(50):
+            sd, _info = TS.train_step(sd, lr, hr, state, stn=True)
+        _, info = TS.train_step(sd, lr, hr, {}, stn=stn)
+    finally:
+        torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark = det, bench_
+    m = env["TSRN"](STN=stn).to(DEV)
+    m.load_state_dict({k: v for k, v in sd.items() if stn or not (k.startswith("stn_head") or k.startswith("tps"))})
+    m.train()
+    sr = m(lr)
+    loss = F.mse_loss(sr, hr)
+    (loss * 100).backward()
+    torch.cuda.synchronize()
+    grads = {k: p.grad for k, p in m.named_parameters() if p.grad is not None}
+    gmax = max(g.norm().item() for g in info["grads"].values())
+    rel = {k: _rel(grads[k], g) for k, g in info["grads"].items()
+           if k in grads and g.norm().item() >= 1e-4 * gmax and not k.startswith("stn_head.")}
+    gn = torch.sqrt(sum((g.double() ** 2).sum() for g in grads.values())).item()
+    rep = {"sr_rel_l2": _rel(sr.detach(), info["sr"]), "loss": [loss.item(), info["mse"].item()],
+           "grad_rel_median": statistics.median(rel.values()), "grad_rel_max": max(rel.values()),
+           "grad_rel_worst": max(rel, key=rel.get), "grad_norm": [gn, info["grad_norm"].item()]}
+    REPORT[f"train_conditioned_stn{int(stn)}"] = rep
+    _dump()
+    assert rep["sr_rel_l2"] < 1e-2, rep
+    assert abs(loss.item() - info["mse"].item()) < 5e-3 * info["mse"].item(), rep
+    assert rep["grad_rel_median"] < 8e-2, rep      # measured 4.5e-2 / 6.5e-2 (the BiGRU recurrences; TBSRN: 3.0e-2)
+    assert abs(gn - info["grad_norm"].item()) < 0.03 * info["grad_norm"].item(), rep
+
+
 def test_trainer_steps_and_full_size(env):
     """fused step on TSRN: loss falls, bit-reproducible, B = 256 (BASELINE configs[2] uses TSRN at batch 256)"""
     from fudanocr_b200.trainer import TBSRNTrainer
