@@ -83,6 +83,8 @@ _SIGS = {
     "focr_ctc_loss_workspace_bytes": (_sz, [_i, _i, _i]),
     "focr_ctc_loss": (C.c_int, [_fp, _i, _i, _i, _vp, _i, _vp, _vp, _i, _i, _i, _f, _fp, _fp, _fp, _vp, _sz, _vp]),
     "focr_ctc_loss_status": (C.c_int, [_vp, _i, _i, _i, C.POINTER(C.c_int), _vp]),
+    "focr_clip_contrastive_workspace_bytes": (_sz, [_i, _i]),
+    "focr_clip_contrastive_loss": (C.c_int, [_fp, _fp, _fp, _vp, _i, _i, _fp, _fp, _fp, _fp, _vp, _vp, _sz, _vp]),
     "focr_recog_epoch_set": (C.c_int, [_u, _vp]),
     "focr_recog_epoch_advance": (C.c_int, [_vp]),
     "focr_mha_small_fwd": (C.c_int, [_vp, _l, _vp, _l, _vp, _l, _vp, _l, _fp, _i, _i, _i, _i, _i, _i, _f, _u, _u, _vp]),

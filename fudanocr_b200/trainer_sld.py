@@ -94,8 +94,8 @@ class _FlatAdadeltaTrainer:
         return self.loss
 
     # ---- graph replay -----------------------------------------------------------------------------------------------------------
-    def _graphable(self, image, lr):
-        return (self.use_graph and lr is None and image.is_cuda and not L.prof_enabled() and not L.status_checks()
+    def _graphable(self, image):
+        return (self.use_graph and image.is_cuda and not L.prof_enabled() and not L.status_checks()
                 and not torch.cuda.is_current_stream_capturing())
 
     @staticmethod
@@ -107,11 +107,13 @@ class _FlatAdadeltaTrainer:
         Tb = (T + _T_BUCKET - 1) // _T_BUCKET * _T_BUCKET
         return B, T, Tb
 
-    def _run_graph(self, image, length, text_input, text_gt, body):
+    def _run_graph(self, image, length, text_input, text_gt, body, lr=None):
         """body(image, length, text_input, text_gt) -> tuple of device scalars (total loss first); runs one eager step per new
         shape, then captures, then replays.  Returns the tuple of (static) outputs."""
         B, T, Tb = self._pad_text(length, text_input, text_gt)
-        key = (tuple(image.shape), image.dtype, Tb, getattr(self.model, "dropout_p", None))   # what the captured launches bake in
+        # what the captured launches bake in; a per-step learning rate (image-ids-CTR drives it with a per-EPOCH scheduler,
+        # train.py:29,92) is a host number in the optimiser launch: one graph per value, the oldest dropped beyond eight
+        key = (tuple(image.shape), image.dtype, Tb, getattr(self.model, "dropout_p", None), lr)
         ent = self._graphs.get(key)
         if ent is None:
             if self._seen.get(key, 0) < 1:            # first step of this shape: eager (also the kernels' lazy initialisation)
@@ -140,6 +142,8 @@ class _FlatAdadeltaTrainer:
                 self._begin()
                 outs = body(st_image, st_len, st_in, st_gt)
             ent = (g, (st_image, st_len, st_in, st_gt), outs, int(L.lib.focr_launch_count() - n0))
+            if len(self._graphs) >= 8:
+                del self._graphs[next(iter(self._graphs))]
             self._graphs[key] = ent
         g, (st_image, st_len, st_in, st_gt), outs, n_nodes = ent
         self.kernel_launches += n_nodes
@@ -162,7 +166,7 @@ class SLDTrainer(_FlatAdadeltaTrainer):
 
     def step(self, image: torch.Tensor, length: torch.Tensor, text_input: torch.Tensor, text_gt: torch.Tensor) -> torch.Tensor:
         """one optimisation step on device-resident tensors; returns this rank's (device) loss, nothing blocks the host"""
-        if self._graphable(image, None):
+        if self._graphable(image):
             outs = self._run_graph(image, length, text_input, text_gt,
                                    lambda im, ln, ti, gt: (self._finish(self.model.loss(im, ln, ti, gt)),))
             if outs is not None:
@@ -192,12 +196,12 @@ class IDSTrainer(_FlatAdadeltaTrainer):
         self.loss_rec = self.loss_dis = None
 
     def step(self, image, length, text_input, text_gt, lr: Optional[float] = None) -> torch.Tensor:
-        """`lr` given per step (a scheduler value is a host number baked into the optimiser launch) keeps the eager path"""
+        """`lr`: this step's learning rate (None = the constructor's); constant within an epoch under the reference's scheduler"""
         def body(im, ln, ti, gt):
             loss, rec, dis = self.model.loss(im, ln, ti, gt, self.text_features, self.text_features_padded)
             return self._finish(loss, lr), rec.detach(), dis.detach()
-        if self._graphable(image, lr):
-            outs = self._run_graph(image, length, text_input, text_gt, body)
+        if self._graphable(image):
+            outs = self._run_graph(image, length, text_input, text_gt, body, None if lr is None else float(lr))
             if outs is not None:
                 self.loss, self.loss_rec, self.loss_dis = outs
                 return self.loss

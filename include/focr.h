@@ -265,6 +265,16 @@ int focr_resize_bicubic_normalize(const void* pixels, const long long* meta, int
  * focr_add_relu / focr_relu_bwd: BasicBlock tail :69-71 (out += residual; relu) and its gradient from the stored output.
  * focr_maxpool2x2_*: nn.MaxPool2d((2,2),(2,2)) :84,130 on NHWC maps; focr_dropout: nn.Dropout with a counter-hash mask - calling
  *   it on the gradient with the same (seed, stream_id) is its backward. */
+/* Contrastive head of the CCR-CLIP pre-training stage - image-ids-CTR/CCR-CLIP/model.py:209-222 (L2-normalise both feature sets,
+ * logit_scale.exp()) and main.py:98-110 (logits_per_image = scale * I T^T, logits_per_text its transpose, loss = (CE(logits_per_image,
+ * gt) + CE(logits_per_text, gt)) / 2) - value and gradients in one call.  image / text: fp32 (B, D) UN-normalised tower outputs (on a
+ * data-parallel run: the all-gathered global batch), logit_scale: the log-parameter (1 float, device), gt: int64 (B), gt[i] = first
+ * sample with sample i's label (main.py:103-105).  d_image / d_text (B, D) + d_logit_scale may be NULL.  *status (optional) is set
+ * when a target is outside [0, B).  The towers themselves are not part of this library (out of scope). */
+size_t focr_clip_contrastive_workspace_bytes(int B, int D);
+int focr_clip_contrastive_loss(const float* image, const float* text, const float* logit_scale, const long long* gt, int B, int D,
+                               float* loss, float* d_image, float* d_text, float* d_logit_scale, int* status, void* ws,
+                               size_t ws_bytes, void* stream);
 /* dropout epoch: a device word XOR-ed into every dropout key of the recogniser kernels (attention map, positional-encoding and
  * FFN dropout).  0 = keys exactly as passed (default).  A step replayed as a CUDA graph freezes its seed arguments; the trainer
  * captures focr_recog_epoch_advance at the head of the step so that every replay draws fresh masks (nn.Dropout's behaviour). */

@@ -116,6 +116,11 @@ def test_ids_eval_forward_fused_trainer_and_reference_loop():
     l2 = tr.step(image, length, text_input, text_gt, lr=0.5)
     torch.cuda.synchronize()
     assert torch.isfinite(l2)
+    # a per-step learning rate is part of the graph key: first step at 0.25 eager, second captured, third replayed
+    for _ in range(3):
+        l3 = tr.step(image, length, text_input, text_gt, lr=0.25)
+    torch.cuda.synchronize()
+    assert torch.isfinite(l3) and torch.isfinite(tr.loss_rec) and any(k[-1] == 0.25 for k in tr._graphs)
     model.dropout_p = 0.1
     assert torch.isfinite(tr.step(image, length, text_input, text_gt))
     names = set(tr.names)

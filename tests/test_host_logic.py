@@ -367,3 +367,68 @@ def test_recogniser_ops_have_no_cpu_fallback():
         Transformer("stroke").encode(torch.zeros(2, 3, 32, 72))       # 16 x 36 maps do not cut into 128-pixel TMA boxes
     with pytest.raises(L.FocrError):
         Transformer("stroke").encode(torch.zeros(2, 3, 32, 320))      # 16 x 160 maps tile (32 x 4 boxes); CPU tensors still refused
+
+
+CLIP_WORKER = textwrap.dedent("""
+    import os, sys, torch, torch.distributed as dist
+    sys.path.insert(0, %r)
+    from fudanocr_b200.loss import clip_contrastive as CC
+    from oracle import clip_oracle as CO
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%%s" %% sys.argv[1], rank=int(sys.argv[2]), world_size=2)
+    rank = dist.get_rank()
+    torch.set_num_threads(2)
+
+    def fused_standin(image, text, logit_scale, gt, want_grad):      # the kernel's contract, in torch (test stand-in: no GPU here)
+        with torch.enable_grad():                                     # (called from inside Function.forward)
+            i, t, s = (x.detach().double().requires_grad_(True) for x in (image, text, logit_scale))
+            loss, _ = CO.contrastive_loss(i, t, s[0], gt)
+            loss.backward()
+        return loss.detach().float().reshape(1), i.grad.float(), t.grad.float(), s.grad.float()
+    CC._fused = fused_standin
+
+    torch.manual_seed(0)
+    B, Din, D = 8, 12, 16
+    x_img, x_txt = torch.randn(B, Din), torch.randn(B, Din)
+    labels = list("abacbdae")
+    gt = CC.ground_truth_from_labels(labels)
+
+    def towers():
+        torch.manual_seed(1)
+        return torch.nn.Linear(Din, D), torch.nn.Linear(Din, D), torch.nn.Parameter(torch.tensor(2.0))
+    # single process, whole batch (what nn.DataParallel's main device computes in the reference)
+    fi, ft, ls = towers()
+    ref, _ = CO.contrastive_loss(fi(x_img), ft(x_txt), ls, gt)
+    ref.backward()
+    for mode in ("sum", "mean"):
+        gi, gtw, gls = towers()
+        sl = slice(rank * 4, rank * 4 + 4)
+        loss = CC.clip_contrastive_loss(gi(x_img[sl]), gtw(x_txt[sl]), gls, gt, grad_reduce=mode)
+        loss.backward()
+        assert abs(float(loss) - float(ref)) < 1e-5, (float(loss), float(ref))
+        for p, q in ((gi.weight, fi.weight), (gi.bias, fi.bias), (gtw.weight, ft.weight), (gls, ls)):
+            g = p.grad.clone()
+            dist.all_reduce(g)                     # what the data-parallel trainer does with the flat gradient
+            if mode == "mean":
+                g /= 2
+            assert torch.allclose(g, q.grad, rtol=1e-4, atol=1e-6), (mode, (g - q.grad).abs().max())
+    dist.destroy_process_group()
+    print("ok", rank)
+""")
+
+
+def test_two_rank_gloo_clip_contrastive_head(tmp_path):
+    """the data-parallel form of the CCR-CLIP contrastive head: all-gathered features, the global B x B loss on every rank, local
+    gradient rows - after the usual gradient all-reduce (sum, or mean) every parameter gradient equals the single-process one"""
+    script = tmp_path / "clip_worker.py"
+    script.write_text(CLIP_WORKER % ROOT)
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    procs = [subprocess.Popen([sys.executable, str(script), str(port), str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=300)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+        assert "ok" in o

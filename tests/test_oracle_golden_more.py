@@ -1,4 +1,5 @@
 """CPU: the CRNN and TSRN oracle restatements vs golden vectors recorded from the real reference modules."""
+import os
 import hashlib
 
 import torch
@@ -180,3 +181,47 @@ def test_ctc_oracle_vs_torch_golden():
     _, nll3, _ = CO.ctc_loss(x, np.array([[1, 1]]), [3], [2], 0, "sum")
     lp = CO.log_softmax(x)[:, 0]
     assert abs(nll3[0] + (lp[0, 1] + lp[1, 0] + lp[2, 1])) < 1e-12
+
+
+def test_clip_oracle_matches_the_reference_loop():
+    """oracle/clip_oracle.py against the reference's OWN code: CLIP.forward (image-ids-CTR/CCR-CLIP/model.py:209-222, the real class
+    with a small text tower) produces the normalised features and logit_scale.exp(); lines 99-107 of main.py - read from the
+    checkout and executed verbatim, minus .cuda() - produce the loss.  Skipped where the reference checkout is absent."""
+    import importlib.util
+    import sys
+    import textwrap
+    ref = "/root/reference/image-ids-CTR/CCR-CLIP"
+    if not os.path.isdir(ref):
+        pytest.skip("reference checkout not present")
+    from oracle import clip_oracle as CO
+    sys.path.insert(0, ref)
+    try:
+        spec = importlib.util.spec_from_file_location("ccr_clip_model_ref", os.path.join(ref, "model.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        torch.manual_seed(0)
+        model = mod.CLIP(embed_dim=2048, context_length=30, vocab_size=40, transformer_width=64, transformer_heads=2,
+                         transformer_layers=1).eval()
+    finally:
+        sys.path.remove(ref)
+        sys.modules.pop("resnet50", None)
+    B = 6
+    image = torch.rand(B, 3, 32, 32)
+    text = torch.randint(1, 39, (B, 30))
+    text[:, -1] = 39                                          # the end token carries the arg-max (model.py:205)
+    label = ["a", "b", "a", "c", "b", "d"]
+    with torch.no_grad():
+        image_features, text_features, logit_scale = model(image, text)
+        raw_i, raw_t = model.encode_image(image), model.encode_text(text)
+    src = open(os.path.join(ref, "main.py")).read().split("\n")
+    lines = textwrap.dedent("\n".join(src[98:107])).replace(".cuda()", "")       # main.py:99-107
+    assert lines.lstrip().startswith("logits_per_image") and "total_loss" in lines
+    env = dict(torch=torch, image=image, label=label, image_features=image_features, text_features=text_features,
+               logit_scale=logit_scale.reshape(1),           # nn.DataParallel gathers the 0-dim scale into a vector (main.py:98 indexes it)
+               loss_img=torch.nn.CrossEntropyLoss(), loss_txt=torch.nn.CrossEntropyLoss())
+    exec(lines, env)
+    gt = CO.ground_truth(label)
+    assert torch.equal(gt, env["ground_truth"]) and gt.tolist() == [0, 1, 0, 3, 1, 5]
+    loss, logits = CO.contrastive_loss(raw_i, raw_t, model.logit_scale.detach(), gt)
+    assert torch.allclose(logits, env["logits_per_image"], rtol=1e-5, atol=1e-6)
+    assert abs(float(loss) - float(env["total_loss"])) < 1e-6 * abs(float(env["total_loss"])) + 1e-7
