@@ -40,8 +40,8 @@ WORKLOAD = {
     2: "TBSRN train step (STN on, dropout 0.1, MSE loss x100, clip 0.25, Adam 1e-4), LR 16x64 -> HR 32x128 (BASELINE configs[1])",
     3: "TSRN (STN) + StrokeFocusLoss(lambda 50) train step (frozen recogniser: HR fwd, SR fwd, SR input-gradient chain), "
        "clip 0.25, Adam (BASELINE configs[2])",
-    4: "stroke-level-decomposition Transformer('stroke') train step, 32x32 crops (the reference's size; 32x320 per "
-       "--width 320), CE + Adadelta(lr 1, rho 0.9), dropout 0.1 (BASELINE configs[3])",
+    4: "stroke-level-decomposition Transformer('stroke') train step on 32 x --width crops (320 = BASELINE configs[3]; the "
+       "reference itself trains on 32x32, --width 32), CE + Adadelta(lr 1, rho 0.9), dropout 0.1, replayed as one CUDA graph",
     5: "TBSRN eval -> PSNR/SSIM -> bicubic+gray -> CRNN -> greedy CTC decode, strings on the host (BASELINE configs[4])",
 }
 
@@ -124,7 +124,8 @@ def parse_args():
                     help="BASELINE.json configuration, 1-based (2 = configs[1], the headline)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--batch", type=int, default=0, help=argparse.SUPPRESS)   # per-GPU override (tuning runs)
-    ap.add_argument("--width", type=int, default=32, help="config 4: crop width (32 = reference, 320 = BASELINE variant)")
+    ap.add_argument("--width", type=int, default=320,
+                    help="config 4: crop width (320 = BASELINE configs[3]; 32 = the size the reference itself trains on, SURVEY D4)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-strong-point", action="store_true", help="config 2: skip the extra strong-scaling measurement")
     return ap.parse_args()
@@ -159,10 +160,32 @@ class TBSRNTrain:
     def step(self, i):
         return self.trainer.step(self.lr, self.hr, seed=i)
 
+    def _upload(self, slot):
+        """pinned host batch -> device buffers of `slot` on the copy stream (what a prefetching loader does)"""
+        torch = self.torch
+        with torch.cuda.stream(self._copy_stream):
+            self._dev[slot][0].copy_(self.lr_h, non_blocking=True)
+            self._dev[slot][1].copy_(self.hr_h, non_blocking=True)
+            self._ready[slot].record(self._copy_stream)
+
     def step_e2e(self, i):
-        self.lr.copy_(self.lr_h, non_blocking=True)
-        self.hr.copy_(self.hr_h, non_blocking=True)
-        loss = self.trainer.step(self.lr, self.hr, seed=i)
+        # every step: one H2D copy of a batch (15.7 MB from pinned memory) and one D2H read of the loss, both inside the timed
+        # region.  Double-buffered: the batch of step i + 1 is uploaded on a copy stream while step i computes (the loss read
+        # below has retired step i - 1, the last reader of that buffer, before the upload is issued).
+        torch = self.torch
+        if not hasattr(self, "_dev"):
+            self._copy_stream = torch.cuda.Stream()
+            self._dev = [(self.lr, self.hr), (torch.empty_like(self.lr), torch.empty_like(self.hr))]
+            self._ready = [torch.cuda.Event(), torch.cuda.Event()]
+            self._uploaded = -1
+        slot = i & 1
+        if self._uploaded != i:                       # first step (nothing prefetched yet)
+            self._copy_stream.wait_stream(torch.cuda.current_stream())
+            self._upload(slot)
+        torch.cuda.current_stream().wait_event(self._ready[slot])
+        loss = self.trainer.step(self._dev[slot][0], self._dev[slot][1], seed=i)
+        self._upload(slot ^ 1)
+        self._uploaded = i + 1
         return loss.cpu()  # the scalar a user logs every step (super_resolution.py:74-76)
 
     def result(self):
@@ -378,7 +401,7 @@ class SLDTrain:
         sec = batch / r["value"]
         return r["value"], r["cores"], sec, f"oracle SLD train step on 32x{SLDTrain.WIDTH} crops (torch CPU fp32, all host threads)"
     CPU_BATCH = 8
-    WIDTH = 32      # set from --width by main()
+    WIDTH = 320     # set from --width by main()
 
 
 class EvalPipeline:
