@@ -71,6 +71,11 @@ bool conv3x3_wgrad_tc_supported(int H, int W);
 size_t conv3x3_wgrad_tc_partial_bytes();
 int conv3x3_wgrad_tc(const bf16* dy, long dy_pix, long dy_row, long dy_img, const bf16* x, int B, int H, int co_mul, int co_add,
                      float* dw, float* partial, cudaStream_t s);
+// ... and for any channel counts / map widths (the recognisers' encoders): implicit shifted operand instead of a materialised im2col
+bool conv3x3_wgrad_tc_general_supported(int B, int H, int W, int Ci, int Co);
+size_t conv3x3_wgrad_tc_general_partial_bytes(int B, int H, int W, int Ci, int Co);
+int conv3x3_wgrad_tc_general(const bf16* dy, const bf16* x, int B, int H, int W, int Ci, int Co, float* dw, float* partial,
+                             cudaStream_t s);
 int linear_wgrad_tc(const bf16* dy, long ld_dy, const bf16* x, long ld_x, long T, int N, float* dw, float* db, float* partial,
                     cudaStream_t s);
 

@@ -1391,6 +1391,8 @@ int focr_packed_feat_mse(const void* y, int B, int T, int C, const long long* le
 // col^T: 9Ci x M) so that the same TMA / tcgen05 kernel that runs the forward GEMMs applies, fp32 accumulation in TMEM over all
 // of M, fp32 output.  Co % 128 == 0 and M % 128 == 0 (the 64-channel stem keeps the streaming kernel).
 size_t focr_conv3x3_wgrad_tc_workspace_bytes(int B, int H, int W, int Ci, int Co) {
+  if (conv3x3_wgrad_tc_general_supported(B, H, W, Ci, Co))   // implicit operand: only the per-CTA partials and the bias-gradient scratch
+    return up(conv3x3_wgrad_tc_general_partial_bytes(B, H, W, Ci, Co), 256) + up((size_t)Co * 4, 256) + ((size_t)16 << 20);
   const size_t M = (size_t)B * H * W, Kp = up((size_t)9 * Ci, 128);
   return up(M * Kp * 2, 256) + up((size_t)Co * M * 2, 256) + up((size_t)Co * Kp * 4, 256) + up((size_t)Co * 4, 256) + ((size_t)16 << 20);
 }
@@ -1402,6 +1404,18 @@ int focr_conv3x3_wgrad_tc(const void* dy, const void* x_nhwc, const float* x_nch
   FOCR_REQUIRE(Co % 128 == 0 && M % 128 == 0 && Ci % 64 == 0 && Ci >= 64,
                "conv3x3_wgrad_tc: Co=%d (mult. of 128), Ci=%d (mult. of 64), B*H*W=%ld (mult. of 128)", Co, Ci, M);
   FOCR_REQUIRE(ws_bytes >= focr_conv3x3_wgrad_tc_workspace_bytes(B, H, W, Ci, Co), "conv3x3_wgrad_tc: workspace too small");
+  if (conv3x3_wgrad_tc_general_supported(B, H, W, Ci, Co)) {
+    // implicit form (wgrad_tc.cu): the shifted operand comes straight from x through TMA halo boxes, no col^T, no transposes
+    float* part = (float*)ws;
+    float* partial_b = (float*)((char*)ws + up(conv3x3_wgrad_tc_general_partial_bytes(B, H, W, Ci, Co), 256) + up((size_t)Co * 4, 256));
+    {
+      ProfScope _ps("conv_wgrad_tc", s);
+      int rc2 = conv3x3_wgrad_tc_general((const bf16*)dy, (const bf16*)x_nhwc, B, H, W, Ci, Co, dw, part, s);
+      if (rc2) return rc2;
+    }
+    if (db) return colsum((const bf16*)dy, Co, M, Co, db, partial_b, s);
+    return FOCR_OK;
+  }
   const int Kp = (int)up((size_t)9 * Ci, 128);
   char* base = (char*)ws;
   bf16* colT = (bf16*)base;

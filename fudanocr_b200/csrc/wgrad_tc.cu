@@ -412,6 +412,198 @@ __global__ void conv3x3_wgrad_tc_reduce_kernel(const float* __restrict__ partial
   dw[((long)(co * co_mul + co_add) * 64 + ci) * 9 + tap] = (float)s;
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// The same product for ANY channel counts and map widths (the ResNet encoders of the trainable recognisers: 64 ... 1024 channels,
+// 16 x 16 ... 16 x 160 maps): a CTA owns one (64 input channels) x (64 output channels) block of dW for all nine taps and a range
+// of 128-pixel tiles; the grid is (channel blocks) x (pixel splits), partial[split][block][tap][co][ci] is summed by a second
+// kernel straight into the torch layout.  Replaces the materialised transposed im2col matrix (9 Ci x pixels, 4.25 GB per step at
+// batch 64) + plain GEMM of round 1: the shifted operand is formed by TMA.  A tile is bw x (128 / bw) pixels (bw = the map width
+// when it is 16 / 32 / 64 / 128, else the largest of 128 / 64 / 32 / 16 dividing it - 32 for the 160-wide maps), the halo box has
+// two more rows, the vertical taps are windows bw x 128 B apart.
+// ------------------------------------------------------------------------------------------------------------------
+struct ConvWgGeom {
+  int bw, tile_rows, wblocks, tiles_per_img, tiles_total;
+  int ci_blocks, co_blocks, ksplit;
+  int xbox_bytes, stage_bytes, stages;
+};
+
+__global__ void __launch_bounds__(kCvThreads, 1)
+conv3x3_wgrad_tc_general_kernel(const __grid_constant__ CUtensorMap mX, const __grid_constant__ CUtensorMap mY,
+                                const ConvWgGeom g, float* __restrict__ partial) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + g.stages * g.stage_bytes);
+  uint64_t* empty = full + 4;
+  uint64_t* done = empty + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_blocks = g.ci_blocks * g.co_blocks;
+  const int blk = blockIdx.x % n_blocks, split = blockIdx.x / n_blocks;   // neighbours share the pixel range (L2 reuse)
+  const int ci0 = (blk % g.ci_blocks) * 64, co0 = (blk / g.ci_blocks) * 64;
+  const int t_begin = (int)((long)g.tiles_total * split / g.ksplit);
+  const int t_end = (int)((long)g.tiles_total * (split + 1) / g.ksplit);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mX);
+    tma_prefetch_desc(&mY);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < g.stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = t_begin; tile < t_end; ++tile) {
+        const int b = tile / g.tiles_per_img, r = tile - b * g.tiles_per_img;
+        const int h0 = (r / g.wblocks) * g.tile_rows, w0 = (r % g.wblocks) * g.bw;
+        mbar_wait_parked(&empty[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&full[stage], (uint32_t)g.stage_bytes);
+        uint8_t* st = smem + stage * g.stage_bytes;
+        for (int dxi = 0; dxi < 3; ++dxi) tma_load_4d(st + dxi * g.xbox_bytes, &mX, &full[stage], ci0, w0 + dxi - 1, h0 - 1, b);
+        tma_load_4d(st + 3 * g.xbox_bytes, &mY, &full[stage], co0, w0, h0, b);
+        if (++stage == g.stages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = umma_idesc_bf16_ex(128, 64, 1, 1);
+    const uint32_t win = (uint32_t)g.bw * 128;   // bytes between vertically adjacent tap windows
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = t_begin; tile < t_end; ++tile) {
+      mbar_wait_parked(&full[stage], phase);
+      tc_fence_after();
+      const uint32_t st = smem_u32(smem + stage * g.stage_bytes);
+      const uint32_t xb = (uint32_t)g.xbox_bytes;
+      const uint64_t db = umma_desc(st + 3 * xb, 16, 1024, 2);
+      const uint32_t a0[5] = {st, st + xb, st + 2 * xb, st + 2 * win, st + 2 * xb + win};
+      const uint32_t lbo[5] = {win, win, win, xb, win};
+      const uint32_t acc = tile > t_begin ? 1u : 0u;
+      if (elect_one()) {
+#pragma unroll
+        for (int pr = 0; pr < 5; ++pr) {
+          const uint64_t da = umma_desc(a0[pr], lbo[pr], 1024, 2);
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)
+            tc_mma_bf16(tmem_base + pr * 64, da + 128 * ks, db + 128 * ks, idesc, acc | (ks > 0 ? 1u : 0u));
+        }
+        tc_commit(&empty[stage]);
+      }
+      __syncwarp();
+      if (++stage == g.stages) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+    if (elect_one()) tc_commit(done);
+    __syncwarp();
+  } else if (warp >= 4) {
+    const int ew = warp & 3;
+    mbar_wait_parked(done, 0);
+    tc_fence_after();
+    const bool has_work = t_end > t_begin;
+    const int row = ew * 32 + lane;
+    const int half = row >> 6, ci = row & 63;
+    const int tap_of[5][2] = {{0, 3}, {1, 4}, {2, 5}, {6, 7}, {-1, 8}};
+    float* out = partial + ((long)split * n_blocks + blk) * 9 * 4096;
+#pragma unroll 1
+    for (int pr = 0; pr < 5; ++pr) {
+      const int tap = tap_of[pr][half];
+      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + pr * 64;
+#pragma unroll 1
+      for (int c0 = 0; c0 < 64; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(taddr + c0, r);
+        tmem_ld_wait();
+        if (tap >= 0) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) out[(long)tap * 4096 + (c0 + j) * 64 + ci] = has_work ? __uint_as_float(r[j]) : 0.f;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// dw[co][ci][tap] (torch (Co, Ci, 3, 3)) = sum_split partial[split][block][tap][co % 64][ci % 64]
+__global__ void conv3x3_wgrad_tc_general_reduce_kernel(const float* __restrict__ partial, int ksplit, int ci_blocks, int co_blocks,
+                                                       int Ci, float* __restrict__ dw) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int n_blocks = ci_blocks * co_blocks;
+  if (i >= (long)n_blocks * 9 * 4096) return;
+  const long stride = (long)n_blocks * 9 * 4096;
+  double s = 0.0;
+  int p = 0;
+  for (; p + 4 <= ksplit; p += 4) {
+    float v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = __ldcg(partial + (long)(p + u) * stride + i);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) s += v[u];
+  }
+  for (; p < ksplit; ++p) s += __ldcg(partial + (long)p * stride + i);
+  const int e = (int)(i % (9 * 4096)), blk = (int)(i / (9 * 4096));
+  const int ci = e & 63, co = (e >> 6) & 63, tap = e >> 12;
+  const int cig = (blk % ci_blocks) * 64 + ci, cog = (blk / ci_blocks) * 64 + co;
+  dw[((long)cog * Ci + cig) * 9 + tap] = (float)s;
+}
+
+bool conv_wg_geom(int B, int H, int W, int Ci, int Co, ConvWgGeom* g) {
+  if (Ci % 64 || Co % 64 || Ci < 64 || Co < 64) return false;
+  int bw = 0;
+  if (W == 16 || W == 32 || W == 64 || W == 128) bw = W;
+  else
+    for (int c = 128; c >= 16; c >>= 1)
+      if (W % c == 0 && H % (128 / c) == 0) {
+        bw = c;
+        break;
+      }
+  if (!bw) return false;
+  const int tile_rows = 128 / bw;
+  if (H % tile_rows != 0) return false;   // (maps smaller than a tile - the 2 x 16 maps of image-ids-CTR - keep the im2col path)
+  g->bw = bw;
+  g->tile_rows = tile_rows;
+  g->wblocks = W / bw;
+  g->tiles_per_img = g->wblocks * (H / tile_rows);
+  g->tiles_total = B * g->tiles_per_img;
+  g->ci_blocks = Ci / 64;
+  g->co_blocks = Co / 64;
+  const int n_blocks = g->ci_blocks * g->co_blocks;
+  int ks = (2 * wg_num_sms() + n_blocks - 1) / n_blocks;   // about two CTAs' worth of work per SM
+  if (n_blocks >= wg_num_sms()) ks = 1;
+  if (ks > g->tiles_total) ks = g->tiles_total;
+  if (ks < 1) ks = 1;
+  g->ksplit = ks;
+  g->xbox_bytes = (tile_rows + 2) * bw * 128;
+  g->stage_bytes = 3 * g->xbox_bytes + kCvYTile;
+  g->stages = (220 * 1024) / g->stage_bytes;
+  if (g->stages > 4) g->stages = 4;
+  return g->stages >= 1;
+}
+
 }  // namespace
 
 bool linear_wgrad_tc_supported(long T, int N, int K, long ld_dy, long ld_x) {
@@ -489,6 +681,51 @@ int conv3x3_wgrad_tc(const bf16* dy, long dy_pix, long dy_row, long dy_img, cons
   conv3x3_wgrad_tc_kernel<<<grid, kCvThreads, smem, s>>>(mX, mY, tiles, tiles_per_img, partial);
   FOCR_LAUNCH_CHECK();
   conv3x3_wgrad_tc_reduce_kernel<<<focr_cdiv(9 * 4096, 256), 256, 0, s>>>(partial, grid, co_mul, co_add, dw);
+  FOCR_LAUNCH_CHECK();
+  return FOCR_OK;
+}
+
+// ---- 3x3 conv weight gradient, any channel counts (multiples of 64) and map widths that cut into 128-pixel boxes ------------------
+bool conv3x3_wgrad_tc_general_supported(int B, int H, int W, int Ci, int Co) {
+  static int off = -1;
+  if (off < 0) off = getenv("FOCR_CONV_WGRAD_IM2COL") ? 1 : 0;   // tuning / cross-check knob: keep the im2col + GEMM path
+  ConvWgGeom g;
+  return !off && conv_wg_geom(B, H, W, Ci, Co, &g);
+}
+size_t conv3x3_wgrad_tc_general_partial_bytes(int B, int H, int W, int Ci, int Co) {
+  ConvWgGeom g;
+  if (!conv_wg_geom(B, H, W, Ci, Co, &g)) return 0;
+  return (size_t)g.ksplit * g.ci_blocks * g.co_blocks * 9 * 4096 * 4;
+}
+// x (B, H, W, Ci), dy (B, H, W, Co) NHWC bf16; dw fp32 (Co, Ci, 3, 3)
+int conv3x3_wgrad_tc_general(const bf16* dy, const bf16* x, int B, int H, int W, int Ci, int Co, float* dw, float* partial,
+                             cudaStream_t s) {
+  ConvWgGeom g;
+  FOCR_REQUIRE(conv_wg_geom(B, H, W, Ci, Co, &g), "conv3x3_wgrad_tc_general: B=%d H=%d W=%d Ci=%d Co=%d", B, H, W, Ci, Co);
+  CUtensorMap mX, mY;
+  {
+    const unsigned long long dims[4] = {(unsigned long long)Ci, (unsigned long long)W, (unsigned long long)H, (unsigned long long)B};
+    const unsigned long long str[3] = {(unsigned long long)Ci * 2, (unsigned long long)W * Ci * 2, (unsigned long long)H * W * Ci * 2};
+    const unsigned box[4] = {64, (unsigned)g.bw, (unsigned)(g.tile_rows + 2), 1};
+    TRY_RC(focr_make_tmap_4d(&mX, x, dims, str, box));
+  }
+  {
+    const unsigned long long dims[4] = {(unsigned long long)Co, (unsigned long long)W, (unsigned long long)H, (unsigned long long)B};
+    const unsigned long long str[3] = {(unsigned long long)Co * 2, (unsigned long long)W * Co * 2, (unsigned long long)H * W * Co * 2};
+    const unsigned box[4] = {64, (unsigned)g.bw, (unsigned)g.tile_rows, 1};
+    TRY_RC(focr_make_tmap_4d(&mY, dy, dims, str, box));
+  }
+  const size_t smem = (size_t)g.stages * g.stage_bytes + 256 + 1024;
+  static size_t attr = 0;
+  if (smem > attr) {
+    FOCR_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_tc_general_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  const int n_blocks = g.ci_blocks * g.co_blocks;
+  conv3x3_wgrad_tc_general_kernel<<<n_blocks * g.ksplit, kCvThreads, smem, s>>>(mX, mY, g, partial);
+  FOCR_LAUNCH_CHECK();
+  const long n = (long)n_blocks * 9 * 4096;
+  conv3x3_wgrad_tc_general_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(partial, g.ksplit, g.ci_blocks, g.co_blocks, Ci, dw);
   FOCR_LAUNCH_CHECK();
   return FOCR_OK;
 }
