@@ -130,7 +130,7 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    n0 = L.lib.focr_launch_count()
+    n0 = trainer.kernel_launches
     e0.record()
     for _ in range(K):
         loss = trainer.step(image, length, text_input, text_gt)
@@ -159,11 +159,14 @@ def main():
                                                   "distance term, Adadelta(lr 1, rho 0.9, wd 1e-4), dropout 0.1") if ids else
                                                  (f"SLD Transformer('stroke') train step, 32x{args.width} crops, batch {B} per GPU, "
                                                   "CE + Adadelta(lr 1, rho 0.9), dropout 0.1"), "T": T},
-                          "tflops_required": flop / (ms / K / 1e3) / 1e12, "launches_per_step": (L.lib.focr_launch_count() - n0) / K,
+                          "tflops_required": flop / (ms / K / 1e3) / 1e12, "launches_per_step": (trainer.kernel_launches - n0) / K,
                           "final_loss": float(loss), "ranks_identical": ranks_identical, "breakdown_ms_per_step": dict(top),
                           "cpu_baseline": cpu_baseline(args.model) if args.cpu_baseline else None}))
-    if world > 1:
-        dist.destroy_process_group()
+    if world > 1:   # NCCL work captured in the step graph: leave without destroy_process_group (it can hang on the graph's references)
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
