@@ -44,7 +44,7 @@ def test_clip_contrastive_loss_and_gradients(B, D, n_chars):
     assert abs(float(loss) - float(ref)) < 1e-5 * abs(float(ref)) + 1e-6, (float(loss), float(ref))
     assert _rel(ei.grad.cpu() / 3.0, ri.grad) < 1e-4
     assert _rel(et.grad.cpu() / 3.0, rt.grad) < 1e-4
-    assert abs(float(el.grad) / 3.0 - float(rl.grad)) < 1e-4 * abs(float(rl.grad)) + 1e-6
+    assert abs(float(el.grad) / 3.0 - float(rl.grad)) < 1e-4 * abs(float(rl.grad)) + 2e-5   # (fp32 exp / log noise x exp(logit_scale) = 14)
     # bf16 tower outputs are accepted (cast to fp32 inside), gradients come back in the input dtype
     bi, bt = (t.to(DEV).to(torch.bfloat16).requires_grad_(True) for t in (img, txt))
     lb = clip_contrastive_loss(bi, bt, ls.to(DEV), gt.to(DEV))
