@@ -33,6 +33,16 @@ def _call(fn, what, *args):
     L.check(fn(*args), what)
 
 
+def _out(t, shape, dev):
+    """the caller's gradient buffer (a view of a trainer's flat gradient: the kernel then writes the parameter gradient in place,
+    no autograd accumulation pass) or a fresh fp32 tensor"""
+    if t is None:
+        return torch.empty(shape, dtype=torch.float32, device=dev)
+    if t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != int(torch.Size(shape).numel()):
+        raise ValueError(f"gradient sink {tuple(t.shape)} {t.dtype} does not match a contiguous fp32 {tuple(shape)}")
+    return t
+
+
 # ---- convolutions ---------------------------------------------------------------------------------------------------
 def conv_first_fwd(x_nchw, w, b):
     """3-channel fp32 NCHW image -> (B, H, W, Co) bf16 through im2col + tcgen05 GEMM"""
@@ -46,12 +56,12 @@ def conv_first_fwd(x_nchw, w, b):
     return y
 
 
-def conv_first_wgrad(dy, x_nchw, w_shape):
+def conv_first_wgrad(dy, x_nchw, w_shape, out_w=None, out_b=None):
     dev = _dev(dy)
     B, Ci, H, W = x_nchw.shape
     Co = w_shape[0]
-    dw = torch.empty(w_shape, dtype=torch.float32, device=dev)
-    db = torch.empty(Co, dtype=torch.float32, device=dev)
+    dw = _out(out_w, w_shape, dev)
+    db = _out(out_b, (Co,), dev)
     ws = _ws(L.lib.focr_conv3x3_gemm_workspace_bytes(B, H, W, Ci, Co), dev)
     _call(L.lib.focr_conv3x3_gemm_wgrad, "conv3x3_gemm_wgrad", dy.data_ptr(), 0, x_nchw.data_ptr(), dw.data_ptr(), db.data_ptr(), B,
           H, W, Ci, Co, ws.data_ptr(), ws.numel(), L.cur_stream())
@@ -81,14 +91,14 @@ def conv_dgrad(dy, w):
     return dx
 
 
-def conv_wgrad(dy, x, w_shape):
+def conv_wgrad(dy, x, w_shape, out_w=None, out_b=None):
     """dW, db of a 3x3 convolution from dy (B,H,W,Co) and the layer input x (B,H,W,Ci): im2col, then dW = dY^T col on the tcgen05
     GEMM (focr_conv3x3_wgrad_tc: Co % 128 == 0 and B*H*W % 128 == 0) or on the streaming mma.sync kernel (the 64-channel stem)"""
     dev = _dev(dy)
     B, H, W, Ci = x.shape
     Co = w_shape[0]
-    dw = torch.empty(w_shape, dtype=torch.float32, device=dev)
-    db = torch.empty(Co, dtype=torch.float32, device=dev)
+    dw = _out(out_w, w_shape, dev)
+    db = _out(out_b, (Co,), dev)
     if TC_WGRAD and Co % 128 == 0 and Ci % 64 == 0 and (B * H * W) % 128 == 0:
         ws = _ws(L.lib.focr_conv3x3_wgrad_tc_workspace_bytes(B, H, W, Ci, Co), dev)
         _call(L.lib.focr_conv3x3_wgrad_tc, "conv3x3_wgrad_tc", dy.data_ptr(), x.data_ptr(), 0, dw.data_ptr(), db.data_ptr(), B, H, W,
@@ -128,13 +138,13 @@ def bn_eval_fwd(x, gamma, beta, rm, rv, act):
     return y
 
 
-def bn_bwd(dy, x, stats, act):
+def bn_bwd(dy, x, stats, act, out_g=None, out_b=None):
     dev = _dev(dy)
     C = x.shape[-1]
     T = x.numel() // C
     dx = torch.empty_like(x)
-    dg = torch.empty(C, dtype=torch.float32, device=dev)
-    db = torch.empty(C, dtype=torch.float32, device=dev)
+    dg = _out(out_g, (C,), dev)
+    db = _out(out_b, (C,), dev)
     ws = _ws(L.lib.focr_bn_workspace_bytes(), dev)
     _call(L.lib.focr_bn_bwd, "bn_bwd", dy.data_ptr(), x.data_ptr(), stats.data_ptr(), dx.data_ptr(), dg.data_ptr(), db.data_ptr(), T, C,
           act, ws.data_ptr(), ws.numel(), L.cur_stream())
@@ -203,13 +213,13 @@ def linear_dgrad(dy, w):
     return dx
 
 
-def linear_wgrad(dy, x):
+def linear_wgrad(dy, x, out_w=None, out_b=None):
     """dw (N, K) fp32 = dy^T x and db (N) = column sums of dy"""
     dev = _dev(dy)
     M, N = dy.shape
     K = x.shape[1]
-    dw = torch.empty(N, K, dtype=torch.float32, device=dev)
-    db = torch.empty(N, dtype=torch.float32, device=dev)
+    dw = _out(out_w, (N, K), dev)
+    db = _out(out_b, (N,), dev)
     ws = _ws(L.lib.focr_wgrad_workspace_bytes(), dev)
     _call(L.lib.focr_linear_wgrad, "linear_wgrad", dy.data_ptr(), x.data_ptr(), dw.data_ptr(), M, K, N, ws.data_ptr(), ws.numel(),
           L.cur_stream())
@@ -253,12 +263,12 @@ def ln_fwd(x, res, a, b, eps=1e-6):
     return xs, y
 
 
-def ln_bwd(dy, xs, a, eps=1e-6):
+def ln_bwd(dy, xs, a, eps=1e-6, out_a=None, out_b=None):
     dev = _dev(dy)
     T, C = xs.shape
     dx = torch.empty_like(xs)
-    da = torch.empty(C, dtype=torch.float32, device=dev)
-    db = torch.empty(C, dtype=torch.float32, device=dev)
+    da = _out(out_a, (C,), dev)
+    db = _out(out_b, (C,), dev)
     ws = _ws(L.lib.focr_layernorm_wide_workspace_bytes(C), dev)
     _call(L.lib.focr_layernorm_wide_bwd, "layernorm_wide_bwd", dy.data_ptr(), xs.data_ptr(), a.data_ptr(), dx.data_ptr(), da.data_ptr(),
           db.data_ptr(), T, C, eps, ws.data_ptr(), ws.numel(), L.cur_stream())
@@ -279,10 +289,10 @@ def embed_fwd(idx, lut, rows_pad, p, seed, sid):
     return out
 
 
-def embed_bwd(idx, d_out, vocab, E):
+def embed_bwd(idx, d_out, vocab, E, out=None):
     dev = _dev(d_out)
     B, T = idx.shape
-    d_lut = torch.empty(vocab, E, dtype=torch.float32, device=dev)
+    d_lut = _out(out, (vocab, E), dev)
     _call(L.lib.focr_text_embed_bwd, "text_embed_bwd", idx.data_ptr(), d_out.data_ptr(), vocab, E, B, T, d_lut.data_ptr(),
           L.cur_stream())
     return d_lut

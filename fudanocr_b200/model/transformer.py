@@ -51,24 +51,65 @@ def _map_tiles(h: int, w: int) -> bool:
     return any(w % c == 0 and h % (128 // c) == 0 for c in (128, 64, 32, 16))
 
 
+# Gradient sinks.  Autograd adds every parameter gradient a Function returns into `p.grad` with one at::add kernel per parameter
+# (193 of them per step here).  The fused trainers (trainer_sld.py) own a flat gradient buffer that `p.grad` already views; inside
+# their step they publish {parameter data pointer: gradient view} and the backward bodies below hand those views to the kernels as
+# OUTPUT buffers and return None for the parameter - the gradient lands in place, nothing is accumulated.  Each parameter of these
+# models is used once per forward, so overwrite == accumulate into the zeroed buffer.  Outside a trainer step (the reference's own
+# loop: loss.backward(); optimizer.step()) the table is None and autograd's semantics - accumulation included - are untouched.
+_GRAD_SINKS = None
+
+
+class grad_sinks:
+    """context manager: parameter gradients of every backward run inside are written straight into `table[param.data_ptr()]`"""
+
+    def __init__(self, table):
+        self.table = table
+
+    def __enter__(self):
+        global _GRAD_SINKS
+        self.prev, _GRAD_SINKS = _GRAD_SINKS, self.table
+        return self
+
+    def __exit__(self, *exc):
+        global _GRAD_SINKS
+        _GRAD_SINKS = self.prev
+        return False
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _sink(ptr):
+    return None if (_GRAD_SINKS is None or not ptr) else _GRAD_SINKS.get(ptr)
+
+
+def _ret(sink, grad):
+    return None if sink is not None else grad
+
+
 class _ConvFirst(Function):
     @staticmethod
     def forward(ctx, x, w, b):
         ctx.save_for_backward(x)
         ctx.wshape = tuple(w.shape)
+        ctx.ptrs = (_ptr(w), _ptr(b))
         return ops.conv_first_fwd(x, w, b)
 
     @staticmethod
     def backward(ctx, dy):
         (x,) = ctx.saved_tensors
-        dw, db = ops.conv_first_wgrad(_bf(dy).contiguous(), x, ctx.wshape)
-        return None, dw, db
+        sw, sb = _sink(ctx.ptrs[0]), _sink(ctx.ptrs[1])
+        dw, db = ops.conv_first_wgrad(_bf(dy).contiguous(), x, ctx.wshape, sw, sb)
+        return None, _ret(sw, dw), _ret(sb, db)
 
 
 class _Conv(Function):
     @staticmethod
     def forward(ctx, x, w, b):
         ctx.save_for_backward(x, w)
+        ctx.ptrs = (_ptr(w), _ptr(b))
         return ops.conv_fwd(x, w, b)
 
     @staticmethod
@@ -76,8 +117,9 @@ class _Conv(Function):
         x, w = ctx.saved_tensors
         dy = _bf(dy).contiguous()
         dx = ops.conv_dgrad(dy, w) if ctx.needs_input_grad[0] else None
-        dw, db = ops.conv_wgrad(dy, x, tuple(w.shape))
-        return dx, dw, db
+        sw, sb = _sink(ctx.ptrs[0]), _sink(ctx.ptrs[1])
+        dw, db = ops.conv_wgrad(dy, x, tuple(w.shape), sw, sb)
+        return dx, _ret(sw, dw), _ret(sb, db)
 
 
 class _BNTrain(Function):
@@ -86,13 +128,15 @@ class _BNTrain(Function):
         y, stats = ops.bn_train_fwd(x, gamma, beta, rm, rv, nbt, act)
         ctx.save_for_backward(x, stats)
         ctx.act = act
+        ctx.ptrs = (_ptr(gamma), _ptr(beta))
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, stats = ctx.saved_tensors
-        dx, dg, db = ops.bn_bwd(_bf(dy).contiguous(), x, stats, ctx.act)
-        return dx, dg, db, None, None, None, None
+        sg, sb = _sink(ctx.ptrs[0]), _sink(ctx.ptrs[1])
+        dx, dg, db = ops.bn_bwd(_bf(dy).contiguous(), x, stats, ctx.act, sg, sb)
+        return dx, _ret(sg, dg), _ret(sb, db), None, None, None, None
 
 
 class _AddRelu(Function):
@@ -127,6 +171,7 @@ class _Linear(Function):
     def forward(ctx, x, w, b, relu, fp32_out):
         y = ops.linear_fwd(x, w, b, relu, fp32_out)
         ctx.relu = relu
+        ctx.ptrs = (_ptr(w), _ptr(b))
         ctx.save_for_backward(x, w, y if relu else None)
         return y
 
@@ -139,7 +184,10 @@ class _Linear(Function):
         dx = ops.linear_dgrad(dy, w) if ctx.needs_input_grad[0] else None
         dw = db = None
         if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:   # frozen operands (the CLIP text features of image-ids-CTR) skip this
-            dw, db = ops.linear_wgrad(dy, x)
+            sw = _sink(ctx.ptrs[0]) if ctx.needs_input_grad[1] else None
+            sb = _sink(ctx.ptrs[1]) if ctx.needs_input_grad[2] else None
+            dw, db = ops.linear_wgrad(dy, x, sw, sb)
+            dw, db = _ret(sw, dw), _ret(sb, db)
         return dx, dw, (db if ctx.needs_input_grad[2] else None), None, None
 
 
@@ -165,13 +213,15 @@ class _LN(Function):
     def forward(ctx, x, res, a, b):
         xs, y = ops.ln_fwd(x, res, a, b)
         ctx.save_for_backward(xs, a)
+        ctx.ptrs = (_ptr(a), _ptr(b))
         return y
 
     @staticmethod
     def backward(ctx, dy):
         xs, a = ctx.saved_tensors
-        dx, da, db = ops.ln_bwd(_bf(dy).contiguous(), xs, a)
-        return dx, dx, da, db
+        sa, sb = _sink(ctx.ptrs[0]), _sink(ctx.ptrs[1])
+        dx, da, db = ops.ln_bwd(_bf(dy).contiguous(), xs, a, out_a=sa, out_b=sb)
+        return dx, dx, _ret(sa, da), _ret(sb, db)
 
 
 class _Embed(Function):
@@ -179,12 +229,14 @@ class _Embed(Function):
     def forward(ctx, idx, lut, rows_pad, p, seed, sid):
         ctx.save_for_backward(idx)
         ctx.shape = tuple(lut.shape)
+        ctx.ptrs = (_ptr(lut),)
         return ops.embed_fwd(idx, lut, rows_pad, p, seed, sid)
 
     @staticmethod
     def backward(ctx, d_out):
         (idx,) = ctx.saved_tensors
-        return None, ops.embed_bwd(idx, _bf(d_out).contiguous(), *ctx.shape), None, None, None, None
+        sl = _sink(ctx.ptrs[0])
+        return None, _ret(sl, ops.embed_bwd(idx, _bf(d_out).contiguous(), *ctx.shape, out=sl)), None, None, None, None
 
 
 class _Dropout(Function):

@@ -68,6 +68,8 @@ class _FlatAdadeltaTrainer:
                              self.flat_sq.data_ptr() + 4 * (o + k), self.flat_acc.data_ptr() + 4 * (o + k), ln])
                 k += ln
         self.grad_views = [p.grad for p in plist]
+        # parameter data pointer -> its gradient view: inside a step the backward kernels write there directly (model/transformer.py)
+        self._sinks = {p.data_ptr(): g for p, g in zip(plist, self.grad_views)}
         self.plist = plist
         self.chunks = torch.tensor(recs, dtype=torch.int64, device=dev)
         self.loss: Optional[torch.Tensor] = None
@@ -85,7 +87,9 @@ class _FlatAdadeltaTrainer:
                 p.grad = g
 
     def _finish(self, loss, lr=None):
-        loss.backward()
+        from .model.transformer import grad_sinks
+        with grad_sinks(self._sinks):
+            loss.backward()
         if self.world > 1:
             dist.all_reduce(self.flat_g, group=self.pg)    # sum; the mean is taken inside the optimizer kernel
         ops.adadelta_step(self.chunks, self.chunks.shape[0], 1.0 / self.world, self.lr if lr is None else lr, self.rho, self.eps,

@@ -22,13 +22,21 @@ def _nhwc(x):
     return x.permute(0, 2, 3, 1).contiguous()
 
 
+def _into(out, t):
+    """the kernels' output-buffer contract (recog_ops._out): write the result into the caller's gradient view when one is given"""
+    if out is None:
+        return t
+    out.copy_(t.reshape(out.shape))
+    return out
+
+
 def conv_first_fwd(x, w, b):
     return _nhwc(F.conv2d(x, w, b, padding=1))
 
 
-def conv_first_wgrad(dy, x, wshape):
+def conv_first_wgrad(dy, x, wshape, out_w=None, out_b=None):
     g = _nchw(dy)
-    return torch.nn.grad.conv2d_weight(x, wshape, g, padding=1), g.sum((0, 2, 3))
+    return _into(out_w, torch.nn.grad.conv2d_weight(x, wshape, g, padding=1)), _into(out_b, g.sum((0, 2, 3)))
 
 
 def conv_fwd(x, w, b):
@@ -39,9 +47,9 @@ def conv_dgrad(dy, w):
     return _nhwc(F.conv_transpose2d(_nchw(dy), w, padding=1))
 
 
-def conv_wgrad(dy, x, wshape):
+def conv_wgrad(dy, x, wshape, out_w=None, out_b=None):
     g = _nchw(dy)
-    return torch.nn.grad.conv2d_weight(_nchw(x), wshape, g, padding=1), g.sum((0, 2, 3))
+    return _into(out_w, torch.nn.grad.conv2d_weight(_nchw(x), wshape, g, padding=1)), _into(out_b, g.sum((0, 2, 3)))
 
 
 def bn_train_fwd(x, gamma, beta, rm, rv, nbt, act):
@@ -68,7 +76,7 @@ def bn_eval_fwd(x, gamma, beta, rm, rv, act):
     return F.relu(y) if act == ACT_RELU else y
 
 
-def bn_bwd(dy, x, stats, act):
+def bn_bwd(dy, x, stats, act, out_g=None, out_b=None):
     mean, invstd, scale, shift = stats
     if act == ACT_RELU:
         dy = dy * ((x * scale + shift) > 0)
@@ -78,7 +86,7 @@ def bn_bwd(dy, x, stats, act):
     dgamma, dbeta = (g * xh).sum(0), g.sum(0)
     n = g.shape[0]
     dx = scale * (g - dbeta / n - xh * dgamma / n)
-    return dx.reshape(x.shape), dgamma, dbeta
+    return dx.reshape(x.shape), _into(out_g, dgamma), _into(out_b, dbeta)
 
 
 def add_relu(a, b):
@@ -119,8 +127,8 @@ def linear_dgrad(dy, w):
     return dy @ w
 
 
-def linear_wgrad(dy, x):
-    return dy.t() @ x, dy.sum(0)
+def linear_wgrad(dy, x, out_w=None, out_b=None):
+    return _into(out_w, dy.t() @ x), _into(out_b, dy.sum(0))
 
 
 def _heads(t, B, T, H, dk):
@@ -164,12 +172,12 @@ def ln_fwd(x, res, a, b, eps=1e-6):
     return xs, _ln(xs, a, b, eps)
 
 
-def ln_bwd(dy, xs, a, eps=1e-6):
+def ln_bwd(dy, xs, a, eps=1e-6, out_a=None, out_b=None):
     xr, ar = xs.detach().clone().requires_grad_(True), a.detach().clone().requires_grad_(True)
     br = torch.zeros_like(ar).requires_grad_(True)
     with torch.enable_grad():
         _ln(xr, ar, br, eps).backward(dy)
-    return torch.nan_to_num(xr.grad), torch.nan_to_num(ar.grad), br.grad   # constant (padding) rows: the kernel emits 0
+    return torch.nan_to_num(xr.grad), _into(out_a, torch.nan_to_num(ar.grad)), _into(out_b, br.grad)   # constant (padding) rows: the kernel emits 0
 
 
 def embed_fwd(idx, lut, rows_pad, p, seed, sid):
@@ -187,8 +195,8 @@ def embed_fwd(idx, lut, rows_pad, p, seed, sid):
     return out
 
 
-def embed_bwd(idx, d_out, vocab, E):
-    return torch.zeros(vocab, E).index_add_(0, idx.reshape(-1), d_out[:idx.numel(), :E]) * math.sqrt(E)
+def embed_bwd(idx, d_out, vocab, E, out=None):
+    return _into(out, torch.zeros(vocab, E).index_add_(0, idx.reshape(-1), d_out[:idx.numel(), :E]) * math.sqrt(E))
 
 
 def packed_ce(logits, B, T, C, length, gt, gscale=1.0, want_grad=True):
