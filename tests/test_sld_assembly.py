@@ -191,3 +191,44 @@ def test_character_mode_assembles_with_a_wide_generator(monkeypatch):
     for k in ("generator_word.proj.weight", "generator_word.proj.bias", "embedding_word.lut.weight"):
         a, b = dict(model.named_parameters())[k].grad, osd[k].grad
         assert float((a - b).norm() / b.norm()) < 2e-3, k
+
+
+def test_gradient_sinks_write_in_place_and_leave_autograd_alone_outside(monkeypatch):
+    """inside `grad_sinks` (what the fused trainers wrap their backward in) every parameter gradient is written by the backward
+    body straight into the published view and equals autograd's own; outside, a second backward ACCUMULATES as torch defines"""
+    model, g, image = _setup(monkeypatch)
+    from fudanocr_b200.model.transformer import grad_sinks
+    model.train()
+    model.dropout_p = 0.0
+
+    def loss_fn():
+        out = model(image, g["length"], g["text_input"])
+        return torch.nn.CrossEntropyLoss()(out["pred"], g["text_gt"])
+    model.zero_grad(set_to_none=True)
+    loss_fn().backward()
+    plain = {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
+    loss_fn().backward()                                                    # no sinks: autograd accumulates
+    for k, p in model.named_parameters():
+        if k in plain:
+            assert torch.allclose(p.grad, 2 * plain[k], rtol=1e-5, atol=1e-8), k
+    # the trainer's arrangement: .grad views of one flat buffer, published by parameter data pointer
+    names = [k for k in plain]
+    params = dict(model.named_parameters())
+    flat = torch.zeros(sum(params[k].numel() for k in names))
+    table, off = {}, 0
+    for k in names:
+        n = params[k].numel()
+        params[k].grad = flat[off:off + n].view_as(params[k])
+        table[params[k].data_ptr()] = params[k].grad
+        off += n
+    flat.fill_(7.0)                                                         # stale content must be overwritten, not added to
+    with grad_sinks(table):
+        loss_fn().backward()
+    direct = [k for k in names if "generator_word" not in k]                # the generator's weight enters padded (F.pad): autograd's path
+    for k in direct:
+        assert torch.allclose(params[k].grad, plain[k], rtol=1e-5, atol=1e-8), k
+    for k in names:
+        if k not in direct:
+            assert torch.allclose(params[k].grad, plain[k] + 7.0, rtol=1e-5, atol=1e-6), k
+    from fudanocr_b200.model import transformer as T
+    assert T._GRAD_SINKS is None                                            # the table is gone once the step is over
