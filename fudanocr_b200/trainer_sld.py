@@ -141,10 +141,18 @@ class _FlatAdadeltaTrainer:
             st_in[:, :T].copy_(text_input)
             st_gt[:text_gt.numel()].copy_(text_gt)
             n0 = L.lib.focr_launch_count()
-            with torch.cuda.graph(g, pool=self._pool):
-                L.check(L.lib.focr_recog_epoch_advance(L.cur_stream()), "recog_epoch_advance")
+            try:
+                with torch.cuda.graph(g, pool=self._pool):
+                    L.check(L.lib.focr_recog_epoch_advance(L.cur_stream()), "recog_epoch_advance")
+                    self._begin()
+                    outs = body(st_image, st_len, st_in, st_gt)
+            except Exception as ex:   # noqa: BLE001 - e.g. a collective the installed NCCL cannot capture: keep training eagerly
+                import warnings
+                warnings.warn(f"focr: the recogniser step could not be captured as a CUDA graph ({ex}); continuing with eager launches")
+                self.use_graph = False
+                torch.cuda.synchronize()
                 self._begin()
-                outs = body(st_image, st_len, st_in, st_gt)
+                return None
             ent = (g, (st_image, st_len, st_in, st_gt), outs, int(L.lib.focr_launch_count() - n0))
             if len(self._graphs) >= 8:
                 del self._graphs[next(iter(self._graphs))]
