@@ -157,8 +157,54 @@ def main_b32():
     print(f"sld b32 golden: loss {float(loss):.6f}, {(gd / 'sld_b32.pt').stat().st_size / 1e6:.2f} MB")
 
 
+def wide_batch(B):
+    """(B, 3, 32, 320) crops: ten synthetic squares side by side (the same construction as tests/test_gpu_sld.py::_setup_wide)"""
+    parts = [SO.synth_batch(B, seed=1234 + 17 * i) for i in range(10)]
+    return torch.cat([p[0] for p in parts], dim=3), parts[0][1]
+
+
+def main_w320():
+    """the UNMODIFIED reference module on 32 x 320 crops (BASELINE configs[3]; its ResNet is fully convolutional,
+    model/transformer.py:126-164, so the 16 x 160 map simply becomes 2 560 image tokens): loss, output norms, every gradient norm
+    and gradient samples at batch 2 - the pin of oracle/sld_oracle.py at the shape the GPU tests of that configuration use"""
+    torch.manual_seed(0)
+    torch.set_num_threads(os.cpu_count())
+    Transformer, util = load_reference()
+    model = Transformer("stroke")
+    gd = synth.GOLDEN_DIR
+    sd = synth.synth_state_dict(synth.load_spec("sld"), 1234)
+    model.load_state_dict(sd, strict=False)
+    for m in model.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    B = 2
+    image, strings = wide_batch(B)
+    length, text_input, text_gt = SO.converter_stroke(strings)
+    model.train()
+    out = model(image, length, text_input)
+    assert out["conv"].shape == (B, 1024, 16, 160) and out["map"].shape[-1] == 2560
+    loss = torch.nn.CrossEntropyLoss()(out["pred"], text_gt)
+    model.zero_grad()
+    loss.backward()
+    ref_grads = {k: p.grad for k, p in model.named_parameters()}
+    golden = {
+        "B": B, "strings": strings, "length": length, "text_input": text_input, "text_gt": text_gt,
+        "image_checksum": float(image.double().sum()), "loss": loss.detach(), "pred": out["pred"].detach(),
+        "map_sample": out["map"].detach()[:, :, :, ::64].clone(), "conv_norm": out["conv"].detach().norm(),
+        "grad_norms": {k: (g.norm() if g is not None else None) for k, g in ref_grads.items()},
+        "grad_samples": {k: g.reshape(-1)[::max(g.numel() // 256, 1)][:256].clone() for k, g in ref_grads.items() if g is not None},
+    }
+    torch.save(golden, gd / "sld_w320_b2.pt")
+    h = hashlib.sha256((gd / "sld_w320_b2.pt").read_bytes()).hexdigest()
+    sums = [ln for ln in (gd / "SHA256SUMS").read_text().splitlines() if "sld_w320_b2.pt" not in ln]
+    (gd / "SHA256SUMS").write_text("\n".join(sums + [f"{h}  sld_w320_b2.pt"]) + "\n")
+    print(f"sld 32x320 golden: loss {float(loss):.6f}, {(gd / 'sld_w320_b2.pt').stat().st_size / 1e6:.2f} MB")
+
+
 if __name__ == "__main__":
     if "--b32" in sys.argv:
         main_b32()
+    elif "--w320" in sys.argv:
+        main_w320()
     else:
         main()

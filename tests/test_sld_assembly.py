@@ -232,3 +232,43 @@ def test_gradient_sinks_write_in_place_and_leave_autograd_alone_outside(monkeypa
             assert torch.allclose(params[k].grad, plain[k] + 7.0, rtol=1e-5, atol=1e-6), k
     from fudanocr_b200.model import transformer as T
     assert T._GRAD_SINKS is None                                            # the table is gone once the step is over
+
+
+def test_oracle_and_assembled_model_on_32x320_crops_match_the_reference_golden(monkeypatch):
+    """BASELINE configs[3]: 32 x 320 crops -> 16 x 160 maps, 2 560 image tokens.  tests/golden/sld_w320_b2.pt was recorded from the
+    UNMODIFIED reference module (oracle/make_golden_sld.py --w320); the oracle restatement - the checker of the GPU tests of that
+    configuration - and the assembled drop-in model (kernel wrappers swapped for the torch stand-ins) must reproduce its loss,
+    predictions, attention-map samples and every gradient norm"""
+    import _recog_mock
+    _recog_mock.install(monkeypatch)
+    from fudanocr_b200.model.transformer import Transformer
+    g = torch.load(synth.GOLDEN_DIR / "sld_w320_b2.pt", weights_only=False)
+    parts = [SO.synth_batch(g["B"], seed=1234 + 17 * i) for i in range(10)]
+    image = torch.cat([p[0] for p in parts], dim=3)
+    assert image.shape == (g["B"], 3, 32, 320) and parts[0][1] == g["strings"]
+    assert abs(float(image.double().sum()) - g["image_checksum"]) < 1e-6
+    sd = synth.synth_state_dict(synth.load_spec("sld"), 1234)
+    # (1) the oracle
+    osd = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in sd.items()}
+    o_loss, o_logits, o_map, o_conv = SO.loss_fn(osd, image, g["length"], g["text_input"], g["text_gt"])
+    o_loss.backward()
+    assert abs(float(o_loss) - float(g["loss"])) < 1e-5 * float(g["loss"])
+    assert torch.allclose(SO.pack(o_logits, g["length"]), g["pred"], rtol=1e-4, atol=1e-5)
+    assert o_map.shape[-1] == 2560 and torch.allclose(o_map[:, :, :, ::64], g["map_sample"], rtol=1e-4, atol=1e-7)
+    nmax = max(float(n) for n in g["grad_norms"].values() if n is not None)
+    for k, n in g["grad_norms"].items():
+        if n is None:
+            assert osd[k].grad is None, k
+        elif float(n) > 1e-6 * nmax:
+            assert abs(float(osd[k].grad.norm()) - float(n)) < 5e-3 * float(n), k
+    # (2) the assembled model
+    model = Transformer("stroke")
+    model.load_state_dict(sd, strict=False)
+    model.train()
+    model.dropout_p = 0.0
+    out = model(image, g["length"], g["text_input"])
+    assert out["conv"].shape == (g["B"], 1024, 16, 160)
+    assert torch.allclose(out["pred"], g["pred"], rtol=1e-3, atol=1e-4)
+    assert torch.allclose(out["map"][:, :, :, ::64], g["map_sample"], rtol=1e-3, atol=1e-6)
+    loss = torch.nn.CrossEntropyLoss()(out["pred"], g["text_gt"])
+    assert abs(float(loss) - float(g["loss"])) < 1e-4
